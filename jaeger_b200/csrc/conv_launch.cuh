@@ -1,0 +1,57 @@
+// Host-side launchers for the conv layer kernels.
+#pragma once
+#include "conv_ref.cuh"
+#include "conv_tc.cuh"
+
+namespace jg {
+
+constexpr unsigned kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+// Fills the descriptor fields for the canonical no-swizzle K-major operand layouts.
+inline void conv_fill_descriptors(ConvParams& p) {
+  const unsigned rows_a = kTileM + p.halo_l + p.halo_r;
+  p.a_lbo = rows_a * 16;  // distance between the two 8-channel planes of one K=16 MMA
+  p.a_sbo = 128;          // distance between 8-row groups: rows are linear at 16 B pitch
+  p.b_lbo = p.cout * 16;
+  p.b_sbo = 128;
+}
+
+// Returns 0 on success, a negative code when the layer does not fit the kernel's constraints.
+inline int conv_tc_stages(const ConvParams& p) {
+  if (p.cin % 16 != 0 || p.cout % 32 != 0 || p.cout > 256 || p.ntaps > kMaxTaps) return -1;
+  for (int s = 4; s >= 2; --s) {
+    tc::SmemLayout L = tc::smem_layout(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, s);
+    if (L.total <= kMaxSmem) return s;
+  }
+  return -2;  // weights + 2 stages exceed shared memory
+}
+
+inline cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  const int stages = conv_tc_stages(p);
+  if (stages < 0) return cudaErrorInvalidConfiguration;
+  tc::SmemLayout L = tc::smem_layout(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, stages);
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  cudaError_t e;
+#define JG_LAUNCH(S)                                                                            \
+  e = cudaFuncSetAttribute(tc::conv_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                           static_cast<int>(L.total));                                          \
+  if (e != cudaSuccess) return e;                                                               \
+  tc::conv_tc_kernel<S><<<grid, tc::kThreads, L.total, stream>>>(p);
+  if (stages == 4) { JG_LAUNCH(4) }
+  else if (stages == 3) { JG_LAUNCH(3) }
+  else { JG_LAUNCH(2) }
+#undef JG_LAUNCH
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_conv_ref(const ConvParams& p, cudaStream_t stream) {
+  const long long total = static_cast<long long>(p.n_tiles) * kTileM * p.cout;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  ref::conv_ref_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace jg

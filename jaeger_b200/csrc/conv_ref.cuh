@@ -1,0 +1,49 @@
+// CUDA-core restatement of the conv layer (same ConvParams contract as conv_tc.cuh).
+// It exists so that the tensor-core kernel can be validated ON THE GPU at sizes no CPU
+// oracle finishes in reasonable time (tests call both through the C ABI and compare);
+// it is never on the product path.
+#pragma once
+#include "conv_common.cuh"
+
+namespace jg {
+namespace ref {
+
+__global__ void conv_ref_kernel(const ConvParams p) {
+  const long long total = static_cast<long long>(p.n_tiles) * kTileM * p.cout;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / p.cout;
+    const int co = static_cast<int>(idx % p.cout);
+    float acc = 0.0f;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const long long r = row + p.shifts[t];
+      for (int ci = 0; ci < p.cin; ++ci) {
+        const float xv = __bfloat162float(p.x[(static_cast<long long>(ci >> 3) * p.x_plane + r) * 8 + (ci & 7)]);
+        const int k = t * p.cin + ci;
+        const float wv = __bfloat162float(p.w[(static_cast<long long>(k >> 3) * p.cout + co) * 8 + (k & 7)]);
+        acc = fmaf(xv, wv, acc);
+      }
+    }
+    const bool valid = p.out_mask[row] != 0;
+    const int win = static_cast<int>(row / p.rows_per_window);
+    if (p.tap_mode == 1 && valid)
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, acc + p.bias[co]);
+    float v = fmaf(acc, p.scale1[co], p.shift1[co]);
+    if (p.sc) {
+      const bool scv = p.sc_mask ? p.sc_mask[row] != 0 : true;
+      v += scv ? __bfloat162float(p.sc[(static_cast<long long>(co >> 3) * p.y_plane + row) * 8 + (co & 7)])
+               : (p.sc_const ? p.sc_const[co] : 0.0f);
+    }
+    v = act_apply(v, p.act1);
+    if (p.tap_mode == 2 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, v);
+    if (p.has_affine2) v = act_apply(fmaf(v, p.scale2[co], p.shift2[co]), p.act2);
+    if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + co, v);
+    if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * p.cout + co, v);
+    if (p.y)
+      p.y[(static_cast<long long>(co >> 3) * p.y_plane + row) * 8 + (co & 7)] =
+          __float2bfloat16_rn(valid ? v : 0.0f);
+  }
+}
+
+}  // namespace ref
+}  // namespace jg

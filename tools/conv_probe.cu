@@ -1,0 +1,191 @@
+// Standalone hardware probe for the tcgen05 conv kernel (not part of the product library).
+//   conv_probe <shape> <variant> [n_windows] [time_iters]
+// shape:   0 = residual conv (Cin 128, Cout 128, k5 d3, SAME, shortcut + taps + pool)
+//          1 = stem conv     (Cin 64,  Cout 128, k7 d1, VALID, raw tap)
+//          2 = narrow conv   (Cin 32,  Cout 32,  k3 d1, SAME)
+// variant: 0 = canonical descriptors (LBO = plane pitch, SBO = 128)
+//          1 = LBO/SBO swapped
+// Compares conv_tc_kernel against conv_ref_kernel on the same random inputs and prints
+// max |diff|; with time_iters > 0 also times the tensor-core kernel with CUDA events.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../jaeger_b200/csrc/conv_launch.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
+
+static uint32_t rng_state = 12345u;
+static inline float frand() {  // uniform [-1, 1)
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+static inline uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static inline float bf2f(uint16_t h) { uint32_t u = static_cast<uint32_t>(h) << 16; float f; memcpy(&f, &u, 4); return f; }
+
+int main(int argc, char** argv) {
+  const int shape = argc > 1 ? atoi(argv[1]) : 0;
+  const int variant = argc > 2 ? atoi(argv[2]) : 0;
+  const int n_win = argc > 3 ? atoi(argv[3]) : 2;
+  const int iters = argc > 4 ? atoi(argv[4]) : 0;
+
+  int cin, cout, k, dil, pad_left, l_in, l_out;
+  const int frames = 6, period = 665, rpw = 4096;
+  if (shape == 0) { cin = 128; cout = 128; k = 5; dil = 3; pad_left = 6; l_in = 659; l_out = 659; }
+  else if (shape == 1) { cin = 64; cout = 128; k = 7; dil = 1; pad_left = 0; l_in = 665; l_out = 659; }
+  else { cin = 32; cout = 32; k = 3; dil = 1; pad_left = 1; l_in = 659; l_out = 659; }
+
+  const long long R = static_cast<long long>(n_win) * rpw;
+  const long long plane = R + 2 * jg::kGuardRows;
+  std::vector<uint16_t> hx(static_cast<size_t>(cin / 8) * plane * 8, 0), hsc(static_cast<size_t>(cout / 8) * plane * 8, 0);
+  std::vector<uint8_t> hmask(R, 0), hscmask(R, 0);
+  for (long long r = 0; r < R; ++r) {
+    const int rw = static_cast<int>(r % rpw);
+    const int f = rw / period, pos = rw % period;
+    const bool in_frame_in = f < frames && pos < l_in;
+    const bool in_frame_out = f < frames && pos < l_out;
+    // knock a few rows out of the masks to exercise the masked paths
+    const bool knocked = (r % 97) == 13;
+    hmask[r] = in_frame_out && !knocked;
+    hscmask[r] = in_frame_out && ((r % 89) != 7);
+    if (in_frame_in)
+      for (int c = 0; c < cin; ++c)
+        hx[(static_cast<size_t>(c >> 3) * plane + jg::kGuardRows + r) * 8 + (c & 7)] = f2bf(frand());
+    if (hscmask[r])
+      for (int c = 0; c < cout; ++c)
+        hsc[(static_cast<size_t>(c >> 3) * plane + jg::kGuardRows + r) * 8 + (c & 7)] = f2bf(frand());
+  }
+  const int ktot = k * cin;
+  std::vector<uint16_t> hw(static_cast<size_t>(ktot) * cout);
+  const float wscale = 1.0f / sqrtf(static_cast<float>(ktot));
+  for (int kk = 0; kk < ktot; ++kk)
+    for (int co = 0; co < cout; ++co)
+      hw[(static_cast<size_t>(kk >> 3) * cout + co) * 8 + (kk & 7)] = f2bf(frand() * wscale * 1.7f);
+  std::vector<float> hpar(6 * cout);
+  for (int c = 0; c < cout; ++c) {
+    hpar[c] = 1.0f + 0.25f * frand();          // scale1
+    hpar[cout + c] = 0.1f * frand();           // shift1
+    hpar[2 * cout + c] = 1.0f + 0.25f * frand();
+    hpar[3 * cout + c] = 0.1f * frand();
+    hpar[4 * cout + c] = 0.05f * frand();      // bias
+    hpar[5 * cout + c] = 0.3f * frand();       // sc_const
+  }
+
+  uint16_t *dx, *dsc, *dw, *dy_ref, *dy_tc;
+  uint8_t *dmask, *dscmask;
+  float *dpar, *dtap_ref, *dtap_tc, *dpool_ref, *dpool_tc;
+  int* derr;
+  const size_t ybytes = static_cast<size_t>(cout / 8) * plane * 16;
+  CK(cudaMalloc(&dx, hx.size() * 2)); CK(cudaMalloc(&dsc, hsc.size() * 2)); CK(cudaMalloc(&dw, hw.size() * 2));
+  CK(cudaMalloc(&dy_ref, ybytes)); CK(cudaMalloc(&dy_tc, ybytes));
+  CK(cudaMalloc(&dmask, R)); CK(cudaMalloc(&dscmask, R)); CK(cudaMalloc(&dpar, hpar.size() * 4));
+  CK(cudaMalloc(&dtap_ref, n_win * cout * 4)); CK(cudaMalloc(&dtap_tc, n_win * cout * 4));
+  CK(cudaMalloc(&dpool_ref, n_win * cout * 4)); CK(cudaMalloc(&dpool_tc, n_win * cout * 4));
+  CK(cudaMalloc(&derr, 4)); CK(cudaMemset(derr, 0, 4));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dsc, hsc.data(), hsc.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dmask, hmask.data(), R, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dscmask, hscmask.data(), R, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dpar, hpar.data(), hpar.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dy_ref, 0, ybytes)); CK(cudaMemset(dy_tc, 0, ybytes));
+  CK(cudaMemset(dtap_ref, 0, n_win * cout * 4)); CK(cudaMemset(dtap_tc, 0, n_win * cout * 4));
+  std::vector<float> sentinel(static_cast<size_t>(n_win) * cout, -1.0e9f);
+  CK(cudaMemcpy(dpool_ref, sentinel.data(), sentinel.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dpool_tc, sentinel.data(), sentinel.size() * 4, cudaMemcpyHostToDevice));
+
+  jg::ConvParams p{};
+  p.x = reinterpret_cast<const __nv_bfloat16*>(dx) + jg::kGuardRows * 8;
+  p.sc = (shape == 0) ? reinterpret_cast<const __nv_bfloat16*>(dsc) + jg::kGuardRows * 8 : nullptr;
+  p.sc_mask = (shape == 0) ? dscmask : nullptr;
+  p.sc_const = dpar + 5 * cout;
+  p.out_mask = dmask;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(dw);
+  p.bias = dpar + 4 * cout;
+  p.scale1 = dpar; p.shift1 = dpar + cout; p.scale2 = dpar + 2 * cout; p.shift2 = dpar + 3 * cout;
+  p.x_plane = plane; p.y_plane = plane;
+  p.n_tiles = static_cast<int>(R / jg::kTileM);
+  p.rows_per_window = rpw;
+  p.cin = cin; p.cout = cout; p.ntaps = k;
+  int mn = 0, mx = 0;
+  for (int t = 0; t < k; ++t) { p.shifts[t] = t * dil - pad_left; mn = p.shifts[t] < mn ? p.shifts[t] : mn; mx = p.shifts[t] > mx ? p.shifts[t] : mx; }
+  p.halo_l = -mn; p.halo_r = mx;
+  p.act1 = jg::ACT_GELU_TANH; p.act2 = jg::ACT_GELU_TANH;
+  p.has_affine2 = (shape == 0);
+  p.tap_mode = (shape == 0) ? 2 : (shape == 1 ? 1 : 0);
+  p.pool_mode = (shape == 0) ? 1 : 0;
+  p.err = derr;
+  jg::conv_fill_descriptors(p);
+  if (variant == 1) { unsigned t = p.a_lbo; p.a_lbo = p.a_sbo; p.a_sbo = t; t = p.b_lbo; p.b_lbo = p.b_sbo; p.b_sbo = t; }
+
+  int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
+  printf("shape %d variant %d windows %d tiles %d sms %d stages %d\n", shape, variant, n_win, p.n_tiles, dev_sms, jg::conv_tc_stages(p));
+
+  jg::ConvParams pr = p;
+  pr.y = reinterpret_cast<__nv_bfloat16*>(dy_ref) + jg::kGuardRows * 8; pr.tap_sum = dtap_ref; pr.pool = dpool_ref;
+  CK(jg::launch_conv_ref(pr, 0));
+  CK(cudaDeviceSynchronize());
+
+  jg::ConvParams pt = p;
+  pt.y = reinterpret_cast<__nv_bfloat16*>(dy_tc) + jg::kGuardRows * 8; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
+  CK(jg::launch_conv_tc(pt, dev_sms, 0));
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) {
+    int herr = -1; cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
+    printf("tc kernel failed: %s (err code %d)\n", cudaGetErrorString(se), herr);
+    return 3;
+  }
+
+  std::vector<uint16_t> yr(ybytes / 2), yt(ybytes / 2);
+  CK(cudaMemcpy(yr.data(), dy_ref, ybytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(yt.data(), dy_tc, ybytes, cudaMemcpyDeviceToHost));
+  double maxdiff = 0, maxref = 0; size_t nbad = 0;
+  for (size_t i = 0; i < yr.size(); ++i) {
+    const double a = bf2f(yr[i]), b = bf2f(yt[i]);
+    const double d = fabs(a - b);
+    if (d > maxdiff) maxdiff = d;
+    if (fabs(a) > maxref) maxref = fabs(a);
+    if (d > 0.03 + 0.02 * fabs(a)) ++nbad;
+  }
+  std::vector<float> tr(n_win * cout), tt(n_win * cout), pr_(n_win * cout), pt_(n_win * cout);
+  CK(cudaMemcpy(tr.data(), dtap_ref, tr.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tt.data(), dtap_tc, tt.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pr_.data(), dpool_ref, tr.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pt_.data(), dpool_tc, tr.size() * 4, cudaMemcpyDeviceToHost));
+  double tapdiff = 0, tapmax = 0, pooldiff = 0;
+  for (size_t i = 0; i < tr.size(); ++i) {
+    tapdiff = fmax(tapdiff, fabs(tr[i] - tt[i])); tapmax = fmax(tapmax, fabs(tr[i]));
+    pooldiff = fmax(pooldiff, fabs(pr_[i] - pt_[i]));
+  }
+  printf("y: max|ref| %.4f max|diff| %.5f bad %zu / %zu ; tap max|ref| %.3f max|diff| %.5f ; pool max|diff| %.5f\n",
+         maxref, maxdiff, nbad, yr.size(), tapmax, tapdiff, pooldiff);
+  const bool ok = nbad == 0 && tapdiff <= 1e-3 * (1.0 + tapmax) * 4 && pooldiff < 0.05;
+  printf("RESULT shape %d variant %d: %s\n", shape, variant, ok ? "MATCH" : "MISMATCH");
+
+  if (iters > 0 && ok) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // warm up for ~1.5 s so the SM clock has left its idle state before timing
+    {
+      cudaEvent_t w0, w1; cudaEventCreate(&w0); cudaEventCreate(&w1);
+      float wms = 0; CK(cudaEventRecord(w0));
+      while (wms < 1500.0f) {
+        for (int i = 0; i < 20; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
+        CK(cudaEventRecord(w1)); CK(cudaEventSynchronize(w1));
+        cudaEventElapsedTime(&wms, w0, w1);
+      }
+    }
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+    const double flops = 2.0 * static_cast<double>(R) * ktot * cout;
+    printf("TIMING shape %d windows %d: %.3f ms/launch, %.1f TFLOP/s (rows incl. gaps), %.1f us/tile-wave\n",
+           shape, n_win, ms, flops / ms * 1e-9, ms * 1e3 / ((p.n_tiles + dev_sms - 1) / dev_sms));
+  }
+  return ok ? 0 : 1;
+}
