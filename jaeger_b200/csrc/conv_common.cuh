@@ -1,15 +1,19 @@
 // Shared definitions for the stage-3 (masked dilated Conv1D stack) kernels.
 //
-// Activation layout in HBM ("planar-8", channels split in chunks of 8):
-//     act[c8][row][8]  bf16,   c8 = C/8,  row in [-GUARD, R + GUARD)
+// Activation layout in HBM ("g64sw": channel groups of 64, rows pre-swizzled):
+//     act[g][row][64]  bf16,   g = C/64,  row in [-GUARD, R + GUARD)
+// inside a row's 128 bytes the eight 16-byte chunks are stored XOR-swizzled by the row
+// number (chunk c of row r sits at chunk position c ^ (r & 7)).  That is exactly the
+// shared-memory image the tensor core's SWIZZLE_128B K-major operand layout expects when
+// a span of rows starting at a multiple of 8 is copied linearly to a 1024-byte aligned
+// shared-memory address, so ONE bulk-TMA copy per 64-channel stage stages a whole
+// halo'd A tile and no tensor map is needed.
 // A "row" is one codon position of one frame of one window.  Frame f of window w
 // lives at rows  w*rows_per_window + f*period + [0, L) ; every other row (the gap
 // between frames, the tail of the window, the guard rows) is kept at zero, so a
 // dilated tap that reaches past a frame edge reads the zero padding the reference
 // gets from TF "SAME" padding (reference: src/jaeger/nnlib/v2/layers.py:1217-1280).
-// With this layout a conv tap is a pure row shift, each 8-channel plane of an
-// A tile is one contiguous span (one bulk-TMA copy), and the epilogue's 16-byte
-// stores are fully coalesced across the 32 lanes of a warp (lane == row).
+// With this layout a conv tap is a pure row shift of the operand descriptor.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -26,13 +30,13 @@ enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_RELU = 2, ACT_GELU_ERF = 3
 // One conv layer launch.  All pointers are device pointers.
 struct ConvParams {
   // tensors -------------------------------------------------------------
-  const __nv_bfloat16* x;       // input, planar-8, points at row 0 of plane 0
-  __nv_bfloat16* y;             // output, planar-8 (may alias sc), or nullptr (pool-only last layer)
+  const __nv_bfloat16* x;       // input, g64sw, points at row 0 of group 0
+  __nv_bfloat16* y;             // output, g64sw (may alias sc), or nullptr (pool-only last layer)
   const __nv_bfloat16* sc;      // residual shortcut tensor (Cout channels) or nullptr
   const uint8_t* sc_mask;       // row mask the shortcut tensor was stored with (nullptr = all valid)
   const float* sc_const;        // [Cout] value of the shortcut at rows its mask zeroed
   const uint8_t* out_mask;      // [R] 1 = valid output row (in frame and mask-propagated)
-  const __nv_bfloat16* w;       // weights, smem image [ntaps*Cin/8][Cout][8]
+  const __nv_bfloat16* w;       // weights, smem image (see w_index)
   const float* bias;            // [Cout] conv bias (used only when tap_raw)
   const float* scale1;          // [Cout] affine after conv (norm folded; bias folded unless tap_raw)
   const float* shift1;
@@ -53,10 +57,23 @@ struct ConvParams {
   int has_affine2;
   int tap_mode;                 // 0 none, 1 raw conv output (acc+bias), 2 after act1
   int pool_mode;                // 0 none, 1 masked max, 2 masked sum
-  // tcgen05 operand descriptors (host-computed so a probe can vary them)
-  unsigned a_lbo, a_sbo, b_lbo, b_sbo;   // bytes
   int* err;                     // device int, set non-zero on a barrier time-out
+  long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)
 };
+
+// element index of (row, channel c) inside a g64sw tensor whose groups are `plane` rows apart
+__host__ __device__ __forceinline__ long long act_index(long long row, int c, long long plane) {
+  const int g = c >> 6, cl = c & 63;
+  const int chunk = (cl >> 3) ^ static_cast<int>(row & 7);
+  return (static_cast<long long>(g) * plane + row) * 64 + chunk * 8 + (cl & 7);
+}
+// element index of weight (tap t, in-channel ci, out-channel co) inside the smem image:
+// blocks [t][ci/64] of [cout rows][64 k] bf16, 16-byte chunks swizzled by (co & 7)
+__host__ __device__ __forceinline__ long long w_index(int t, int ci, int co, int cin, int cout) {
+  const int g = ci >> 6, cl = ci & 63;
+  const int chunk = (cl >> 3) ^ (co & 7);
+  return (static_cast<long long>(t * (cin >> 6) + g) * cout + co) * 64 + chunk * 8 + (cl & 7);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_GELU_TANH) {
@@ -72,6 +89,22 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
   }
   return v;
+}
+
+// Activation over a register array with the (warp-uniform) selector hoisted out of the loop,
+// so only the selected formula is executed.
+template <int N>
+__device__ __forceinline__ void act_apply_vec(float (&v)[N], int act) {
+  if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = act_apply(v[j], ACT_GELU_TANH);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (act == ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = act_apply(v[j], ACT_GELU_ERF);
+  }
 }
 
 // float atomic max through the sign-split integer trick (no NaNs on this path)

@@ -7,18 +7,9 @@ namespace jg {
 
 constexpr unsigned kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
-// Fills the descriptor fields for the canonical no-swizzle K-major operand layouts.
-inline void conv_fill_descriptors(ConvParams& p) {
-  const unsigned rows_a = kTileM + p.halo_l + p.halo_r;
-  p.a_lbo = rows_a * 16;  // distance between the two 8-channel planes of one K=16 MMA
-  p.a_sbo = 128;          // distance between 8-row groups: rows are linear at 16 B pitch
-  p.b_lbo = p.cout * 16;
-  p.b_sbo = 128;
-}
-
 // Returns 0 on success, a negative code when the layer does not fit the kernel's constraints.
 inline int conv_tc_stages(const ConvParams& p) {
-  if (p.cin % 16 != 0 || p.cout % 32 != 0 || p.cout > 256 || p.ntaps > kMaxTaps) return -1;
+  if (p.cin % 64 != 0 || p.cout % 32 != 0 || p.cout > 256 || p.ntaps > kMaxTaps) return -1;
   for (int s = 4; s >= 2; --s) {
     tc::SmemLayout L = tc::smem_layout(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, s);
     if (L.total <= kMaxSmem) return s;

@@ -7,24 +7,27 @@
 // 918-941, 1882-1915, 517-529; src/jaeger/nnlib/v2/nmd.py:43-77).
 //
 // GEMM view of one tile:  D[128 rows, Cout] = sum_t  X[rows + shift_t, Cin] * W_t[Cin, Cout]
-//   * A operand: one halo'd activation tile [Cin/8 planes][128+halo rows][8 ch] is brought
-//     into shared memory once per 64-channel stage; every tap re-reads it through a
-//     shared-memory descriptor whose start address is advanced by shift_t rows (the
-//     no-swizzle K-major canonical layout makes a row shift a 16-byte address shift),
-//     so the k-fold im2col re-read never leaves the SM.
-//   * B operand: the whole layer's weights [ntaps*Cin/8][Cout][8] stay resident in
-//     shared memory for the life of the (persistent) CTA.
-//   * D: fp32 in TMEM, double buffered (2 x Cout columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1.
+//   * A operand: one halo'd activation tile [8+128+8 rows][64 ch] (SWIZZLE_128B K-major
+//     image, pre-swizzled in HBM) is brought into shared memory by ONE bulk-TMA copy per
+//     64-channel stage; every tap re-reads it through a shared-memory descriptor whose
+//     start address is advanced by shift_t rows (128 B each), so the k-fold im2col
+//     re-read never leaves the SM.
+//   * B operand: the whole layer's weights (blocks [tap][Cin/64] of [Cout][64], swizzled)
+//     stay resident in shared memory for the life of the (persistent) CTA.
+//   * D: fp32 in TMEM, a ring of 4 accumulators (4 x Cout columns) so the MMAs run up to
+//     three tiles ahead of the epilogues.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+// warp 2 = TMEM allocator, warps 4..11 = two epilogue groups (TMEM lane quarter = warp % 4)
+// that drain alternate tiles, so the latency chain of one tile's epilogue (mask/shortcut
+// loads, TMEM reads, stores) overlaps the next tile's.
 #pragma once
 #include "conv_common.cuh"
 
 namespace jg {
 namespace tc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -53,16 +56,38 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      if (err) atomicExch(err, code);
-      __trap();
-    }
-  }
+// Bounded wait, written as ONE opaque asm block so the compiler keeps treating the calling
+// warp as converged (a C++ spin loop makes every later value "divergent" and forces the
+// MMA descriptors through per-lane registers).  A protocol bug must surface as a launch
+// error, never as a hung GPU: after ~2^24 failed (hardware-suspended) probes the warp traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "JG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra JG_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 16777216;\n"
+      "@p bra JG_WAIT;\n"
+      "trap;\n"
+      "JG_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
                                          uint32_t bar) {
@@ -121,19 +146,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, no-swizzle ("interleaved") shared-memory matrix descriptor.
-//   element (row r, k-chunk j of 8 bf16) lives at  start + (r%8)*16 + (r/8)*SBO + j*LBO
-// With SBO = 128 the rows are linear at a 16-byte pitch, which is what lets a conv tap
-// be expressed as  start += shift*16.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;  // descriptor version 1 (sm_100)
-  return d;         // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows are 128 bytes (64 bf16) apart,
+// 8-row groups 1024 bytes apart (SBO); the 16-byte chunks of a row are XOR-swizzled with
+// address bits [7,10).  The hardware applies the XOR to the absolute shared-memory address,
+// so advancing the start address by whole rows (a conv tap) or by 32 bytes (a K=16 step)
+// keeps addressing the data a linear copy of the pre-swizzled HBM rows put there.
+// hi word is constant; lo word = (addr >> 4) | LBO field, so stepping an operand by `bytes`
+// is  lo += bytes >> 4  (the 14-bit address field cannot overflow below 256 KB).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) {
+  return ((saddr >> 4) & 0x3FFFu) | (1u << 16);
 }
-
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 // Column-wise reduction across the 32 lanes of a warp of a [32 lanes][32 columns]
 // register tile.  Afterwards v[0] on lane l holds the reduction of column l.
 template <bool kMax>
@@ -153,44 +179,47 @@ __device__ __forceinline__ void warp_cols_reduce(float (&v)[32], int lane) {
 
 struct SmemLayout {
   uint32_t w_off, stage_off, par_off, bar_off, total;
-  uint32_t stage_bytes, plane_a, rows_a, ch_stage, stages_per_tile, w_bytes;
+  uint32_t stage_bytes, stage_pitch, rows_a, lead, groups, w_bytes;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int cin, int cout, int ntaps, int halo_l,
                                                   int halo_r, int n_stages) {
   SmemLayout L;
-  L.rows_a = kTileM + halo_l + halo_r;
-  L.plane_a = L.rows_a * 16;
-  L.ch_stage = (cin >= 64) ? 8 : (cin / 8);
-  L.stages_per_tile = (cin / 8) / L.ch_stage;
-  L.stage_bytes = L.ch_stage * L.plane_a;
+  L.lead = static_cast<uint32_t>((halo_l + 7) / 8 * 8);   // tile loads start at a multiple of 8 rows
+  L.rows_a = L.lead + kTileM + static_cast<uint32_t>((halo_r + 7) / 8 * 8);
+  L.groups = cin / 64;                                      // one stage per 64 input channels
+  L.stage_bytes = L.rows_a * 128;
+  L.stage_pitch = (L.stage_bytes + 1023u) & ~1023u;
   L.w_bytes = static_cast<uint32_t>(ntaps) * cin * cout * 2;
   L.w_off = 0;
-  L.stage_off = (L.w_bytes + 127u) & ~127u;
-  L.par_off = L.stage_off + n_stages * ((L.stage_bytes + 127u) & ~127u);
+  L.stage_off = (L.w_bytes + 1023u) & ~1023u;
+  L.par_off = L.stage_off + n_stages * L.stage_pitch;
   L.bar_off = L.par_off + 6u * cout * 4u;
-  L.total = L.bar_off + 256u;
+  L.total = L.bar_off + 256u + 1024u;                       // + slack to align the base to 1024 B
   return L;
 }
 
 template <int kStages>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const SmemLayout L = smem_layout(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, kStages);
-  const uint32_t stage_pitch = (L.stage_bytes + 127u) & ~127u;
+  const uint32_t stage_pitch = L.stage_pitch;
 
   float* s_par = reinterpret_cast<float*>(smem + L.par_off);  // scale1,shift1,scale2,shift2,bias,sc_const
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  // barrier slots: [0,S) full, [S,2S) empty, 2S wbar, 2S+1..2 tmem_full, 2S+3..4 tmem_empty
+  // barrier slots: [0,S) full, [S,2S) empty, 2S wbar, 2S+1..4 tmem_full, 2S+5..8 tmem_empty
   const uint32_t bar0 = smem_u32(s_bar);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (kStages + s); };
   const uint32_t WBAR = bar0 + 8u * (2 * kStages);
   auto TFULL = [&](int a) { return bar0 + 8u * (2 * kStages + 1 + a); };
-  auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * kStages + 3 + a); };
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 5);
+  auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 9);
+  // accumulator ring in TMEM: 4 x cout columns when they fit the 512 columns, else 2
+  const int n_acc = (4 * p.cout <= 512) ? 4 : 2;
 
   const uint32_t w_base = smem_u32(smem + L.w_off);
   const uint32_t st_base = smem_u32(smem + L.stage_off);
@@ -214,14 +243,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(EMPTY(s), 1);
     }
     mbar_init(WBAR, 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(TFULL(a), 1);
-      mbar_init(TEMPTY(a), 128);
+      mbar_init(TEMPTY(a), kEpiThreads / 2);  // one epilogue group (4 warps) drains a tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tmem_cols = (2 * p.cout <= 32) ? 32u : (2 * p.cout <= 64) ? 64u
-                           : (2 * p.cout <= 128) ? 128u : (2 * p.cout <= 256) ? 256u : 512u;
+  const uint32_t acc_cols = static_cast<uint32_t>(n_acc * p.cout);
+  const uint32_t tmem_cols = (acc_cols <= 32) ? 32u : (acc_cols <= 64) ? 64u
+                           : (acc_cols <= 128) ? 128u : (acc_cols <= 256) ? 256u : 512u;
   if (warp == 2) tmem_alloc(smem_u32(s_tmem), tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -229,101 +259,125 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp stays converged; one elected lane issues) =====
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(WBAR, L.w_bytes);
       for (uint32_t off = 0; off < L.w_bytes; off += 32768u) {
         uint32_t n = L.w_bytes - off < 32768u ? L.w_bytes - off : 32768u;
         bulk_g2s(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, WBAR);
       }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const long long r_first = static_cast<long long>(tile) * kTileM - p.halo_l;
-        for (uint32_t h = 0; h < L.stages_per_tile; ++h) {
-          mbar_wait(EMPTY(s), ph ^ 1u, p.err, 1);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const long long r_first = static_cast<long long>(tile) * kTileM - L.lead;
+      for (uint32_t g = 0; g < L.groups; ++g) {
+        mbar_wait(EMPTY(s), ph ^ 1u);
+        if (leader) {
           mbar_expect_tx(FULL(s), L.stage_bytes);
-          for (uint32_t c = 0; c < L.ch_stage; ++c) {
-            const __nv_bfloat16* src =
-                p.x + (static_cast<long long>(h * L.ch_stage + c) * p.x_plane + r_first) * 8;
-            bulk_g2s(st_base + s * stage_pitch + c * L.plane_a, src, L.plane_a, FULL(s));
-          }
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          const __nv_bfloat16* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
+          bulk_g2s(st_base + s * stage_pitch, src, L.stage_bytes, FULL(s));
         }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=cout, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             (static_cast<uint32_t>(p.cout >> 3) << 17) |
-                             (static_cast<uint32_t>(kTileM >> 4) << 24);
-      mbar_wait(WBAR, 0, p.err, 2);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1u;
-        mbar_wait(TEMPTY(as), aph ^ 1u, p.err, 3);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.cout);
-        uint32_t accumulate = 0;
-        for (uint32_t h = 0; h < L.stages_per_tile; ++h) {
-          mbar_wait(FULL(s), ph, p.err, 4);
-          tc_fence_after();
-          const uint32_t a_stage = st_base + s * stage_pitch;
-          for (int t = 0; t < p.ntaps; ++t) {
-            const uint32_t a_tap = a_stage + static_cast<uint32_t>(p.halo_l + p.shifts[t]) * 16u;
-            const uint32_t b_tap =
-                w_base + static_cast<uint32_t>(t * (p.cin >> 3) + h * L.ch_stage) * (p.cout * 16u);
-            for (uint32_t j = 0; j < L.ch_stage / 2; ++j) {
-              const uint64_t adesc = make_desc(a_tap + 2 * j * L.plane_a, p.a_lbo, p.a_sbo);
-              const uint64_t bdesc = make_desc(b_tap + 2 * j * (p.cout * 16u), p.b_lbo, p.b_sbo);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-          }
-          umma_commit(EMPTY(s));  // frees the smem stage when these MMAs retire
-          if (++s == kStages) { s = 0; ph ^= 1u; }
-        }
-        umma_commit(TFULL(as));   // accumulator complete -> epilogue
-      }
-    }
-    __syncwarp();
-  } else if (warp >= kEpiWarp0) {
-    // ===== epilogue: TMEM -> registers -> fused affine/residual/activation/taps -> HBM =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const float* s_scale1 = s_par;
-    const float* s_shift1 = s_par + p.cout;
-    const float* s_scale2 = s_par + 2 * p.cout;
-    const float* s_shift2 = s_par + 3 * p.cout;
-    const float* s_bias = s_par + 4 * p.cout;
-    const float* s_scc = s_par + 5 * p.cout;
+    // ===== MMA issuer (whole warp converged, tcgen05.mma predicated on one elected lane) =====
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=cout, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                           (static_cast<uint32_t>(p.cout >> 3) << 17) |
+                           (static_cast<uint32_t>(kTileM >> 4) << 24);
+    const uint32_t b_group_step = static_cast<uint32_t>(p.cout) * 8u;  // one [cout][64] block
+    const uint32_t b_tap_step = b_group_step * L.groups;
+    const uint32_t b_lo0 = desc_lo_sw128(w_base);
+    mbar_wait(WBAR, 0);
+    int s = 0;
+    uint32_t ph = 0;
     int it = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1u;
+      const int as = it % n_acc;
+      const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
+      mbar_wait(TEMPTY(as), aph ^ 1u);
+      tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && leader && it < 64) p.dbg[it * 8 + 0] = clock64();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.cout);
+      uint32_t accumulate = 0;
+      for (uint32_t g = 0; g < L.groups; ++g) {
+        mbar_wait(FULL(s), ph);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo_sw128(st_base + s * stage_pitch + L.lead * 128u);
+        const uint32_t b_lo = b_lo0 + g * b_group_step;
+#pragma unroll 1
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t a_tap = a_lo + static_cast<uint32_t>(p.shifts[t] * 8);  // 128 B / 16 per row
+          const uint32_t b_tap = b_lo + static_cast<uint32_t>(t) * b_tap_step;
+#pragma unroll
+          for (uint32_t k16 = 0; k16 < 4; ++k16) {
+            if (leader)
+              umma_bf16(d_tmem, desc_pack(a_tap + k16 * 2u, kDescHiSw128),
+                        desc_pack(b_tap + k16 * 2u, kDescHiSw128), idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        if (leader) umma_commit(EMPTY(s));  // frees the smem stage when these MMAs retire
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
+      if (leader) umma_commit(TFULL(as));   // accumulator complete -> epilogue
+      if (p.dbg && blockIdx.x == 0 && leader && it < 64) p.dbg[it * 8 + 1] = clock64();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue: TMEM -> registers -> fused affine/residual/activation/taps -> HBM =====
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int grp = (warp - kEpiWarp0) >> 2;   // epilogue group: drains tiles with (it & 1) == grp
+    const int n_cb = p.cout / 32;
+    const float4* s_scale1 = reinterpret_cast<const float4*>(s_par);
+    const float4* s_shift1 = reinterpret_cast<const float4*>(s_par + p.cout);
+    const float4* s_scale2 = reinterpret_cast<const float4*>(s_par + 2 * p.cout);
+    const float4* s_shift2 = reinterpret_cast<const float4*>(s_par + 3 * p.cout);
+    const float4* s_bias = reinterpret_cast<const float4*>(s_par + 4 * p.cout);
+    const float4* s_scc = reinterpret_cast<const float4*>(s_par + 5 * p.cout);
+    const bool has_sc = p.sc != nullptr;
+    for (int tile = tile_begin + grp, it = grp; tile < tile_end; tile += 2, it += 2) {
+      const int as = it % n_acc;
+      const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
       const long long row = static_cast<long long>(tile) * kTileM + q * 32 + lane;
+      const int sw = static_cast<int>(row & 7);
       const int win = static_cast<int>((static_cast<long long>(tile) * kTileM) / p.rows_per_window);
       const bool valid = p.out_mask[row] != 0;
-      const bool sc_valid = p.sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
-      mbar_wait(TFULL(as), aph, p.err, 5);
+      const bool sc_valid = has_sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
+      // the shortcut does not depend on the MMAs: fetch the first batch before waiting on them
+      uint4 scv[4];
+      if (sc_valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          scv[j] = *reinterpret_cast<const uint4*>(p.sc + row * 64 + ((j ^ sw) * 8));
+      }
+      if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 2] = clock64();
+      mbar_wait(TFULL(as), aph);
       tc_fence_after();
-      for (int cb = 0; cb < p.cout / 32; ++cb) {
+      if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
+      for (int cb = 0; cb < n_cb; ++cb) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                       static_cast<uint32_t>(as * p.cout + cb * 32), raw);
-        uint4 scv[4];
-        if (p.sc && sc_valid) {
+        uint4 scc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) scc[j] = scv[j];
+        if (sc_valid && cb + 1 < n_cb) {  // prefetch the next batch's shortcut
+          const int nb = cb + 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             scv[j] = *reinterpret_cast<const uint4*>(
-                p.sc + (static_cast<long long>(cb * 4 + j) * p.y_plane + row) * 8);
+                p.sc + (static_cast<long long>(nb >> 1) * p.y_plane + row) * 64 +
+                ((((nb & 1) * 4 + j) ^ sw) * 8));
         }
         tmem_ld_wait();
+        if (cb + 1 == n_cb) {  // every TMEM read of this tile has landed: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(TEMPTY(as));
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -331,33 +385,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (p.tap_mode == 1) {
           float tv[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] + s_bias[cb * 32 + j] : 0.0f;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = s_bias[cb * 8 + j4];
+            tv[j4 * 4 + 0] = valid ? v[j4 * 4 + 0] + b.x : 0.0f;
+            tv[j4 * 4 + 1] = valid ? v[j4 * 4 + 1] + b.y : 0.0f;
+            tv[j4 * 4 + 2] = valid ? v[j4 * 4 + 2] + b.z : 0.0f;
+            tv[j4 * 4 + 3] = valid ? v[j4 * 4 + 3] + b.w : 0.0f;
+          }
           warp_cols_reduce<false>(tv, lane);
           atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale1[cb * 32 + j], s_shift1[cb * 32 + j]);
-        if (p.sc) {
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 a = s_scale1[cb * 8 + j4], b = s_shift1[cb * 8 + j4];
+          v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
+          v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
+          v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
+          v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
+        }
+        if (has_sc) {
           if (sc_valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&scv[j]);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&scc[j]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h2[e]);
+                const float2 f = __bfloat1622float2(h2[e]);
                 v[j * 8 + 2 * e] += f.x;
                 v[j * 8 + 2 * e + 1] += f.y;
               }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += s_scc[cb * 32 + j];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 c = s_scc[cb * 8 + j4];
+              v[j4 * 4 + 0] += c.x; v[j4 * 4 + 1] += c.y; v[j4 * 4 + 2] += c.z; v[j4 * 4 + 3] += c.w;
+            }
           }
         }
-        if (p.act1 != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.act1);
-        }
+        act_apply_vec(v, p.act1);
         if (p.tap_mode == 2) {
           float tv[32];
 #pragma unroll
@@ -367,8 +433,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         if (p.has_affine2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = act_apply(fmaf(v[j], s_scale2[cb * 32 + j], s_shift2[cb * 32 + j]), p.act2);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a = s_scale2[cb * 8 + j4], b = s_shift2[cb * 8 + j4];
+            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
+            v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
+            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
+            v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
+          }
+          act_apply_vec(v, p.act2);
         }
         if (p.pool_mode != 0) {
           float tv[32];
@@ -386,22 +458,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         if (p.y) {
+          __nv_bfloat16* yrow = p.y + (static_cast<long long>(cb >> 1) * p.y_plane + row) * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = valid ? v[j * 8 + 2 * e] : 0.0f;
-              float b = valid ? v[j * 8 + 2 * e + 1] : 0.0f;
-              h2[e] = __floats2bfloat162_rn(a, b);
-            }
-            *reinterpret_cast<uint4*>(p.y + (static_cast<long long>(cb * 4 + j) * p.y_plane + row) * 8) = o;
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(yrow + ((((cb & 1) * 4 + j) ^ sw) * 8)) = o;
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(TEMPTY(as));
+      if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 4] = clock64();
     }
   }
 

@@ -1,0 +1,23 @@
+"""CPU oracle for the `jaeger predict` hot path  --  TEST INFRASTRUCTURE ONLY.
+
+A plain NumPy / torch-fp32 restatement of the reference algorithm for every stage of the
+path (windowing, encoding, conv stack, per-contig aggregation, prophage region calling).
+Each function cites the reference file:line it follows (paths relative to
+/root/reference/src/jaeger).
+
+Who may import this package: `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py`, and there only as the checker or the timed CPU
+baseline.  Nothing under `jaeger_b200/` imports it; the product path fails loudly when the
+CUDA library is missing instead of falling back to this code.
+
+Pinning status (see DESIGN.md "Oracle"):
+  * windows, window metadata, encoder tokens, post-processing helpers, per-contig
+    aggregation, TSV summary and score smoothing are pinned against golden vectors produced
+    by importing the reference's own Python modules in the build container
+    (tests/golden/make_goldens.py) and against the reference tests' known answers.
+  * conv-stack logits: PARITY UNPINNED - TensorFlow/Keras cannot be installed here, so the
+    forward pass is a restatement of nnlib/v2/layers.py checked only against the reference
+    tests' mask / pooling known answers.
+  * change-point segmentation (ruptures KernelCPD + kneed): PARITY UNPINNED - restated from
+    the published algorithms (PELT with L2 cost; Kneedle), libraries absent.
+"""

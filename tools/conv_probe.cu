@@ -2,9 +2,8 @@
 //   conv_probe <shape> <variant> [n_windows] [time_iters]
 // shape:   0 = residual conv (Cin 128, Cout 128, k5 d3, SAME, shortcut + taps + pool)
 //          1 = stem conv     (Cin 64,  Cout 128, k7 d1, VALID, raw tap)
-//          2 = narrow conv   (Cin 32,  Cout 32,  k3 d1, SAME)
-// variant: 0 = canonical descriptors (LBO = plane pitch, SBO = 128)
-//          1 = LBO/SBO swapped
+//          2 = wide-dilation conv (Cin 64, Cout 64, k5 d8, SAME)
+// variant: unused (kept for CLI compatibility)
 // Compares conv_tc_kernel against conv_ref_kernel on the same random inputs and prints
 // max |diff|; with time_iters > 0 also times the tensor-core kernel with CUDA events.
 #include <cstdio>
@@ -33,16 +32,19 @@ int main(int argc, char** argv) {
   const int variant = argc > 2 ? atoi(argv[2]) : 0;
   const int n_win = argc > 3 ? atoi(argv[3]) : 2;
   const int iters = argc > 4 ? atoi(argv[4]) : 0;
+  const int strip = argc > 5 ? atoi(argv[5]) : 0;  // 1: no taps/pool, 2: no activations/affine2, 4: no shortcut
 
   int cin, cout, k, dil, pad_left, l_in, l_out;
   const int frames = 6, period = 665, rpw = 4096;
   if (shape == 0) { cin = 128; cout = 128; k = 5; dil = 3; pad_left = 6; l_in = 659; l_out = 659; }
   else if (shape == 1) { cin = 64; cout = 128; k = 7; dil = 1; pad_left = 0; l_in = 665; l_out = 659; }
-  else { cin = 32; cout = 32; k = 3; dil = 1; pad_left = 1; l_in = 659; l_out = 659; }
+  else if (shape == 2) { cin = 64; cout = 64; k = 5; dil = 8; pad_left = 16; l_in = 640; l_out = 640; }
+  else if (shape == 3) { cin = 128; cout = 256; k = 2; dil = 3; pad_left = 3; l_in = 659; l_out = 659; }
+  else { cin = 128; cout = 64; k = 5; dil = 3; pad_left = 6; l_in = 659; l_out = 659; }
 
   const long long R = static_cast<long long>(n_win) * rpw;
   const long long plane = R + 2 * jg::kGuardRows;
-  std::vector<uint16_t> hx(static_cast<size_t>(cin / 8) * plane * 8, 0), hsc(static_cast<size_t>(cout / 8) * plane * 8, 0);
+  std::vector<uint16_t> hx(static_cast<size_t>(cin / 64) * plane * 64, 0), hsc(static_cast<size_t>(cout / 64) * plane * 64, 0);
   std::vector<uint8_t> hmask(R, 0), hscmask(R, 0);
   for (long long r = 0; r < R; ++r) {
     const int rw = static_cast<int>(r % rpw);
@@ -55,17 +57,18 @@ int main(int argc, char** argv) {
     hscmask[r] = in_frame_out && ((r % 89) != 7);
     if (in_frame_in)
       for (int c = 0; c < cin; ++c)
-        hx[(static_cast<size_t>(c >> 3) * plane + jg::kGuardRows + r) * 8 + (c & 7)] = f2bf(frand());
+        hx[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2bf(frand());
     if (hscmask[r])
       for (int c = 0; c < cout; ++c)
-        hsc[(static_cast<size_t>(c >> 3) * plane + jg::kGuardRows + r) * 8 + (c & 7)] = f2bf(frand());
+        hsc[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2bf(frand());
   }
   const int ktot = k * cin;
   std::vector<uint16_t> hw(static_cast<size_t>(ktot) * cout);
   const float wscale = 1.0f / sqrtf(static_cast<float>(ktot));
-  for (int kk = 0; kk < ktot; ++kk)
-    for (int co = 0; co < cout; ++co)
-      hw[(static_cast<size_t>(kk >> 3) * cout + co) * 8 + (kk & 7)] = f2bf(frand() * wscale * 1.7f);
+  for (int t = 0; t < k; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co)
+        hw[jg::w_index(t, ci, co, cin, cout)] = f2bf(frand() * wscale * 1.7f);
   std::vector<float> hpar(6 * cout);
   for (int c = 0; c < cout; ++c) {
     hpar[c] = 1.0f + 0.25f * frand();          // scale1
@@ -80,7 +83,7 @@ int main(int argc, char** argv) {
   uint8_t *dmask, *dscmask;
   float *dpar, *dtap_ref, *dtap_tc, *dpool_ref, *dpool_tc;
   int* derr;
-  const size_t ybytes = static_cast<size_t>(cout / 8) * plane * 16;
+  const size_t ybytes = static_cast<size_t>(cout / 64) * plane * 128;
   CK(cudaMalloc(&dx, hx.size() * 2)); CK(cudaMalloc(&dsc, hsc.size() * 2)); CK(cudaMalloc(&dw, hw.size() * 2));
   CK(cudaMalloc(&dy_ref, ybytes)); CK(cudaMalloc(&dy_tc, ybytes));
   CK(cudaMalloc(&dmask, R)); CK(cudaMalloc(&dscmask, R)); CK(cudaMalloc(&dpar, hpar.size() * 4));
@@ -100,8 +103,8 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dpool_tc, sentinel.data(), sentinel.size() * 4, cudaMemcpyHostToDevice));
 
   jg::ConvParams p{};
-  p.x = reinterpret_cast<const __nv_bfloat16*>(dx) + jg::kGuardRows * 8;
-  p.sc = (shape == 0) ? reinterpret_cast<const __nv_bfloat16*>(dsc) + jg::kGuardRows * 8 : nullptr;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(dx) + jg::kGuardRows * 64;
+  p.sc = (shape == 0) ? reinterpret_cast<const __nv_bfloat16*>(dsc) + jg::kGuardRows * 64 : nullptr;
   p.sc_mask = (shape == 0) ? dscmask : nullptr;
   p.sc_const = dpar + 5 * cout;
   p.out_mask = dmask;
@@ -119,20 +122,23 @@ int main(int argc, char** argv) {
   p.has_affine2 = (shape == 0);
   p.tap_mode = (shape == 0) ? 2 : (shape == 1 ? 1 : 0);
   p.pool_mode = (shape == 0) ? 1 : 0;
+  if (strip & 1) { p.tap_mode = 0; p.pool_mode = 0; }
+  if (strip & 2) { p.act1 = jg::ACT_NONE; p.act2 = jg::ACT_NONE; p.has_affine2 = 0; }
+  if (strip & 4) { p.sc = nullptr; p.sc_mask = nullptr; }
   p.err = derr;
-  jg::conv_fill_descriptors(p);
-  if (variant == 1) { unsigned t = p.a_lbo; p.a_lbo = p.a_sbo; p.a_sbo = t; t = p.b_lbo; p.b_lbo = p.b_sbo; p.b_sbo = t; }
+  (void)variant;
 
   int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
   printf("shape %d variant %d windows %d tiles %d sms %d stages %d\n", shape, variant, n_win, p.n_tiles, dev_sms, jg::conv_tc_stages(p));
 
   jg::ConvParams pr = p;
-  pr.y = reinterpret_cast<__nv_bfloat16*>(dy_ref) + jg::kGuardRows * 8; pr.tap_sum = dtap_ref; pr.pool = dpool_ref;
+  pr.y = reinterpret_cast<__nv_bfloat16*>(dy_ref) + jg::kGuardRows * 64; pr.tap_sum = dtap_ref; pr.pool = dpool_ref;
   CK(jg::launch_conv_ref(pr, 0));
   CK(cudaDeviceSynchronize());
 
   jg::ConvParams pt = p;
-  pt.y = reinterpret_cast<__nv_bfloat16*>(dy_tc) + jg::kGuardRows * 8; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
+  pt.y = reinterpret_cast<__nv_bfloat16*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
+  if (strip & 8) { pt.y = nullptr; }
   CK(jg::launch_conv_tc(pt, dev_sms, 0));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
@@ -167,6 +173,18 @@ int main(int argc, char** argv) {
   const bool ok = nbad == 0 && tapdiff <= 1e-3 * (1.0 + tapmax) * 4 && pooldiff < 0.05;
   printf("RESULT shape %d variant %d: %s\n", shape, variant, ok ? "MATCH" : "MISMATCH");
 
+  if (getenv("JG_TRACE")) {
+    long long* ddbg; CK(cudaMalloc(&ddbg, 64 * 8 * 8)); CK(cudaMemset(ddbg, 0, 64 * 8 * 8));
+    jg::ConvParams pd = pt; pd.dbg = ddbg;
+    for (int i = 0; i < 3; ++i) CK(jg::launch_conv_tc(pd, dev_sms, 0));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(64 * 8);
+    CK(cudaMemcpy(h.data(), ddbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    const long long t0 = h[0];
+    printf("trace (cycles rel. to first MMA start): it  mma_start mma_issued | epi_arrive_wait tfull_ready epi_done\n");
+    for (int i = 0; i < 16 && h[i * 8] != 0; ++i)
+      printf("  %2d  %8lld %8lld | %8lld %8lld %8lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0);
+  }
   if (iters > 0 && ok) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     // warm up for ~1.5 s so the SM clock has left its idle state before timing
@@ -184,8 +202,8 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     const double flops = 2.0 * static_cast<double>(R) * ktot * cout;
-    printf("TIMING shape %d windows %d: %.3f ms/launch, %.1f TFLOP/s (rows incl. gaps), %.1f us/tile-wave\n",
-           shape, n_win, ms, flops / ms * 1e-9, ms * 1e3 / ((p.n_tiles + dev_sms - 1) / dev_sms));
+    printf("TIMING strip %d shape %d windows %d: %.3f ms/launch, %.1f TFLOP/s (rows incl. gaps), %.1f us/tile-wave\n",
+           strip, shape, n_win, ms, flops / ms * 1e-9, ms * 1e3 / ((p.n_tiles + dev_sms - 1) / dev_sms));
   }
   return ok ? 0 : 1;
 }
