@@ -1,0 +1,162 @@
+/* jaeger_b200 -- C ABI of the B200-native `jaeger predict` hot path.
+ *
+ * Every entry point replaces one piece of the reference's Python/TensorFlow path
+ * (paths relative to /root/reference/src/jaeger):
+ *
+ *   jg_pack_bases        seqops/io.py:103-104 (.upper()) + encode.py:27-33 alphabet handling:
+ *                        ASCII contig bytes -> 2-bit codes + validity bitmap in HBM
+ *   jg_plan_windows      seqops/io.py:38-71 (_window_indices) + :112-145 (window loop,
+ *                        is_last flags, short whole-contig windows)         [host integer code]
+ *   jg_encode_windows    seqops/io.py:124-133 (G/C/A/T counts, gc_skew) +
+ *                        seqops/encode.py:229-302 (process_string_inference) and
+ *                        preprocess/v1/convert.py:75-99 (legacy process_string)
+ *   jg_model_create /    nnlib/inference.py:311-339 (InferModel signature call) = the graph of
+ *   jg_model_forward     nnlib/builder.py:844-894,982-1193 + nnlib/v2/layers.py (MaskedConv1D
+ *                        1217-1280, MaskedBatchNorm 918-941, ResidualBlock 1882-1915,
+ *                        MaskedGlobalMaxPooling 517-529, MaskedGlobalAvgPooling 460-480) +
+ *                        nnlib/v2/nmd.py:43-77 + dense heads builder.py:589-596,705-713
+ *   jg_aggregate_contigs postprocess/collect.py:293-403 (pred_to_dict per-contig reductions),
+ *                        postprocess/helpers.py:175-235 (entropy, energy, sigmoid)
+ *   jg_smooth_scores     postprocess/prophages.py:126-151 (softmax + width-4 box sum)
+ *   jg_segment_scores    postprocess/prophages.py:554-595 (KernelCPD/PELT at pen 1..9)
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, with a
+ * message retrievable through jg_last_error().  Pointers named d_* are DEVICE pointers (the
+ * Python host passes torch tensors' data_ptr()), h_* are host pointers.  All work is
+ * stream-ordered on the context's stream; nothing synchronises unless stated.  There is no
+ * CPU fallback: without a CUDA device jg_ctx_create fails.
+ */
+#ifndef JAEGER_B200_H_
+#define JAEGER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jg_ctx jg_ctx;
+typedef struct jg_model jg_model;
+
+const char* jg_last_error(void);
+int jg_version(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+int jg_ctx_create(int device, jg_ctx** out);
+int jg_ctx_destroy(jg_ctx* ctx);
+int jg_ctx_sync(jg_ctx* ctx);
+/* raw cudaStream_t of the context (so the host can bracket work with its own events) */
+void* jg_ctx_stream(jg_ctx* ctx);
+/* number of CUDA kernels this library has launched on the context since creation */
+int64_t jg_ctx_launch_count(jg_ctx* ctx);
+
+/* ---- stage 1: pack ---------------------------------------------------------------------
+ * d_ascii: n bases (contigs concatenated, no separators).  d_codes: ceil(n/16) uint32, base i
+ * in bits [2(i%16), 2(i%16)+2) with A=0 C=1 T=2 G=3 (complement = code ^ 2).  d_valid:
+ * ceil(n/32) uint32, bit set when the (case-folded) base is A/C/G/T.  Both outputs must be
+ * allocated with 2 extra zeroed words of slack. */
+int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_codes,
+                  uint32_t* d_valid);
+
+/* ---- stage 2a: window plan (host) -------------------------------------------------------
+ * For contig c of length len[c]: fixed stride windows range(0, len-(fsize-1), stride), or the
+ * dynamic-stride placement when enabled; contigs with min_len <= len < fsize yield one
+ * whole-contig window when `short_pass` is non-zero and are skipped otherwise; contigs longer
+ * than max_len (when max_len > 0) are skipped.  Call with out pointers NULL to get the count.
+ * Outputs (host, caller allocated, n_windows entries): contig index, window start,
+ * window length in bases, ordinal within contig, is_last flag. */
+int jg_plan_windows(const int64_t* h_len, int64_t n_contigs, int32_t fsize, int32_t stride,
+                    int32_t dynamic_stride, double dynamic_stride_threshold, int32_t min_len,
+                    int64_t max_len, int32_t short_pass, int64_t* n_windows,
+                    int32_t* h_contig, int64_t* h_start, int32_t* h_nbases, int32_t* h_ordinal,
+                    uint8_t* h_is_last);
+
+/* ---- stage 2b: encode ------------------------------------------------------------------
+ * d_win_base[w]: absolute base offset of window w in the packed arrays; d_win_nbases[w]: its
+ * length (<= crop).  d_soft: optional soft-mask bitmap (same layout as d_valid) or NULL.
+ * lut64: token of codon (b0*16 + b1*4 + b2) in the A0 C1 T2 G3 code; unknown codons -> 0.
+ * case_sensitive != 0 makes soft-masked bases unknown for the tokens (reference masking=True
+ * and the legacy encoder); counts always ignore soft-masked bases.
+ * Outputs: d_tokens [n][6][pitch] uint8 (pitch >= lc, multiple of 4; zero padded), d_counts [n][4] int32 in G,C,A,T order
+ * (meta_5..meta_8), d_skew100 [n] int16 = gc_skew*100 with Python round() semantics, bit 14
+ * set when the value is a negative zero ("-0.000"). */
+int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid,
+                      const uint32_t* d_soft, const int64_t* d_win_base,
+                      const int32_t* d_win_nbases, int64_t n_windows, int32_t crop, int32_t lc,
+                      int32_t pitch, const uint8_t* h_lut64, int32_t case_sensitive, uint8_t* d_tokens,
+                      int32_t* d_counts, int16_t* d_skew100);
+
+/* ---- stage 3: model ---------------------------------------------------------------------
+ * The plan is a flat int32/float32 description compiled by the host from project.yaml; see
+ * jaeger_b200/plan.py for the field layout (JG_PLAN_* below).  Weights are fp32 host arrays in
+ * TensorFlow layout ([k, Cin, Cout] conv kernels, [in, out] dense kernels). */
+#define JG_LAYER_INT_FIELDS 24
+#define JG_LAYER_PTR_FIELDS 12
+typedef struct jg_layer_desc {
+  int32_t i[JG_LAYER_INT_FIELDS];
+  const float* p[JG_LAYER_PTR_FIELDS];
+} jg_layer_desc;
+
+typedef struct jg_head_desc {
+  int32_t n_classes;        /* classifier units */
+  int32_t feat_dim;         /* pooled feature width */
+  int32_t pool_mode;        /* 1 max, 2 average */
+  int32_t n_taps;           /* NMD taps (0 = no reliability head) */
+  int32_t rel_hidden;       /* units of the reliability hidden dense (gelu) */
+  int32_t reserved[3];
+  const float* cls_w;       /* [feat_dim][n_classes] */
+  const float* cls_b;       /* [n_classes] */
+  const float* rel_w1;      /* [sum tap widths][rel_hidden] */
+  const float* rel_b1;      /* [rel_hidden] */
+  const float* rel_w2;      /* [rel_hidden][1] */
+  const float* rel_b2;      /* [1] */
+} jg_head_desc;
+
+int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers,
+                    const jg_head_desc* head, int32_t frames, int32_t vocab, jg_model** out);
+int jg_model_destroy(jg_model* m);
+/* Largest number of windows one jg_model_forward call may take for a given lc with the
+ * workspace budget (bytes) -- the host chunks its window stream with it. */
+int64_t jg_model_max_windows(jg_model* m, int32_t lc, int64_t workspace_bytes);
+/* d_tokens [n][6][pitch] uint8; d_lpad [n] int32 = padded frame length of each window (lc for the
+ * long pass; the batch maximum for the reference's padded short pass).  Outputs (device,
+ * fp32): d_logits [n][n_classes]; optional d_rel [n], d_emb [n][feat_dim], d_nmd [n][sum taps]
+ * (NULL to skip).  use_ref != 0 routes the convolutions through the CUDA-core check kernels
+ * (tests only). */
+int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const int32_t* d_lpad,
+                     int64_t n_windows, int32_t lc, int32_t pitch, float* d_logits, float* d_rel,
+                     float* d_emb, float* d_nmd, int32_t use_ref);
+/* bytes of device workspace currently held by the model */
+int64_t jg_model_workspace_bytes(jg_model* m);
+/* useful FLOPs of one window at frame length lc (2*L_out*6*k*Cin*Cout summed over convs) */
+double jg_model_flops_per_window(jg_model* m, int32_t lc);
+
+/* ---- stage 4: per-contig aggregation ------------------------------------------------------
+ * Windows of contig c are rows [d_offsets[c], d_offsets[c+1]) of d_logits [W][n_cls].
+ * Outputs per contig: mean/var as IEEE half bits (sequential fp32 accumulation then fp16
+ * rounding, the arithmetic of np.mean / np.var on a float32 [T, C] array), consensus =
+ * first-max argmax of the half means, per-class window counts of the per-window argmax,
+ * entropy / energy means (half bits), fraction of windows with sigmoid(rel) > 0.5 (fp32;
+ * NaN when d_rel is NULL), per-window argmax. */
+int jg_aggregate_contigs(jg_ctx* ctx, const float* d_logits, const float* d_rel,
+                         const int64_t* d_offsets, int64_t n_contigs, int32_t n_cls,
+                         uint16_t* d_mean_h, uint16_t* d_var_h, int32_t* d_consensus,
+                         int32_t* d_counts, uint16_t* d_entropy_h, uint16_t* d_energy_h,
+                         float* d_rel_frac, int32_t* d_frag_pred);
+
+/* ---- stage 4b: prophage score smoothing + segmentation -------------------------------------
+ * jg_smooth_scores: row softmax of logits (float64), then per class the width-`box` box SUM with
+ * numpy.convolve(mode="same") alignment, per contig segment.  d_out [W][n_cls] float64. */
+int jg_smooth_scores(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets,
+                     int64_t n_contigs, int32_t n_cls, int32_t box, double* d_out);
+/* jg_segment_scores: for one signal of n points, optimal partitioning with the L2 segment
+ * cost, minimum segment length min_size and penalties pen = 1..n_pen (what
+ * ruptures.KernelCPD(kernel="linear", min_size, jump=1).predict(pen=) minimises).
+ * d_bkps [n_pen][n] int32: ascending segment ends for each penalty (last = n), d_nbkps [n_pen]. */
+int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size,
+                      int32_t n_pen, int32_t* d_bkps, int32_t* d_nbkps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAEGER_B200_H_ */

@@ -1,0 +1,588 @@
+// C-ABI implementation of the B200-native `jaeger predict` hot path (see include/jaeger_b200.h).
+#include "../../include/jaeger_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "conv_launch.cuh"
+#include "model_kernels.cuh"
+#include "post_kernels.cuh"
+#include "seq_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+#define JG_CUDA(x)                                          \
+  do {                                                      \
+    cudaError_t e_ = (x);                                   \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x);        \
+  } while (0)
+
+inline int grid_for(long long n, int block, int num_sms, int per_sm = 8) {
+  long long g = (n + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms) * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FC0;  // NaN
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+struct jg_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+};
+
+// layer descriptor integer fields (mirrored in jaeger_b200/plan.py)
+enum LayerField {
+  LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
+  LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
+  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN
+};
+enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN };
+
+struct Layer {
+  int32_t f[JG_LAYER_INT_FIELDS];
+  __nv_bfloat16* w = nullptr;
+  float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const  (6 x cout)
+  int* shifts = nullptr;  // device copy for the mask kernel
+  int shifts_h[jg::kMaxTaps];
+  int halo_l = 0, halo_r = 0;
+};
+
+struct jg_model {
+  jg_ctx* ctx = nullptr;
+  std::vector<Layer> layers;
+  int frames = 6, vocab = 65;
+  int n_bufs = 0, n_masks = 0, n_taps = 0, tap_width = 0;
+  std::vector<int> buf_channels;
+  jg_head_desc head{};
+  float *cls_w = nullptr, *cls_b = nullptr, *rel_w1 = nullptr, *rel_b1 = nullptr, *rel_w2 = nullptr,
+        *rel_b2 = nullptr, *tap_mean = nullptr;
+  int final_mask = 0;
+  std::vector<int> tap_mask_slot;
+  // workspace -------------------------------------------------------------------------------
+  long long cap_rows = 0, cap_windows = 0;
+  std::vector<__nv_bfloat16*> bufs;
+  std::vector<uint8_t*> masks;
+  int* counts = nullptr;        // [n_masks][cap_windows]
+  float* tap_sum = nullptr;     // [n_taps][cap_windows][tap_width]
+  float* pool = nullptr;        // [cap_windows][feat]
+  const int** tap_count_ptrs = nullptr;
+  int* err = nullptr;
+  int64_t ws_bytes = 0;
+};
+
+namespace {
+
+void model_geometry(const jg_model* m, int lc, int* period, int* rpw) {
+  int p = lc;
+  for (const Layer& L : m->layers) {
+    const int l_in = lc - L.f[LF_CUM_SHRINK_IN];
+    const int halo = L.halo_l > L.halo_r ? L.halo_l : L.halo_r;
+    const int need = l_in + (L.f[LF_SHRINK] == 0 ? halo : 0);
+    if (need > p) p = need;
+  }
+  *period = p;
+  *rpw = (m->frames * p + jg::kTileM - 1) / jg::kTileM * jg::kTileM;
+}
+
+long long bytes_per_window(const jg_model* m, int rpw) {
+  long long b = 0;
+  for (int c : m->buf_channels) b += static_cast<long long>(rpw) * c * 2;
+  b += static_cast<long long>(m->n_masks) * rpw;
+  b += static_cast<long long>(m->n_masks) * 4 + static_cast<long long>(m->n_taps) * m->tap_width * 4 +
+       static_cast<long long>(m->head.feat_dim) * 4;
+  return b;
+}
+
+void free_workspace(jg_model* m) {
+  for (auto p : m->bufs) cudaFree(p);
+  for (auto p : m->masks) cudaFree(p);
+  m->bufs.clear();
+  m->masks.clear();
+  cudaFree(m->counts); m->counts = nullptr;
+  cudaFree(m->tap_sum); m->tap_sum = nullptr;
+  cudaFree(m->pool); m->pool = nullptr;
+  cudaFree(m->tap_count_ptrs); m->tap_count_ptrs = nullptr;
+  m->cap_rows = m->cap_windows = 0;
+  m->ws_bytes = 0;
+}
+
+int ensure_workspace(jg_model* m, long long n_windows, long long rows) {
+  if (rows <= m->cap_rows && n_windows <= m->cap_windows) return 0;
+  free_workspace(m);
+  const long long plane = rows + 2 * jg::kGuardRows;
+  int64_t total = 0;
+  for (int c : m->buf_channels) {
+    __nv_bfloat16* p = nullptr;
+    const size_t bytes = static_cast<size_t>(c / 64) * plane * 128;
+    JG_CUDA(cudaMalloc(&p, bytes));
+    JG_CUDA(cudaMemsetAsync(p, 0, bytes, m->ctx->stream));
+    m->bufs.push_back(p);
+    total += bytes;
+  }
+  for (int i = 0; i < m->n_masks; ++i) {
+    uint8_t* p = nullptr;
+    JG_CUDA(cudaMalloc(&p, plane));
+    JG_CUDA(cudaMemsetAsync(p, 0, plane, m->ctx->stream));
+    m->masks.push_back(p);
+    total += plane;
+  }
+  JG_CUDA(cudaMalloc(&m->counts, static_cast<size_t>(m->n_masks) * n_windows * 4));
+  const size_t tap_bytes = static_cast<size_t>(m->n_taps > 0 ? m->n_taps : 1) * n_windows * (m->tap_width > 0 ? m->tap_width : 1) * 4;
+  JG_CUDA(cudaMalloc(&m->tap_sum, tap_bytes));
+  JG_CUDA(cudaMalloc(&m->pool, static_cast<size_t>(n_windows) * m->head.feat_dim * 4));
+  JG_CUDA(cudaMalloc(&m->tap_count_ptrs, sizeof(int*) * (m->n_taps > 0 ? m->n_taps : 1)));
+  std::vector<const int*> ptrs(m->n_taps > 0 ? m->n_taps : 1, nullptr);
+  for (int t = 0; t < m->n_taps; ++t) ptrs[t] = m->counts + static_cast<long long>(m->tap_mask_slot[t]) * n_windows;
+  JG_CUDA(cudaMemcpyAsync(m->tap_count_ptrs, ptrs.data(), sizeof(int*) * ptrs.size(), cudaMemcpyHostToDevice, m->ctx->stream));
+  JG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  total += static_cast<int64_t>(m->n_masks) * n_windows * 4 + tap_bytes + static_cast<int64_t>(n_windows) * m->head.feat_dim * 4;
+  m->cap_rows = rows;
+  m->cap_windows = n_windows;
+  m->ws_bytes = total;
+  return 0;
+}
+
+int upload_f32(const float* h, size_t n, float** d) {
+  JG_CUDA(cudaMalloc(d, n * 4));
+  JG_CUDA(cudaMemcpy(*d, h, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jg_last_error(void) { return g_err.c_str(); }
+int jg_version(void) { return 1; }
+
+int jg_ctx_create(int device, jg_ctx** out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail("no CUDA device: the jaeger_b200 hot path has no CPU fallback");
+  if (device < 0 || device >= n) return fail("invalid device index");
+  JG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  JG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(std::string("jaeger_b200 is built for sm_100a only; found ") + prop.name);
+  jg_ctx* c = new jg_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  JG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+int jg_ctx_destroy(jg_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+int jg_ctx_sync(jg_ctx* ctx) {
+  JG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void* jg_ctx_stream(jg_ctx* ctx) { return ctx->stream; }
+int64_t jg_ctx_launch_count(jg_ctx* ctx) { return ctx->launches; }
+
+// ---- stage 1 -----------------------------------------------------------------------------------
+int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_codes, uint32_t* d_valid) {
+  if (n <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  const long long groups = (n + 31) / 32;
+  jg::pack_bases_kernel<<<grid_for(groups, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(d_ascii, n, d_codes, d_valid);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- stage 2a ----------------------------------------------------------------------------------
+int jg_plan_windows(const int64_t* h_len, int64_t n_contigs, int32_t fsize, int32_t stride,
+                    int32_t dynamic_stride, double dynamic_stride_threshold, int32_t min_len,
+                    int64_t max_len, int32_t short_pass, int64_t* n_windows, int32_t* h_contig,
+                    int64_t* h_start, int32_t* h_nbases, int32_t* h_ordinal, uint8_t* h_is_last) {
+  if (fsize <= 0 || stride <= 0) return fail("fsize and stride must be positive");
+  int64_t n = 0;
+  const bool write = h_contig != nullptr;
+  std::vector<int64_t> idx;
+  for (int64_t c = 0; c < n_contigs; ++c) {
+    const int64_t len = h_len[c];
+    if (max_len > 0 && len > max_len) continue;
+    idx.clear();
+    int32_t nb = fsize;
+    if (len >= fsize) {
+      if (!dynamic_stride || static_cast<double>(len) >= dynamic_stride_threshold * fsize) {
+        for (int64_t s = 0; s < len - (fsize - 1); s += stride) idx.push_back(s);
+      } else {
+        // seqops/io.py:56-71
+        int64_t nw = static_cast<int64_t>(std::ceil(static_cast<double>(len) / static_cast<double>(fsize)));
+        if (nw < 1) nw = 1;
+        if (nw == 1) {
+          idx.push_back(0);
+        } else {
+          const double raw = static_cast<double>(len - fsize) / static_cast<double>(nw - 1);
+          std::vector<int64_t> tmp(nw);
+          for (int64_t i = 0; i < nw; ++i) tmp[i] = static_cast<int64_t>(std::nearbyint(static_cast<double>(i) * raw));
+          tmp[nw - 1] = len - fsize;
+          std::unordered_set<int64_t> seen;
+          for (int64_t v : tmp)
+            if (seen.insert(v).second) idx.push_back(v);
+        }
+      }
+    } else if (len >= min_len && short_pass) {
+      idx.push_back(0);
+      nb = static_cast<int32_t>(len);
+    }
+    for (size_t i = 0; i < idx.size(); ++i) {
+      if (write) {
+        h_contig[n] = static_cast<int32_t>(c);
+        h_start[n] = idx[i];
+        h_nbases[n] = nb;
+        h_ordinal[n] = static_cast<int32_t>(i);
+        h_is_last[n] = (i + 1 == idx.size());
+      }
+      ++n;
+    }
+  }
+  *n_windows = n;
+  return 0;
+}
+
+// ---- stage 2b ----------------------------------------------------------------------------------
+int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid, const uint32_t* d_soft,
+                      const int64_t* d_win_base, const int32_t* d_win_nbases, int64_t n_windows,
+                      int32_t crop, int32_t lc, int32_t pitch, const uint8_t* h_lut64,
+                      int32_t case_sensitive, uint8_t* d_tokens, int32_t* d_counts, int16_t* d_skew100) {
+  if (n_windows <= 0) return 0;
+  if (pitch % 4 != 0 || pitch < lc) return fail("token pitch must be a multiple of 4 and >= lc");
+  JG_CUDA(cudaSetDevice(ctx->device));
+  uint8_t* d_lut = nullptr;
+  JG_CUDA(cudaMallocAsync(&d_lut, 64, ctx->stream));
+  JG_CUDA(cudaMemcpyAsync(d_lut, h_lut64, 64, cudaMemcpyHostToDevice, ctx->stream));
+  const int words_c = (crop + 15) / 16 + 1, words_b = (crop + 31) / 32 + 1;
+  const size_t smem = static_cast<size_t>(words_c + 2 * words_b) * 4;
+  long long grid = n_windows;
+  const long long cap = static_cast<long long>(ctx->num_sms) * 16;
+  if (grid > cap) grid = cap;
+  jg::encode_windows_kernel<<<static_cast<int>(grid), jg::kEncThreads, smem, ctx->stream>>>(
+      d_codes, d_valid, d_soft, reinterpret_cast<const long long*>(d_win_base), d_win_nbases, n_windows, crop,
+      lc, pitch, d_lut, case_sensitive, d_tokens, d_counts, d_skew100);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+  JG_CUDA(cudaFreeAsync(d_lut, ctx->stream));
+  return 0;
+}
+
+// ---- stage 3 -----------------------------------------------------------------------------------
+int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, const jg_head_desc* head,
+                    int32_t frames, int32_t vocab, jg_model** out) {
+  JG_CUDA(cudaSetDevice(ctx->device));
+  jg_model* m = new jg_model();
+  m->ctx = ctx;
+  m->frames = frames;
+  m->vocab = vocab;
+  m->head = *head;
+  int max_buf = -1, max_mask = -1, max_tap = -1;
+  for (int l = 0; l < n_layers; ++l) {
+    Layer L;
+    std::memcpy(L.f, layers[l].i, sizeof(L.f));
+    const int cin = L.f[LF_CIN], cout = L.f[LF_COUT], k = L.f[LF_K];
+    if (L.f[LF_KIND] != 1) { delete m; return fail("unknown layer kind in plan"); }
+    if (cin % 64 != 0 || cout % 64 != 0 || cout > 256 || k > jg::kMaxTaps) {
+      delete m;
+      return fail("conv layer outside the tensor-core kernel's envelope (Cin, Cout multiples of 64, Cout <= 256, k <= 16)");
+    }
+    int mn = 0, mx = 0;
+    for (int t = 0; t < k; ++t) {
+      L.shifts_h[t] = t * L.f[LF_DIL] - L.f[LF_PAD_LEFT];
+      mn = L.shifts_h[t] < mn ? L.shifts_h[t] : mn;
+      mx = L.shifts_h[t] > mx ? L.shifts_h[t] : mx;
+    }
+    L.halo_l = -mn;
+    L.halo_r = mx;
+    if (L.halo_l > jg::kGuardRows - 8 || L.halo_r > jg::kGuardRows - 8) { delete m; return fail("conv halo exceeds guard rows"); }
+    // weights: TF layout [k][cin][cout] fp32 -> swizzled bf16 shared-memory image
+    std::vector<uint16_t> img(static_cast<size_t>(k) * cin * cout);
+    const float* wk = layers[l].p[LP_KERNEL];
+    for (int t = 0; t < k; ++t)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          img[jg::w_index(t, ci, co, cin, cout)] = f32_to_bf16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
+    JG_CUDA(cudaMalloc(&L.w, img.size() * 2));
+    JG_CUDA(cudaMemcpy(L.w, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<float> par(6 * static_cast<size_t>(cout), 0.0f);
+    const int order[6] = {LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST};
+    for (int a = 0; a < 6; ++a) {
+      const float* src = layers[l].p[order[a]];
+      for (int c = 0; c < cout; ++c) par[a * cout + c] = src ? src[c] : ((order[a] == LP_SCALE1 || order[a] == LP_SCALE2) ? 1.0f : 0.0f);
+    }
+    if (upload_f32(par.data(), par.size(), &L.par)) { delete m; return 2; }
+    JG_CUDA(cudaMalloc(&L.shifts, sizeof(int) * jg::kMaxTaps));
+    JG_CUDA(cudaMemcpy(L.shifts, L.shifts_h, sizeof(int) * k, cudaMemcpyHostToDevice));
+    for (int b : {L.f[LF_IN_BUF], L.f[LF_OUT_BUF], L.f[LF_SC_BUF]}) max_buf = b > max_buf ? b : max_buf;
+    for (int s : {L.f[LF_MASK_IN], L.f[LF_MASK_OUT], L.f[LF_SC_MASK]}) max_mask = s > max_mask ? s : max_mask;
+    if (L.f[LF_TAP_MODE] != 0) max_tap = L.f[LF_TAP_SLOT] > max_tap ? L.f[LF_TAP_SLOT] : max_tap;
+    m->layers.push_back(L);
+  }
+  m->n_bufs = max_buf + 1;
+  m->n_masks = max_mask + 1;
+  m->n_taps = max_tap + 1;
+  if (m->n_taps != head->n_taps) { delete m; return fail("head n_taps does not match the taps in the layer plan"); }
+  m->buf_channels.assign(m->n_bufs, 64);
+  m->tap_mask_slot.assign(m->n_taps > 0 ? m->n_taps : 1, 0);
+  for (const Layer& L : m->layers) {
+    int& ci = m->buf_channels[L.f[LF_IN_BUF]];
+    ci = L.f[LF_CIN] > ci ? L.f[LF_CIN] : ci;
+    if (L.f[LF_OUT_BUF] >= 0) { int& co = m->buf_channels[L.f[LF_OUT_BUF]]; co = L.f[LF_COUT] > co ? L.f[LF_COUT] : co; }
+    if (L.f[LF_TAP_MODE] != 0) {
+      m->tap_mask_slot[L.f[LF_TAP_SLOT]] = L.f[LF_MASK_OUT];
+      if (m->tap_width != 0 && m->tap_width != L.f[LF_COUT]) { delete m; return fail("NMD taps of different widths are not supported"); }
+      m->tap_width = L.f[LF_COUT];
+    }
+    if (L.f[LF_POOL_MODE] != 0) m->final_mask = L.f[LF_MASK_OUT];
+  }
+  // heads
+  const int feat = head->feat_dim, ncls = head->n_classes;
+  if (upload_f32(head->cls_w, static_cast<size_t>(feat) * ncls, &m->cls_w)) return 2;
+  if (upload_f32(head->cls_b, ncls, &m->cls_b)) return 2;
+  if (m->n_taps > 0) {
+    const int nmd_dim = m->n_taps * m->tap_width;
+    std::vector<float> means(static_cast<size_t>(nmd_dim), 0.0f);
+    for (int l = 0; l < n_layers; ++l)
+      if (layers[l].i[LF_TAP_MODE] != 0 && layers[l].p[LP_TAP_MEAN])
+        std::memcpy(means.data() + static_cast<size_t>(layers[l].i[LF_TAP_SLOT]) * m->tap_width, layers[l].p[LP_TAP_MEAN], m->tap_width * 4);
+    if (upload_f32(means.data(), means.size(), &m->tap_mean)) return 2;
+    if (head->rel_w1) {
+      if (upload_f32(head->rel_w1, static_cast<size_t>(nmd_dim) * head->rel_hidden, &m->rel_w1)) return 2;
+      if (upload_f32(head->rel_b1, head->rel_hidden, &m->rel_b1)) return 2;
+      if (upload_f32(head->rel_w2, head->rel_hidden, &m->rel_w2)) return 2;
+      if (upload_f32(head->rel_b2, 1, &m->rel_b2)) return 2;
+    }
+  }
+  JG_CUDA(cudaMalloc(&m->err, 4));
+  JG_CUDA(cudaMemset(m->err, 0, 4));
+  *out = m;
+  return 0;
+}
+
+int jg_model_destroy(jg_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->ctx->device);
+  free_workspace(m);
+  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.par); cudaFree(L.shifts); }
+  for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean}) cudaFree(p);
+  cudaFree(m->err);
+  delete m;
+  return 0;
+}
+
+int64_t jg_model_max_windows(jg_model* m, int32_t lc, int64_t workspace_bytes) {
+  int period, rpw;
+  model_geometry(m, lc, &period, &rpw);
+  const long long per = bytes_per_window(m, rpw);
+  return per > 0 ? workspace_bytes / per : 0;
+}
+int64_t jg_model_workspace_bytes(jg_model* m) { return m->ws_bytes; }
+
+double jg_model_flops_per_window(jg_model* m, int32_t lc) {
+  double f = 0.0;
+  for (const Layer& L : m->layers) {
+    const int l_out = lc - L.f[LF_CUM_SHRINK_IN] - L.f[LF_SHRINK];
+    f += 2.0 * m->frames * l_out * L.f[LF_K] * static_cast<double>(L.f[LF_CIN]) * L.f[LF_COUT];
+  }
+  return f;
+}
+
+int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const int32_t* d_lpad, int64_t n_windows,
+                     int32_t lc, int32_t pitch, float* d_logits, float* d_rel, float* d_emb, float* d_nmd,
+                     int32_t use_ref) {
+  if (n_windows <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  int period, rpw;
+  model_geometry(m, lc, &period, &rpw);
+  const long long rows = n_windows * rpw;
+  if (rows / jg::kTileM > 0x7FFFFFFFLL) return fail("too many windows in one forward call");
+  if (ensure_workspace(m, n_windows, rows)) return 2;
+  cudaStream_t st = ctx->stream;
+  const long long plane = m->cap_rows + 2 * jg::kGuardRows;
+  const jg::RowGeom geom{rpw, period, m->frames};
+  // rows [rows, rows + guard) may hold stale data of an earlier, larger call
+  if (rows < m->cap_rows) {
+    for (int b = 0; b < m->n_bufs; ++b)
+      for (int g = 0; g < m->buf_channels[b] / 64; ++g)
+        JG_CUDA(cudaMemsetAsync(m->bufs[b] + (static_cast<long long>(g) * plane + jg::kGuardRows + rows) * 64, 0, jg::kGuardRows * 128, st));
+    for (int s = 0; s < m->n_masks; ++s) JG_CUDA(cudaMemsetAsync(m->masks[s] + jg::kGuardRows + rows, 0, jg::kGuardRows, st));
+  }
+  JG_CUDA(cudaMemsetAsync(m->counts, 0, static_cast<size_t>(m->n_masks) * m->cap_windows * 4, st));
+  if (m->n_taps > 0) JG_CUDA(cudaMemsetAsync(m->tap_sum, 0, static_cast<size_t>(m->n_taps) * n_windows * m->tap_width * 4, st));
+  const long long pool_n = n_windows * m->head.feat_dim;
+  jg::fill_f32_kernel<<<grid_for(pool_n, 256, ctx->num_sms), 256, 0, st>>>(m->pool, pool_n, m->head.pool_mode == 1 ? -1.0e9f : 0.0f);
+  ctx->launches++;
+
+  auto buf_row0 = [&](int b) { return m->bufs[b] + static_cast<long long>(jg::kGuardRows) * 64; };
+  auto mask_row0 = [&](int s) { return m->masks[s] + jg::kGuardRows; };
+
+  // stem operand: one-hot rows + token mask
+  jg::expand_tokens_kernel<<<grid_for(rows * 8, 256, ctx->num_sms, 16), 256, 0, st>>>(
+      d_tokens, d_lpad, rows, lc, pitch, geom, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
+      m->counts + static_cast<long long>(m->layers[0].f[LF_MASK_IN]) * m->cap_windows);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+
+  for (Layer& L : m->layers) {
+    const int cout = L.f[LF_COUT];
+    jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
+        mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN] + L.f[LF_SHRINK], L.f[LF_K], L.shifts,
+        L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
+    ctx->launches++;
+    jg::ConvParams p{};
+    p.x = buf_row0(L.f[LF_IN_BUF]);
+    p.y = L.f[LF_OUT_BUF] >= 0 ? buf_row0(L.f[LF_OUT_BUF]) : nullptr;
+    p.sc = L.f[LF_SC_BUF] >= 0 ? buf_row0(L.f[LF_SC_BUF]) : nullptr;
+    p.sc_mask = (L.f[LF_SC_BUF] >= 0 && L.f[LF_SC_MASK] >= 0) ? mask_row0(L.f[LF_SC_MASK]) : nullptr;
+    p.out_mask = mask_row0(L.f[LF_MASK_OUT]);
+    p.w = L.w;
+    p.bias = L.par;
+    p.scale1 = L.par + cout;
+    p.shift1 = L.par + 2 * cout;
+    p.scale2 = L.par + 3 * cout;
+    p.shift2 = L.par + 4 * cout;
+    p.sc_const = L.par + 5 * cout;
+    p.tap_sum = L.f[LF_TAP_MODE] != 0 ? m->tap_sum + static_cast<long long>(L.f[LF_TAP_SLOT]) * n_windows * m->tap_width : nullptr;
+    p.pool = L.f[LF_POOL_MODE] != 0 ? m->pool : nullptr;
+    p.x_plane = plane;
+    p.y_plane = plane;
+    p.n_tiles = static_cast<int>(rows / jg::kTileM);
+    p.rows_per_window = rpw;
+    p.cin = L.f[LF_CIN];
+    p.cout = cout;
+    p.ntaps = L.f[LF_K];
+    for (int t = 0; t < L.f[LF_K]; ++t) p.shifts[t] = L.shifts_h[t];
+    p.halo_l = L.halo_l;
+    p.halo_r = L.halo_r;
+    p.act1 = L.f[LF_ACT1];
+    p.act2 = L.f[LF_ACT2];
+    p.has_affine2 = L.f[LF_HAS_AFF2];
+    p.tap_mode = L.f[LF_TAP_MODE];
+    p.pool_mode = L.f[LF_POOL_MODE];
+    p.err = m->err;
+    p.dbg = nullptr;
+    cudaError_t e = use_ref ? jg::launch_conv_ref(p, st) : jg::launch_conv_tc(p, ctx->num_sms, st);
+    ctx->launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+  }
+
+  jg::HeadParams hp{};
+  hp.pool = m->pool;
+  hp.pool_count = m->counts + static_cast<long long>(m->final_mask) * m->cap_windows;
+  hp.tap_sum = m->tap_sum;
+  hp.tap_count = m->tap_count_ptrs;
+  hp.tap_mean = m->tap_mean;
+  hp.cls_w = m->cls_w; hp.cls_b = m->cls_b;
+  hp.rel_w1 = m->rel_w1; hp.rel_b1 = m->rel_b1; hp.rel_w2 = m->rel_w2; hp.rel_b2 = m->rel_b2;
+  hp.logits = d_logits;
+  hp.rel = m->rel_w1 ? d_rel : nullptr;
+  hp.emb = d_emb;
+  hp.nmd = d_nmd;
+  hp.n_windows = static_cast<int>(n_windows);
+  hp.feat = m->head.feat_dim;
+  hp.n_classes = m->head.n_classes;
+  hp.pool_mode = m->head.pool_mode;
+  hp.n_taps = m->n_taps;
+  hp.tap_width = m->tap_width;
+  hp.rel_hidden = m->head.rel_hidden;
+  hp.masking = m->layers.back().f[LF_MASKING];
+  const int warps = 4;
+  const size_t smem = static_cast<size_t>(warps) * (hp.feat + hp.n_taps * hp.tap_width) * 4;
+  jg::heads_kernel<<<grid_for(n_windows, warps, ctx->num_sms, 16), warps * 32, smem, st>>>(hp);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- stage 4 -----------------------------------------------------------------------------------
+int jg_aggregate_contigs(jg_ctx* ctx, const float* d_logits, const float* d_rel, const int64_t* d_offsets,
+                         int64_t n_contigs, int32_t n_cls, uint16_t* d_mean_h, uint16_t* d_var_h,
+                         int32_t* d_consensus, int32_t* d_counts, uint16_t* d_entropy_h, uint16_t* d_energy_h,
+                         float* d_rel_frac, int32_t* d_frag_pred) {
+  if (n_contigs <= 0) return 0;
+  if (n_cls < 1 || n_cls > 32) return fail("n_cls must be in [1, 32]");
+  JG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  long long n_windows = 0;
+  JG_CUDA(cudaMemcpyAsync(&n_windows, d_offsets + n_contigs, 8, cudaMemcpyDeviceToHost, st));
+  JG_CUDA(cudaStreamSynchronize(st));
+  if (n_windows <= 0) return 0;
+  float* ent = nullptr;
+  double* en = nullptr;
+  JG_CUDA(cudaMallocAsync(&ent, n_windows * 4, st));
+  JG_CUDA(cudaMallocAsync(&en, n_windows * 8, st));
+  const long long* off = reinterpret_cast<const long long*>(d_offsets);
+  jg::window_scalars_kernel<<<grid_for(n_windows, 256, ctx->num_sms), 256, 0, st>>>(d_logits, n_windows, n_cls, d_frag_pred, ent, en);
+  jg::contig_moments_kernel<<<grid_for(n_contigs * n_cls, 128, ctx->num_sms, 16), 128, 0, st>>>(
+      d_logits, off, n_contigs, n_cls, reinterpret_cast<__half*>(d_mean_h), reinterpret_cast<__half*>(d_var_h));
+  jg::contig_summary_kernel<<<grid_for(n_contigs * 32, 256, ctx->num_sms, 16), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(d_mean_h), d_frag_pred, ent, en, d_rel, off, n_contigs, n_cls, d_consensus, d_counts,
+      reinterpret_cast<__half*>(d_entropy_h), reinterpret_cast<__half*>(d_energy_h), d_rel_frac);
+  ctx->launches += 3;
+  JG_CUDA(cudaGetLastError());
+  JG_CUDA(cudaFreeAsync(ent, st));
+  JG_CUDA(cudaFreeAsync(en, st));
+  return 0;
+}
+
+int jg_smooth_scores(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int64_t n_contigs,
+                     int32_t n_cls, int32_t box, double* d_out) {
+  if (n_contigs <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  dim3 grid(ctx->num_sms, static_cast<unsigned>(n_contigs < 64 ? n_contigs : 64));
+  jg::smooth_scores_kernel<<<grid, 128, 0, ctx->stream>>>(d_logits, reinterpret_cast<const long long*>(d_offsets), n_contigs, n_cls, box, d_out);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size, int32_t n_pen,
+                      int32_t* d_bkps, int32_t* d_nbkps) {
+  if (n <= 0 || n_pen <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  double* work = nullptr;
+  const size_t doubles = 2ull * (n + 1) + static_cast<size_t>(n_pen) * (n + 1);
+  const size_t bytes = doubles * 8 + static_cast<size_t>(n_pen) * (n + 1) * 4 + 16;
+  JG_CUDA(cudaMallocAsync(&work, bytes, st));
+  jg::prefix_sums_kernel<<<1, 32, 0, st>>>(d_signal, n, work);
+  jg::segment_scores_kernel<<<n_pen, 256, 32 * 8 + 32 * 4, st>>>(d_signal, n, min_size, n_pen, work, d_bkps, d_nbkps);
+  ctx->launches += 2;
+  JG_CUDA(cudaGetLastError());
+  JG_CUDA(cudaFreeAsync(work, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// Stage 4: per-contig aggregation of window logits, score smoothing and change-point
+// segmentation.  Reference: postprocess/collect.py:293-403, postprocess/helpers.py:175-235,
+// postprocess/prophages.py:126-151, 554-595 (paths relative to /root/reference/src/jaeger).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jg {
+
+// ---- per-window scalars: argmax, entropy term, energy term --------------------------------
+// entropy: helpers.py:175-177 applies -sum(p*log2 p) to the CLIPPED RAW LOGITS (not a softmax).
+// energy : helpers.py:189-219 -- for n_cls != 2 the code falls into its "binary" branch, i.e.
+//          -log(exp(z)+1) per element (float64), later averaged over windows AND classes.
+__global__ void window_scalars_kernel(const float* __restrict__ logits, long long n_windows, int n_cls,
+                                      int* __restrict__ frag_pred, float* __restrict__ entropy,
+                                      double* __restrict__ energy_sum) {
+  for (long long w = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; w < n_windows;
+       w += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float* z = logits + w * n_cls;
+    int best = 0;
+    float bv = z[0];
+    float ent = 0.0f;
+    double en = 0.0;
+    if (n_cls == 2) {
+      // multiclass-softmax branch of energy(): -logsumexp over the class axis
+      const double a = z[0], b = z[1];
+      const double m = a > b ? a : b;
+      en = -(m + log(exp(a - m) + exp(b - m)));
+    }
+    for (int k = 0; k < n_cls; ++k) {
+      const float v = z[k];
+      if (v > bv) { bv = v; best = k; }          // first maximum wins, like np.argmax
+      const float c = fminf(fmaxf(v, 1e-12f), 1.0f);
+      ent = __fadd_rn(ent, __fmul_rn(c, log2f(c)));
+      if (n_cls != 2) {
+        const double zd = v;
+        const double m = zd > 0.0 ? zd : 0.0;    // logsumexp([z, 0])
+        en += -(m + log(exp(zd - m) + exp(0.0 - m)));
+      }
+    }
+    frag_pred[w] = best;
+    entropy[w] = -ent;
+    energy_sum[w] = en;
+  }
+}
+
+// ---- per-contig reductions -----------------------------------------------------------------
+// One thread per (contig, class) reproduces numpy's arithmetic exactly: np.mean / np.var over
+// axis 0 of a C-contiguous float32 [T, C] array add the rows sequentially in float32, divide
+// by T in float32, and the results are then cast to float16 (collect.py:332-337).
+__global__ void contig_moments_kernel(const float* __restrict__ logits, const long long* __restrict__ offsets,
+                                      long long n_contigs, int n_cls, __half* __restrict__ mean_h,
+                                      __half* __restrict__ var_h) {
+  const long long total = n_contigs * n_cls;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long c = idx / n_cls;
+    const int k = static_cast<int>(idx - c * n_cls);
+    const long long b = offsets[c], e = offsets[c + 1];
+    const float cnt = static_cast<float>(e - b);
+    float s = 0.0f;
+    for (long long w = b; w < e; ++w) s = __fadd_rn(s, logits[w * n_cls + k]);
+    const float mean = __fdiv_rn(s, cnt);
+    float v = 0.0f;
+    for (long long w = b; w < e; ++w) {
+      const float d = __fsub_rn(logits[w * n_cls + k], mean);
+      v = __fadd_rn(v, __fmul_rn(d, d));
+    }
+    mean_h[idx] = __float2half_rn(mean);
+    var_h[idx] = __float2half_rn(__fdiv_rn(v, cnt));
+  }
+}
+
+// One warp per contig: consensus (argmax of the fp16 means, first max), per-class counts of
+// the window argmax, entropy / energy means, reliability fraction.
+__global__ void contig_summary_kernel(const __half* __restrict__ mean_h, const int* __restrict__ frag_pred,
+                                      const float* __restrict__ entropy, const double* __restrict__ energy_sum,
+                                      const float* __restrict__ rel, const long long* __restrict__ offsets,
+                                      long long n_contigs, int n_cls, int* __restrict__ consensus,
+                                      int* __restrict__ counts, __half* __restrict__ entropy_h,
+                                      __half* __restrict__ energy_h, float* __restrict__ rel_frac) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long c = warp0; c < n_contigs; c += n_warps) {
+    const long long b = offsets[c], e = offsets[c + 1];
+    // per-class counts: lane k counts class k (n_cls <= 32)
+    int my_count = 0;
+    double ent = 0.0, en = 0.0;
+    int rel_pos = 0;
+    for (long long w = b + lane; w < e; w += 32) {
+      ent += static_cast<double>(entropy[w]);
+      en += energy_sum[w];
+      if (rel) {
+        // helpers.py:222-235 sigmoid in the logits' dtype, collect.py:233-244 "> 0.5"
+        const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rel[w])));
+        rel_pos += sg > 0.5f;
+      }
+    }
+    for (long long w0 = b; w0 < e; w0 += 32) {
+      const long long w = w0 + lane;
+      const int fp = w < e ? frag_pred[w] : -1;
+      for (int k = 0; k < n_cls; ++k) {
+        const unsigned bal = __ballot_sync(0xffffffffu, fp == k);
+        if (lane == k) my_count += __popc(bal);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      ent += __shfl_xor_sync(0xffffffffu, ent, off);
+      en += __shfl_xor_sync(0xffffffffu, en, off);
+      rel_pos += __shfl_xor_sync(0xffffffffu, rel_pos, off);
+    }
+    if (lane < n_cls) counts[c * n_cls + lane] = my_count;
+    if (lane == 0) {
+      int best = 0;
+      float bv = __half2float(mean_h[c * n_cls]);
+      for (int k = 1; k < n_cls; ++k) {
+        const float v = __half2float(mean_h[c * n_cls + k]);
+        if (v > bv) { bv = v; best = k; }
+      }
+      consensus[c] = best;
+      const double t = static_cast<double>(e - b);
+      // np.mean of a float32 vector returns float32; the fp16 cast follows (collect.py:397-402)
+      entropy_h[c] = __float2half_rn(static_cast<float>(ent / t));
+      const double denom = (n_cls == 2) ? t : t * n_cls;
+      energy_h[c] = __double2half(en / denom);
+      if (rel_frac) rel_frac[c] = rel ? static_cast<float>(static_cast<double>(rel_pos) / t) : nanf("");
+    }
+  }
+}
+
+// ---- prophage score smoothing ----------------------------------------------------------------
+// prophages.py:126-131: softmax over classes, then np.convolve(p, ones(box), mode="same") per
+// class inside each contig.  For a kernel of length M <= N, "same" output i sums inputs
+// i - (M-1)//2 - ... : out[i] = sum_{j} p[i + (M-1)/2 - j], j = 0..M-1 (zero outside).
+__global__ void smooth_scores_kernel(const float* __restrict__ logits, const long long* __restrict__ offsets,
+                                     long long n_contigs, int n_cls, int box, double* __restrict__ out) {
+  for (long long c = blockIdx.y; c < n_contigs; c += gridDim.y) {
+    const long long b = offsets[c], e = offsets[c + 1];
+    const long long n = e - b;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      for (int k = 0; k < n_cls; ++k) {
+        double acc = 0.0;
+        // numpy swaps the operands when the kernel is longer than the signal; then the
+        // output has the kernel's length -- not reachable here (contigs have >= box windows
+        // whenever prophage mode applies, lc >= 500 kbp), so only the M <= N case is coded.
+        const long long lo = i + (box - 1) / 2 - (box - 1), hi = i + (box - 1) / 2;
+        for (long long j = lo; j <= hi; ++j) {
+          if (j < 0 || j >= n) continue;
+          const float* z = logits + (b + j) * n_cls;
+          double m = z[0];
+          for (int q = 1; q < n_cls; ++q) m = fmax(m, static_cast<double>(z[q]));
+          double den = 0.0;
+          for (int q = 0; q < n_cls; ++q) den += exp(static_cast<double>(z[q]) - m);
+          acc += exp(static_cast<double>(z[k]) - m) / den;
+        }
+        out[(b + i) * n_cls + k] = acc;
+      }
+    }
+  }
+}
+
+// ---- change-point segmentation ---------------------------------------------------------------
+// Optimal partitioning (the objective PELT minimises exactly) with the L2 cost
+//   cost(s, t) = sum x^2 - (sum x)^2 / (t - s)   over x[s:t],
+// every segment >= min_size, total = sum cost + pen * (#segments - 1)... ruptures adds `pen`
+// per change point.  One CTA per penalty; the inner minimisation over the last change point
+// is a block-wide min-reduction (warp shuffles), the outer loop over t is sequential.
+__global__ void prefix_sums_kernel(const double* __restrict__ x, int n, double* __restrict__ work) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double* S1 = work;
+    double* S2 = work + (n + 1);
+    double a = 0.0, b = 0.0;
+    S1[0] = 0.0; S2[0] = 0.0;
+    for (int i = 0; i < n; ++i) { a += x[i]; b += x[i] * x[i]; S1[i + 1] = a; S2[i + 1] = b; }
+  }
+}
+
+__global__ void segment_scores_kernel(const double* __restrict__ x, int n, int min_size, int n_pen,
+                                      double* __restrict__ work, int* __restrict__ bkps, int* __restrict__ nbkps) {
+  extern __shared__ double s_red[];
+  int* s_idx = reinterpret_cast<int*>(s_red + 32);
+  const int pen_i = blockIdx.x;
+  if (pen_i >= n_pen) return;
+  const double pen = static_cast<double>(pen_i + 1);
+  const double* S1 = work;                 // prefix sums from prefix_sums_kernel
+  const double* S2 = work + (n + 1);
+  double* F = work + 2 * (n + 1) + static_cast<long long>(pen_i) * (n + 1);
+  int* prev = reinterpret_cast<int*>(work + 2 * (n + 1) + static_cast<long long>(n_pen) * (n + 1)) +
+              static_cast<long long>(pen_i) * (n + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int t = 0; t <= n; ++t) {
+    if (threadIdx.x == 0) { if (t == 0) { F[0] = -pen; prev[0] = 0; } }
+    __syncthreads();
+    if (t == 0) continue;
+    double best = 1e300;
+    int best_s = -1;
+    if (t >= min_size) {
+      for (int s = threadIdx.x; s <= t - min_size; s += blockDim.x) {
+        if (s != 0 && s < min_size) continue;      // the first segment must also be >= min_size
+        const double f = F[s];
+        if (f >= 1e299) continue;
+        const double sum = S1[t] - S1[s];
+        const double c = (S2[t] - S2[s]) - sum * sum / static_cast<double>(t - s);
+        const double v = f + c + pen;
+        if (v < best || (v == best && s < best_s)) { best = v; best_s = s; }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int os = __shfl_xor_sync(0xffffffffu, best_s, off);
+      if (ov < best || (ov == best && os >= 0 && (best_s < 0 || os < best_s))) { best = ov; best_s = os; }
+    }
+    if (lane == 0) { s_red[warp] = best; s_idx[warp] = best_s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int wv = 1; wv < nwarps; ++wv)
+        if (s_red[wv] < best || (s_red[wv] == best && s_idx[wv] >= 0 && (best_s < 0 || s_idx[wv] < best_s))) {
+          best = s_red[wv]; best_s = s_idx[wv];
+        }
+      F[t] = best_s >= 0 ? best : 1e300;
+      prev[t] = best_s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // backtrack: segment ends in ascending order, last = n
+    int cnt = 0;
+    int t = n;
+    int* out = bkps + static_cast<long long>(pen_i) * n;
+    while (t > 0 && prev[t] >= 0) { out[cnt++] = t; t = prev[t]; }
+    for (int i = 0; i < cnt / 2; ++i) { const int tmp = out[i]; out[i] = out[cnt - 1 - i]; out[cnt - 1 - i] = tmp; }
+    nbkps[pen_i] = cnt;
+  }
+}
+
+}  // namespace jg

@@ -1,0 +1,207 @@
+// Stages 1-2 of the hot path: ASCII -> 2-bit pack, and fragment windowing + N-masking +
+// six-frame translation + codon encoding + base counts in one kernel.  HBM-bound integer work:
+// coalesced vector loads, shared-memory staging of the window's packed bases, word-wide token
+// stores.  Reference behaviour: seqops/io.py:103-133, seqops/encode.py:229-302,
+// preprocess/v1/convert.py:75-99 (paths relative to /root/reference/src/jaeger).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jg {
+
+// ---- stage 1 -------------------------------------------------------------------------------
+// One thread packs 32 bases: two 16-byte loads -> one 64-bit code word + one validity word.
+// A=0 C=1 T=2 G=3 is (ascii >> 1) & 3 on the case-folded letter; complement = code ^ 2.
+__global__ void pack_bases_kernel(const uint8_t* __restrict__ ascii, long long n,
+                                  uint32_t* __restrict__ codes, uint32_t* __restrict__ valid) {
+  const long long n_groups = (n + 31) / 32;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < n_groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long base = g * 32;
+    uint32_t bytes[8];
+    if (base + 32 <= n && ((reinterpret_cast<uintptr_t>(ascii) + base) & 15) == 0) {
+      const uint4 a = *reinterpret_cast<const uint4*>(ascii + base);
+      const uint4 b = *reinterpret_cast<const uint4*>(ascii + base + 16);
+      bytes[0] = a.x; bytes[1] = a.y; bytes[2] = a.z; bytes[3] = a.w;
+      bytes[4] = b.x; bytes[5] = b.y; bytes[6] = b.z; bytes[7] = b.w;
+    } else {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long i = base + w * 4 + k;
+          v |= static_cast<uint32_t>(i < n ? ascii[i] : 0) << (8 * k);
+        }
+        bytes[w] = v;
+      }
+    }
+    uint32_t lo = 0, hi = 0, vmask = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t c = (bytes[i >> 2] >> (8 * (i & 3))) & 0xDFu;  // fold case
+      const uint32_t code = (c >> 1) & 3u;
+      const bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+      if (i < 16) lo |= code << (2 * i); else hi |= code << (2 * (i - 16));
+      vmask |= static_cast<uint32_t>(ok) << i;
+    }
+    codes[2 * g] = lo;
+    codes[2 * g + 1] = hi;
+    valid[g] = vmask;
+  }
+}
+
+// ---- stage 2 -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t get_code(const uint32_t* s_codes, int i) {
+  return (s_codes[i >> 4] >> (2 * (i & 15))) & 3u;
+}
+__device__ __forceinline__ uint32_t get_bit(const uint32_t* s_bits, int i) {
+  return (s_bits[i >> 5] >> (i & 31)) & 1u;
+}
+
+// Exact emulation of Python's round(x, 2) for x = n/d (d > 0), returning hundredths.
+// Python rounds the double x = fl(n/d) correctly (half-even on the exact binary value); the
+// product 100*x is recovered exactly as p + e with an FMA, so the comparison with k + 0.5 is
+// exact.  (reference: utils/misc.py:117-123 safe_divide, seqops/io.py:128,133)
+__device__ __forceinline__ int round_hundredths(int num, int den) {
+  if (den == 0) return 0;
+  const double x = fabs(static_cast<double>(num) / static_cast<double>(den));
+  const double p = x * 100.0;
+  const double e = fma(x, 100.0, -p);
+  const double k = floor(p);
+  double r = (p - k) - 0.5;  // exact: both are multiples of ulp(p) and close together
+  // sign of (r + e) decides; a tie needs r + e == 0 exactly
+  const double s = r + e;
+  int kk = static_cast<int>(k);
+  if (s > 0.0) kk += 1;
+  else if (s == 0.0 && (r == -e)) kk += (kk & 1);  // half -> even
+  return num < 0 ? -kk : kk;
+}
+
+constexpr int kEncThreads = 128;
+
+// One CTA per window.  Shared memory holds the window's packed codes / validity / soft-mask
+// re-based to bit 0, so every codon is three 2-bit extracts.
+__global__ void __launch_bounds__(kEncThreads)
+encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid,
+                      const uint32_t* __restrict__ soft, const long long* __restrict__ win_base,
+                      const int* __restrict__ win_nbases, long long n_windows, int crop, int lc,
+                      int pitch, const uint8_t* __restrict__ lut64, int case_sensitive,
+                      uint8_t* __restrict__ tokens, int* __restrict__ counts,
+                      short* __restrict__ skew100) {
+  extern __shared__ uint32_t s_mem[];
+  const int words_c = (crop + 15) / 16 + 1;
+  const int words_b = (crop + 31) / 32 + 1;
+  uint32_t* s_codes = s_mem;
+  uint32_t* s_valid = s_codes + words_c;   // valid for tokens (soft-masked removed if case_sensitive)
+  uint32_t* s_count = s_valid + words_b;   // valid & ~soft (what the G/C/A/T counts see)
+  __shared__ uint8_t s_lut[64];
+  __shared__ int s_cnt[4];
+  if (threadIdx.x < 64) s_lut[threadIdx.x] = lut64[threadIdx.x];
+
+  for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+    const long long base = win_base[w];
+    int n = win_nbases[w];
+    if (n > crop) n = crop;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    // re-based copies: code word j holds bases [16j, 16j+16) of the window
+    const int sh_c = static_cast<int>(base & 15) * 2;
+    const long long w0_c = base >> 4;
+    for (int j = threadIdx.x; j < words_c; j += kEncThreads) {
+      const uint32_t a = codes[w0_c + j], b = codes[w0_c + j + 1];
+      s_codes[j] = sh_c ? ((a >> sh_c) | (b << (32 - sh_c))) : a;
+    }
+    const int sh_b = static_cast<int>(base & 31);
+    const long long w0_b = base >> 5;
+    for (int j = threadIdx.x; j < words_b; j += kEncThreads) {
+      const uint32_t a = valid[w0_b + j], b = valid[w0_b + j + 1];
+      uint32_t v = sh_b ? ((a >> sh_b) | (b << (32 - sh_b))) : a;
+      uint32_t sm = 0;
+      if (soft) {
+        const uint32_t c = soft[w0_b + j], d = soft[w0_b + j + 1];
+        sm = sh_b ? ((c >> sh_b) | (d << (32 - sh_b))) : c;
+      }
+      // clip to the window length
+      const int first = j * 32;
+      uint32_t keep = (first + 32 <= n) ? 0xFFFFFFFFu : (first >= n ? 0u : ((1u << (n - first)) - 1u));
+      v &= keep;
+      s_count[j] = v & ~sm;
+      s_valid[j] = case_sensitive ? (v & ~sm) : v;
+    }
+    __syncthreads();
+
+    // ---- base counts (upper-case, un-masked A/C/G/T) ------------------------------------
+    {
+      int cg = 0, cc = 0, ca = 0, ct = 0;
+      for (int j = threadIdx.x; j * 16 < n; j += kEncThreads) {
+        const uint32_t cw = s_codes[j];
+        const uint32_t vb = (s_count[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+        // spread the 16 validity bits to the low bit of each 2-bit lane
+        uint32_t m = vb;
+        m = (m | (m << 8)) & 0x00FF00FFu;
+        m = (m | (m << 4)) & 0x0F0F0F0Fu;
+        m = (m | (m << 2)) & 0x33333333u;
+        m = (m | (m << 1)) & 0x55555555u;
+        const uint32_t lo = cw & 0x55555555u, hi = (cw >> 1) & 0x55555555u;
+        ca += __popc(m & ~lo & ~hi);  // 00
+        cc += __popc(m & lo & ~hi);   // 01
+        ct += __popc(m & ~lo & hi);   // 10
+        cg += __popc(m & lo & hi);    // 11
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        cg += __shfl_xor_sync(0xffffffffu, cg, off);
+        cc += __shfl_xor_sync(0xffffffffu, cc, off);
+        ca += __shfl_xor_sync(0xffffffffu, ca, off);
+        ct += __shfl_xor_sync(0xffffffffu, ct, off);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], cg); atomicAdd(&s_cnt[1], cc);
+        atomicAdd(&s_cnt[2], ca); atomicAdd(&s_cnt[3], ct);
+      }
+    }
+
+    // ---- tokens: frames f1,f2,f3 (forward) r1,r2,r3 (reverse complement) ------------------
+    // encode.py:232-236: the slice offset comes from crop % 3, not from the true length.
+    const int off = (crop % 3 == 0) ? -2 : (crop % 3 == 1 ? -1 : 0);
+    int nc = (n - 5 + off + 2) / 3;          // ceil((n - 5 + off) / 3)
+    if (n - 5 + off <= 0) nc = 0;
+    if (nc > lc) nc = lc;
+    uint8_t* out = tokens + w * 6ll * pitch;   // pitch is a multiple of 4: word-wide stores
+    const int words_per_frame = pitch / 4;
+    for (int idx = threadIdx.x; idx < 6 * words_per_frame; idx += kEncThreads) {
+      const int f = idx / words_per_frame;
+      const int j0 = (idx % words_per_frame) * 4;
+      uint32_t packed = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        uint32_t tok = 0;
+        if (j < nc) {
+          int p0, p1, p2;
+          uint32_t flip;
+          if (f < 3) { p0 = f + 3 * j; p1 = p0 + 1; p2 = p0 + 2; flip = 0; }
+          else { p0 = n - 1 - (f - 3) - 3 * j; p1 = p0 - 1; p2 = p0 - 2; flip = 2; }
+          const uint32_t ok = get_bit(s_valid, p0) & get_bit(s_valid, p1) & get_bit(s_valid, p2);
+          const uint32_t ci = ((get_code(s_codes, p0) ^ flip) << 4) | ((get_code(s_codes, p1) ^ flip) << 2) |
+                              (get_code(s_codes, p2) ^ flip);
+          tok = ok ? s_lut[ci] : 0u;
+        }
+        packed |= tok << (8 * e);
+      }
+      *reinterpret_cast<uint32_t*>(out + static_cast<long long>(f) * pitch + j0) = packed;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int g = s_cnt[0], c = s_cnt[1];
+      counts[w * 4 + 0] = g; counts[w * 4 + 1] = c; counts[w * 4 + 2] = s_cnt[2]; counts[w * 4 + 3] = s_cnt[3];
+      const int h = round_hundredths(g - c, g + c);
+      short v = static_cast<short>(h);
+      if (h == 0 && g - c < 0 && g + c != 0) v = static_cast<short>(1 << 14);  // "-0.000"
+      skew100[w] = v;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace jg

@@ -1,0 +1,347 @@
+"""B200Engine -- the fifth inference engine behind the reference's engine contract.
+
+The reference's `commands/predict.py:687-747` programs against an object with
+`class_map`, `string_processor_config` and `predict(dataset) -> dict[str, np.ndarray]`
+(`InferModel`, nnlib/inference.py:300-421).  `B200Engine` keeps that contract and owns the
+whole device pipeline: 2-bit pack -> window/encode kernel -> tcgen05 conv stack -> heads.
+
+    engine = B200Engine(path_dict)                  # AvailableModels.info[name], or spec=/weights=
+    y = engine.predict(WindowSource(fasta, fsize=2000, stride=1500, ...))
+    y["prediction"] [W, n_cls] f32, y["reliability"] [W, 1], y["embedding"], y["nmd"],
+    y["meta_0".."meta_9"] byte-string arrays in window order (long pass then short pass).
+
+`predict` also accepts the reference's dataset protocol -- an iterable of
+`(inputs_dict, meta_0, ..., meta_9)` batches with `inputs_dict["translated"]` holding tokens
+[B, 6, L] (or one-hot [B, 6, L, depth]) -- in which case only stage 3 runs on the device.
+
+PyTorch is used for device / pinned memory and streams only.  No CPU fallback exists: the
+constructor raises without the CUDA library or a B200.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any, Iterable
+
+import numpy as np
+import torch
+import yaml
+
+from . import _cabi, codon_tables
+from ._cabi import check, lib
+from .modelspec import ModelSpec, init_random, load_project, string_processor_config
+from .plan import Plan, compile_plan, to_ctypes
+
+_SKEW_STR = np.array([f"{v / 100: .3f}" for v in range(-100, 101)] + ["-0.000"], dtype="S6")
+
+
+def read_fasta(path: str | Path):
+    """(name, sequence) pairs: name = header up to the first whitespace, sequence = the
+    record's lines joined (pyfastx semantics used at seqops/io.py:98-104)."""
+    name, chunks = None, []
+    with open(path, "rb") as fh:
+        for line in fh:
+            if line.startswith(b">"):
+                if name is not None:
+                    yield name, b"".join(chunks)
+                fields = line[1:].split()
+                name = fields[0].decode() if fields else ""
+                chunks = []
+            elif name is not None:
+                chunks.append(line.strip())
+    if name is not None:
+        yield name, b"".join(chunks)
+
+
+@dataclass
+class WindowSource:
+    """What `fragment_generator` + `process_string_inference` are parameterised with
+    (commands/predict.py:186-245): where the contigs come from and how to window them."""
+    fasta: str | Path | None = None
+    records: list[tuple[str, bytes | str]] | None = None
+    fsize: int = 2000
+    stride: int = 1500
+    min_len: int | None = None           # < fsize enables the two-pass short-contig mode
+    dynamic_stride: bool = False
+    dynamic_stride_threshold: float = 10.0
+    batch: int = 96                      # only shapes the short pass' padded batches
+    softmasks: dict[str, np.ndarray] | None = None   # per-contig bool arrays (dustmask stand-in)
+
+    def load(self) -> list[tuple[str, bytes]]:
+        recs = self.records if self.records is not None else list(read_fasta(self.fasta))
+        return [(n, s.encode() if isinstance(s, str) else bytes(s)) for n, s in recs]
+
+
+@dataclass
+class WindowTable:
+    """Numeric per-window metadata of the last `predict` call (what meta_0..9 encode)."""
+    headers: list[str] = field(default_factory=list)        # per contig, in window order
+    contig: np.ndarray | None = None     # window -> index into headers
+    start: np.ndarray | None = None
+    nbases: np.ndarray | None = None
+    ordinal: np.ndarray | None = None
+    is_last: np.ndarray | None = None
+    seqlen: np.ndarray | None = None
+    counts: np.ndarray | None = None     # [W, 4] G, C, A, T
+    skew100: np.ndarray | None = None
+
+
+class B200Engine:
+    def __init__(self, path_dict: dict[str, Any] | None = None, *, spec: ModelSpec | None = None,
+                 weights: dict[str, Any] | None = None, device: int = 0, workspace_gb: float = 16.0,
+                 seed: int = 0, use_ref_kernels: bool = False):
+        if not torch.cuda.is_available():
+            raise _cabi.JaegerB200Error("no CUDA device: jaeger_b200 has no CPU fallback")
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self.ctx = _cabi.Context(self.device)
+        self.use_ref_kernels = bool(use_ref_kernels)
+        self.class_map = None
+        if path_dict is not None:
+            project = path_dict.get("project")
+            if project is None:
+                raise ValueError("model has no *_project.yaml; only layer-list fragment models are supported")
+            spec = load_project(project)
+            self.class_map = self._load_class_map(path_dict.get("classes"))
+            if weights is None:
+                from .weights import load_saved_model_weights
+                weights = load_saved_model_weights(path_dict, spec)
+        if spec is None:
+            raise ValueError("B200Engine needs a path_dict or a ModelSpec")
+        self.spec = spec
+        self.weights = weights if weights is not None else init_random(spec, seed)
+        if self.class_map is None and spec.classes:
+            self.class_map = {"num_classes": len(spec.classes), "class": [c["class"] for c in spec.classes],
+                              "index": [c["label"] for c in spec.classes]}
+        self.string_processor_config = string_processor_config(spec)
+        self.plan: Plan = compile_plan(spec, self.weights)
+        layers, head = to_ctypes(self.plan)
+        h = ctypes.c_void_p()
+        check(lib.jg_model_create(self.ctx.handle, layers, len(self.plan.launches), ctypes.byref(head), 6, 65,
+                                  ctypes.byref(h)))
+        self.model = h
+        self.workspace_bytes = int(workspace_gb * (1 << 30))
+        self.lut = codon_tables.device_lut(self.string_processor_config["codon_id"], plus_one=True)
+        self.case_sensitive = int(self.string_processor_config["masking"])
+        self.windows = WindowTable()
+        self.timings: dict[str, float] = {}
+
+    # ---- reference-compatible helpers ---------------------------------------------------------
+    @staticmethod
+    def _load_class_map(path):
+        """nnlib/inference.py:411-421."""
+        if path is None:
+            return None
+        cm = yaml.safe_load(Path(path).read_text())["classes"]
+        return {"num_classes": len(cm), "class": [i["class"] for i in cm], "index": [i["label"] for i in cm]}
+
+    def close(self):
+        if getattr(self, "model", None):
+            lib.jg_model_destroy(self.model)
+            self.model = None
+        self.ctx.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- torch plumbing -----------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.ExternalStream(self.ctx.stream, device=self.tdev)
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.tdev)
+
+    def _h2d(self, arr: np.ndarray, pinned: bool = True) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.tdev, non_blocking=True)
+
+    def codons_per_frame(self, n_bases: int, crop: int) -> int:
+        off = (-2, -1, 0)[crop % 3]
+        v = n_bases - 5 + off
+        return 0 if v <= 0 else (v + 2) // 3
+
+    # ---- stages -------------------------------------------------------------------------------
+    def pack(self, ascii_dev: torch.Tensor):
+        n = ascii_dev.numel()
+        codes = torch.zeros((n + 15) // 16 + 4, dtype=torch.int32, device=self.tdev)
+        valid = torch.zeros((n + 31) // 32 + 4, dtype=torch.int32, device=self.tdev)
+        check(lib.jg_pack_bases(self.ctx.handle, ascii_dev.data_ptr(), n, codes.data_ptr(), valid.data_ptr()))
+        return codes, valid
+
+    @staticmethod
+    def plan_windows(lens: np.ndarray, fsize: int, stride: int, dynamic_stride=False, threshold=10.0,
+                     min_len: int | None = None, max_len: int = 0, short_pass: bool = False):
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        n = ctypes.c_int64(0)
+        lp = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        args = (lp, len(lens), int(fsize), int(stride), int(bool(dynamic_stride)), float(threshold),
+                int(fsize if min_len is None else min_len), int(max_len), int(bool(short_pass)))
+        null = [ctypes.POINTER(t)() for t in (ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint8)]
+        check(lib.jg_plan_windows(*args, ctypes.byref(n), *null))
+        w = n.value
+        contig = np.empty(w, np.int32); start = np.empty(w, np.int64); nb = np.empty(w, np.int32)
+        ordinal = np.empty(w, np.int32); last = np.empty(w, np.uint8)
+        if w:
+            check(lib.jg_plan_windows(*args, ctypes.byref(n),
+                                      contig.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                      start.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                      nb.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                      ordinal.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                      last.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+        return contig, start, nb, ordinal, last
+
+    def encode(self, codes, valid, win_base: torch.Tensor, win_nbases: torch.Tensor, crop: int, lc: int,
+               soft: torch.Tensor | None = None, lut: np.ndarray | None = None, case_sensitive: int | None = None):
+        w = win_base.numel()
+        pitch = (lc + 3) // 4 * 4
+        tokens = self._empty((w, 6, pitch), torch.uint8)
+        counts = self._empty((w, 4), torch.int32)
+        skew = self._empty((w,), torch.int16)
+        lut = self.lut if lut is None else np.ascontiguousarray(lut, np.uint8)
+        check(lib.jg_encode_windows(self.ctx.handle, codes.data_ptr(), valid.data_ptr(),
+                                    soft.data_ptr() if soft is not None else None, win_base.data_ptr(),
+                                    win_nbases.data_ptr(), w, int(crop), int(lc), pitch,
+                                    lut.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                    self.case_sensitive if case_sensitive is None else int(case_sensitive),
+                                    tokens.data_ptr(), counts.data_ptr(), skew.data_ptr()))
+        return tokens, counts, skew
+
+    def forward(self, tokens: torch.Tensor, lpad: torch.Tensor, lc: int):
+        """tokens [W, 6, pitch] uint8 on device -> dict of device tensors."""
+        w, _, pitch = tokens.shape
+        p = self.plan
+        out = {"prediction": self._empty((w, p.n_classes), torch.float32),
+               "embedding": self._empty((w, p.feat_dim), torch.float32)}
+        if p.n_taps:
+            out["nmd"] = self._empty((w, p.n_taps * p.tap_width), torch.float32)
+        if p.rel is not None:
+            out["reliability"] = self._empty((w, 1), torch.float32)
+        chunk = int(lib.jg_model_max_windows(self.model, int(lc), self.workspace_bytes))
+        if chunk < 1:
+            raise _cabi.JaegerB200Error("workspace budget too small for one window")
+        for b in range(0, w, chunk):
+            e = min(w, b + chunk)
+            check(lib.jg_model_forward(
+                self.ctx.handle, self.model, tokens[b:e].data_ptr(), lpad[b:e].data_ptr(), e - b, int(lc), int(pitch),
+                out["prediction"][b:e].data_ptr(),
+                out["reliability"][b:e].data_ptr() if "reliability" in out else None,
+                out["embedding"][b:e].data_ptr(),
+                out["nmd"][b:e].data_ptr() if "nmd" in out else None, int(self.use_ref_kernels)))
+        return out
+
+    # ---- the engine contract --------------------------------------------------------------------
+    def predict(self, dataset, no_progress: bool = False) -> dict[str, np.ndarray]:
+        if isinstance(dataset, WindowSource):
+            return self._predict_source(dataset)
+        return self._predict_batches(dataset)
+
+    def _predict_batches(self, dataset: Iterable) -> dict[str, np.ndarray]:
+        """Reference dataset protocol: (inputs_dict, meta_0..meta_9) batches (inference.py:341-373)."""
+        acc: dict[str, list] = {}
+        with torch.cuda.stream(self._stream()):
+            for inputs, *meta in dataset:
+                x = np.asarray(inputs["translated"] if isinstance(inputs, dict) else inputs)
+                if x.ndim == 4:      # one-hot [B,6,L,depth] -> tokens (all-zero row = 0)
+                    tok = np.where(x.sum(-1) > 0, x.argmax(-1) + 1, 0).astype(np.uint8)
+                else:
+                    tok = x.astype(np.uint8)
+                b, _, lc = tok.shape
+                pitch = (lc + 3) // 4 * 4
+                padded = np.zeros((b, 6, pitch), np.uint8)
+                padded[:, :, :lc] = tok
+                lpad = torch.full((b,), lc, dtype=torch.int32, device=self.tdev)
+                out = self.forward(self._h2d(padded), lpad, lc)
+                for k, v in out.items():
+                    acc.setdefault(k, []).append(v.cpu().numpy())
+                for i, mt in enumerate(meta):
+                    acc.setdefault(f"meta_{i}", []).append(np.asarray(mt))
+        self.ctx.sync()
+        return {k: np.concatenate(v, axis=0) for k, v in acc.items()}
+
+    def _predict_source(self, src: WindowSource) -> dict[str, np.ndarray]:
+        recs = src.load()
+        fsize, stride = int(src.fsize), int(src.stride)
+        names = [n.strip().replace(",", "___") for n, _ in recs]          # seqops/io.py:109
+        lens = np.array([len(s) for _, s in recs], dtype=np.int64)
+        offsets = np.zeros(len(recs) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        total = int(offsets[-1])
+        two_pass = src.min_len is not None and src.min_len < fsize      # commands/predict.py:771-810
+        passes = [self.plan_windows(lens, fsize, stride, src.dynamic_stride, src.dynamic_stride_threshold,
+                                    min_len=fsize, short_pass=False)]
+        if two_pass:
+            passes.append(self.plan_windows(lens, fsize, stride, src.dynamic_stride, src.dynamic_stride_threshold,
+                                            min_len=src.min_len, max_len=fsize - 1, short_pass=True))
+        lc_full = self.codons_per_frame(fsize, fsize)
+        results: list[dict[str, torch.Tensor]] = []
+        tables = []
+        with torch.cuda.stream(self._stream()):
+            host = torch.empty(total, dtype=torch.uint8).pin_memory()
+            hv = host.numpy()
+            for (o, (_, s)) in zip(offsets[:-1], recs):
+                hv[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+            ascii_dev = host.to(self.tdev, non_blocking=True)
+            codes, valid = self.pack(ascii_dev)
+            soft = None
+            if src.softmasks:
+                bits = np.zeros(total, dtype=bool)
+                for (o, (n, _)) in zip(offsets[:-1], recs):
+                    if n in src.softmasks:
+                        m = np.asarray(src.softmasks[n], dtype=bool)
+                        bits[o:o + len(m)] = m
+                packed = np.packbits(bits, bitorder="little")
+                words = np.zeros((total + 31) // 32 * 4 + 16, np.uint8)
+                words[:len(packed)] = packed
+                soft = self._h2d(words.view(np.int32))
+            for pi, (contig, start, nb, ordinal, last) in enumerate(passes):
+                w = len(contig)
+                if w == 0:
+                    continue
+                base = self._h2d(offsets[contig] + start)
+                nbd = self._h2d(nb)
+                if pi == 0:
+                    lc = lc_full
+                    lpad_h = np.full(w, lc, np.int32)
+                else:
+                    # padded_batch pads every batch of `batch` windows to its longest member
+                    per = np.array([self.codons_per_frame(int(n), fsize) for n in nb], np.int32)
+                    lpad_h = per.copy()
+                    for b in range(0, w, src.batch):
+                        lpad_h[b:b + src.batch] = per[b:b + src.batch].max()
+                    lc = int(per.max())
+                tokens, counts, skew = self.encode(codes, valid, base, nbd, fsize, lc, soft)
+                out = self.forward(tokens, self._h2d(lpad_h), lc)
+                out["_counts"], out["_skew"] = counts, skew
+                results.append(out)
+                tables.append((contig, start, nb, ordinal, last))
+            host_out = [{k: v.cpu() for k, v in r.items()} for r in results]
+        self.ctx.sync()
+        if not host_out:
+            return {}
+        y: dict[str, np.ndarray] = {}
+        for k in host_out[0]:
+            y[k] = np.concatenate([r[k].numpy() for r in host_out], axis=0)
+        contig = np.concatenate([t[0] for t in tables]); start = np.concatenate([t[1] for t in tables])
+        nb = np.concatenate([t[2] for t in tables]); ordinal = np.concatenate([t[3] for t in tables])
+        last = np.concatenate([t[4] for t in tables])
+        counts, skew = y.pop("_counts"), y.pop("_skew")
+        self.windows = WindowTable(headers=names, contig=contig, start=start, nbases=nb, ordinal=ordinal,
+                                   is_last=last, seqlen=lens[contig], counts=counts, skew100=skew)
+        # meta_0..meta_9 exactly as process_string_inference forwards them (encode.py:304-316)
+        name_arr = np.array([n.encode() for n in names], dtype="S")
+        y["meta_0"] = name_arr[contig]
+        y["meta_1"] = start.astype("S")
+        y["meta_2"] = last.astype(np.int32).astype("S")
+        y["meta_3"] = ordinal.astype("S")
+        y["meta_4"] = lens[contig].astype("S")
+        for i in range(4):
+            y[f"meta_{5 + i}"] = counts[:, i].astype("S")
+        idx = np.where(skew == (1 << 14), 201, skew.astype(np.int32) + 100)
+        y["meta_9"] = _SKEW_STR[idx]
+        return y

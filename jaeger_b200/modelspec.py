@@ -1,0 +1,301 @@
+"""project.yaml -> model specification + weights container.
+
+Mirrors what the reference's `DynamicModelBuilder` reads from a model's `*_project.yaml`
+(nnlib/builder.py:844-894 embedding, 982-1193 `_build_block`, 589-596 / 705-713 heads) for
+the residual-CNN family the fragment models use, and what `InferModel` reads from it
+(nnlib/inference.py:423-483).  Anything outside that family raises NotImplementedError
+instead of being approximated.
+
+The weights container is a plain nested dict of float32 NumPy arrays in TensorFlow layout
+(conv kernels [k, Cin, Cout], dense kernels [in, out]):
+
+    {"embedding": [vocab, E] | None,
+     "layers": [per hidden layer: {} | {"kernel","bias"} | {"gamma","beta","mean","var"} |
+                {"moving_mean"} | {"blocks": [{"conv1","bn1","conv2","bn2"}]}],
+     "classifier": [{"kernel","bias"}...], "reliability": [{"kernel","bias"}...]}
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import yaml
+
+CODON_TABLE_NAMES = ("CODON_ID", "AA_ID", "MURPHY10_ID", "PC5_ID")
+
+
+@dataclass
+class LayerSpec:
+    kind: str                      # conv | nmd | norm | act | resblock
+    cfg: dict[str, Any] = field(default_factory=dict)
+
+
+@dataclass
+class ModelSpec:
+    name: str
+    classes: list[dict[str, Any]]
+    embedding: dict[str, Any]
+    string_processor: dict[str, Any]
+    layers: list[LayerSpec]
+    pooling: str
+    classifier: list[dict[str, Any]]      # dense layer cfgs (units, activation)
+    reliability: list[dict[str, Any]] | None
+    use_masking: bool = True
+
+    @property
+    def n_classes(self) -> int:
+        return self.classifier[-1]["units"]
+
+    @property
+    def embedding_size(self) -> int:
+        return int(self.embedding.get("embedding_size", 4))
+
+    @property
+    def uses_token_input(self) -> bool:
+        """True when the SavedModel input is [B,6,L] token ids (Embedding, mask_zero)."""
+        return bool(self.embedding.get("use_embedding_layer", False))
+
+
+def _act_name(cfg: dict[str, Any], default: str | None = None) -> str | None:
+    a = cfg.get("activation", default)
+    if a in (None, "linear"):
+        return None
+    a = str(a).lower()
+    if a not in ("gelu", "relu"):
+        raise NotImplementedError(f"activation {a!r} is not on the supported hot path")
+    return a
+
+
+def parse_project(cfg: dict[str, Any]) -> ModelSpec:
+    """Compile the `model:` section of a project.yaml (layer-list schema)."""
+    model = cfg["model"] if "model" in cfg else cfg
+    emb = dict(model.get("embedding", {}))
+    sp = dict(model.get("string_processor", {}))
+    if emb.get("input_type", emb.get("type", "translated")) != "translated":
+        raise NotImplementedError("only the translated (six-frame codon) input is on the hot path")
+    rep = model.get("representation_learner")
+    if rep is None or "hidden_layers" not in rep:
+        raise NotImplementedError("flat (pre-layer-list) project schema is not supported yet")
+    use_masking = bool(model.get("use_masking", True))
+    layers: list[LayerSpec] = []
+    for lc in rep["hidden_layers"]:
+        name = str(lc.get("name", "")).lower()
+        c = dict(lc.get("config") or {})
+        if name == "masked_conv1d":
+            if int(c.get("strides", 1)) != 1:
+                raise NotImplementedError("strided convolutions are not supported")
+            mode = c.get("mask_mode", "any")
+            if c.get("use_masking", use_masking) and mode != "any":
+                raise NotImplementedError(f"mask_mode={mode!r}: only 'any' (the default) is supported")
+            layers.append(LayerSpec("conv", dict(
+                filters=int(c["filters"]), kernel_size=int(c["kernel_size"]),
+                dilation=int(c.get("dilation_rate", 1)), padding=str(c.get("padding", "valid")).lower(),
+                use_bias=bool(c.get("use_bias", True)), activation=_act_name(c),
+                use_masking=bool(c.get("use_masking", use_masking)))))
+        elif name == "nmd":
+            layers.append(LayerSpec("nmd"))
+        elif name == "masked_batchnorm":
+            if c.get("return_nmd"):
+                raise NotImplementedError("masked_batchnorm(return_nmd=True) is not supported; use an nmd layer")
+            layers.append(LayerSpec("norm", dict(epsilon=float(c.get("epsilon", 1e-5)))))
+        elif name in ("activation", "gelu", "relu"):
+            layers.append(LayerSpec("act", dict(activation=_act_name(c, name if name != "activation" else None))))
+        elif name == "residual_block":
+            if int(c.get("strides", 1)) != 1 or c.get("use_1x1conv", False):
+                raise NotImplementedError("strided / 1x1-bypass residual blocks are not supported")
+            if str(c.get("norm_type", "masked_batchnorm")).lower() != "masked_batchnorm":
+                raise NotImplementedError("only masked_batchnorm residual blocks are supported")
+            if c.get("return_nmd"):
+                raise NotImplementedError("residual_block(return_nmd=True) is not supported; use an nmd layer")
+            layers.append(LayerSpec("resblock", dict(
+                block_size=int(c.get("block_size", 1)), filters=int(c["filters"]),
+                kernel_size=int(c.get("kernel_size", 3)), dilation=int(c.get("dilation_rate", 1)),
+                use_bias=bool(c.get("use_bias", True)), activation=_act_name(c, model.get("activation", "gelu")) or "gelu",
+                use_masking=bool(c.get("use_masking", use_masking)))))
+        elif name == "dropout":
+            continue
+        else:
+            raise NotImplementedError(f"layer {name!r} is outside the supported residual-CNN family")
+    pooling = str(rep.get("pooling", "max")).lower()
+    if pooling not in ("max", "average"):
+        raise NotImplementedError(f"pooling {pooling!r} is not supported")
+
+    def dense_stack(section):
+        out = []
+        for lc in section.get("hidden_layers", []):
+            if str(lc.get("name", "")).lower() == "dense":
+                c = lc.get("config") or {}
+                out.append(dict(units=int(c["units"]), activation=_act_name(c), use_bias=bool(c.get("use_bias", True))))
+        return out
+
+    classifier = dense_stack(model["classifier"])
+    if len(classifier) != 1 or classifier[0]["activation"] is not None:
+        raise NotImplementedError("classifier head must be a single linear Dense layer")
+    reliability = None
+    if "reliability_model" in model:
+        rm = model["reliability_model"]
+        if rm.get("mode", "nmd") != "nmd":
+            raise NotImplementedError("reliability_model.mode other than 'nmd' is not supported")
+        reliability = dense_stack(rm)
+        if len(reliability) != 2 or reliability[1]["units"] != 1:
+            raise NotImplementedError("reliability head must be Dense(h, act) -> Dense(1)")
+    return ModelSpec(name=str(model.get("name", "jaeger")), classes=list(model.get("class_label_map", [])),
+                     embedding=emb, string_processor=sp, layers=layers, pooling=pooling,
+                     classifier=classifier, reliability=reliability, use_masking=use_masking)
+
+
+def load_project(path: str | Path) -> ModelSpec:
+    """nnlib/inference.py:438 reads the file with plain yaml.safe_load."""
+    return parse_project(yaml.safe_load(Path(path).read_text()) or {})
+
+
+def string_processor_config(spec: ModelSpec) -> dict[str, Any]:
+    """What InferModel._load_string_processor_config derives (nnlib/inference.py:423-483)."""
+    cfg = dict(spec.embedding)
+    cfg.update(spec.string_processor)
+    cfg["input_type"] = cfg.get("type", "translated")
+    codon_id_name = cfg.get("codon_id", "CODON_ID")
+    if codon_id_name not in CODON_TABLE_NAMES:
+        raise NotImplementedError(f"codon_id {codon_id_name!r} is not supported (dicodons are out of scope)")
+    from . import codon_tables
+    ids = codon_tables.TABLES[codon_id_name]
+    cfg["codon_id_name"] = codon_id_name
+    cfg["codon_id"] = ids
+    cfg["codon_depth"] = max(ids) + 1
+    cfg["vocab_size"] = len(ids) + 1
+    cfg["ngram_width"] = 3
+    shape = spec.embedding.get("input_shape")
+    if cfg.get("seq_onehot") is None and shape is not None:
+        cfg["seq_onehot"] = len(shape) == 3 and shape[-1] is not None and shape[-1] > 1
+    cfg["seq_onehot"] = bool(cfg.get("seq_onehot", False))
+    if not cfg["seq_onehot"]:
+        cfg["codon_depth"] = 1
+    cfg["masking"] = bool(cfg.get("masking", False))
+    return cfg
+
+
+# ---- weights ---------------------------------------------------------------------------------
+
+def _glorot(rng, shape, fan_in, fan_out):
+    lim = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def _bn(rng, c):
+    return dict(gamma=np.ones(c, np.float32), beta=np.zeros(c, np.float32),
+                mean=rng.normal(0.0, 0.1, c).astype(np.float32),
+                var=rng.uniform(0.5, 1.5, c).astype(np.float32))
+
+
+def _conv(rng, k, cin, cout):
+    return dict(kernel=_glorot(rng, (k, cin, cout), k * cin, k * cout), bias=np.zeros(cout, np.float32))
+
+
+def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
+    """Random-init weights of the architecture (SURVEY.md 8d config 2 recipe: Glorot-uniform
+    kernels, zero bias, BN gamma=1 beta=0 mean~N(0,0.1) var~U(0.5,1.5))."""
+    rng = np.random.default_rng(seed)
+    e = spec.embedding_size
+    w: dict[str, Any] = {"layers": []}
+    if e > 0:
+        if spec.uses_token_input:
+            q, _ = np.linalg.qr(rng.normal(size=(max(65, e), max(65, e))))
+            w["embedding"] = q[:65, :e].astype(np.float32)
+        else:
+            q, _ = np.linalg.qr(rng.normal(size=(max(64, e), max(64, e))))
+            w["embedding"] = q[:64, :e].astype(np.float32)
+        ch = e
+    else:
+        w["embedding"] = None
+        ch = 64
+    for layer in spec.layers:
+        c = layer.cfg
+        if layer.kind == "conv":
+            w["layers"].append(_conv(rng, c["kernel_size"], ch, c["filters"]))
+            ch = c["filters"]
+        elif layer.kind == "norm":
+            w["layers"].append(_bn(rng, ch))
+        elif layer.kind == "nmd":
+            w["layers"].append(dict(moving_mean=rng.normal(0.0, 0.1, ch).astype(np.float32)))
+        elif layer.kind == "resblock":
+            blocks = []
+            for _ in range(c["block_size"]):
+                blocks.append(dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=_bn(rng, c["filters"]),
+                                   conv2=_conv(rng, c["kernel_size"], c["filters"], c["filters"]),
+                                   bn2=_bn(rng, c["filters"])))
+                ch = c["filters"]
+            w["layers"].append(dict(blocks=blocks))
+        else:
+            w["layers"].append({})
+    feat = ch
+    w["classifier"] = [dict(kernel=_glorot(rng, (feat, spec.n_classes), feat, spec.n_classes),
+                            bias=np.zeros(spec.n_classes, np.float32))]
+    if spec.reliability is not None:
+        n_nmd = sum(1 for layer in spec.layers if layer.kind == "nmd")
+        nmd_dim = 0
+        chn = e if e > 0 else 64
+        for layer in spec.layers:
+            if layer.kind in ("conv", "resblock"):
+                chn = layer.cfg["filters"]
+            if layer.kind == "nmd":
+                nmd_dim += chn
+        h = spec.reliability[0]["units"]
+        w["reliability"] = [dict(kernel=_glorot(rng, (nmd_dim, h), nmd_dim, h), bias=np.zeros(h, np.float32)),
+                            dict(kernel=_glorot(rng, (h, 1), h, 1), bias=np.zeros(1, np.float32))]
+        assert n_nmd > 0, "reliability head needs at least one nmd layer"
+    return w
+
+
+def count_params(spec: ModelSpec, weights: dict[str, Any], representation_only: bool = True) -> int:
+    """Parameter count as Keras' rep_model.count_params() sees it (all variables incl. the
+    BN moving statistics and NMD moving means)."""
+    n = 0
+    if weights.get("embedding") is not None:
+        n += weights["embedding"].size
+    for lw in weights["layers"]:
+        if "blocks" in lw:
+            for b in lw["blocks"]:
+                for part in b.values():
+                    n += sum(v.size for v in part.values())
+        else:
+            n += sum(v.size for v in lw.values())
+    if not representation_only:
+        for sec in ("classifier", "reliability"):
+            for d in weights.get(sec) or []:
+                n += d["kernel"].size + d["bias"].size
+    return int(n)
+
+
+def standin_1p4m_config() -> dict[str, Any]:
+    """The declared stand-in for `jaeger_38341_1.4M_fragment`: the
+    nmd_merge family of train_config/nn_config_1500bp_nmd_merge_6_class_brain.yaml with four
+    residual stacks instead of three."""
+    def conv(f, k):
+        return {"name": "masked_conv1d", "config": {"filters": f, "kernel_size": k, "strides": 1,
+                                                    "dilation_rate": 1, "use_bias": True, "activation": None}}
+    tail = [{"name": "nmd"}, {"name": "masked_batchnorm", "config": {"return_nmd": False}},
+            {"name": "activation", "config": {"activation": "gelu"}}]
+    block = {"name": "residual_block", "config": {"use_1x1conv": False, "block_size": 2, "filters": 128,
+                                                  "kernel_size": 5, "dilation_rate": 3, "use_bias": True}}
+    hidden = [conv(128, 7)] + tail
+    for _ in range(4):
+        hidden += [block] + tail
+    classes = ["bacteria", "phage", "eukarya", "archaea", "plasmid", "virus"]
+    return {"model": {
+        "name": "jaeger_standin_1p4M", "activation": "gelu", "classifier_out_dim": 6,
+        "class_label_map": [{"class": c, "label": i} for i, c in enumerate(classes)],
+        "embedding": {"use_embedding_layer": True, "input_type": "translated", "frames": 6,
+                      "input_shape": [6, None], "embedding_size": 128},
+        "string_processor": {"seq_onehot": False, "codon": "CODON", "codon_id": "CODON_ID", "masking": False},
+        "representation_learner": {"hidden_layers": hidden, "pooling": "max"},
+        "classifier": {"input_shape": 128, "hidden_layers": [
+            {"name": "dropout", "config": {"rate": 0.1}},
+            {"name": "dense", "config": {"units": 6, "activation": None, "use_bias": True}}]},
+        "reliability_model": {"merge": {"mode": "concat", "axis": -1}, "input_shape": 640, "hidden_layers": [
+            {"name": "dropout", "config": {"rate": 0.3}},
+            {"name": "dense", "config": {"units": 8, "activation": "gelu", "use_bias": True}},
+            {"name": "dropout", "config": {"rate": 0.1}},
+            {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]},
+    }}

@@ -1,0 +1,317 @@
+"""ModelSpec + weights -> the fused conv-launch plan the CUDA library executes.
+
+Each `masked_conv1d` / residual-block convolution becomes ONE kernel launch whose epilogue
+absorbs the element-wise layers that follow it in the reference graph:
+
+    conv(+bias) -> [NMD tap on the raw output] -> norm (folded to scale/shift) -> [+ shortcut]
+    -> activation -> [NMD tap] -> [stand-alone norm -> activation] -> [global pool]
+
+(reference graph: nnlib/builder.py:982-1193; layer math: nnlib/v2/layers.py:918-941 inference
+BatchNorm, 1882-1915 ResidualBlock.call, 1217-1280 MaskedConv1D, nnlib/v2/nmd.py:43-77.)
+
+Mask bookkeeping.  A tensor is stored multiplied by the Keras mask it carries; the reference
+does NOT re-mask after BatchNorm / activation / add, so where a stored tensor is later used
+outside a convolution (residual shortcut) the value at a masked row is reconstructed: with
+mask_mode "any" a masked output row has seen only zeroed inputs, hence equals a per-channel
+constant (`sc_const`) computed here by pushing a zero accumulator through the same epilogue.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from .modelspec import ModelSpec
+
+ACT = {None: 0, "gelu": 1, "relu": 2, "gelu_erf": 3}
+LAYER_INT_FIELDS = 24
+LAYER_PTR_FIELDS = 12
+# int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
+(LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
+ LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
+ LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN) = range(21)
+(LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN) = range(8)
+
+
+class LayerDesc(ctypes.Structure):
+    _fields_ = [("i", ctypes.c_int32 * LAYER_INT_FIELDS),
+                ("p", ctypes.POINTER(ctypes.c_float) * LAYER_PTR_FIELDS)]
+
+
+class HeadDesc(ctypes.Structure):
+    _fields_ = [("n_classes", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("pool_mode", ctypes.c_int32),
+                ("n_taps", ctypes.c_int32), ("rel_hidden", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+                ("cls_w", ctypes.POINTER(ctypes.c_float)), ("cls_b", ctypes.POINTER(ctypes.c_float)),
+                ("rel_w1", ctypes.POINTER(ctypes.c_float)), ("rel_b1", ctypes.POINTER(ctypes.c_float)),
+                ("rel_w2", ctypes.POINTER(ctypes.c_float)), ("rel_b2", ctypes.POINTER(ctypes.c_float))]
+
+
+@dataclass
+class ConvLaunch:
+    """One fused conv launch (host-side view, also used by tests to read the plan)."""
+    kernel: np.ndarray                 # [k, Cin, Cout] fp32 (stem: embedding already folded in)
+    bias: np.ndarray
+    dilation: int
+    pad_left: int
+    shrink: int                        # L_out = L_in - shrink
+    in_buf: int
+    out_buf: int
+    sc_buf: int = -1
+    scale1: np.ndarray | None = None
+    shift1: np.ndarray | None = None
+    act1: str | None = None
+    scale2: np.ndarray | None = None
+    shift2: np.ndarray | None = None
+    act2: str | None = None
+    tap_mode: int = 0
+    tap_slot: int = 0
+    tap_mean: np.ndarray | None = None
+    pool_mode: int = 0
+    mask_in: int = 0
+    mask_out: int = 0
+    sc_mask: int = -1
+    masking: int = 1
+    cum_shrink_in: int = 0
+    sc_const: np.ndarray | None = None
+    out_const: np.ndarray | None = None   # value of this launch's output at rows its mask zeroed
+    stage: int = 0                        # epilogue fill state while compiling
+
+
+@dataclass
+class Plan:
+    launches: list[ConvLaunch]
+    n_classes: int
+    feat_dim: int
+    pool_mode: int
+    n_taps: int
+    tap_width: int
+    cls_w: np.ndarray
+    cls_b: np.ndarray
+    rel: list[np.ndarray] | None
+    rel_hidden: int
+    total_shrink: int
+    flops_per_window_formula: Any = None
+    keep: list[Any] = field(default_factory=list)   # keeps ctypes-referenced arrays alive
+
+    def flops_per_window(self, lc: int, frames: int = 6, algorithmic_stem_cin: int | None = None) -> float:
+        """2 * frames * L_out * k * Cin * Cout summed over the convolutions.
+        `algorithmic_stem_cin` replaces the folded stem's Cin = 64 by the embedding width the
+        reference multiplies with."""
+        f = 0.0
+        for i, c in enumerate(self.launches):
+            k, cin, cout = c.kernel.shape
+            if i == 0 and algorithmic_stem_cin:
+                cin = algorithmic_stem_cin
+            f += 2.0 * frames * (lc - c.cum_shrink_in - c.shrink) * k * cin * cout
+        return f
+
+
+def _np32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + np.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+
+
+def _act_np(x, a):
+    if a == "gelu":
+        return _gelu(x)
+    if a == "relu":
+        return np.maximum(x, 0.0)
+    return x
+
+
+def _bn_fold(bn: dict[str, np.ndarray], eps: float):
+    scale = bn["gamma"].astype(np.float64) / np.sqrt(bn["var"].astype(np.float64) + eps)
+    shift = bn["beta"].astype(np.float64) - scale * bn["mean"].astype(np.float64)
+    return scale, shift
+
+
+def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
+    launches: list[ConvLaunch] = []
+    emb = weights.get("embedding")
+    # buffers: 0 = one-hot stem operand, 1 / 2 = ping-pong activations
+    cur_buf, cur_mask, cur_const = 0, 0, None
+    cum_shrink = 0
+    n_masks = 1
+    n_taps = 0
+    ch = 64
+
+    def new_mask():
+        nonlocal n_masks
+        n_masks += 1
+        return n_masks - 1
+
+    def other_buf(*used):
+        for b in (1, 2, 3):
+            if b not in used:
+                return b
+        raise AssertionError
+
+    def add_conv(kernel, bias, dilation, padding, use_masking, in_buf, in_mask, out_buf, sc_buf=-1, sc_mask=-1, sc_const=None):
+        nonlocal cum_shrink
+        k = kernel.shape[0]
+        span = dilation * (k - 1)
+        if padding == "same":
+            pad_left, shrink = span // 2, 0
+        else:
+            pad_left, shrink = 0, span
+        c = ConvLaunch(kernel=_np32(kernel), bias=_np32(bias), dilation=dilation, pad_left=pad_left, shrink=shrink,
+                       in_buf=in_buf, out_buf=out_buf, sc_buf=sc_buf, mask_in=in_mask, mask_out=new_mask(),
+                       sc_mask=sc_mask, masking=int(use_masking), cum_shrink_in=cum_shrink, sc_const=sc_const)
+        cum_shrink += shrink
+        launches.append(c)
+        return c
+
+    def finish(c: ConvLaunch):
+        """Fold bias into shift1 and compute the masked-row constant of the launch output."""
+        cout = c.kernel.shape[2]
+        s1 = np.ones(cout) if c.scale1 is None else c.scale1
+        t1 = np.zeros(cout) if c.shift1 is None else c.shift1
+        c.scale1 = _np32(s1)
+        c.shift1 = _np32(t1 + s1 * c.bias.astype(np.float64))     # acc*s1 + (t1 + s1*bias)
+        v = c.shift1.astype(np.float64)
+        if c.sc_buf >= 0:
+            v = v + (np.zeros(cout) if c.sc_const is None else c.sc_const.astype(np.float64))
+            c.sc_const = _np32(np.zeros(cout) if c.sc_const is None else c.sc_const)
+        v = _act_np(v, c.act1)
+        if c.scale2 is not None:
+            c.scale2, c.shift2 = _np32(c.scale2), _np32(c.shift2)
+            v = _act_np(v * c.scale2 + c.shift2, c.act2)
+        c.out_const = _np32(v)
+
+    cur: ConvLaunch | None = None
+    for layer, lw in zip(spec.layers, weights["layers"]):
+        cfg = layer.cfg
+        if layer.kind == "conv":
+            kernel = lw["kernel"]
+            if not launches:
+                # fold the embedding / dense-on-one-hot into the stem: W'[t] = E[1:65] @ W[t]
+                if emb is not None:
+                    table = emb[1:65] if spec.uses_token_input else emb[:64]
+                    kernel = np.einsum("ve,keo->kvo", table.astype(np.float64), kernel.astype(np.float64))
+                elif kernel.shape[1] != 64:
+                    raise NotImplementedError("stem conv without embedding must take the 64-wide one-hot")
+            bias = lw.get("bias") if cfg["use_bias"] else None
+            bias = np.zeros(kernel.shape[2], np.float32) if bias is None else bias
+            out_buf = other_buf(cur_buf)
+            cur = add_conv(kernel, bias, cfg["dilation"], cfg["padding"], cfg["use_masking"] and spec.use_masking,
+                           cur_buf, cur_mask, out_buf)
+            if cfg.get("activation"):
+                cur.act1, cur.stage = cfg["activation"], 2
+            cur_buf, cur_mask, ch = out_buf, cur.mask_out, kernel.shape[2]
+        elif layer.kind == "resblock":
+            masking = cfg["use_masking"] and spec.use_masking
+            for blk in lw["blocks"]:
+                x_buf, x_mask = cur_buf, cur_mask
+                if cur is not None and cur.out_const is None:
+                    finish(cur)
+                x_const = launches[-1].out_const if launches else None
+                h_buf = other_buf(x_buf)
+                c1 = add_conv(blk["conv1"]["kernel"], blk["conv1"]["bias"], cfg["dilation"], "same", masking,
+                              x_buf, x_mask, h_buf)
+                c1.scale1, c1.shift1 = _bn_fold(blk["bn1"], 1e-5)
+                c1.act1, c1.stage = cfg["activation"], 2
+                finish(c1)
+                # conv2 writes the block output in place over the block input (same rows, same thread)
+                c2 = add_conv(blk["conv2"]["kernel"], blk["conv2"]["bias"], cfg["dilation"], "same", masking,
+                              h_buf, c1.mask_out, x_buf, sc_buf=x_buf, sc_mask=x_mask if masking else -1,
+                              sc_const=x_const)
+                c2.scale1, c2.shift1 = _bn_fold(blk["bn2"], 1e-5)
+                c2.act1, c2.stage = cfg["activation"], 2
+                cur = c2
+                cur_buf, cur_mask = x_buf, c2.mask_out
+            ch = cfg["filters"]
+        elif layer.kind == "nmd":
+            if cur is None or cur.tap_mode != 0:
+                raise NotImplementedError("nmd layer placement cannot be fused (one tap per convolution)")
+            if cur.stage == 0:
+                cur.tap_mode = 1
+            elif cur.stage == 2:
+                cur.tap_mode = 2
+            else:
+                raise NotImplementedError("nmd layer between a norm and its activation cannot be fused")
+            cur.tap_slot, cur.tap_mean = n_taps, _np32(lw["moving_mean"])
+            n_taps += 1
+        elif layer.kind == "norm":
+            if cur is None:
+                raise NotImplementedError("norm before the first convolution")
+            s, t = _bn_fold(lw, cfg.get("epsilon", 1e-5))
+            if cur.stage == 0:
+                cur.scale1, cur.shift1, cur.stage = s, t, 1
+            elif cur.stage == 2 and cur.scale2 is None:
+                cur.scale2, cur.shift2, cur.stage = s, t, 3
+            else:
+                raise NotImplementedError("more element-wise layers after a convolution than the fused epilogue holds")
+        elif layer.kind == "act":
+            a = cfg.get("activation")
+            if cur is None:
+                raise NotImplementedError("activation before the first convolution")
+            if cur.stage in (0, 1):
+                cur.act1, cur.stage = a, 2
+            elif cur.stage == 3:
+                cur.act2, cur.stage = a, 4
+            else:
+                raise NotImplementedError("more element-wise layers after a convolution than the fused epilogue holds")
+    if cur is None:
+        raise NotImplementedError("model without convolutions")
+    for c in launches:
+        if c.out_const is None:
+            finish(c)
+    last = launches[-1]
+    last.pool_mode = 1 if spec.pooling == "max" else 2
+    last.out_buf = -1                    # the final feature map is only pooled: nothing reads it
+    tap_width = 0
+    for c in launches:
+        if c.tap_mode:
+            w = c.kernel.shape[2]
+            if tap_width and tap_width != w:
+                raise NotImplementedError("NMD taps of different widths")
+            tap_width = w
+    rel = None
+    rel_hidden = 0
+    if spec.reliability is not None and "reliability" in weights:
+        r = weights["reliability"]
+        if spec.reliability[0]["activation"] != "gelu":
+            raise NotImplementedError("reliability hidden activation other than gelu")
+        rel = [_np32(r[0]["kernel"]), _np32(r[0]["bias"]), _np32(r[1]["kernel"]), _np32(r[1]["bias"])]
+        rel_hidden = r[0]["kernel"].shape[1]
+    return Plan(launches=launches, n_classes=spec.n_classes, feat_dim=ch, pool_mode=last.pool_mode, n_taps=n_taps,
+                tap_width=tap_width, cls_w=_np32(weights["classifier"][0]["kernel"]),
+                cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel, rel_hidden=rel_hidden, total_shrink=cum_shrink)
+
+
+def _fptr(a: np.ndarray | None):
+    if a is None:
+        return ctypes.POINTER(ctypes.c_float)()
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def to_ctypes(plan: Plan):
+    """(LayerDesc array, HeadDesc) referencing the plan's arrays (kept alive by `plan.keep`)."""
+    arr = (LayerDesc * len(plan.launches))()
+    for d, c in zip(arr, plan.launches):
+        k, cin, cout = c.kernel.shape
+        vals = {LF_KIND: 1, LF_CIN: cin, LF_COUT: cout, LF_K: k, LF_DIL: c.dilation, LF_PAD_LEFT: c.pad_left,
+                LF_SHRINK: c.shrink, LF_IN_BUF: c.in_buf, LF_OUT_BUF: c.out_buf, LF_SC_BUF: c.sc_buf,
+                LF_ACT1: ACT[c.act1], LF_HAS_AFF2: int(c.scale2 is not None), LF_ACT2: ACT[c.act2],
+                LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
+                LF_MASK_OUT: c.mask_out, LF_SC_MASK: c.sc_mask, LF_MASKING: c.masking,
+                LF_CUM_SHRINK_IN: c.cum_shrink_in}
+        for i, v in vals.items():
+            d.i[i] = int(v)
+        ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,
+                LP_SHIFT2: c.shift2, LP_SC_CONST: c.sc_const, LP_TAP_MEAN: c.tap_mean}
+        for i, a in ptrs.items():
+            d.p[i] = _fptr(a)
+    h = HeadDesc()
+    h.n_classes, h.feat_dim, h.pool_mode = plan.n_classes, plan.feat_dim, plan.pool_mode
+    h.n_taps, h.rel_hidden = plan.n_taps, plan.rel_hidden
+    h.cls_w, h.cls_b = _fptr(plan.cls_w), _fptr(plan.cls_b)
+    if plan.rel is not None:
+        h.rel_w1, h.rel_b1, h.rel_w2, h.rel_b2 = (_fptr(a) for a in plan.rel)
+    plan.keep = [arr, h]
+    return arr, h

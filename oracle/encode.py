@@ -12,9 +12,10 @@ from __future__ import annotations
 
 import numpy as np
 
-# seqops/maps.py:3-68  (T,C,A,G-major order)
+# seqops/maps.py:3-68
 _BASES = "TCAG"
-CODONS = [a + b + c for a in _BASES for b in _BASES for c in _BASES]
+# second base outermost, then first base, then third (TTT TTC TTA TTG CTT ...)
+CODONS = [b + a + c for a in _BASES for b in _BASES for c in _BASES]
 CODON_ID = list(range(64))
 # seqops/maps.py:137-202 (AA_ID), :408-473 (MURPHY10_ID), :475-540 (PC5_ID); values copied as data
 AA_ID = [1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8, 8, 9, 9,

@@ -1,0 +1,172 @@
+"""Oracle (test infrastructure): the fragment model's forward pass on the CPU (torch).
+
+A layer-by-layer restatement of what the reference's SavedModel graph computes, written
+against the un-fused ModelSpec + raw weights so that it shares no code with the product's
+plan compiler (BN folding, embedding folding, masked-row constants) or kernels:
+
+  embedding / mask_zero ............. nnlib/builder.py:844-894
+  MaskedConv1D ...................... nnlib/v2/layers.py:1217-1280 (x*mask, conv, mask "any")
+  MaskedBatchNorm (inference) ....... nnlib/v2/layers.py:918-941  (no re-masking)
+  activation gelu (tanh approx.) .... nnlib/v2/layers.py:27-29; Keras 3 `gelu(approximate=True)`
+  ResidualBlock / Stack ............. nnlib/v2/layers.py:1882-1915, 2696-2704
+  NMDLayer .......................... nnlib/v2/nmd.py:43-77
+  MaskedGlobalMax/AvgPooling ........ nnlib/v2/layers.py:517-529, 460-480
+  heads ............................. nnlib/builder.py:589-596, 705-713
+
+Mask carried out of a ResidualBlock: Keras 3 `Layer._set_mask_metadata` keeps a mask that an
+inner layer already attached to the output tensor, so the block output carries conv2's
+(twice-dilated) mask, not the block input's mask.
+
+PARITY UNPINNED for logits: TensorFlow cannot be installed in the build container, so this
+restatement is checked only against the reference tests' mask / pooling known answers
+(tests/unit/test_mask_mode.py, test_masked_pooling.py) -- see tests/test_oracle_goldens.py.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def gelu_tanh(x):
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def _act(x, name):
+    if name == "gelu":
+        return gelu_tanh(x)
+    if name == "relu":
+        return torch.relu(x)
+    return x
+
+
+def _conv1d_tf(x, kernel, dilation, padding):
+    """x [N, L, Cin], kernel [k, Cin, Cout] (TF layout) -> [N, L', Cout] with TF padding rules."""
+    k = kernel.shape[0]
+    xt = x.transpose(1, 2)
+    if padding == "same":
+        total = dilation * (k - 1)
+        left = total // 2
+        xt = F.pad(xt, (left, total - left))
+    w = kernel.permute(2, 1, 0).contiguous()      # [Cout, Cin, k]
+    return F.conv1d(xt, w, dilation=dilation).transpose(1, 2)
+
+
+def masked_conv1d(x, mask, kernel, bias, dilation=1, padding="valid", activation=None, mask_mode="any"):
+    """layers.py:1217-1280.  x [B,6,L,C]; mask [B,6,L] float or None."""
+    b, f, l, c = x.shape
+    out_mask = None
+    if mask is not None:
+        x = x * mask.unsqueeze(-1)
+        k = kernel.shape[0]
+        ones = torch.ones(k, 1, 1, dtype=x.dtype)
+        mc = _conv1d_tf(mask.reshape(b * f, l, 1), ones, dilation, padding)
+        if mask_mode == "any":
+            om = mc > 0
+        elif mask_mode == "majority":
+            om = mc >= (k + 1) // 2
+        else:
+            om = mc == float(k)
+        out_mask = om.squeeze(-1).reshape(b, f, -1).to(x.dtype)
+    y = _conv1d_tf(x.reshape(b * f, l, c), kernel, dilation, padding)
+    if bias is not None:
+        y = y + bias
+    y = _act(y, activation)
+    return y.reshape(b, f, y.shape[1], y.shape[2]), out_mask
+
+
+def batchnorm(x, bn, eps=1e-5):
+    """layers.py:918-941 inference branch."""
+    inv = torch.rsqrt(bn["var"] + eps)
+    return bn["gamma"] * ((x - bn["mean"]) * inv) + bn["beta"]
+
+
+def nmd_vector(x, mask, moving_mean, eps=1e-5):
+    """nmd.py:52-77 inference branch."""
+    if mask is not None:
+        m = mask.unsqueeze(-1)
+        s = (x * m).sum(dim=(1, 2))
+        n = m.sum(dim=(1, 2)) + eps
+        mean = s / n
+    else:
+        mean = x.mean(dim=(1, 2))
+    return mean - moving_mean
+
+
+def masked_global_max(x, mask):
+    """layers.py:517-529."""
+    if mask is None:
+        return x.amax(dim=(1, 2))
+    m = mask.unsqueeze(-1)
+    pooled = torch.where(m > 0, x, torch.tensor(-1.0e9, dtype=x.dtype)).amax(dim=(1, 2))
+    has = m.amax(dim=(1, 2))
+    return torch.where(has > 0, pooled, torch.zeros_like(pooled))
+
+
+def masked_global_avg(x, mask):
+    """layers.py:460-480."""
+    if mask is None:
+        return x.mean(dim=(1, 2))
+    m = mask.unsqueeze(-1)
+    s = (x * m).sum(dim=(1, 2))
+    n = torch.clamp(m.sum(dim=(1, 2)), min=1e-7)
+    return torch.where(n > 0, s / n, torch.zeros_like(s))
+
+
+def _t(a, dtype):
+    return torch.as_tensor(np.asarray(a), dtype=dtype)
+
+
+def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str, np.ndarray]:
+    """tokens [B, 6, L] uint8 (0 = unknown / padding) -> prediction, embedding, nmd, reliability."""
+    tok = torch.as_tensor(np.asarray(tokens).astype(np.int64))
+    emb = weights.get("embedding")
+    if emb is not None:
+        e = _t(emb, dtype)
+        if spec.uses_token_input:
+            x = e[tok]                                        # Embedding(vocab 65, mask_zero)
+        else:
+            onehot = F.one_hot(tok, 65)[..., 1:].to(dtype)    # all-zero row for token 0
+            x = onehot @ e                                    # Dense(E, use_bias=False)
+    else:
+        x = F.one_hot(tok, 65)[..., 1:].to(dtype)
+    mask = (tok != 0).to(dtype) if spec.use_masking else None
+    nmds = []
+    for layer, lw in zip(spec.layers, weights["layers"]):
+        c = layer.cfg
+        if layer.kind == "conv":
+            m_in = mask if c["use_masking"] else None
+            x, mask = masked_conv1d(x, m_in, _t(lw["kernel"], dtype),
+                                    _t(lw["bias"], dtype) if c["use_bias"] else None,
+                                    c["dilation"], c["padding"], c.get("activation"))
+        elif layer.kind == "nmd":
+            nmds.append(nmd_vector(x, mask, _t(lw["moving_mean"], dtype)))
+        elif layer.kind == "norm":
+            x = batchnorm(x, {k: _t(v, dtype) for k, v in lw.items()}, c.get("epsilon", 1e-5))
+        elif layer.kind == "act":
+            x = _act(x, c.get("activation"))
+        elif layer.kind == "resblock":
+            for blk in lw["blocks"]:
+                m_in = mask if c["use_masking"] else None
+                h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
+                                      c["dilation"], "same")
+                h = _act(batchnorm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}), c["activation"])
+                h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
+                                       c["dilation"], "same")
+                h2 = batchnorm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()})
+                x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
+                mask = m2 if m_in is not None else mask
+        else:
+            raise NotImplementedError(layer.kind)
+    feat = masked_global_max(x, mask) if spec.pooling == "max" else masked_global_avg(x, mask)
+    cls = weights["classifier"][0]
+    out = {"prediction": feat @ _t(cls["kernel"], dtype) + _t(cls["bias"], dtype), "embedding": feat}
+    if nmds:
+        out["nmd"] = torch.cat(nmds, dim=-1)
+        if spec.reliability is not None and "reliability" in weights:
+            r = weights["reliability"]
+            h = _act(out["nmd"] @ _t(r[0]["kernel"], dtype) + _t(r[0]["bias"], dtype), spec.reliability[0]["activation"])
+            out["reliability"] = h @ _t(r[1]["kernel"], dtype) + _t(r[1]["bias"], dtype)
+    return {k: v.to(torch.float32).numpy() for k, v in out.items()}
