@@ -131,18 +131,25 @@ int64_t jg_model_workspace_bytes(jg_model* m);
 /* useful FLOPs of one window at frame length lc (2*L_out*6*k*Cin*Cout summed over convs) */
 double jg_model_flops_per_window(jg_model* m, int32_t lc);
 
+/* Per-conv-launch timing with CUDA events on the context stream (bench.py's roofline leg).
+ * jg_model_get_profile synchronises the stream and returns, per layer of the plan, the summed
+ * kernel milliseconds, the number of launches and the number of windows they covered. */
+int jg_model_set_profiling(jg_model* m, int32_t on);
+int jg_model_get_profile(jg_model* m, int32_t n_layers, double* ms, int64_t* launches, double* windows);
+
 /* ---- stage 4: per-contig aggregation ------------------------------------------------------
- * Windows of contig c are rows [d_offsets[c], d_offsets[c+1]) of d_logits [W][n_cls].
+ * Windows of contig c are rows [d_offsets[c], d_offsets[c+1]) of d_logits [n_windows][n_cls].
  * Outputs per contig: mean/var as IEEE half bits (sequential fp32 accumulation then fp16
  * rounding, the arithmetic of np.mean / np.var on a float32 [T, C] array), consensus =
  * first-max argmax of the half means, per-class window counts of the per-window argmax,
- * entropy / energy means (half bits), fraction of windows with sigmoid(rel) > 0.5 (fp32;
- * NaN when d_rel is NULL), per-window argmax. */
+ * entropy / energy means (half bits), number of windows with sigmoid(rel) > 0.5 (-1 when d_rel
+ * is NULL; the host divides by the window count in double like np.mean), per-window argmax. */
 int jg_aggregate_contigs(jg_ctx* ctx, const float* d_logits, const float* d_rel,
-                         const int64_t* d_offsets, int64_t n_contigs, int32_t n_cls,
+                         const int64_t* d_offsets, int64_t n_contigs, int64_t n_windows,
+                         int32_t n_cls,
                          uint16_t* d_mean_h, uint16_t* d_var_h, int32_t* d_consensus,
                          int32_t* d_counts, uint16_t* d_entropy_h, uint16_t* d_energy_h,
-                         float* d_rel_frac, int32_t* d_frag_pred);
+                         int32_t* d_rel_pos, int32_t* d_frag_pred);
 
 /* ---- stage 4b: prophage score smoothing + segmentation -------------------------------------
  * jg_smooth_scores: row softmax of logits (float64), then per class the width-`box` box SUM with

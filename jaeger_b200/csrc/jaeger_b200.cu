@@ -94,6 +94,13 @@ struct jg_model {
   const int** tap_count_ptrs = nullptr;
   int* err = nullptr;
   int64_t ws_bytes = 0;
+  // per-conv-launch CUDA-event timing (jg_model_set_profiling)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // pending (start, stop) pairs
+  std::vector<int> prof_layer;
+  std::vector<double> prof_ms;        // accumulated per layer
+  std::vector<int64_t> prof_launches;
+  std::vector<double> prof_rows;      // accumulated rows (tiles*128) per layer
 };
 
 namespace {
@@ -387,6 +394,9 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
   }
   JG_CUDA(cudaMalloc(&m->err, 4));
   JG_CUDA(cudaMemset(m->err, 0, 4));
+  m->prof_ms.assign(m->layers.size(), 0.0);
+  m->prof_launches.assign(m->layers.size(), 0);
+  m->prof_rows.assign(m->layers.size(), 0.0);
   *out = m;
   return 0;
 }
@@ -493,9 +503,21 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.pool_mode = L.f[LF_POOL_MODE];
     p.err = m->err;
     p.dbg = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (m->profiling) {
+      JG_CUDA(cudaEventCreate(&ev0));
+      JG_CUDA(cudaEventCreate(&ev1));
+      JG_CUDA(cudaEventRecord(ev0, st));
+    }
     cudaError_t e = use_ref ? jg::launch_conv_ref(p, st) : jg::launch_conv_tc(p, ctx->num_sms, st);
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+    if (m->profiling) {
+      JG_CUDA(cudaEventRecord(ev1, st));
+      m->prof_events.emplace_back(ev0, ev1);
+      m->prof_layer.push_back(static_cast<int>(&L - m->layers.data()));
+      m->prof_rows[&L - m->layers.data()] += static_cast<double>(n_windows);
+    }
   }
 
   jg::HeadParams hp{};
@@ -526,18 +548,46 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   return 0;
 }
 
+int jg_model_set_profiling(jg_model* m, int32_t on) {
+  m->profiling = on != 0;
+  m->prof_ms.assign(m->layers.size(), 0.0);
+  m->prof_launches.assign(m->layers.size(), 0);
+  m->prof_rows.assign(m->layers.size(), 0.0);
+  for (auto& pr : m->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  m->prof_events.clear();
+  m->prof_layer.clear();
+  return 0;
+}
+
+int jg_model_get_profile(jg_model* m, int32_t n_layers, double* ms, int64_t* launches, double* windows) {
+  JG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  for (size_t i = 0; i < m->prof_events.size(); ++i) {
+    float t = 0.0f;
+    JG_CUDA(cudaEventElapsedTime(&t, m->prof_events[i].first, m->prof_events[i].second));
+    m->prof_ms[m->prof_layer[i]] += t;
+    m->prof_launches[m->prof_layer[i]] += 1;
+    cudaEventDestroy(m->prof_events[i].first);
+    cudaEventDestroy(m->prof_events[i].second);
+  }
+  m->prof_events.clear();
+  m->prof_layer.clear();
+  for (int l = 0; l < n_layers && l < static_cast<int>(m->layers.size()); ++l) {
+    ms[l] = m->prof_ms[l];
+    launches[l] = m->prof_launches[l];
+    windows[l] = m->prof_rows[l];
+  }
+  return 0;
+}
+
 // ---- stage 4 -----------------------------------------------------------------------------------
 int jg_aggregate_contigs(jg_ctx* ctx, const float* d_logits, const float* d_rel, const int64_t* d_offsets,
-                         int64_t n_contigs, int32_t n_cls, uint16_t* d_mean_h, uint16_t* d_var_h,
+                         int64_t n_contigs, int64_t n_windows, int32_t n_cls, uint16_t* d_mean_h, uint16_t* d_var_h,
                          int32_t* d_consensus, int32_t* d_counts, uint16_t* d_entropy_h, uint16_t* d_energy_h,
-                         float* d_rel_frac, int32_t* d_frag_pred) {
+                         int32_t* d_rel_pos, int32_t* d_frag_pred) {
   if (n_contigs <= 0) return 0;
   if (n_cls < 1 || n_cls > 32) return fail("n_cls must be in [1, 32]");
   JG_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  long long n_windows = 0;
-  JG_CUDA(cudaMemcpyAsync(&n_windows, d_offsets + n_contigs, 8, cudaMemcpyDeviceToHost, st));
-  JG_CUDA(cudaStreamSynchronize(st));
   if (n_windows <= 0) return 0;
   float* ent = nullptr;
   double* en = nullptr;
@@ -549,7 +599,7 @@ int jg_aggregate_contigs(jg_ctx* ctx, const float* d_logits, const float* d_rel,
       d_logits, off, n_contigs, n_cls, reinterpret_cast<__half*>(d_mean_h), reinterpret_cast<__half*>(d_var_h));
   jg::contig_summary_kernel<<<grid_for(n_contigs * 32, 256, ctx->num_sms, 16), 256, 0, st>>>(
       reinterpret_cast<const __half*>(d_mean_h), d_frag_pred, ent, en, d_rel, off, n_contigs, n_cls, d_consensus, d_counts,
-      reinterpret_cast<__half*>(d_entropy_h), reinterpret_cast<__half*>(d_energy_h), d_rel_frac);
+      reinterpret_cast<__half*>(d_entropy_h), reinterpret_cast<__half*>(d_energy_h), d_rel_pos);
   ctx->launches += 3;
   JG_CUDA(cudaGetLastError());
   JG_CUDA(cudaFreeAsync(ent, st));

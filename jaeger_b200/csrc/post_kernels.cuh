@@ -79,7 +79,7 @@ __global__ void contig_summary_kernel(const __half* __restrict__ mean_h, const i
                                       const float* __restrict__ rel, const long long* __restrict__ offsets,
                                       long long n_contigs, int n_cls, int* __restrict__ consensus,
                                       int* __restrict__ counts, __half* __restrict__ entropy_h,
-                                      __half* __restrict__ energy_h, float* __restrict__ rel_frac) {
+                                      __half* __restrict__ energy_h, int* __restrict__ rel_pos_out) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -126,7 +126,7 @@ __global__ void contig_summary_kernel(const __half* __restrict__ mean_h, const i
       entropy_h[c] = __float2half_rn(static_cast<float>(ent / t));
       const double denom = (n_cls == 2) ? t : t * n_cls;
       energy_h[c] = __double2half(en / denom);
-      if (rel_frac) rel_frac[c] = rel ? static_cast<float>(static_cast<double>(rel_pos) / t) : nanf("");
+      if (rel_pos_out) rel_pos_out[c] = rel ? rel_pos : -1;
     }
   }
 }
@@ -150,12 +150,11 @@ __global__ void smooth_scores_kernel(const float* __restrict__ logits, const lon
         const long long lo = i + (box - 1) / 2 - (box - 1), hi = i + (box - 1) / 2;
         for (long long j = lo; j <= hi; ++j) {
           if (j < 0 || j >= n) continue;
+          // prophages.py:126: np.exp(value) / np.sum(np.exp(value), axis=1) in the logits' float32
           const float* z = logits + (b + j) * n_cls;
-          double m = z[0];
-          for (int q = 1; q < n_cls; ++q) m = fmax(m, static_cast<double>(z[q]));
-          double den = 0.0;
-          for (int q = 0; q < n_cls; ++q) den += exp(static_cast<double>(z[q]) - m);
-          acc += exp(static_cast<double>(z[k]) - m) / den;
+          float den = 0.0f;
+          for (int q = 0; q < n_cls; ++q) den = __fadd_rn(den, expf(z[q]));
+          acc += static_cast<double>(__fdiv_rn(expf(z[k]), den));
         }
         out[(b + i) * n_cls + k] = acc;
       }

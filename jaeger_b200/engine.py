@@ -235,6 +235,51 @@ class B200Engine:
                 out["nmd"][b:e].data_ptr() if "nmd" in out else None, int(self.use_ref_kernels)))
         return out
 
+    def aggregate(self, logits: torch.Tensor, rel: torch.Tensor | None, offsets: torch.Tensor) -> dict[str, torch.Tensor]:
+        """Stage 4 on the device: per-contig reductions of window logits (collect.py:293-403).
+        offsets [n_contigs + 1] int64: windows of contig c are rows offsets[c]:offsets[c+1]."""
+        nc = offsets.numel() - 1
+        w, ncls = logits.shape
+        out = {"pred_sum": self._empty((nc, ncls), torch.float16), "pred_var": self._empty((nc, ncls), torch.float16),
+               "consensus": self._empty((nc,), torch.int32), "per_class_counts": self._empty((nc, ncls), torch.int32),
+               "entropy": self._empty((nc,), torch.float16), "energy": self._empty((nc,), torch.float16),
+               "rel_pos": self._empty((nc,), torch.int32), "frag_pred": self._empty((w,), torch.int32)}
+        check(lib.jg_aggregate_contigs(
+            self.ctx.handle, logits.data_ptr(), rel.data_ptr() if rel is not None else None, offsets.data_ptr(), nc,
+            w, ncls, out["pred_sum"].data_ptr(), out["pred_var"].data_ptr(), out["consensus"].data_ptr(),
+            out["per_class_counts"].data_ptr(), out["entropy"].data_ptr(), out["energy"].data_ptr(),
+            out["rel_pos"].data_ptr(), out["frag_pred"].data_ptr()))
+        return out
+
+    def set_profiling(self, on: bool) -> None:
+        check(lib.jg_model_set_profiling(self.model, int(bool(on))))
+
+    def get_profile(self):
+        """Per conv launch of the plan: (summed kernel ms, launches, windows covered)."""
+        n = len(self.plan.launches)
+        ms = (ctypes.c_double * n)(); cnt = (ctypes.c_int64 * n)(); win = (ctypes.c_double * n)()
+        check(lib.jg_model_get_profile(self.model, n, ms, cnt, win))
+        return [(ms[i], cnt[i], win[i]) for i in range(n)]
+
+    def classify_long(self, ascii_dev: torch.Tensor, lens: np.ndarray, fsize: int, stride: int):
+        """pack -> plan -> encode -> forward -> aggregate for contigs already in device memory
+        (long pass only).  Returns (per-contig dict of device tensors, n_windows, n_contigs_with_windows)."""
+        offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        codes, valid = self.pack(ascii_dev)
+        contig, start, nb, ordinal, last = self.plan_windows(lens, fsize, stride)
+        w = len(contig)
+        if w == 0:
+            return {}, 0, 0
+        lc = self.codons_per_frame(fsize, fsize)
+        tokens, counts, skew = self.encode(codes, valid, self._h2d(offsets[contig] + start), self._h2d(nb), fsize, lc)
+        out = self.forward(tokens, torch.full((w,), lc, dtype=torch.int32, device=self.tdev), lc)
+        ends = np.flatnonzero(last) + 1
+        woff = np.concatenate([[0], ends]).astype(np.int64)
+        agg = self.aggregate(out["prediction"], out.get("reliability"), self._h2d(woff))
+        agg["gc_counts"] = counts
+        return agg, w, len(ends)
+
     # ---- the engine contract --------------------------------------------------------------------
     def predict(self, dataset, no_progress: bool = False) -> dict[str, np.ndarray]:
         if isinstance(dataset, WindowSource):

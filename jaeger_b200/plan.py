@@ -190,13 +190,25 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             kernel = lw["kernel"]
             if not launches:
                 # fold the embedding / dense-on-one-hot into the stem: W'[t] = E[1:65] @ W[t]
+                extra_bias = None
                 if emb is not None:
-                    table = emb[1:65] if spec.uses_token_input else emb[:64]
-                    kernel = np.einsum("ve,keo->kvo", table.astype(np.float64), kernel.astype(np.float64))
+                    table = (emb[1:65] if spec.uses_token_input else emb[:64]).astype(np.float64)
+                    if spec.uses_token_input and not (cfg["use_masking"] and spec.use_masking):
+                        # Embedding without mask consumption: token 0 is a real row E[0].  Write
+                        # x = onehot @ (E[1:] - E[0]) + E[0]; the constant part is a bias of the
+                        # (VALID) stem conv.
+                        if cfg["padding"] != "valid":
+                            raise NotImplementedError("un-masked Embedding input needs a VALID stem conv")
+                        e0 = emb[0].astype(np.float64)
+                        table = table - e0
+                        extra_bias = np.einsum("e,keo->o", e0, kernel.astype(np.float64))
+                    kernel = np.einsum("ve,keo->kvo", table, kernel.astype(np.float64))
                 elif kernel.shape[1] != 64:
                     raise NotImplementedError("stem conv without embedding must take the 64-wide one-hot")
             bias = lw.get("bias") if cfg["use_bias"] else None
             bias = np.zeros(kernel.shape[2], np.float32) if bias is None else bias
+            if not launches and extra_bias is not None:
+                bias = bias.astype(np.float64) + extra_bias
             out_buf = other_buf(cur_buf)
             cur = add_conv(kernel, bias, cfg["dilation"], cfg["padding"], cfg["use_masking"] and spec.use_masking,
                            cur_buf, cur_mask, out_buf)

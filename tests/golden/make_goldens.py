@@ -1,0 +1,212 @@
+"""Generates the golden vectors under tests/golden/ by importing the REFERENCE's own Python
+modules from /root/reference/src (build container only; the GPU box never runs this).
+
+Third-party native modules the reference imports at module top but which are not installed
+here (pyfastx, pydustmasker, parasail, ruptures, kneed, matplotlib, pycirclize, tensorflow)
+are replaced by inert stubs; only reference functions that are pure Python / NumPy / numba
+are executed:
+
+  jaeger.seqops.io._window_indices, fragment_generator (dustmask=False; FASTA iteration through
+      a stub with pyfastx's (name, sequence) record semantics)
+  jaeger.dataops.convert._process_batch_numba   (the reference's TF-free six-frame encoder)
+  jaeger.postprocess.collect.pred_to_dict, generate_summary
+  jaeger.postprocess.prophages.logits_to_df_v2
+  jaeger.postprocess.helpers.merge_overlapping_ranges
+
+usage:  python tests/golden/make_goldens.py
+"""
+from __future__ import annotations
+
+import json
+import sys
+import types
+import zlib
+from pathlib import Path
+
+import numpy as np
+
+REF = Path("/root/reference/src")
+OUT = Path(__file__).resolve().parent
+sys.path.insert(0, str(REF))
+sys.path.insert(0, str(OUT.parent.parent))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+class _Fasta:
+    """pyfastx.Fasta(path, build_index=False) iteration: (name, sequence) tuples, name = header up
+    to the first whitespace, sequence = lines joined."""
+
+    def __init__(self, path, build_index=False):
+        self.path = path
+
+    def __iter__(self):
+        name, chunks = None, []
+        with open(self.path) as fh:
+            for line in fh:
+                if line.startswith(">"):
+                    if name is not None:
+                        yield name, "".join(chunks)
+                    name, chunks = line[1:].split()[0], []
+                elif name is not None:
+                    chunks.append(line.strip())
+        if name is not None:
+            yield name, "".join(chunks)
+
+
+_stub("pyfastx", Fasta=_Fasta)
+_stub("pydustmasker", DustMasker=None)
+_stub("parasail")
+_stub("ruptures")
+_stub("kneed", KneeLocator=None)
+_stub("pycirclize", Circos=None)
+mpl = _stub("matplotlib")
+_stub("matplotlib.pyplot")
+_stub("matplotlib.patches", Patch=None)
+_stub("matplotlib.lines", Line2D=None)
+
+
+def main():
+    import pandas as pd
+    from jaeger.seqops import io as rio
+    from jaeger.dataops import convert as rconv
+    from jaeger.postprocess import collect as rcollect
+    from jaeger.postprocess import helpers as rhelp
+    from jaeger.postprocess import prophages as rpro
+
+    # ---- window indices ---------------------------------------------------------------------
+    cases = []
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        fs = int(rng.choice([500, 1500, 2000, 2048]))
+        L = int(rng.integers(fs, fs * 14))
+        st = int(rng.choice([fs, fs // 2, 1500, 700]))
+        dyn = bool(rng.integers(0, 2))
+        thr = float(rng.choice([10.0, 3.0, 1.5]))
+        cases.append(dict(seqlen=L, fsize=fs, stride=st, dyn=dyn, thr=thr,
+                          idx=rio._window_indices(L, fs, st, dyn, thr)))
+    # the reference tests' own known answers (tests/unit/test_seqops_io.py)
+    for L, fs, st, dyn, thr in [(3400, 2000, 2000, False, 10.0), (3400, 2000, 2000, True, 10.0),
+                                (3999, 2000, 2000, True, 10.0), (6000, 2000, 2000, True, 10.0)]:
+        cases.append(dict(seqlen=L, fsize=fs, stride=st, dyn=dyn, thr=thr, idx=rio._window_indices(L, fs, st, dyn, thr)))
+    (OUT / "window_indices.json").write_text(json.dumps(cases))
+
+    # ---- a synthetic FASTA of our own (travels to the GPU box; the reference's test FASTA does not)
+    rng = np.random.default_rng(11)
+    syn = OUT / "synthetic_contigs.fasta"
+    with open(syn, "w") as fh:
+        for i, L in enumerate([9275, 12001, 44776, 2000, 1999, 650, 20480, 3400, 15000, 137, 2048, 5000]):
+            seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+            if i == 2:
+                seq[3000:3100] = ord("N")
+            if i == 6:
+                seq[100:700] |= 0x20                       # lower-case stretch
+                seq[[5, 900, 4000]] = [ord("R"), ord("y"), ord("K")]
+            name = f"syn{i}" + (",with,commas" if i == 7 else "") + " description text"
+            fh.write(f">{name}\n")
+            s_ = seq.tobytes().decode()
+            for a in range(0, L, 80):
+                fh.write(s_[a:a + 80] + "\n")
+
+    def frag_rows(path, fs, st, min_len, max_len=None, dyn=False):
+        rows = []
+        for s in rio.fragment_generator(str(path), fragsize=fs, stride=st, dustmask=False, min_len=min_len,
+                                        max_len=max_len, dynamic_stride=dyn):
+            f = s.split(",")
+            rows.append([zlib.crc32(f[0].encode()), len(f[0])] + f[1:])
+        return rows
+
+    fragsyn = {}
+    for fs, st, min_len, max_len, dyn in [(2000, 1500, None, None, False), (2048, 2048, None, None, False),
+                                          (2000, 1500, 500, 1999, False), (500, 500, None, None, False),
+                                          (2000, 2000, None, None, True)]:
+        fragsyn[f"{fs}_{st}_{min_len}_{max_len}_{int(dyn)}"] = frag_rows(syn, fs, st, min_len, max_len, dyn)
+    (OUT / "fragments_synthetic.json").write_text(json.dumps(fragsyn))
+
+    # ---- fragment_generator on the reference's health FASTA ------------------------------------
+    fasta = REF / "jaeger" / "data" / "test" / "test_contigs.fasta"
+    frag = {}
+    for fs, st, min_len in [(2000, 1500, None), (2048, 2048, None), (2000, 1500, 500), (12000, 4000, 9000)]:
+        rows = []
+        for s in rio.fragment_generator(str(fasta), fragsize=fs, stride=st, dustmask=False, min_len=min_len,
+                                        max_len=None):
+            f = s.split(",")
+            rows.append([zlib.crc32(f[0].encode()), len(f[0])] + f[1:])
+        frag[f"{fs}_{st}_{min_len}"] = rows
+    (OUT / "fragments_test_contigs.json").write_text(json.dumps(frag))
+
+    # ---- six-frame tokens from the reference's numba encoder ------------------------------------
+    recs = list(_Fasta(str(syn)))
+    seqs = []
+    for name, seq in recs:
+        seq = seq.upper()
+        for st in (0, 1500, 3001):
+            if st + 2000 <= len(seq):
+                seqs.append(seq[st:st + 2000])
+    # add ambiguity codes the way real assemblies carry them
+    s = list(seqs[0]); s[100:140] = "N" * 40; s[777] = "R"; seqs.append("".join(s))
+    codon_lut, ascii_lut, comp_lut = rconv._build_numba_lookups()
+    arr = np.zeros((len(seqs), 2000), dtype=np.uint8)
+    for i, q in enumerate(seqs):
+        arr[i] = np.frombuffer(q.encode(), dtype=np.uint8)
+    tok = rconv._process_batch_numba(arr, np.full(len(seqs), 2000, np.int64), 2000, 665, codon_lut, comp_lut, ascii_lut)
+    np.savez_compressed(OUT / "tokens_2000.npz", seqs=np.array(seqs), tokens=tok.astype(np.uint8))
+
+    # ---- pred_to_dict / generate_summary ---------------------------------------------------------
+    rng = np.random.default_rng(5)
+    n_win = [1, 2, 7, 29, 3, 140, 1, 12]
+    W = sum(n_win)
+    pred = (rng.normal(0, 2.0, (W, 6))).astype(np.float32)
+    pred[5:9] = pred[4]                                   # exact ties between windows
+    rel = rng.normal(0, 1.5, (W, 1)).astype(np.float32)
+    meta = {f"meta_{i}": [] for i in range(10)}
+    for ci, n in enumerate(n_win):
+        for j in range(n):
+            g, c, a, t = (int(x) for x in rng.integers(300, 600, 4))
+            skew = round((g - c) / (g + c), 2)
+            for i, v in enumerate([f"contig___{ci}", j * 1500, int(j == n - 1), j, 2000 + 1500 * (n - 1), g, c, a, t,
+                                   f"{skew: .3f}"]):
+                meta[f"meta_{i}"].append(str(v).encode())
+    y = {"prediction": pred, "reliability": rel, **{k: np.array(v) for k, v in meta.items()}}
+    classes = ["bacteria", "phage", "eukarya", "archaea", "plasmid", "virus"]
+    class_map = {"num_classes": 6, "class": classes, "index": list(range(6))}
+    rep = pd.DataFrame({"contig_id": [f"contig___{i}" for i in range(len(n_win))],
+                        "terminal_repeats": [None] * len(n_win), "repeat_length": [None] * len(n_win)})
+    data, data_full = rcollect.pred_to_dict(y, fsize=2000, class_map=class_map, term_repeats=rep)
+    df = rcollect.generate_summary(data, labels=classes, indices=list(range(6)))
+    np.savez_compressed(
+        OUT / "pred_to_dict.npz", prediction=pred, reliability=rel,
+        **{k: np.array(v) for k, v in meta.items()},
+        pred_sum=data["pred_sum"], pred_var=data["pred_var"], consensus=data["consensus"],
+        per_class_counts=np.array([[d[k] for k in range(6)] for d in data["per_class_counts"]]),
+        ood=data["ood"], entropy=data["entropy"], energy=data["energy"], host_contam=data["host_contam"],
+        prophage_contam=data["prophage_contam"], frag_pred=np.concatenate(data["frag_pred"]),
+        gc_mean=np.array([np.mean(x) for x in data["gc"]]), ns_mean=np.array([np.mean(x) for x in data["ns"]]))
+    df.to_csv(OUT / "summary.tsv", sep="\t", index=False, float_format="%.3f")
+
+    # ---- prophage score smoothing ------------------------------------------------------------------
+    rng = np.random.default_rng(9)
+    T = 400
+    logits = rng.normal(0, 1.5, (T, 6)).astype(np.float32)
+    logits[120:160, 1] += 6.0
+    gsk = rng.normal(0, 0.1, T).round(2)
+    out = rpro.logits_to_df_v2(class_map, {"lc": 1000, "stride": 1500, "fsize": 2000}, np.array(["g1"]), [logits],
+                               np.array([1500 * (T - 1) + 2000]), [gsk.copy()], [np.full(T, 0.5)])
+    t = out["g1"][0]
+    np.savez_compressed(OUT / "smooth.npz", logits=logits, gc_skew_in=gsk, smoothed=t[classes].to_numpy(),
+                        x=t["length"].to_numpy(), gc_skew=t["gc_skew"].to_numpy())
+    merges = []
+    for arr_ in ([[0, 3], [2, 5], [8, 9]], [[1, 2]], [[0, 10], [2, 3], [11, 12], [12, 20]]):
+        merges.append(dict(inp=arr_, out=[list(map(int, r)) for r in rhelp.merge_overlapping_ranges(np.array(arr_))]))
+    (OUT / "merge_ranges.json").write_text(json.dumps(merges))
+    print("goldens written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+"""CPU tests of the host logic: project.yaml parsing, the fused-launch plan compiler (against
+the un-fused oracle), the C-ABI surface and the host window planner."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from jaeger_b200 import _cabi
+from jaeger_b200.engine import B200Engine
+from jaeger_b200.modelspec import count_params, init_random, parse_project, standin_1p4m_config, string_processor_config
+from jaeger_b200.plan import compile_plan, to_ctypes
+from oracle import forward as ofw
+from tests.plan_interp import run_plan
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_CFG = Path("/root/reference/train_config")
+
+
+def small_config(pooling="max", use_masking=True, reliability=True):
+    cfg = standin_1p4m_config()
+    m = cfg["model"]
+    m["use_masking"] = use_masking
+    m["representation_learner"]["pooling"] = pooling
+    m["representation_learner"]["hidden_layers"] = m["representation_learner"]["hidden_layers"][:12]   # stem + 2 stacks
+    if reliability:
+        m["reliability_model"]["input_shape"] = 384
+    else:
+        del m["reliability_model"]
+    return cfg
+
+
+def test_standin_matches_survey_parameter_count():
+    spec = parse_project(standin_1p4m_config())
+    w = init_random(spec, 0)
+    assert count_params(spec, w) == 1_447_296                       # SURVEY.md 8d config 2 ("1.4M")
+    plan = compile_plan(spec, w)
+    assert len(plan.launches) == 17 and plan.n_taps == 5
+    assert plan.flops_per_window(665, algorithmic_stem_cin=128) == pytest.approx(11.27e9, rel=1e-3)
+
+
+@pytest.mark.skipif(not REF_CFG.exists(), reason="reference checkout not mounted")
+def test_reference_train_config_parses():
+    cfg = yaml.safe_load((REF_CFG / "nn_config_1500bp_nmd_merge_6_class_brain.yaml").read_text())
+    spec = parse_project(cfg)
+    sp = string_processor_config(spec)
+    assert sp["seq_onehot"] is False and sp["codon_depth"] == 1 and sp["vocab_size"] == 65 and sp["ngram_width"] == 3
+    w = init_random(spec, 0)
+    plan = compile_plan(spec, w)
+    assert len(plan.launches) == 13 and plan.n_taps == 4           # stem + 3 stacks of 2 blocks
+    assert plan.flops_per_window(665, algorithmic_stem_cin=128) == pytest.approx(8.68e9, rel=2e-3)
+
+
+def _tokens(seed, b, lc, n_frac=0.02, pad_from=None):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(1, 65, size=(b, 6, lc)).astype(np.uint8)
+    t[rng.random(t.shape) < n_frac] = 0
+    t[0, :, 40:75] = 0                     # a long unknown run (survives several 'any' dilations)
+    if pad_from is not None:
+        t[1, :, pad_from:] = 0             # right padding like a short contig in a padded batch
+    return t
+
+
+@pytest.mark.parametrize("pooling,masking,rel", [("max", True, True), ("average", True, False), ("max", False, True)])
+def test_plan_equals_unfused_oracle(pooling, masking, rel):
+    spec = parse_project(small_config(pooling, masking, rel))
+    w = init_random(spec, 3)
+    # non-trivial biases / BN betas so the masked-row constants matter
+    rng = np.random.default_rng(1)
+    for lw in w["layers"]:
+        for part in ([lw] if "blocks" not in lw else [p for b in lw["blocks"] for p in b.values()]):
+            for k in ("bias", "beta"):
+                if k in part:
+                    part[k] = rng.normal(0, 0.3, part[k].shape).astype(np.float32)
+    tok = _tokens(0, 3, 120, pad_from=70)
+    ref = ofw.forward(spec, w, tok, dtype=torch.float64)
+    got = run_plan(compile_plan(spec, w), tok)
+    for k in ref:
+        assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
+
+
+def test_unsupported_layers_fail_loudly():
+    cfg = small_config()
+    cfg["model"]["representation_learner"]["hidden_layers"].insert(1, {"name": "masked_bilstm", "config": {"units": 8}})
+    with pytest.raises(NotImplementedError):
+        parse_project(cfg)
+    cfg = small_config()
+    cfg["model"]["representation_learner"]["hidden_layers"][0]["config"]["mask_mode"] = "strict"
+    with pytest.raises(NotImplementedError):
+        parse_project(cfg)
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = (ROOT / "include" / "jaeger_b200.h").read_text()
+    declared = set(re.findall(r"\b(jg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"jg_ctx", "jg_model"}
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_cabi.LIB_PATH))
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_cabi.EXPORTED), declared ^ set(_cabi.EXPORTED)
+    assert lib.jg_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    with pytest.raises(_cabi.JaegerB200Error):
+        _cabi.Context(0)
+    with pytest.raises(_cabi.JaegerB200Error):
+        B200Engine(spec=parse_project(small_config()))
+
+
+def test_host_window_planner_matches_reference_goldens():
+    cases = json.loads((ROOT / "tests" / "golden" / "window_indices.json").read_text())
+    for c in cases:
+        contig, start, nb, ordinal, last = B200Engine.plan_windows(
+            np.array([c["seqlen"]]), c["fsize"], c["stride"], c["dyn"], c["thr"])
+        assert start.tolist() == c["idx"], c
+        assert ordinal.tolist() == list(range(len(c["idx"]))) and last.tolist() == [0] * (len(c["idx"]) - 1) + [1]
+        assert (nb == c["fsize"]).all()
+
+
+def test_host_window_planner_two_pass_and_ragged():
+    lens = np.array([5000, 1999, 0, 650, 2000, 137, 100000], dtype=np.int64)
+    contig, start, nb, ordinal, last = B200Engine.plan_windows(lens, 2000, 1500)
+    assert contig.tolist() == [0, 0, 0, 4] + [6] * 66                   # range(0, L-1999, 1500)
+    assert start[:4].tolist() == [0, 1500, 3000, 0]
+    c2, s2, nb2, o2, l2 = B200Engine.plan_windows(lens, 2000, 1500, min_len=500, max_len=1999, short_pass=True)
+    assert c2.tolist() == [1, 3] and nb2.tolist() == [1999, 650] and l2.tolist() == [1, 1] and s2.tolist() == [0, 0]
+    # empty input
+    c3, *_ = B200Engine.plan_windows(np.zeros(0, dtype=np.int64), 2000, 1500)
+    assert len(c3) == 0
