@@ -256,7 +256,8 @@ def run_b200(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)
     value = tot_bases / 1e6 / (ms / 1e3)
     # ---- roofline of the dominant kernel: the k5 d3 residual conv launches ---------------------
     plan = eng.plan
@@ -276,7 +277,9 @@ def run_b200(args):
     summ = ROOT / "profiles" / "ncu_summary_r1.json"
     if summ.exists():
         try:
-            traffic = json.loads(summ.read_text()).get("conv_tc_dram_bytes_per_launch")
+            per_window = json.loads(summ.read_text()).get("conv_tc_dram_bytes_per_window_mean")
+            # the ncu capture is per window of one launch; scale to this run's average launch
+            traffic = per_window * (sum(p[2] for p in prof[1:]) / max(1.0, res_launch)) if per_window else None
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": "jg::tc::conv_tc_kernel (k5 d3 C128 residual convs, 16 of 17 conv launches)",
@@ -301,9 +304,7 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    eng.close()
-    del pinned, host_batches
-    torch.cuda.synchronize()
+    sys.stdout.flush()
     os._exit(0)      # skip interpreter-exit destructors that race the CUDA context teardown
 
 
