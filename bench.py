@@ -40,9 +40,8 @@ WORKLOAD = ("configs[1]: jaeger 1.4M-parameter fragment architecture (declared s
             "fsize 2000 stride 1500")
 
 
-def synth_batch(seed: int, target_bases: int):
-    """Contig lengths ~ U{2000..50000} until the sum reaches target_bases; i.i.d. uniform bases;
-    0.1 % of contigs get one run of 50-500 N."""
+def synth_lens(seed: int, target_bases: int) -> np.ndarray:
+    """Contig lengths ~ U{2000..50000} until the sum reaches target_bases."""
     rng = np.random.default_rng(seed)
     lens = []
     tot = 0
@@ -50,14 +49,25 @@ def synth_batch(seed: int, target_bases: int):
         n = int(rng.integers(2000, 50001))
         lens.append(n)
         tot += n
-    lens = np.array(lens, dtype=np.int64)
+    return np.array(lens, dtype=np.int64)
+
+
+def synth_bases(seed: int, lens: np.ndarray) -> np.ndarray:
+    """i.i.d. uniform bases; 0.1 % of contigs get one run of 50-500 N."""
+    rng = np.random.default_rng(seed)
+    tot = int(lens.sum())
     seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=tot, dtype=np.uint8)]
     off = np.concatenate([[0], np.cumsum(lens)])
     for c in np.flatnonzero(rng.random(len(lens)) < 0.001):
         run = int(rng.integers(50, 501))
         a = int(off[c] + rng.integers(0, max(1, lens[c] - run)))
         seq[a:a + run] = ord("N")
-    return seq, lens
+    return seq
+
+
+def synth_batch(seed: int, target_bases: int):
+    lens = synth_lens(seed, target_bases)
+    return synth_bases(seed + 1_000_003, lens), lens
 
 
 class ClockSampler(threading.Thread):
@@ -140,6 +150,7 @@ def run_reference(args):
         return
     spec = parse_project(standin_1p4m_config())
     weights = init_random(spec, 0)
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: use every host core
     cores = torch.get_num_threads()
     sample = int(args.ref_sample_kbp * 1000)
     times, bases, wins = [], 0, 0
@@ -176,6 +187,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "") and not os.environ.get("JG_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = parse_project(standin_1p4m_config())
     eng = B200Engine(spec=spec, device=local, seed=0, workspace_gb=args.workspace_gb)
@@ -183,8 +196,16 @@ def run_b200(args):
     stream = eng._stream()
     target = int(args.batch_mbp * 1e6)
     n_batches = args.warmup + args.steps
-    # contig sharding: every rank classifies its own contigs (weak scaling: fixed bases per GPU)
-    host_batches = [synth_batch(7919 * rank + i + 1, target) for i in range(n_batches)]
+    # Length-balanced contig sharding: the step's contig list (world x batch Mbp,
+    # identical on every rank) is bin-packed on window counts; a rank materialises only its shard.
+    from jaeger_b200.parallel import gather_contig_records, shard_contigs
+    host_batches, shard_ids, n_global = [], [], []
+    for i in range(n_batches):
+        glens = synth_lens(i + 1, world * target)
+        mine = shard_contigs(glens, world, FSIZE, STRIDE)[rank]
+        host_batches.append((synth_bases(7919 * (i + 1) + rank, glens[mine]), glens[mine]))
+        shard_ids.append(torch.from_numpy(mine))
+        n_global.append(len(glens))
     pinned = [torch.from_numpy(s).pin_memory() for s, _ in host_batches]
 
     def barrier():
@@ -192,19 +213,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
-    def gather_results(agg):
+    def gather_results(agg, i):
         """NCCL is used only to gather the per-contig results on rank 0."""
         if world == 1 or not agg:
             return
         rec = torch.cat([agg["pred_sum"].float(), agg["consensus"].float().unsqueeze(1)], dim=1)
-        n = torch.tensor([rec.shape[0]], device=dev, dtype=torch.int64)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        m = int(max(int(s.item()) for s in sizes))
-        pad = torch.zeros((m, rec.shape[1]), device=dev)
-        pad[:rec.shape[0]] = rec
-        out = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, out, dst=0)
+        gather_contig_records(rec, shard_ids[i].to(dev), n_global[i], dst=0)
 
     results = {}
     with torch.cuda.stream(stream):
@@ -212,7 +226,7 @@ def run_b200(args):
         dev_batches = [p.to(dev) for p in pinned]
         for i in range(args.warmup):
             agg, _, _ = eng.classify_long(dev_batches[i], host_batches[i][1], FSIZE, STRIDE)
-            gather_results(agg)
+            gather_results(agg, i)
         barrier()
         eng.set_profiling(True)
         sampler = ClockSampler(local)
@@ -223,7 +237,7 @@ def run_b200(args):
         n_bases = n_windows = n_contigs = 0
         for i in range(args.warmup, n_batches):
             agg, w, c = eng.classify_long(dev_batches[i], host_batches[i][1], FSIZE, STRIDE)
-            gather_results(agg)
+            gather_results(agg, i)
             n_bases += int(host_batches[i][1].sum()); n_windows += w; n_contigs += c
         ev1.record(stream)
         barrier()
@@ -240,7 +254,7 @@ def run_b200(args):
         for i in range(args.warmup, n_batches):
             x = pinned[i].to(dev, non_blocking=True)
             agg, w, c = eng.classify_long(x, host_batches[i][1], FSIZE, STRIDE)
-            gather_results(agg)
+            gather_results(agg, i)
             host = {k: agg[k].cpu() for k in ("pred_sum", "pred_var", "consensus", "per_class_counts", "entropy", "energy", "rel_pos")}
             d2h_bytes = sum(v.numel() * v.element_size() for v in host.values())
         barrier()
@@ -293,7 +307,7 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_mbp_per_gpu_per_step": args.batch_mbp,
                        "l2_policy": "inputs larger than L2: a different 64 Mbp batch every step, ~100 GB of activations per step",
-                       "parallelism": f"contig-sharded x{world}, NCCL gather of per-contig results only"},
+                       "parallelism": f"length-balanced contig sharding x{world} (LPT on window counts), NCCL gather of per-contig records only"},
             "windows_per_s": tot_windows / (ms / 1e3),
             "roofline": roofline,
             "e2e": {"value": tot_bases / 1e6 / (e2e_ms / 1e3), "unit": "Mbp/s",
@@ -311,6 +325,7 @@ def run_b200(args):
 def cpu_baseline(spec, weights, budget_s: float):
     """Oracle port of the reference path timed on the host cores over a bounded sample."""
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     seq, lens = synth_batch(4242, 60_000)
     t0 = time.perf_counter()

@@ -1,0 +1,70 @@
+"""Contig sharding over the GPUs of one node and the final gather of per-contig records.
+
+The reference has no multi-process inference path (commands/predict.py:602 exposes one GPU).
+Contigs are independent units of the hot path: every rank classifies its own
+shard with no collective on the data path, and one gather of fixed-width per-contig records at
+the end rebuilds the input order on rank 0.  Works over NCCL (GPU tensors) and gloo (CPU tensors).
+"""
+from __future__ import annotations
+
+import heapq
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def window_counts(lens: np.ndarray, fsize: int, stride: int) -> np.ndarray:
+    """Windows per contig for the fixed-stride long pass: len(range(0, L - (fsize-1), stride))."""
+    lens = np.asarray(lens, dtype=np.int64)
+    n = (lens - fsize) // stride + 1
+    return np.where(lens >= fsize, n, 0)
+
+
+def shard_contigs(lens: np.ndarray, world: int, fsize: int, stride: int) -> list[np.ndarray]:
+    """Longest-processing-time greedy bin packing on window counts (the FLOP proxy).
+    Returns, per rank, the sorted indices of its contigs; contigs without windows go to the
+    lightest rank so every contig has an owner."""
+    w = window_counts(lens, fsize, stride)
+    order = np.argsort(-w, kind="stable")
+    heap = [(0, r) for r in range(world)]
+    heapq.heapify(heap)
+    owner = np.empty(len(w), dtype=np.int64)
+    for c in order:
+        load, r = heapq.heappop(heap)
+        owner[c] = r
+        heapq.heappush(heap, (load + int(w[c]), r))
+    return [np.flatnonzero(owner == r) for r in range(world)]
+
+
+def gather_contig_records(records: torch.Tensor, contig_ids: torch.Tensor, n_total: int, dst: int = 0,
+                          group=None) -> torch.Tensor | None:
+    """records [n_local, width] (any float/int dtype), contig_ids [n_local] int64 = positions in the
+    global contig list.  Returns on `dst` the [n_total, width] table in global order (rows of
+    contigs nobody reported stay zero), None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = records.device
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    m = max(int(s.item()) for s in sizes)
+    width = records.shape[1]
+    pad_r = torch.zeros((m, width), dtype=records.dtype, device=dev)
+    pad_i = torch.full((m,), -1, dtype=torch.int64, device=dev)
+    pad_r[:records.shape[0]] = records
+    pad_i[:records.shape[0]] = contig_ids
+    if rank == dst:
+        out_r = [torch.zeros_like(pad_r) for _ in range(world)]
+        out_i = [torch.zeros_like(pad_i) for _ in range(world)]
+    else:
+        out_r = out_i = None
+    dist.gather(pad_r, out_r, dst=dst, group=group)
+    dist.gather(pad_i, out_i, dst=dst, group=group)
+    if rank != dst:
+        return None
+    table = torch.zeros((n_total, width), dtype=records.dtype, device=dev)
+    for r_, i_ in zip(out_r, out_i):
+        keep = i_ >= 0
+        table[i_[keep]] = r_[keep]
+    return table

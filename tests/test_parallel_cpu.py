@@ -1,0 +1,53 @@
+"""CPU tests of the multi-GPU host logic with the gloo backend (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from jaeger_b200.parallel import gather_contig_records, shard_contigs, window_counts
+
+
+def test_window_counts_match_planner_formula():
+    lens = np.array([1999, 2000, 3499, 3500, 50000, 0, 2001])
+    assert window_counts(lens, 2000, 1500).tolist() == [len(range(0, int(L) - 1999, 1500)) for L in lens]
+
+
+def test_shard_contigs_balances_and_partitions():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(2000, 50001, size=20000)
+    lens[:5] = 5_000_000                                     # a few genomes
+    for world in (1, 2, 4, 8):
+        shards = shard_contigs(lens, world, 2000, 1500)
+        allc = np.sort(np.concatenate(shards))
+        assert np.array_equal(allc, np.arange(len(lens)))    # a partition
+        loads = np.array([window_counts(lens[s], 2000, 1500).sum() for s in shards])
+        assert loads.max() / loads.mean() < 1.01             # balanced to < 1 %
+
+
+def _worker(rank, world, port, n_total):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    lens = rng.integers(2000, 50001, size=n_total)
+    mine = shard_contigs(lens, world, 2000, 1500)[rank]
+    # a stand-in for the per-contig records every rank computes on its own GPU
+    rec = torch.tensor(np.stack([mine * 3.0 + 1.0, lens[mine].astype(np.float64)], axis=1))
+    table = gather_contig_records(rec, torch.tensor(mine), n_total, dst=0)
+    if rank == 0:
+        want = np.stack([np.arange(n_total) * 3.0 + 1.0, lens.astype(np.float64)], axis=1)
+        assert np.array_equal(table.numpy(), want)
+    else:
+        assert table is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_contig_records_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, 501), nprocs=2, join=True)
