@@ -1,0 +1,136 @@
+"""Windows -> contigs summary and TSV output on top of the stage-4 device kernels.
+
+Product-side counterpart of the reference's `pred_to_dict` / `generate_summary` /
+`write_output` (postprocess/collect.py:247-608): the per-contig reductions run on the GPU
+(`jg_aggregate_contigs`), only string assembly and the DataFrame live on the host.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+
+
+def _split_points(is_last: np.ndarray) -> np.ndarray:
+    """Window offsets of the contigs: [0, end_0, end_1, ...] (collect.py:260-287)."""
+    ends = np.flatnonzero(np.asarray(is_last).astype(np.int32) == 1) + 1
+    n = len(is_last)
+    if len(ends) == 0 or ends[-1] != n:
+        ends = np.append(ends, n)           # trailing windows without an is_last flag form a contig
+    return np.concatenate([[0], ends]).astype(np.int64)
+
+
+def window_summaries(frag_pred: np.ndarray, offsets: np.ndarray, class_map: dict[int, str],
+                     classes=("virus", "phage")) -> list[str]:
+    """helpers.py:73-108 for every contig: "<run length><class initial>" runs, upper-case
+    initial for the viral classes."""
+    initial = np.array([(class_map[k][0].upper() if class_map[k].lower() in classes else class_map[k][0].lower())
+                        for k in sorted(class_map)])
+    keys = np.array(sorted(class_map))
+    fp = np.asarray(frag_pred)
+    n = len(fp)
+    if n == 0:
+        return []
+    start = np.ones(n, dtype=bool)
+    start[1:] = fp[1:] != fp[:-1]
+    start[offsets[:-1]] = True
+    run_starts = np.flatnonzero(start)
+    run_len = np.diff(np.append(run_starts, n))
+    run_val = fp[run_starts]
+    lut = {int(k): str(c) for k, c in zip(keys, initial)}
+    pieces = [f"{ln}{lut.get(int(v), '')}" for ln, v in zip(run_len, run_val)]
+    owner = np.searchsorted(offsets, run_starts, side="right") - 1
+    out = [""] * (len(offsets) - 1)
+    bounds = np.flatnonzero(np.diff(owner, prepend=-1))
+    for i, b in enumerate(bounds):
+        e = bounds[i + 1] if i + 1 < len(bounds) else len(pieces)
+        out[owner[b]] = "".join(pieces[b:e])
+    return out
+
+
+def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats=None) -> dict[str, Any]:
+    """The `data` dict of the reference's pred_to_dict (softmax classifier, no CRF), with the
+    numeric columns produced by the device aggregation kernels."""
+    pred = np.ascontiguousarray(y_pred["prediction"], dtype=np.float32)
+    n_cls = pred.shape[1]
+    if n_cls < 2:
+        raise NotImplementedError("binary (single-logit) classifiers are not on the supported path")
+    offsets = _split_points(y_pred["meta_2"])
+    rel = y_pred.get("reliability")
+    with torch.cuda.stream(engine._stream()):
+        agg = engine.aggregate(engine._h2d(pred), engine._h2d(np.ascontiguousarray(rel, np.float32)) if rel is not None else None,
+                               engine._h2d(offsets))
+        agg = {k: v.cpu().numpy() for k, v in agg.items()}
+    engine.ctx.sync()
+    first = offsets[:-1]
+    n_win = np.diff(offsets)
+    headers = np.array(y_pred["meta_0"], dtype=str)[first]
+    lengths = np.array(y_pred["meta_4"], dtype=np.int32)[first]
+    g, c, a, t = (np.asarray(y_pred[k]).astype(float) for k in ("meta_5", "meta_6", "meta_7", "meta_8"))
+    ns = (fsize - (a + t + g + c)) / fsize                       # collect.py:319-324
+    gcs = (g + c) / fsize
+    pred_sum, pred_var, consensus = agg["pred_sum"], agg["pred_var"], agg["consensus"].astype(np.int64)
+    ood = None
+    if rel is not None:
+        ood = np.array([f"{k / n:.2f}" for k, n in zip(agg["rel_pos"], n_win)], dtype=np.float16)   # collect.py:233-244, 391-395
+    return {
+        "headers": headers, "length": lengths, "consensus": consensus,
+        "per_class_counts": agg["per_class_counts"], "pred_sum": pred_sum, "pred_var": pred_var,
+        "frag_pred": agg["frag_pred"], "offsets": offsets, "ood": ood, "has_reliability": rel is not None,
+        "entropy": agg["entropy"], "energy": agg["energy"],
+        "host_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 1),       # collect.py:357-358
+        "prophage_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 0),
+        "repeats": term_repeats,
+        "gc_mean": np.add.reduceat(gcs, first) / n_win, "ns_mean": np.add.reduceat(ns, first) / n_win,
+        "predictions": pred, "gc_skews": np.asarray(y_pred["meta_9"]).astype(float), "gcs": gcs,
+    }
+
+
+def generate_summary(data: dict[str, Any], labels, indices):
+    """Column order of collect.py:472-518 (+ left join of the terminal-repeat columns, 527-532)."""
+    import pandas as pd
+    class_map = {int(k): v for k, v in zip(indices, labels)}
+    n = len(data["headers"])
+    rel = data["ood"] if data.get("has_reliability", True) else ["unavailable"] * n
+    cols = {"contig_id": data["headers"], "length": data["length"],
+            "prediction": [class_map[int(x)] for x in data["consensus"]], "entropy": data["entropy"],
+            "energy": data["energy"], "reliability_score": rel, "host_contam": data["host_contam"],
+            "prophage_contam": data["prophage_contam"], "G+C": data["gc_mean"], "N%": data["ns_mean"]}
+    if len(class_map) > 2:
+        for i, label in class_map.items():
+            cols[f"#_{label}_windows"] = data["per_class_counts"][:, i]
+        for i, label in class_map.items():
+            cols[f"{label}_score"] = data["pred_sum"][:, i]
+            cols[f"{label}_var"] = data["pred_var"][:, i]
+    else:
+        for i, label in class_map.items():
+            cols[f"#_{label}_windows"] = data["per_class_counts"][:, i]
+        cols["score"] = list(data["pred_sum"])
+        cols["var"] = list(data["pred_var"])
+    cols["window_summary"] = window_summaries(data["frag_pred"], data["offsets"], class_map)
+    df = pd.DataFrame(cols)
+    if data.get("repeats") is not None:
+        df = pd.merge(left=df, right=data["repeats"][["contig_id", "terminal_repeats", "repeat_length"]],
+                      on="contig_id", how="left")
+    df["contig_id"] = df["contig_id"].str.replace("___", ",")
+    return df
+
+
+def write_output(data: dict[str, Any], labels, indices, output_table_path: str | Path,
+                 output_phage_table_path: str | Path, reliability_cutoff: float = 0.5, phage_score: float = 1) -> int:
+    """collect.py:561-608: `N% < 0.3` filter, %.3f TSV, and the phage subset."""
+    df = generate_summary(data, labels, indices).query("`N%` < 0.3")
+    df.to_csv(output_table_path, sep="\t", index=False, float_format="%.3f")
+    lower = [str(x).lower() for x in labels]
+    viral = "phage"
+    if "phage" in lower:
+        viral = labels[lower.index("phage")]
+    elif "virus" in lower:
+        viral = labels[lower.index("virus")]
+    clause = f" and (reliability_score > {reliability_cutoff})" if data.get("has_reliability", True) else ""
+    phage_df = df.query(f'(prediction == "{viral}") and ({viral}_score > {phage_score}){clause}')
+    if not phage_df.empty:
+        phage_df.to_csv(output_phage_table_path, sep="\t", index=False, float_format="%.3f")
+    return len(df)

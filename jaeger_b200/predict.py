@@ -1,0 +1,146 @@
+"""`jaeger predict` on the B200 engine: model lookup, engine call, post-processing, outputs.
+
+Mirrors the reference driver `commands/predict.py:488-861` for the options that touch the hot
+path (the option names and defaults are the reference CLI's, cli.py:122-371): same model
+registry (`config.json["model_paths"]`, scanned like `AvailableModels`, utils/misc.py:334-392),
+same output locations `<-o>/<model_id>/<base>.tsv` and `<base>_phages.tsv`, same `--overwrite`
+rule, same prophage table source.  Options outside the path (--refine, --crf, plots, --onnx ...)
+are not accepted.
+
+    python -m jaeger_b200.predict -i contigs.fasta -o out -m jaeger_xxx_1.4M_fragment --config config.json
+    python -m jaeger_b200.predict -i contigs.fasta -o out -m standin      # random-init stand-in architecture
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import sys
+import time
+from collections import defaultdict
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+logger = logging.getLogger("Jaeger")
+
+
+def available_models(paths) -> dict[str, dict[str, Path]]:
+    """utils/misc.py:346-392: every directory named `model` under each path."""
+    models: dict[str, dict[str, Path]] = defaultdict(dict)
+    for path in [Path(p) for p in ([paths] if isinstance(paths, (str, Path)) else paths)]:
+        model_dirs = [p for p in path.rglob("model") if p.is_dir()]
+        if path.name == "model" and path.is_dir():
+            model_dirs.append(path)
+        for md in model_dirs:
+            for e in md.iterdir():
+                if e.is_dir() and e.name.endswith("_graph"):
+                    models[e.name.removesuffix("_graph")]["graph"] = e
+                elif e.is_file():
+                    for suffix, key in (("_classes.yaml", "classes"), ("_project.yaml", "project"), (".weights.h5", "weights")):
+                        if e.name.endswith(suffix):
+                            models[e.name[:-len(suffix)]][key] = e
+    return dict(models)
+
+
+def get_model_id(model: str) -> str:
+    """utils/misc.py:395."""
+    return model.split("_", 1)[1].rsplit("_", 1)[0]
+
+
+def run_core(**kwargs: Any) -> dict[str, Any]:
+    from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
+    from .engine import read_fasta
+    from .postprocess import contig_table, write_output
+    from .prophage import call_regions
+
+    t0 = time.time()
+    input_path = Path(kwargs["input"])
+    model_name = kwargs.get("model") or "standin"
+    fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
+    if model_name == "standin":
+        engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=int(kwargs.get("physicalid") or 0))
+        model_id = "standin"
+    else:
+        cfg = json.loads(Path(kwargs["config"]).read_text()) if kwargs.get("config") else {}
+        info = available_models(cfg.get("model_paths", []))
+        if model_name not in info:
+            raise ValueError(f"model {model_name!r} not found; available: {sorted(info)}")
+        engine = B200Engine(info[model_name], device=int(kwargs.get("physicalid") or 0))
+        model_id = get_model_id(model_name)
+    out_dir = Path(kwargs["output"]) / model_id                          # predict.py:551
+    out_dir.mkdir(parents=True, exist_ok=True)
+    base = input_path.stem
+    table, phage_table = out_dir / f"{base}.tsv", out_dir / f"{base}_phages.tsv"      # predict.py:571-572
+    if table.exists() and not kwargs.get("overwrite"):
+        raise FileExistsError(f"{table} exists; use --overwrite")                     # predict.py:574-578
+    min_len = kwargs.get("min_len")
+    recs = list(read_fasta(input_path))
+    n_ok = sum(len(s) >= (min_len or fsize) for _, s in recs)
+    if n_ok == 0:
+        raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
+    src = WindowSource(records=recs, fsize=fsize, stride=stride, min_len=min_len,
+                       dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
+                       dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
+                       batch=int(kwargs.get("batch", 96)))
+    y_pred = engine.predict(src)
+    t1 = time.time()
+    data = contig_table(engine, y_pred, fsize)
+    cm = engine.class_map
+    n_written = write_output(data, cm["class"], cm["index"], table, phage_table,
+                             reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
+    result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": len(recs),
+              "windows": int(y_pred["prediction"].shape[0]), "predict_seconds": t1 - t0}
+    logger.info(f"processed {n_written}/{len(recs)} sequences")
+    if kwargs.get("prophage"):
+        regions = call_regions(engine, data, cm, fsize, stride, lc=int(kwargs.get("lc", 500_000)),
+                               sensitivity=float(kwargs.get("sensitivity", 1.5)))
+        rows = ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
+        for name, r in regions.items():
+            for (ws, we), (s, e), sc in zip(r["ranges"], r["coords"], r["scores"]):
+                rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
+        (out_dir / f"{base}_prophage_regions.tsv").write_text("\n".join(rows) + "\n")
+        result["prophage_regions"] = regions
+    if kwargs.get("window_scores"):                                       # predict.py:458-470
+        off = data["offsets"]
+        np.savez(out_dir / f"{base}_window_scores.npz", headers=data["headers"], lengths=data["length"],
+                 predictions=np.array([data["predictions"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
+                 gc_skews=np.array([data["gc_skews"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
+                 gcs=np.array([data["gcs"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object), allow_pickle=True)
+    return result
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="jaeger_b200 predict", description=__doc__.split("\n")[0])
+    ap.add_argument("-i", "--input", required=True)
+    ap.add_argument("-o", "--output", required=True)
+    ap.add_argument("-m", "--model", default="standin")
+    ap.add_argument("--config", default=None, help="config.json with model_paths (utils/misc.py:309-331)")
+    ap.add_argument("--fsize", type=int, default=2000)
+    ap.add_argument("--stride", type=int, default=1500)
+    ap.add_argument("--batch", type=int, default=96)
+    ap.add_argument("--min-len", dest="min_len", type=int, default=None)
+    ap.add_argument("--dynamic-stride", dest="dynamic_stride", action="store_true")
+    ap.add_argument("--dynamic-stride-threshold", dest="dynamic_stride_threshold", type=float, default=10.0)
+    ap.add_argument("--rc", type=float, default=0.1)
+    ap.add_argument("--pc", type=float, default=3)
+    ap.add_argument("-p", "--prophage", action="store_true")
+    ap.add_argument("--lc", type=int, default=500_000)
+    ap.add_argument("-s", "--sensitivity", type=float, default=1.5)
+    ap.add_argument("--physicalid", type=int, default=0)
+    ap.add_argument("--window-scores", dest="window_scores", action="store_true")
+    ap.add_argument("--overwrite", action="store_true")
+    args = ap.parse_args(argv)
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s [jaeger_b200] %(message)s")
+    try:
+        res = run_core(**vars(args))
+    except Exception as e:                                               # predict.py:811-816
+        logger.error(f"an error {e} occured during inference")
+        return 1
+    logger.info(f"wrote {res['table']} ({res['num_written']} contigs, {res['windows']} windows, {res['predict_seconds']:.2f} s)")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

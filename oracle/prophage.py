@@ -82,46 +82,47 @@ def optimal_partition(x: np.ndarray, pen: float, min_size: int = 3) -> list[int]
 
 
 def knee_locator(x, y, S: float = 1.0):
-    """Kneedle, curve="convex", direction="decreasing", offline; returns the knee x or None.
+    """kneed.KneeLocator(x, y, curve="convex", direction="decreasing"), defaults S=1.0,
+    interp_method="interp1d" (identity on the given points), online=False.  Returns knee x or None.
 
-    Steps (kneed.KneeLocator): interp1d = identity on the given points; min-max normalise x
-    and y; convex+decreasing -> transform to the concave-increasing form by flipping:
-    y_n = 1 - y_n reversed...  kneed's implementation: for curve 'convex' and direction
-    'decreasing', x_difference = x_n, y_difference = (y_max - y_n) reversed handling reduces to
-    y_d = x_n + y_n - 1 negated; the knee is the first local maximum of the difference curve
-    whose subsequent drop crosses threshold T = d_max - S * mean(diff(x_n))."""
+    1. min-max normalise x and y;  2. transform_y for convex+decreasing: y = y.max() - y;
+    3. difference curve yd = y - x;  4. local maxima / minima with argrelextrema(>=, <=), whose
+    default mode="clip" lets end points qualify;  5. thresholds Tmx = yd[max] - S*|mean(diff(x))|;
+    6. walk the curve from the first maximum: a maximum (re)arms the threshold, a minimum resets
+    it to 0, the first point whose successor drops below the threshold yields x[threshold index]."""
     x = np.asarray(x, dtype=float)
     y = np.asarray(y, dtype=float)
-    if len(x) < 3 or np.ptp(x) == 0 or np.ptp(y) == 0:
+    if len(x) < 2 or x.max() == x.min() or y.max() == y.min():
         return None
     xn = (x - x.min()) / (x.max() - x.min())
     yn = (y - y.min()) / (y.max() - y.min())
-    # kneed.transform_y: convex + decreasing -> y = y.max() - y  (no flip of x)
     yn = yn.max() - yn
     yd = yn - xn
-    xd = xn
-    # local maxima / minima of the difference curve
-    mx = [i for i in range(1, len(yd) - 1) if yd[i - 1] < yd[i] >= yd[i + 1]]
-    mn = [i for i in range(1, len(yd) - 1) if yd[i - 1] > yd[i] <= yd[i + 1]]
+    n = len(yd)
+    mx, mn = [], []
+    for i in range(n):
+        l, r = yd[max(i - 1, 0)], yd[min(i + 1, n - 1)]
+        if yd[i] >= l and yd[i] >= r:
+            mx.append(i)
+        if yd[i] <= l and yd[i] <= r:
+            mn.append(i)
     if not mx:
         return None
-    tm = {i: yd[i] - S * np.abs(np.diff(xn).mean()) for i in mx}
-    knee = None
-    thr = None
-    thr_i = None
-    for i in range(len(xd)):
+    step = abs(np.diff(xn).mean())
+    thr, thr_i, used = None, None, 0
+    for i in range(n):
         if i < mx[0]:
             continue
-        if i == len(xd) - 1:
+        if i == n - 1:
             break
         if i in mx:
-            thr, thr_i = tm[i], i
+            thr, thr_i = yd[i] - S * step, i
+            used += 1
         if i in mn:
             thr = 0.0
         if thr is not None and yd[i + 1] < thr:
-            knee = x[thr_i]
-            break
-    return knee
+            return x[thr_i]
+    return None
 
 
 def segment(phage_col: np.ndarray, sensitivity: float = 1.5):

@@ -331,3 +331,54 @@ def test_smoothing_vs_reference_golden_and_segmentation_vs_oracle(standin):
         want = opro.optimal_partition(col, float(p + 1), 3)
         assert bk[p, :nb[p]].tolist() == want, p
         assert want[-1] == T and all(b - a >= 3 for a, b in zip([0] + want[:-1], want))
+
+
+def test_predict_driver_tsv_equals_oracle_pipeline(standin, tmp_path):
+    """End to end through the reference-style driver: the TSV written from the device aggregates
+    equals what the oracle's pred_to_dict + generate_summary produce from the same window logits."""
+    import io
+    import pandas as pd
+    from jaeger_b200 import WindowSource
+    from jaeger_b200.postprocess import contig_table, generate_summary
+    from jaeger_b200.predict import run_core
+    from oracle import postprocess as opp
+    spec, weights, eng = standin
+    res = run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin", fsize=2000, stride=1500,
+                   min_len=500, overwrite=True)
+    gold = json.loads((G / "fragments_synthetic.json").read_text())
+    assert res["table"].exists()
+    assert res["windows"] == len(gold["2000_1500_None_None_0"]) + len(gold["2000_1500_500_1999_0"])   # long + short pass
+    with pytest.raises(FileExistsError):
+        run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin")
+    y = eng.predict(WindowSource(fasta=G / "synthetic_contigs.fasta", fsize=2000, stride=1500, min_len=500))
+    data = contig_table(eng, y, 2000)
+    got = generate_summary(data, eng.class_map["class"], eng.class_map["index"])
+    odata, _ = opp.pred_to_dict(y, 2000, eng.class_map)
+    want = opp.generate_summary(odata, eng.class_map["class"], eng.class_map["index"])
+    assert list(got.columns) == list(want.columns)
+    for col in want.columns:
+        if want[col].dtype.kind in "fc" or str(want[col].dtype) == "float16":
+            a, b = got[col].to_numpy(dtype=np.float64), want[col].to_numpy(dtype=np.float64)
+            assert np.allclose(a, b, rtol=0, atol=1e-3 if col in ("entropy", "energy") else 1e-12), col
+        else:
+            assert got[col].tolist() == want[col].tolist(), col
+    assert "syn7,with,commas" in got["contig_id"].tolist()                 # "___" restored (collect.py:556)
+    tsv = pd.read_csv(res["table"], sep="\t")
+    assert len(tsv) == (got["N%"] < 0.3).sum()
+
+
+def test_prophage_region_calling_vs_oracle(standin):
+    from jaeger_b200 import prophage as ppro
+    from oracle import prophage as opro
+    _, _, eng = standin
+    rng = np.random.default_rng(17)
+    for T, islands in [(3333, [(400, 430), (1500, 1530), (2800, 2825)]), (700, [(100, 140)]), (350, [])]:
+        logits = rng.normal(0, 1.0, (T, 6)).astype(np.float32)
+        for a, b in islands:
+            logits[a:b, 1] += 7.0
+        ranges, scores = ppro.segment_contig(eng, logits, 1, 1.5)
+        want_r, want_s = opro.segment(opro.smooth_scores(logits)[:, 1], 1.5)
+        assert ranges == want_r, (T, ranges, want_r)
+        assert np.allclose(scores, want_s, atol=1e-6)
+        if islands:
+            assert len(ranges) >= 1 and all(any(abs(r[0] - a) <= 12 and abs(r[1] - b) <= 12 for a, b in islands) for r in ranges)
