@@ -88,8 +88,12 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
 
 /* ---- stage 3: model ---------------------------------------------------------------------
  * The plan is a flat int32/float32 description compiled by the host from project.yaml; see
- * jaeger_b200/plan.py for the field layout (JG_PLAN_* below).  Weights are fp32 host arrays in
- * TensorFlow layout ([k, Cin, Cout] conv kernels, [in, out] dense kernels). */
+ * jaeger_b200/plan.py for the field layout.  Layer kinds: 1 = conv with fused epilogue, 2 =
+ * MaxPooling1D(2) per frame, 3 = sum over frames + global max pool (legacy graph,
+ * nnlib/v1/layers.py:65-69, 207, 413).  tok_offset: token t feeds one-hot channel t - tok_offset
+ * (1 for the v2 encoder whose token 0 is the masked unknown codon, 0 for the legacy amino-acid
+ * ids).  Weights are fp32 host arrays in TensorFlow layout ([k, Cin, Cout] conv kernels,
+ * [in, out] dense kernels). */
 #define JG_LAYER_INT_FIELDS 24
 #define JG_LAYER_PTR_FIELDS 12
 typedef struct jg_layer_desc {
@@ -103,17 +107,23 @@ typedef struct jg_head_desc {
   int32_t pool_mode;        /* 1 max, 2 average */
   int32_t n_taps;           /* NMD taps (0 = no reliability head) */
   int32_t rel_hidden;       /* units of the reliability hidden dense (gelu) */
-  int32_t reserved[3];
+  int32_t mlp_hidden;       /* legacy head: two Dense(mlp_hidden, act) before the classifier (0 = none) */
+  int32_t mlp_act;          /* activation code of those layers (3 = erf GELU) */
+  int32_t reserved[1];
   const float* cls_w;       /* [feat_dim][n_classes] */
   const float* cls_b;       /* [n_classes] */
   const float* rel_w1;      /* [sum tap widths][rel_hidden] */
   const float* rel_b1;      /* [rel_hidden] */
   const float* rel_w2;      /* [rel_hidden][1] */
   const float* rel_b2;      /* [1] */
+  const float* mlp_w1;      /* [feat_dim][mlp_hidden] */
+  const float* mlp_b1;
+  const float* mlp_w2;      /* [mlp_hidden][mlp_hidden]; its output is the "embedding" */
+  const float* mlp_b2;
 } jg_head_desc;
 
 int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers,
-                    const jg_head_desc* head, int32_t frames, int32_t vocab, jg_model** out);
+                    const jg_head_desc* head, int32_t frames, int32_t tok_offset, jg_model** out);
 int jg_model_destroy(jg_model* m);
 /* Largest number of windows one jg_model_forward call may take for a given lc with the
  * workspace budget (bytes) -- the host chunks its window stream with it. */

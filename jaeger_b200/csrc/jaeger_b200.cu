@@ -60,8 +60,9 @@ struct jg_ctx {
 enum LayerField {
   LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
   LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
-  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN
+  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS
 };
+// layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
 enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN };
 
 struct Layer {
@@ -76,12 +77,13 @@ struct Layer {
 struct jg_model {
   jg_ctx* ctx = nullptr;
   std::vector<Layer> layers;
-  int frames = 6, vocab = 65;
+  int frames = 6, tok_offset = 1;
   int n_bufs = 0, n_masks = 0, n_taps = 0, tap_width = 0;
   std::vector<int> buf_channels;
   jg_head_desc head{};
   float *cls_w = nullptr, *cls_b = nullptr, *rel_w1 = nullptr, *rel_b1 = nullptr, *rel_w2 = nullptr,
-        *rel_b2 = nullptr, *tap_mean = nullptr;
+        *rel_b2 = nullptr, *tap_mean = nullptr, *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr,
+        *mlp_b2 = nullptr;
   int final_mask = 0;
   std::vector<int> tap_mask_slot;
   // workspace -------------------------------------------------------------------------------
@@ -108,7 +110,8 @@ namespace {
 void model_geometry(const jg_model* m, int lc, int* period, int* rpw) {
   int p = lc;
   for (const Layer& L : m->layers) {
-    const int l_in = lc - L.f[LF_CUM_SHRINK_IN];
+    if (L.f[LF_KIND] != 1) continue;
+    const int l_in = (lc - L.f[LF_CUM_SHRINK_IN]) >> L.f[LF_HALVINGS];
     const int halo = L.halo_l > L.halo_r ? L.halo_l : L.halo_r;
     const int need = l_in + (L.f[LF_SHRINK] == 0 ? halo : 0);
     if (need > p) p = need;
@@ -308,18 +311,25 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
 
 // ---- stage 3 -----------------------------------------------------------------------------------
 int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, const jg_head_desc* head,
-                    int32_t frames, int32_t vocab, jg_model** out) {
+                    int32_t frames, int32_t tok_offset, jg_model** out) {
   JG_CUDA(cudaSetDevice(ctx->device));
   jg_model* m = new jg_model();
   m->ctx = ctx;
   m->frames = frames;
-  m->vocab = vocab;
+  m->tok_offset = tok_offset;
   m->head = *head;
   int max_buf = -1, max_mask = -1, max_tap = -1;
   for (int l = 0; l < n_layers; ++l) {
     Layer L;
     std::memcpy(L.f, layers[l].i, sizeof(L.f));
     const int cin = L.f[LF_CIN], cout = L.f[LF_COUT], k = L.f[LF_K];
+    if (L.f[LF_KIND] == 2 || L.f[LF_KIND] == 3) {
+      if (cin % 64 != 0) { delete m; return fail("pooling layers need a channel count that is a multiple of 64"); }
+      for (int b : {L.f[LF_IN_BUF], L.f[LF_OUT_BUF]}) max_buf = b > max_buf ? b : max_buf;
+      for (int sl : {L.f[LF_MASK_IN], L.f[LF_MASK_OUT]}) max_mask = sl > max_mask ? sl : max_mask;
+      m->layers.push_back(L);
+      continue;
+    }
     if (L.f[LF_KIND] != 1) { delete m; return fail("unknown layer kind in plan"); }
     if (cin % 64 != 0 || cout % 64 != 0 || cout > 256 || k > jg::kMaxTaps) {
       delete m;
@@ -367,6 +377,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     int& ci = m->buf_channels[L.f[LF_IN_BUF]];
     ci = L.f[LF_CIN] > ci ? L.f[LF_CIN] : ci;
     if (L.f[LF_OUT_BUF] >= 0) { int& co = m->buf_channels[L.f[LF_OUT_BUF]]; co = L.f[LF_COUT] > co ? L.f[LF_COUT] : co; }
+    if (L.f[LF_KIND] != 1) continue;
     if (L.f[LF_TAP_MODE] != 0) {
       m->tap_mask_slot[L.f[LF_TAP_SLOT]] = L.f[LF_MASK_OUT];
       if (m->tap_width != 0 && m->tap_width != L.f[LF_COUT]) { delete m; return fail("NMD taps of different widths are not supported"); }
@@ -378,6 +389,13 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
   const int feat = head->feat_dim, ncls = head->n_classes;
   if (upload_f32(head->cls_w, static_cast<size_t>(feat) * ncls, &m->cls_w)) return 2;
   if (upload_f32(head->cls_b, ncls, &m->cls_b)) return 2;
+  if (head->mlp_hidden > 0) {
+    if (head->mlp_hidden != feat || feat > 256) { delete m; return fail("MLP head needs hidden width == feature width <= 256"); }
+    if (upload_f32(head->mlp_w1, static_cast<size_t>(feat) * feat, &m->mlp_w1)) return 2;
+    if (upload_f32(head->mlp_b1, feat, &m->mlp_b1)) return 2;
+    if (upload_f32(head->mlp_w2, static_cast<size_t>(feat) * feat, &m->mlp_w2)) return 2;
+    if (upload_f32(head->mlp_b2, feat, &m->mlp_b2)) return 2;
+  }
   if (m->n_taps > 0) {
     const int nmd_dim = m->n_taps * m->tap_width;
     std::vector<float> means(static_cast<size_t>(nmd_dim), 0.0f);
@@ -406,7 +424,8 @@ int jg_model_destroy(jg_model* m) {
   cudaSetDevice(m->ctx->device);
   free_workspace(m);
   for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.par); cudaFree(L.shifts); }
-  for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean}) cudaFree(p);
+  for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
+                   m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
   delete m;
   return 0;
@@ -423,7 +442,8 @@ int64_t jg_model_workspace_bytes(jg_model* m) { return m->ws_bytes; }
 double jg_model_flops_per_window(jg_model* m, int32_t lc) {
   double f = 0.0;
   for (const Layer& L : m->layers) {
-    const int l_out = lc - L.f[LF_CUM_SHRINK_IN] - L.f[LF_SHRINK];
+    if (L.f[LF_KIND] != 1) continue;
+    const int l_out = ((lc - L.f[LF_CUM_SHRINK_IN]) >> L.f[LF_HALVINGS]) - L.f[LF_SHRINK];
     f += 2.0 * m->frames * l_out * L.f[LF_K] * static_cast<double>(L.f[LF_CIN]) * L.f[LF_COUT];
   }
   return f;
@@ -460,16 +480,33 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
 
   // stem operand: one-hot rows + token mask
   jg::expand_tokens_kernel<<<grid_for(rows * 8, 256, ctx->num_sms, 16), 256, 0, st>>>(
-      d_tokens, d_lpad, rows, lc, pitch, geom, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
+      d_tokens, d_lpad, rows, lc, pitch, geom, m->tok_offset, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
       m->counts + static_cast<long long>(m->layers[0].f[LF_MASK_IN]) * m->cap_windows);
   ctx->launches++;
   JG_CUDA(cudaGetLastError());
 
+  bool pool_final = false;
   for (Layer& L : m->layers) {
     const int cout = L.f[LF_COUT];
+    if (L.f[LF_KIND] == 2) {
+      jg::maxpool2_kernel<<<grid_for(rows * 8 * (L.f[LF_CIN] / 64), 256, ctx->num_sms, 16), 256, 0, st>>>(
+          buf_row0(L.f[LF_IN_BUF]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_CIN] / 64, plane,
+          buf_row0(L.f[LF_OUT_BUF]), mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
+      ctx->launches++;
+      continue;
+    }
+    if (L.f[LF_KIND] == 3) {
+      const int threads = (L.f[LF_CIN] / 8) * 8;
+      jg::framesum_globalmax_kernel<<<grid_for(n_windows, 1, ctx->num_sms, 8), threads, static_cast<size_t>(8) * L.f[LF_CIN] * 4, st>>>(
+          buf_row0(L.f[LF_IN_BUF]), d_lpad, static_cast<int>(n_windows), geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS],
+          L.f[LF_CIN], plane, m->pool);
+      ctx->launches++;
+      pool_final = true;
+      continue;
+    }
     jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
-        mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN] + L.f[LF_SHRINK], L.f[LF_K], L.shifts,
-        L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
+        mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_SHRINK], L.f[LF_K],
+        L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
     ctx->launches++;
     jg::ConvParams p{};
     p.x = buf_row0(L.f[LF_IN_BUF]);
@@ -540,6 +577,10 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   hp.tap_width = m->tap_width;
   hp.rel_hidden = m->head.rel_hidden;
   hp.masking = m->layers.back().f[LF_MASKING];
+  hp.mlp_w1 = m->mlp_w1; hp.mlp_b1 = m->mlp_b1; hp.mlp_w2 = m->mlp_w2; hp.mlp_b2 = m->mlp_b2;
+  hp.mlp_hidden = m->head.mlp_hidden;
+  hp.mlp_act = m->head.mlp_act;
+  hp.pool_final = pool_final ? 1 : 0;
   const int warps = 4;
   const size_t smem = static_cast<size_t>(warps) * (hp.feat + hp.n_taps * hp.tap_width) * 4;
   jg::heads_kernel<<<grid_for(n_windows, warps, ctx->num_sms, 16), warps * 32, smem, st>>>(hp);

@@ -17,7 +17,7 @@ struct RowGeom {
 // One thread per 16-byte chunk, 8 threads per row; every row of the window block is written
 // (gap / tail rows get zeros) so the buffer can be recycled between chunks of windows.
 __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const int* __restrict__ lpad,
-                                     long long n_rows, int lc, int pitch, RowGeom g,
+                                     long long n_rows, int lc, int pitch, RowGeom g, int tok_offset,
                                      __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ mask,
                                      int* __restrict__ count) {
   const long long total = n_rows * 8;
@@ -29,10 +29,13 @@ __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const i
     const long long w = row / g.rpw;
     const int rw = static_cast<int>(row - w * g.rpw);
     const int f = rw / g.period, j = rw - f * g.period;
-    int tok = 0;
+    int tok = -1;
     if (f < g.frames && j < lc && j < lpad[w]) tok = tokens[(w * g.frames + f) * pitch + j];
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    const int ch = tok - 1;                               // token t -> one-hot channel t-1
+    // token t -> one-hot channel t - tok_offset (v2: offset 1, token 0 = unknown = zero row;
+    // legacy: offset 0, every in-frame position has a channel)
+    const int ch = tok - tok_offset;
+    tok = (tok >= tok_offset) ? 1 : 0;
     if (tok > 0 && (ch >> 3) == chunk) {
       const uint32_t one = 0x3F80u << (16 * (ch & 1));
       const int word = (ch & 7) >> 1;
@@ -50,15 +53,15 @@ __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const i
 // (nnlib/v2/layers.py:1245-1252, mask_mode "any").  Also accumulates the per-window count of
 // valid rows that the NMD taps and the pooling need.
 __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const int* __restrict__ lpad,
-                                      long long n_rows, RowGeom g, int shrink_out, int ntaps,
-                                      const int* __restrict__ shifts, int masking,
+                                      long long n_rows, RowGeom g, int shrink_in, int halvings, int shrink,
+                                      int ntaps, const int* __restrict__ shifts, int masking,
                                       uint8_t* __restrict__ out_mask, int* __restrict__ count) {
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
        row += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long w = row / g.rpw;
     const int rw = static_cast<int>(row - w * g.rpw);
     const int f = rw / g.period, j = rw - f * g.period;
-    int ok = (f < g.frames) && (j < lpad[w] - shrink_out);
+    int ok = (f < g.frames) && (j < ((lpad[w] - shrink_in) >> halvings) - shrink);
     if (ok && masking) {
       int any = 0;
       for (int t = 0; t < ntaps; ++t) any |= in_mask[row + shifts[t]];
@@ -76,6 +79,87 @@ __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const
   }
 }
 
+// MaxPooling1D(pool_size=2) inside every frame (legacy graph, nnlib/v1/layers.py:65-69):
+// out[w,f,j] = max(in[w,f,2j], in[w,f,2j+1]) for j < L_in/2, zero elsewhere.  One thread per
+// 16-byte chunk of an output row; both tensors are g64sw, so the chunk position is re-swizzled
+// for every row it touches.
+__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ lpad, long long n_rows,
+                                RowGeom g, int shrink_in, int halvings, int groups, long long plane,
+                                __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ out_mask, int* __restrict__ count) {
+  const long long total = n_rows * 8 * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pc = static_cast<int>(idx & 7);
+    const long long t = idx >> 3;
+    const long long row = t % n_rows;
+    const int grp = static_cast<int>(t / n_rows);
+    const long long w = row / g.rpw;
+    const int rw = static_cast<int>(row - w * g.rpw);
+    const int f = rw / g.period, j = rw - f * g.period;
+    const int l_out = ((lpad[w] - shrink_in) >> halvings) >> 1;
+    const bool ok = f < g.frames && j < l_out;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) {
+      const int chunk = pc ^ static_cast<int>(row & 7);
+      const long long r0 = w * g.rpw + static_cast<long long>(f) * g.period + 2 * j, r1 = r0 + 1;
+      const uint4 a = *reinterpret_cast<const uint4*>(x + (grp * plane + r0) * 64 + ((chunk ^ static_cast<int>(r0 & 7)) * 8));
+      const uint4 b = *reinterpret_cast<const uint4*>(x + (grp * plane + r1) * 64 + ((chunk ^ static_cast<int>(r1 & 7)) * 8));
+      const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) po[e] = __hmax2(pa[e], pb[e]);
+    }
+    *reinterpret_cast<uint4*>(y + (grp * plane + row) * 64 + pc * 8) = o;
+    if (grp == 0 && pc == 0) {
+      out_mask[row] = ok;
+      if (ok) atomicAdd(count + w, 1);
+    }
+  }
+}
+
+// Add over the six frames followed by GlobalMaxPool1D over the positions (legacy graph,
+// nnlib/v1/layers.py:207, 413).  One CTA per window; thread = (8-channel chunk, position lane).
+__global__ void framesum_globalmax_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ lpad,
+                                          int n_windows, RowGeom g, int shrink_in, int halvings, int channels,
+                                          long long plane, float* __restrict__ pool) {
+  extern __shared__ float s_max[];     // [pos lanes][channels]
+  const int chunks = channels / 8;
+  const int lanes = blockDim.x / chunks;
+  const int chunk = threadIdx.x % chunks, lane = threadIdx.x / chunks;
+  for (int w = blockIdx.x; w < n_windows; w += gridDim.x) {
+    const int L = (lpad[w] - shrink_in) >> halvings;
+    float best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -3.0e38f;
+    for (int j = lane; j < L; j += lanes) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int f = 0; f < g.frames; ++f) {
+        const long long row = static_cast<long long>(w) * g.rpw + static_cast<long long>(f) * g.period + j;
+        const uint4 v = *reinterpret_cast<const uint4*>(x + ((chunk >> 3) * plane + row) * 64 + (((chunk & 7) ^ static_cast<int>(row & 7)) * 8));
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 q = __bfloat1622float2(pv[e]);
+          acc[2 * e] += q.x;
+          acc[2 * e + 1] += q.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) best[e] = fmaxf(best[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_max[lane * channels + chunk * 8 + e] = best[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+      float m = -3.0e38f;
+      for (int l = 0; l < lanes; ++l) m = fmaxf(m, s_max[l * channels + c]);
+      pool[static_cast<long long>(w) * channels + c] = L > 0 ? m : 0.0f;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) p[i] = v;
@@ -89,8 +173,10 @@ struct HeadParams {
   const float* tap_mean;    // [n_taps][tap_width] moving means
   const float* cls_w; const float* cls_b;
   const float* rel_w1; const float* rel_b1; const float* rel_w2; const float* rel_b2;
+  const float* mlp_w1; const float* mlp_b1; const float* mlp_w2; const float* mlp_b2;   // optional Dense, Dense before the classifier
   float* logits; float* rel; float* emb; float* nmd;
   int n_windows, feat, n_classes, pool_mode, n_taps, tap_width, rel_hidden, masking;
+  int mlp_hidden, mlp_act, pool_final;   // pool_final: the pool buffer already holds finished features
 };
 
 // One warp per window: finalise the pooled features, classifier dense, NMD vector,
@@ -103,14 +189,35 @@ __global__ void heads_kernel(const HeadParams p) {
   float* feat = s_feat + static_cast<size_t>(warp) * (p.feat + nmd_dim);
   float* nmdv = feat + p.feat;
   for (int w = blockIdx.x * warps_per_block + warp; w < p.n_windows; w += gridDim.x * warps_per_block) {
-    const int cnt = p.pool_count[w];
+    const int cnt = p.pool_final ? 1 : p.pool_count[w];
     for (int c = lane; c < p.feat; c += 32) {
       float v = p.pool[static_cast<long long>(w) * p.feat + c];
-      if (p.pool_mode == 1) v = cnt > 0 ? v : 0.0f;   // all-masked sample pools to zeros
+      if (p.pool_final) { /* finished features */ }
+      else if (p.pool_mode == 1) v = cnt > 0 ? v : 0.0f;   // all-masked sample pools to zeros
       else v = p.masking ? (cnt > 0 ? v / fmaxf(static_cast<float>(cnt), 1e-7f) : 0.0f)
                          : v / static_cast<float>(cnt);
       feat[c] = v;
-      if (p.emb) p.emb[static_cast<long long>(w) * p.feat + c] = v;
+      if (p.emb && p.mlp_hidden == 0) p.emb[static_cast<long long>(w) * p.feat + c] = v;
+    }
+    if (p.mlp_hidden > 0) {
+      // legacy head: Dense(h, gelu) -> Dense(h, gelu) = "embedding" (nnlib/v1/layers.py:414-419);
+      // requires mlp_hidden == feat so the buffers can be reused
+      __syncwarp();
+      for (int layer = 0; layer < 2; ++layer) {
+        const float* W = layer == 0 ? p.mlp_w1 : p.mlp_w2;
+        const float* B = layer == 0 ? p.mlp_b1 : p.mlp_b2;
+        float outv[8];                                   // up to 256 hidden units per warp
+        for (int h = lane, i = 0; h < p.mlp_hidden; h += 32, ++i) {
+          float acc = 0.0f;
+          for (int c = 0; c < p.feat; ++c) acc = fmaf(feat[c], W[c * p.mlp_hidden + h], acc);
+          outv[i] = act_apply(acc + B[h], p.mlp_act);
+        }
+        __syncwarp();
+        for (int h = lane, i = 0; h < p.mlp_hidden; h += 32, ++i) feat[h] = outv[i];
+        __syncwarp();
+      }
+      if (p.emb)
+        for (int c = lane; c < p.feat; c += 32) p.emb[static_cast<long long>(w) * p.feat + c] = feat[c];
     }
     for (int i = lane; i < nmd_dim; i += 32) {
       const int t = i / p.tap_width, c = i - t * p.tap_width;

@@ -90,7 +90,8 @@ class WindowTable:
 class B200Engine:
     def __init__(self, path_dict: dict[str, Any] | None = None, *, spec: ModelSpec | None = None,
                  weights: dict[str, Any] | None = None, device: int = 0, workspace_gb: float = 16.0,
-                 seed: int = 0, use_ref_kernels: bool = False):
+                 seed: int = 0, use_ref_kernels: bool = False, legacy_weights: dict[str, Any] | None = None,
+                 all_labels: bool = False):
         if not torch.cuda.is_available():
             raise _cabi.JaegerB200Error("no CUDA device: jaeger_b200 has no CPU fallback")
         self.device = int(device)
@@ -98,6 +99,17 @@ class B200Engine:
         self.ctx = _cabi.Context(self.device)
         self.use_ref_kernels = bool(use_ref_kernels)
         self.class_map = None
+        if legacy_weights is not None:
+            # the bundled `default` model (predict_legacy.py:188-221): fixed graph, legacy encoder
+            from . import legacy
+            self.spec, self.weights = None, legacy_weights
+            labels = legacy.ALL_LABELS if all_labels else legacy.DEFAULT_LABELS
+            self.class_map = {"num_classes": 4, "class": [labels[i] for i in range(4)], "index": [0, 1, 2, 3]}
+            self.string_processor_config = {"input_type": "translated", "legacy": True, "masking": True}
+            self.plan = legacy.compile_legacy_plan(legacy_weights)
+            self.lut, self.case_sensitive = legacy.LEGACY_LUT, 1
+            self._create_model(workspace_gb)
+            return
         if path_dict is not None:
             project = path_dict.get("project")
             if project is None:
@@ -116,14 +128,17 @@ class B200Engine:
                               "index": [c["label"] for c in spec.classes]}
         self.string_processor_config = string_processor_config(spec)
         self.plan: Plan = compile_plan(spec, self.weights)
-        layers, head = to_ctypes(self.plan)
-        h = ctypes.c_void_p()
-        check(lib.jg_model_create(self.ctx.handle, layers, len(self.plan.launches), ctypes.byref(head), 6, 65,
-                                  ctypes.byref(h)))
-        self.model = h
-        self.workspace_bytes = int(workspace_gb * (1 << 30))
         self.lut = codon_tables.device_lut(self.string_processor_config["codon_id"], plus_one=True)
         self.case_sensitive = int(self.string_processor_config["masking"])
+        self._create_model(workspace_gb)
+
+    def _create_model(self, workspace_gb: float) -> None:
+        layers, head = to_ctypes(self.plan)
+        h = ctypes.c_void_p()
+        check(lib.jg_model_create(self.ctx.handle, layers, len(self.plan.launches), ctypes.byref(head), 6,
+                                  int(self.plan.tok_offset), ctypes.byref(h)))
+        self.model = h
+        self.workspace_bytes = int(workspace_gb * (1 << 30))
         self.windows = WindowTable()
         self.timings: dict[str, float] = {}
 

@@ -31,7 +31,7 @@ LAYER_PTR_FIELDS = 12
 # int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
- LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN) = range(21)
+ LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS) = range(22)
 (LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN) = range(8)
 
 
@@ -42,10 +42,13 @@ class LayerDesc(ctypes.Structure):
 
 class HeadDesc(ctypes.Structure):
     _fields_ = [("n_classes", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("pool_mode", ctypes.c_int32),
-                ("n_taps", ctypes.c_int32), ("rel_hidden", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+                ("n_taps", ctypes.c_int32), ("rel_hidden", ctypes.c_int32), ("mlp_hidden", ctypes.c_int32),
+                ("mlp_act", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1),
                 ("cls_w", ctypes.POINTER(ctypes.c_float)), ("cls_b", ctypes.POINTER(ctypes.c_float)),
                 ("rel_w1", ctypes.POINTER(ctypes.c_float)), ("rel_b1", ctypes.POINTER(ctypes.c_float)),
-                ("rel_w2", ctypes.POINTER(ctypes.c_float)), ("rel_b2", ctypes.POINTER(ctypes.c_float))]
+                ("rel_w2", ctypes.POINTER(ctypes.c_float)), ("rel_b2", ctypes.POINTER(ctypes.c_float)),
+                ("mlp_w1", ctypes.POINTER(ctypes.c_float)), ("mlp_b1", ctypes.POINTER(ctypes.c_float)),
+                ("mlp_w2", ctypes.POINTER(ctypes.c_float)), ("mlp_b2", ctypes.POINTER(ctypes.c_float))]
 
 
 @dataclass
@@ -77,6 +80,8 @@ class ConvLaunch:
     sc_const: np.ndarray | None = None
     out_const: np.ndarray | None = None   # value of this launch's output at rows its mask zeroed
     stage: int = 0                        # epilogue fill state while compiling
+    kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool
+    halvings: int = 0                     # MaxPool(2) stages applied to the frame length before this layer
 
 
 @dataclass
@@ -92,6 +97,9 @@ class Plan:
     rel: list[np.ndarray] | None
     rel_hidden: int
     total_shrink: int
+    tok_offset: int = 1
+    mlp: list[np.ndarray] | None = None        # legacy head: [w1, b1, w2, b2]
+    mlp_act: str | None = None
     flops_per_window_formula: Any = None
     keep: list[Any] = field(default_factory=list)   # keeps ctypes-referenced arrays alive
 
@@ -101,10 +109,12 @@ class Plan:
         reference multiplies with."""
         f = 0.0
         for i, c in enumerate(self.launches):
+            if c.kind != 1:
+                continue
             k, cin, cout = c.kernel.shape
             if i == 0 and algorithmic_stem_cin:
                 cin = algorithmic_stem_cin
-            f += 2.0 * frames * (lc - c.cum_shrink_in - c.shrink) * k * cin * cout
+            f += 2.0 * frames * (((lc - c.cum_shrink_in) >> c.halvings) - c.shrink) * k * cin * cout
         return f
 
 
@@ -307,7 +317,7 @@ def to_ctypes(plan: Plan):
     arr = (LayerDesc * len(plan.launches))()
     for d, c in zip(arr, plan.launches):
         k, cin, cout = c.kernel.shape
-        vals = {LF_KIND: 1, LF_CIN: cin, LF_COUT: cout, LF_K: k, LF_DIL: c.dilation, LF_PAD_LEFT: c.pad_left,
+        vals = {LF_KIND: c.kind, LF_HALVINGS: c.halvings, LF_CIN: cin, LF_COUT: cout, LF_K: k, LF_DIL: c.dilation, LF_PAD_LEFT: c.pad_left,
                 LF_SHRINK: c.shrink, LF_IN_BUF: c.in_buf, LF_OUT_BUF: c.out_buf, LF_SC_BUF: c.sc_buf,
                 LF_ACT1: ACT[c.act1], LF_HAS_AFF2: int(c.scale2 is not None), LF_ACT2: ACT[c.act2],
                 LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
@@ -325,5 +335,8 @@ def to_ctypes(plan: Plan):
     h.cls_w, h.cls_b = _fptr(plan.cls_w), _fptr(plan.cls_b)
     if plan.rel is not None:
         h.rel_w1, h.rel_b1, h.rel_w2, h.rel_b2 = (_fptr(a) for a in plan.rel)
+    if plan.mlp is not None:
+        h.mlp_hidden, h.mlp_act = plan.mlp[0].shape[1], ACT[plan.mlp_act]
+        h.mlp_w1, h.mlp_b1, h.mlp_w2, h.mlp_b2 = (_fptr(a) for a in plan.mlp)
     plan.keep = [arr, h]
     return arr, h

@@ -205,6 +205,15 @@ def main():
     for arr_ in ([[0, 3], [2, 5], [8, 9]], [[1, 2]], [[0, 10], [2, 3], [11, 12], [12, 20]]):
         merges.append(dict(inp=arr_, out=[list(map(int, r)) for r in rhelp.merge_overlapping_ranges(np.array(arr_))]))
     (OUT / "merge_ranges.json").write_text(json.dumps(merges))
+    # ---- BASELINE config 1 fixture: the bundled legacy `default` weights + the health FASTA --------
+    from jaeger_b200 import legacy
+    from jaeger_b200.weights import read_tf_bundle, _flatten
+    w = legacy.weights_from_bundle(read_tf_bundle(REF / "jaeger" / "data" / "models" / "test" / "jaeger_fragment_graph" / "variables"))
+    flat = {}
+    _flatten(w, "", flat)
+    health = list(_Fasta(str(fasta)))
+    np.savez_compressed(OUT / "legacy_default.npz", names=np.array([n for n, _ in health]),
+                        seqs=np.array([q for _, q in health]), **{f"w/{k}": v for k, v in flat.items()})
     print("goldens written to", OUT)
 
 

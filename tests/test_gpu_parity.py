@@ -382,3 +382,48 @@ def test_prophage_region_calling_vs_oracle(standin):
         assert np.allclose(scores, want_s, atol=1e-6)
         if islands:
             assert len(ranges) >= 1 and all(any(abs(r[0] - a) <= 12 and abs(r[1] - b) <= 12 for a, b in islands) for r in ranges)
+
+
+def _legacy_fixture():
+    from jaeger_b200.weights import load_npz_weights
+    z = np.load(G / "legacy_default.npz")
+    flat = {k[2:]: z[k] for k in z.files if k.startswith("w/")}
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".npz") as fh:
+        np.savez(fh.name, **flat)
+        w = load_npz_weights(fh.name)
+    recs = [(str(n), str(s)) for n, s in zip(z["names"], z["seqs"])]
+    return w, recs
+
+
+def test_legacy_default_model_on_health_fasta_vs_oracle():
+    """BASELINE config 1: the bundled `default` weights on the reference's health FASTA
+    (135 windows at the CLI defaults).  Tolerance: bf16 activations vs the fp32 oracle with real
+    weights, |logit| ~ 3-10: max |diff| <= 0.15 and identical per-window / per-contig labels."""
+    from jaeger_b200 import B200Engine, WindowSource
+    from jaeger_b200 import codon_tables as ct
+    from jaeger_b200.postprocess import contig_table
+    from oracle import encode as oenc
+    from oracle import legacy as oleg
+    from oracle import postprocess as opp
+    from oracle import seqwin
+    w, recs = _legacy_fixture()
+    eng = B200Engine(legacy_weights=w)
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500))
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    assert len(wins) == 135 == y["prediction"].shape[0]                 # SURVEY.md 8d config 1
+    table = dict(zip(oenc.CODONS, ct.LEGACY_AA_ID))
+    tok = np.stack([oenc.encode_window_legacy(x.seq, 2000, table) for x in wins]).astype(np.uint8)
+    ref = oleg.forward(w, tok)
+    d = np.abs(ref["output"] - y["prediction"])
+    assert d.max() <= 0.15, d.max()
+    assert np.abs(ref["embedding"] - y["embedding"]).max() <= 0.15
+    differ = np.flatnonzero(ref["output"].argmax(1) != y["prediction"].argmax(1))
+    top2 = np.sort(ref["output"], axis=1)
+    margins = top2[:, -1] - top2[:, -2]
+    assert len(differ) <= 2 and np.all(margins[differ] < 2 * d.max()), (differ, margins[differ], d.max())   # only near-ties may flip
+    print(f"legacy: max|logit diff| {d.max():.4f}, windows with different argmax {len(differ)} (margins {margins[differ]})")
+    data = contig_table(eng, y, 2000)
+    agg = opp.aggregate_numeric(ref["output"], None, np.array([x.is_last for x in wins]))
+    assert np.array_equal(data["consensus"], agg["consensus"])           # 9 / 9 contig labels
+    eng.close()
