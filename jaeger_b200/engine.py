@@ -248,6 +248,8 @@ class B200Engine:
                 out["reliability"][b:e].data_ptr() if "reliability" in out else None,
                 out["embedding"][b:e].data_ptr(),
                 out["nmd"][b:e].data_ptr() if "nmd" in out else None, int(self.use_ref_kernels)))
+        if p.real_feat_dim is not None and p.real_feat_dim != p.feat_dim:
+            out["embedding"] = out["embedding"][:, :p.real_feat_dim]     # drop the zero padding channels
         return out
 
     def aggregate(self, logits: torch.Tensor, rel: torch.Tensor | None, offsets: torch.Tensor) -> dict[str, torch.Tensor]:

@@ -97,6 +97,7 @@ class Plan:
     rel: list[np.ndarray] | None
     rel_hidden: int
     total_shrink: int
+    real_feat_dim: int | None = None           # feature width before padding to a multiple of 64
     tok_offset: int = 1
     mlp: list[np.ndarray] | None = None        # legacy head: [w1, b1, w2, b2]
     mlp_act: str | None = None
@@ -283,6 +284,31 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
     for c in launches:
         if c.out_const is None:
             finish(c)
+    # The tensor-core kernel works on channel groups of 64: narrower layers (e.g. the 32-filter
+    # 500 bp model) are zero-padded -- padded output channels stay exactly 0 through bias-free
+    # affine / GELU / residual / pooling, padded input channels meet zero weights.
+    real_feat = ch
+    for c in launches:
+        k, cin, cout = c.kernel.shape
+        cin_p, cout_p = -(-cin // 64) * 64, -(-cout // 64) * 64
+        if (cin_p, cout_p) == (cin, cout):
+            continue
+        if c.tap_mode:
+            raise NotImplementedError("NMD taps on layers narrower than a multiple of 64 channels")
+        kp = np.zeros((k, cin_p, cout_p), np.float32)
+        kp[:, :cin, :cout] = c.kernel
+        c.kernel = kp
+
+        def pad(a, fill):
+            if a is None:
+                return None
+            out = np.full(cout_p, fill, np.float32)
+            out[:cout] = a
+            return out
+        c.bias, c.shift1, c.shift2 = pad(c.bias, 0.0), pad(c.shift1, 0.0), pad(c.shift2, 0.0)
+        c.scale1, c.scale2 = pad(c.scale1, 1.0), pad(c.scale2, 1.0)
+        c.sc_const, c.out_const = pad(c.sc_const, 0.0), pad(c.out_const, 0.0)
+    ch = -(-ch // 64) * 64
     last = launches[-1]
     last.pool_mode = 1 if spec.pooling == "max" else 2
     last.out_buf = -1                    # the final feature map is only pooled: nothing reads it
@@ -301,9 +327,11 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             raise NotImplementedError("reliability hidden activation other than gelu")
         rel = [_np32(r[0]["kernel"]), _np32(r[0]["bias"]), _np32(r[1]["kernel"]), _np32(r[1]["bias"])]
         rel_hidden = r[0]["kernel"].shape[1]
+    cls_w = np.zeros((ch, spec.n_classes), np.float32)
+    cls_w[:real_feat] = weights["classifier"][0]["kernel"]
     return Plan(launches=launches, n_classes=spec.n_classes, feat_dim=ch, pool_mode=last.pool_mode, n_taps=n_taps,
-                tap_width=tap_width, cls_w=_np32(weights["classifier"][0]["kernel"]),
-                cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel, rel_hidden=rel_hidden, total_shrink=cum_shrink)
+                tap_width=tap_width, cls_w=cls_w, cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel,
+                rel_hidden=rel_hidden, total_shrink=cum_shrink, real_feat_dim=real_feat)
 
 
 def _fptr(a: np.ndarray | None):

@@ -66,7 +66,8 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
             pooled = (v * mo).sum(dim=(1, 2)) / torch.clamp(m_out.sum(dim=(1, 2)).unsqueeze(-1), min=1e-7)
         if c.out_buf >= 0:
             bufs[c.out_buf] = v * mo
-    out = {"embedding": pooled, "prediction": pooled @ torch.as_tensor(plan.cls_w, dtype=dt) + torch.as_tensor(plan.cls_b, dtype=dt)}
+    real = plan.real_feat_dim or plan.feat_dim
+    out = {"embedding": pooled[:, :real], "prediction": pooled @ torch.as_tensor(plan.cls_w, dtype=dt) + torch.as_tensor(plan.cls_b, dtype=dt)}
     if taps:
         out["nmd"] = torch.cat([taps[i] for i in range(len(taps))], dim=-1)
         if plan.rel is not None:

@@ -427,3 +427,34 @@ def test_legacy_default_model_on_health_fasta_vs_oracle():
     agg = opp.aggregate_numeric(ref["output"], None, np.array([x.is_last for x in wins]))
     assert np.array_equal(data["consensus"], agg["consensus"])           # 9 / 9 contig labels
     eng.close()
+
+
+def test_500bp_baseline_model_config3():
+    """BASELINE config 3: the 500 bp / 32-filter / average-pool architecture (random init) on
+    500 bp fragments; channels zero-padded to 64 on the device."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    def conv(f, k):
+        return {"name": "masked_conv1d", "config": {"filters": f, "kernel_size": k, "strides": 1, "dilation_rate": 1, "use_bias": True, "activation": None}}
+    bn_act = [{"name": "masked_batchnorm", "config": {"return_nmd": False}}, {"name": "activation", "config": {"activation": "gelu"}}]
+    cfg = {"model": {"name": "jaeger_500bp_baseline", "activation": "gelu",
+                     "class_label_map": [{"class": c, "label": i} for i, c in enumerate(["chromosome", "virus", "plasmid"])],
+                     "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 64},
+                     "string_processor": {"seq_onehot": False, "codon": "CODON", "codon_id": "CODON_ID", "crop_size": 500, "masking": False},
+                     "representation_learner": {"hidden_layers": [conv(32, 7)] + bn_act + [
+                         {"name": "residual_block", "config": {"use_1x1conv": False, "block_size": 2, "filters": 32, "kernel_size": 3, "use_bias": True}}] + bn_act,
+                         "pooling": "average"},
+                     "classifier": {"input_shape": 32, "hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None, "use_bias": True}}]}}}
+    spec = parse_project(cfg)
+    w = init_random(spec, 2)
+    eng = B200Engine(spec=spec, weights=w)
+    recs = random_contigs(2, [500] * 300 + [499, 1700], n_run_every=7, lower_every=0)
+    y = eng.predict(WindowSource(records=recs, fsize=500, stride=500))
+    seqs = [s[i:i + 500] for _, s in recs for i in range(0, len(s) - 499, 500)]
+    assert y["prediction"].shape == (len(seqs), 3) == (303, 3) and y["embedding"].shape[1] == 32
+    ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 500))
+    assert np.abs(ref["prediction"] - y["prediction"]).max() <= 4e-3
+    assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2
+    eng.close()

@@ -134,3 +134,20 @@ def test_host_window_planner_two_pass_and_ragged():
     # empty input
     c3, *_ = B200Engine.plan_windows(np.zeros(0, dtype=np.int64), 2000, 1500)
     assert len(c3) == 0
+
+
+@pytest.mark.skipif(not REF_CFG.exists(), reason="reference checkout not mounted")
+def test_500bp_baseline_config_with_narrow_layers_is_padded_correctly():
+    """BASELINE config 3 (nn_config_500bp_baseline.yaml: 32 filters): channels are zero-padded to
+    64 for the tensor-core kernel; the padded plan must still equal the un-fused oracle."""
+    cfg = yaml.safe_load((REF_CFG / "nn_config_500bp_baseline.yaml").read_text())
+    spec = parse_project(cfg)
+    w = init_random(spec, 2)
+    plan = compile_plan(spec, w)
+    assert [c.kernel.shape for c in plan.launches] == [(7, 64, 64)] + [(3, 64, 64)] * 4
+    assert plan.feat_dim == 64 and plan.real_feat_dim == 32 and plan.pool_mode == 2 and plan.rel is None
+    tok = _tokens(4, 3, 165)
+    ref = ofw.forward(spec, w, tok, dtype=torch.float64)
+    got = run_plan(plan, tok)
+    for k in ref:
+        assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), k
