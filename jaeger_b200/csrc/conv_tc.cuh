@@ -17,8 +17,8 @@
 //   * D: fp32 in TMEM, a ring of 4 accumulators (4 x Cout columns) so the MMAs run up to
 //     three tiles ahead of the epilogues.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4..11 = two epilogue groups (TMEM lane quarter = warp % 4)
-// that drain alternate tiles, so the latency chain of one tile's epilogue (mask/shortcut
+// warp 2 = TMEM allocator, warps 4.. = kEpiGroups epilogue groups (TMEM lane quarter = warp % 4)
+// that drain tiles round-robin, so the latency chain of one tile's epilogue (mask/shortcut
 // loads, TMEM reads, stores) overlaps the next tile's.
 #pragma once
 #include "conv_common.cuh"
@@ -26,8 +26,11 @@
 namespace jg {
 namespace tc {
 
-constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
-constexpr int kEpiThreads = 256;
+#ifndef JG_EPI_GROUPS
+#define JG_EPI_GROUPS 3
+#endif
+constexpr int kEpiGroups = JG_EPI_GROUPS;                // epilogue warpgroups (4 warps each)
+constexpr int kThreads = 128 + 128 * kEpiGroups;         // 4 control warps + the epilogue warps
 constexpr int kEpiWarp0 = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.n_tiles / gridDim.x);
   const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.n_tiles / gridDim.x);
 
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[519] = clock64();
   // ---- one-time setup ------------------------------------------------------------------
   for (int i = threadIdx.x; i < p.cout; i += kThreads) {
     s_par[i] = p.scale1[i];
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     mbar_init(WBAR, 1);
     for (int a = 0; a < 4; ++a) {
       mbar_init(TFULL(a), 1);
-      mbar_init(TEMPTY(a), kEpiThreads / 2);  // one epilogue group (4 warps) drains a tile
+      mbar_init(TEMPTY(a), 128);  // one epilogue group (4 warps) drains a tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -273,7 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long r_first = static_cast<long long>(tile) * kTileM - L.lead;
       for (uint32_t g = 0; g < L.groups; ++g) {
+        const long long tw0 = p.dbg ? clock64() : 0;
         mbar_wait(EMPTY(s), ph ^ 1u);
+        if (p.dbg && blockIdx.x == 0 && leader) p.dbg[520] += clock64() - tw0;      // producer: wait for a free stage
         if (leader) {
           mbar_expect_tx(FULL(s), L.stage_bytes);
           const __nv_bfloat16* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
@@ -299,14 +305,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int as = it % n_acc;
       const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
+      const long long tw1 = p.dbg ? clock64() : 0;
       mbar_wait(TEMPTY(as), aph ^ 1u);
       tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && leader) p.dbg[521] += clock64() - tw1;        // MMA: wait for a free accumulator
       if (p.dbg && blockIdx.x == 0 && leader && it < 64) p.dbg[it * 8 + 0] = clock64();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.cout);
       uint32_t accumulate = 0;
       for (uint32_t g = 0; g < L.groups; ++g) {
+        const long long tw2 = p.dbg ? clock64() : 0;
         mbar_wait(FULL(s), ph);
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && leader) p.dbg[522] += clock64() - tw2;      // MMA: wait for operands
         const uint32_t a_lo = desc_lo_sw128(st_base + s * stage_pitch + L.lead * 128u);
         const uint32_t b_lo = b_lo0 + g * b_group_step;
 #pragma unroll 1
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> fused affine/residual/activation/taps -> HBM =====
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int grp = (warp - kEpiWarp0) >> 2;   // epilogue group: drains tiles with (it & 1) == grp
+    const int grp = (warp - kEpiWarp0) >> 2;   // epilogue group: drains tiles with it % kEpiGroups == grp
     const int n_cb = p.cout / 32;
     const float4* s_scale1 = reinterpret_cast<const float4*>(s_par);
     const float4* s_shift1 = reinterpret_cast<const float4*>(s_par + p.cout);
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const float4* s_bias = reinterpret_cast<const float4*>(s_par + 4 * p.cout);
     const float4* s_scc = reinterpret_cast<const float4*>(s_par + 5 * p.cout);
     const bool has_sc = p.sc != nullptr;
-    for (int tile = tile_begin + grp, it = grp; tile < tile_end; tile += 2, it += 2) {
+    for (int tile = tile_begin + grp, it = grp; tile < tile_end; tile += kEpiGroups, it += kEpiGroups) {
       const int as = it % n_acc;
       const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
       const long long row = static_cast<long long>(tile) * kTileM + q * 32 + lane;
@@ -355,8 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           scv[j] = *reinterpret_cast<const uint4*>(p.sc + row * 64 + ((j ^ sw) * 8));
       }
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 2] = clock64();
+      const long long tw3 = p.dbg ? clock64() : 0;
       mbar_wait(TFULL(as), aph);
       tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0) p.dbg[524 + grp] += clock64() - tw3;   // epilogue group: wait for MMAs
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
       for (int cb = 0; cb < n_cb; ++cb) {
         uint32_t raw[32];
@@ -474,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   }
 
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[523] = clock64();
   // ---- teardown ------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();

@@ -174,16 +174,20 @@ int main(int argc, char** argv) {
   printf("RESULT shape %d variant %d: %s\n", shape, variant, ok ? "MATCH" : "MISMATCH");
 
   if (getenv("JG_TRACE")) {
-    long long* ddbg; CK(cudaMalloc(&ddbg, 64 * 8 * 8)); CK(cudaMemset(ddbg, 0, 64 * 8 * 8));
+    long long* ddbg; CK(cudaMalloc(&ddbg, 1024 * 8)); CK(cudaMemset(ddbg, 0, 1024 * 8));
     jg::ConvParams pd = pt; pd.dbg = ddbg;
-    for (int i = 0; i < 3; ++i) CK(jg::launch_conv_tc(pd, dev_sms, 0));
+    for (int i = 0; i < 3; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
+    CK(jg::launch_conv_tc(pd, dev_sms, 0));
     CK(cudaDeviceSynchronize());
-    std::vector<long long> h(64 * 8);
+    std::vector<long long> h(1024);
     CK(cudaMemcpy(h.data(), ddbg, h.size() * 8, cudaMemcpyDeviceToHost));
     const long long t0 = h[0];
     printf("trace (cycles rel. to first MMA start): it  mma_start mma_issued | epi_arrive_wait tfull_ready epi_done\n");
     for (int i = 0; i < 16 && h[i * 8] != 0; ++i)
       printf("  %2d  %8lld %8lld | %8lld %8lld %8lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0);
+    const int my_tiles = p.n_tiles / dev_sms;
+    printf("CTA0: total %lld cycles for %d tiles (%.0f /tile); first MMA starts at +%lld; waits: producer(free stage) %lld, MMA(free acc) %lld, MMA(operands) %lld, epi groups(wait MMA) %lld %lld %lld\n",
+           h[523] - h[519], my_tiles, double(h[523] - h[519]) / my_tiles, t0 - h[519], h[520], h[521], h[522], h[524], h[525], h[526]);
   }
   if (iters > 0 && ok) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
