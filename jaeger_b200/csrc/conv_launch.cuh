@@ -2,6 +2,7 @@
 #pragma once
 #include "conv_ref.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 
 namespace jg {
 
@@ -33,6 +34,26 @@ inline cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t
   else if (stages == 3) { JG_LAUNCH(3) }
   else { JG_LAUNCH(2) }
 #undef JG_LAUNCH
+  return cudaGetLastError();
+}
+
+// CTA-pair kernel: eligible when Cout is a multiple of 64, the tile count is even and the
+// per-CTA weights half + 4 stages + the output staging tiles fit in shared memory.
+inline bool conv_tc2_eligible(const ConvParams& p) {
+  if (p.cin % 64 != 0 || p.cout % 64 != 0 || p.cout > 256 || p.ntaps > kMaxTaps || (p.n_tiles & 1)) return false;
+  return tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r).total <= kMaxSmem;
+}
+
+inline cudaError_t launch_conv_tc2(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if (!conv_tc2_eligible(p)) return cudaErrorInvalidConfiguration;
+  const tc2::SmemLayout2 L = tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r);
+  int pairs = num_sms / 2;
+  if (pairs > p.n_tiles / 2) pairs = p.n_tiles / 2;
+  if (pairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(L.total));
+  if (e != cudaSuccess) return e;
+  tc2::conv_tc2_kernel<<<2 * pairs, tc2::kThreads2, L.total, stream>>>(p);
   return cudaGetLastError();
 }
 

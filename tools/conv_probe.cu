@@ -3,7 +3,7 @@
 // shape:   0 = residual conv (Cin 128, Cout 128, k5 d3, SAME, shortcut + taps + pool)
 //          1 = stem conv     (Cin 64,  Cout 128, k7 d1, VALID, raw tap)
 //          2 = wide-dilation conv (Cin 64, Cout 64, k5 d8, SAME)
-// variant: unused (kept for CLI compatibility)
+// variant: 0 = single-CTA kernel (conv_tc.cuh), 2 = CTA-pair kernel (conv_tc2.cuh)
 // Compares conv_tc_kernel against conv_ref_kernel on the same random inputs and prints
 // max |diff|; with time_iters > 0 also times the tensor-core kernel with CUDA events.
 #include <cstdio>
@@ -93,6 +93,14 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dsc, hsc.data(), hsc.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  // the CTA-pair kernel reads the same weights from its own (half-split) image
+  std::vector<uint16_t> hw2(hw.size());
+  for (int t = 0; t < k; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co)
+        hw2[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = hw[jg::w_index(t, ci, co, cin, cout)];
+  uint16_t* dw2; CK(cudaMalloc(&dw2, hw2.size() * 2));
+  CK(cudaMemcpy(dw2, hw2.data(), hw2.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dmask, hmask.data(), R, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dscmask, hscmask.data(), R, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dpar, hpar.data(), hpar.size() * 4, cudaMemcpyHostToDevice));
@@ -125,6 +133,7 @@ int main(int argc, char** argv) {
   if (strip & 1) { p.tap_mode = 0; p.pool_mode = 0; }
   if (strip & 2) { p.act1 = jg::ACT_NONE; p.act2 = jg::ACT_NONE; p.has_affine2 = 0; }
   if (strip & 4) { p.sc = nullptr; p.sc_mask = nullptr; }
+  if (strip & 16) { p.has_affine2 = 0; p.act2 = jg::ACT_NONE; }
   p.err = derr;
   (void)variant;
 
@@ -139,7 +148,9 @@ int main(int argc, char** argv) {
   jg::ConvParams pt = p;
   pt.y = reinterpret_cast<__nv_bfloat16*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
   if (strip & 8) { pt.y = nullptr; }
-  CK(jg::launch_conv_tc(pt, dev_sms, 0));
+  auto launch = [&](const jg::ConvParams& q) { return variant == 2 ? jg::launch_conv_tc2(q, dev_sms, 0) : jg::launch_conv_tc(q, dev_sms, 0); };
+  if (variant == 2) pt.w = reinterpret_cast<const __nv_bfloat16*>(dw2);
+  CK(launch(pt));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
     int herr = -1; cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
@@ -176,8 +187,8 @@ int main(int argc, char** argv) {
   if (getenv("JG_TRACE")) {
     long long* ddbg; CK(cudaMalloc(&ddbg, 1024 * 8)); CK(cudaMemset(ddbg, 0, 1024 * 8));
     jg::ConvParams pd = pt; pd.dbg = ddbg;
-    for (int i = 0; i < 3; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
-    CK(jg::launch_conv_tc(pd, dev_sms, 0));
+    for (int i = 0; i < 3; ++i) CK(launch(pt));
+    CK(launch(pd));
     CK(cudaDeviceSynchronize());
     std::vector<long long> h(1024);
     CK(cudaMemcpy(h.data(), ddbg, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -185,7 +196,7 @@ int main(int argc, char** argv) {
     printf("trace (cycles rel. to first MMA start): it  mma_start mma_issued | epi_arrive_wait tfull_ready epi_done\n");
     for (int i = 0; i < 16 && h[i * 8] != 0; ++i)
       printf("  %2d  %8lld %8lld | %8lld %8lld %8lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0);
-    const int my_tiles = p.n_tiles / dev_sms;
+    const int my_tiles = p.n_tiles / dev_sms;   // per CTA (pair kernel: 128-row tiles of this CTA)
     printf("CTA0: total %lld cycles for %d tiles (%.0f /tile); first MMA starts at +%lld; waits: producer(free stage) %lld, MMA(free acc) %lld, MMA(operands) %lld, epi groups(wait MMA) %lld %lld %lld\n",
            h[523] - h[519], my_tiles, double(h[523] - h[519]) / my_tiles, t0 - h[519], h[520], h[521], h[522], h[524], h[525], h[526]);
   }
@@ -196,13 +207,13 @@ int main(int argc, char** argv) {
       cudaEvent_t w0, w1; cudaEventCreate(&w0); cudaEventCreate(&w1);
       float wms = 0; CK(cudaEventRecord(w0));
       while (wms < 1500.0f) {
-        for (int i = 0; i < 20; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
+        for (int i = 0; i < 20; ++i) CK(launch(pt));
         CK(cudaEventRecord(w1)); CK(cudaEventSynchronize(w1));
         cudaEventElapsedTime(&wms, w0, w1);
       }
     }
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(jg::launch_conv_tc(pt, dev_sms, 0));
+    for (int i = 0; i < iters; ++i) CK(launch(pt));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     const double flops = 2.0 * static_cast<double>(R) * ktot * cout;
