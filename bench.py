@@ -304,7 +304,7 @@ def run_b200(args):
                 "whole_model_tflops": plan.flops_per_window(lc, algorithmic_stem_cin=spec.embedding_size) * tot_windows / world / (ms * 1e-3) / 1e12}
     line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_mbp_per_gpu_per_step": args.batch_mbp,
                        "l2_policy": "inputs larger than L2: a different 64 Mbp batch every step, ~100 GB of activations per step",
                        "parallelism": f"length-balanced contig sharding x{world} (LPT on window counts), NCCL gather of per-contig records only"},

@@ -1,7 +1,7 @@
 // Shared definitions for the stage-3 (masked dilated Conv1D stack) kernels.
 //
 // Activation layout in HBM ("g64sw": channel groups of 64, rows pre-swizzled):
-//     act[g][row][64]  bf16,   g = C/64,  row in [-GUARD, R + GUARD)
+//     act[g][row][64]  fp16,   g = C/64,  row in [-GUARD, R + GUARD)
 // inside a row's 128 bytes the eight 16-byte chunks are stored XOR-swizzled by the row
 // number (chunk c of row r sits at chunk position c ^ (r & 7)).  That is exactly the
 // shared-memory image the tensor core's SWIZZLE_128B K-major operand layout expects when
@@ -15,11 +15,17 @@
 // gets from TF "SAME" padding (reference: src/jaeger/nnlib/v2/layers.py:1217-1280).
 // With this layout a conv tap is a pure row shift of the operand descriptor.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace jg {
+
+// Activations and conv weights are stored as IEEE fp16 (11 significand bits; fp32 accumulation in
+// the tensor core, fp32 BatchNorm affine).  fp16 rather than bf16 because the epilogue can then
+// run its GELU / residual / second affine as packed half2 arithmetic directly on the stored
+// format, which halves its instruction count; conversions saturate at +-65504.
+using act_t = __half;
 
 constexpr int kTileM = 128;        // rows (positions) per MMA tile == TMEM lanes
 constexpr int kMaxTaps = 16;
@@ -30,13 +36,13 @@ enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_RELU = 2, ACT_GELU_ERF = 3
 // One conv layer launch.  All pointers are device pointers.
 struct ConvParams {
   // tensors -------------------------------------------------------------
-  const __nv_bfloat16* x;       // input, g64sw, points at row 0 of group 0
-  __nv_bfloat16* y;             // output, g64sw (may alias sc), or nullptr (pool-only last layer)
-  const __nv_bfloat16* sc;      // residual shortcut tensor (Cout channels) or nullptr
+  const act_t* x;       // input, g64sw, points at row 0 of group 0
+  act_t* y;             // output, g64sw (may alias sc), or nullptr (pool-only last layer)
+  const act_t* sc;      // residual shortcut tensor (Cout channels) or nullptr
   const uint8_t* sc_mask;       // row mask the shortcut tensor was stored with (nullptr = all valid)
   const float* sc_const;        // [Cout] value of the shortcut at rows its mask zeroed
   const uint8_t* out_mask;      // [R] 1 = valid output row (in frame and mask-propagated)
-  const __nv_bfloat16* w;       // weights, smem image (see w_index)
+  const act_t* w;       // weights, smem image (see w_index)
   const float* bias;            // [Cout] conv bias (used only when tap_raw)
   const float* scale1;          // [Cout] affine after conv (norm folded; bias folded unless tap_raw)
   const float* shift1;
@@ -89,6 +95,40 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
   }
   return v;
+}
+
+// ---- packed half2 epilogue math ------------------------------------------------------------
+__device__ __forceinline__ __half2 cvt_sat_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // hi <- b, lo <- a
+  return *reinterpret_cast<__half2*>(&r);
+}
+// tanh-approximate GELU on two values: hx + hx * tanh(x * (k0 + k0*k1 * x^2)), hx = x/2
+__device__ __forceinline__ __half2 gelu_tanh_h2(__half2 x) {
+  const __half2 k0 = __float2half2_rn(0.7978845608028654f);
+  const __half2 k01 = __float2half2_rn(0.7978845608028654f * 0.044715f);
+  const __half2 u = __hmul2(x, __hfma2(__hmul2(x, x), k01, k0));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  return __hfma2(hx, *reinterpret_cast<const __half2*>(&ti), hx);
+}
+template <int N>
+__device__ __forceinline__ void act_apply_h2(__half2 (&h)[N], int act) {
+  if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = gelu_tanh_h2(h[j]);
+  } else if (act == ACT_RELU) {
+    const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = __hmax2(h[j], z);
+  } else if (act == ACT_GELU_ERF) {      // legacy graph only: exact erf form in fp32
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float2 f = __half22float2(h[j]);
+      h[j] = cvt_sat_h2(act_apply(f.x, ACT_GELU_ERF), act_apply(f.y, ACT_GELU_ERF));
+    }
+  }
 }
 
 // Activation over a register array with the (warp-uniform) selector hoisted out of the loop,

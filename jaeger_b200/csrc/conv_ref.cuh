@@ -18,8 +18,8 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     for (int t = 0; t < p.ntaps; ++t) {
       const long long r = row + p.shifts[t];
       for (int ci = 0; ci < p.cin; ++ci) {
-        const float xv = __bfloat162float(p.x[act_index(r, ci, p.x_plane)]);
-        const float wv = __bfloat162float(p.w[w_index(t, ci, co, p.cin, p.cout)]);
+        const float xv = __half2float(p.x[act_index(r, ci, p.x_plane)]);
+        const float wv = __half2float(p.w[w_index(t, ci, co, p.cin, p.cout)]);
         acc = fmaf(xv, wv, acc);
       }
     }
@@ -30,7 +30,7 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     float v = fmaf(acc, p.scale1[co], p.shift1[co]);
     if (p.sc) {
       const bool scv = p.sc_mask ? p.sc_mask[row] != 0 : true;
-      v += scv ? __bfloat162float(p.sc[act_index(row, co, p.y_plane)])
+      v += scv ? __half2float(p.sc[act_index(row, co, p.y_plane)])
                : (p.sc_const ? p.sc_const[co] : 0.0f);
     }
     v = act_apply(v, p.act1);
@@ -39,7 +39,7 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.y)
-      p.y[act_index(row, co, p.y_plane)] = __float2bfloat16_rn(valid ? v : 0.0f);
+      p.y[act_index(row, co, p.y_plane)] = __float2half_rn(valid ? v : 0.0f);
   }
 }
 

@@ -21,7 +21,7 @@
 // that drain tiles round-robin, so the latency chain of one tile's epilogue (mask/shortcut
 // loads, TMEM reads, stores) overlaps the next tile's.
 #pragma once
-#include "conv_common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace jg {
 namespace tc {
@@ -163,23 +163,6 @@ __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
-// Column-wise reduction across the 32 lanes of a warp of a [32 lanes][32 columns]
-// register tile.  Afterwards v[0] on lane l holds the reduction of column l.
-template <bool kMax>
-__device__ __forceinline__ void warp_cols_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < off; ++j) {
-      float send = hi ? v[j] : v[j + off];
-      float keep = hi ? v[j + off] : v[j];
-      float r = __shfl_xor_sync(0xffffffffu, send, off);
-      v[j] = kMax ? fmaxf(keep, r) : (keep + r);
-    }
-  }
-}
-
 struct SmemLayout {
   uint32_t w_off, stage_off, par_off, bar_off, total;
   uint32_t stage_bytes, stage_pitch, rows_a, lead, groups, w_bytes;
@@ -233,14 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[519] = clock64();
   // ---- one-time setup ------------------------------------------------------------------
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) {
-    s_par[i] = p.scale1[i];
-    s_par[p.cout + i] = p.shift1[i];
-    s_par[2 * p.cout + i] = p.has_affine2 ? p.scale2[i] : 1.0f;
-    s_par[3 * p.cout + i] = p.has_affine2 ? p.shift2[i] : 0.0f;
-    s_par[4 * p.cout + i] = p.bias ? p.bias[i] : 0.0f;
-    s_par[5 * p.cout + i] = p.sc_const ? p.sc_const[i] : 0.0f;
-  }
+  epi_params_fill(s_par, p, threadIdx.x, kThreads);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(FULL(s), 1);
@@ -282,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (p.dbg && blockIdx.x == 0 && leader) p.dbg[520] += clock64() - tw0;      // producer: wait for a free stage
         if (leader) {
           mbar_expect_tx(FULL(s), L.stage_bytes);
-          const __nv_bfloat16* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
+          const act_t* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
           bulk_g2s(st_base + s * stage_pitch, src, L.stage_bytes, FULL(s));
         }
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -291,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp converged, tcgen05.mma predicated on one elected lane) =====
     const bool leader = elect_one();
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=cout, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N=cout, M=128
+    const uint32_t idesc = (1u << 4) |                    // D = f32, A = B = f16 (format 0)
                            (static_cast<uint32_t>(p.cout >> 3) << 17) |
                            (static_cast<uint32_t>(kTileM >> 4) << 24);
     const uint32_t b_group_step = static_cast<uint32_t>(p.cout) * 8u;  // one [cout][64] block
@@ -342,12 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int grp = (warp - kEpiWarp0) >> 2;   // epilogue group: drains tiles with it % kEpiGroups == grp
     const int n_cb = p.cout / 32;
-    const float4* s_scale1 = reinterpret_cast<const float4*>(s_par);
-    const float4* s_shift1 = reinterpret_cast<const float4*>(s_par + p.cout);
-    const float4* s_scale2 = reinterpret_cast<const float4*>(s_par + 2 * p.cout);
-    const float4* s_shift2 = reinterpret_cast<const float4*>(s_par + 3 * p.cout);
-    const float4* s_bias = reinterpret_cast<const float4*>(s_par + 4 * p.cout);
-    const float4* s_scc = reinterpret_cast<const float4*>(s_par + 5 * p.cout);
+    const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
     for (int tile = tile_begin + grp, it = grp; tile < tile_end; tile += kEpiGroups, it += kEpiGroups) {
       const int as = it % n_acc;
@@ -390,96 +361,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tc_fence_before();
           mbar_arrive(TEMPTY(as));
         }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-
-        if (p.tap_mode == 1) {
-          float tv[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = s_bias[cb * 8 + j4];
-            tv[j4 * 4 + 0] = valid ? v[j4 * 4 + 0] + b.x : 0.0f;
-            tv[j4 * 4 + 1] = valid ? v[j4 * 4 + 1] + b.y : 0.0f;
-            tv[j4 * 4 + 2] = valid ? v[j4 * 4 + 2] + b.z : 0.0f;
-            tv[j4 * 4 + 3] = valid ? v[j4 * 4 + 3] + b.w : 0.0f;
-          }
-          warp_cols_reduce<false>(tv, lane);
-          atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-        }
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 a = s_scale1[cb * 8 + j4], b = s_shift1[cb * 8 + j4];
-          v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
-          v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
-          v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
-          v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
-        }
-        if (has_sc) {
-          if (sc_valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&scc[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                v[j * 8 + 2 * e] += f.x;
-                v[j * 8 + 2 * e + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 c = s_scc[cb * 8 + j4];
-              v[j4 * 4 + 0] += c.x; v[j4 * 4 + 1] += c.y; v[j4 * 4 + 2] += c.z; v[j4 * 4 + 3] += c.w;
-            }
-          }
-        }
-        act_apply_vec(v, p.act1);
-        if (p.tap_mode == 2) {
-          float tv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
-          warp_cols_reduce<false>(tv, lane);
-          atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-        }
-        if (p.has_affine2) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 a = s_scale2[cb * 8 + j4], b = s_shift2[cb * 8 + j4];
-            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
-            v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
-            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
-            v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
-          }
-          act_apply_vec(v, p.act2);
-        }
-        if (p.pool_mode != 0) {
-          float tv[32];
-          if (p.pool_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : -3.0e38f;
-            warp_cols_reduce<true>(tv, lane);
-            if (tv[0] > -1.0e38f)
-              atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
-            warp_cols_reduce<false>(tv, lane);
-            atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-          }
-        }
+        uint4 out[4];
+        epilogue_batch(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
         if (p.y) {
-          __nv_bfloat16* yrow = p.y + (static_cast<long long>(cb >> 1) * p.y_plane + row) * 64;
+          act_t* yrow = p.y + (static_cast<long long>(cb >> 1) * p.y_plane + row) * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(yrow + ((((cb & 1) * 4 + j) ^ sw) * 8)) = o;
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(yrow + ((((cb & 1) * 4 + j) ^ sw) * 8)) = out[j];
         }
       }
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 4] = clock64();

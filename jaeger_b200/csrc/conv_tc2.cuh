@@ -152,14 +152,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
 
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[519] = clock64();
   // ---- one-time setup ------------------------------------------------------------------
-  for (int i = threadIdx.x; i < p.cout; i += kThreads2) {
-    s_par[i] = p.scale1[i];
-    s_par[p.cout + i] = p.shift1[i];
-    s_par[2 * p.cout + i] = p.has_affine2 ? p.scale2[i] : 1.0f;
-    s_par[3 * p.cout + i] = p.has_affine2 ? p.shift2[i] : 0.0f;
-    s_par[4 * p.cout + i] = p.bias ? p.bias[i] : 0.0f;
-    s_par[5 * p.cout + i] = p.sc_const ? p.sc_const[i] : 0.0f;
-  }
+  epi_params_fill(s_par, p, threadIdx.x, kThreads2);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(FULL(s), is_leader ? 2 : 1);     // leader: own producer + the peer's relay
@@ -203,7 +196,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         if (p.dbg && blockIdx.x == 0 && leader_lane) p.dbg[520] += clock64() - tw0;
         if (leader_lane) {
           mbar_expect_tx(FULL(s), L.stage_bytes);
-          const __nv_bfloat16* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
+          const act_t* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
           bulk_g2s(st_base + s * L.stage_pitch, src, L.stage_bytes, FULL(s));
         }
         if (++s == kStages2) { s = 0; ph ^= 1u; }
@@ -213,7 +206,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     if (is_leader) {
       // ===== MMA issuer (leader CTA): one instruction drives both SMs' tensor cores =====
       const bool leader_lane = elect_one();
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.cout >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.cout >> 3) << 17) |   // D f32, A/B f16
                              (static_cast<uint32_t>((2 * kTileM) >> 4) << 24);          // M = 256
       const uint32_t b_group_step = static_cast<uint32_t>(p.cout / 2) * 8u;              // one [cout/2][64] block (>>4)
       const uint32_t b_tap_step = b_group_step * L.groups;
@@ -277,12 +270,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int q = warp & 3;
     const int grp = (warp - kEpiWarp0) >> 2;
     const int n_cb = p.cout / 32;
-    const float4* s_scale1 = reinterpret_cast<const float4*>(s_par);
-    const float4* s_shift1 = reinterpret_cast<const float4*>(s_par + p.cout);
-    const float4* s_scale2 = reinterpret_cast<const float4*>(s_par + 2 * p.cout);
-    const float4* s_shift2 = reinterpret_cast<const float4*>(s_par + 3 * p.cout);
-    const float4* s_bias = reinterpret_cast<const float4*>(s_par + 4 * p.cout);
-    const float4* s_scc = reinterpret_cast<const float4*>(s_par + 5 * p.cout);
+    const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
     const int tid_g = threadIdx.x - (kEpiWarp0 + 4 * grp) * 32;     // 0..127 inside the group
     const uint32_t stage_out = out_base + grp * L.out_groups * L.out_group_bytes;
@@ -329,96 +317,15 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(map_to_cta(TEMPTY(as), 0));
         }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.tap_mode == 1) {
-          float tv[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = s_bias[cb * 8 + j4];
-            tv[j4 * 4 + 0] = valid ? v[j4 * 4 + 0] + b.x : 0.0f;
-            tv[j4 * 4 + 1] = valid ? v[j4 * 4 + 1] + b.y : 0.0f;
-            tv[j4 * 4 + 2] = valid ? v[j4 * 4 + 2] + b.z : 0.0f;
-            tv[j4 * 4 + 3] = valid ? v[j4 * 4 + 3] + b.w : 0.0f;
-          }
-          warp_cols_reduce<false>(tv, lane);
-          atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-        }
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 a = s_scale1[cb * 8 + j4], b = s_shift1[cb * 8 + j4];
-          v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
-          v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
-          v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
-          v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
-        }
-        if (has_sc) {
-          if (sc_valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&scc[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                v[j * 8 + 2 * e] += f.x;
-                v[j * 8 + 2 * e + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 c = s_scc[cb * 8 + j4];
-              v[j4 * 4 + 0] += c.x; v[j4 * 4 + 1] += c.y; v[j4 * 4 + 2] += c.z; v[j4 * 4 + 3] += c.w;
-            }
-          }
-        }
-        act_apply_vec(v, p.act1);
-        if (p.tap_mode == 2) {
-          float tv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
-          warp_cols_reduce<false>(tv, lane);
-          atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-        }
-        if (p.has_affine2) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 a = s_scale2[cb * 8 + j4], b = s_shift2[cb * 8 + j4];
-            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x);
-            v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
-            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z);
-            v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
-          }
-          act_apply_vec(v, p.act2);
-        }
-        if (p.pool_mode != 0) {
-          float tv[32];
-          if (p.pool_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : -3.0e38f;
-            warp_cols_reduce<true>(tv, lane);
-            if (tv[0] > -1.0e38f)
-              atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
-            warp_cols_reduce<false>(tv, lane);
-            atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
-          }
-        }
+        uint4 out[4];
+        epilogue_batch(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
         if (p.y) {
           // staging tile = the exact g64sw image of rows [tile_row0, +128) of channel group cb/2
           const uint32_t srow = stage_out + (cb >> 1) * L.out_group_bytes + row_in_tile * 128u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
             const uint32_t a = srow + ((((cb & 1) * 4 + j) ^ sw) * 16);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(out[j].x), "r"(out[j].y), "r"(out[j].z), "r"(out[j].w) : "memory");
           }
         }
       }

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -39,12 +40,11 @@ inline int grid_for(long long n, int block, int num_sms, int per_sm = 8) {
   return static_cast<int>(g);
 }
 
-inline uint16_t f32_to_bf16(float f) {
-  uint32_t u;
-  std::memcpy(&u, &f, 4);
-  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FC0;  // NaN
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>(u >> 16);
+inline uint16_t f32_to_f16(float f) {
+  const __half h = __float2half_rn(f);        // host-callable; saturates to inf only beyond 65504 (weights never are)
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
 }
 
 }  // namespace
@@ -67,7 +67,8 @@ enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIF
 
 struct Layer {
   int32_t f[JG_LAYER_INT_FIELDS];
-  __nv_bfloat16* w = nullptr;
+  jg::act_t* w = nullptr;      // weights image of the single-CTA kernel (w_index)
+  jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
   float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const  (6 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
   int shifts_h[jg::kMaxTaps];
@@ -85,10 +86,11 @@ struct jg_model {
         *rel_b2 = nullptr, *tap_mean = nullptr, *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr,
         *mlp_b2 = nullptr;
   int final_mask = 0;
+  int conv_impl = 0;            // 0 auto, 1 single-CTA kernel only, 2 CTA-pair kernel wherever eligible (JG_CONV_IMPL)
   std::vector<int> tap_mask_slot;
   // workspace -------------------------------------------------------------------------------
   long long cap_rows = 0, cap_windows = 0;
-  std::vector<__nv_bfloat16*> bufs;
+  std::vector<jg::act_t*> bufs;
   std::vector<uint8_t*> masks;
   int* counts = nullptr;        // [n_masks][cap_windows]
   float* tap_sum = nullptr;     // [n_taps][cap_windows][tap_width]
@@ -117,7 +119,8 @@ void model_geometry(const jg_model* m, int lc, int* period, int* rpw) {
     if (need > p) p = need;
   }
   *period = p;
-  *rpw = (m->frames * p + jg::kTileM - 1) / jg::kTileM * jg::kTileM;
+  // a multiple of 256 rows so that the CTA-pair kernel always sees an even tile count
+  *rpw = (m->frames * p + 2 * jg::kTileM - 1) / (2 * jg::kTileM) * (2 * jg::kTileM);
 }
 
 long long bytes_per_window(const jg_model* m, int rpw) {
@@ -148,7 +151,7 @@ int ensure_workspace(jg_model* m, long long n_windows, long long rows) {
   const long long plane = rows + 2 * jg::kGuardRows;
   int64_t total = 0;
   for (int c : m->buf_channels) {
-    __nv_bfloat16* p = nullptr;
+    jg::act_t* p = nullptr;
     const size_t bytes = static_cast<size_t>(c / 64) * plane * 128;
     JG_CUDA(cudaMalloc(&p, bytes));
     JG_CUDA(cudaMemsetAsync(p, 0, bytes, m->ctx->stream));
@@ -350,9 +353,15 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     for (int t = 0; t < k; ++t)
       for (int ci = 0; ci < cin; ++ci)
         for (int co = 0; co < cout; ++co)
-          img[jg::w_index(t, ci, co, cin, cout)] = f32_to_bf16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
+          img[jg::w_index(t, ci, co, cin, cout)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
     JG_CUDA(cudaMalloc(&L.w, img.size() * 2));
     JG_CUDA(cudaMemcpy(L.w, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    for (int t = 0; t < k; ++t)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
+    JG_CUDA(cudaMalloc(&L.w2, img.size() * 2));
+    JG_CUDA(cudaMemcpy(L.w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     std::vector<float> par(6 * static_cast<size_t>(cout), 0.0f);
     const int order[6] = {LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST};
     for (int a = 0; a < 6; ++a) {
@@ -412,6 +421,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
   }
   JG_CUDA(cudaMalloc(&m->err, 4));
   JG_CUDA(cudaMemset(m->err, 0, 4));
+  if (const char* impl = std::getenv("JG_CONV_IMPL")) m->conv_impl = std::atoi(impl);
   m->prof_ms.assign(m->layers.size(), 0.0);
   m->prof_launches.assign(m->layers.size(), 0);
   m->prof_rows.assign(m->layers.size(), 0.0);
@@ -423,7 +433,7 @@ int jg_model_destroy(jg_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->ctx->device);
   free_workspace(m);
-  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.par); cudaFree(L.shifts); }
+  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.par); cudaFree(L.shifts); }
   for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
                    m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
@@ -546,7 +556,13 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       JG_CUDA(cudaEventCreate(&ev1));
       JG_CUDA(cudaEventRecord(ev0, st));
     }
-    cudaError_t e = use_ref ? jg::launch_conv_ref(p, st) : jg::launch_conv_tc(p, ctx->num_sms, st);
+    // Kernel choice (profiles/conv_kernel_r1.md): the CTA-pair kernel wins on light epilogues; layers
+    // with an NMD tap / second affine are epilogue-bound and run better with three epilogue groups.
+    const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
+    const bool pair = !use_ref && m->conv_impl != 1 && (m->conv_impl == 2 || !heavy) && jg::conv_tc2_eligible(p);
+    if (pair) p.w = L.w2;
+    cudaError_t e = use_ref ? jg::launch_conv_ref(p, st)
+                            : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
     if (m->profiling) {

@@ -18,7 +18,7 @@ struct RowGeom {
 // (gap / tail rows get zeros) so the buffer can be recycled between chunks of windows.
 __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const int* __restrict__ lpad,
                                      long long n_rows, int lc, int pitch, RowGeom g, int tok_offset,
-                                     __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ mask,
+                                     act_t* __restrict__ x, uint8_t* __restrict__ mask,
                                      int* __restrict__ count) {
   const long long total = n_rows * 8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -37,7 +37,7 @@ __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const i
     const int ch = tok - tok_offset;
     tok = (tok >= tok_offset) ? 1 : 0;
     if (tok > 0 && (ch >> 3) == chunk) {
-      const uint32_t one = 0x3F80u << (16 * (ch & 1));
+      const uint32_t one = 0x3C00u << (16 * (ch & 1));      // fp16 1.0
       const int word = (ch & 7) >> 1;
       if (word == 0) o.x = one; else if (word == 1) o.y = one; else if (word == 2) o.z = one; else o.w = one;
     }
@@ -83,9 +83,9 @@ __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const
 // out[w,f,j] = max(in[w,f,2j], in[w,f,2j+1]) for j < L_in/2, zero elsewhere.  One thread per
 // 16-byte chunk of an output row; both tensors are g64sw, so the chunk position is re-swizzled
 // for every row it touches.
-__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ lpad, long long n_rows,
+__global__ void maxpool2_kernel(const act_t* __restrict__ x, const int* __restrict__ lpad, long long n_rows,
                                 RowGeom g, int shrink_in, int halvings, int groups, long long plane,
-                                __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ out_mask, int* __restrict__ count) {
+                                act_t* __restrict__ y, uint8_t* __restrict__ out_mask, int* __restrict__ count) {
   const long long total = n_rows * 8 * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -104,9 +104,9 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, const int* 
       const long long r0 = w * g.rpw + static_cast<long long>(f) * g.period + 2 * j, r1 = r0 + 1;
       const uint4 a = *reinterpret_cast<const uint4*>(x + (grp * plane + r0) * 64 + ((chunk ^ static_cast<int>(r0 & 7)) * 8));
       const uint4 b = *reinterpret_cast<const uint4*>(x + (grp * plane + r1) * 64 + ((chunk ^ static_cast<int>(r1 & 7)) * 8));
-      const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+      const __half2* pa = reinterpret_cast<const __half2*>(&a);
+      const __half2* pb = reinterpret_cast<const __half2*>(&b);
+      __half2* po = reinterpret_cast<__half2*>(&o);
 #pragma unroll
       for (int e = 0; e < 4; ++e) po[e] = __hmax2(pa[e], pb[e]);
     }
@@ -120,7 +120,7 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, const int* 
 
 // Add over the six frames followed by GlobalMaxPool1D over the positions (legacy graph,
 // nnlib/v1/layers.py:207, 413).  One CTA per window; thread = (8-channel chunk, position lane).
-__global__ void framesum_globalmax_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ lpad,
+__global__ void framesum_globalmax_kernel(const act_t* __restrict__ x, const int* __restrict__ lpad,
                                           int n_windows, RowGeom g, int shrink_in, int halvings, int channels,
                                           long long plane, float* __restrict__ pool) {
   extern __shared__ float s_max[];     // [pos lanes][channels]
@@ -137,10 +137,10 @@ __global__ void framesum_globalmax_kernel(const __nv_bfloat16* __restrict__ x, c
       for (int f = 0; f < g.frames; ++f) {
         const long long row = static_cast<long long>(w) * g.rpw + static_cast<long long>(f) * g.period + j;
         const uint4 v = *reinterpret_cast<const uint4*>(x + ((chunk >> 3) * plane + row) * 64 + (((chunk & 7) ^ static_cast<int>(row & 7)) * 8));
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const __half2* pv = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 q = __bfloat1622float2(pv[e]);
+          const float2 q = __half22float2(pv[e]);
           acc[2 * e] += q.x;
           acc[2 * e + 1] += q.y;
         }

@@ -3,10 +3,10 @@ against the CPU oracle on the same seeded inputs and against the committed golde
 
 Tolerances.  Integer / byte / index outputs (window starts, flags, tokens, base counts,
 gc_skew strings, per-window argmax, class counts, fp16 means / variances): bit-exact.
-Conv-stack outputs: the device keeps activations and weights in bf16 with fp32 accumulation and
-an fp32 epilogue, the oracle is fp32 throughout; with the random-init stand-in (|logit| <~ 0.3)
-the bound asserted is  max|logit - oracle| <= 4e-3  and  max|embedding - oracle| <= 1e-2
-(observed 3e-4 / 1e-3), and tensor-core vs CUDA-core kernels agree to 2e-3.
+Conv-stack outputs: the device keeps activations and weights in fp16 (fp32 accumulation, fp32
+BatchNorm affine, packed-fp16 GELU / residual add), the oracle is fp32 throughout; with the
+random-init stand-in (|logit| <~ 0.3) the bound asserted is  max|logit - oracle| <= 4e-3  and
+max|embedding - oracle| <= 1e-2, and tensor-core vs CUDA-core kernels agree to 2e-3.
 """
 import json
 import zlib
@@ -398,7 +398,7 @@ def _legacy_fixture():
 
 def test_legacy_default_model_on_health_fasta_vs_oracle():
     """BASELINE config 1: the bundled `default` weights on the reference's health FASTA
-    (135 windows at the CLI defaults).  Tolerance: bf16 activations vs the fp32 oracle with real
+    (135 windows at the CLI defaults).  Tolerance: fp16 activations vs the fp32 oracle with real
     weights, |logit| ~ 3-10: max |diff| <= 0.15 and identical per-window / per-contig labels."""
     from jaeger_b200 import B200Engine, WindowSource
     from jaeger_b200 import codon_tables as ct

@@ -20,12 +20,8 @@ static inline float frand() {  // uniform [-1, 1)
   rng_state = rng_state * 1664525u + 1013904223u;
   return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
 }
-static inline uint16_t f2bf(float f) {
-  uint32_t u; memcpy(&u, &f, 4);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>(u >> 16);
-}
-static inline float bf2f(uint16_t h) { uint32_t u = static_cast<uint32_t>(h) << 16; float f; memcpy(&f, &u, 4); return f; }
+static inline uint16_t f2bf(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }   // fp16 storage
+static inline float bf2f(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
 
 int main(int argc, char** argv) {
   const int shape = argc > 1 ? atoi(argv[1]) : 0;
@@ -111,12 +107,12 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dpool_tc, sentinel.data(), sentinel.size() * 4, cudaMemcpyHostToDevice));
 
   jg::ConvParams p{};
-  p.x = reinterpret_cast<const __nv_bfloat16*>(dx) + jg::kGuardRows * 64;
-  p.sc = (shape == 0) ? reinterpret_cast<const __nv_bfloat16*>(dsc) + jg::kGuardRows * 64 : nullptr;
+  p.x = reinterpret_cast<const jg::act_t*>(dx) + jg::kGuardRows * 64;
+  p.sc = (shape == 0) ? reinterpret_cast<const jg::act_t*>(dsc) + jg::kGuardRows * 64 : nullptr;
   p.sc_mask = (shape == 0) ? dscmask : nullptr;
   p.sc_const = dpar + 5 * cout;
   p.out_mask = dmask;
-  p.w = reinterpret_cast<const __nv_bfloat16*>(dw);
+  p.w = reinterpret_cast<const jg::act_t*>(dw);
   p.bias = dpar + 4 * cout;
   p.scale1 = dpar; p.shift1 = dpar + cout; p.scale2 = dpar + 2 * cout; p.shift2 = dpar + 3 * cout;
   p.x_plane = plane; p.y_plane = plane;
@@ -141,15 +137,15 @@ int main(int argc, char** argv) {
   printf("shape %d variant %d windows %d tiles %d sms %d stages %d\n", shape, variant, n_win, p.n_tiles, dev_sms, jg::conv_tc_stages(p));
 
   jg::ConvParams pr = p;
-  pr.y = reinterpret_cast<__nv_bfloat16*>(dy_ref) + jg::kGuardRows * 64; pr.tap_sum = dtap_ref; pr.pool = dpool_ref;
+  pr.y = reinterpret_cast<jg::act_t*>(dy_ref) + jg::kGuardRows * 64; pr.tap_sum = dtap_ref; pr.pool = dpool_ref;
   CK(jg::launch_conv_ref(pr, 0));
   CK(cudaDeviceSynchronize());
 
   jg::ConvParams pt = p;
-  pt.y = reinterpret_cast<__nv_bfloat16*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
+  pt.y = reinterpret_cast<jg::act_t*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
   if (strip & 8) { pt.y = nullptr; }
   auto launch = [&](const jg::ConvParams& q) { return variant == 2 ? jg::launch_conv_tc2(q, dev_sms, 0) : jg::launch_conv_tc(q, dev_sms, 0); };
-  if (variant == 2) pt.w = reinterpret_cast<const __nv_bfloat16*>(dw2);
+  if (variant == 2) pt.w = reinterpret_cast<const jg::act_t*>(dw2);
   CK(launch(pt));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
