@@ -63,6 +63,14 @@ struct ConvParams {
   int has_affine2;
   int tap_mode;                 // 0 none, 1 raw conv output (acc+bias), 2 after act1
   int pool_mode;                // 0 none, 1 masked max, 2 masked sum
+  // fused mask propagation (tensor-core kernels): when fuse_mask != 0 the epilogue derives the row's
+  // validity itself -- in-frame test + OR over the taps of the INPUT mask (layers.py:1245-1252,
+  // mode "any") -- writes it to out_mask_w and adds the tile's valid rows to count[window]
+  const uint8_t* in_mask;       // [R] mask the input tensor was stored with (guard rows readable)
+  uint8_t* out_mask_w;          // [R] mask of this launch's output
+  const int* lpad;              // [n_windows] padded frame length of every window
+  int* count;                   // [n_windows] valid output rows
+  int fuse_mask, masking, period, frames, shrink_in, halvings, shrink;
   int* err;                     // device int, set non-zero on a barrier time-out
   long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)
 };

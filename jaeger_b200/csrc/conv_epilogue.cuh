@@ -66,6 +66,25 @@ __device__ __forceinline__ void epi_params_fill(float* s_par, const ConvParams& 
   }
 }
 
+// Validity of this thread's output row.  With fuse_mask the propagate_mask_kernel launch is folded
+// in here: one thread owns one row of the tile, so it also publishes the mask and the warp adds
+// its valid-row count to the window's counter.
+__device__ __forceinline__ bool row_valid(const ConvParams& p, long long row, int win, int lane) {
+  if (!p.fuse_mask) return p.out_mask[row] != 0;
+  const int rw = static_cast<int>(row - static_cast<long long>(win) * p.rows_per_window);
+  const int f = rw / p.period, j = rw - f * p.period;
+  bool ok = f < p.frames && j < ((p.lpad[win] - p.shrink_in) >> p.halvings) - p.shrink;
+  if (ok && p.masking) {
+    int any = 0;
+    for (int t = 0; t < p.ntaps; ++t) any |= p.in_mask[row + p.shifts[t]];
+    ok = any != 0;
+  }
+  p.out_mask_w[row] = static_cast<uint8_t>(ok);
+  const unsigned b = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0 && b) atomicAdd(p.count + win, __popc(b));
+  return ok;
+}
+
 // raw: 32 fp32 accumulators (as bits) of channels [32*cb, 32*cb+32) of this thread's row.
 // scc: the shortcut's 32 fp16 values for the same channels (4 x uint4, logical chunk order).
 // out: the 32 fp16 results (4 x uint4, logical chunk order), zero when the row is masked.

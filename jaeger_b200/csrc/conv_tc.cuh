@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const long long row = static_cast<long long>(tile) * kTileM + q * 32 + lane;
       const int sw = static_cast<int>(row & 7);
       const int win = static_cast<int>((static_cast<long long>(tile) * kTileM) / p.rows_per_window);
-      const bool valid = p.out_mask[row] != 0;
+      const bool valid = row_valid(p, row, win, lane);
       const bool sc_valid = has_sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
       // the shortcut does not depend on the MMAs: fetch the first batch before waiting on them
       uint4 scv[4];

@@ -282,7 +282,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       const long long row = tile_row0 + row_in_tile;
       const int sw = static_cast<int>(row & 7);
       const int win = static_cast<int>(tile_row0 / p.rows_per_window);
-      const bool valid = p.out_mask[row] != 0;
+      const bool valid = row_valid(p, row, win, lane);
       const bool sc_valid = has_sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
       uint4 scv[4];
       if (sc_valid) {

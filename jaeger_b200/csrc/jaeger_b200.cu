@@ -514,10 +514,12 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       pool_final = true;
       continue;
     }
-    jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
-        mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_SHRINK], L.f[LF_K],
-        L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
-    ctx->launches++;
+    if (use_ref) {   // the CUDA-core check path keeps the stand-alone mask kernel
+      jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
+          mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_SHRINK], L.f[LF_K],
+          L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
+      ctx->launches++;
+    }
     jg::ConvParams p{};
     p.x = buf_row0(L.f[LF_IN_BUF]);
     p.y = L.f[LF_OUT_BUF] >= 0 ? buf_row0(L.f[LF_OUT_BUF]) : nullptr;
@@ -548,6 +550,17 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.has_affine2 = L.f[LF_HAS_AFF2];
     p.tap_mode = L.f[LF_TAP_MODE];
     p.pool_mode = L.f[LF_POOL_MODE];
+    p.fuse_mask = use_ref ? 0 : 1;
+    p.in_mask = mask_row0(L.f[LF_MASK_IN]);
+    p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
+    p.lpad = d_lpad;
+    p.count = m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows;
+    p.masking = L.f[LF_MASKING];
+    p.period = period;
+    p.frames = m->frames;
+    p.shrink_in = L.f[LF_CUM_SHRINK_IN];
+    p.halvings = L.f[LF_HALVINGS];
+    p.shrink = L.f[LF_SHRINK];
     p.err = m->err;
     p.dbg = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -45,7 +45,7 @@ def test_library_is_loaded_and_launches_kernels(standin):
     n0 = eng.ctx.launch_count
     from jaeger_b200 import WindowSource
     eng.predict(WindowSource(fasta=G / "synthetic_contigs.fasta"))
-    assert eng.ctx.launch_count - n0 >= 2 + 2 * 17 + 1           # pack, encode, (mask + conv) x 17, heads
+    assert eng.ctx.launch_count - n0 >= 2 + 2 + 17 + 1           # pack, encode, pool fill + expand, 17 convs (mask fused), heads
 
 
 @pytest.mark.parametrize("key", ["2000_1500_None_None_0", "2048_2048_None_None_0", "500_500_None_None_0", "2000_2000_None_None_1"])
