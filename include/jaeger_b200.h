@@ -5,6 +5,7 @@
  *
  *   jg_pack_bases        seqops/io.py:103-104 (.upper()) + encode.py:27-33 alphabet handling:
  *                        ASCII contig bytes -> 2-bit codes + validity bitmap in HBM
+ *   jg_dust_mask         seqops/io.py:105-108 (pydustmasker sdust, window 64, threshold 20)
  *   jg_plan_windows      seqops/io.py:38-71 (_window_indices) + :112-145 (window loop,
  *                        is_last flags, short whole-contig windows)         [host integer code]
  *   jg_encode_windows    seqops/io.py:124-133 (G/C/A/T counts, gc_skew) +
@@ -57,6 +58,17 @@ int64_t jg_ctx_launch_count(jg_ctx* ctx);
  * allocated with 2 extra zeroed words of slack. */
 int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_codes,
                   uint32_t* d_valid);
+
+/* ---- stage 1b: low-complexity soft-mask (symmetric DUST, window 64) ------------------------------
+ * Replaces pydustmasker.DustMasker(seq, window_size=64, score_threshold=threshold).mask()
+ * (seqops/io.py:105-108).  The host cuts every contig into chunks; chunk i scans
+ * [max(contig_begin, core_begin - 128), min(contig_end, core_end + 64)) and sets the bits of the
+ * masked bases that fall inside [core_begin, core_end) in d_soft (same layout as d_valid, zeroed
+ * by the caller).  All offsets are absolute base offsets into the packed arrays. */
+int jg_dust_mask(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid,
+                 const int64_t* d_core_begin, const int64_t* d_core_end,
+                 const int64_t* d_contig_begin, const int64_t* d_contig_end, int64_t n_chunks,
+                 int32_t threshold, uint32_t* d_soft);
 
 /* ---- stage 2a: window plan (host) -------------------------------------------------------
  * For contig c of length len[c]: fixed stride windows range(0, len-(fsize-1), stride), or the

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "jg_ctx_stream": (c_void_p, [c_void_p]),
     "jg_ctx_launch_count": (c_int64, [c_void_p]),
     "jg_pack_bases": (c_int32, [c_void_p, _P, c_int64, _P, _P]),
+    "jg_dust_mask": (c_int32, [c_void_p, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "jg_plan_windows": (c_int32, [POINTER(c_int64), c_int64, c_int32, c_int32, c_int32, c_double, c_int32, c_int64,
                                   c_int32, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64), POINTER(c_int32),
                                   POINTER(c_int32), POINTER(c_uint8)]),

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "conv_launch.cuh"
+#include "dust_kernels.cuh"
 #include "model_kernels.cuh"
 #include "post_kernels.cuh"
 #include "seq_kernels.cuh"
@@ -230,6 +231,22 @@ int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_co
   JG_CUDA(cudaSetDevice(ctx->device));
   const long long groups = (n + 31) / 32;
   jg::pack_bases_kernel<<<grid_for(groups, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(d_ascii, n, d_codes, d_valid);
+  ctx->launches++;
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- stage 1b: low-complexity soft-mask ----------------------------------------------------------
+int jg_dust_mask(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid, const int64_t* d_core_begin,
+                 const int64_t* d_core_end, const int64_t* d_contig_begin, const int64_t* d_contig_end, int64_t n_chunks,
+                 int32_t threshold, uint32_t* d_soft) {
+  if (n_chunks <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  const int block = 64;
+  jg::dust_kernel<<<static_cast<unsigned>((n_chunks + block - 1) / block), block, 0, ctx->stream>>>(
+      d_codes, d_valid, reinterpret_cast<const long long*>(d_core_begin), reinterpret_cast<const long long*>(d_core_end),
+      reinterpret_cast<const long long*>(d_contig_begin), reinterpret_cast<const long long*>(d_contig_end), n_chunks,
+      threshold, d_soft);
   ctx->launches++;
   JG_CUDA(cudaGetLastError());
   return 0;

@@ -66,7 +66,8 @@ class WindowSource:
     dynamic_stride: bool = False
     dynamic_stride_threshold: float = 10.0
     batch: int = 96                      # only shapes the short pass' padded batches
-    softmasks: dict[str, np.ndarray] | None = None   # per-contig bool arrays (dustmask stand-in)
+    dustmask: bool = False               # symmetric DUST soft-masking on the device (reference default: on)
+    softmasks: dict[str, np.ndarray] | None = None   # explicit per-contig bool arrays (overrides dustmask)
 
     def load(self) -> list[tuple[str, bytes]]:
         recs = self.records if self.records is not None else list(read_fasta(self.fasta))
@@ -188,6 +189,25 @@ class B200Engine:
         valid = torch.zeros((n + 31) // 32 + 4, dtype=torch.int32, device=self.tdev)
         check(lib.jg_pack_bases(self.ctx.handle, ascii_dev.data_ptr(), n, codes.data_ptr(), valid.data_ptr()))
         return codes, valid
+
+    def dust(self, codes, valid, offsets: np.ndarray, threshold: int = 20, chunk: int = 1024) -> torch.Tensor:
+        """Soft-mask bitmap (layout of `valid`) of the low-complexity bases of every contig:
+        pydustmasker.DustMasker(seq, window_size=64, score_threshold=20) at seqops/io.py:105-108."""
+        lens = np.diff(offsets)
+        n_chunks = (lens + chunk - 1) // chunk
+        owner = np.repeat(np.arange(len(lens)), n_chunks)
+        first = np.concatenate([[0], np.cumsum(n_chunks)])[:-1]
+        k = np.arange(int(n_chunks.sum())) - np.repeat(first, n_chunks)
+        cbeg = offsets[owner] + k * chunk
+        cend = np.minimum(cbeg + chunk, offsets[owner + 1])
+        soft = torch.zeros_like(valid)
+        if len(cbeg):
+            # keep the device copies referenced until the launch is enqueued (a temporary's block
+            # would be recycled by the next _h2d of the same expression)
+            d_cb, d_ce, d_gb, d_ge = (self._h2d(a) for a in (cbeg, cend, offsets[owner], offsets[owner + 1]))
+            check(lib.jg_dust_mask(self.ctx.handle, codes.data_ptr(), valid.data_ptr(), d_cb.data_ptr(), d_ce.data_ptr(),
+                                   d_gb.data_ptr(), d_ge.data_ptr(), len(cbeg), int(threshold), soft.data_ptr()))
+        return soft
 
     @staticmethod
     def plan_windows(lens: np.ndarray, fsize: int, stride: int, dynamic_stride=False, threshold=10.0,
@@ -351,6 +371,8 @@ class B200Engine:
             ascii_dev = host.to(self.tdev, non_blocking=True)
             codes, valid = self.pack(ascii_dev)
             soft = None
+            if src.dustmask and not src.softmasks:
+                soft = self.dust(codes, valid, offsets)
             if src.softmasks:
                 bits = np.zeros(total, dtype=bool)
                 for (o, (n, _)) in zip(offsets[:-1], recs):

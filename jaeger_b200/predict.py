@@ -83,7 +83,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     src = WindowSource(records=recs, fsize=fsize, stride=stride, min_len=min_len,
                        dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
                        dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
-                       batch=int(kwargs.get("batch", 96)))
+                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)))   # cli.py: --dustmask default on
     y_pred = engine.predict(src)
     t1 = time.time()
     data = contig_table(engine, y_pred, fsize)
@@ -123,6 +123,8 @@ def main(argv=None) -> int:
     ap.add_argument("--min-len", dest="min_len", type=int, default=None)
     ap.add_argument("--dynamic-stride", dest="dynamic_stride", action="store_true")
     ap.add_argument("--dynamic-stride-threshold", dest="dynamic_stride_threshold", type=float, default=10.0)
+    ap.add_argument("--dustmask", dest="dustmask", action="store_true", default=True)
+    ap.add_argument("--no-dustmask", dest="dustmask", action="store_false")
     ap.add_argument("--rc", type=float, default=0.1)
     ap.add_argument("--pc", type=float, default=3)
     ap.add_argument("-p", "--prophage", action="store_true")

@@ -458,3 +458,50 @@ def test_500bp_baseline_model_config3():
     assert np.abs(ref["prediction"] - y["prediction"]).max() <= 4e-3
     assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2
     eng.close()
+
+
+def test_dustmask_kernel_vs_sdust_oracle(standin):
+    """Symmetric DUST soft-masking on the device vs the oracle's restatement of SDUST, including
+    chunk boundaries (contigs of several chunks), N-breaks and low-complexity inserts; then the
+    counts / N% path: soft-masked bases are not counted (seqops/io.py:124-127)."""
+    from jaeger_b200 import WindowSource
+    from oracle import dust as odust
+    from oracle import seqwin
+    _, _, eng = standin
+    rng = np.random.default_rng(12)
+    recs = []
+    for i, n in enumerate([5000, 2300, 1024, 1023, 1025, 9000, 70, 3, 4000]):
+        s = rng.choice(list("ACGT"), n)
+        for _ in range(max(1, n // 700)):
+            a = int(rng.integers(0, max(1, n - 80)))
+            kind = int(rng.integers(0, 3))
+            rep = (["A", "AC", "GGT"][kind] * 80)
+            ln = min(int(rng.integers(15, 70)), n - a)
+            s[a:a + ln] = list(rep[:ln])
+        if i == 5:
+            s[1000:1010] = "N"
+            s[1020:1060] = "T"          # poly-T right after an N break, straddling a chunk boundary
+        recs.append((f"d{i}", "".join(s)))
+    buf = "".join(s for _, s in recs).encode()
+    lens = np.array([len(s) for _, s in recs], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    with torch.cuda.stream(eng._stream()):
+        dev = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy()).to(eng.tdev)
+        codes, valid = eng.pack(dev)
+        soft = eng.dust(codes, valid, off).cpu().numpy()
+    eng.ctx.sync()
+    bits = np.unpackbits(soft.view(np.uint8), bitorder="little")[:off[-1]].astype(bool)
+    n_masked = 0
+    for (name, s), a, b in zip(recs, off[:-1], off[1:]):
+        want = odust.mask_bits(s)
+        assert np.array_equal(bits[a:b], want), (name, np.flatnonzero(bits[a:b] != want)[:10])
+        n_masked += int(want.sum())
+    assert n_masked > 300
+    # end to end: metadata with dustmask on == oracle windows over the soft-masked sequences
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500, dustmask=True))
+    masks = {n: odust.mask_bits(s) for n, s in recs}
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500, softmasks=masks))
+    assert len(wins) == len(y["meta_0"])
+    for i, w in enumerate(wins):
+        assert [int(y[f"meta_{k}"][i]) for k in (5, 6, 7, 8)] == [w.g, w.c, w.a, w.t], i
+        assert y["meta_9"][i].decode() == w.gc_skew

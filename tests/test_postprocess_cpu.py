@@ -57,3 +57,20 @@ def test_weights_npz_roundtrip(tmp_path):
     assert np.array_equal(r["embedding"], w["embedding"])
     assert np.array_equal(r["classifier"][0]["kernel"], w["classifier"][0]["kernel"])
     assert np.array_equal(r["layers"][4]["blocks"][1]["conv2"]["kernel"], w["layers"][4]["blocks"][1]["conv2"]["kernel"])
+
+
+def test_sdust_oracle_masks_low_complexity_only():
+    from oracle import dust as odust
+    rng = np.random.default_rng(0)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))          # noqa: E731
+    s = rnd(300) + "A" * 40 + rnd(200) + "AC" * 14 + rnd(300) + "NNNNN" + "T" * 21 + rnd(100)
+    iv = odust.sdust_intervals(s)
+    assert len(iv) == 4
+    assert iv[0][0] <= 300 and iv[0][1] >= 340                    # the poly-A run
+    assert 535 <= iv[1][0] <= 545 and 565 <= iv[1][1] <= 575      # the (AC)n repeat
+    assert iv[3][0] >= 873                                        # poly-T after the N break, not merged across it
+    m = odust.mask(s)
+    assert m[310] == "a" and m[100] == s[100] and m[868:873] == "NNNNN"
+    # random sequence: almost nothing is low-complexity at T = 20
+    assert odust.mask_bits(rnd(20000)).mean() < 0.002
+    assert odust.sdust_intervals("ACG") == [] and odust.sdust_intervals("") == []
