@@ -251,14 +251,23 @@ def run_b200(args):
         d2h_bytes = 0
         barrier()
         t0 = time.perf_counter()
+        e2e_ev = []
         for i in range(args.warmup, n_batches):
+            if os.environ.get("JG_BENCH_DEBUG"):
+                e2e_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), time.perf_counter()))
+                e2e_ev[-1][0].record(stream)
             x = pinned[i].to(dev, non_blocking=True)
             agg, w, c = eng.classify_long(x, host_batches[i][1], FSIZE, STRIDE)
             gather_results(agg, i)
             host = {k: agg[k].cpu() for k in ("pred_sum", "pred_var", "consensus", "per_class_counts", "entropy", "energy", "rel_pos")}
             d2h_bytes = sum(v.numel() * v.element_size() for v in host.values())
+            if e2e_ev:
+                e2e_ev[-1][1].record(stream)
+                e2e_ev[-1] = e2e_ev[-1] + (time.perf_counter(),)
         barrier()
         e2e_s = time.perf_counter() - t0
+        for a, b, h0, h1 in e2e_ev:
+            sys.stderr.write(f"[e2e step] device {a.elapsed_time(b):.1f} ms  host {1e3 * (h1 - h0):.1f} ms\n")
     t = torch.tensor([ms, e2e_s * 1e3, float(n_bases), float(n_windows), float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -3,6 +3,7 @@
  * Every entry point replaces one piece of the reference's Python/TensorFlow path
  * (paths relative to /root/reference/src/jaeger):
  *
+ *   jg_fasta_scan/load   utils/fs.py:99-115, seqops/io.py:98-104 (pyfastx record iteration)    [host]
  *   jg_pack_bases        seqops/io.py:103-104 (.upper()) + encode.py:27-33 alphabet handling:
  *                        ASCII contig bytes -> 2-bit codes + validity bitmap in HBM
  *   jg_dust_mask         seqops/io.py:105-108 (pydustmasker sdust, window 64, threshold 20)
@@ -44,12 +45,23 @@ int jg_version(void);
 
 /* ---- context ------------------------------------------------------------------------- */
 int jg_ctx_create(int device, jg_ctx** out);
+/* Same, on a caller-owned stream (never destroyed by the library): the Python host passes a
+ * torch.cuda.Stream so that torch's pinned-memory bookkeeping never sees a dead stream. */
+int jg_ctx_create_on_stream(int device, void* stream, jg_ctx** out);
 int jg_ctx_destroy(jg_ctx* ctx);
 int jg_ctx_sync(jg_ctx* ctx);
 /* raw cudaStream_t of the context (so the host can bracket work with its own events) */
 void* jg_ctx_stream(jg_ctx* ctx);
 /* number of CUDA kernels this library has launched on the context since creation */
 int64_t jg_ctx_launch_count(jg_ctx* ctx);
+
+/* ---- stage 0: FASTA ingest (host) ------------------------------------------------------------
+ * Replaces the pyfastx passes of the reference (utils/fs.py:99-115, seqops/io.py:98-104): one
+ * streaming pass. jg_fasta_scan sizes the outputs; jg_fasta_load fills h_bases (n_bases bytes,
+ * ideally pinned memory: it is the H2D source), h_offsets (n_records + 1) and h_names (record
+ * names = header up to the first whitespace, NUL-terminated, back to back). */
+int jg_fasta_scan(const char* path, int64_t* n_records, int64_t* n_bases, int64_t* name_bytes);
+int jg_fasta_load(const char* path, uint8_t* h_bases, int64_t* h_offsets, char* h_names);
 
 /* ---- stage 1: pack ---------------------------------------------------------------------
  * d_ascii: n bases (contigs concatenated, no separators).  d_codes: ceil(n/16) uint32, base i

@@ -33,10 +33,13 @@ _SIGNATURES = {
     "jg_last_error": (ctypes.c_char_p, []),
     "jg_version": (c_int32, []),
     "jg_ctx_create": (c_int32, [c_int32, POINTER(c_void_p)]),
+    "jg_ctx_create_on_stream": (c_int32, [c_int32, c_void_p, POINTER(c_void_p)]),
     "jg_ctx_destroy": (c_int32, [c_void_p]),
     "jg_ctx_sync": (c_int32, [c_void_p]),
     "jg_ctx_stream": (c_void_p, [c_void_p]),
     "jg_ctx_launch_count": (c_int64, [c_void_p]),
+    "jg_fasta_scan": (c_int32, [ctypes.c_char_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "jg_fasta_load": (c_int32, [ctypes.c_char_p, _P, POINTER(c_int64), ctypes.c_char_p]),
     "jg_pack_bases": (c_int32, [c_void_p, _P, c_int64, _P, _P]),
     "jg_dust_mask": (c_int32, [c_void_p, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "jg_plan_windows": (c_int32, [POINTER(c_int64), c_int64, c_int32, c_int32, c_int32, c_double, c_int32, c_int64,
@@ -72,9 +75,12 @@ def check(rc: int) -> None:
 class Context:
     """One CUDA context handle (device + stream) of the library."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream: int | None = None):
         h = c_void_p()
-        check(lib.jg_ctx_create(int(device), ctypes.byref(h)))
+        if stream:
+            check(lib.jg_ctx_create_on_stream(int(device), c_void_p(int(stream)), ctypes.byref(h)))
+        else:
+            check(lib.jg_ctx_create(int(device), ctypes.byref(h)))
         self.handle = h
         self.device = int(device)
 

@@ -54,6 +54,7 @@ struct jg_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  bool owns_stream = true;
   int64_t launches = 0;
 };
 
@@ -195,7 +196,9 @@ extern "C" {
 const char* jg_last_error(void) { return g_err.c_str(); }
 int jg_version(void) { return 1; }
 
-int jg_ctx_create(int device, jg_ctx** out) {
+int jg_ctx_create(int device, jg_ctx** out) { return jg_ctx_create_on_stream(device, nullptr, out); }
+
+int jg_ctx_create_on_stream(int device, void* stream, jg_ctx** out) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail("no CUDA device: the jaeger_b200 hot path has no CPU fallback");
@@ -207,14 +210,19 @@ int jg_ctx_create(int device, jg_ctx** out) {
   jg_ctx* c = new jg_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  JG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (stream) {
+    c->stream = static_cast<cudaStream_t>(stream);
+    c->owns_stream = false;
+  } else {
+    JG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  }
   *out = c;
   return 0;
 }
 int jg_ctx_destroy(jg_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
 }
@@ -224,6 +232,65 @@ int jg_ctx_sync(jg_ctx* ctx) {
 }
 void* jg_ctx_stream(jg_ctx* ctx) { return ctx->stream; }
 int64_t jg_ctx_launch_count(jg_ctx* ctx) { return ctx->launches; }
+
+// ---- stage 0: FASTA ingest (host) ----------------------------------------------------------------
+// One pass over the file: record name = header up to the first whitespace, sequence = the record's
+// lines with line ends and blanks removed (what pyfastx hands to seqops/io.py:98-104).
+namespace {
+struct FastaScan { int64_t n_records = 0, n_bases = 0, name_bytes = 0; };
+
+int fasta_walk(const char* path, FastaScan* scan, uint8_t* bases, int64_t* offsets, char* names) {
+  FILE* fh = std::fopen(path, "rb");
+  if (!fh) return fail(std::string("cannot open ") + path);
+  std::vector<char> buf(1 << 22);
+  int64_t rec = -1, nb = 0, nn = 0;
+  bool in_header = false, header_name_done = false, at_line_start = true;
+  size_t got;
+  while ((got = std::fread(buf.data(), 1, buf.size(), fh)) > 0) {
+    for (size_t i = 0; i < got; ++i) {
+      const char c = buf[i];
+      if (at_line_start && c == '>') {
+        ++rec;
+        if (offsets) offsets[rec] = nb;
+        in_header = true; header_name_done = false; at_line_start = false;
+        continue;
+      }
+      if (c == '\n') {
+        if (in_header) { if (names) names[nn] = 0; ++nn; in_header = false; }
+        at_line_start = true;
+        continue;
+      }
+      at_line_start = false;
+      if (in_header) {
+        if (!header_name_done) {
+          if (c == ' ' || c == '\t' || c == '\r') header_name_done = true;
+          else { if (names) names[nn] = c; ++nn; }
+        }
+      } else if (rec >= 0 && c != '\r' && c != ' ' && c != '\t') {
+        if (bases) bases[nb] = static_cast<uint8_t>(c);
+        ++nb;
+      }
+    }
+  }
+  if (in_header) { if (names) names[nn] = 0; ++nn; }
+  std::fclose(fh);
+  if (offsets) offsets[rec + 1] = nb;
+  scan->n_records = rec + 1; scan->n_bases = nb; scan->name_bytes = nn;
+  return 0;
+}
+}  // namespace
+
+int jg_fasta_scan(const char* path, int64_t* n_records, int64_t* n_bases, int64_t* name_bytes) {
+  FastaScan sc;
+  if (fasta_walk(path, &sc, nullptr, nullptr, nullptr)) return 1;
+  *n_records = sc.n_records; *n_bases = sc.n_bases; *name_bytes = sc.name_bytes;
+  return 0;
+}
+
+int jg_fasta_load(const char* path, uint8_t* h_bases, int64_t* h_offsets, char* h_names) {
+  FastaScan sc;
+  return fasta_walk(path, &sc, h_bases, h_offsets, h_names);
+}
 
 // ---- stage 1 -----------------------------------------------------------------------------------
 int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_codes, uint32_t* d_valid) {

@@ -54,6 +54,22 @@ def read_fasta(path: str | Path):
         yield name, b"".join(chunks)
 
 
+def load_fasta(path: str | Path) -> tuple[list[str], torch.Tensor, np.ndarray]:
+    """Native one-pass FASTA ingest (jg_fasta_scan / jg_fasta_load): record names, all bases back
+    to back in one PINNED host buffer (the H2D source) and the n+1 record offsets."""
+    cpath = str(path).encode()
+    n, nb, nn = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    check(lib.jg_fasta_scan(cpath, ctypes.byref(n), ctypes.byref(nb), ctypes.byref(nn)))
+    host = torch.empty(max(nb.value, 1), dtype=torch.uint8)
+    if torch.cuda.is_available():
+        host = host.pin_memory()
+    offsets = np.zeros(n.value + 1, dtype=np.int64)
+    names = ctypes.create_string_buffer(max(nn.value, 1))
+    check(lib.jg_fasta_load(cpath, ctypes.c_void_p(host.data_ptr()), offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), names))
+    name_list = [x.decode() for x in names.raw[:nn.value].split(b"\0")[:n.value]]
+    return name_list, host[:nb.value], offsets
+
+
 @dataclass
 class WindowSource:
     """What `fragment_generator` + `process_string_inference` are parameterised with
@@ -69,9 +85,24 @@ class WindowSource:
     dustmask: bool = False               # symmetric DUST soft-masking on the device (reference default: on)
     softmasks: dict[str, np.ndarray] | None = None   # explicit per-contig bool arrays (overrides dustmask)
 
-    def load(self) -> list[tuple[str, bytes]]:
-        recs = self.records if self.records is not None else list(read_fasta(self.fasta))
-        return [(n, s.encode() if isinstance(s, str) else bytes(s)) for n, s in recs]
+    def load(self) -> tuple[list[str], torch.Tensor, np.ndarray]:
+        """(names, bases in one pinned host buffer, record offsets); read once and kept."""
+        if getattr(self, "_loaded", None) is not None:
+            return self._loaded
+        if self.records is None:
+            self._loaded = load_fasta(self.fasta)
+            return self._loaded
+        recs = [(n, s.encode() if isinstance(s, str) else bytes(s)) for n, s in self.records]
+        offsets = np.zeros(len(recs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for _, s in recs], out=offsets[1:])
+        host = torch.empty(max(int(offsets[-1]), 1), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            host = host.pin_memory()
+        hv = host.numpy()
+        for o, (_, s) in zip(offsets[:-1], recs):
+            hv[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        self._loaded = [n for n, _ in recs], host[:int(offsets[-1])], offsets
+        return self._loaded
 
 
 @dataclass
@@ -97,7 +128,10 @@ class B200Engine:
             raise _cabi.JaegerB200Error("no CUDA device: jaeger_b200 has no CPU fallback")
         self.device = int(device)
         self.tdev = torch.device("cuda", self.device)
-        self.ctx = _cabi.Context(self.device)
+        # a torch pool stream: it outlives the engine, so pinned buffers that were copied from on it
+        # can be released by torch's host allocator at any later time
+        self._tstream = torch.cuda.Stream(device=self.tdev)
+        self.ctx = _cabi.Context(self.device, self._tstream.cuda_stream)
         self.use_ref_kernels = bool(use_ref_kernels)
         self.class_map = None
         if legacy_weights is not None:
@@ -166,7 +200,7 @@ class B200Engine:
 
     # ---- torch plumbing -----------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.ExternalStream(self.ctx.stream, device=self.tdev)
+        return self._tstream
 
     def _empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.tdev)
@@ -347,12 +381,10 @@ class B200Engine:
         return {k: np.concatenate(v, axis=0) for k, v in acc.items()}
 
     def _predict_source(self, src: WindowSource) -> dict[str, np.ndarray]:
-        recs = src.load()
+        raw_names, host, offsets = src.load()
         fsize, stride = int(src.fsize), int(src.stride)
-        names = [n.strip().replace(",", "___") for n, _ in recs]          # seqops/io.py:109
-        lens = np.array([len(s) for _, s in recs], dtype=np.int64)
-        offsets = np.zeros(len(recs) + 1, dtype=np.int64)
-        np.cumsum(lens, out=offsets[1:])
+        names = [n.strip().replace(",", "___") for n in raw_names]        # seqops/io.py:109
+        lens = np.diff(offsets)
         total = int(offsets[-1])
         two_pass = src.min_len is not None and src.min_len < fsize      # commands/predict.py:771-810
         passes = [self.plan_windows(lens, fsize, stride, src.dynamic_stride, src.dynamic_stride_threshold,
@@ -364,10 +396,6 @@ class B200Engine:
         results: list[dict[str, torch.Tensor]] = []
         tables = []
         with torch.cuda.stream(self._stream()):
-            host = torch.empty(total, dtype=torch.uint8).pin_memory()
-            hv = host.numpy()
-            for (o, (_, s)) in zip(offsets[:-1], recs):
-                hv[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
             ascii_dev = host.to(self.tdev, non_blocking=True)
             codes, valid = self.pack(ascii_dev)
             soft = None
@@ -375,7 +403,7 @@ class B200Engine:
                 soft = self.dust(codes, valid, offsets)
             if src.softmasks:
                 bits = np.zeros(total, dtype=bool)
-                for (o, (n, _)) in zip(offsets[:-1], recs):
+                for o, n in zip(offsets[:-1], raw_names):
                     if n in src.softmasks:
                         m = np.asarray(src.softmasks[n], dtype=bool)
                         bits[o:o + len(m)] = m

@@ -51,7 +51,6 @@ def get_model_id(model: str) -> str:
 
 def run_core(**kwargs: Any) -> dict[str, Any]:
     from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
-    from .engine import read_fasta
     from .postprocess import contig_table, write_output
     from .prophage import call_regions
 
@@ -76,23 +75,23 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if table.exists() and not kwargs.get("overwrite"):
         raise FileExistsError(f"{table} exists; use --overwrite")                     # predict.py:574-578
     min_len = kwargs.get("min_len")
-    recs = list(read_fasta(input_path))
-    n_ok = sum(len(s) >= (min_len or fsize) for _, s in recs)
-    if n_ok == 0:
-        raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
-    src = WindowSource(records=recs, fsize=fsize, stride=stride, min_len=min_len,
+    src = WindowSource(fasta=input_path, fsize=fsize, stride=stride, min_len=min_len,
                        dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
                        dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
                        batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)))   # cli.py: --dustmask default on
+    rec_off = src.load()[2]
+    n_records = len(rec_off) - 1
+    if not (np.diff(rec_off) >= (min_len or fsize)).any():
+        raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
     y_pred = engine.predict(src)
     t1 = time.time()
     data = contig_table(engine, y_pred, fsize)
     cm = engine.class_map
     n_written = write_output(data, cm["class"], cm["index"], table, phage_table,
                              reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
-    result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": len(recs),
+    result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
               "windows": int(y_pred["prediction"].shape[0]), "predict_seconds": t1 - t0}
-    logger.info(f"processed {n_written}/{len(recs)} sequences")
+    logger.info(f"processed {n_written}/{n_records} sequences")
     if kwargs.get("prophage"):
         regions = call_regions(engine, data, cm, fsize, stride, lc=int(kwargs.get("lc", 500_000)),
                                sensitivity=float(kwargs.get("sensitivity", 1.5)))

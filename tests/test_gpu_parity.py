@@ -384,6 +384,37 @@ def test_prophage_region_calling_vs_oracle(standin):
             assert len(ranges) >= 1 and all(any(abs(r[0] - a) <= 12 and abs(r[1] - b) <= 12 for a, b in islands) for r in ranges)
 
 
+def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
+    """BASELINE config 4: one 5 Mbp record through the driver with -p.  3333 windows, one TSV row,
+    the prophage table equal to the oracle's segmentation of the same window logits."""
+    from jaeger_b200.predict import run_core
+    from oracle import prophage as opro
+    _, _, eng = standin
+    rng = np.random.default_rng(404)
+    n = 5_000_000
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+    seq[1_234_000:1_236_500] = ord("N")
+    fa = tmp_path / "genome.fna"
+    with open(fa, "wb") as fh:
+        fh.write(b">chr1 synthetic genome\n")
+        for i in range(0, n, 80):
+            fh.write(seq[i:i + 80].tobytes() + b"\n")
+    res = run_core(input=str(fa), output=str(tmp_path / "out"), model="standin", fsize=2000, stride=1500,
+                   prophage=True, lc=500_000, sensitivity=1.5, overwrite=True, window_scores=True)
+    assert res["num"] == 1 and res["num_written"] == 1
+    assert res["windows"] == (n - 2000) // 1500 + 1
+    z = np.load(tmp_path / "out" / "standin" / "genome_window_scores.npz", allow_pickle=True)
+    logits = np.asarray(z["predictions"][0], dtype=np.float32)
+    assert logits.shape[0] == res["windows"]
+    cm = eng.class_map
+    k = cm["index"][[c.lower() for c in cm["class"]].index("phage")]
+    want_r, want_s = opro.segment(opro.smooth_scores(logits)[:, k], 1.5)
+    got = res["prophage_regions"].get("chr1", {"ranges": [], "scores": np.array([])})
+    assert got["ranges"] == want_r
+    assert np.allclose(got["scores"], want_s, atol=1e-6)
+    assert (tmp_path / "out" / "standin" / "genome_prophage_regions.tsv").exists()
+
+
 def _legacy_fixture():
     from jaeger_b200.weights import load_npz_weights
     z = np.load(G / "legacy_default.npz")

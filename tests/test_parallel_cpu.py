@@ -1,5 +1,6 @@
 """CPU tests of the multi-GPU host logic with the gloo backend (world_size 2)."""
 import os
+from pathlib import Path
 import socket
 
 import numpy as np
@@ -51,3 +52,21 @@ def test_gather_contig_records_gloo_world2():
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, 501), nprocs=2, join=True)
+
+
+def test_native_fasta_loader_matches_line_reader(tmp_path):
+    """jg_fasta_scan / jg_fasta_load (host-only entry points): names, bases and offsets equal the
+    record iteration the reference gets from pyfastx (seqops/io.py:98-104)."""
+    from jaeger_b200.engine import load_fasta, read_fasta
+    p = tmp_path / "x.fa"
+    p.write_bytes(b">a desc here\nACGT\nNNAC\r\n\n>b\tx\nGG\n>c\n>d\nTTTT")
+    for path in (p, Path(__file__).parent / "golden" / "synthetic_contigs.fasta"):
+        names, host, off = load_fasta(path)
+        ref = list(read_fasta(path))
+        assert names == [r[0] for r in ref]
+        assert bytes(host.numpy()) == b"".join(r[1] for r in ref)
+        assert np.diff(off).tolist() == [len(r[1]) for r in ref]
+    empty = tmp_path / "e.fa"
+    empty.write_bytes(b"")
+    names, host, off = load_fasta(empty)
+    assert names == [] and host.numel() == 0 and off.tolist() == [0]
