@@ -29,6 +29,56 @@ __device__ __forceinline__ void warp_cols_reduce(float (&v)[32], int lane) {
   }
 }
 
+// The same reduction for a tile held as 16 packed fp16 pairs (h[i] = columns 2i, 2i+1).  The two
+// widest exchange levels run on the packed registers (half the shuffles and selects; a max is
+// exact in fp16, a sum rounds two of its 31 additions to fp16), the narrow ones in fp32.
+// Returns the reduction of column `lane`.
+template <bool kMax>
+__device__ __forceinline__ float warp_cols_reduce_h2(const __half2 (&h)[16], int lane) {
+  uint32_t v[8];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(&h[j]), b = *reinterpret_cast<const uint32_t*>(&h[j + 8]);
+      const uint32_t r = __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+      const uint32_t k = hi ? b : a;
+      const __half2 x = *reinterpret_cast<const __half2*>(&k), y = *reinterpret_cast<const __half2*>(&r);
+      const __half2 z = kMax ? __hmax2(x, y) : __hadd2(x, y);
+      v[j] = *reinterpret_cast<const uint32_t*>(&z);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t r = __shfl_xor_sync(0xffffffffu, hi ? v[j] : v[j + 4], 8);
+      const uint32_t k = hi ? v[j + 4] : v[j];
+      const __half2 x = *reinterpret_cast<const __half2*>(&k), y = *reinterpret_cast<const __half2*>(&r);
+      const __half2 z = kMax ? __hmax2(x, y) : __hadd2(x, y);
+      v[j] = *reinterpret_cast<const uint32_t*>(&z);
+    }
+  }
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&v[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+#pragma unroll
+  for (int off = 4; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float r = __shfl_xor_sync(0xffffffffu, hi ? f[j] : f[j + off], off);
+      const float k = hi ? f[j + off] : f[j];
+      f[j] = kMax ? fmaxf(k, r) : (k + r);
+    }
+  }
+  return f[0];
+}
+
 // Per-channel parameters staged in shared memory: fp32 for the stage that touches the fp32
 // accumulator, fp16 pairs for the packed stages.
 struct EpiParams {
@@ -66,32 +116,75 @@ __device__ __forceinline__ void epi_params_fill(float* s_par, const ConvParams& 
   }
 }
 
-// Validity of this thread's output row.  With fuse_mask the propagate_mask_kernel launch is folded
-// in here: one thread owns one row of the tile, so it also publishes the mask and the warp adds
-// its valid-row count to the window's counter.
-__device__ __forceinline__ bool row_valid(const ConvParams& p, long long row, int win, int lane) {
-  if (!p.fuse_mask) return p.out_mask[row] != 0;
-  const int rw = static_cast<int>(row - static_cast<long long>(win) * p.rows_per_window);
-  const int f = rw / p.period, j = rw - f * p.period;
-  bool ok = f < p.frames && j < ((p.lpad[win] - p.shrink_in) >> p.halvings) - p.shrink;
-  if (ok && p.masking) {
-    int any = 0;
-    for (int t = 0; t < p.ntaps; ++t) any |= p.in_mask[row + p.shifts[t]];
-    ok = any != 0;
+// Row validity travels through shared memory: a helper warp (otherwise idle) evaluates it a few
+// tiles ahead of the epilogue warps, so the global loads behind it (window length, input masks,
+// shortcut mask) never stall the warps the kernel is bound by.  bit 0: output row valid,
+// bit 1: shortcut row valid.  Ring of kVSlots tiles x 128 rows, one byte per row.
+constexpr int kVSlots = 4;
+// One warp evaluates the 128 rows of the tile starting at tile_row0 (lane = row within each of the
+// four 32-row chunks) and writes the codes to dst[128].  Every global load of the tile is issued
+// before the first dependent instruction, so the tile costs one memory round trip, not one per
+// chunk and tap.  With fuse_mask this is also the mask propagation of the layer: it publishes the
+// output mask (one byte per row) and adds the valid rows to the window's counter.
+// The mask buffers carry kGuardRows bytes on either side, so row + shift is always in bounds.
+__device__ __forceinline__ void tile_validity(const ConvParams& p, long long tile_row0, int lane, volatile uint8_t* dst) {
+  const int win = static_cast<int>(tile_row0 / p.rows_per_window);
+  uint32_t any[4] = {0u, 0u, 0u, 0u}, scm[4];
+  int lp = 0;
+  if (p.fuse_mask) {
+    lp = p.lpad[win];
+    if (p.masking) {
+      for (int t0 = 0; t0 < p.ntaps; t0 += 8) {
+        uint32_t m[4][8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool on = t0 + u < p.ntaps;
+          const int sh = on ? p.shifts[t0 + u] : 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m[c][u] = on ? p.in_mask[tile_row0 + c * 32 + lane + sh] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) any[c] |= m[c][u];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) any[c] = p.out_mask[tile_row0 + c * 32 + lane];
   }
-  p.out_mask_w[row] = static_cast<uint8_t>(ok);
-  const unsigned b = __ballot_sync(0xffffffffu, ok);
-  if (lane == 0 && b) atomicAdd(p.count + win, __popc(b));
-  return ok;
+  const bool has_scm = p.sc != nullptr && p.sc_mask != nullptr;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) scm[c] = has_scm ? p.sc_mask[tile_row0 + c * 32 + lane] : (p.sc != nullptr ? 1u : 0u);
+  const int limit = ((lp - p.shrink_in) >> p.halvings) - p.shrink;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const long long row = tile_row0 + c * 32 + lane;
+    bool ok;
+    if (p.fuse_mask) {
+      const int rw = static_cast<int>(row - static_cast<long long>(win) * p.rows_per_window);
+      const int f = rw / p.period, j = rw - f * p.period;
+      ok = f < p.frames && j < limit && (!p.masking || any[c] != 0u);
+      p.out_mask_w[row] = static_cast<uint8_t>(ok);
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0 && bal) atomicAdd(p.count + win, __popc(bal));
+    } else {
+      ok = any[c] != 0u;
+    }
+    dst[c * 32 + lane] = static_cast<uint8_t>((ok ? 1u : 0u) | (scm[c] != 0u ? 2u : 0u));
+  }
 }
 
 // raw: 32 fp32 accumulators (as bits) of channels [32*cb, 32*cb+32) of this thread's row.
 // scc: the shortcut's 32 fp16 values for the same channels (4 x uint4, logical chunk order).
 // out: the 32 fp16 results (4 x uint4, logical chunk order), zero when the row is masked.
+// kLight: the layer has no NMD tap, no second affine and no pooling (the caller checked), so that
+// code is not instantiated -- the callers unroll the light path over the batches of a tile.
+template <bool kLight = false>
 __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiParams& e, int cb, const uint32_t (&raw)[32],
                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane,
                                                int win, uint4 (&out)[4]) {
-  if (p.tap_mode == 1) {   // NMD tap on the raw conv output (acc + bias), stem only
+  if (!kLight && p.tap_mode == 1) {   // NMD tap on the raw conv output (acc + bias), stem only
     float tv[32];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -121,18 +214,14 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     }
   }
   act_apply_h2(h, p.act1);
-  if (p.tap_mode == 2) {   // NMD tap on the block output
-    float tv[32];
+  if (!kLight && p.tap_mode == 2) {   // NMD tap on the block output
+    __half2 tv[16];
+    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 f = __half22float2(h[i]);
-      tv[2 * i] = valid ? f.x : 0.0f;
-      tv[2 * i + 1] = valid ? f.y : 0.0f;
-    }
-    warp_cols_reduce<false>(tv, lane);
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
   }
-  if (p.has_affine2) {
+  if (!kLight && p.has_affine2) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 a = e.scale2[cb * 4 + j], b = e.shift2[cb * 4 + j];
@@ -143,21 +232,17 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     }
     act_apply_h2(h, p.act2);
   }
-  if (p.pool_mode != 0) {
-    float tv[32];
-    const float fill = p.pool_mode == 1 ? -3.0e38f : 0.0f;
+  if (!kLight && p.pool_mode != 0) {
+    __half2 tv[16];
+    const uint32_t fill_bits = p.pool_mode == 1 ? 0xFC00FC00u : 0u;      // -inf for the max, 0 for the sum
+    const __half2 fill = *reinterpret_cast<const __half2*>(&fill_bits);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 f = __half22float2(h[i]);
-      tv[2 * i] = valid ? f.x : fill;
-      tv[2 * i + 1] = valid ? f.y : fill;
-    }
+    for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : fill;
     if (p.pool_mode == 1) {
-      warp_cols_reduce<true>(tv, lane);
-      if (tv[0] > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+      const float m = warp_cols_reduce_h2<true>(tv, lane);
+      if (m > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, m);
     } else {
-      warp_cols_reduce<false>(tv, lane);
-      atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+      atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
     }
   }
 #pragma unroll

@@ -164,7 +164,7 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 struct SmemLayout {
-  uint32_t w_off, stage_off, par_off, bar_off, total;
+  uint32_t w_off, stage_off, par_off, bar_off, val_off, total;
   uint32_t stage_bytes, stage_pitch, rows_a, lead, groups, w_bytes;
 };
 
@@ -181,7 +181,8 @@ __host__ __device__ inline SmemLayout smem_layout(int cin, int cout, int ntaps, 
   L.stage_off = (L.w_bytes + 1023u) & ~1023u;
   L.par_off = L.stage_off + n_stages * L.stage_pitch;
   L.bar_off = L.par_off + 6u * cout * 4u;
-  L.total = L.bar_off + 256u + 1024u;                       // + slack to align the base to 1024 B
+  L.val_off = L.bar_off + 256u;                             // validity ring: kVSlots x 128 bytes
+  L.total = L.val_off + kVSlots * 128u + 1024u;             // + slack to align the base to 1024 B
   return L;
 }
 
@@ -204,6 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto TFULL = [&](int a) { return bar0 + 8u * (2 * kStages + 1 + a); };
   auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 9);
+  auto VFULL = [&](int v) { return bar0 + 8u * (2 * kStages + 10 + v); };
+  auto VEMPTY = [&](int v) { return bar0 + 8u * (2 * kStages + 10 + kVSlots + v); };
+  volatile uint8_t* s_valid = smem + L.val_off;
   // accumulator ring in TMEM: 4 x cout columns when they fit the 512 columns, else 2
   const int n_acc = (4 * p.cout <= 512) ? 4 : 2;
 
@@ -226,6 +230,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int a = 0; a < 4; ++a) {
       mbar_init(TFULL(a), 1);
       mbar_init(TEMPTY(a), 128);  // one epilogue group (4 warps) drains a tile
+    }
+    for (int v = 0; v < kVSlots; ++v) {
+      mbar_init(VFULL(v), 1);
+      mbar_init(VEMPTY(v), 4);    // one lane per warp of the draining group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -313,6 +321,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (leader) umma_commit(TFULL(as));   // accumulator complete -> epilogue
       if (p.dbg && blockIdx.x == 0 && leader && it < 64) p.dbg[it * 8 + 1] = clock64();
     }
+  } else if (warp == 3) {
+    // ===== validity helper: row masks / window counts of this CTA's tiles, kVSlots tiles ahead =====
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int slot = it & (kVSlots - 1);
+      mbar_wait(VEMPTY(slot), ((static_cast<uint32_t>(it) / kVSlots) & 1u) ^ 1u);
+      const long long tile_row0 = static_cast<long long>(tile) * kTileM;
+      tile_validity(p, tile_row0, lane, s_valid + slot * 128);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(VFULL(slot));
+    }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> fused affine/residual/activation/taps -> HBM =====
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -326,8 +345,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const long long row = static_cast<long long>(tile) * kTileM + q * 32 + lane;
       const int sw = static_cast<int>(row & 7);
       const int win = static_cast<int>((static_cast<long long>(tile) * kTileM) / p.rows_per_window);
-      const bool valid = row_valid(p, row, win, lane);
-      const bool sc_valid = has_sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
+      const int vslot = it & (kVSlots - 1);
+      mbar_wait(VFULL(vslot), (static_cast<uint32_t>(it) / kVSlots) & 1u);
+      const uint32_t vcode = s_valid[vslot * 128 + q * 32 + lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(VEMPTY(vslot));
+      const bool valid = (vcode & 1u) != 0, sc_valid = (vcode & 2u) != 0;
       // the shortcut does not depend on the MMAs: fetch the first batch before waiting on them
       uint4 scv[4];
       if (sc_valid) {

@@ -19,6 +19,7 @@
 // Barriers: FULL/EMPTY per stage, TFULL/TEMPTY per accumulator; tcgen05.commit multicasts EMPTY and
 // TFULL to both CTAs, the peer's epilogue and relay arrive remotely on the leader's barriers.
 #pragma once
+#include <type_traits>
 #include "conv_tc.cuh"
 
 namespace jg {
@@ -47,6 +48,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -77,13 +81,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 struct SmemLayout2 {
-  uint32_t w_off, stage_off, out_off, par_off, bar_off, total;
+  uint32_t w_off, stage_off, out_off, par_off, bar_off, val_off, total;
   uint32_t stage_bytes, stage_pitch, rows_a, lead, groups, w_bytes, out_group_bytes, out_groups;
 };
 
@@ -102,7 +107,8 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps
   L.out_off = L.stage_off + kStages2 * L.stage_pitch;
   L.par_off = L.out_off + kEpiGroups2 * L.out_groups * L.out_group_bytes;
   L.bar_off = L.par_off + 6u * cout * 4u;
-  L.total = L.bar_off + 256u + 1024u;
+  L.val_off = L.bar_off + 256u;                                         // validity ring: kVSlots x 128 bytes
+  L.total = L.val_off + kVSlots * 128u + 1024u;
   return L;
 }
 
@@ -138,6 +144,9 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   auto TFULL = [&](int a) { return bar0 + 8u * (2 * kStages2 + 1 + a); };
   auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * kStages2 + 5 + a); };
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages2 + 9);
+  auto VFULL = [&](int v) { return bar0 + 8u * (2 * kStages2 + 10 + v); };
+  auto VEMPTY = [&](int v) { return bar0 + 8u * (2 * kStages2 + 10 + kVSlots + v); };
+  volatile uint8_t* s_valid = smem + L.val_off;
   const int n_acc = (4 * p.cout <= 512) ? 4 : 2;
 
   const uint32_t w_base = smem_u32(smem + L.w_off);
@@ -162,6 +171,10 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     for (int a = 0; a < 4; ++a) {
       mbar_init(TFULL(a), 1);
       mbar_init(TEMPTY(a), 8);                   // one elected lane per epilogue warp (4) in each CTA
+    }
+    for (int v = 0; v < kVSlots; ++v) {
+      mbar_init(VFULL(v), 1);
+      mbar_init(VEMPTY(v), 4);                   // the 4 warps of the group that drains the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,6 +262,17 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         if (leader_lane) umma_commit_pair(TFULL(as));
       }
     }
+  } else if (warp == 2) {
+    // ===== validity helper: row masks / window counts of this CTA's tiles, kVSlots tiles ahead =====
+    int it = 0;
+    for (int pt = pt_begin; pt < pt_end; ++pt, ++it) {
+      const int slot = it & (kVSlots - 1);
+      mbar_wait(VEMPTY(slot), ((static_cast<uint32_t>(it) / kVSlots) & 1u) ^ 1u);
+      const long long tile_row0 = (static_cast<long long>(pt) * 2 + rank) * kTileM;
+      tile_validity(p, tile_row0, lane, s_valid + slot * 128);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(VFULL(slot));
+    }
   } else if (warp == 3) {
     if (!is_leader) {
       // ===== relay (peer CTA): tell the leader when this CTA's operands have landed =====
@@ -267,40 +291,49 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> fused math -> smem staging -> bulk-TMA store =====
+    // Every warp works alone: it owns 32 rows of the tile, i.e. 4 KB contiguous per 64-channel
+    // group both in the staging tile and in HBM, stages them and issues its own bulk stores.
+    // TMEM loads run one batch ahead of the math.
     const int q = warp & 3;
     const int grp = (warp - kEpiWarp0) >> 2;
     const int n_cb = p.cout / 32;
     const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
-    const int tid_g = threadIdx.x - (kEpiWarp0 + 4 * grp) * 32;     // 0..127 inside the group
-    const uint32_t stage_out = out_base + grp * L.out_groups * L.out_group_bytes;
+    const bool light = p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2;
+    const uint32_t warp_stage = out_base + grp * L.out_groups * L.out_group_bytes + static_cast<uint32_t>(q) * 32u * 128u;
     for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kEpiGroups2, it += kEpiGroups2) {
       const int as = it % n_acc;
       const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
+      const bool tr_on = p.dbg && blockIdx.x == 0 && grp == 0 && q == 0 && lane == 0 && (it / kEpiGroups2) < 24;
+      long long* tr = tr_on ? p.dbg + 600 + 16 * (it / kEpiGroups2) : nullptr;
+      if (tr_on) tr[0] = clock64();
       const long long tile_row0 = (static_cast<long long>(pt) * 2 + rank) * kTileM;
       const int row_in_tile = q * 32 + lane;
       const long long row = tile_row0 + row_in_tile;
       const int sw = static_cast<int>(row & 7);
       const int win = static_cast<int>(tile_row0 / p.rows_per_window);
-      const bool valid = row_valid(p, row, win, lane);
-      const bool sc_valid = has_sc ? (p.sc_mask ? p.sc_mask[row] != 0 : true) : false;
+      const int vslot = it & (kVSlots - 1);
+      mbar_wait(VFULL(vslot), (static_cast<uint32_t>(it) / kVSlots) & 1u);
+      const uint32_t vcode = s_valid[vslot * 128 + row_in_tile];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(VEMPTY(vslot));
+      const bool valid = (vcode & 1u) != 0, sc_valid = (vcode & 2u) != 0;
       uint4 scv[4];
       if (sc_valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) scv[j] = *reinterpret_cast<const uint4*>(p.sc + row * 64 + ((j ^ sw) * 8));
       }
-      // the previous tile's bulk stores must have finished READING the staging tile
-      if (p.y) {
-        if (tid_g == 0) bulk_wait_read0();
-        group_bar(1 + grp);
-      }
       const long long tw3 = p.dbg ? clock64() : 0;
+      if (tr_on) tr[1] = tw3;
       mbar_wait(TFULL(as), aph);
       tc_fence_after();
+      if (tr_on) tr[2] = clock64();
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0) p.dbg[524 + grp] += clock64() - tw3;
-      for (int cb = 0; cb < n_cb; ++cb) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.cout + cb * 32), raw);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.cout);
+
+      // one 32-channel batch whose accumulators are already in `raw`
+      auto batch = [&](int cb, const uint32_t (&raw)[32], auto light_tag) {
+        constexpr bool kLight = decltype(light_tag)::value;
         uint4 scc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) scc[j] = scv[j];
@@ -311,36 +344,80 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
             scv[j] = *reinterpret_cast<const uint4*>(p.sc + (static_cast<long long>(nb >> 1) * p.y_plane + row) * 64 +
                                                      ((((nb & 1) * 4 + j) ^ sw) * 8));
         }
-        tmem_ld_wait();
-        if (cb + 1 == n_cb) {   // all TMEM reads of this tile landed: hand the accumulator back to the leader
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(map_to_cta(TEMPTY(as), 0));
-        }
         uint4 out[4];
-        epilogue_batch(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
+        epilogue_batch<kLight>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
         if (p.y) {
-          // staging tile = the exact g64sw image of rows [tile_row0, +128) of channel group cb/2
-          const uint32_t srow = stage_out + (cb >> 1) * L.out_group_bytes + row_in_tile * 128u;
+          const int og = cb >> 1;
+          if ((cb & 1) == 0) {
+            // this warp's previous store from the same staging rows must have finished READING them
+            if (lane == 0) {
+              if (L.out_groups == 2) bulk_wait_read<1>();
+              else if (L.out_groups == 4) bulk_wait_read<3>();
+              else bulk_wait_read<0>();
+            }
+            __syncwarp();
+          }
+          // staging rows = the exact g64sw image of rows [tile_row0 + 32 q, +32) of channel group og
+          const uint32_t srow = warp_stage + og * L.out_group_bytes + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t a = srow + ((((cb & 1) * 4 + j) ^ sw) * 16);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(out[j].x), "r"(out[j].y), "r"(out[j].z), "r"(out[j].w) : "memory");
           }
+          if (cb & 1) {   // 32 rows x 64 channels staged: 4 KB, contiguous in HBM
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(p.y + (static_cast<long long>(og) * p.y_plane + tile_row0 + q * 32) * 64, warp_stage + og * L.out_group_bytes, 32u * 128u);
+              bulk_commit();
+            }
+          }
+        }
+        if (tr_on && cb < 4) tr[4 + 2 * cb] = clock64();
+      };
+      // all TMEM reads of this tile landed: hand the accumulator back to the leader.  No generic-proxy
+      // data is published with it, so the arrive is relaxed (a release here costs a full membar).
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(TEMPTY(as), 0));
+      };
+
+      if (n_cb == 4 && light) {
+        // light layers (conv1 / conv2 of a residual block): unrolled, TMEM loads one batch ahead
+        using L1 = std::true_type;
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(t_addr, r0);
+        tmem_ld_wait();
+        if (tr_on) tr[3] = clock64();
+        tmem_ld32(t_addr + 32u, r1);
+        batch(0, r0, L1{});
+        tmem_ld_wait();
+        if (tr_on) tr[5] = clock64();
+        tmem_ld32(t_addr + 64u, r2);
+        batch(1, r1, L1{});
+        tmem_ld_wait();
+        if (tr_on) tr[7] = clock64();
+        tmem_ld32(t_addr + 96u, r3);
+        batch(2, r2, L1{});
+        tmem_ld_wait();
+        if (tr_on) tr[9] = clock64();
+        release_acc();
+        batch(3, r3, L1{});
+      } else {
+        // everything else: one rolled copy of the full epilogue (it would not fit the instruction cache unrolled)
+        for (int cb = 0; cb < n_cb; ++cb) {
+          uint32_t r0[32];
+          tmem_ld32(t_addr + static_cast<uint32_t>(cb * 32), r0);
+          tmem_ld_wait();
+          if (tr_on && cb < 4) tr[3 + 2 * cb] = clock64();
+          if (cb + 1 == n_cb) release_acc();
+          batch(cb, r0, std::false_type{});
         }
       }
-      if (p.y) {   // the whole 128 x Cout tile is staged: one fence + one barrier, then a 16 KB bulk store per channel group
-        fence_async_smem();
-        group_bar(1 + grp);
-        if (tid_g == 0) {
-          for (uint32_t og = 0; og < L.out_groups; ++og)
-            bulk_s2g(p.y + (static_cast<long long>(og) * p.y_plane + tile_row0) * 64, stage_out + og * L.out_group_bytes,
-                     L.out_group_bytes);
-          bulk_commit();
-        }
-      }
+      if (tr_on) tr[11] = clock64();
     }
-    if (p.y && tid_g == 0) bulk_wait_all();      // stores complete before the kernel ends
+    if (p.y && lane == 0) bulk_wait_all();      // stores complete before the kernel ends
   }
 
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[523] = clock64();

@@ -192,6 +192,15 @@ int main(int argc, char** argv) {
     printf("trace (cycles rel. to first MMA start): it  mma_start mma_issued | epi_arrive_wait tfull_ready epi_done\n");
     for (int i = 0; i < 16 && h[i * 8] != 0; ++i)
       printf("  %2d  %8lld %8lld | %8lld %8lld %8lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0);
+    if (variant == 2 && h[600] != 0) {
+      printf("pair epilogue trace, group 0 warp 0 (cycles rel. to tile start; prev = since previous tile start):\n  it  prev | rowvalid+sc  tfull | ld0 b0 ld1 b1 ld2 b2 ld3 b3 | end\n");
+      for (int i = 0; i < 24 && h[600 + 16 * i] != 0; ++i) {
+        const long long* t = &h[600 + 16 * i];
+        printf("  %2d %6lld | %6lld %6lld |", i, i ? t[0] - h[600 + 16 * (i - 1)] : 0LL, t[1] - t[0], t[2] - t[0]);
+        for (int k = 3; k <= 10; ++k) printf(" %5lld", t[k] - t[0]);
+        printf(" | %6lld\n", t[11] - t[0]);
+      }
+    }
     const int my_tiles = p.n_tiles / dev_sms;   // per CTA (pair kernel: 128-row tiles of this CTA)
     printf("CTA0: total %lld cycles for %d tiles (%.0f /tile); first MMA starts at +%lld; waits: producer(free stage) %lld, MMA(free acc) %lld, MMA(operands) %lld, epi groups(wait MMA) %lld %lld %lld\n",
            h[523] - h[519], my_tiles, double(h[523] - h[519]) / my_tiles, t0 - h[519], h[520], h[521], h[522], h[524], h[525], h[526]);
