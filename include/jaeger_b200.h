@@ -21,6 +21,7 @@
  *                        postprocess/helpers.py:175-235 (entropy, energy, sigmoid)
  *   jg_smooth_scores     postprocess/prophages.py:126-151 (softmax + width-4 box sum)
  *   jg_segment_scores    postprocess/prophages.py:554-595 (KernelCPD/PELT at pen 1..9)
+ *   jg_viterbi_decode    postprocess/helpers.py:393-449 (--crf window decoding)
  *
  * Conventions: every function returns 0 on success and a non-zero code on failure, with a
  * message retrievable through jg_last_error().  Pointers named d_* are DEVICE pointers (the
@@ -196,6 +197,13 @@ int jg_smooth_scores(jg_ctx* ctx, const float* d_logits, const int64_t* d_offset
  * d_bkps [n_pen][n] int32: ascending segment ends for each penalty (last = n), d_nbkps [n_pen]. */
 int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size,
                       int32_t n_pen, int32_t* d_bkps, int32_t* d_nbkps);
+
+/* Linear-chain CRF (Viterbi) decoding of every contig's window labels: replaces viterbi_decode
+ * (postprocess/helpers.py:393-449) as called per contig from pred_to_dict (collect.py:343-346,
+ * 367-375).  d_costs [n_cls][n_cls] float64 = build_transition_costs(...) (helpers.py:345-390).
+ * Outputs: d_path [n_windows] decoded class per window, d_counts [n_contigs][n_cls]. n_cls <= 8. */
+int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int32_t n_contigs, int64_t n_windows,
+                      int32_t n_cls, const double* d_costs, int32_t* d_path, int32_t* d_counts);
 
 #ifdef __cplusplus
 }

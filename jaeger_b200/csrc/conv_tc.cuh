@@ -339,7 +339,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int n_cb = p.cout / 32;
     const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
-    for (int tile = tile_begin + grp, it = grp; tile < tile_end; tile += kEpiGroups, it += kEpiGroups) {
+    // A group may only wait on an accumulator barrier whose previous phase has surely completed:
+    // that holds when no more groups rotate over the tiles than there are accumulators (Cout = 256
+    // has two), so the surplus groups sit such a layer out.
+    const int n_grp = n_acc < kEpiGroups ? n_acc : kEpiGroups;
+    for (int tile = tile_begin + grp, it = grp; grp < n_grp && tile < tile_end; tile += n_grp, it += n_grp) {
       const int as = it % n_acc;
       const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
       const long long row = static_cast<long long>(tile) * kTileM + q * 32 + lane;

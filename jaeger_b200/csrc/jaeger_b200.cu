@@ -598,7 +598,14 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       pool_final = true;
       continue;
     }
-    if (use_ref) {   // the CUDA-core check path keeps the stand-alone mask kernel
+    // A layer whose weights do not fit either tensor-core kernel's shared memory (e.g. 128 -> 256
+    // channels with k >= 3) runs on the CUDA-core kernel, like the whole model does under use_ref.
+    jg::ConvParams geo{};
+    geo.cin = L.f[LF_CIN]; geo.cout = cout; geo.ntaps = L.f[LF_K]; geo.halo_l = L.halo_l; geo.halo_r = L.halo_r;
+    geo.n_tiles = static_cast<int>(rows / jg::kTileM);
+    const bool fits_tc = jg::conv_tc_stages(geo) >= 0, fits_tc2 = jg::conv_tc2_eligible(geo);
+    const bool layer_ref = use_ref || (!fits_tc && !fits_tc2);
+    if (layer_ref) {   // the CUDA-core path keeps the stand-alone mask kernel
       jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
           mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_SHRINK], L.f[LF_K],
           L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
@@ -634,7 +641,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.has_affine2 = L.f[LF_HAS_AFF2];
     p.tap_mode = L.f[LF_TAP_MODE];
     p.pool_mode = L.f[LF_POOL_MODE];
-    p.fuse_mask = use_ref ? 0 : 1;
+    p.fuse_mask = layer_ref ? 0 : 1;
     p.in_mask = mask_row0(L.f[LF_MASK_IN]);
     p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
     p.lpad = d_lpad;
@@ -656,9 +663,9 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     // Kernel choice (profiles/conv_kernel_r1.md): the CTA-pair kernel wins on light epilogues; layers
     // with an NMD tap / second affine are epilogue-bound and run better with three epilogue groups.
     const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
-    const bool pair = !use_ref && m->conv_impl != 1 && (m->conv_impl == 2 || !heavy) && jg::conv_tc2_eligible(p);
+    const bool pair = !layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy)));
     if (pair) p.w = L.w2;
-    cudaError_t e = use_ref ? jg::launch_conv_ref(p, st)
+    cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
                             : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
@@ -786,6 +793,22 @@ int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t mi
   ctx->launches += 2;
   JG_CUDA(cudaGetLastError());
   JG_CUDA(cudaFreeAsync(work, st));
+  return 0;
+}
+
+int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int32_t n_contigs, int64_t n_windows,
+                      int32_t n_cls, const double* d_costs, int32_t* d_path, int32_t* d_counts) {
+  if (n_cls < 1 || n_cls > jg::kMaxCrfClasses) return fail("jg_viterbi_decode: n_cls must be in [1, 8]");
+  if (n_contigs <= 0 || n_windows <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  uint8_t* bp = nullptr;
+  JG_CUDA(cudaMallocAsync(&bp, static_cast<size_t>(n_windows) * n_cls, st));
+  jg::viterbi_kernel<<<grid_for(n_contigs, 64, ctx->num_sms, 8), 64, 0, st>>>(
+      d_logits, reinterpret_cast<const long long*>(d_offsets), n_contigs, n_cls, d_costs, bp, d_path, d_counts);
+  ctx->launches += 1;
+  JG_CUDA(cudaGetLastError());
+  JG_CUDA(cudaFreeAsync(bp, st));
   return 0;
 }
 

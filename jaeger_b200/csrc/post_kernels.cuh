@@ -237,4 +237,60 @@ __global__ void segment_scores_kernel(const double* __restrict__ x, int n, int m
   }
 }
 
+
+// ---- linear-chain CRF (Viterbi) decoding of each contig's window labels ---------------------------
+// postprocess/helpers.py:393-449: emissions = log-softmax of the logits in float64, switching from
+// class a to b costs costs[a][b]; delta/backpointer recursion, first index wins every argmax (as
+// np.argmax).  One thread walks one contig (the recursion is sequential in t; contigs are the
+// parallel axis); back-pointers go through a [W][n_cls] byte scratch.  Also returns the per-contig
+// class counts of the decoded path (collect.py:349-355).
+constexpr int kMaxCrfClasses = 8;
+__global__ void viterbi_kernel(const float* __restrict__ logits, const long long* __restrict__ offsets, int n_contigs,
+                               int n_cls, const double* __restrict__ costs, uint8_t* __restrict__ backptr,
+                               int* __restrict__ path, int* __restrict__ counts) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_contigs; c += gridDim.x * blockDim.x) {
+    const long long w0 = offsets[c], w1 = offsets[c + 1];
+    int cnt[kMaxCrfClasses];
+    for (int k = 0; k < kMaxCrfClasses; ++k) cnt[k] = 0;
+    if (w1 > w0) {
+      double cost[kMaxCrfClasses][kMaxCrfClasses], delta[kMaxCrfClasses], em[kMaxCrfClasses];
+      for (int a = 0; a < n_cls; ++a)
+        for (int b = 0; b < n_cls; ++b) cost[a][b] = costs[a * n_cls + b];
+      auto emissions = [&](long long w) {
+        double mx = -1.0e300;
+        for (int k = 0; k < n_cls; ++k) { em[k] = static_cast<double>(logits[w * n_cls + k]); mx = em[k] > mx ? em[k] : mx; }
+        double s = 0.0;
+        for (int k = 0; k < n_cls; ++k) s += exp(em[k] - mx);
+        const double lse = mx + log(s);
+        for (int k = 0; k < n_cls; ++k) em[k] -= lse;
+      };
+      emissions(w0);
+      for (int k = 0; k < n_cls; ++k) delta[k] = em[k];
+      for (long long w = w0 + 1; w < w1; ++w) {
+        emissions(w);
+        double nd[kMaxCrfClasses];
+        for (int cur = 0; cur < n_cls; ++cur) {
+          int best = 0;
+          double bs = delta[0] - cost[0][cur];
+          for (int prev = 1; prev < n_cls; ++prev) {
+            const double sc = delta[prev] - cost[prev][cur];
+            if (sc > bs) { bs = sc; best = prev; }
+          }
+          backptr[w * n_cls + cur] = static_cast<uint8_t>(best);
+          nd[cur] = em[cur] + bs;
+        }
+        for (int k = 0; k < n_cls; ++k) delta[k] = nd[k];
+      }
+      int cur = 0;
+      for (int k = 1; k < n_cls; ++k) if (delta[k] > delta[cur]) cur = k;
+      for (long long w = w1 - 1; w >= w0; --w) {
+        path[w] = cur;
+        ++cnt[cur];
+        if (w > w0) cur = backptr[w * n_cls + cur];
+      }
+    }
+    for (int k = 0; k < n_cls; ++k) counts[c * n_cls + k] = cnt[k];
+  }
+}
+
 }  // namespace jg

@@ -322,6 +322,16 @@ class B200Engine:
             out["rel_pos"].data_ptr(), out["frag_pred"].data_ptr()))
         return out
 
+    def viterbi(self, logits: torch.Tensor, offsets: torch.Tensor, costs: np.ndarray) -> tuple[torch.Tensor, torch.Tensor]:
+        """--crf window decoding on the device (helpers.py:393-449): (path [W] int32, counts [n_contigs, n_cls] int32)."""
+        nc = offsets.numel() - 1
+        w, ncls = logits.shape
+        costs_dev = self._h2d(np.ascontiguousarray(costs, dtype=np.float64))
+        path, counts = self._empty((w,), torch.int32), self._empty((nc, ncls), torch.int32)
+        check(lib.jg_viterbi_decode(self.ctx.handle, logits.data_ptr(), offsets.data_ptr(), nc, w, ncls, costs_dev.data_ptr(),
+                                    path.data_ptr(), counts.data_ptr()))
+        return path, counts
+
     def set_profiling(self, on: bool) -> None:
         check(lib.jg_model_set_profiling(self.model, int(bool(on))))
 

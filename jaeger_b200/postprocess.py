@@ -50,9 +50,43 @@ def window_summaries(frag_pred: np.ndarray, offsets: np.ndarray, class_map: dict
     return out
 
 
-def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats=None) -> dict[str, Any]:
-    """The `data` dict of the reference's pred_to_dict (softmax classifier, no CRF), with the
-    numeric columns produced by the device aggregation kernels."""
+# helpers.py:291-315: co-occurrence tiers of the --crf transition prior (lower-cased class names)
+_CRF_PRIOR_TIERS = (
+    (0.5, (("bacteria", "phage"), ("bacteria", "plasmid"), ("archaea", "phage"), ("archaea", "plasmid"),
+           ("phage", "plasmid"), ("eukarya", "virus"))),
+    (3.0, (("bacteria", "eukarya"), ("archaea", "eukarya"), ("bacteria", "archaea"), ("eukarya", "phage"),
+           ("eukarya", "plasmid"))),
+)
+
+
+def build_transition_costs(class_names, switch_cost: float, prior: str = "biological", user_matrix: dict | None = None) -> np.ndarray:
+    """lambda * P of helpers.py:345-390 (P: zero diagonal, 1.0 neutral, tiers or user entries symmetric)."""
+    names = [str(n).lower() for n in class_names]
+    p = np.ones((len(names), len(names)), dtype=np.float64)
+    np.fill_diagonal(p, 0.0)
+    if user_matrix:
+        for a, row in user_matrix.items():
+            a = str(a).lower()
+            if a not in names or not isinstance(row, dict):
+                continue
+            for b, value in row.items():
+                b = str(b).lower()
+                if b in names:
+                    p[names.index(a), names.index(b)] = p[names.index(b), names.index(a)] = float(value)
+        np.fill_diagonal(p, 0.0)
+    elif prior != "uniform":
+        for value, pairs in _CRF_PRIOR_TIERS:
+            for a, b in pairs:
+                if a in names and b in names:
+                    p[names.index(a), names.index(b)] = p[names.index(b), names.index(a)] = value
+    return float(switch_cost) * p
+
+
+def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats=None, crf_switch_cost: float | None = None,
+                 crf_prior: str = "biological", crf_transition_matrix: dict | None = None) -> dict[str, Any]:
+    """The `data` dict of the reference's pred_to_dict (softmax classifier), with the numeric
+    columns produced by the device aggregation kernels.  With crf_switch_cost the per-window labels
+    and class counts come from the device Viterbi decoder (collect.py:269-287, 343-346)."""
     pred = np.ascontiguousarray(y_pred["prediction"], dtype=np.float32)
     n_cls = pred.shape[1]
     if n_cls < 2:
@@ -60,8 +94,13 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
     offsets = _split_points(y_pred["meta_2"])
     rel = y_pred.get("reliability")
     with torch.cuda.stream(engine._stream()):
-        agg = engine.aggregate(engine._h2d(pred), engine._h2d(np.ascontiguousarray(rel, np.float32)) if rel is not None else None,
-                               engine._h2d(offsets))
+        pred_dev, off_dev = engine._h2d(pred), engine._h2d(offsets)
+        agg = engine.aggregate(pred_dev, engine._h2d(np.ascontiguousarray(rel, np.float32)) if rel is not None else None, off_dev)
+        if crf_switch_cost is not None:
+            cm = engine.class_map
+            names = [n for _, n in sorted(zip(cm["index"], cm["class"]), key=lambda t: int(t[0]))]
+            costs = build_transition_costs(names, crf_switch_cost, crf_prior, crf_transition_matrix)
+            agg["frag_pred"], agg["per_class_counts"] = engine.viterbi(pred_dev, off_dev, costs)
         agg = {k: v.cpu().numpy() for k, v in agg.items()}
     engine.ctx.sync()
     first = offsets[:-1]

@@ -1,10 +1,10 @@
 """`jaeger predict` on the B200 engine: model lookup, engine call, post-processing, outputs.
 
 Mirrors the reference driver `commands/predict.py:488-861` for the options that touch the hot
-path (the option names and defaults are the reference CLI's, cli.py:122-371): same model
+path (the option names and defaults are the reference CLI's, cli.py:122-371, including the experimental --crf family): same model
 registry (`config.json["model_paths"]`, scanned like `AvailableModels`, utils/misc.py:334-392),
 same output locations `<-o>/<model_id>/<base>.tsv` and `<base>_phages.tsv`, same `--overwrite`
-rule, same prophage table source.  Options outside the path (--refine, --crf, plots, --onnx ...)
+rule, same prophage table source.  Options outside the path (--refine, plots, --onnx ...)
 are not accepted.
 
     python -m jaeger_b200.predict -i contigs.fasta -o out -m jaeger_xxx_1.4M_fragment --config config.json
@@ -85,7 +85,14 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
     y_pred = engine.predict(src)
     t1 = time.time()
-    data = contig_table(engine, y_pred, fsize)
+    crf_cost, crf_matrix = None, kwargs.get("crf_transition_matrix")          # predict.py:288-307
+    if kwargs.get("crf"):
+        logger.warning("CRF window decoding is experimental; results may change between releases")
+        crf_cost = float(kwargs.get("crf_switch_cost", 2.0))
+        if isinstance(crf_matrix, (str, Path)):
+            crf_matrix = json.loads(Path(crf_matrix).read_text())
+    data = contig_table(engine, y_pred, fsize, crf_switch_cost=crf_cost, crf_prior=kwargs.get("crf_prior", "biological"),
+                        crf_transition_matrix=crf_matrix)
     cm = engine.class_map
     n_written = write_output(data, cm["class"], cm["index"], table, phage_table,
                              reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
@@ -124,6 +131,10 @@ def main(argv=None) -> int:
     ap.add_argument("--dynamic-stride-threshold", dest="dynamic_stride_threshold", type=float, default=10.0)
     ap.add_argument("--dustmask", dest="dustmask", action="store_true", default=True)
     ap.add_argument("--no-dustmask", dest="dustmask", action="store_false")
+    ap.add_argument("--crf", action="store_true", help="(experimental) joint Viterbi decoding of window labels")
+    ap.add_argument("--crf-switch-cost", dest="crf_switch_cost", type=float, default=2.0)
+    ap.add_argument("--crf-prior", dest="crf_prior", choices=["biological", "uniform"], default="biological")
+    ap.add_argument("--crf-transition-matrix", dest="crf_transition_matrix", default=None)
     ap.add_argument("--rc", type=float, default=0.1)
     ap.add_argument("--pc", type=float, default=3)
     ap.add_argument("-p", "--prophage", action="store_true")

@@ -162,3 +162,67 @@ def generate_summary(data, labels, indices):
                       on="contig_id", how="left")
     df["contig_id"] = df["contig_id"].str.replace("___", ",")
     return df
+
+
+# ---- --crf window decoding (postprocess/helpers.py:291-449) ------------------------------------
+CRF_PRIOR_TIERS = (
+    (0.5, (("bacteria", "phage"), ("bacteria", "plasmid"), ("archaea", "phage"), ("archaea", "plasmid"),
+           ("phage", "plasmid"), ("eukarya", "virus"))),
+    (3.0, (("bacteria", "eukarya"), ("archaea", "eukarya"), ("bacteria", "archaea"), ("eukarya", "phage"),
+           ("eukarya", "plasmid"))),
+)
+
+
+def build_transition_costs(class_names, switch_cost, prior="biological", user_matrix=None):
+    """helpers.py:345-390."""
+    names = [str(n).lower() for n in class_names]
+    n = len(names)
+    p = np.ones((n, n), dtype=np.float64)
+    np.fill_diagonal(p, 0.0)
+    if user_matrix:
+        for a, row in user_matrix.items():
+            a = str(a).lower()
+            if a not in names or not isinstance(row, dict):
+                continue
+            for b, value in row.items():
+                b = str(b).lower()
+                if b not in names:
+                    continue
+                i, j = names.index(a), names.index(b)
+                p[i, j] = p[j, i] = float(value)
+        np.fill_diagonal(p, 0.0)
+    elif prior != "uniform":
+        for value, pairs in CRF_PRIOR_TIERS:
+            for a, b in pairs:
+                if a in names and b in names:
+                    i, j = names.index(a), names.index(b)
+                    p[i, j] = p[j, i] = value
+    return float(switch_cost) * p
+
+
+def viterbi_decode(logits, switch_cost=2.0, transition_costs=None):
+    """helpers.py:393-449: float64 log-softmax emissions, delta/back-pointer recursion, first index
+    wins each argmax."""
+    z = np.asarray(logits, dtype=np.float64)
+    if z.ndim == 1:
+        z = z.reshape(1, -1)
+    t_len, n_classes = z.shape
+    em = z - logsumexp(z, axis=-1)[:, None]
+    if t_len == 1 or n_classes == 1:
+        return np.argmax(em, axis=-1)
+    if transition_costs is None:
+        costs = np.full((n_classes, n_classes), float(switch_cost))
+        np.fill_diagonal(costs, 0.0)
+    else:
+        costs = np.asarray(transition_costs, dtype=np.float64)
+    delta = em[0].copy()
+    back = np.zeros((t_len, n_classes), dtype=np.int64)
+    for t in range(1, t_len):
+        scores = delta[:, None] - costs
+        back[t] = np.argmax(scores, axis=0)
+        delta = em[t] + scores[back[t], np.arange(n_classes)]
+    path = np.empty(t_len, dtype=np.int64)
+    path[-1] = int(np.argmax(delta))
+    for t in range(t_len - 2, -1, -1):
+        path[t] = back[t + 1][path[t + 1]]
+    return path

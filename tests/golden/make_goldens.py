@@ -11,7 +11,7 @@ are executed:
   jaeger.dataops.convert._process_batch_numba   (the reference's TF-free six-frame encoder)
   jaeger.postprocess.collect.pred_to_dict, generate_summary
   jaeger.postprocess.prophages.logits_to_df_v2
-  jaeger.postprocess.helpers.merge_overlapping_ranges
+  jaeger.postprocess.helpers.merge_overlapping_ranges, viterbi_decode, build_transition_costs
 
 usage:  python tests/golden/make_goldens.py
 """
@@ -70,6 +70,46 @@ mpl = _stub("matplotlib")
 _stub("matplotlib.pyplot")
 _stub("matplotlib.patches", Patch=None)
 _stub("matplotlib.lines", Line2D=None)
+
+
+def viterbi_goldens(rhelp, rcollect):
+    """--crf decoding: reference viterbi_decode / build_transition_costs / pred_to_dict(crf_switch_cost=...)."""
+    rng = np.random.default_rng(11)
+    classes = ["bacteria", "phage", "eukarya", "archaea", "plasmid", "virus"]
+    n_win = [1, 2, 3, 50, 400, 7, 3000, 1, 25]
+    W = sum(n_win)
+    pred = rng.normal(0, 1.2, (W, 6)).astype(np.float32)
+    seg = rng.integers(0, 6, W // 20 + 1)
+    pred[np.arange(W), seg[np.arange(W) // 20]] += 1.5          # piecewise-constant signal under the noise
+    pred[10:14] = pred[9]                                        # exact ties between consecutive windows
+    out = {"prediction": pred, "n_win": np.array(n_win)}
+    splits = np.cumsum(n_win)[:-1]
+    user = {"Bacteria": {"phage": 0.25, "virus": 2.0}, "plasmid": {"archaea": 4.0}, "unknown": {"phage": 9.0}}
+    variants = {"potts2": (2.0, None), "potts0": (0.0, None),
+                "bio2": (2.0, rhelp.build_transition_costs(classes, 2.0, "biological")),
+                "uni05": (0.5, rhelp.build_transition_costs(classes, 0.5, "uniform")),
+                "user3": (3.0, rhelp.build_transition_costs(classes, 3.0, "biological", user))}
+    for name, (lam, costs) in variants.items():
+        out[f"path_{name}"] = np.concatenate([rhelp.viterbi_decode(p, lam, costs) for p in np.split(pred, splits)])
+        if costs is not None:
+            out[f"costs_{name}"] = costs
+    out["costs_4cls"] = rhelp.build_transition_costs(["bacteria", "phage", "eukarya", "archaea"], 2.0)
+    z = rng.normal(0, 2.0, (500, 1)).astype(np.float32)         # binary head: stacked [0, z] (collect.py:367-375)
+    out["binary_logit"] = z
+    out["binary_path"] = rhelp.viterbi_decode(np.concatenate([np.zeros_like(z), z], axis=-1), 2.0)
+    # through pred_to_dict: per-class counts with CRF labels
+    meta = {f"meta_{i}": [] for i in range(10)}
+    for ci, n in enumerate(n_win):
+        for j in range(n):
+            for i, v in enumerate([f"c{ci}", j * 1500, int(j == n - 1), j, 2000 + 1500 * (n - 1), 500, 500, 500, 500, " 0.000"]):
+                meta[f"meta_{i}"].append(str(v).encode())
+    y = {"prediction": pred, **{k: np.array(v) for k, v in meta.items()}}
+    class_map = {"num_classes": 6, "class": classes, "index": list(range(6))}
+    data, _ = rcollect.pred_to_dict(y, fsize=2000, class_map=class_map, term_repeats=None, crf_switch_cost=2.0,
+                                    crf_prior="biological")
+    out["crf_counts"] = np.array([[d[k] for k in range(6)] for d in data["per_class_counts"]])
+    out["crf_frag_pred"] = np.concatenate(data["frag_pred"])
+    np.savez_compressed(OUT / "viterbi.npz", **out)
 
 
 def main():
@@ -205,6 +245,9 @@ def main():
     for arr_ in ([[0, 3], [2, 5], [8, 9]], [[1, 2]], [[0, 10], [2, 3], [11, 12], [12, 20]]):
         merges.append(dict(inp=arr_, out=[list(map(int, r)) for r in rhelp.merge_overlapping_ranges(np.array(arr_))]))
     (OUT / "merge_ranges.json").write_text(json.dumps(merges))
+    viterbi_goldens(rhelp, rcollect)
+    if "--only-viterbi" in sys.argv:
+        return
     # ---- BASELINE config 1 fixture: the bundled legacy `default` weights + the health FASTA --------
     from jaeger_b200 import legacy
     from jaeger_b200.weights import read_tf_bundle, _flatten

@@ -236,6 +236,39 @@ def test_other_architectures_avg_pool_no_masking_relu(standin):
         assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2, (pooling, masking)
 
 
+@pytest.mark.parametrize("ksize", [2, 3])
+def test_wide_256_channel_layer_with_accumulator_reuse(ksize):
+    """A 128 -> 256 channel convolution has only two TMEM accumulators; with several tiles per SM
+    they are reused while three epilogue groups rotate (the case a phase-parity wait can get wrong).
+    k = 2 fits the tensor-core kernel's shared memory; k = 3 does not and takes the CUDA-core kernel."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project, standin_1p4m_config
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import seqwin
+    from tests.helpers import random_contigs
+    cfg = standin_1p4m_config()
+    m = cfg["model"]
+    hl = m["representation_learner"]["hidden_layers"][:4]
+    hl += [{"name": "masked_conv1d", "config": {"filters": 256, "kernel_size": ksize, "strides": 1, "dilation_rate": 2,
+                                                  "use_bias": True, "activation": None}},
+           {"name": "masked_batchnorm", "config": {"return_nmd": False}}, {"name": "activation", "config": {"activation": "gelu"}}]
+    m["representation_learner"]["hidden_layers"] = hl
+    m["classifier"]["input_shape"] = 256
+    m["reliability_model"]["input_shape"] = 128
+    spec = parse_project(cfg)
+    w = init_random(spec, 4)
+    recs = random_contigs(21, [2000] * 4 + [30000, 50000, 41000])      # 85 windows = 2720 tiles, ~18 per SM
+    eng = B200Engine(spec=spec, weights=w)
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500))
+    eng.close()
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    assert y["prediction"].shape[0] == len(wins)
+    ref = ofw.forward(spec, w, oenc.encode_windows([x.seq for x in wins], 2000))
+    assert np.abs(ref["prediction"] - y["prediction"]).max() <= 4e-3
+    assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2
+    assert np.abs(ref["nmd"] - y["nmd"]).max() <= 4e-3
+
+
 def test_window_independence_and_chunking_at_scale(standin):
     """Size-independent property at a realistic size: a window's logits do not depend on which
     forward chunk it lands in (4 000 windows through 3 different workspace budgets)."""
@@ -413,6 +446,42 @@ def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
     assert got["ranges"] == want_r
     assert np.allclose(got["scores"], want_s, atol=1e-6)
     assert (tmp_path / "out" / "standin" / "genome_prophage_regions.tsv").exists()
+
+
+def test_crf_viterbi_decoding_vs_reference_golden(standin):
+    """--crf: device Viterbi paths and per-contig class counts are index-exact against the
+    reference's viterbi_decode / pred_to_dict(crf_switch_cost=2.0) goldens, on every cost variant."""
+    import torch
+    from jaeger_b200.postprocess import build_transition_costs, contig_table
+    _, _, eng = standin
+    z = np.load(G / "viterbi.npz")
+    classes = ["bacteria", "phage", "eukarya", "archaea", "plasmid", "virus"]
+    pred, n_win = z["prediction"], z["n_win"]
+    off = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
+    potts = lambda lam: lam * (1.0 - np.eye(6))
+    with torch.cuda.stream(eng._stream()):
+        pd_, od = eng._h2d(pred), eng._h2d(off)
+        for name, costs in [("potts2", potts(2.0)), ("potts0", potts(0.0)), ("bio2", build_transition_costs(classes, 2.0)),
+                            ("uni05", build_transition_costs(classes, 0.5, "uniform")), ("user3", z["costs_user3"])]:
+            path, counts = eng.viterbi(pd_, od, costs)
+            path, counts = path.cpu().numpy(), counts.cpu().numpy()
+            assert np.array_equal(path, z[f"path_{name}"]), name
+            assert np.array_equal(counts, np.stack([np.bincount(path[a:b], minlength=6) for a, b in zip(off[:-1], off[1:])])), name
+        b = z["binary_logit"]
+        two = np.concatenate([np.zeros_like(b), b], -1)
+        path, _ = eng.viterbi(eng._h2d(two), eng._h2d(np.array([0, len(b)], np.int64)), 2.0 * (1.0 - np.eye(2)))
+        assert np.array_equal(path.cpu().numpy(), z["binary_path"])
+    assert np.array_equal(build_transition_costs(classes, 2.0), z["costs_bio2"])
+    # through the driver-level table
+    meta = {f"meta_{i}": [] for i in range(10)}
+    for ci, n in enumerate(n_win):
+        for j in range(n):
+            for i, v in enumerate([f"c{ci}", j * 1500, int(j == n - 1), j, 2000 + 1500 * (n - 1), 500, 500, 500, 500, " 0.000"]):
+                meta[f"meta_{i}"].append(str(v).encode())
+    y = {"prediction": pred, **{k: np.array(v) for k, v in meta.items()}}
+    data = contig_table(eng, y, 2000, crf_switch_cost=2.0)
+    assert np.array_equal(data["per_class_counts"], z["crf_counts"])
+    assert np.array_equal(data["frag_pred"], z["crf_frag_pred"])
 
 
 def _legacy_fixture():

@@ -114,3 +114,23 @@ def test_pred_to_dict_and_summary_match_reference():
     common = [c for c in gold_df.columns if c in got_df.columns]
     assert [c for c in gold_df.columns if c not in ("terminal_repeats", "repeat_length")] == list(got_df.columns)
     pd.testing.assert_frame_equal(gold_df[list(got_df.columns)], got_df[common], check_dtype=False)
+
+
+def test_viterbi_and_transition_costs_vs_reference_golden():
+    """--crf decoding (helpers.py:345-449): the restatement equals the reference on every variant."""
+    from oracle import postprocess as opp
+    z = np.load(G / "viterbi.npz")
+    classes = ["bacteria", "phage", "eukarya", "archaea", "plasmid", "virus"]
+    user = {"Bacteria": {"phage": 0.25, "virus": 2.0}, "plasmid": {"archaea": 4.0}, "unknown": {"phage": 9.0}}
+    assert np.array_equal(opp.build_transition_costs(classes, 2.0, "biological"), z["costs_bio2"])
+    assert np.array_equal(opp.build_transition_costs(classes, 0.5, "uniform"), z["costs_uni05"])
+    assert np.array_equal(opp.build_transition_costs(classes, 3.0, "biological", user), z["costs_user3"])
+    assert np.array_equal(opp.build_transition_costs(classes[:4], 2.0), z["costs_4cls"])
+    splits = np.cumsum(z["n_win"])[:-1]
+    for name, lam, costs in [("potts2", 2.0, None), ("potts0", 0.0, None), ("bio2", 2.0, z["costs_bio2"]),
+                             ("uni05", 0.5, z["costs_uni05"]), ("user3", 3.0, z["costs_user3"])]:
+        got = np.concatenate([opp.viterbi_decode(p, lam, costs) for p in np.split(z["prediction"], splits)])
+        assert np.array_equal(got, z[f"path_{name}"]), name
+    assert np.array_equal(z["path_potts0"], z["prediction"].argmax(1))        # lambda = 0 is the plain argmax
+    b = z["binary_logit"]
+    assert np.array_equal(opp.viterbi_decode(np.concatenate([np.zeros_like(b), b], -1), 2.0), z["binary_path"])

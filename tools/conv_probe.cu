@@ -163,7 +163,14 @@ int main(int argc, char** argv) {
     const double d = fabs(a - b);
     if (d > maxdiff) maxdiff = d;
     if (fabs(a) > maxref) maxref = fabs(a);
-    if (d > 0.03 + 0.02 * fabs(a)) ++nbad;
+    if (d > 0.03 + 0.02 * fabs(a)) {
+      if (nbad < 6 || (nbad % 4000037) == 0) {   // decode [group][row][64] -> (row, channel) ignoring the chunk swizzle
+        const size_t g = i / (static_cast<size_t>(plane) * 64), rem = i % (static_cast<size_t>(plane) * 64);
+        printf("  bad at group %zu row %lld chunk %zu elem %zu: ref %.4f got %.4f\n", g, static_cast<long long>(rem / 64) - jg::kGuardRows,
+               (rem % 64) / 8, rem % 8, a, b);
+      }
+      ++nbad;
+    }
   }
   std::vector<float> tr(n_win * cout), tt(n_win * cout), pr_(n_win * cout), pt_(n_win * cout);
   CK(cudaMemcpy(tr.data(), dtap_ref, tr.size() * 4, cudaMemcpyDeviceToHost));
