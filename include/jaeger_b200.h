@@ -22,6 +22,7 @@
  *   jg_smooth_scores     postprocess/prophages.py:126-151 (softmax + width-4 box sum)
  *   jg_segment_scores    postprocess/prophages.py:554-595 (KernelCPD/PELT at pen 1..9)
  *   jg_viterbi_decode    postprocess/helpers.py:393-449 (--crf window decoding)
+ *   jg_legacy_reliability postprocess/helpers.py:558-565 + collect.py:121-123 (legacy reliability_score)
  *
  * Conventions: every function returns 0 on success and a non-zero code on failure, with a
  * message retrievable through jg_last_error().  Pointers named d_* are DEVICE pointers (the
@@ -204,6 +205,15 @@ int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t mi
  * Outputs: d_path [n_windows] decoded class per window, d_counts [n_contigs][n_cls]. n_cls <= 8. */
 int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int32_t n_contigs, int64_t n_windows,
                       int32_t n_cls, const double* d_costs, int32_t* d_path, int32_t* d_counts);
+
+/* Legacy `default` model reliability: replaces ood_predict_default(..., type "sklearn")
+ * (postprocess/helpers.py:558-565; parameters loaded at commands/predict_legacy.py:99-109) per
+ * window and np.mean per contig (collect.py:121-123).  coef / intercept are the logistic
+ * regression's, cal_a / cal_b the prefit sigmoid calibrator's.  d_window_p0 [n_windows] float64,
+ * d_contig_mean [n_contigs] float64 (may be NULL). */
+int jg_legacy_reliability(jg_ctx* ctx, const float* d_embedding, int64_t n_windows, int32_t dim, const float* d_batch_mean,
+                          const float* d_batch_std, const double* d_coef, double intercept, double cal_a, double cal_b,
+                          const int64_t* d_offsets, int32_t n_contigs, double* d_window_p0, double* d_contig_mean);
 
 #ifdef __cplusplus
 }

@@ -812,4 +812,22 @@ int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offse
   return 0;
 }
 
+int jg_legacy_reliability(jg_ctx* ctx, const float* d_embedding, int64_t n_windows, int32_t dim, const float* d_batch_mean,
+                          const float* d_batch_std, const double* d_coef, double intercept, double cal_a, double cal_b,
+                          const int64_t* d_offsets, int32_t n_contigs, double* d_window_p0, double* d_contig_mean) {
+  if (n_windows <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  jg::legacy_reliability_kernel<<<grid_for(n_windows * 32, 256, ctx->num_sms, 8), 256, 0, st>>>(
+      d_embedding, n_windows, dim, d_batch_mean, d_batch_std, d_coef, intercept, cal_a, cal_b, d_window_p0);
+  ctx->launches += 1;
+  if (n_contigs > 0 && d_contig_mean) {
+    jg::segment_mean_f64_kernel<<<grid_for(n_contigs, 128, ctx->num_sms, 8), 128, 0, st>>>(
+        d_window_p0, reinterpret_cast<const long long*>(d_offsets), n_contigs, d_contig_mean);
+    ctx->launches += 1;
+  }
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

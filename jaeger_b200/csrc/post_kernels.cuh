@@ -293,4 +293,46 @@ __global__ void viterbi_kernel(const float* __restrict__ logits, const long long
   }
 }
 
+
+// ---- legacy `default` model: per-window reliability from the embedding ---------------------------
+// postprocess/helpers.py:558-565 (ood_predict_default, "sklearn" variant) with the bundled model
+// written out: features = l2_normalise((embedding - batch_mean) / batch_std) in float32, decision =
+// features . coef + intercept in float64 (LogisticRegression), probability of class 0 after the
+// prefit sigmoid calibration = 1 - 1 / (1 + exp(a * decision + b)).  One warp per window; a second
+// pass takes the per-contig mean (generate_summary_legacy's reliability_score, collect.py:121-123).
+__global__ void legacy_reliability_kernel(const float* __restrict__ emb, long long n_windows, int dim,
+                                          const float* __restrict__ mean, const float* __restrict__ sd,
+                                          const double* __restrict__ coef, double intercept, double cal_a, double cal_b,
+                                          double* __restrict__ p0) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = warp; w < n_windows; w += n_warps) {
+    float ss = 0.0f;
+    for (int k = lane; k < dim; k += 32) {
+      const float f = __fdiv_rn(__fsub_rn(emb[w * dim + k], mean[k]), sd[k]);
+      ss = __fmaf_rn(f, f, ss);
+    }
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = __fsqrt_rn(ss);
+    double dec = 0.0;
+    for (int k = lane; k < dim; k += 32) {
+      const float f = __fdiv_rn(__fdiv_rn(__fsub_rn(emb[w * dim + k], mean[k]), sd[k]), nrm);
+      dec += static_cast<double>(f) * coef[k];
+    }
+    for (int o = 16; o >= 1; o >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, o);
+    if (lane == 0) p0[w] = 1.0 - 1.0 / (1.0 + exp(cal_a * (dec + intercept) + cal_b));
+  }
+}
+
+__global__ void segment_mean_f64_kernel(const double* __restrict__ v, const long long* __restrict__ offsets, int n_seg,
+                                        double* __restrict__ out) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_seg; c += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (long long w = offsets[c]; w < offsets[c + 1]; ++w) s += v[w];
+    const long long n = offsets[c + 1] - offsets[c];
+    out[c] = n > 0 ? s / static_cast<double>(n) : 0.0;
+  }
+}
+
 }  // namespace jg

@@ -332,6 +332,18 @@ class B200Engine:
                                     path.data_ptr(), counts.data_ptr()))
         return path, counts
 
+    def legacy_reliability(self, embedding: torch.Tensor, offsets: torch.Tensor, ood: dict[str, Any]) -> tuple[torch.Tensor, torch.Tensor]:
+        """Legacy `default` reliability (helpers.py:558-565): per-window P(class 0) and its per-contig mean, float64."""
+        w, dim = embedding.shape
+        nc = offsets.numel() - 1
+        mean, sd = self._h2d(np.ascontiguousarray(ood["batch_mean"], np.float32)), self._h2d(np.ascontiguousarray(ood["batch_std"], np.float32))
+        coef = self._h2d(np.ascontiguousarray(ood["coef"], np.float64))
+        p0, cmean = self._empty((w,), torch.float64), self._empty((nc,), torch.float64)
+        check(lib.jg_legacy_reliability(self.ctx.handle, embedding.data_ptr(), w, dim, mean.data_ptr(), sd.data_ptr(), coef.data_ptr(),
+                                        float(ood["intercept"]), float(ood["cal_a"]), float(ood["cal_b"]), offsets.data_ptr(), nc,
+                                        p0.data_ptr(), cmean.data_ptr()))
+        return p0, cmean
+
     def set_profiling(self, on: bool) -> None:
         check(lib.jg_model_set_profiling(self.model, int(bool(on))))
 

@@ -23,6 +23,28 @@ BN_EPS = 1e-3      # keras.layers.BatchNormalization default
 DILATIONS = [1, 2] + [3 + i for i in range(5) for _ in range(2)]
 DEFAULT_LABELS = {0: "non-phage", 1: "phage", 2: "non-phage", 3: "non-phage"}     # data/config.json default_labels
 ALL_LABELS = {0: "bacteria", 1: "phage", 2: "eukarya", 3: "archaea"}
+SECOND_LABELS = {1: "eukarya", 2: "archaea", 3: "bacteria", 0: ""}                # data/config.json "second"
+VINDEX = 1                                                                         # data/config.json "vindex"
+
+
+def load_ood_params(model_dir) -> dict[str, Any]:
+    """The reliability model of the legacy `default` run (commands/predict_legacy.py:99-109):
+    LR_ood_4_class_default.pkl (a prefit sigmoid-calibrated logistic regression) + batch_means.npy
+    + batch_std.npy, reduced to the arrays the device kernel needs.  scikit-learn is only used to
+    unpickle; nothing of it runs on the prediction path."""
+    from pathlib import Path
+    d = Path(model_dir)
+    if d.suffix == ".npz":        # the same arrays exported once (keys as below, optionally prefixed "ood_")
+        z = np.load(d)
+        get = lambda k: z[k] if k in z.files else z["ood_" + k]
+        return {"coef": np.asarray(get("coef"), np.float64).ravel(), "intercept": float(get("intercept")), "cal_a": float(get("cal_a")),
+                "cal_b": float(get("cal_b")), "batch_mean": np.asarray(get("batch_mean"), np.float32), "batch_std": np.asarray(get("batch_std"), np.float32)}
+    import joblib
+    model = joblib.load(d / "LR_ood_4_class_default.pkl")
+    cc = model.calibrated_classifiers_[0]
+    return {"coef": np.asarray(cc.estimator.coef_, np.float64).ravel(), "intercept": float(cc.estimator.intercept_[0]),
+            "cal_a": float(cc.calibrators[0].a_), "cal_b": float(cc.calibrators[0].b_),
+            "batch_mean": np.load(d / "batch_means.npy").astype(np.float32), "batch_std": np.load(d / "batch_std.npy").astype(np.float32)}
 
 
 def weights_from_bundle(tensors: dict[str, np.ndarray]) -> dict[str, Any]:

@@ -173,3 +173,84 @@ def write_output(data: dict[str, Any], labels, indices, output_table_path: str |
     if not phage_df.empty:
         phage_df.to_csv(output_phage_table_path, sep="\t", index=False, float_format="%.3f")
     return len(df)
+
+
+# ---- legacy `default` model tables (collect.py:21-229) --------------------------------------------
+def contig_table_legacy(engine, y_pred: dict[str, np.ndarray], fsize: int, ood_params: dict | None, term_repeats=None) -> dict[str, Any]:
+    """pred_to_dict_legacy (collect.py:21-96): the modern per-contig reductions plus the
+    embedding-based reliability of every window and its per-contig mean, all on the device."""
+    pred = np.ascontiguousarray(y_pred["prediction"], dtype=np.float32)
+    offsets = _split_points(y_pred["meta_2"])
+    with torch.cuda.stream(engine._stream()):
+        pred_dev, off_dev = engine._h2d(pred), engine._h2d(offsets)
+        agg = engine.aggregate(pred_dev, None, off_dev)
+        rel = None
+        if ood_params is not None:
+            p0, cmean = engine.legacy_reliability(engine._h2d(np.ascontiguousarray(y_pred["embedding"], np.float32)), off_dev, ood_params)
+            rel = (p0.cpu().numpy(), cmean.cpu().numpy())
+        agg = {k: v.cpu().numpy() for k, v in agg.items()}
+    engine.ctx.sync()
+    first, n_win = offsets[:-1], np.diff(offsets)
+    g, c, a, t = (np.asarray(y_pred[k]).astype(float) for k in ("meta_5", "meta_6", "meta_7", "meta_8"))
+    ns = (fsize - (a + t + g + c)) / fsize
+    gcs = (g + c) / fsize
+    pred_sum, pred_var, consensus = agg["pred_sum"], agg["pred_var"], agg["consensus"].astype(np.int64)
+    return {
+        "headers": np.array(y_pred["meta_0"], dtype=str)[first], "length": np.array(y_pred["meta_4"], dtype=np.int32)[first],
+        "consensus": consensus, "per_class_counts": agg["per_class_counts"], "pred_sum": pred_sum, "pred_var": pred_var,
+        "frag_pred": agg["frag_pred"], "offsets": offsets, "ood_windows": rel[0] if rel else None,
+        "reliability_score": rel[1] if rel else None, "has_reliability": rel is not None, "entropy": agg["entropy"],
+        "host_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 1),
+        "prophage_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 0),
+        "repeats": term_repeats, "gc_mean": np.add.reduceat(gcs, first) / n_win, "ns_mean": np.add.reduceat(ns, first) / n_win,
+        "predictions": pred, "gc_skews": np.asarray(y_pred["meta_9"]).astype(float), "gcs": gcs,
+    }
+
+
+def window_summaries_legacy(frag_pred: np.ndarray, offsets: np.ndarray, phage_pos: int) -> list[str]:
+    """get_window_summary_legacy (helpers.py:43-70): runs of phage / non-phage windows as "<n>V" / "<n>n"."""
+    return window_summaries((np.asarray(frag_pred) == phage_pos).astype(np.int64), offsets, {0: "n", 1: "V"}, classes=("v",))
+
+
+def generate_summary_legacy(data: dict[str, Any], labels: list[str], model: str = "default"):
+    """generate_summary_legacy (collect.py:99-178) for the bundled `default` model; `labels` is the
+    prediction label of each class index (default_labels, or all_labels with --getalllabels)."""
+    import pandas as pd
+    from . import legacy
+    n = len(data["headers"])
+    cols: dict[str, Any] = {
+        "contig_id": data["headers"], "length": data["length"], "prediction": [labels[x] for x in data["consensus"]],
+        "entropy": data["entropy"],
+        "reliability_score": data["reliability_score"] if data.get("has_reliability", True) else ["unavailable"] * n,
+        "host_contam": data["host_contam"], "prophage_contam": data["prophage_contam"],
+    }
+    if model == "default":
+        cols["G+C"] = data["gc_mean"]
+        cols["N%"] = data["ns_mean"]
+        order = np.argsort(data["pred_sum"], axis=1)[:, 2:4]                       # collect.py:139-155
+        second = (np.prod(order == np.array([2, 1]), axis=1) + 2 * np.prod(order == np.array([3, 1]), axis=1)
+                  + 3 * np.prod(order == np.array([0, 1]), axis=1))
+        cols["prediction_2"] = [legacy.SECOND_LABELS[int(x)] for x in second]
+    for i, label in legacy.ALL_LABELS.items():
+        cols[f"#_{label}_windows"] = data["per_class_counts"][:, i]
+        cols[f"{label}_score"] = data["pred_sum"][:, i]
+        cols[f"{label}_var"] = data["pred_var"][:, i]
+    cols["window_summary"] = window_summaries_legacy(data["frag_pred"], data["offsets"], legacy.VINDEX)
+    df = pd.DataFrame(cols).set_index("contig_id")
+    rep = data.get("repeats")
+    if rep is None:
+        rep = pd.DataFrame({"contig_id": data["headers"], "terminal_repeats": [None] * n, "repeat_length": [None] * n})
+    df = df.join(rep.set_index("contig_id")[["terminal_repeats", "repeat_length"]], how="left").reset_index(names="contig_id")
+    df["contig_id"] = df["contig_id"].str.replace("___", ",")
+    return df
+
+
+def write_output_legacy(data: dict[str, Any], labels: list[str], output_table_path, output_phage_table_path,
+                        reliability_cutoff: float = 0.5, phage_score: float = 3, model: str = "default") -> int:
+    """write_output_legacy (collect.py:181-229)."""
+    df = generate_summary_legacy(data, labels, model)
+    df.to_csv(output_table_path, sep="\t", index=False, float_format="%.3f")
+    clause = f" and (reliability_score > {reliability_cutoff})" if data.get("has_reliability", True) else ""
+    df.query(f'(prediction == "phage") and (phage_score > {phage_score}){clause}').to_csv(
+        output_phage_table_path, sep="\t", index=False, float_format="%.3f")
+    return len(df)

@@ -49,7 +49,54 @@ def get_model_id(model: str) -> str:
     return model.split("_", 1)[1].rsplit("_", 1)[0]
 
 
+def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
+    """`jaeger predict -m default` (commands/predict_legacy.py:34-357) on the B200 engine: the bundled
+    legacy graph, the legacy encoder, pred_to_dict_legacy / write_output_legacy tables.
+    legacy_weights: a SavedModel `variables/` directory holding the graph's tensors, or an .npz written
+    by jaeger_b200.weights.save_npz_weights.  legacy_ood_dir: the reference's data/models/default
+    directory (LR_ood_4_class_default.pkl, batch_means.npy, batch_std.npy); omitted -> no reliability."""
+    from . import B200Engine, WindowSource, legacy
+    from .postprocess import contig_table_legacy, write_output_legacy
+    from .weights import load_npz_weights, read_tf_bundle
+
+    t0 = time.time()
+    input_path = Path(kwargs["input"])
+    fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
+    min_len = kwargs.get("min_len") or fsize
+    if min_len < fsize:                                                  # predict_legacy.py:57-64
+        logger.warning(f"--min-len < --fsize is not supported in legacy prediction mode; using --min-len={fsize}.")
+        min_len = fsize
+    wpath = Path(kwargs["legacy_weights"])
+    weights = load_npz_weights(wpath) if wpath.suffix == ".npz" else legacy.weights_from_bundle(read_tf_bundle(wpath))
+    ood = legacy.load_ood_params(kwargs["legacy_ood_dir"]) if kwargs.get("legacy_ood_dir") else None
+    engine = B200Engine(legacy_weights=weights, all_labels=bool(kwargs.get("getalllabels")), device=int(kwargs.get("physicalid") or 0))
+    out_dir = Path(kwargs["output"]) / "default"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    base = input_path.stem
+    table, phage_table = out_dir / f"{base}_jaeger.tsv", out_dir / f"{base}_phages_jaeger.tsv"     # predict_legacy.py:71-72
+    if table.exists() and not kwargs.get("overwrite"):
+        raise FileExistsError(f"{table} exists; use --overwrite")
+    src = WindowSource(fasta=input_path, fsize=fsize, stride=stride, min_len=None,
+                       dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
+                       dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
+                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)))
+    rec_off = src.load()[2]
+    if not (np.diff(rec_off) >= min_len).any():
+        raise ValueError(f"all records in {input_path} are < {min_len}bp")
+    y_pred = engine.predict(src)
+    t1 = time.time()
+    data = contig_table_legacy(engine, y_pred, fsize, ood)
+    labels = legacy.ALL_LABELS if kwargs.get("getalllabels") else legacy.DEFAULT_LABELS
+    n_written = write_output_legacy(data, [labels[i] for i in range(4)], table, phage_table,
+                                    reliability_cutoff=float(kwargs.get("rc", 0.5)), phage_score=float(kwargs.get("pc", 3)))
+    logger.info(f"processed {n_written}/{len(rec_off) - 1} sequences")
+    return {"table": table, "phage_table": phage_table, "num_written": n_written, "num": len(rec_off) - 1,
+            "windows": int(y_pred["prediction"].shape[0]), "predict_seconds": t1 - t0, "data": data}
+
+
 def run_core(**kwargs: Any) -> dict[str, Any]:
+    if (kwargs.get("model") or "") == "default":
+        return run_core_legacy(**kwargs)
     from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
     from .postprocess import contig_table, write_output
     from .prophage import call_regions
@@ -123,6 +170,9 @@ def main(argv=None) -> int:
     ap.add_argument("-o", "--output", required=True)
     ap.add_argument("-m", "--model", default="standin")
     ap.add_argument("--config", default=None, help="config.json with model_paths (utils/misc.py:309-331)")
+    ap.add_argument("--legacy-weights", dest="legacy_weights", default=None, help="-m default: SavedModel variables/ dir or .npz")
+    ap.add_argument("--legacy-ood-dir", dest="legacy_ood_dir", default=None, help="-m default: dir with the reliability model files")
+    ap.add_argument("--getalllabels", action="store_true")
     ap.add_argument("--fsize", type=int, default=2000)
     ap.add_argument("--stride", type=int, default=1500)
     ap.add_argument("--batch", type=int, default=96)

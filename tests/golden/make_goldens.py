@@ -12,6 +12,8 @@ are executed:
   jaeger.postprocess.collect.pred_to_dict, generate_summary
   jaeger.postprocess.prophages.logits_to_df_v2
   jaeger.postprocess.helpers.merge_overlapping_ranges, viterbi_decode, build_transition_costs
+  jaeger.postprocess.collect.pred_to_dict_legacy, generate_summary_legacy; helpers.ood_predict_default
+      (the bundled LR_ood_4_class_default.pkl through the installed scikit-learn)
 
 usage:  python tests/golden/make_goldens.py
 """
@@ -110,6 +112,52 @@ def viterbi_goldens(rhelp, rcollect):
     out["crf_counts"] = np.array([[d[k] for k in range(6)] for d in data["per_class_counts"]])
     out["crf_frag_pred"] = np.concatenate(data["frag_pred"])
     np.savez_compressed(OUT / "viterbi.npz", **out)
+
+
+def legacy_post_goldens(rhelp, rcollect):
+    """Legacy (`default` model) post-processing: ood_predict_default (sklearn variant) on the bundled
+    calibrated logistic regression, pred_to_dict_legacy, generate_summary_legacy."""
+    import warnings
+    import joblib
+    warnings.filterwarnings("ignore")
+    mdir = REF / "jaeger" / "data" / "models" / "default"
+    model = joblib.load(mdir / "LR_ood_4_class_default.pkl")
+    cc = model.calibrated_classifiers_[0]
+    ood_fix = dict(coef=cc.estimator.coef_.astype(np.float64).ravel(), intercept=np.float64(cc.estimator.intercept_[0]),
+                   cal_a=np.float64(cc.calibrators[0].a_), cal_b=np.float64(cc.calibrators[0].b_),
+                   batch_mean=np.load(mdir / "batch_means.npy"), batch_std=np.load(mdir / "batch_std.npy"))
+    params = {"type": "sklearn", "model": model, "batch_mean": ood_fix["batch_mean"], "batch_std": ood_fix["batch_std"]}
+    rng = np.random.default_rng(23)
+    n_win = [1, 2, 9, 40, 3, 135, 1, 6]
+    W = sum(n_win)
+    out = rng.normal(0, 2.5, (W, 4)).astype(np.float32)
+    out[20:24] = out[19]
+    emb = (rng.normal(0, 1.0, (W, 128)) * rng.uniform(0.2, 3.0, (W, 1)) + ood_fix["batch_mean"]).astype(np.float32)
+    meta = [[] for _ in range(10)]
+    for ci, n in enumerate(n_win):
+        for j in range(n):
+            g, c, a, t = (int(x) for x in rng.integers(300, 600, 4))
+            skew = round((g - c) / (g + c), 2)
+            for i, v in enumerate([f"contig___{ci}", j * 1500, int(j == n - 1), j, 2000 + 1500 * (n - 1), g, c, a, t, f"{skew: .3f}"]):
+                meta[i].append(str(v).encode())
+    meta = tuple(np.array(m) for m in meta)
+    y = {"y_hat": {"output": out, "embedding": emb}, "meta": meta}
+    config = json.loads((REF / "jaeger" / "data" / "config.json").read_text())["default"]
+    config["model"] = "default"
+    import pandas as pd
+    rep = pd.DataFrame({"contig_id": [f"contig___{i}" for i in range(len(n_win))], "terminal_repeats": [None] * len(n_win),
+                        "repeat_length": [None] * len(n_win)})
+    res = {}
+    for tag, labels in (("default", "default_labels"), ("all", "all_labels")):
+        config["labels"] = [v for k, v in config[labels].items()]
+        data, _ = rcollect.pred_to_dict_legacy(config, y, model="default", fsize=2000, ood_params=params, term_repeats=rep)
+        df = rcollect.generate_summary_legacy(config, data)
+        df.to_csv(OUT / f"summary_legacy_{tag}.tsv", sep="\t", index=False, float_format="%.3f")
+        res = data
+    np.savez_compressed(OUT / "legacy_post.npz", output=out, embedding=emb, **{f"meta_{i}": m for i, m in enumerate(meta)},
+                        ood_windows=np.concatenate(res["ood"]), pred_sum=res["pred_sum"], pred_var=res["pred_var"],
+                        consensus=res["consensus"], entropy=res["entropy"],
+                        **{f"ood_{k}": v for k, v in ood_fix.items()})
 
 
 def main():
@@ -246,7 +294,8 @@ def main():
         merges.append(dict(inp=arr_, out=[list(map(int, r)) for r in rhelp.merge_overlapping_ranges(np.array(arr_))]))
     (OUT / "merge_ranges.json").write_text(json.dumps(merges))
     viterbi_goldens(rhelp, rcollect)
-    if "--only-viterbi" in sys.argv:
+    legacy_post_goldens(rhelp, rcollect)
+    if "--only-post" in sys.argv:
         return
     # ---- BASELINE config 1 fixture: the bundled legacy `default` weights + the health FASTA --------
     from jaeger_b200 import legacy

@@ -484,6 +484,34 @@ def test_crf_viterbi_decoding_vs_reference_golden(standin):
     assert np.array_equal(data["frag_pred"], z["crf_frag_pred"])
 
 
+def test_legacy_postprocess_tables_vs_reference_golden(tmp_path):
+    """Legacy `default` post-processing on the device (aggregation + reliability kernel): the TSV
+    equals the reference's generate_summary_legacy output for both label sets; per-window reliability
+    within 1e-6 of the pickled scikit-learn model (float32 feature normalisation, float64 logit)."""
+    import pandas as pd
+    from jaeger_b200 import B200Engine, legacy
+    from jaeger_b200.postprocess import contig_table_legacy, write_output_legacy
+    z = np.load(G / "legacy_post.npz")
+    ood = {k[4:]: z[k] for k in z.files if k.startswith("ood_") and k != "ood_windows"}
+    y = {"prediction": z["output"], "embedding": z["embedding"], **{f"meta_{i}": z[f"meta_{i}"] for i in range(10)}}
+    eng = B200Engine(legacy_weights=legacy.random_weights(0))
+    data = contig_table_legacy(eng, y, 2000, ood)
+    assert np.abs(data["ood_windows"] - z["ood_windows"]).max() <= 1e-6
+    assert np.array_equal(data["pred_sum"], z["pred_sum"]) and np.array_equal(data["pred_var"], z["pred_var"])
+    assert np.array_equal(data["consensus"], z["consensus"]) and np.array_equal(data["entropy"], z["entropy"])
+    for tag, labels in (("default", legacy.DEFAULT_LABELS), ("all", legacy.ALL_LABELS)):
+        n = write_output_legacy(data, [labels[i] for i in range(4)], tmp_path / f"{tag}.tsv", tmp_path / f"{tag}_phages.tsv")
+        got = pd.read_csv(tmp_path / f"{tag}.tsv", sep="\t", keep_default_na=False)
+        want = pd.read_csv(G / f"summary_legacy_{tag}.tsv", sep="\t", keep_default_na=False)
+        assert n == len(want) and list(got.columns) == list(want.columns)
+        for col in want.columns:
+            assert got[col].tolist() == want[col].tolist(), (tag, col)
+        phages = pd.read_csv(tmp_path / f"{tag}_phages.tsv", sep="\t", keep_default_na=False)
+        sel = want[(want["prediction"] == "phage") & (want["phage_score"] > 3) & (want["reliability_score"] > 0.5)]
+        assert phages["contig_id"].tolist() == sel["contig_id"].tolist()
+    eng.close()
+
+
 def _legacy_fixture():
     from jaeger_b200.weights import load_npz_weights
     z = np.load(G / "legacy_default.npz")
@@ -527,6 +555,50 @@ def test_legacy_default_model_on_health_fasta_vs_oracle():
     agg = opp.aggregate_numeric(ref["output"], None, np.array([x.is_last for x in wins]))
     assert np.array_equal(data["consensus"], agg["consensus"])           # 9 / 9 contig labels
     eng.close()
+
+
+def test_legacy_default_driver_end_to_end_tsv(tmp_path):
+    """BASELINE config 1 through the driver (`-m default`): FASTA in, `<base>_jaeger.tsv` out.  Parity
+    target of SURVEY.md 8d: identical `prediction` column, scores within tolerance -- against the
+    oracle's forward pass + the restated legacy tables (fp16 activations: |score diff| <= 0.1,
+    reliability within 0.02)."""
+    import pandas as pd
+    from jaeger_b200 import codon_tables as ct
+    from jaeger_b200.predict import run_core
+    from jaeger_b200.weights import save_npz_weights
+    from oracle import encode as oenc
+    from oracle import legacy as oleg
+    from oracle import seqwin
+    w, recs = _legacy_fixture()
+    fa = tmp_path / "health.fasta"
+    fa.write_text("".join(f">{n} some description\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n" for n, s in recs))
+    save_npz_weights(tmp_path / "w.npz", w)
+    res = run_core(input=str(fa), output=str(tmp_path / "out"), model="default", legacy_weights=str(tmp_path / "w.npz"),
+                   legacy_ood_dir=str(G / "legacy_post.npz"), fsize=2000, stride=1500, dustmask=False, overwrite=True)
+    assert res["table"].name == "health_jaeger.tsv" and res["windows"] == 135 and res["num_written"] == 9
+    got = pd.read_csv(res["table"], sep="\t", keep_default_na=False)
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    table = dict(zip(oenc.CODONS, ct.LEGACY_AA_ID))
+    tok = np.stack([oenc.encode_window_legacy(x.seq, 2000, table) for x in wins]).astype(np.uint8)
+    ref = oleg.forward(w, tok)
+    z = np.load(G / "legacy_post.npz")
+    ood = {k[4:]: z[k] for k in z.files if k.startswith("ood_") and k != "ood_windows"}
+    meta = [np.array([str(v).encode() for v in col]) for col in zip(*[
+        (x.header, x.index, int(x.is_last), x.ordinal, x.seqlen, x.g, x.c, x.a, x.t, x.gc_skew) for x in wins])]
+    all_labels = {0: "bacteria", 1: "phage", 2: "eukarya", 3: "archaea"}
+    cols, _ = oleg.summary_legacy(ref["output"], ref["embedding"], tuple(meta), 2000, ood,
+                                  ["non-phage", "phage", "non-phage", "non-phage"], all_labels,
+                                  {1: "eukarya", 2: "archaea", 3: "bacteria", 0: ""}, 1)
+    want = pd.DataFrame(cols)
+    assert got["contig_id"].tolist() == want["contig_id"].tolist()
+    assert got["prediction"].tolist() == want["prediction"].tolist()
+    assert got["length"].tolist() == want["length"].tolist()
+    for c in ("G+C", "N%"):
+        assert np.allclose(got[c].to_numpy(float), want[c].to_numpy(float), atol=5e-4)
+    for lab in all_labels.values():
+        assert np.abs(got[f"{lab}_score"].to_numpy(float) - want[f"{lab}_score"].to_numpy(float)).max() <= 0.1, lab
+        assert np.abs(got[f"#_{lab}_windows"].to_numpy(int) - want[f"#_{lab}_windows"].to_numpy(int)).max() <= 2, lab
+    assert np.abs(got["reliability_score"].to_numpy(float) - want["reliability_score"].to_numpy(float)).max() <= 0.02
 
 
 def test_500bp_baseline_model_config3():

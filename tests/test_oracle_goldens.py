@@ -134,3 +134,31 @@ def test_viterbi_and_transition_costs_vs_reference_golden():
     assert np.array_equal(z["path_potts0"], z["prediction"].argmax(1))        # lambda = 0 is the plain argmax
     b = z["binary_logit"]
     assert np.array_equal(opp.viterbi_decode(np.concatenate([np.zeros_like(b), b], -1), 2.0), z["binary_path"])
+
+
+def _legacy_post_fixture():
+    z = np.load(G / "legacy_post.npz")
+    ood = {k[4:]: z[k] for k in z.files if k.startswith("ood_") and k != "ood_windows"}
+    meta = tuple(z[f"meta_{i}"] for i in range(10))
+    return z, ood, meta
+
+
+def test_legacy_postprocess_vs_reference_golden():
+    """pred_to_dict_legacy + generate_summary_legacy + the pickled reliability model: the restatement
+    reproduces the reference's TSV (both label sets) and the per-window reliability of the sklearn model."""
+    import io
+    import pandas as pd
+    from oracle import legacy as oleg
+    z, ood, meta = _legacy_post_fixture()
+    all_labels = {0: "bacteria", 1: "phage", 2: "eukarya", 3: "archaea"}
+    second = {1: "eukarya", 2: "archaea", 3: "bacteria", 0: ""}
+    for tag, labels in (("default", ["non-phage", "phage", "non-phage", "non-phage"]), ("all", list(all_labels.values()))):
+        cols, ood_w = oleg.summary_legacy(z["output"], z["embedding"], meta, 2000, ood, labels, all_labels, second, 1)
+        assert np.allclose(ood_w, z["ood_windows"], rtol=0, atol=1e-6)
+        got = pd.DataFrame(cols)
+        buf = io.StringIO()
+        got.to_csv(buf, sep="\t", index=False, float_format="%.3f")
+        got = pd.read_csv(io.StringIO(buf.getvalue()), sep="\t", keep_default_na=False)
+        want = pd.read_csv(G / f"summary_legacy_{tag}.tsv", sep="\t", keep_default_na=False)
+        for col in got.columns:
+            assert got[col].tolist() == want[col].tolist(), (tag, col)
