@@ -305,9 +305,19 @@ def run_b200(args):
             traffic = per_window * (sum(p[2] for p in prof[1:]) / max(1.0, res_launch)) if per_window else None
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "jg::tc::conv_tc_kernel (k5 d3 C128 residual convs, 16 of 17 conv launches)",
+    hbm_peak = None
+    try:
+        hbm_peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs"))
+    except Exception:
+        pass
+    avg_launch_s = res_ms / max(1.0, res_launch) * 1e-3
+    roofline = {"bound": "tensor",
+                "kernel": "the 16 k5 d3 C128 residual-conv launches of a forward pass: jg::tc2::conv_tc2_kernel (CTA pair, 12 launches) + "
+                          "jg::tc::conv_tc_kernel<3> (4 launches with NMD tap + second affine)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_ms": res_ms / max(1.0, res_launch),
+                "hbm_gbs_at_measured_traffic": (traffic / avg_launch_s / 1e9) if traffic and avg_launch_s > 0 else None,
+                "hbm_peak_gbs": hbm_peak,
                 "algorithmic_flop_per_window_per_launch": 2.0 * 6 * 659 * 5 * 128 * 128,
                 "kernel_share_of_step": conv_ms_total / ms,
                 "whole_model_tflops": plan.flops_per_window(lc, algorithmic_stem_cin=spec.embedding_size) * tot_windows / world / (ms * 1e-3) / 1e12}

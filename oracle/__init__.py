@@ -12,7 +12,8 @@ CUDA library is missing instead of falling back to this code.
 
 Pinning status (see DESIGN.md "Oracle"):
   * windows, window metadata, encoder tokens, post-processing helpers, per-contig
-    aggregation, TSV summary and score smoothing are pinned against golden vectors produced
+    aggregation (modern and legacy, incl. the pickled legacy reliability model), TSV
+    summaries, CRF / Viterbi decoding and score smoothing are pinned against golden vectors produced
     by importing the reference's own Python modules in the build container
     (tests/golden/make_goldens.py) and against the reference tests' known answers.
   * conv-stack logits: PARITY UNPINNED - TensorFlow/Keras cannot be installed here, so the
@@ -20,4 +21,6 @@ Pinning status (see DESIGN.md "Oracle"):
     tests' mask / pooling known answers.
   * change-point segmentation (ruptures KernelCPD + kneed): PARITY UNPINNED - restated from
     the published algorithms (PELT with L2 cost; Kneedle), libraries absent.
+  * low-complexity soft-masking (pydustmasker): PARITY UNPINNED - restated from the published
+    SDUST algorithm (oracle/dust.py), library absent.
 """
