@@ -85,7 +85,11 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
         raise ValueError(f"all records in {input_path} are < {min_len}bp")
     y_pred = engine.predict(src)
     t1 = time.time()
-    data = contig_table_legacy(engine, y_pred, fsize, ood)
+    term = None
+    if kwargs.get("terminal_repeats", True):
+        from .termini import scan_source
+        term = scan_source(engine, src, fsize)
+    data = contig_table_legacy(engine, y_pred, fsize, ood, term_repeats=term)
     labels = legacy.ALL_LABELS if kwargs.get("getalllabels") else legacy.DEFAULT_LABELS
     n_written = write_output_legacy(data, [labels[i] for i in range(4)], table, phage_table,
                                     reliability_cutoff=float(kwargs.get("rc", 0.5)), phage_score=float(kwargs.get("pc", 3)))
@@ -138,8 +142,12 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         crf_cost = float(kwargs.get("crf_switch_cost", 2.0))
         if isinstance(crf_matrix, (str, Path)):
             crf_matrix = json.loads(Path(crf_matrix).read_text())
-    data = contig_table(engine, y_pred, fsize, crf_switch_cost=crf_cost, crf_prior=kwargs.get("crf_prior", "biological"),
-                        crf_transition_matrix=crf_matrix)
+    term = None
+    if kwargs.get("terminal_repeats", True):                                  # predict.py:679-685 (always on in the reference)
+        from .termini import scan_source
+        term = scan_source(engine, src, fsize)
+    data = contig_table(engine, y_pred, fsize, term_repeats=term, crf_switch_cost=crf_cost,
+                        crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix)
     cm = engine.class_map
     n_written = write_output(data, cm["class"], cm["index"], table, phage_table,
                              reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
@@ -185,6 +193,8 @@ def main(argv=None) -> int:
     ap.add_argument("--crf-switch-cost", dest="crf_switch_cost", type=float, default=2.0)
     ap.add_argument("--crf-prior", dest="crf_prior", choices=["biological", "uniform"], default="biological")
     ap.add_argument("--crf-transition-matrix", dest="crf_transition_matrix", default=None)
+    ap.add_argument("--no-terminal-repeats", dest="terminal_repeats", action="store_false", default=True,
+                    help="skip the terminal-repeat scan (the reference always runs it)")
     ap.add_argument("--rc", type=float, default=0.1)
     ap.add_argument("--pc", type=float, default=3)
     ap.add_argument("-p", "--prophage", action="store_true")

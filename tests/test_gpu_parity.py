@@ -512,6 +512,80 @@ def test_legacy_postprocess_tables_vs_reference_golden(tmp_path):
     eng.close()
 
 
+def _repeat_contigs():
+    from oracle import termini as ot
+    rng = np.random.default_rng(77)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    core, long_core = rnd(120), rnd(700)
+    mut = core[:60] + ("A" if core[60] != "A" else "C") + core[61:]
+    recs = [("plain", rnd(3000)), ("dtr", core + rnd(3000) + core), ("itr,comma", core + rnd(2500) + ot.reverse_complement(core)),
+            ("mismatch", core + rnd(2500) + mut), ("gap", core + rnd(2500) + core[:60] + core[62:]),
+            ("qgap", core[:58] + core[59:] + rnd(2600) + core), ("ltr", long_core + rnd(30000) + long_core),
+            ("short", rnd(900)), ("nrun", "N" * 30 + core + rnd(2200) + core + "n" * 10),
+            ("lower", core.lower() + rnd(2400) + core), ("long", rnd(20) + core + rnd(48000) + core + rnd(33)),
+            ("both", core + rnd(1200) + ot.reverse_complement(core[:80]) + rnd(900) + core[:100])]
+    return recs
+
+
+def test_terminal_repeat_scan_vs_oracle(standin):
+    """device Smith-Waterman scans (DTR / ITR / LTR, mismatch, gaps in either line,
+    N runs, soft-masked letters, scan lengths 400..2000) against the oracle restatement -- every field
+    of the reference's table is index-exact.  parasail itself: parity unpinned (oracle/termini.py)."""
+    import torch
+    from jaeger_b200 import WindowSource
+    from jaeger_b200.termini import scan_source
+    from oracle import termini as ot
+    _, _, eng = standin
+    recs = _repeat_contigs()
+    got = scan_source(eng, WindowSource(records=recs, fsize=2000, stride=1500), 2000)
+    want = ot.scan_for_terminal_repeats(recs, 2000)
+    assert len(got) == len(want) == len(recs) - 1                     # the 900 bp record is skipped
+    kinds = []
+    for g, w in zip(got.to_dict("records"), want):
+        for k, v in w.items():
+            gv = g[k]
+            if v is None:
+                assert gv is None or gv != gv, (w["contig_id"], k, gv)
+            elif isinstance(v, float):
+                assert abs(gv - v) < 1e-12, (w["contig_id"], k)
+            else:
+                assert gv == v, (w["contig_id"], k, gv, v)
+        kinds.append(w["terminal_repeats"])
+    assert kinds[:7] == [None, "DTR", "ITR", "DTR", "DTR", "DTR", "LTR_DTR"]
+    # raw scan parity on random pairs (ties between equal maxima resolved identically)
+    from jaeger_b200.termini import JOB, _run_scan
+    rng = np.random.default_rng(5)
+    seq = "".join(rng.choice(list("ACGTN"), 6000, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+    jobs = np.zeros(8, dtype=JOB)
+    spans = [(0, 400, 0), (0, 400, 1), (100, 517, 0), (100, 517, 1), (0, 1000, 0), (3, 33, 0), (2000, 1999, 1), (50, 1, 0)]
+    for k, (q0, n, inv) in enumerate(spans):
+        jobs[k] = (q0, 6000 - n - q0 // 2, n, inv)
+    with torch.cuda.stream(eng._stream()):
+        codes, valid = eng.pack(eng._h2d(np.frombuffer(seq.encode(), np.uint8).copy()))
+    res = _run_scan(eng, codes, valid, jobs)
+    for k, (q0, n, inv) in enumerate(spans):
+        r0 = 6000 - n - q0 // 2
+        ref = seq[r0:r0 + n]
+        a = ot.sw_align(seq[q0:q0 + n], ot.reverse_complement(ref) if inv else ref)
+        assert (res[k, 0], res[k, 1], res[k, 2]) == (a["score"], a["end_query"], a["end_ref"]), (k, res[k], a)
+        if a["score"] < 104:
+            assert res[k, 3] == a["cols"], (k, res[k], a)
+
+
+def test_driver_tsv_carries_terminal_repeat_columns(standin, tmp_path):
+    import pandas as pd
+    from jaeger_b200.predict import run_core
+    recs = _repeat_contigs()
+    fa = tmp_path / "rep.fasta"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
+    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False)
+    tsv = pd.read_csv(res["table"], sep="\t", keep_default_na=False).set_index("contig_id")
+    assert tsv.loc["dtr", "terminal_repeats"] == "DTR" and int(float(tsv.loc["dtr", "repeat_length"])) == 120
+    assert tsv.loc["itr,comma", "terminal_repeats"] == "ITR"
+    assert tsv.loc["ltr", "terminal_repeats"] == "LTR_DTR" and int(float(tsv.loc["ltr", "repeat_length"])) == 700
+    assert tsv.loc["plain", "terminal_repeats"] == ""
+
+
 def _legacy_fixture():
     from jaeger_b200.weights import load_npz_weights
     z = np.load(G / "legacy_default.npz")
