@@ -38,22 +38,30 @@ inline cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t
 }
 
 // CTA-pair kernel: eligible when Cout is a multiple of 64, the tile count is even and the
-// per-CTA weights half + 4 stages + the output staging tiles fit in shared memory.
-inline bool conv_tc2_eligible(const ConvParams& p) {
+// per-CTA weights half + 4 stages (+ the output staging tiles of the 2-group variant) fit in
+// shared memory.  groups = 2: staged bulk stores (light layers); groups = 3: direct stores.
+inline bool conv_tc2_eligible(const ConvParams& p, int groups = 2) {
   if (p.cin % 64 != 0 || p.cout % 64 != 0 || p.cout > 256 || p.ntaps > kMaxTaps || (p.n_tiles & 1)) return false;
-  return tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r).total <= kMaxSmem;
+  if (groups == 3 && 4 * p.cout > 512) return false;      // three groups need at least three accumulators
+  return tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, groups == 2 ? 2 : 0).total <= kMaxSmem;
 }
 
-inline cudaError_t launch_conv_tc2(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  if (!conv_tc2_eligible(p)) return cudaErrorInvalidConfiguration;
-  const tc2::SmemLayout2 L = tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r);
+inline cudaError_t launch_conv_tc2(const ConvParams& p, int num_sms, cudaStream_t stream, int groups = 2) {
+  if (!conv_tc2_eligible(p, groups)) return cudaErrorInvalidConfiguration;
+  const tc2::SmemLayout2 L = tc2::smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, groups == 2 ? 2 : 0);
   int pairs = num_sms / 2;
   if (pairs > p.n_tiles / 2) pairs = p.n_tiles / 2;
   if (pairs <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(L.total));
-  if (e != cudaSuccess) return e;
-  tc2::conv_tc2_kernel<<<2 * pairs, tc2::kThreads2, L.total, stream>>>(p);
+  cudaError_t e;
+  if (groups == 2) {
+    e = cudaFuncSetAttribute(tc2::conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total));
+    if (e != cudaSuccess) return e;
+    tc2::conv_tc2_kernel<2><<<2 * pairs, tc2::kThreads2, L.total, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(tc2::conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total));
+    if (e != cudaSuccess) return e;
+    tc2::conv_tc2_kernel<3><<<2 * pairs, tc2::kThreads2H, L.total, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

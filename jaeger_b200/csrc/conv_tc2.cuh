@@ -27,8 +27,9 @@ namespace tc2 {
 
 using namespace jg::tc;
 
-constexpr int kThreads2 = 384;
+constexpr int kThreads2 = 384;        // kG = 2 epilogue groups (light layers, staged bulk stores)
 constexpr int kEpiGroups2 = 2;
+constexpr int kThreads2H = 512;       // kG = 3 epilogue groups (heavy layers, direct stores, no staging tiles)
 constexpr int kStages2 = 4;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -92,7 +93,8 @@ struct SmemLayout2 {
   uint32_t stage_bytes, stage_pitch, rows_a, lead, groups, w_bytes, out_group_bytes, out_groups;
 };
 
-__host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps, int halo_l, int halo_r) {
+__host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps, int halo_l, int halo_r,
+                                                    int staged_groups = kEpiGroups2) {
   SmemLayout2 L;
   L.lead = static_cast<uint32_t>((halo_l + 7) / 8 * 8);
   L.rows_a = L.lead + kTileM + static_cast<uint32_t>((halo_r + 7) / 8 * 8);
@@ -105,7 +107,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps
   L.w_off = 0;
   L.stage_off = (L.w_bytes + 1023u) & ~1023u;
   L.out_off = L.stage_off + kStages2 * L.stage_pitch;
-  L.par_off = L.out_off + kEpiGroups2 * L.out_groups * L.out_group_bytes;
+  L.par_off = L.out_off + static_cast<uint32_t>(staged_groups) * L.out_groups * L.out_group_bytes;
   L.bar_off = L.par_off + 6u * cout * 4u;
   L.val_off = L.bar_off + 256u;                                         // validity ring: kVSlots x 128 bytes
   L.total = L.val_off + kVSlots * 128u + 1024u;
@@ -124,15 +126,21 @@ __host__ __device__ __forceinline__ long long w2_index(int t, int ci, int co, in
   return h * half_elems + ((static_cast<long long>(t) * (cin >> 6) + g) * half + n) * 64 + chunk * 8 + (cl & 7);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// kG = 2: two epilogue groups, output staged in shared memory and bulk-stored (light layers).
+// kG = 3: three epilogue groups at 128 registers, direct global stores and no staging tiles, rolled
+//         epilogue only: for layers bound by epilogue instruction issue (NMD tap / second affine / pool).
+template <int kG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * kG, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
+  constexpr bool kStage = kG == 2;
+  constexpr int kNThreads = 128 + 128 * kG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool is_leader = rank == 0;
-  const SmemLayout2 L = smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r);
+  const SmemLayout2 L = smem_layout2(p.cin, p.cout, p.ntaps, p.halo_l, p.halo_r, kStage ? kG : 0);
 
   float* s_par = reinterpret_cast<float*>(smem + L.par_off);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
@@ -161,7 +169,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
 
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[519] = clock64();
   // ---- one-time setup ------------------------------------------------------------------
-  epi_params_fill(s_par, p, threadIdx.x, kThreads2);
+  epi_params_fill(s_par, p, threadIdx.x, kNThreads);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(FULL(s), is_leader ? 2 : 1);     // leader: own producer + the peer's relay
@@ -301,11 +309,11 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const bool has_sc = p.sc != nullptr;
     const bool light = p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2;
     const uint32_t warp_stage = out_base + grp * L.out_groups * L.out_group_bytes + static_cast<uint32_t>(q) * 32u * 128u;
-    for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kEpiGroups2, it += kEpiGroups2) {
+    for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kG, it += kG) {
       const int as = it % n_acc;
       const uint32_t aph = static_cast<uint32_t>(it / n_acc) & 1u;
-      const bool tr_on = p.dbg && blockIdx.x == 0 && grp == 0 && q == 0 && lane == 0 && (it / kEpiGroups2) < 24;
-      long long* tr = tr_on ? p.dbg + 600 + 16 * (it / kEpiGroups2) : nullptr;
+      const bool tr_on = p.dbg && blockIdx.x == 0 && grp == 0 && q == 0 && lane == 0 && (it / kG) < 24;
+      long long* tr = tr_on ? p.dbg + 600 + 16 * (it / kG) : nullptr;
       if (tr_on) tr[0] = clock64();
       const long long tile_row0 = (static_cast<long long>(pt) * 2 + rank) * kTileM;
       const int row_in_tile = q * 32 + lane;
@@ -346,32 +354,38 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         }
         uint4 out[4];
         epilogue_batch<kLight>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
-        if (p.y) {
-          const int og = cb >> 1;
-          if ((cb & 1) == 0) {
-            // this warp's previous store from the same staging rows must have finished READING them
-            if (lane == 0) {
-              if (L.out_groups == 2) bulk_wait_read<1>();
-              else if (L.out_groups == 4) bulk_wait_read<3>();
-              else bulk_wait_read<0>();
+        if constexpr (kStage) {
+          if (p.y) {
+            const int og = cb >> 1;
+            if ((cb & 1) == 0) {
+              // this warp's previous store from the same staging rows must have finished READING them
+              if (lane == 0) {
+                if (L.out_groups == 2) bulk_wait_read<1>();
+                else if (L.out_groups == 4) bulk_wait_read<3>();
+                else bulk_wait_read<0>();
+              }
+              __syncwarp();
             }
-            __syncwarp();
+            // staging rows = the exact g64sw image of rows [tile_row0 + 32 q, +32) of channel group og
+            const uint32_t srow = warp_stage + og * L.out_group_bytes + static_cast<uint32_t>(lane) * 128u;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = srow + ((((cb & 1) * 4 + j) ^ sw) * 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(out[j].x), "r"(out[j].y), "r"(out[j].z), "r"(out[j].w) : "memory");
+            }
+            if (cb & 1) {   // 32 rows x 64 channels staged: 4 KB, contiguous in HBM
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                bulk_s2g(p.y + (static_cast<long long>(og) * p.y_plane + tile_row0 + q * 32) * 64, warp_stage + og * L.out_group_bytes, 32u * 128u);
+                bulk_commit();
+              }
+            }
           }
-          // staging rows = the exact g64sw image of rows [tile_row0 + 32 q, +32) of channel group og
-          const uint32_t srow = warp_stage + og * L.out_group_bytes + static_cast<uint32_t>(lane) * 128u;
+        } else if (p.y) {
+          act_t* yrow = p.y + (static_cast<long long>(cb >> 1) * p.y_plane + row) * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t a = srow + ((((cb & 1) * 4 + j) ^ sw) * 16);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(out[j].x), "r"(out[j].y), "r"(out[j].z), "r"(out[j].w) : "memory");
-          }
-          if (cb & 1) {   // 32 rows x 64 channels staged: 4 KB, contiguous in HBM
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              bulk_s2g(p.y + (static_cast<long long>(og) * p.y_plane + tile_row0 + q * 32) * 64, warp_stage + og * L.out_group_bytes, 32u * 128u);
-              bulk_commit();
-            }
-          }
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(yrow + ((((cb & 1) * 4 + j) ^ sw) * 8)) = out[j];
         }
         if (tr_on && cb < 4) tr[4 + 2 * cb] = clock64();
       };
@@ -383,7 +397,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(TEMPTY(as), 0));
       };
 
-      if (n_cb == 4 && light) {
+      if (kStage && n_cb == 4 && light) {
         // light layers (conv1 / conv2 of a residual block): unrolled, TMEM loads one batch ahead
         using L1 = std::true_type;
         uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -417,7 +431,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       }
       if (tr_on) tr[11] = clock64();
     }
-    if (p.y && lane == 0) bulk_wait_all();      // stores complete before the kernel ends
+    if (kStage && p.y && lane == 0) bulk_wait_all();      // stores complete before the kernel ends
   }
 
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[523] = clock64();

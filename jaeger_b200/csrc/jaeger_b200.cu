@@ -89,7 +89,7 @@ struct jg_model {
         *rel_b2 = nullptr, *tap_mean = nullptr, *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr,
         *mlp_b2 = nullptr;
   int final_mask = 0;
-  int conv_impl = 0;            // 0 auto, 1 single-CTA kernel only, 2 CTA-pair kernel wherever eligible (JG_CONV_IMPL)
+  int conv_impl = 0;            // 0 auto, 1 single-CTA kernel only, 2 CTA-pair kernel wherever eligible, 3 = 0 (JG_CONV_IMPL)
   std::vector<int> tap_mask_slot;
   // workspace -------------------------------------------------------------------------------
   long long cap_rows = 0, cap_windows = 0;
@@ -661,13 +661,17 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       JG_CUDA(cudaEventCreate(&ev1));
       JG_CUDA(cudaEventRecord(ev0, st));
     }
-    // Kernel choice (profiles/conv_kernel_r1.md): the CTA-pair kernel wins on light epilogues; layers
-    // with an NMD tap / second affine are epilogue-bound and run better with three epilogue groups.
+    // Kernel choice (profiles/conv_kernel_r1.md): light epilogues -> CTA-pair kernel with two epilogue
+    // groups and staged bulk stores; layers with an NMD tap / second affine / pool are bound by epilogue
+    // instruction issue -> three epilogue groups: the pair kernel's 3-group variant when Cin >= 128
+    // (+13 % over the single-CTA kernel in the forward pass), else the single-CTA kernel (stem).
     const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
-    const bool pair = !layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy)));
+    const bool pair3 = !layer_ref && heavy && p.cin >= 128 && (m->conv_impl == 0 || m->conv_impl == 3) &&
+                       jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
+    const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
     if (pair) p.w = L.w2;
     cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
-                            : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st) : jg::launch_conv_tc(p, ctx->num_sms, st));
+                            : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
     if (m->profiling) {

@@ -144,8 +144,8 @@ int main(int argc, char** argv) {
   jg::ConvParams pt = p;
   pt.y = reinterpret_cast<jg::act_t*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
   if (strip & 8) { pt.y = nullptr; }
-  auto launch = [&](const jg::ConvParams& q) { return variant == 2 ? jg::launch_conv_tc2(q, dev_sms, 0) : jg::launch_conv_tc(q, dev_sms, 0); };
-  if (variant == 2) pt.w = reinterpret_cast<const jg::act_t*>(dw2);
+  auto launch = [&](const jg::ConvParams& q) { return variant >= 2 ? jg::launch_conv_tc2(q, dev_sms, 0, variant) : jg::launch_conv_tc(q, dev_sms, 0); };
+  if (variant >= 2) pt.w = reinterpret_cast<const jg::act_t*>(dw2);
   CK(launch(pt));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
@@ -199,7 +199,7 @@ int main(int argc, char** argv) {
     printf("trace (cycles rel. to first MMA start): it  mma_start mma_issued | epi_arrive_wait tfull_ready epi_done\n");
     for (int i = 0; i < 16 && h[i * 8] != 0; ++i)
       printf("  %2d  %8lld %8lld | %8lld %8lld %8lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0);
-    if (variant == 2 && h[600] != 0) {
+    if (variant >= 2 && h[600] != 0) {
       printf("pair epilogue trace, group 0 warp 0 (cycles rel. to tile start; prev = since previous tile start):\n  it  prev | rowvalid+sc  tfull | ld0 b0 ld1 b1 ld2 b2 ld3 b3 | end\n");
       for (int i = 0; i < 24 && h[600 + 16 * i] != 0; ++i) {
         const long long* t = &h[600 + 16 * i];
