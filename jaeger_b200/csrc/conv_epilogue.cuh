@@ -178,13 +178,21 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
 // raw: 32 fp32 accumulators (as bits) of channels [32*cb, 32*cb+32) of this thread's row.
 // scc: the shortcut's 32 fp16 values for the same channels (4 x uint4, logical chunk order).
 // out: the 32 fp16 results (4 x uint4, logical chunk order), zero when the row is masked.
-// kLight: the layer has no NMD tap, no second affine and no pooling (the caller checked), so that
-// code is not instantiated -- the callers unroll the light path over the batches of a tile.
-template <bool kLight = false>
+// kMode specialises the epilogue at compile time for the layer shapes that carry the time, so that
+// the flag tests disappear and the whole batch is one scheduling region (the runtime-flag version
+// splits it into basic blocks the compiler cannot overlap):
+//   EPI_GENERIC  every feature behind its runtime flag
+//   EPI_LIGHT    tanh-GELU only: no NMD tap, no second affine, no pooling (conv1 / conv2 of a residual block)
+//   EPI_FINAL    shortcut + tanh-GELU + NMD tap on the block output + second affine + tanh-GELU
+//   EPI_FINAL_POOL  the same + masked global max pool (last layer)
+// The caller checks that the layer matches the mode it picks.
+enum EpiMode { EPI_GENERIC = 0, EPI_LIGHT = 1, EPI_FINAL = 2, EPI_FINAL_POOL = 3 };
+template <int kMode = EPI_GENERIC>
 __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiParams& e, int cb, const uint32_t (&raw)[32],
                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane,
                                                int win, uint4 (&out)[4]) {
-  if (!kLight && p.tap_mode == 1) {   // NMD tap on the raw conv output (acc + bias), stem only
+  constexpr bool kGen = kMode == EPI_GENERIC, kFinal = kMode == EPI_FINAL || kMode == EPI_FINAL_POOL;
+  if (kGen && p.tap_mode == 1) {   // NMD tap on the raw conv output (acc + bias), stem only
     float tv[32];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -204,7 +212,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     h[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
     h[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
   }
-  if (has_sc) {
+  if (kFinal || has_sc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 s = sc_valid ? scc[j] : e.scc[cb * 4 + j];
@@ -213,15 +221,15 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       for (int k = 0; k < 4; ++k) h[j * 4 + k] = __hadd2(h[j * 4 + k], s2[k]);
     }
   }
-  act_apply_h2(h, p.act1);
-  if (!kLight && p.tap_mode == 2) {   // NMD tap on the block output
+  if (kFinal || kMode == EPI_LIGHT) act_apply_h2(h, ACT_GELU_TANH); else act_apply_h2(h, p.act1);
+  if (kFinal || (kGen && p.tap_mode == 2)) {   // NMD tap on the block output
     __half2 tv[16];
     const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
     atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
   }
-  if (!kLight && p.has_affine2) {
+  if (kFinal || (kGen && p.has_affine2)) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 a = e.scale2[cb * 4 + j], b = e.shift2[cb * 4 + j];
@@ -230,15 +238,16 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
 #pragma unroll
       for (int k = 0; k < 4; ++k) h[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
     }
-    act_apply_h2(h, p.act2);
+    if (kFinal) act_apply_h2(h, ACT_GELU_TANH); else act_apply_h2(h, p.act2);
   }
-  if (!kLight && p.pool_mode != 0) {
+  if (kMode == EPI_FINAL_POOL || (kGen && p.pool_mode != 0)) {
     __half2 tv[16];
-    const uint32_t fill_bits = p.pool_mode == 1 ? 0xFC00FC00u : 0u;      // -inf for the max, 0 for the sum
+    const bool pool_max = kMode == EPI_FINAL_POOL || p.pool_mode == 1;
+    const uint32_t fill_bits = pool_max ? 0xFC00FC00u : 0u;      // -inf for the max, 0 for the sum
     const __half2 fill = *reinterpret_cast<const __half2*>(&fill_bits);
 #pragma unroll
     for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : fill;
-    if (p.pool_mode == 1) {
+    if (pool_max) {
       const float m = warp_cols_reduce_h2<true>(tv, lane);
       if (m > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, m);
     } else {

@@ -307,7 +307,9 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int n_cb = p.cout / 32;
     const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
-    const bool light = p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2;
+    const bool light = p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.act1 == ACT_GELU_TANH;
+    const bool final_shape = has_sc && p.tap_mode == 2 && p.has_affine2 && p.act1 == ACT_GELU_TANH && p.act2 == ACT_GELU_TANH;
+    const int epi_mode = final_shape ? (p.pool_mode == 0 ? EPI_FINAL : (p.pool_mode == 1 ? EPI_FINAL_POOL : EPI_GENERIC)) : EPI_GENERIC;
     const uint32_t warp_stage = out_base + grp * L.out_groups * L.out_group_bytes + static_cast<uint32_t>(q) * 32u * 128u;
     for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kG, it += kG) {
       const int as = it % n_acc;
@@ -340,8 +342,8 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.cout);
 
       // one 32-channel batch whose accumulators are already in `raw`
-      auto batch = [&](int cb, const uint32_t (&raw)[32], auto light_tag) {
-        constexpr bool kLight = decltype(light_tag)::value;
+      auto batch = [&](int cb, const uint32_t (&raw)[32], auto mode_tag) {
+        constexpr int kMode = decltype(mode_tag)::value;
         uint4 scc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) scc[j] = scv[j];
@@ -353,7 +355,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
                                                      ((((nb & 1) * 4 + j) ^ sw) * 8));
         }
         uint4 out[4];
-        epilogue_batch<kLight>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
+        epilogue_batch<kMode>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
         if constexpr (kStage) {
           if (p.y) {
             const int og = cb >> 1;
@@ -399,7 +401,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
 
       if (kStage && n_cb == 4 && light) {
         // light layers (conv1 / conv2 of a residual block): unrolled, TMEM loads one batch ahead
-        using L1 = std::true_type;
+        using L1 = std::integral_constant<int, EPI_LIGHT>;
         uint32_t r0[32], r1[32], r2[32], r3[32];
         tmem_ld32(t_addr, r0);
         tmem_ld_wait();
@@ -419,15 +421,21 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         release_acc();
         batch(3, r3, L1{});
       } else {
-        // everything else: one rolled copy of the full epilogue (it would not fit the instruction cache unrolled)
-        for (int cb = 0; cb < n_cb; ++cb) {
-          uint32_t r0[32];
-          tmem_ld32(t_addr + static_cast<uint32_t>(cb * 32), r0);
-          tmem_ld_wait();
-          if (tr_on && cb < 4) tr[3 + 2 * cb] = clock64();
-          if (cb + 1 == n_cb) release_acc();
-          batch(cb, r0, std::false_type{});
-        }
+        // everything else: rolled copies of the full epilogue (unrolled it would not fit the instruction
+        // cache), specialised for the two block-final shapes, generic otherwise
+        auto rolled = [&](auto mode_tag) {
+          for (int cb = 0; cb < n_cb; ++cb) {
+            uint32_t r0[32];
+            tmem_ld32(t_addr + static_cast<uint32_t>(cb * 32), r0);
+            tmem_ld_wait();
+            if (tr_on && cb < 4) tr[3 + 2 * cb] = clock64();
+            if (cb + 1 == n_cb) release_acc();
+            batch(cb, r0, mode_tag);
+          }
+        };
+        if (epi_mode == EPI_FINAL) rolled(std::integral_constant<int, EPI_FINAL>{});
+        else if (epi_mode == EPI_FINAL_POOL) rolled(std::integral_constant<int, EPI_FINAL_POOL>{});
+        else rolled(std::integral_constant<int, EPI_GENERIC>{});
       }
       if (tr_on) tr[11] = clock64();
     }
