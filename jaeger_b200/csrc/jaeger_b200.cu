@@ -74,6 +74,7 @@ struct Layer {
   jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
   float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const  (6 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
+  float* w_tap = nullptr;      // stem with an NMD tap on one-hot input: fp16-rounded weights [k][64][cout] + their tap sum [64][cout]
   int shifts_h[jg::kMaxTaps];
   int halo_l = 0, halo_r = 0;
 };
@@ -447,6 +448,18 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
           img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
     JG_CUDA(cudaMalloc(&L.w2, img.size() * 2));
     JG_CUDA(cudaMemcpy(L.w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    if (l == 0 && L.f[LF_TAP_MODE] == 1 && cin == 64) {   // linear stem tap (stem_tap_kernel)
+      std::vector<float> wt(static_cast<size_t>(k + 1) * 64 * cout, 0.0f);
+      for (int t = 0; t < k; ++t)
+        for (int ci = 0; ci < 64; ++ci)
+          for (int co = 0; co < cout; ++co) {
+            const float v = __half2float(__float2half_rn(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]));
+            wt[(static_cast<size_t>(t) * 64 + ci) * cout + co] = v;
+            wt[(static_cast<size_t>(k) * 64 + ci) * cout + co] += v;
+          }
+      JG_CUDA(cudaMalloc(&L.w_tap, wt.size() * 4));
+      JG_CUDA(cudaMemcpy(L.w_tap, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    }
     std::vector<float> par(6 * static_cast<size_t>(cout), 0.0f);
     const int order[6] = {LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST};
     for (int a = 0; a < 6; ++a) {
@@ -518,7 +531,7 @@ int jg_model_destroy(jg_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->ctx->device);
   free_workspace(m);
-  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.par); cudaFree(L.shifts); }
+  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.w_tap); cudaFree(L.par); cudaFree(L.shifts); }
   for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
                    m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
@@ -641,6 +654,10 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.act2 = L.f[LF_ACT2];
     p.has_affine2 = L.f[LF_HAS_AFF2];
     p.tap_mode = L.f[LF_TAP_MODE];
+    // The stem's tap is linear in its one-hot input: it is taken from token counts after the conv
+    // (stem_tap_kernel), which leaves the stem a light layer for the CTA-pair kernel.
+    const bool linear_tap = !use_ref && L.w_tap != nullptr && L.f[LF_SHRINK] >= 0 && L.f[LF_CUM_SHRINK_IN] == 0 && L.f[LF_HALVINGS] == 0;
+    if (linear_tap) { p.tap_mode = 0; p.tap_sum = nullptr; }
     p.pool_mode = L.f[LF_POOL_MODE];
     p.fuse_mask = layer_ref ? 0 : 1;
     p.in_mask = mask_row0(L.f[LF_MASK_IN]);
@@ -674,6 +691,18 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
                             : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+    if (linear_tap) {
+      jg::StemTapParams tp{};
+      tp.tokens = d_tokens; tp.lpad = d_lpad; tp.count = p.count;
+      tp.w = L.w_tap; tp.wsum = L.w_tap + static_cast<size_t>(L.f[LF_K]) * 64 * cout; tp.bias = L.par;
+      tp.tap = m->tap_sum + static_cast<long long>(L.f[LF_TAP_SLOT]) * n_windows * m->tap_width;
+      tp.n_windows = n_windows; tp.lc = lc; tp.pitch = pitch; tp.frames = m->frames; tp.tok_offset = m->tok_offset;
+      tp.ntaps = L.f[LF_K]; tp.shrink = L.f[LF_SHRINK]; tp.cout = cout;
+      for (int t = 0; t < L.f[LF_K]; ++t) tp.shifts[t] = L.shifts_h[t];
+      jg::stem_tap_kernel<<<grid_for(n_windows, 1, ctx->num_sms, 16), 128, 0, st>>>(tp);
+      ctx->launches++;
+      JG_CUDA(cudaGetLastError());
+    }
     if (m->profiling) {
       JG_CUDA(cudaEventRecord(ev1, st));
       m->prof_events.emplace_back(ev0, ev1);

@@ -254,4 +254,67 @@ __global__ void heads_kernel(const HeadParams p) {
   }
 }
 
+
+// NMD tap of the stem without touching the conv output.  The tap is the sum over a window's valid
+// output rows of (conv output + bias) per channel (nnlib/v2/nmd.py:52-77 applied to the first
+// masked_conv1d).  The stem's input is a one-hot token row, so that sum is linear in token counts:
+//   tap[c] = sum_t sum_v H[t][v] * W[t][v][c] + (number of valid rows) * bias[c],
+//   H[t][v] = #{positions i of the window's frames holding symbol v with 0 <= i - shift_t < limit}.
+// A token that exists makes its rows valid in mask mode `any`, so H does not depend on the mask.
+// Positions inside [max shift, limit + min shift) feed every tap (one histogram, weights summed
+// over the taps); the few positions at the frame ends are counted per tap.  One CTA per window.
+struct StemTapParams {
+  const uint8_t* tokens; const int* lpad; const int* count;
+  const float* w;      // [ntaps][64][cout], the fp16-rounded weights the MMA uses
+  const float* wsum;   // [64][cout] = sum over taps
+  const float* bias;   // [cout]
+  float* tap;          // [n_windows][cout]
+  long long n_windows;
+  int lc, pitch, frames, tok_offset, ntaps, shrink, cout;
+  int shifts[16];
+};
+__global__ void stem_tap_kernel(const StemTapParams p) {
+  __shared__ int s_total[64];
+  __shared__ int s_edge[16 * 64];
+  int lo = p.shifts[0], mn = p.shifts[0];
+  for (int t = 1; t < p.ntaps; ++t) { lo = p.shifts[t] > lo ? p.shifts[t] : lo; mn = p.shifts[t] < mn ? p.shifts[t] : mn; }
+  for (long long w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_total[i] = 0;
+    for (int i = threadIdx.x; i < p.ntaps * 64; i += blockDim.x) s_edge[i] = 0;
+    __syncthreads();
+    const int lp = p.lpad[w];
+    const int len = lp < p.lc ? lp : p.lc;
+    const int limit = lp - p.shrink;
+    const int hi = limit + mn;
+    for (int idx = threadIdx.x; idx < p.frames * len; idx += blockDim.x) {
+      const int f = idx / len, i = idx - f * len;
+      const int ch = static_cast<int>(p.tokens[(w * p.frames + f) * p.pitch + i]) - p.tok_offset;
+      if (ch < 0 || ch >= 64) continue;
+      if (i >= lo && i < hi) {
+        atomicAdd(&s_total[ch], 1);
+      } else {
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int j = i - p.shifts[t];
+          if (j >= 0 && j < limit) atomicAdd(&s_edge[t * 64 + ch], 1);
+        }
+      }
+    }
+    __syncthreads();
+    const float n_valid = static_cast<float>(p.count[w]);
+    for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
+      float acc = 0.0f;
+      for (int v = 0; v < 64; ++v) {
+        const int n = s_total[v];
+        if (n) acc = fmaf(static_cast<float>(n), p.wsum[v * p.cout + c], acc);
+      }
+      for (int tv = 0; tv < p.ntaps * 64; ++tv) {
+        const int n = s_edge[tv];
+        if (n) acc = fmaf(static_cast<float>(n), p.w[static_cast<long long>(tv) * p.cout + c], acc);
+      }
+      p.tap[w * p.cout + c] = fmaf(n_valid, p.bias[c], acc);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace jg
