@@ -587,8 +587,8 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   auto mask_row0 = [&](int s) { return m->masks[s] + jg::kGuardRows; };
 
   // stem operand: one-hot rows + token mask
-  jg::expand_tokens_kernel<<<grid_for(rows * 8, 256, ctx->num_sms, 16), 256, 0, st>>>(
-      d_tokens, d_lpad, rows, lc, pitch, geom, m->tok_offset, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
+  jg::expand_tokens_kernel<<<grid_for(n_windows * (m->frames + 1), 1, ctx->num_sms, 8), 256, 0, st>>>(
+      d_tokens, d_lpad, n_windows, lc, pitch, geom, m->tok_offset, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
       m->counts + static_cast<long long>(m->layers[0].f[LF_MASK_IN]) * m->cap_windows);
   ctx->launches++;
   JG_CUDA(cudaGetLastError());

@@ -14,38 +14,48 @@ struct RowGeom {
 };
 
 // tokens [W][6][pitch] -> one-hot rows (64 channels, g64sw) + input mask (token != 0).
-// One thread per 16-byte chunk, 8 threads per row; every row of the window block is written
-// (gap / tail rows get zeros) so the buffer can be recycled between chunks of windows.
+// One CTA per (window, frame) segment -- plus one per window for the zero tail rows -- so the row
+// geometry costs no per-thread division; one thread per 16-byte chunk, consecutive threads write
+// consecutive chunks.  Every row of the window block is written (gap / tail rows get zeros) so the
+// buffer can be recycled between chunks of windows.
 __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const int* __restrict__ lpad,
-                                     long long n_rows, int lc, int pitch, RowGeom g, int tok_offset,
+                                     long long n_windows, int lc, int pitch, RowGeom g, int tok_offset,
                                      act_t* __restrict__ x, uint8_t* __restrict__ mask,
                                      int* __restrict__ count) {
-  const long long total = n_rows * 8;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = idx >> 3;
-    const int pc = static_cast<int>(idx & 7);            // physical chunk position
-    const int chunk = pc ^ static_cast<int>(row & 7);    // logical chunk = channels 8*chunk..
-    const long long w = row / g.rpw;
-    const int rw = static_cast<int>(row - w * g.rpw);
-    const int f = rw / g.period, j = rw - f * g.period;
-    int tok = -1;
-    if (f < g.frames && j < lc && j < lpad[w]) tok = tokens[(w * g.frames + f) * pitch + j];
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    // token t -> one-hot channel t - tok_offset (v2: offset 1, token 0 = unknown = zero row;
-    // legacy: offset 0, every in-frame position has a channel)
-    const int ch = tok - tok_offset;
-    tok = (tok >= tok_offset) ? 1 : 0;
-    if (tok > 0 && (ch >> 3) == chunk) {
-      const uint32_t one = 0x3C00u << (16 * (ch & 1));      // fp16 1.0
-      const int word = (ch & 7) >> 1;
-      if (word == 0) o.x = one; else if (word == 1) o.y = one; else if (word == 2) o.z = one; else o.w = one;
+  const int n_part = g.frames + 1;
+  const long long n_seg = n_windows * n_part;
+  for (long long sg = blockIdx.x; sg < n_seg; sg += gridDim.x) {
+    const long long w = sg / n_part;
+    const int f = static_cast<int>(sg - w * n_part);
+    const int row_lo = f * g.period;
+    const int n_rows = (f < g.frames) ? g.period : g.rpw - row_lo;
+    int lim = 0;
+    if (f < g.frames) { lim = lpad[w]; lim = lim < lc ? lim : lc; }
+    const uint8_t* tk = tokens + (w * g.frames + (f < g.frames ? f : 0)) * pitch;
+    const long long row0 = w * g.rpw + row_lo;
+    int cnt = 0;
+    for (int t = threadIdx.x; t < n_rows * 8; t += blockDim.x) {
+      const int j = t >> 3, pc = t & 7;                      // row of the segment, physical chunk position
+      const long long row = row0 + j;
+      const int chunk = pc ^ static_cast<int>(row & 7);      // logical chunk = channels 8*chunk..
+      // token t -> one-hot channel t - tok_offset (v2: offset 1, token 0 = unknown = zero row;
+      // legacy: offset 0, every in-frame position has a channel)
+      const int ch = (j < lim ? static_cast<int>(tk[j]) : -1) - tok_offset;
+      const bool on = ch >= 0 && j < lim;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (on && (ch >> 3) == chunk) {
+        const uint32_t one = 0x3C00u << (16 * (ch & 1));     // fp16 1.0
+        const int word = (ch & 7) >> 1;
+        if (word == 0) o.x = one; else if (word == 1) o.y = one; else if (word == 2) o.z = one; else o.w = one;
+      }
+      *reinterpret_cast<uint4*>(x + row * 64 + pc * 8) = o;
+      if (pc == 0) {
+        mask[row] = on;
+        cnt += on ? 1 : 0;
+      }
     }
-    *reinterpret_cast<uint4*>(x + row * 64 + pc * 8) = o;
-    if (pc == 0) {
-      mask[row] = tok > 0;
-      if (tok > 0) atomicAdd(count + w, 1);
-    }
+    for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(count + w, cnt);
   }
 }
 

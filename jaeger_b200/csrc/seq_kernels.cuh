@@ -95,9 +95,14 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
   uint32_t* s_codes = s_mem;
   uint32_t* s_valid = s_codes + words_c;   // valid for tokens (soft-masked removed if case_sensitive)
   uint32_t* s_count = s_valid + words_b;   // valid & ~soft (what the G/C/A/T counts see)
-  __shared__ uint8_t s_lut[64];
+  __shared__ uint8_t s_lut[64];       // index = (first base << 4) | (second << 2) | third
+  __shared__ uint8_t s_lut_fwd[64];   // index = first | (second << 2) | (third << 4)
   __shared__ int s_cnt[4];
-  if (threadIdx.x < 64) s_lut[threadIdx.x] = lut64[threadIdx.x];
+  if (threadIdx.x < 64) {
+    const uint32_t i = threadIdx.x;
+    s_lut[i] = lut64[i];
+    s_lut_fwd[i] = lut64[((i & 3u) << 4) | (i & 12u) | (i >> 4)];
+  }
 
   for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
     const long long base = win_base[w];
@@ -171,21 +176,23 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
     const int words_per_frame = pitch / 4;
     for (int idx = threadIdx.x; idx < 6 * words_per_frame; idx += kEncThreads) {
       const int f = idx / words_per_frame;
-      const int j0 = (idx % words_per_frame) * 4;
+      const int j0 = (idx - f * words_per_frame) * 4;
       uint32_t packed = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = j0 + e;
         uint32_t tok = 0;
         if (j < nc) {
-          int p0, p1, p2;
-          uint32_t flip;
-          if (f < 3) { p0 = f + 3 * j; p1 = p0 + 1; p2 = p0 + 2; flip = 0; }
-          else { p0 = n - 1 - (f - 3) - 3 * j; p1 = p0 - 1; p2 = p0 - 2; flip = 2; }
-          const uint32_t ok = get_bit(s_valid, p0) & get_bit(s_valid, p1) & get_bit(s_valid, p2);
-          const uint32_t ci = ((get_code(s_codes, p0) ^ flip) << 4) | ((get_code(s_codes, p1) ^ flip) << 2) |
-                              (get_code(s_codes, p2) ^ flip);
-          tok = ok ? s_lut[ci] : 0u;
+          // a codon is 6 contiguous bits of the packed stream starting at its lowest base:
+          // forward frames read them first-base-lowest (the LUT copy with the base order reversed),
+          // reverse frames first-base-highest, complemented by xor 0b101010
+          const int lowest = (f < 3) ? f + 3 * j : n - 3 - (f - 3) - 3 * j;
+          const int cb = 2 * lowest, cw = cb >> 5;
+          const uint32_t six = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31) & 63u;
+          const int vw = lowest >> 5;
+          const uint32_t ok3 = __funnelshift_r(s_valid[vw], s_valid[vw + 1], lowest & 31) & 7u;
+          const uint32_t t = (f < 3) ? s_lut_fwd[six] : s_lut[six ^ 0x2Au];
+          tok = ok3 == 7u ? t : 0u;
         }
         packed |= tok << (8 * e);
       }
