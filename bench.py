@@ -312,8 +312,8 @@ def run_b200(args):
         pass
     avg_launch_s = res_ms / max(1.0, res_launch) * 1e-3
     roofline = {"bound": "tensor",
-                "kernel": "the 16 k5 d3 C128 residual-conv launches of a forward pass: jg::tc2::conv_tc2_kernel (CTA pair, 12 launches) + "
-                          "jg::tc::conv_tc_kernel<3> (4 launches with NMD tap + second affine)",
+                "kernel": "the 16 k5 d3 C128 residual-conv launches of a forward pass: jg::tc2::conv_tc2_kernel<2> (CTA pair, 12 launches) + "
+                          "jg::tc2::conv_tc2_kernel<3> (CTA pair with 3 epilogue groups, the 4 launches with NMD tap + second affine)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_ms": res_ms / max(1.0, res_launch),
                 "hbm_gbs_at_measured_traffic": (traffic / avg_launch_s / 1e9) if traffic and avg_launch_s > 0 else None,
