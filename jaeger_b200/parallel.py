@@ -68,3 +68,39 @@ def gather_contig_records(records: torch.Tensor, contig_ids: torch.Tensor, n_tot
         keep = i_ >= 0
         table[i_[keep]] = r_[keep]
     return table
+
+
+# ---- driver-level sharding (python -m torch.distributed.run ... -m jaeger_b200.predict) ----------
+def dist_env() -> tuple[int, int, int]:
+    """(world, rank, local_rank) from the torchrun environment; (1, 0, 0) when not launched by it."""
+    import os
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_loaded(loaded, mine: np.ndarray):
+    """Sub-select records `mine` (sorted global indices) of a loaded FASTA (names, bases, offsets):
+    the shard's bases are copied back to back into a fresh (pinned when CUDA is present) buffer."""
+    names, host, offsets = loaded
+    lens = np.diff(offsets)[mine]
+    sub_off = np.zeros(len(mine) + 1, dtype=np.int64)
+    np.cumsum(lens, out=sub_off[1:])
+    buf = torch.empty(max(int(sub_off[-1]), 1), dtype=torch.uint8)
+    if torch.cuda.is_available():
+        buf = buf.pin_memory()
+    dst, srcv = buf.numpy(), host.numpy()
+    for k, c in enumerate(mine):
+        dst[sub_off[k]:sub_off[k + 1]] = srcv[offsets[c]:offsets[c + 1]]
+    return [names[c] for c in mine], buf[:int(sub_off[-1])], sub_off
+
+
+def merge_rank_frames(frames):
+    """Per-rank summary tables (each with helper columns `_pass`, `_gid` = pass of the contig's windows
+    and its index in the FASTA) -> one table in the single-process row order: long-pass contigs in
+    FASTA order, then short-pass contigs in FASTA order."""
+    import pandas as pd
+    frames = [f for f in frames if f is not None and len(f)]
+    if not frames:
+        return pd.DataFrame()
+    df = pd.concat(frames, ignore_index=True)
+    df = df.sort_values(["_pass", "_gid"], kind="stable").reset_index(drop=True)
+    return df.drop(columns=["_pass", "_gid"])

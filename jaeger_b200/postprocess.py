@@ -160,7 +160,14 @@ def generate_summary(data: dict[str, Any], labels, indices):
 def write_output(data: dict[str, Any], labels, indices, output_table_path: str | Path,
                  output_phage_table_path: str | Path, reliability_cutoff: float = 0.5, phage_score: float = 1) -> int:
     """collect.py:561-608: `N% < 0.3` filter, %.3f TSV, and the phage subset."""
-    df = generate_summary(data, labels, indices).query("`N%` < 0.3")
+    return write_tables(generate_summary(data, labels, indices), labels, data.get("has_reliability", True), output_table_path,
+                        output_phage_table_path, reliability_cutoff, phage_score)
+
+
+def write_tables(df, labels, has_reliability: bool, output_table_path: str | Path, output_phage_table_path: str | Path,
+                 reliability_cutoff: float = 0.5, phage_score: float = 1) -> int:
+    """The file-writing half of write_output, on an assembled (possibly multi-rank) summary table."""
+    df = df.query("`N%` < 0.3")
     df.to_csv(output_table_path, sep="\t", index=False, float_format="%.3f")
     lower = [str(x).lower() for x in labels]
     viral = "phage"
@@ -168,7 +175,7 @@ def write_output(data: dict[str, Any], labels, indices, output_table_path: str |
         viral = labels[lower.index("phage")]
     elif "virus" in lower:
         viral = labels[lower.index("virus")]
-    clause = f" and (reliability_score > {reliability_cutoff})" if data.get("has_reliability", True) else ""
+    clause = f" and (reliability_score > {reliability_cutoff})" if has_reliability else ""
     phage_df = df.query(f'(prediction == "{viral}") and ({viral}_score > {phage_score}){clause}')
     if not phage_df.empty:
         phage_df.to_csv(output_phage_table_path, sep="\t", index=False, float_format="%.3f")

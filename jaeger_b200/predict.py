@@ -102,13 +102,23 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if (kwargs.get("model") or "") == "default":
         return run_core_legacy(**kwargs)
     from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
-    from .postprocess import contig_table, write_output
+    from .parallel import dist_env, merge_rank_frames, shard_contigs, shard_loaded
+    from .postprocess import contig_table, generate_summary, write_tables
     from .prophage import call_regions
 
     t0 = time.time()
     input_path = Path(kwargs["input"])
     model_name = kwargs.get("model") or "standin"
     fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
+    # one process per GPU under torchrun: contigs are sharded over the ranks, rank 0 writes
+    world, rank, local_rank = dist_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        kwargs["physicalid"] = local_rank
     if model_name == "standin":
         engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=int(kwargs.get("physicalid") or 0))
         model_id = "standin"
@@ -134,6 +144,13 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     n_records = len(rec_off) - 1
     if not (np.diff(rec_off) >= (min_len or fsize)).any():
         raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
+    mine = np.arange(n_records)
+    if world > 1:
+        # balance on long-pass window counts; a short contig of the two-pass mode is one window
+        lens = np.diff(rec_off)
+        eff = np.where((lens < fsize) & (lens >= (min_len or fsize)), fsize, lens)
+        mine = shard_contigs(eff, world, fsize, stride)[rank]
+        src._loaded = shard_loaded(src.load(), mine)
     y_pred = engine.predict(src)
     t1 = time.time()
     crf_cost, crf_matrix = None, kwargs.get("crf_transition_matrix")          # predict.py:288-307
@@ -147,23 +164,47 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         from .termini import scan_source
         term = scan_source(engine, src, fsize)
     data = contig_table(engine, y_pred, fsize, term_repeats=term, crf_switch_cost=crf_cost,
-                        crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix)
+                        crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix) if y_pred else None
     cm = engine.class_map
-    n_written = write_output(data, cm["class"], cm["index"], table, phage_table,
-                             reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
-    result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
-              "windows": int(y_pred["prediction"].shape[0]), "predict_seconds": t1 - t0}
-    logger.info(f"processed {n_written}/{n_records} sequences")
-    if kwargs.get("prophage"):
+    df = generate_summary(data, cm["class"], cm["index"]) if data else None
+    regions = None
+    if kwargs.get("prophage") and data:
         regions = call_regions(engine, data, cm, fsize, stride, lc=int(kwargs.get("lc", 500_000)),
                                sensitivity=float(kwargs.get("sensitivity", 1.5)))
+    n_windows = int(y_pred["prediction"].shape[0]) if y_pred else 0
+    if world > 1:
+        if df is not None:       # row -> (pass, index of the contig in the FASTA), the single-process row order
+            first = data["offsets"][:-1]
+            local = engine.windows.contig[first]
+            df["_pass"] = (engine.windows.seqlen[first] < fsize).astype(np.int64)
+            df["_gid"] = mine[local]
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object({"df": df, "regions": regions, "windows": n_windows}, gathered, dst=0)
+        if kwargs.get("window_scores") and data:       # per-window arrays stay with the rank that owns the contigs
+            off = data["offsets"]
+            np.savez(out_dir / f"{base}_window_scores.rank{rank}.npz", headers=data["headers"], lengths=data["length"],
+                     predictions=np.array([data["predictions"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
+                     allow_pickle=True)
+            kwargs["window_scores"] = False
+        if rank != 0:
+            return {"table": table, "phage_table": phage_table, "rank": rank, "windows": n_windows, "predict_seconds": t1 - t0}
+        df = merge_rank_frames([g["df"] for g in gathered])
+        n_windows = sum(g["windows"] for g in gathered)
+        if kwargs.get("prophage"):
+            regions = {k: v for g in gathered if g["regions"] for k, v in g["regions"].items()}
+    n_written = write_tables(df, cm["class"], bool(data.get("has_reliability", True)) if data else True, table, phage_table,
+                             reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
+    result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
+              "windows": n_windows, "predict_seconds": t1 - t0}
+    logger.info(f"processed {n_written}/{n_records} sequences")
+    if kwargs.get("prophage"):
         rows = ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
         for name, r in regions.items():
             for (ws, we), (s, e), sc in zip(r["ranges"], r["coords"], r["scores"]):
                 rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
         (out_dir / f"{base}_prophage_regions.tsv").write_text("\n".join(rows) + "\n")
         result["prophage_regions"] = regions
-    if kwargs.get("window_scores"):                                       # predict.py:458-470
+    if kwargs.get("window_scores") and data:                              # predict.py:458-470
         off = data["offsets"]
         np.savez(out_dir / f"{base}_window_scores.npz", headers=data["headers"], lengths=data["length"],
                  predictions=np.array([data["predictions"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
@@ -210,6 +251,12 @@ def main(argv=None) -> int:
     except Exception as e:                                               # predict.py:811-816
         logger.error(f"an error {e} occured during inference")
         return 1
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    if res.get("rank"):
+        return 0
     logger.info(f"wrote {res['table']} ({res['num_written']} contigs, {res['windows']} windows, {res['predict_seconds']:.2f} s)")
     return 0
 

@@ -70,3 +70,31 @@ def test_native_fasta_loader_matches_line_reader(tmp_path):
     empty.write_bytes(b"")
     names, host, off = load_fasta(empty)
     assert names == [] and host.numel() == 0 and off.tolist() == [0]
+
+
+def test_driver_sharding_helpers_round_trip():
+    """shard_loaded gives each rank exactly its records; merge_rank_frames restores the single-process
+    row order (long-pass contigs in FASTA order, then short-pass contigs)."""
+    import pandas as pd
+    from jaeger_b200.engine import WindowSource
+    from jaeger_b200.parallel import merge_rank_frames, shard_contigs, shard_loaded
+    rng = np.random.default_rng(3)
+    lens = [2500, 700, 9000, 2000, 1200, 30000, 4100, 650]
+    recs = [(f"c{i}", "".join(rng.choice(list("ACGT"), n))) for i, n in enumerate(lens)]
+    loaded = WindowSource(records=recs).load()
+    eff = np.where(np.array(lens) < 2000, 2000, np.array(lens))
+    shards = shard_contigs(eff, 3, 2000, 1500)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(len(lens)))
+    frames = []
+    for mine in shards:
+        names, buf, off = shard_loaded(loaded, mine)
+        assert names == [recs[c][0] for c in mine]
+        for k, c in enumerate(mine):
+            assert bytes(buf.numpy()[off[k]:off[k + 1]]) == recs[c][1].encode()
+        # a rank's table: its long-pass contigs first, then its short ones (the engine's window order)
+        order = [c for c in mine if lens[c] >= 2000] + [c for c in mine if lens[c] < 2000]
+        frames.append(pd.DataFrame({"contig_id": [f"c{c}" for c in order], "_pass": [int(lens[c] < 2000) for c in order],
+                                    "_gid": order}))
+    merged = merge_rank_frames(frames + [None])
+    want = [f"c{c}" for c in range(len(lens)) if lens[c] >= 2000] + [f"c{c}" for c in range(len(lens)) if lens[c] < 2000]
+    assert merged["contig_id"].tolist() == want and list(merged.columns) == ["contig_id"]
