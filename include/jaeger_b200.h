@@ -60,7 +60,7 @@ int64_t jg_ctx_launch_count(jg_ctx* ctx);
 
 /* ---- stage 0: FASTA ingest (host) ------------------------------------------------------------
  * Replaces the pyfastx passes of the reference (utils/fs.py:99-115, seqops/io.py:98-104): one
- * streaming pass. jg_fasta_scan sizes the outputs; jg_fasta_load fills h_bases (n_bases bytes,
+ * streaming pass over a plain or gzip-compressed file. jg_fasta_scan sizes the outputs; jg_fasta_load fills h_bases (n_bases bytes,
  * ideally pinned memory: it is the H2D source), h_offsets (n_records + 1) and h_names (record
  * names = header up to the first whitespace, NUL-terminated, back to back). */
 int jg_fasta_scan(const char* path, int64_t* n_records, int64_t* n_bases, int64_t* name_bytes);

@@ -9,6 +9,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <zlib.h>
+
 #include "conv_launch.cuh"
 #include "dust_kernels.cuh"
 #include "model_kernels.cuh"
@@ -236,20 +238,21 @@ void* jg_ctx_stream(jg_ctx* ctx) { return ctx->stream; }
 int64_t jg_ctx_launch_count(jg_ctx* ctx) { return ctx->launches; }
 
 // ---- stage 0: FASTA ingest (host) ----------------------------------------------------------------
-// One pass over the file: record name = header up to the first whitespace, sequence = the record's
+// One pass over the file (plain or gzip, through zlib): record name = header up to the first whitespace, sequence = the record's
 // lines with line ends and blanks removed (what pyfastx hands to seqops/io.py:98-104).
 namespace {
 struct FastaScan { int64_t n_records = 0, n_bases = 0, name_bytes = 0; };
 
 int fasta_walk(const char* path, FastaScan* scan, uint8_t* bases, int64_t* offsets, char* names) {
-  FILE* fh = std::fopen(path, "rb");
+  gzFile fh = gzopen(path, "rb");            // reads plain and gzip-compressed files alike
   if (!fh) return fail(std::string("cannot open ") + path);
+  gzbuffer(fh, 1 << 20);
   std::vector<char> buf(1 << 22);
   int64_t rec = -1, nb = 0, nn = 0;
   bool in_header = false, header_name_done = false, at_line_start = true;
-  size_t got;
-  while ((got = std::fread(buf.data(), 1, buf.size(), fh)) > 0) {
-    for (size_t i = 0; i < got; ++i) {
+  int got;
+  while ((got = gzread(fh, buf.data(), static_cast<unsigned>(buf.size()))) > 0) {
+    for (int i = 0; i < got; ++i) {
       const char c = buf[i];
       if (at_line_start && c == '>') {
         ++rec;
@@ -275,7 +278,9 @@ int fasta_walk(const char* path, FastaScan* scan, uint8_t* bases, int64_t* offse
     }
   }
   if (in_header) { if (names) names[nn] = 0; ++nn; }
-  std::fclose(fh);
+  const bool read_error = got < 0;
+  gzclose(fh);
+  if (read_error) return fail(std::string("read error (corrupt gzip stream?) in ") + path);
   if (offsets) offsets[rec + 1] = nb;
   scan->n_records = rec + 1; scan->n_bases = nb; scan->name_bytes = nn;
   return 0;

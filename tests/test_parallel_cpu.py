@@ -66,6 +66,11 @@ def test_native_fasta_loader_matches_line_reader(tmp_path):
         assert names == [r[0] for r in ref]
         assert bytes(host.numpy()) == b"".join(r[1] for r in ref)
         assert np.diff(off).tolist() == [len(r[1]) for r in ref]
+    import gzip
+    gz = tmp_path / "x.fa.gz"
+    gz.write_bytes(gzip.compress(p.read_bytes()))
+    names, host, off = load_fasta(gz)
+    assert names == ["a", "b", "c", "d"] and bytes(host.numpy()) == b"ACGTNNACGGTTTT" and off.tolist() == [0, 8, 10, 10, 14]
     empty = tmp_path / "e.fa"
     empty.write_bytes(b"")
     names, host, off = load_fasta(empty)
