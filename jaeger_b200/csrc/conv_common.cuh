@@ -82,7 +82,7 @@ __host__ __device__ __forceinline__ long long act_index(long long row, int c, lo
   return (static_cast<long long>(g) * plane + row) * 64 + chunk * 8 + (cl & 7);
 }
 // element index of weight (tap t, in-channel ci, out-channel co) inside the smem image:
-// blocks [t][ci/64] of [cout rows][64 k] bf16, 16-byte chunks swizzled by (co & 7)
+// blocks [t][ci/64] of [cout rows][64 k] fp16, 16-byte chunks swizzled by (co & 7)
 __host__ __device__ __forceinline__ long long w_index(int t, int ci, int co, int cin, int cout) {
   const int g = ci >> 6, cl = ci & 63;
   const int chunk = (cl >> 3) ^ (co & 7);

@@ -17,7 +17,8 @@
 //   * D: fp32 in TMEM, a ring of 4 accumulators (4 x Cout columns) so the MMAs run up to
 //     three tiles ahead of the epilogues.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4.. = kEpiGroups epilogue groups (TMEM lane quarter = warp % 4)
+// warp 2 = TMEM allocator, warp 3 = validity helper (row masks a few tiles ahead, conv_epilogue.cuh),
+// warps 4.. = kEpiGroups epilogue groups (TMEM lane quarter = warp % 4)
 // that drain tiles round-robin, so the latency chain of one tile's epilogue (mask/shortcut
 // loads, TMEM reads, stores) overlaps the next tile's.
 #pragma once
@@ -149,7 +150,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows are 128 bytes (64 bf16) apart,
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows are 128 bytes (64 fp16) apart,
 // 8-row groups 1024 bytes apart (SBO); the 16-byte chunks of a row are XOR-swizzled with
 // address bits [7,10).  The hardware applies the XOR to the absolute shared-memory address,
 // so advancing the start address by whole rows (a conv tap) or by 32 bytes (a K=16 step)

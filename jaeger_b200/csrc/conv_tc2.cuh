@@ -7,17 +7,19 @@
 // any epilogue LSU traffic (row-strided 16-byte stores, parameter loads) stalls the tensor
 // pipe (117 instead of 64 cycles per MMA).  In the pair each CTA feeds its own 128 rows of A but
 // only HALF of the weights (B is split along N), i.e. 6 KB per MMA, the weights shrink to 80 KB
-// per CTA, and the freed shared memory holds an output staging tile so the stores become two
-// 16 KB bulk copies per tile instead of 2048 strided sector writes.
+// per CTA, and the freed shared memory holds output staging rows so the stores become 4 KB bulk
+// copies per warp instead of row-strided sector writes.
 //
 // Per CTA (rank r of the pair, rows (2*pt + r)*128 .. +128 of pair-tile pt):
 //   warp 0  producer: bulk-TMA loads of its own halo'd A stage
 //   warp 1  MMA issuer (leader CTA only): tcgen05.mma.cta_group::2, M=256 x N=Cout x K=16
-//   warp 2  TMEM allocator (cta_group::2, both CTAs)
+//   warp 2  TMEM allocator (cta_group::2, both CTAs), then the validity helper (conv_epilogue.cuh)
 //   warp 3  relay (peer CTA only): forwards "my stage landed" to the leader's FULL barriers
-//   warps 4-11  two epilogue groups draining alternate tiles of this CTA's accumulator ring
-// Barriers: FULL/EMPTY per stage, TFULL/TEMPTY per accumulator; tcgen05.commit multicasts EMPTY and
-// TFULL to both CTAs, the peer's epilogue and relay arrive remotely on the leader's barriers.
+//   warps 4..  kG epilogue groups draining alternate tiles of this CTA's accumulator ring:
+//              kG = 2 (light layers, staged bulk stores) or kG = 3 (tap / second-affine layers)
+// Barriers: FULL/EMPTY per stage, TFULL/TEMPTY per accumulator, VFULL/VEMPTY per validity slot;
+// tcgen05.commit multicasts EMPTY and TFULL to both CTAs, the peer's epilogue and relay arrive
+// remotely on the leader's barriers.
 #pragma once
 #include <type_traits>
 #include "conv_tc.cuh"
@@ -86,7 +88,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 struct SmemLayout2 {
   uint32_t w_off, stage_off, out_off, par_off, bar_off, val_off, total;
@@ -103,7 +104,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps
   L.stage_pitch = (L.stage_bytes + 1023u) & ~1023u;
   L.w_bytes = static_cast<uint32_t>(ntaps) * cin * (cout / 2) * 2;     // this CTA's half of the weights
   L.out_groups = cout / 64;
-  L.out_group_bytes = kTileM * 128;                                     // 128 rows x 64 channels bf16
+  L.out_group_bytes = kTileM * 128;                                     // 128 rows x 64 channels fp16
   L.w_off = 0;
   L.stage_off = (L.w_bytes + 1023u) & ~1023u;
   L.out_off = L.stage_off + kStages2 * L.stage_pitch;

@@ -438,7 +438,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     L.halo_l = -mn;
     L.halo_r = mx;
     if (L.halo_l > jg::kGuardRows - 8 || L.halo_r > jg::kGuardRows - 8) { delete m; return fail("conv halo exceeds guard rows"); }
-    // weights: TF layout [k][cin][cout] fp32 -> swizzled bf16 shared-memory image
+    // weights: TF layout [k][cin][cout] fp32 -> swizzled fp16 shared-memory image
     std::vector<uint16_t> img(static_cast<size_t>(k) * cin * cout);
     const float* wk = layers[l].p[LP_KERNEL];
     for (int t = 0; t < k; ++t)

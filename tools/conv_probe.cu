@@ -20,8 +20,8 @@ static inline float frand() {  // uniform [-1, 1)
   rng_state = rng_state * 1664525u + 1013904223u;
   return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
 }
-static inline uint16_t f2bf(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }   // fp16 storage
-static inline float bf2f(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+static inline uint16_t f2h(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }   // fp16 storage
+static inline float h2f(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
 
 int main(int argc, char** argv) {
   const int shape = argc > 1 ? atoi(argv[1]) : 0;
@@ -53,10 +53,10 @@ int main(int argc, char** argv) {
     hscmask[r] = in_frame_out && ((r % 89) != 7);
     if (in_frame_in)
       for (int c = 0; c < cin; ++c)
-        hx[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2bf(frand());
+        hx[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2h(frand());
     if (hscmask[r])
       for (int c = 0; c < cout; ++c)
-        hsc[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2bf(frand());
+        hsc[jg::kGuardRows * 64 + jg::act_index(r, c, plane)] = f2h(frand());
   }
   const int ktot = k * cin;
   std::vector<uint16_t> hw(static_cast<size_t>(ktot) * cout);
@@ -64,7 +64,7 @@ int main(int argc, char** argv) {
   for (int t = 0; t < k; ++t)
     for (int ci = 0; ci < cin; ++ci)
       for (int co = 0; co < cout; ++co)
-        hw[jg::w_index(t, ci, co, cin, cout)] = f2bf(frand() * wscale * 1.7f);
+        hw[jg::w_index(t, ci, co, cin, cout)] = f2h(frand() * wscale * 1.7f);
   std::vector<float> hpar(6 * cout);
   for (int c = 0; c < cout; ++c) {
     hpar[c] = 1.0f + 0.25f * frand();          // scale1
@@ -159,7 +159,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(yt.data(), dy_tc, ybytes, cudaMemcpyDeviceToHost));
   double maxdiff = 0, maxref = 0; size_t nbad = 0;
   for (size_t i = 0; i < yr.size(); ++i) {
-    const double a = bf2f(yr[i]), b = bf2f(yt[i]);
+    const double a = h2f(yr[i]), b = h2f(yt[i]);
     const double d = fabs(a - b);
     if (d > maxdiff) maxdiff = d;
     if (fabs(a) > maxref) maxref = fabs(a);
