@@ -251,29 +251,46 @@ int fasta_walk(const char* path, FastaScan* scan, uint8_t* bases, int64_t* offse
   int64_t rec = -1, nb = 0, nn = 0;
   bool in_header = false, header_name_done = false, at_line_start = true;
   int got;
+  // line-wise over each chunk: memchr finds the line end, sequence lines are block-copied (the
+  // per-character path only runs for lines that contain blanks)
   while ((got = gzread(fh, buf.data(), static_cast<unsigned>(buf.size()))) > 0) {
-    for (int i = 0; i < got; ++i) {
-      const char c = buf[i];
-      if (at_line_start && c == '>') {
+    const char* p = buf.data();
+    const char* end = p + got;
+    while (p < end) {
+      if (at_line_start && *p == '>') {
         ++rec;
         if (offsets) offsets[rec] = nb;
         in_header = true; header_name_done = false; at_line_start = false;
+        ++p;
         continue;
       }
-      if (c == '\n') {
+      const char* nl = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(end - p)));
+      const char* seg_end = nl ? nl : end;
+      if (in_header) {
+        for (const char* q = p; q < seg_end && !header_name_done; ++q) {
+          if (*q == ' ' || *q == '\t' || *q == '\r') header_name_done = true;
+          else { if (names) names[nn] = *q; ++nn; }
+        }
+      } else if (rec >= 0 && seg_end > p) {
+        const char* last = seg_end;
+        if (nl && last[-1] == '\r') --last;                       // CRLF line end
+        const size_t len = static_cast<size_t>(last - p);
+        const bool blanks = std::memchr(p, ' ', len) || std::memchr(p, '\t', len) || std::memchr(p, '\r', len);
+        if (!blanks) {
+          if (bases) std::memcpy(bases + nb, p, len);
+          nb += static_cast<int64_t>(len);
+        } else {
+          for (const char* q = p; q < last; ++q)
+            if (*q != ' ' && *q != '\t' && *q != '\r') { if (bases) bases[nb] = static_cast<uint8_t>(*q); ++nb; }
+        }
+      }
+      if (seg_end > p) at_line_start = false;
+      if (nl) {
         if (in_header) { if (names) names[nn] = 0; ++nn; in_header = false; }
         at_line_start = true;
-        continue;
-      }
-      at_line_start = false;
-      if (in_header) {
-        if (!header_name_done) {
-          if (c == ' ' || c == '\t' || c == '\r') header_name_done = true;
-          else { if (names) names[nn] = c; ++nn; }
-        }
-      } else if (rec >= 0 && c != '\r' && c != ' ' && c != '\t') {
-        if (bases) bases[nb] = static_cast<uint8_t>(c);
-        ++nb;
+        p = nl + 1;
+      } else {
+        p = end;
       }
     }
   }

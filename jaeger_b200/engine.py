@@ -84,6 +84,8 @@ class WindowSource:
     batch: int = 96                      # only shapes the short pass' padded batches
     dustmask: bool = False               # symmetric DUST soft-masking on the device (reference default: on)
     softmasks: dict[str, np.ndarray] | None = None   # explicit per-contig bool arrays (overrides dustmask)
+    outputs: tuple[str, ...] | None = None   # model outputs to bring back (None = all: prediction, reliability, embedding, nmd)
+    lazy_meta: bool = False              # build the meta_0..9 byte-string arrays only when they are read
 
     def load(self) -> tuple[list[str], torch.Tensor, np.ndarray]:
         """(names, bases in one pinned host buffer, record offsets); read once and kept."""
@@ -103,6 +105,31 @@ class WindowSource:
             hv[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
         self._loaded = [n for n, _ in recs], host[:int(offsets[-1])], offsets
         return self._loaded
+
+
+class PredictResult(dict):
+    """The dict `engine.predict` returns.  With lazy meta the ten `meta_i` byte-string arrays of the
+    reference protocol (encode.py:304-316) are built from the numeric window table on first access."""
+    window_table = None
+
+    def _build(self, key):
+        t = self.window_table
+        i = int(key[5:])
+        if i == 0:
+            return np.array([n.encode() for n in t.headers], dtype="S")[t.contig]
+        if i == 9:
+            idx = np.where(t.skew100 == (1 << 14), 201, t.skew100.astype(np.int32) + 100)
+            return _SKEW_STR[idx]
+        src = {1: t.start, 2: t.is_last.astype(np.int32), 3: t.ordinal, 4: t.seqlen}.get(i)
+        if src is None:
+            src = t.counts[:, i - 5]
+        return src.astype("S")
+
+    def __missing__(self, key):
+        if self.window_table is not None and isinstance(key, str) and key.startswith("meta_") and key[5:].isdigit() and int(key[5:]) < 10:
+            self[key] = v = self._build(key)
+            return v
+        raise KeyError(key)
 
 
 @dataclass
@@ -454,7 +481,8 @@ class B200Engine:
                 out["_counts"], out["_skew"] = counts, skew
                 results.append(out)
                 tables.append((contig, start, nb, ordinal, last))
-            host_out = [{k: v.cpu() for k, v in r.items()} for r in results]
+            keep = None if src.outputs is None else set(src.outputs)
+            host_out = [{k: v.cpu() for k, v in r.items() if keep is None or k in keep or k.startswith("_")} for r in results]
         self.ctx.sync()
         if not host_out:
             return {}
@@ -468,14 +496,9 @@ class B200Engine:
         self.windows = WindowTable(headers=names, contig=contig, start=start, nbases=nb, ordinal=ordinal,
                                    is_last=last, seqlen=lens[contig], counts=counts, skew100=skew)
         # meta_0..meta_9 exactly as process_string_inference forwards them (encode.py:304-316)
-        name_arr = np.array([n.encode() for n in names], dtype="S")
-        y["meta_0"] = name_arr[contig]
-        y["meta_1"] = start.astype("S")
-        y["meta_2"] = last.astype(np.int32).astype("S")
-        y["meta_3"] = ordinal.astype("S")
-        y["meta_4"] = lens[contig].astype("S")
-        for i in range(4):
-            y[f"meta_{5 + i}"] = counts[:, i].astype("S")
-        idx = np.where(skew == (1 << 14), 201, skew.astype(np.int32) + 100)
-        y["meta_9"] = _SKEW_STR[idx]
-        return y
+        res = PredictResult(y)
+        res.window_table = self.windows
+        if not src.lazy_meta:
+            for i in range(10):
+                res[f"meta_{i}"]
+        return res

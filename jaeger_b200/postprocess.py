@@ -82,6 +82,22 @@ def build_transition_costs(class_names, switch_cost: float, prior: str = "biolog
     return float(switch_cost) * p
 
 
+def _window_numbers(y_pred) -> dict[str, np.ndarray]:
+    """Per-window numbers the tables need.  Taken from the engine's numeric window table when the
+    result carries one (no round trip through the meta byte strings), else parsed from meta_0..9."""
+    t = getattr(y_pred, "window_table", None)
+    if t is not None and t.contig is not None:
+        names = np.array(t.headers, dtype=str)
+        skew = np.where(t.skew100 == (1 << 14), 0, t.skew100).astype(float) / 100.0
+        return {"is_last": t.is_last, "headers": names[t.contig], "seqlen": t.seqlen.astype(np.int32),
+                "g": t.counts[:, 0].astype(float), "c": t.counts[:, 1].astype(float), "a": t.counts[:, 2].astype(float),
+                "t": t.counts[:, 3].astype(float), "gc_skew": skew}
+    return {"is_last": np.asarray(y_pred["meta_2"]), "headers": np.array(y_pred["meta_0"], dtype=str),
+            "seqlen": np.array(y_pred["meta_4"], dtype=np.int32),
+            **{k: np.asarray(y_pred[m]).astype(float) for k, m in (("g", "meta_5"), ("c", "meta_6"), ("a", "meta_7"), ("t", "meta_8"))},
+            "gc_skew": np.asarray(y_pred["meta_9"]).astype(float)}
+
+
 def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats=None, crf_switch_cost: float | None = None,
                  crf_prior: str = "biological", crf_transition_matrix: dict | None = None) -> dict[str, Any]:
     """The `data` dict of the reference's pred_to_dict (softmax classifier), with the numeric
@@ -91,7 +107,8 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
     n_cls = pred.shape[1]
     if n_cls < 2:
         raise NotImplementedError("binary (single-logit) classifiers are not on the supported path")
-    offsets = _split_points(y_pred["meta_2"])
+    wn = _window_numbers(y_pred)
+    offsets = _split_points(wn["is_last"])
     rel = y_pred.get("reliability")
     with torch.cuda.stream(engine._stream()):
         pred_dev, off_dev = engine._h2d(pred), engine._h2d(offsets)
@@ -105,9 +122,9 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
     engine.ctx.sync()
     first = offsets[:-1]
     n_win = np.diff(offsets)
-    headers = np.array(y_pred["meta_0"], dtype=str)[first]
-    lengths = np.array(y_pred["meta_4"], dtype=np.int32)[first]
-    g, c, a, t = (np.asarray(y_pred[k]).astype(float) for k in ("meta_5", "meta_6", "meta_7", "meta_8"))
+    headers = wn["headers"][first]
+    lengths = wn["seqlen"][first]
+    g, c, a, t = wn["g"], wn["c"], wn["a"], wn["t"]
     ns = (fsize - (a + t + g + c)) / fsize                       # collect.py:319-324
     gcs = (g + c) / fsize
     pred_sum, pred_var, consensus = agg["pred_sum"], agg["pred_var"], agg["consensus"].astype(np.int64)
@@ -123,7 +140,7 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
         "prophage_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 0),
         "repeats": term_repeats,
         "gc_mean": np.add.reduceat(gcs, first) / n_win, "ns_mean": np.add.reduceat(ns, first) / n_win,
-        "predictions": pred, "gc_skews": np.asarray(y_pred["meta_9"]).astype(float), "gcs": gcs,
+        "predictions": pred, "gc_skews": wn["gc_skew"], "gcs": gcs,
     }
 
 
@@ -187,7 +204,8 @@ def contig_table_legacy(engine, y_pred: dict[str, np.ndarray], fsize: int, ood_p
     """pred_to_dict_legacy (collect.py:21-96): the modern per-contig reductions plus the
     embedding-based reliability of every window and its per-contig mean, all on the device."""
     pred = np.ascontiguousarray(y_pred["prediction"], dtype=np.float32)
-    offsets = _split_points(y_pred["meta_2"])
+    wn = _window_numbers(y_pred)
+    offsets = _split_points(wn["is_last"])
     with torch.cuda.stream(engine._stream()):
         pred_dev, off_dev = engine._h2d(pred), engine._h2d(offsets)
         agg = engine.aggregate(pred_dev, None, off_dev)
@@ -198,19 +216,19 @@ def contig_table_legacy(engine, y_pred: dict[str, np.ndarray], fsize: int, ood_p
         agg = {k: v.cpu().numpy() for k, v in agg.items()}
     engine.ctx.sync()
     first, n_win = offsets[:-1], np.diff(offsets)
-    g, c, a, t = (np.asarray(y_pred[k]).astype(float) for k in ("meta_5", "meta_6", "meta_7", "meta_8"))
+    g, c, a, t = wn["g"], wn["c"], wn["a"], wn["t"]
     ns = (fsize - (a + t + g + c)) / fsize
     gcs = (g + c) / fsize
     pred_sum, pred_var, consensus = agg["pred_sum"], agg["pred_var"], agg["consensus"].astype(np.int64)
     return {
-        "headers": np.array(y_pred["meta_0"], dtype=str)[first], "length": np.array(y_pred["meta_4"], dtype=np.int32)[first],
+        "headers": wn["headers"][first], "length": wn["seqlen"][first],
         "consensus": consensus, "per_class_counts": agg["per_class_counts"], "pred_sum": pred_sum, "pred_var": pred_var,
         "frag_pred": agg["frag_pred"], "offsets": offsets, "ood_windows": rel[0] if rel else None,
         "reliability_score": rel[1] if rel else None, "has_reliability": rel is not None, "entropy": agg["entropy"],
         "host_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 1),
         "prophage_contam": (pred_sum[:, 1] < pred_var[:, 1]) & (consensus == 0),
         "repeats": term_repeats, "gc_mean": np.add.reduceat(gcs, first) / n_win, "ns_mean": np.add.reduceat(ns, first) / n_win,
-        "predictions": pred, "gc_skews": np.asarray(y_pred["meta_9"]).astype(float), "gcs": gcs,
+        "predictions": pred, "gc_skews": wn["gc_skew"], "gcs": gcs,
     }
 
 

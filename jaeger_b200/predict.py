@@ -79,7 +79,8 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
     src = WindowSource(fasta=input_path, fsize=fsize, stride=stride, min_len=None,
                        dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
                        dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
-                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)))
+                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)),
+                       outputs=("prediction", "embedding"), lazy_meta=True)
     rec_off = src.load()[2]
     if not (np.diff(rec_off) >= min_len).any():
         raise ValueError(f"all records in {input_path} are < {min_len}bp")
@@ -139,9 +140,12 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     src = WindowSource(fasta=input_path, fsize=fsize, stride=stride, min_len=min_len,
                        dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
                        dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
-                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)))   # cli.py: --dustmask default on
+                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)),    # cli.py: --dustmask default on
+                       outputs=("prediction", "reliability"), lazy_meta=True)       # the tables need neither embeddings nor meta strings
+    t_load = time.time()
     rec_off = src.load()[2]
     n_records = len(rec_off) - 1
+    logger.info(f"read {n_records} records, {int(rec_off[-1])} bases in {time.time() - t_load:.2f} s")
     if not (np.diff(rec_off) >= (min_len or fsize)).any():
         raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
     mine = np.arange(n_records)
@@ -151,8 +155,10 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         eff = np.where((lens < fsize) & (lens >= (min_len or fsize)), fsize, lens)
         mine = shard_contigs(eff, world, fsize, stride)[rank]
         src._loaded = shard_loaded(src.load(), mine)
+    t_pred = time.time()
     y_pred = engine.predict(src)
     t1 = time.time()
+    logger.info(f"classified {int(y_pred['prediction'].shape[0]) if y_pred else 0} windows in {t1 - t_pred:.2f} s")
     crf_cost, crf_matrix = None, kwargs.get("crf_transition_matrix")          # predict.py:288-307
     if kwargs.get("crf"):
         logger.warning("CRF window decoding is experimental; results may change between releases")
@@ -162,7 +168,10 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     term = None
     if kwargs.get("terminal_repeats", True):                                  # predict.py:679-685 (always on in the reference)
         from .termini import scan_source
+        t_term = time.time()
         term = scan_source(engine, src, fsize)
+        logger.info(f"terminal-repeat scan in {time.time() - t_term:.2f} s")
+    t_post = time.time()
     data = contig_table(engine, y_pred, fsize, term_repeats=term, crf_switch_cost=crf_cost,
                         crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix) if y_pred else None
     cm = engine.class_map
@@ -196,6 +205,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                              reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
     result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
               "windows": n_windows, "predict_seconds": t1 - t0}
+    logger.info(f"aggregation + tables in {time.time() - t_post:.2f} s")
     logger.info(f"processed {n_written}/{n_records} sequences")
     if kwargs.get("prophage"):
         rows = ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
