@@ -31,6 +31,24 @@ def scan_lengths(lens: np.ndarray) -> np.ndarray:
     return np.minimum(np.maximum((lens.astype(np.float64) * 0.04).astype(np.int64), 400), 4000)
 
 
+def summary_fields(alig_len: int, f_gaps: int, rc_gaps: int, iden: int, score: int, end_query: int, end_ref: int,
+                   seq_len: int, input_length: int, type_: str) -> dict[str, Any]:
+    """get_alignment_summary (termini.py:17-88) from the traceback counts instead of the strings
+    (identity = safe_divide, utils/misc.py:117-123: rounded to 2 decimals)."""
+    s_start, s_end = (end_query - alig_len + f_gaps) + 1, end_query + 1                 # termini.py:49-50
+    if type_ == "ITR":
+        e_start = (seq_len - input_length) + max(input_length - end_ref, 0)             # termini.py:53-56
+        e_end = e_start + (alig_len - rc_gaps)
+    else:
+        e_start = (seq_len - input_length) + max(end_ref - alig_len, 0)                 # termini.py:59-62
+        e_end = (seq_len - input_length) + end_ref
+        if (s_end - s_start) >= 250:
+            type_ = f"LTR_{type_}"
+    return {"repeat_length": alig_len, "identities": iden, "identity": round(iden / alig_len, 2) if alig_len else 0, "score": score,
+            "terminal_repeats": type_, "fgaps": f_gaps, "rgaps": rc_gaps, "sstart": s_start, "send": s_end, "estart": e_start,
+            "eend": e_end, "seq_len": seq_len}
+
+
 def _threads_for(n: int) -> int:
     return max(32, ((n + 15) // 16 + 31) // 32 * 32)
 
@@ -76,22 +94,8 @@ def scan_terminal_repeats(engine, codes: torch.Tensor, valid: torch.Tensor, offs
             rows.append({"contig_id": header, **{k: None for k in COLUMNS[1:]}, "seq_len": seq_len})
             continue
         alig_len, f_gaps, rc_gaps, iden = (int(x) for x in counts[c])
-        score, end_q, end_r = int(win[c, 0]), int(win[c, 1]), int(win[c, 2])
-        s_start, s_end = (end_q - alig_len + f_gaps) + 1, end_q + 1                     # termini.py:49-50
-        if use_itr[c]:
-            type_ = "ITR"
-            e_start = (seq_len - nn) + max(nn - end_r, 0)                               # termini.py:53-56
-            e_end = e_start + (alig_len - rc_gaps)
-        else:
-            type_ = "DTR"
-            e_start = (seq_len - nn) + max(end_r - alig_len, 0)                         # termini.py:59-62
-            e_end = (seq_len - nn) + end_r
-            if (s_end - s_start) >= 250:
-                type_ = "LTR_DTR"
-        rows.append({"contig_id": header, "repeat_length": alig_len, "identities": iden,
-                     "identity": (iden / alig_len) if alig_len else 0, "score": score, "terminal_repeats": type_, "fgaps": f_gaps,
-                     "rgaps": rc_gaps, "sstart": s_start, "send": s_end, "estart": e_start, "eend": e_end, "seq_len": seq_len,
-                     "front": None, "rear": None})
+        rows.append({"contig_id": header, **summary_fields(alig_len, f_gaps, rc_gaps, iden, int(win[c, 0]), int(win[c, 1]), int(win[c, 2]),
+                                                            seq_len, nn, "ITR" if use_itr[c] else "DTR"), "front": None, "rear": None})
     return pd.DataFrame(rows, columns=COLUMNS)
 
 

@@ -103,7 +103,7 @@ def alignment_summary(res: dict, seq_len: int, record_id: str, input_length: int
         if (s_end - s_start) >= 250:
             type_ = f"LTR_{type_}"
     return {"contig_id": record_id, "repeat_length": alig_len, "identities": res["iden"],
-            "identity": (res["iden"] / alig_len) if alig_len else 0, "score": res["score"], "terminal_repeats": type_,
+            "identity": round(res["iden"] / alig_len, 2) if alig_len else 0, "score": res["score"], "terminal_repeats": type_,
             "fgaps": f_gaps, "rgaps": rc_gaps, "sstart": s_start, "send": s_end, "estart": e_start, "eend": e_end, "seq_len": seq_len}
 
 

@@ -14,6 +14,7 @@ are executed:
   jaeger.postprocess.helpers.merge_overlapping_ranges, viterbi_decode, build_transition_costs
   jaeger.postprocess.collect.pred_to_dict_legacy, generate_summary_legacy; helpers.ood_predict_default
       (the bundled LR_ood_4_class_default.pkl through the installed scikit-learn)
+  jaeger.utils.termini.get_alignment_summary (on mock alignment results; parasail stubbed)
 
 usage:  python tests/golden/make_goldens.py
 """
@@ -112,6 +113,36 @@ def viterbi_goldens(rhelp, rcollect):
     out["crf_counts"] = np.array([[d[k] for k in range(6)] for d in data["per_class_counts"]])
     out["crf_frag_pred"] = np.concatenate(data["frag_pred"])
     np.savez_compressed(OUT / "viterbi.npz", **out)
+
+
+def termini_goldens():
+    """get_alignment_summary (utils/termini.py:17-88) on mock parasail results: pins the coordinate
+    arithmetic of the terminal-repeat table (parasail itself is not installable here)."""
+    _stub("parasail")
+    from jaeger.utils import termini as rterm
+    rng = np.random.default_rng(31)
+    cases = []
+    for k in range(40):
+        n = int(rng.integers(400, 4001))
+        seq_len = int(n / 0.04) + int(rng.integers(0, 5000))
+        cols = int(rng.integers(13, min(n, 900)))
+        qg, rg = (int(x) for x in rng.integers(0, 4, 2)) if k % 3 == 0 else (0, 0)
+        query = "".join(rng.choice(list("ACGT"), cols - qg)) + "-" * qg
+        ref = "".join(rng.choice(list("ACGT"), cols - rg)) + "-" * rg
+        iden = int(rng.integers(cols // 2, cols - qg - rg + 1))
+        comp = "|" * iden + "." * (cols - iden)
+        end_query = int(rng.integers(cols - qg - 1, n))
+        end_ref = int(rng.integers(cols - rg - 1, n))
+        tb = type("TB", (), {"query": query, "ref": ref, "comp": comp})()
+        res = type("R", (), {"score": 2 * iden - 100 * (cols - iden), "end_query": end_query, "end_ref": end_ref, "saturated": False,
+                             "traceback": tb})()
+        for type_ in ("DTR", "ITR"):
+            out = rterm.get_alignment_summary(res, seq_len=seq_len, record_id=f"r{k}", input_length=n, type_=type_)
+            cases.append({"inp": {"cols": cols, "qgaps": qg, "rgaps": rg, "iden": iden, "score": res.score, "end_query": end_query,
+                                  "end_ref": end_ref, "seq_len": seq_len, "n": n, "type": type_},
+                          "out": {k2: out[k2] for k2 in ("repeat_length", "identities", "identity", "score", "terminal_repeats", "fgaps",
+                                                        "rgaps", "sstart", "send", "estart", "eend", "seq_len")}})
+    (OUT / "termini_summary.json").write_text(json.dumps(cases))
 
 
 def legacy_post_goldens(rhelp, rcollect):
@@ -295,6 +326,7 @@ def main():
     (OUT / "merge_ranges.json").write_text(json.dumps(merges))
     viterbi_goldens(rhelp, rcollect)
     legacy_post_goldens(rhelp, rcollect)
+    termini_goldens()
     if "--only-post" in sys.argv:
         return
     # ---- BASELINE config 1 fixture: the bundled legacy `default` weights + the health FASTA --------

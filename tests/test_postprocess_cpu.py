@@ -73,3 +73,42 @@ def test_sdust_oracle_masks_low_complexity_only():
     # random sequence: almost nothing is low-complexity at T = 20
     assert odust.mask_bits(rnd(20000)).mean() < 0.002
     assert odust.sdust_intervals("ACG") == [] and odust.sdust_intervals("") == []
+
+
+def test_terminal_repeat_summary_arithmetic_vs_reference_golden():
+    """get_alignment_summary (utils/termini.py:17-88) on mock alignment results: the oracle's and the
+    product's coordinate arithmetic reproduce the reference for DTR / ITR / LTR, with and without gaps."""
+    from jaeger_b200.termini import summary_fields
+    from oracle import termini as ot
+    cases = json.loads((G / "termini_summary.json").read_text())
+    assert len(cases) == 80
+    for cs in cases:
+        i, want = cs["inp"], cs["out"]
+        got = summary_fields(i["cols"], i["qgaps"], i["rgaps"], i["iden"], i["score"], i["end_query"], i["end_ref"], i["seq_len"],
+                             i["n"], i["type"])
+        orc = ot.alignment_summary({"cols": i["cols"], "qgaps": i["qgaps"], "rgaps": i["rgaps"], "iden": i["iden"], "score": i["score"],
+                                    "end_query": i["end_query"], "end_ref": i["end_ref"]}, i["seq_len"], "r", i["n"], i["type"])
+        for k, v in want.items():
+            assert got[k] == v, (k, got[k], v)
+            assert orc[k] == v, (k, orc[k], v)
+    assert {c["out"]["terminal_repeats"] for c in cases} == {"DTR", "ITR", "LTR_DTR"}
+
+
+def test_terminal_repeat_oracle_known_answers():
+    """Hand-checkable alignments: exact direct / inverted repeats, one mismatch (kept: 2*119 - 100 > 2*60),
+    one deleted base (gap in the query line), nothing in random sequence."""
+    from oracle import termini as ot
+    rng = np.random.default_rng(1)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    core = rnd(120)
+    a = ot.sw_align(core + rnd(300), rnd(300) + core)
+    assert (a["score"], a["cols"], a["qgaps"], a["rgaps"], a["iden"], a["end_query"], a["end_ref"]) == (240, 120, 0, 0, 120, 119, 419)
+    mut = core[:60] + ("A" if core[60] != "A" else "C") + core[61:]
+    b = ot.sw_align(core, mut)
+    assert (b["score"], b["cols"], b["iden"]) == (2 * 119 - 100, 120, 119)
+    c = ot.sw_align(core[:58] + core[59:], core)
+    assert (c["score"], c["cols"], c["qgaps"], c["rgaps"]) == (2 * 119 - 100, 120, 1, 0)
+    d = ot.sw_align("ACGTNNNNACGT", "ACGTACGTACGT")          # letters outside ACGT score 0 against everything
+    assert d["score"] == 16 and d["cols"] == 12
+    rows = ot.scan_for_terminal_repeats([("x", core + rnd(2500) + ot.reverse_complement(core)), ("y", rnd(2600)), ("z", rnd(100))], 2000)
+    assert [r["terminal_repeats"] for r in rows] == ["ITR", None] and rows[0]["repeat_length"] == 120
