@@ -71,6 +71,7 @@ struct ConvParams {
   const int* lpad;              // [n_windows] padded frame length of every window
   int* count;                   // [n_windows] valid output rows
   int fuse_mask, masking, period, frames, shrink_in, halvings, shrink;
+  int folded;              // scale1 is folded into the weights (== 1): the specialised epilogues add shift1 only
   int* err;                     // device int, set non-zero on a barrier time-out
   long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)
 };

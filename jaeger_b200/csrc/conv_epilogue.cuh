@@ -185,6 +185,7 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
 //   EPI_LIGHT    tanh-GELU only: no NMD tap, no second affine, no pooling (conv1 / conv2 of a residual block)
 //   EPI_FINAL    shortcut + tanh-GELU + NMD tap on the block output + second affine + tanh-GELU
 //   EPI_FINAL_POOL  the same + masked global max pool (last layer)
+// The specialised modes also assume the first affine's scale is folded into the weights (p.folded).
 // The caller checks that the layer matches the mode it picks.
 enum EpiMode { EPI_GENERIC = 0, EPI_LIGHT = 1, EPI_FINAL = 2, EPI_FINAL_POOL = 3 };
 template <int kMode = EPI_GENERIC>
@@ -206,11 +207,20 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
   }
   __half2 h[16];
+  if (kGen) {
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 a = e.scale1[cb * 8 + j4], b = e.shift1[cb * 8 + j4];
-    h[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
-    h[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 a = e.scale1[cb * 8 + j4], b = e.shift1[cb * 8 + j4];
+      h[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
+      h[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
+    }
+  } else {          // specialised modes run on layers whose scale is folded into the weights
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 b = e.shift1[cb * 8 + j4];
+      h[j4 * 2 + 0] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 0]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y);
+      h[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
+    }
   }
   if (kFinal || has_sc) {
 #pragma unroll

@@ -76,6 +76,7 @@ struct Layer {
   jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
   float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const  (6 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
+  bool folded = false;         // scale1 folded into the weights (par scale1 == 1)
   float* w_tap = nullptr;      // stem with an NMD tap on one-hot input: fp16-rounded weights [k][64][cout] + their tap sum [64][cout]
   int shifts_h[jg::kMaxTaps];
   int halo_l = 0, halo_r = 0;
@@ -214,6 +215,13 @@ int jg_ctx_create_on_stream(int device, void* stream, jg_ctx** out) {
   jg_ctx* c = new jg_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  // keep stream-ordered scratch allocations cached across synchronisations (the default pool gives
+  // memory back to the driver at every sync, and re-acquiring it stalls synchronous callers)
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
     c->owns_stream = false;
@@ -403,9 +411,8 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
   if (n_windows <= 0) return 0;
   if (pitch % 4 != 0 || pitch < lc) return fail("token pitch must be a multiple of 4 and >= lc");
   JG_CUDA(cudaSetDevice(ctx->device));
-  uint8_t* d_lut = nullptr;
-  JG_CUDA(cudaMallocAsync(&d_lut, 64, ctx->stream));
-  JG_CUDA(cudaMemcpyAsync(d_lut, h_lut64, 64, cudaMemcpyHostToDevice, ctx->stream));
+  jg::CodonLut lut;                       // 64 bytes, passed by value: no allocation or copy on the hot path
+  std::memcpy(lut.v, h_lut64, 64);
   const int words_c = (crop + 15) / 16 + 1, words_b = (crop + 31) / 32 + 1;
   const size_t smem = static_cast<size_t>(words_c + 2 * words_b) * 4;
   long long grid = n_windows;
@@ -413,10 +420,9 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
   if (grid > cap) grid = cap;
   jg::encode_windows_kernel<<<static_cast<int>(grid), jg::kEncThreads, smem, ctx->stream>>>(
       d_codes, d_valid, d_soft, reinterpret_cast<const long long*>(d_win_base), d_win_nbases, n_windows, crop,
-      lc, pitch, d_lut, case_sensitive, d_tokens, d_counts, d_skew100);
+      lc, pitch, lut, case_sensitive, d_tokens, d_counts, d_skew100);
   ctx->launches++;
   JG_CUDA(cudaGetLastError());
-  JG_CUDA(cudaFreeAsync(d_lut, ctx->stream));
   return 0;
 }
 
@@ -458,6 +464,19 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     // weights: TF layout [k][cin][cout] fp32 -> swizzled fp16 shared-memory image
     std::vector<uint16_t> img(static_cast<size_t>(k) * cin * cout);
     const float* wk = layers[l].p[LP_KERNEL];
+    // The first affine's per-channel scale (BatchNorm gamma / sigma) is folded into the fp16 weights, so
+    // the epilogue adds the shift only.  Not for a layer whose NMD tap reads the raw conv output in the
+    // epilogue (tap mode 1 without the linear stem tap): that needs the unscaled accumulator.
+    const bool linear_tap_layer = l == 0 && L.f[LF_TAP_MODE] == 1 && cin == 64;
+    L.folded = (L.f[LF_TAP_MODE] != 1 || linear_tap_layer) && layers[l].p[LP_SCALE1] != nullptr && !std::getenv("JG_NO_BN_FOLD");
+    std::vector<float> wfold;
+    if (L.folded) {
+      wfold.resize(static_cast<size_t>(k) * cin * cout);
+      const float* sc1 = layers[l].p[LP_SCALE1];
+      for (size_t i = 0; i < wfold.size(); ++i) wfold[i] = wk[i] * sc1[i % cout];
+    }
+    const float* wk_raw = wk;
+    if (L.folded) wk = wfold.data();
     for (int t = 0; t < k; ++t)
       for (int ci = 0; ci < cin; ++ci)
         for (int co = 0; co < cout; ++co)
@@ -470,12 +489,12 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
           img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
     JG_CUDA(cudaMalloc(&L.w2, img.size() * 2));
     JG_CUDA(cudaMemcpy(L.w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    if (l == 0 && L.f[LF_TAP_MODE] == 1 && cin == 64) {   // linear stem tap (stem_tap_kernel)
+    if (linear_tap_layer) {   // linear stem tap (stem_tap_kernel): the raw conv output from the unscaled fp32 weights
       std::vector<float> wt(static_cast<size_t>(k + 1) * 64 * cout, 0.0f);
       for (int t = 0; t < k; ++t)
         for (int ci = 0; ci < 64; ++ci)
           for (int co = 0; co < cout; ++co) {
-            const float v = __half2float(__float2half_rn(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]));
+            const float v = wk_raw[(static_cast<size_t>(t) * cin + ci) * cout + co];
             wt[(static_cast<size_t>(t) * 64 + ci) * cout + co] = v;
             wt[(static_cast<size_t>(k) * 64 + ci) * cout + co] += v;
           }
@@ -488,6 +507,8 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
       const float* src = layers[l].p[order[a]];
       for (int c = 0; c < cout; ++c) par[a * cout + c] = src ? src[c] : ((order[a] == LP_SCALE1 || order[a] == LP_SCALE2) ? 1.0f : 0.0f);
     }
+    if (L.folded)
+      for (int c = 0; c < cout; ++c) par[1 * cout + c] = 1.0f;        // scale1 now lives in the weights
     if (upload_f32(par.data(), par.size(), &L.par)) { delete m; return 2; }
     JG_CUDA(cudaMalloc(&L.shifts, sizeof(int) * jg::kMaxTaps));
     JG_CUDA(cudaMemcpy(L.shifts, L.shifts_h, sizeof(int) * k, cudaMemcpyHostToDevice));
@@ -678,10 +699,11 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.tap_mode = L.f[LF_TAP_MODE];
     // The stem's tap is linear in its one-hot input: it is taken from token counts after the conv
     // (stem_tap_kernel), which leaves the stem a light layer for the CTA-pair kernel.
-    const bool linear_tap = !use_ref && L.w_tap != nullptr && L.f[LF_SHRINK] >= 0 && L.f[LF_CUM_SHRINK_IN] == 0 && L.f[LF_HALVINGS] == 0;
+    const bool linear_tap = L.w_tap != nullptr && L.f[LF_SHRINK] >= 0 && L.f[LF_CUM_SHRINK_IN] == 0 && L.f[LF_HALVINGS] == 0;
     if (linear_tap) { p.tap_mode = 0; p.tap_sum = nullptr; }
     p.pool_mode = L.f[LF_POOL_MODE];
     p.fuse_mask = layer_ref ? 0 : 1;
+    p.folded = L.folded ? 1 : 0;
     p.in_mask = mask_row0(L.f[LF_MASK_IN]);
     p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
     p.lpad = d_lpad;

@@ -79,6 +79,7 @@ __device__ __forceinline__ int round_hundredths(int num, int den) {
 }
 
 constexpr int kEncThreads = 128;
+struct CodonLut { uint8_t v[64]; };   // codon (first<<4 | second<<2 | third, 2-bit codes) -> token
 
 // One CTA per window.  Shared memory holds the window's packed codes / validity / soft-mask
 // re-based to bit 0, so every codon is three 2-bit extracts.
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kEncThreads)
 encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid,
                       const uint32_t* __restrict__ soft, const long long* __restrict__ win_base,
                       const int* __restrict__ win_nbases, long long n_windows, int crop, int lc,
-                      int pitch, const uint8_t* __restrict__ lut64, int case_sensitive,
+                      int pitch, const CodonLut lut64, int case_sensitive,
                       uint8_t* __restrict__ tokens, int* __restrict__ counts,
                       short* __restrict__ skew100) {
   extern __shared__ uint32_t s_mem[];
@@ -100,8 +101,8 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
   __shared__ int s_cnt[4];
   if (threadIdx.x < 64) {
     const uint32_t i = threadIdx.x;
-    s_lut[i] = lut64[i];
-    s_lut_fwd[i] = lut64[((i & 3u) << 4) | (i & 12u) | (i >> 4)];
+    s_lut[i] = lut64.v[i];
+    s_lut_fwd[i] = lut64.v[((i & 3u) << 4) | (i & 12u) | (i >> 4)];
   }
 
   for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {

@@ -67,7 +67,7 @@ int main(int argc, char** argv) {
         hw[jg::w_index(t, ci, co, cin, cout)] = f2h(frand() * wscale * 1.7f);
   std::vector<float> hpar(6 * cout);
   for (int c = 0; c < cout; ++c) {
-    hpar[c] = 1.0f + 0.25f * frand();          // scale1
+    hpar[c] = getenv("JG_PROBE_FOLDED") ? 1.0f : 1.0f + 0.25f * frand();          // scale1
     hpar[cout + c] = 0.1f * frand();           // shift1
     hpar[2 * cout + c] = 1.0f + 0.25f * frand();
     hpar[3 * cout + c] = 0.1f * frand();
@@ -131,6 +131,7 @@ int main(int argc, char** argv) {
   if (strip & 4) { p.sc = nullptr; p.sc_mask = nullptr; }
   if (strip & 16) { p.has_affine2 = 0; p.act2 = jg::ACT_NONE; }
   p.err = derr;
+  p.folded = getenv("JG_PROBE_FOLDED") ? 1 : 0;   // with it, scale1 must be 1 (set below) and the specialised epilogues run
   (void)variant;
 
   int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
