@@ -350,7 +350,7 @@ def run_b200(args):
             "roofline": roofline,
             "e2e": {"value": tot_bases / 1e6 / (e2e_ms / 1e3), "unit": "Mbp/s",
                     "h2d_bytes_per_step": int(target + n_windows / args.steps * 12), "d2h_bytes_per_step": int(d2h_bytes),
-                    "sm_mhz": clocks_e2e.get("sm_mhz"), "sm_min_mhz": clocks_e2e.get("sm_min_mhz")},
+                    **({"sm_mhz": clocks_e2e.get("sm_mhz"), "sm_min_mhz": clocks_e2e.get("sm_min_mhz")} if clocks_e2e else {})},
             "gpu_launches": int(launches), "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(eng.spec, eng.weights, args.cpu_baseline_seconds)
