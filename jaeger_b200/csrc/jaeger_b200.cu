@@ -414,8 +414,8 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
   jg::CodonLut lut;                       // 64 bytes, passed by value: no allocation or copy on the hot path
   std::memcpy(lut.v, h_lut64, 64);
   const int words_c = (crop + 15) / 16 + 1, words_b = (crop + 31) / 32 + 1;
-  const size_t smem = static_cast<size_t>(words_c + 2 * words_b) * 4;
-  long long grid = n_windows;
+  const size_t smem = static_cast<size_t>(words_c + 2 * words_b) * 4 * jg::kEncWarps;
+  long long grid = (n_windows + jg::kEncWarps - 1) / jg::kEncWarps;
   const long long cap = static_cast<long long>(ctx->num_sms) * 16;
   if (grid > cap) grid = cap;
   jg::encode_windows_kernel<<<static_cast<int>(grid), jg::kEncThreads, smem, ctx->stream>>>(

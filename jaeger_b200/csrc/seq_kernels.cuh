@@ -81,8 +81,11 @@ __device__ __forceinline__ int round_hundredths(int num, int den) {
 constexpr int kEncThreads = 128;
 struct CodonLut { uint8_t v[64]; };   // codon (first<<4 | second<<2 | third, 2-bit codes) -> token
 
-// One CTA per window.  Shared memory holds the window's packed codes / validity / soft-mask
-// re-based to bit 0, so every codon is three 2-bit extracts.
+// One WARP per window (four windows in flight per CTA, no block-wide barrier): the warp's slice of
+// shared memory holds the window's packed codes / validity / soft-mask re-based to bit 0, so a
+// codon is one funnel shift.  Tokens leave as 32-bit words, the lanes of a warp writing consecutive
+// words of a frame.
+constexpr int kEncWarps = kEncThreads / 32;
 __global__ void __launch_bounds__(kEncThreads)
 encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid,
                       const uint32_t* __restrict__ soft, const long long* __restrict__ win_base,
@@ -93,33 +96,37 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
   extern __shared__ uint32_t s_mem[];
   const int words_c = (crop + 15) / 16 + 1;
   const int words_b = (crop + 31) / 32 + 1;
-  uint32_t* s_codes = s_mem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* s_codes = s_mem + warp * (words_c + 2 * words_b);
   uint32_t* s_valid = s_codes + words_c;   // valid for tokens (soft-masked removed if case_sensitive)
   uint32_t* s_count = s_valid + words_b;   // valid & ~soft (what the G/C/A/T counts see)
   __shared__ uint8_t s_lut[64];       // index = (first base << 4) | (second << 2) | third
   __shared__ uint8_t s_lut_fwd[64];   // index = first | (second << 2) | (third << 4)
-  __shared__ int s_cnt[4];
   if (threadIdx.x < 64) {
     const uint32_t i = threadIdx.x;
     s_lut[i] = lut64.v[i];
     s_lut_fwd[i] = lut64.v[((i & 3u) << 4) | (i & 12u) | (i >> 4)];
   }
+  __syncthreads();
+  // encode.py:232-236: the slice offset comes from crop % 3, not from the true length.
+  const int off = (crop % 3 == 0) ? -2 : (crop % 3 == 1 ? -1 : 0);
+  const int words_per_frame = pitch / 4;       // pitch is a multiple of 4: word-wide stores
 
-  for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+  for (long long w = static_cast<long long>(blockIdx.x) * kEncWarps + warp; w < n_windows;
+       w += static_cast<long long>(gridDim.x) * kEncWarps) {
     const long long base = win_base[w];
     int n = win_nbases[w];
     if (n > crop) n = crop;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     // re-based copies: code word j holds bases [16j, 16j+16) of the window
     const int sh_c = static_cast<int>(base & 15) * 2;
     const long long w0_c = base >> 4;
-    for (int j = threadIdx.x; j < words_c; j += kEncThreads) {
+    for (int j = lane; j < words_c; j += 32) {
       const uint32_t a = codes[w0_c + j], b = codes[w0_c + j + 1];
       s_codes[j] = sh_c ? ((a >> sh_c) | (b << (32 - sh_c))) : a;
     }
     const int sh_b = static_cast<int>(base & 31);
     const long long w0_b = base >> 5;
-    for (int j = threadIdx.x; j < words_b; j += kEncThreads) {
+    for (int j = lane; j < words_b; j += 32) {
       const uint32_t a = valid[w0_b + j], b = valid[w0_b + j + 1];
       uint32_t v = sh_b ? ((a >> sh_b) | (b << (32 - sh_b))) : a;
       uint32_t sm = 0;
@@ -129,86 +136,77 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
       }
       // clip to the window length
       const int first = j * 32;
-      uint32_t keep = (first + 32 <= n) ? 0xFFFFFFFFu : (first >= n ? 0u : ((1u << (n - first)) - 1u));
+      const uint32_t keep = (first + 32 <= n) ? 0xFFFFFFFFu : (first >= n ? 0u : ((1u << (n - first)) - 1u));
       v &= keep;
       s_count[j] = v & ~sm;
       s_valid[j] = case_sensitive ? (v & ~sm) : v;
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- base counts (upper-case, un-masked A/C/G/T) ------------------------------------
-    {
-      int cg = 0, cc = 0, ca = 0, ct = 0;
-      for (int j = threadIdx.x; j * 16 < n; j += kEncThreads) {
-        const uint32_t cw = s_codes[j];
-        const uint32_t vb = (s_count[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-        // spread the 16 validity bits to the low bit of each 2-bit lane
-        uint32_t m = vb;
-        m = (m | (m << 8)) & 0x00FF00FFu;
-        m = (m | (m << 4)) & 0x0F0F0F0Fu;
-        m = (m | (m << 2)) & 0x33333333u;
-        m = (m | (m << 1)) & 0x55555555u;
-        const uint32_t lo = cw & 0x55555555u, hi = (cw >> 1) & 0x55555555u;
-        ca += __popc(m & ~lo & ~hi);  // 00
-        cc += __popc(m & lo & ~hi);   // 01
-        ct += __popc(m & ~lo & hi);   // 10
-        cg += __popc(m & lo & hi);    // 11
-      }
+    int cg = 0, cc = 0, ca = 0, ct = 0;
+    for (int j = lane; j * 16 < n; j += 32) {
+      const uint32_t cw = s_codes[j];
+      const uint32_t vb = (s_count[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+      // spread the 16 validity bits to the low bit of each 2-bit lane
+      uint32_t m = vb;
+      m = (m | (m << 8)) & 0x00FF00FFu;
+      m = (m | (m << 4)) & 0x0F0F0F0Fu;
+      m = (m | (m << 2)) & 0x33333333u;
+      m = (m | (m << 1)) & 0x55555555u;
+      const uint32_t lo = cw & 0x55555555u, hi = (cw >> 1) & 0x55555555u;
+      ca += __popc(m & ~lo & ~hi);  // 00
+      cc += __popc(m & lo & ~hi);   // 01
+      ct += __popc(m & ~lo & hi);   // 10
+      cg += __popc(m & lo & hi);    // 11
+    }
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        cg += __shfl_xor_sync(0xffffffffu, cg, off);
-        cc += __shfl_xor_sync(0xffffffffu, cc, off);
-        ca += __shfl_xor_sync(0xffffffffu, ca, off);
-        ct += __shfl_xor_sync(0xffffffffu, ct, off);
-      }
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_cnt[0], cg); atomicAdd(&s_cnt[1], cc);
-        atomicAdd(&s_cnt[2], ca); atomicAdd(&s_cnt[3], ct);
-      }
+    for (int o = 16; o >= 1; o >>= 1) {
+      cg += __shfl_xor_sync(0xffffffffu, cg, o);
+      cc += __shfl_xor_sync(0xffffffffu, cc, o);
+      ca += __shfl_xor_sync(0xffffffffu, ca, o);
+      ct += __shfl_xor_sync(0xffffffffu, ct, o);
     }
 
     // ---- tokens: frames f1,f2,f3 (forward) r1,r2,r3 (reverse complement) ------------------
-    // encode.py:232-236: the slice offset comes from crop % 3, not from the true length.
-    const int off = (crop % 3 == 0) ? -2 : (crop % 3 == 1 ? -1 : 0);
     int nc = (n - 5 + off + 2) / 3;          // ceil((n - 5 + off) / 3)
     if (n - 5 + off <= 0) nc = 0;
     if (nc > lc) nc = lc;
-    uint8_t* out = tokens + w * 6ll * pitch;   // pitch is a multiple of 4: word-wide stores
-    const int words_per_frame = pitch / 4;
-    for (int idx = threadIdx.x; idx < 6 * words_per_frame; idx += kEncThreads) {
-      const int f = idx / words_per_frame;
-      const int j0 = (idx - f * words_per_frame) * 4;
-      uint32_t packed = 0;
+    uint8_t* out = tokens + w * 6ll * pitch;
+    for (int f = 0; f < 6; ++f) {
+      uint8_t* frame = out + static_cast<long long>(f) * pitch;
+      for (int wd = lane; wd < words_per_frame; wd += 32) {
+        const int j0 = wd * 4;
+        uint32_t packed = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = j0 + e;
-        uint32_t tok = 0;
-        if (j < nc) {
-          // a codon is 6 contiguous bits of the packed stream starting at its lowest base:
-          // forward frames read them first-base-lowest (the LUT copy with the base order reversed),
-          // reverse frames first-base-highest, complemented by xor 0b101010
-          const int lowest = (f < 3) ? f + 3 * j : n - 3 - (f - 3) - 3 * j;
-          const int cb = 2 * lowest, cw = cb >> 5;
-          const uint32_t six = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31) & 63u;
-          const int vw = lowest >> 5;
-          const uint32_t ok3 = __funnelshift_r(s_valid[vw], s_valid[vw + 1], lowest & 31) & 7u;
-          const uint32_t t = (f < 3) ? s_lut_fwd[six] : s_lut[six ^ 0x2Au];
-          tok = ok3 == 7u ? t : 0u;
+        for (int e = 0; e < 4; ++e) {
+          const int j = j0 + e;
+          uint32_t tok = 0;
+          if (j < nc) {
+            // a codon is 6 contiguous bits of the packed stream starting at its lowest base:
+            // forward frames read them first-base-lowest (the LUT copy with the base order reversed),
+            // reverse frames first-base-highest, complemented by xor 0b101010
+            const int lowest = (f < 3) ? f + 3 * j : n - 3 - (f - 3) - 3 * j;
+            const int cb = 2 * lowest, cw = cb >> 5;
+            const uint32_t six = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31) & 63u;
+            const int vw = lowest >> 5;
+            const uint32_t ok3 = __funnelshift_r(s_valid[vw], s_valid[vw + 1], lowest & 31) & 7u;
+            const uint32_t t = (f < 3) ? s_lut_fwd[six] : s_lut[six ^ 0x2Au];
+            tok = ok3 == 7u ? t : 0u;
+          }
+          packed |= tok << (8 * e);
         }
-        packed |= tok << (8 * e);
+        *reinterpret_cast<uint32_t*>(frame + j0) = packed;
       }
-      *reinterpret_cast<uint32_t*>(out + static_cast<long long>(f) * pitch + j0) = packed;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int g = s_cnt[0], c = s_cnt[1];
-      counts[w * 4 + 0] = g; counts[w * 4 + 1] = c; counts[w * 4 + 2] = s_cnt[2]; counts[w * 4 + 3] = s_cnt[3];
-      const int h = round_hundredths(g - c, g + c);
+    if (lane == 0) {
+      counts[w * 4 + 0] = cg; counts[w * 4 + 1] = cc; counts[w * 4 + 2] = ca; counts[w * 4 + 3] = ct;
+      const int h = round_hundredths(cg - cc, cg + cc);
       short v = static_cast<short>(h);
-      if (h == 0 && g - c < 0 && g + c != 0) v = static_cast<short>(1 << 14);  // "-0.000"
+      if (h == 0 && cg - cc < 0 && cg + cc != 0) v = static_cast<short>(1 << 14);  // "-0.000"
       skew100[w] = v;
     }
-    __syncthreads();
+    __syncwarp();          // the slice is rewritten by the next window
   }
 }
 
