@@ -232,23 +232,48 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     }
   }
   if (kFinal || kMode == EPI_LIGHT) act_apply_h2(h, ACT_GELU_TANH); else act_apply_h2(h, p.act1);
-  if (kFinal || (kGen && p.tap_mode == 2)) {   // NMD tap on the block output
-    __half2 tv[16];
-    const __half2 zero = __float2half2_rn(0.0f);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
-  }
-  if (kFinal || (kGen && p.has_affine2)) {
+  // Rows outside the mask are rare (frame ends and the window tail): the masking selects only run
+  // in warps that contain one.
+  const bool any_masked = __any_sync(0xffffffffu, !valid);
+  if (kFinal) {
+    // second affine first (it is the last reader of h), so the tap can mask h in place
+    __half2 x3[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 a = e.scale2[cb * 4 + j], b = e.shift2[cb * 4 + j];
       const __half2* a2 = reinterpret_cast<const __half2*>(&a);
       const __half2* b2 = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) h[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
+      for (int k = 0; k < 4; ++k) x3[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
     }
-    if (kFinal) act_apply_h2(h, ACT_GELU_TANH); else act_apply_h2(h, p.act2);
+    if (any_masked) {
+      const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = valid ? h[i] : zero;
+    }
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(h, lane));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = x3[i];
+    act_apply_h2(h, ACT_GELU_TANH);
+  } else {
+    if (kGen && p.tap_mode == 2) {   // NMD tap on the block output
+      __half2 tv[16];
+      const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
+    }
+    if (kGen && p.has_affine2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = e.scale2[cb * 4 + j], b = e.shift2[cb * 4 + j];
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
+      }
+      act_apply_h2(h, p.act2);
+    }
   }
   if (kMode == EPI_FINAL_POOL || (kGen && p.pool_mode != 0)) {
     __half2 tv[16];
@@ -271,7 +296,11 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     o.y = *reinterpret_cast<const uint32_t*>(&h[j * 4 + 1]);
     o.z = *reinterpret_cast<const uint32_t*>(&h[j * 4 + 2]);
     o.w = *reinterpret_cast<const uint32_t*>(&h[j * 4 + 3]);
-    out[j] = valid ? o : make_uint4(0u, 0u, 0u, 0u);
+    out[j] = o;
+  }
+  if (any_masked) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = valid ? out[j] : make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
