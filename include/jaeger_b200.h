@@ -120,7 +120,11 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
  * nnlib/v1/layers.py:65-69, 207, 413).  tok_offset: token t feeds one-hot channel t - tok_offset
  * (1 for the v2 encoder whose token 0 is the masked unknown codon, 0 for the legacy amino-acid
  * ids).  Weights are fp32 host arrays in TensorFlow layout ([k, Cin, Cout] conv kernels,
- * [in, out] dense kernels). */
+ * [in, out] dense kernels).  A conv layer's epilogue is: conv + bias -> norm 1 -> [+ shortcut] ->
+ * activation 1 -> [NMD tap] -> [norm 2 -> activation 2] -> [masked global pool]; a norm is a
+ * per-channel affine (MaskedBatchNorm folded, nnlib/v2/layers.py:918-941) or, with i[22] / i[23] set,
+ * a MaskedDYT (layers.py:385-444): gamma * tanh(scale * x + shift) + beta with gamma / beta in
+ * p[8..11]. */
 #define JG_LAYER_INT_FIELDS 24
 #define JG_LAYER_PTR_FIELDS 12
 typedef struct jg_layer_desc {

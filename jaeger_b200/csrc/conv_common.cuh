@@ -71,6 +71,8 @@ struct ConvParams {
   const int* lpad;              // [n_windows] padded frame length of every window
   int* count;                   // [n_windows] valid output rows
   int fuse_mask, masking, period, frames, shrink_in, halvings, shrink;
+  const float *dyt_g1, *dyt_b1, *dyt_g2, *dyt_b2;   // MaskedDYT gamma / beta after the tanh (alpha rides in scale1 / scale2)
+  int dyt1, dyt2;          // the first / second norm is a MaskedDYT: y = gamma * tanh(scale * x + shift) + beta
   int folded;              // scale1 is folded into the weights (== 1): the specialised epilogues add shift1 only
   int* err;                     // device int, set non-zero on a barrier time-out
   long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)

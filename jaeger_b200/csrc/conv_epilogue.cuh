@@ -88,7 +88,12 @@ struct EpiParams {
   const uint4* scale2;    // [cout/8] 8 halves each
   const uint4* shift2;
   const uint4* scc;       // shortcut value at masked rows
+  const uint4* g1;        // MaskedDYT gamma / beta of the first and second norm (fp16, only read when p.dyt1 / p.dyt2)
+  const uint4* b1;
+  const uint4* g2;
+  const uint4* b2;
 };
+constexpr int kEpiParFloats = 10;   // shared-memory parameter block: kEpiParFloats * cout floats
 
 __device__ __forceinline__ EpiParams epi_params(float* s_par, int cout) {
   EpiParams e;
@@ -98,6 +103,10 @@ __device__ __forceinline__ EpiParams epi_params(float* s_par, int cout) {
   e.scale2 = reinterpret_cast<const uint4*>(s_par + 3 * cout);
   e.shift2 = reinterpret_cast<const uint4*>(s_par + 4 * cout);
   e.scc = reinterpret_cast<const uint4*>(s_par + 5 * cout);
+  e.g1 = reinterpret_cast<const uint4*>(s_par + 6 * cout);
+  e.b1 = reinterpret_cast<const uint4*>(s_par + 7 * cout);
+  e.g2 = reinterpret_cast<const uint4*>(s_par + 8 * cout);
+  e.b2 = reinterpret_cast<const uint4*>(s_par + 9 * cout);
   return e;
 }
 
@@ -113,6 +122,14 @@ __device__ __forceinline__ void epi_params_fill(float* s_par, const ConvParams& 
     h2[i] = __float2half_rn(p.has_affine2 ? p.scale2[i] : 1.0f);
     t2[i] = __float2half_rn(p.has_affine2 ? p.shift2[i] : 0.0f);
     sc[i] = __float2half_rn(p.sc_const ? p.sc_const[i] : 0.0f);
+    if (p.dyt1) {
+      reinterpret_cast<__half*>(s_par + 6 * p.cout)[i] = __float2half_rn(p.dyt_g1[i]);
+      reinterpret_cast<__half*>(s_par + 7 * p.cout)[i] = __float2half_rn(p.dyt_b1[i]);
+    }
+    if (p.dyt2) {
+      reinterpret_cast<__half*>(s_par + 8 * p.cout)[i] = __float2half_rn(p.dyt_g2[i]);
+      reinterpret_cast<__half*>(s_par + 9 * p.cout)[i] = __float2half_rn(p.dyt_b2[i]);
+    }
   }
 }
 
@@ -178,6 +195,22 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
 // raw: 32 fp32 accumulators (as bits) of channels [32*cb, 32*cb+32) of this thread's row.
 // scc: the shortcut's 32 fp16 values for the same channels (4 x uint4, logical chunk order).
 // out: the 32 fp16 results (4 x uint4, logical chunk order), zero when the row is masked.
+// MaskedDYT after an affine (nnlib/v2/layers.py:432-435): h = gamma * tanh(h) + beta, packed fp16.
+__device__ __forceinline__ void dyt_apply_h2(__half2 (&h)[16], const uint4* g, const uint4* b, int cb) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 gg = g[cb * 4 + j], bb = b[cb * 4 + j];
+    const __half2* g2 = reinterpret_cast<const __half2*>(&gg);
+    const __half2* b2 = reinterpret_cast<const __half2*>(&bb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t u = *reinterpret_cast<const uint32_t*>(&h[j * 4 + k]), t;
+      asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+      h[j * 4 + k] = __hfma2(*reinterpret_cast<const __half2*>(&t), g2[k], b2[k]);
+    }
+  }
+}
+
 // kMode specialises the epilogue at compile time for the layer shapes that carry the time, so that
 // the flag tests disappear and the whole batch is one scheduling region (the runtime-flag version
 // splits it into basic blocks the compiler cannot overlap):
@@ -222,6 +255,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       h[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
     }
   }
+  if (kGen && p.dyt1) dyt_apply_h2(h, e.g1, e.b1, cb);
   if (kFinal || has_sc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -272,6 +306,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
 #pragma unroll
         for (int k = 0; k < 4; ++k) h[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
       }
+      if (p.dyt2) dyt_apply_h2(h, e.g2, e.b2, cb);
       act_apply_h2(h, p.act2);
     }
   }

@@ -28,6 +28,7 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     if (p.tap_mode == 1 && valid)
       atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, acc + p.bias[co]);
     float v = fmaf(acc, p.scale1[co], p.shift1[co]);
+    if (p.dyt1) v = fmaf(tanhf(v), p.dyt_g1[co], p.dyt_b1[co]);
     if (p.sc) {
       const bool scv = p.sc_mask ? p.sc_mask[row] != 0 : true;
       v += scv ? __half2float(p.sc[act_index(row, co, p.y_plane)])
@@ -35,7 +36,11 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     }
     v = act_apply(v, p.act1);
     if (p.tap_mode == 2 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, v);
-    if (p.has_affine2) v = act_apply(fmaf(v, p.scale2[co], p.shift2[co]), p.act2);
+    if (p.has_affine2) {
+      v = fmaf(v, p.scale2[co], p.shift2[co]);
+      if (p.dyt2) v = fmaf(tanhf(v), p.dyt_g2[co], p.dyt_b2[co]);
+      v = act_apply(v, p.act2);
+    }
     if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.y)

@@ -181,7 +181,7 @@ __host__ __device__ inline SmemLayout smem_layout(int cin, int cout, int ntaps, 
   L.w_off = 0;
   L.stage_off = (L.w_bytes + 1023u) & ~1023u;
   L.par_off = L.stage_off + n_stages * L.stage_pitch;
-  L.bar_off = L.par_off + 6u * cout * 4u;
+  L.bar_off = L.par_off + static_cast<uint32_t>(kEpiParFloats) * cout * 4u;
   L.val_off = L.bar_off + 256u;                             // validity ring: kVSlots x 128 bytes
   L.total = L.val_off + kVSlots * 128u + 1024u;             // + slack to align the base to 1024 B
   return L;

@@ -109,7 +109,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int cin, int cout, int ntaps
   L.stage_off = (L.w_bytes + 1023u) & ~1023u;
   L.out_off = L.stage_off + kStages2 * L.stage_pitch;
   L.par_off = L.out_off + static_cast<uint32_t>(staged_groups) * L.out_groups * L.out_group_bytes;
-  L.bar_off = L.par_off + 6u * cout * 4u;
+  L.bar_off = L.par_off + static_cast<uint32_t>(kEpiParFloats) * cout * 4u;
   L.val_off = L.bar_off + 256u;                                         // validity ring: kVSlots x 128 bytes
   L.total = L.val_off + kVSlots * 128u + 1024u;
   return L;
@@ -308,8 +308,8 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int n_cb = p.cout / 32;
     const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
-    const bool light = p.folded && p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.act1 == ACT_GELU_TANH;
-    const bool final_shape = p.folded && has_sc && p.tap_mode == 2 && p.has_affine2 && p.act1 == ACT_GELU_TANH && p.act2 == ACT_GELU_TANH;
+    const bool light = p.folded && !p.dyt1 && p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.act1 == ACT_GELU_TANH;
+    const bool final_shape = p.folded && !p.dyt1 && !p.dyt2 && has_sc && p.tap_mode == 2 && p.has_affine2 && p.act1 == ACT_GELU_TANH && p.act2 == ACT_GELU_TANH;
     const int epi_mode = final_shape ? (p.pool_mode == 0 ? EPI_FINAL : (p.pool_mode == 1 ? EPI_FINAL_POOL : EPI_GENERIC)) : EPI_GENERIC;
     const uint32_t warp_stage = out_base + grp * L.out_groups * L.out_group_bytes + static_cast<uint32_t>(q) * 32u * 128u;
     for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kG, it += kG) {

@@ -65,16 +65,17 @@ struct jg_ctx {
 enum LayerField {
   LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
   LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
-  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS
+  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2
 };
 // layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
-enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN };
+enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
+                LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2 };
 
 struct Layer {
   int32_t f[JG_LAYER_INT_FIELDS];
   jg::act_t* w = nullptr;      // weights image of the single-CTA kernel (w_index)
   jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
-  float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const  (6 x cout)
+  float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const, dyt gamma1, beta1, gamma2, beta2  (10 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
   bool folded = false;         // scale1 folded into the weights (par scale1 == 1)
   float* w_tap = nullptr;      // stem with an NMD tap on one-hot input: fp16-rounded weights [k][64][cout] + their tap sum [64][cout]
@@ -501,9 +502,9 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
       JG_CUDA(cudaMalloc(&L.w_tap, wt.size() * 4));
       JG_CUDA(cudaMemcpy(L.w_tap, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
     }
-    std::vector<float> par(6 * static_cast<size_t>(cout), 0.0f);
-    const int order[6] = {LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST};
-    for (int a = 0; a < 6; ++a) {
+    std::vector<float> par(10 * static_cast<size_t>(cout), 0.0f);
+    const int order[10] = {LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2};
+    for (int a = 0; a < 10; ++a) {
       const float* src = layers[l].p[order[a]];
       for (int c = 0; c < cout; ++c) par[a * cout + c] = src ? src[c] : ((order[a] == LP_SCALE1 || order[a] == LP_SCALE2) ? 1.0f : 0.0f);
     }
@@ -681,6 +682,8 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.scale2 = L.par + 3 * cout;
     p.shift2 = L.par + 4 * cout;
     p.sc_const = L.par + 5 * cout;
+    p.dyt_g1 = L.par + 6 * cout; p.dyt_b1 = L.par + 7 * cout; p.dyt_g2 = L.par + 8 * cout; p.dyt_b2 = L.par + 9 * cout;
+    p.dyt1 = L.f[LF_DYT1]; p.dyt2 = L.f[LF_DYT2];
     p.tap_sum = L.f[LF_TAP_MODE] != 0 ? m->tap_sum + static_cast<long long>(L.f[LF_TAP_SLOT]) * n_windows * m->tap_width : nullptr;
     p.pool = L.f[LF_POOL_MODE] != 0 ? m->pool : nullptr;
     p.x_plane = plane;

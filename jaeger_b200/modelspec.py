@@ -99,21 +99,27 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
         elif name == "masked_batchnorm":
             if c.get("return_nmd"):
                 raise NotImplementedError("masked_batchnorm(return_nmd=True) is not supported; use an nmd layer")
-            layers.append(LayerSpec("norm", dict(epsilon=float(c.get("epsilon", 1e-5)))))
+            layers.append(LayerSpec("norm", dict(type="bn", epsilon=float(c.get("epsilon", 1e-5)))))
+        elif name == "masked_dyt":          # nnlib/v2/layers.py:385-444: gamma * tanh(alpha * x) + beta, re-masked
+            if c.get("return_nmd"):
+                raise NotImplementedError("masked_dyt(return_nmd=True) is rejected by the reference as well")
+            layers.append(LayerSpec("norm", dict(type="dyt", alpha_init=float(c.get("alpha_init", 0.5)))))
         elif name in ("activation", "gelu", "relu"):
             layers.append(LayerSpec("act", dict(activation=_act_name(c, name if name != "activation" else None))))
         elif name == "residual_block":
             if int(c.get("strides", 1)) != 1 or c.get("use_1x1conv", False):
                 raise NotImplementedError("strided / 1x1-bypass residual blocks are not supported")
-            if str(c.get("norm_type", "masked_batchnorm")).lower() != "masked_batchnorm":
-                raise NotImplementedError("only masked_batchnorm residual blocks are supported")
+            norm_type = str(c.get("norm_type", "masked_batchnorm")).lower()
+            if norm_type not in ("masked_batchnorm", "masked_dyt"):
+                raise NotImplementedError(f"residual blocks with norm_type={norm_type!r} are not supported")
             if c.get("return_nmd"):
                 raise NotImplementedError("residual_block(return_nmd=True) is not supported; use an nmd layer")
             layers.append(LayerSpec("resblock", dict(
                 block_size=int(c.get("block_size", 1)), filters=int(c["filters"]),
                 kernel_size=int(c.get("kernel_size", 3)), dilation=int(c.get("dilation_rate", 1)),
                 use_bias=bool(c.get("use_bias", True)), activation=_act_name(c, model.get("activation", "gelu")) or "gelu",
-                use_masking=bool(c.get("use_masking", use_masking)))))
+                use_masking=bool(c.get("use_masking", use_masking)),
+                norm="dyt" if norm_type == "masked_dyt" else "bn", alpha_init=float(c.get("alpha_init", 0.5)))))
         elif name == "dropout":
             continue
         else:
@@ -189,6 +195,12 @@ def _bn(rng, c):
                 var=rng.uniform(0.5, 1.5, c).astype(np.float32))
 
 
+def _dyt(rng, c, alpha_init=0.5):
+    """MaskedDYT variables (layers.py:407-427); randomised away from the initialisers so tests see them."""
+    return dict(alpha=np.array([alpha_init * rng.uniform(0.6, 1.4)], np.float32), gamma=rng.uniform(0.5, 1.5, c).astype(np.float32),
+                beta=rng.normal(0.0, 0.1, c).astype(np.float32))
+
+
 def _conv(rng, k, cin, cout):
     return dict(kernel=_glorot(rng, (k, cin, cout), k * cin, k * cout), bias=np.zeros(cout, np.float32))
 
@@ -216,15 +228,16 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
             w["layers"].append(_conv(rng, c["kernel_size"], ch, c["filters"]))
             ch = c["filters"]
         elif layer.kind == "norm":
-            w["layers"].append(_bn(rng, ch))
+            w["layers"].append(_dyt(rng, ch, c.get("alpha_init", 0.5)) if c.get("type") == "dyt" else _bn(rng, ch))
         elif layer.kind == "nmd":
             w["layers"].append(dict(moving_mean=rng.normal(0.0, 0.1, ch).astype(np.float32)))
         elif layer.kind == "resblock":
             blocks = []
             for _ in range(c["block_size"]):
-                blocks.append(dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=_bn(rng, c["filters"]),
+                norm = (lambda n: _dyt(rng, n, c.get("alpha_init", 0.5))) if c.get("norm") == "dyt" else (lambda n: _bn(rng, n))
+                blocks.append(dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=norm(c["filters"]),
                                    conv2=_conv(rng, c["kernel_size"], c["filters"], c["filters"]),
-                                   bn2=_bn(rng, c["filters"])))
+                                   bn2=norm(c["filters"])))
                 ch = c["filters"]
             w["layers"].append(dict(blocks=blocks))
         else:

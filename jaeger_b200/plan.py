@@ -31,8 +31,9 @@ LAYER_PTR_FIELDS = 12
 # int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
- LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS) = range(22)
-(LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN) = range(8)
+ LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2) = range(24)
+(LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
+ LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2) = range(12)
 
 
 class LayerDesc(ctypes.Structure):
@@ -78,6 +79,12 @@ class ConvLaunch:
     masking: int = 1
     cum_shrink_in: int = 0
     sc_const: np.ndarray | None = None
+    # MaskedDYT in place of either norm (layers.py:385-444): y = gamma * tanh(alpha * x) + beta, where alpha
+    # is carried by scale1 / scale2 (shift 0) and the per-channel gamma / beta below follow the tanh
+    dyt_g1: np.ndarray | None = None
+    dyt_b1: np.ndarray | None = None
+    dyt_g2: np.ndarray | None = None
+    dyt_b2: np.ndarray | None = None
     out_const: np.ndarray | None = None   # value of this launch's output at rows its mask zeroed
     stage: int = 0                        # epilogue fill state while compiling
     kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool
@@ -141,6 +148,16 @@ def _bn_fold(bn: dict[str, np.ndarray], eps: float):
     return scale, shift
 
 
+def _norm_fold(nw: dict[str, np.ndarray], eps: float):
+    """(scale, shift, dyt_gamma, dyt_beta) of a norm layer's weights: BatchNorm folds to an affine,
+    MaskedDYT to the pre-scale alpha plus the post-tanh gamma / beta."""
+    if "alpha" in nw:
+        c = nw["gamma"].shape[0]
+        return np.full(c, float(np.asarray(nw["alpha"]).reshape(-1)[0])), np.zeros(c), nw["gamma"], nw["beta"]
+    s, t = _bn_fold(nw, eps)
+    return s, t, None, None
+
+
 def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
     launches: list[ConvLaunch] = []
     emb = weights.get("embedding")
@@ -185,13 +202,20 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         c.scale1 = _np32(s1)
         c.shift1 = _np32(t1 + s1 * c.bias.astype(np.float64))     # acc*s1 + (t1 + s1*bias)
         v = c.shift1.astype(np.float64)
+        if c.dyt_g1 is not None:          # MaskedDYT multiplies its output by the mask: exactly 0 at masked rows
+            c.dyt_g1, c.dyt_b1 = _np32(c.dyt_g1), _np32(c.dyt_b1)
+            v = np.zeros(cout)
         if c.sc_buf >= 0:
             v = v + (np.zeros(cout) if c.sc_const is None else c.sc_const.astype(np.float64))
             c.sc_const = _np32(np.zeros(cout) if c.sc_const is None else c.sc_const)
         v = _act_np(v, c.act1)
         if c.scale2 is not None:
             c.scale2, c.shift2 = _np32(c.scale2), _np32(c.shift2)
-            v = _act_np(v * c.scale2 + c.shift2, c.act2)
+            v = v * c.scale2 + c.shift2
+            if c.dyt_g2 is not None:
+                c.dyt_g2, c.dyt_b2 = _np32(c.dyt_g2), _np32(c.dyt_b2)
+                v = np.zeros(cout)
+            v = _act_np(v, c.act2)
         c.out_const = _np32(v)
 
     cur: ConvLaunch | None = None
@@ -236,14 +260,14 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                 h_buf = other_buf(x_buf)
                 c1 = add_conv(blk["conv1"]["kernel"], blk["conv1"]["bias"], cfg["dilation"], "same", masking,
                               x_buf, x_mask, h_buf)
-                c1.scale1, c1.shift1 = _bn_fold(blk["bn1"], 1e-5)
+                c1.scale1, c1.shift1, c1.dyt_g1, c1.dyt_b1 = _norm_fold(blk["bn1"], 1e-5)
                 c1.act1, c1.stage = cfg["activation"], 2
                 finish(c1)
                 # conv2 writes the block output in place over the block input (same rows, same thread)
                 c2 = add_conv(blk["conv2"]["kernel"], blk["conv2"]["bias"], cfg["dilation"], "same", masking,
                               h_buf, c1.mask_out, x_buf, sc_buf=x_buf, sc_mask=x_mask if masking else -1,
                               sc_const=x_const)
-                c2.scale1, c2.shift1 = _bn_fold(blk["bn2"], 1e-5)
+                c2.scale1, c2.shift1, c2.dyt_g1, c2.dyt_b1 = _norm_fold(blk["bn2"], 1e-5)
                 c2.act1, c2.stage = cfg["activation"], 2
                 cur = c2
                 cur_buf, cur_mask = x_buf, c2.mask_out
@@ -262,11 +286,11 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         elif layer.kind == "norm":
             if cur is None:
                 raise NotImplementedError("norm before the first convolution")
-            s, t = _bn_fold(lw, cfg.get("epsilon", 1e-5))
+            s, t, dg, db = _norm_fold(lw, cfg.get("epsilon", 1e-5))
             if cur.stage == 0:
-                cur.scale1, cur.shift1, cur.stage = s, t, 1
+                cur.scale1, cur.shift1, cur.dyt_g1, cur.dyt_b1, cur.stage = s, t, dg, db, 1
             elif cur.stage == 2 and cur.scale2 is None:
-                cur.scale2, cur.shift2, cur.stage = s, t, 3
+                cur.scale2, cur.shift2, cur.dyt_g2, cur.dyt_b2, cur.stage = s, t, dg, db, 3
             else:
                 raise NotImplementedError("more element-wise layers after a convolution than the fused epilogue holds")
         elif layer.kind == "act":
@@ -308,6 +332,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         c.bias, c.shift1, c.shift2 = pad(c.bias, 0.0), pad(c.shift1, 0.0), pad(c.shift2, 0.0)
         c.scale1, c.scale2 = pad(c.scale1, 1.0), pad(c.scale2, 1.0)
         c.sc_const, c.out_const = pad(c.sc_const, 0.0), pad(c.out_const, 0.0)
+        c.dyt_g1, c.dyt_b1, c.dyt_g2, c.dyt_b2 = pad(c.dyt_g1, 0.0), pad(c.dyt_b1, 0.0), pad(c.dyt_g2, 0.0), pad(c.dyt_b2, 0.0)
     ch = -(-ch // 64) * 64
     last = launches[-1]
     last.pool_mode = 1 if spec.pooling == "max" else 2
@@ -350,11 +375,12 @@ def to_ctypes(plan: Plan):
                 LF_ACT1: ACT[c.act1], LF_HAS_AFF2: int(c.scale2 is not None), LF_ACT2: ACT[c.act2],
                 LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
                 LF_MASK_OUT: c.mask_out, LF_SC_MASK: c.sc_mask, LF_MASKING: c.masking,
-                LF_CUM_SHRINK_IN: c.cum_shrink_in}
+                LF_CUM_SHRINK_IN: c.cum_shrink_in, LF_DYT1: int(c.dyt_g1 is not None), LF_DYT2: int(c.dyt_g2 is not None)}
         for i, v in vals.items():
             d.i[i] = int(v)
         ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,
-                LP_SHIFT2: c.shift2, LP_SC_CONST: c.sc_const, LP_TAP_MEAN: c.tap_mean}
+                LP_SHIFT2: c.shift2, LP_SC_CONST: c.sc_const, LP_TAP_MEAN: c.tap_mean,
+                LP_DYT_G1: c.dyt_g1, LP_DYT_B1: c.dyt_b1, LP_DYT_G2: c.dyt_g2, LP_DYT_B2: c.dyt_b2}
         for i, a in ptrs.items():
             d.p[i] = _fptr(a)
     h = HeadDesc()

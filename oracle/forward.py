@@ -83,6 +83,16 @@ def batchnorm(x, bn, eps=1e-5):
     return bn["gamma"] * ((x - bn["mean"]) * inv) + bn["beta"]
 
 
+def dyt(x, w, mask):
+    """MaskedDYT (layers.py:432-444): gamma * tanh(alpha * x) + beta, multiplied by the incoming mask."""
+    out = torch.tanh(w["alpha"] * x) * w["gamma"] + w["beta"]
+    return out * mask.unsqueeze(-1) if mask is not None else out
+
+
+def _norm(x, w, mask, eps=1e-5):
+    return dyt(x, w, mask) if "alpha" in w else batchnorm(x, w, eps)
+
+
 def nmd_vector(x, mask, moving_mean, eps=1e-5):
     """nmd.py:52-77 inference branch."""
     if mask is not None:
@@ -144,7 +154,7 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
         elif layer.kind == "nmd":
             nmds.append(nmd_vector(x, mask, _t(lw["moving_mean"], dtype)))
         elif layer.kind == "norm":
-            x = batchnorm(x, {k: _t(v, dtype) for k, v in lw.items()}, c.get("epsilon", 1e-5))
+            x = _norm(x, {k: _t(v, dtype) for k, v in lw.items()}, mask if spec.use_masking else None, c.get("epsilon", 1e-5))
         elif layer.kind == "act":
             x = _act(x, c.get("activation"))
         elif layer.kind == "resblock":
@@ -152,10 +162,10 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
                 m_in = mask if c["use_masking"] else None
                 h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
                                       c["dilation"], "same")
-                h = _act(batchnorm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}), c["activation"])
+                h = _act(_norm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}, m1 if m_in is not None else None), c["activation"])
                 h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
                                        c["dilation"], "same")
-                h2 = batchnorm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()})
+                h2 = _norm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()}, m2 if m_in is not None else None)
                 x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
                 mask = m2 if m_in is not None else mask
         else:

@@ -21,3 +21,15 @@ def random_contigs(seed: int, lengths, n_run_every: int = 3, lower_every: int = 
             s[int(rng.integers(0, n))] = ord("y")
         recs.append((f"c{i}", s.tobytes().decode()))
     return recs
+
+
+def to_dyt(cfg: dict) -> dict:
+    """The same architecture with MaskedDYT in place of every MaskedBatchNorm (the reference's
+    train_config/nn_config_1500bp_nmd_merge_6_class_zeus.yaml family)."""
+    for layer in cfg["model"]["representation_learner"]["hidden_layers"]:
+        if layer["name"] == "masked_batchnorm":
+            layer["name"] = "masked_dyt"
+            layer["config"] = {}
+        elif layer["name"] == "residual_block":
+            layer["config"]["norm_type"] = "masked_dyt"
+    return cfg

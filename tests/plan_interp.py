@@ -47,6 +47,8 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
             taps[c.tap_slot] = ((acc + torch.as_tensor(c.bias, dtype=dt)) * mo).sum(dim=(1, 2)) / (m_out.sum(dim=(1, 2)).unsqueeze(-1) + 1e-5) \
                 - torch.as_tensor(c.tap_mean, dtype=dt)
         v = acc * torch.as_tensor(c.scale1, dtype=dt) + torch.as_tensor(c.shift1, dtype=dt)
+        if c.dyt_g1 is not None:
+            v = torch.tanh(v) * torch.as_tensor(c.dyt_g1, dtype=dt) + torch.as_tensor(c.dyt_b1, dtype=dt)
         if c.sc_buf >= 0:
             sc = bufs[c.sc_buf]
             if c.sc_mask >= 0:
@@ -58,7 +60,10 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
             taps[c.tap_slot] = (v * mo).sum(dim=(1, 2)) / (m_out.sum(dim=(1, 2)).unsqueeze(-1) + 1e-5) \
                 - torch.as_tensor(c.tap_mean, dtype=dt)
         if c.scale2 is not None:
-            v = _act(v * torch.as_tensor(c.scale2, dtype=dt) + torch.as_tensor(c.shift2, dtype=dt), c.act2)
+            v = v * torch.as_tensor(c.scale2, dtype=dt) + torch.as_tensor(c.shift2, dtype=dt)
+            if c.dyt_g2 is not None:
+                v = torch.tanh(v) * torch.as_tensor(c.dyt_g2, dtype=dt) + torch.as_tensor(c.dyt_b2, dtype=dt)
+            v = _act(v, c.act2)
         if c.pool_mode == 1:
             pm = torch.where(mo > 0, v, torch.tensor(-1e9, dtype=dt)).amax(dim=(1, 2))
             pooled = torch.where(m_out.amax(dim=(1, 2)).unsqueeze(-1) > 0, pm, torch.zeros_like(pm))

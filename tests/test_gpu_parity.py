@@ -236,6 +236,37 @@ def test_other_architectures_avg_pool_no_masking_relu(standin):
         assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2, (pooling, masking)
 
 
+@pytest.mark.parametrize("masking", [True, False])
+def test_masked_dyt_model_family_vs_oracle(masking):
+    """The MaskedDYT variant of the architecture (gamma * tanh(alpha x) + beta in place of every BatchNorm,
+    re-masked; train_config/nn_config_1500bp_nmd_merge_6_class_zeus.yaml): logits / embeddings / NMD vectors
+    against the fp32 oracle, long pass and padded short pass, with unknown-codon runs."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project, standin_1p4m_config
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import seqwin
+    from tests.helpers import random_contigs, to_dyt
+    cfg = to_dyt(standin_1p4m_config())
+    cfg["model"]["use_masking"] = masking
+    spec = parse_project(cfg)
+    w = init_random(spec, 6)
+    recs = random_contigs(31, [2000, 6500, 9000, 2300, 1400, 800])
+    eng = B200Engine(spec=spec, weights=w)
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500, min_len=500, batch=2))
+    eng_ref = B200Engine(spec=spec, weights=w, use_ref_kernels=True)
+    y2 = eng_ref.predict(WindowSource(records=recs, fsize=2000, stride=1500, min_len=500, batch=2))
+    eng.close(); eng_ref.close()
+    long_w = list(seqwin.fragment_windows(recs, 2000, 1500, min_len=2000))
+    n = len(long_w)
+    ref = ofw.forward(spec, w, oenc.encode_windows([x.seq for x in long_w], 2000))
+    for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
+        assert np.abs(ref[k] - y[k][:n]).max() <= tol, (k, np.abs(ref[k] - y[k][:n]).max())
+        assert np.abs(y[k] - y2[k]).max() <= 4e-3, k                     # tensor-core path vs CUDA-core restatement
+    short_w = list(seqwin.fragment_windows(recs, 2000, 1500, min_len=500, max_len=1999))
+    r = ofw.forward(spec, w, oenc.encode_windows([x.seq for x in short_w], 2000))
+    assert np.abs(r["prediction"] - y["prediction"][n:]).max() <= 4e-3
+
+
 @pytest.mark.parametrize("ksize", [2, 3])
 def test_wide_256_channel_layer_with_accumulator_reuse(ksize):
     """A 128 -> 256 channel convolution has only two TMEM accumulators; with several tiles per SM

@@ -65,9 +65,12 @@ def _tokens(seed, b, lc, n_frac=0.02, pad_from=None):
     return t
 
 
-@pytest.mark.parametrize("pooling,masking,rel", [("max", True, True), ("average", True, False), ("max", False, True)])
-def test_plan_equals_unfused_oracle(pooling, masking, rel):
-    spec = parse_project(small_config(pooling, masking, rel))
+@pytest.mark.parametrize("pooling,masking,rel,dyt", [("max", True, True, False), ("average", True, False, False), ("max", False, True, False),
+                                                     ("max", True, True, True), ("average", False, False, True)])
+def test_plan_equals_unfused_oracle(pooling, masking, rel, dyt):
+    from tests.helpers import to_dyt
+    cfg = small_config(pooling, masking, rel)
+    spec = parse_project(to_dyt(cfg) if dyt else cfg)
     w = init_random(spec, 3)
     # non-trivial biases / BN betas so the masked-row constants matter
     rng = np.random.default_rng(1)
