@@ -220,8 +220,11 @@ __device__ __forceinline__ void dyt_apply_h2(__half2 (&h)[16], const uint4* g, c
 //   EPI_FINAL_POOL  the same + masked global max pool (last layer)
 // The specialised modes also assume the first affine's scale is folded into the weights (p.folded).
 // The caller checks that the layer matches the mode it picks.
+// kD1 / kD2: in a specialised mode, the first / second norm is a MaskedDYT (tanh + gamma / beta after the affine).
 enum EpiMode { EPI_GENERIC = 0, EPI_LIGHT = 1, EPI_FINAL = 2, EPI_FINAL_POOL = 3 };
-template <int kMode = EPI_GENERIC>
+template <int kMode_, bool kD1_ = false, bool kD2_ = false>
+struct EpiTag { static constexpr int kMode = kMode_; static constexpr bool kD1 = kD1_, kD2 = kD2_; };
+template <int kMode = EPI_GENERIC, bool kD1 = false, bool kD2 = false>
 __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiParams& e, int cb, const uint32_t (&raw)[32],
                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane,
                                                int win, uint4 (&out)[4]) {
@@ -255,7 +258,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       h[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
     }
   }
-  if (kGen && p.dyt1) dyt_apply_h2(h, e.g1, e.b1, cb);
+  if (kD1 || (kGen && p.dyt1)) dyt_apply_h2(h, e.g1, e.b1, cb);
   if (kFinal || has_sc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -280,6 +283,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
 #pragma unroll
       for (int k = 0; k < 4; ++k) x3[j * 4 + k] = __hfma2(h[j * 4 + k], a2[k], b2[k]);
     }
+    if (kD2) dyt_apply_h2(x3, e.g2, e.b2, cb);
     if (any_masked) {
       const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll

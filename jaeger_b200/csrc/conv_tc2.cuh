@@ -308,8 +308,8 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int n_cb = p.cout / 32;
     const EpiParams ep = epi_params(s_par, p.cout);
     const bool has_sc = p.sc != nullptr;
-    const bool light = p.folded && !p.dyt1 && p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.act1 == ACT_GELU_TANH;
-    const bool final_shape = p.folded && !p.dyt1 && !p.dyt2 && has_sc && p.tap_mode == 2 && p.has_affine2 && p.act1 == ACT_GELU_TANH && p.act2 == ACT_GELU_TANH;
+    const bool light = p.folded && p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.act1 == ACT_GELU_TANH;
+    const bool final_shape = p.folded && p.dyt1 == p.dyt2 && has_sc && p.tap_mode == 2 && p.has_affine2 && p.act1 == ACT_GELU_TANH && p.act2 == ACT_GELU_TANH;
     const int epi_mode = final_shape ? (p.pool_mode == 0 ? EPI_FINAL : (p.pool_mode == 1 ? EPI_FINAL_POOL : EPI_GENERIC)) : EPI_GENERIC;
     const uint32_t warp_stage = out_base + grp * L.out_groups * L.out_group_bytes + static_cast<uint32_t>(q) * 32u * 128u;
     for (int pt = pt_begin + grp, it = grp; pt < pt_end; pt += kG, it += kG) {
@@ -344,7 +344,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
 
       // one 32-channel batch whose accumulators are already in `raw`
       auto batch = [&](int cb, const uint32_t (&raw)[32], auto mode_tag) {
-        constexpr int kMode = decltype(mode_tag)::value;
+        using Tag = decltype(mode_tag);
         uint4 scc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) scc[j] = scv[j];
@@ -356,7 +356,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
                                                      ((((nb & 1) * 4 + j) ^ sw) * 8));
         }
         uint4 out[4];
-        epilogue_batch<kMode>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
+        epilogue_batch<Tag::kMode, Tag::kD1, Tag::kD2>(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
         if constexpr (kStage) {
           if (p.y) {
             const int og = cb >> 1;
@@ -400,27 +400,29 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(TEMPTY(as), 0));
       };
 
-      if (kStage && n_cb == 4 && light) {
-        // light layers (conv1 / conv2 of a residual block): unrolled, TMEM loads one batch ahead
-        using L1 = std::integral_constant<int, EPI_LIGHT>;
+      // light layers (conv1 / conv2 of a residual block): unrolled, TMEM loads one batch ahead
+      auto light_tile = [&](auto tag) {
         uint32_t r0[32], r1[32], r2[32], r3[32];
         tmem_ld32(t_addr, r0);
         tmem_ld_wait();
         if (tr_on) tr[3] = clock64();
         tmem_ld32(t_addr + 32u, r1);
-        batch(0, r0, L1{});
+        batch(0, r0, tag);
         tmem_ld_wait();
         if (tr_on) tr[5] = clock64();
         tmem_ld32(t_addr + 64u, r2);
-        batch(1, r1, L1{});
+        batch(1, r1, tag);
         tmem_ld_wait();
         if (tr_on) tr[7] = clock64();
         tmem_ld32(t_addr + 96u, r3);
-        batch(2, r2, L1{});
+        batch(2, r2, tag);
         tmem_ld_wait();
         if (tr_on) tr[9] = clock64();
         release_acc();
-        batch(3, r3, L1{});
+        batch(3, r3, tag);
+      };
+      if (kStage && n_cb == 4 && light) {
+        if (p.dyt1) light_tile(EpiTag<EPI_LIGHT, true>{}); else light_tile(EpiTag<EPI_LIGHT>{});
       } else {
         // everything else: rolled copies of the full epilogue (unrolled it would not fit the instruction
         // cache), specialised for the two block-final shapes, generic otherwise
@@ -434,9 +436,9 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
             batch(cb, r0, mode_tag);
           }
         };
-        if (epi_mode == EPI_FINAL) rolled(std::integral_constant<int, EPI_FINAL>{});
-        else if (epi_mode == EPI_FINAL_POOL) rolled(std::integral_constant<int, EPI_FINAL_POOL>{});
-        else rolled(std::integral_constant<int, EPI_GENERIC>{});
+        if (epi_mode == EPI_FINAL) { if (p.dyt1) rolled(EpiTag<EPI_FINAL, true, true>{}); else rolled(EpiTag<EPI_FINAL>{}); }
+        else if (epi_mode == EPI_FINAL_POOL) { if (p.dyt1) rolled(EpiTag<EPI_FINAL_POOL, true, true>{}); else rolled(EpiTag<EPI_FINAL_POOL>{}); }
+        else rolled(EpiTag<EPI_GENERIC>{});
       }
       if (tr_on) tr[11] = clock64();
     }

@@ -4,7 +4,12 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 from jaeger_b200 import B200Engine, parse_project, standin_1p4m_config
 from bench import synth_batch, FSIZE, STRIDE
-eng = B200Engine(spec=parse_project(standin_1p4m_config()), workspace_gb=24)
+cfg = standin_1p4m_config()
+if os.environ.get("JG_DYT"):            # the MaskedDYT variant of the architecture
+    sys.path.insert(0, "tests")
+    from helpers import to_dyt
+    cfg = to_dyt(cfg)
+eng = B200Engine(spec=parse_project(cfg), workspace_gb=24)
 seq, lens = synth_batch(1, int(16e6))
 with torch.cuda.stream(eng._stream()):
     x = torch.from_numpy(seq).to(eng.tdev)
