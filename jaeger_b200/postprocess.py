@@ -279,3 +279,31 @@ def write_output_legacy(data: dict[str, Any], labels: list[str], output_table_pa
     df.query(f'(prediction == "phage") and (phage_score > {phage_score}){clause}').to_csv(
         output_phage_table_path, sep="\t", index=False, float_format="%.3f")
     return len(df)
+
+
+def write_fasta_from_results(loaded, output_tsv, output_fasta, width: int = 70) -> int:
+    """write_fasta_from_results (collect.py:611-639) from the records already in memory (`loaded` =
+    WindowSource.load(): names, bases, offsets) instead of a further pass over the input file:
+    the records whose name is in the phage table, 70 letters per line.  Returns the record count."""
+    import pandas as pd
+    try:
+        phages = set(pd.read_table(str(output_tsv))["contig_id"].astype(str).to_list())
+    except (FileNotFoundError, pd.errors.EmptyDataError):
+        phages = set()
+    names, host, offsets = loaded
+    data = host.numpy()
+    n = 0
+    with open(str(output_fasta), "wb") as fh:
+        for i, name in enumerate(names):
+            if name not in phages:
+                continue
+            n += 1
+            fh.write(b">" + name.encode() + b"\n")
+            seq = data[offsets[i]:offsets[i + 1]]
+            full = len(seq) // width * width
+            if full:
+                lines = np.concatenate([seq[:full].reshape(-1, width), np.full((full // width, 1), 10, np.uint8)], axis=1)
+                fh.write(lines.tobytes())
+            if len(seq) > full:
+                fh.write(seq[full:].tobytes() + b"\n")
+    return n

@@ -214,6 +214,11 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                 rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
         (out_dir / f"{base}_prophage_regions.tsv").write_text("\n".join(rows) + "\n")
         result["prophage_regions"] = regions
+    if kwargs.get("getsequences"):                                        # predict.py:444-455
+        from .postprocess import write_fasta_from_results
+        full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
+        n_seq = write_fasta_from_results(full, phage_table, out_dir / f"{base}_phages_jaeger.fasta")
+        logger.info(f"{base}_phages_jaeger.fasta created ({n_seq} records)")
     if kwargs.get("window_scores") and data:                              # predict.py:458-470
         off = data["offsets"]
         np.savez(out_dir / f"{base}_window_scores.npz", headers=data["headers"], lengths=data["length"],
@@ -253,6 +258,7 @@ def main(argv=None) -> int:
     ap.add_argument("-s", "--sensitivity", type=float, default=1.5)
     ap.add_argument("--physicalid", type=int, default=0)
     ap.add_argument("--window-scores", dest="window_scores", action="store_true")
+    ap.add_argument("--getsequences", action="store_true", help="write the records of the phage table to <base>_phages_jaeger.fasta")
     ap.add_argument("--overwrite", action="store_true")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s [jaeger_b200] %(message)s")

@@ -112,3 +112,17 @@ def test_terminal_repeat_oracle_known_answers():
     assert d["score"] == 16 and d["cols"] == 12
     rows = ot.scan_for_terminal_repeats([("x", core + rnd(2500) + ot.reverse_complement(core)), ("y", rnd(2600)), ("z", rnd(100))], 2000)
     assert [r["terminal_repeats"] for r in rows] == ["ITR", None] and rows[0]["repeat_length"] == 120
+
+
+def test_write_fasta_from_results(tmp_path):
+    """collect.py:611-639: records named in the phage table, 70 letters per line, input order."""
+    from jaeger_b200.engine import WindowSource
+    recs = [("a", "ACGT" * 40), ("b,x", "G" * 70), ("c", "T" * 5), ("d", "ACG" * 50)]
+    (tmp_path / "p.tsv").write_text("contig_id\tlength\nd\t150\na\t160\nb,x\t70\n")
+    n = pp.write_fasta_from_results(WindowSource(records=recs).load(), tmp_path / "p.tsv", tmp_path / "o.fa")
+    want = ""
+    for name, seq in recs:
+        if name in ("a", "b,x", "d"):
+            want += f">{name}\n" + "".join(seq[i:i + 70] + "\n" for i in range(0, len(seq), 70))
+    assert n == 3 and (tmp_path / "o.fa").read_text() == want
+    assert pp.write_fasta_from_results(WindowSource(records=recs).load(), tmp_path / "missing.tsv", tmp_path / "e.fa") == 0
