@@ -19,7 +19,8 @@ inner layer already attached to the output tensor, so the block output carries c
 
 PARITY UNPINNED for logits: TensorFlow cannot be installed in the build container, so this
 restatement is checked only against the reference tests' mask / pooling known answers
-(tests/unit/test_mask_mode.py, test_masked_pooling.py) -- see tests/test_oracle_goldens.py.
+(tests/unit/test_mask_mode.py, test_masked_pooling.py, test_nnlib_v2_nmd.py, test_inference_crop.py) -- see
+tests/test_oracle_layer_known_answers.py.
 """
 from __future__ import annotations
 

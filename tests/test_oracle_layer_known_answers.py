@@ -1,0 +1,144 @@
+"""Pins oracle/forward.py's layer restatements on the known answers the reference's own unit tests hold for
+them (the only layer-level facts available without TensorFlow): tests/unit/test_mask_mode.py (output-mask rules
+of MaskedConv1D in the three mask modes), tests/unit/test_masked_pooling.py (masked global max / average
+pooling, the fully-masked sample), tests/unit/test_nnlib_v2_nmd.py (NMD vector = masked channel mean minus the
+moving mean) and tests/unit/test_inference_crop.py:42-91 (frame lengths after the VALID stem).  Each test
+names the reference test it restates; inputs are rebuilt with the same shapes / seeds where the reference
+uses NumPy generators."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward as fwd
+
+
+def _out_mask(mask_1d: np.ndarray, mode: str, k: int = 5, padding: str = "valid", dilation: int = 1) -> np.ndarray:
+    """test_mask_mode.py:_run_mask_mode: a MaskedConv1D over ones((1, 1, L, 4)), output mask flattened."""
+    length = mask_1d.shape[-1]
+    x = torch.ones(1, 1, length, 4)
+    kernel = torch.ones(k, 4, 4)
+    _, om = fwd.masked_conv1d(x, torch.as_tensor(mask_1d, dtype=torch.float32).reshape(1, 1, length), kernel, None,
+                              dilation, padding, None, mask_mode=mode)
+    return om.numpy().reshape(-1) > 0
+
+
+def _mask_with_n(length: int, n_pos: list[int]) -> np.ndarray:
+    m = np.ones(length, dtype=bool)
+    m[n_pos] = False
+    return m
+
+
+def test_mask_mode_isolated_n():
+    """test_isolated_n_any_kills_nothing / _strict_kills_kernel_window / _majority_survives."""
+    mask = _mask_with_n(20, [10])
+    assert _out_mask(mask, "any").all()
+    expected = np.ones(16, dtype=bool)
+    expected[6:11] = False
+    np.testing.assert_array_equal(_out_mask(mask, "strict"), expected)
+    assert _out_mask(mask, "majority").all()
+
+
+def test_mask_mode_n_runs():
+    """test_short_n_run_any_kills_nothing, test_long_n_run_any_kills_only_the_run, _strict_kills_run_plus_halo."""
+    assert _out_mask(_mask_with_n(20, [9, 10, 11]), "any").all()
+    run5 = _mask_with_n(20, [9, 10, 11, 12, 13])
+    expected = np.ones(16, dtype=bool)
+    expected[9] = False
+    np.testing.assert_array_equal(_out_mask(run5, "any"), expected)
+    expected = np.ones(16, dtype=bool)
+    expected[5:14] = False
+    np.testing.assert_array_equal(_out_mask(run5, "strict"), expected)
+
+
+def test_mask_mode_right_padding():
+    """test_right_padding_any_keeps_real_content: 10 real positions right-padded to 20."""
+    mask = _mask_with_n(20, list(range(10, 20)))
+    out_any, out_strict = _out_mask(mask, "any"), _out_mask(mask, "strict")
+    assert out_any[:10].all() and not out_any[10:].any()
+    assert out_strict[:6].all() and not out_strict[6:].any()
+
+
+def test_conv_output_lengths():
+    """MaskedConv1D.compute_output_shape (layers.py:1315-1332) and test_inference_crop.py:42-91: a 665-codon
+    frame leaves the VALID k7 stem with 659 positions; SAME keeps the length, dilated or not."""
+    x = torch.zeros(1, 6, 665, 4)
+    y, _ = fwd.masked_conv1d(x, None, torch.zeros(7, 4, 8), None, 1, "valid")
+    assert y.shape == (1, 6, 659, 8)
+    y, _ = fwd.masked_conv1d(y, None, torch.zeros(5, 8, 8), None, 3, "same")
+    assert y.shape == (1, 6, 659, 8)
+    x = torch.zeros(1, 6, 498, 4)
+    assert fwd.masked_conv1d(x, None, torch.zeros(7, 4, 8), None, 1, "valid")[0].shape[2] == 492
+
+
+def test_same_padding_split_is_floor_left_ceil_right():
+    """TF SAME with an even total pad (k4: 3 -> left 1, right 2): an impulse response
+    shows where tap 0 lands."""
+    x = torch.zeros(1, 1, 9, 1)
+    x[0, 0, 4, 0] = 1.0
+    kernel = torch.arange(1.0, 5.0).reshape(4, 1, 1)
+    y, _ = fwd.masked_conv1d(x, None, kernel, None, 1, "same")
+    # y[i] = sum_t w[t] * x[i - 1 + t]  ->  the impulse at 4 shows w[t] at i = 5 - t
+    np.testing.assert_array_equal(y.numpy().reshape(-1), [0, 0, 4, 3, 2, 1, 0, 0, 0])
+
+
+def _padded_pair(batch=2, strands=6, length=32, dim=8, valid=20, seed=0):
+    """test_masked_pooling.py:_padded_pair."""
+    rng = np.random.default_rng(seed)
+    x = torch.as_tensor(rng.normal(size=(batch, strands, length, dim)), dtype=torch.float32)
+    mask = torch.cat([torch.ones(batch, strands, valid), torch.zeros(batch, strands, length - valid)], dim=-1)
+    return x, mask, valid
+
+
+def test_masked_max_pooling_known_answers():
+    """test_masked_max_pooling_matches_truncated_max, _excludes_padded_constants, _no_mask_matches_stock."""
+    x, mask, valid = _padded_pair()
+    np.testing.assert_allclose(fwd.masked_global_max(x, mask).numpy(), x[:, :, :valid].amax(dim=(1, 2)).numpy(), atol=1e-6)
+    x2 = torch.where(mask.unsqueeze(-1) > 0, x * 0.01, torch.tensor(1e6))
+    np.testing.assert_allclose(fwd.masked_global_max(x2, mask).numpy(), x2[:, :, :valid].amax(dim=(1, 2)).numpy(), atol=1e-6)
+    np.testing.assert_allclose(fwd.masked_global_max(x, None).numpy(), x.amax(dim=(1, 2)).numpy(), atol=1e-6)
+
+
+def test_fully_masked_sample_pools_to_zero_not_sentinel():
+    """test_fully_masked_sample_pools_to_zero_not_sentinel."""
+    x = torch.randn(2, 6, 16, 8, generator=torch.Generator().manual_seed(0))
+    mask = torch.cat([torch.ones(1, 6, 16), torch.zeros(1, 6, 16)], dim=0)
+    pooled = fwd.masked_global_max(x, mask).numpy()
+    np.testing.assert_allclose(pooled[0], x[0].amax(dim=(0, 1)).numpy(), atol=1e-6)
+    np.testing.assert_array_equal(pooled[1], np.zeros(8, np.float32))
+
+
+def test_masked_avg_pooling_known_answers():
+    """test_masked_avg_pooling_matches_masked_mean, _no_mask_matches_stock."""
+    x, mask, valid = _padded_pair()
+    np.testing.assert_allclose(fwd.masked_global_avg(x, mask).numpy(), x[:, :, :valid].mean(dim=(1, 2)).numpy(), atol=1e-6)
+    np.testing.assert_allclose(fwd.masked_global_avg(x, None).numpy(), x.mean(dim=(1, 2)).numpy(), atol=1e-6)
+
+
+def test_nmd_vector_is_masked_mean_minus_moving_mean():
+    """test_nmd_matches_masked_batch_norm_with_mask: NMDLayer and MaskedBatchNorm(return_nmd=True) both return
+    (masked per-example channel mean) - moving_mean (nmd.py:52-77, layers.py:943-966); restated from the formula."""
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(4, 6, 32, 8, generator=g)
+    mask = torch.cat([torch.ones(2, 6, 32), (torch.rand(2, 6, 32, generator=g) < 0.7).float()], dim=0)
+    mm = torch.randn(8, generator=g) * 0.1
+    got = fwd.nmd_vector(x, mask, mm).numpy()
+    for b in range(4):
+        sel = mask[b] > 0
+        want = x[b][sel].sum(dim=0) / (sel.sum() + 1e-5) - mm
+        np.testing.assert_allclose(got[b], want.numpy(), atol=1e-5)
+    np.testing.assert_allclose(fwd.nmd_vector(x, None, mm).numpy(), (x.mean(dim=(1, 2)) - mm).numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("mode,thr", [("any", 1), ("majority", 3), ("strict", 5)])
+def test_mask_threshold_rule_on_random_masks(mode, thr):
+    """layers.py:1245-1252: any = count > 0, majority = count >= (k + 1) // 2, strict = count == k, with TF SAME
+    zero padding counting as invalid; checked by brute force on random masks, dilation 3."""
+    rng = np.random.default_rng(3)
+    k, d, length = 5, 3, 40
+    for _ in range(20):
+        m = rng.random(length) < 0.6
+        padded = np.concatenate([np.zeros(6, bool), m, np.zeros(6, bool)])     # total pad d*(k-1) = 12, left 6
+        cnt = np.array([sum(padded[i + t * d] for t in range(k)) for i in range(length)])
+        np.testing.assert_array_equal(_out_mask(m, mode, k, "same", d), cnt >= thr)
