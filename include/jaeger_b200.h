@@ -223,19 +223,24 @@ int jg_legacy_reliability(jg_ctx* ctx, const float* d_embedding, int64_t n_windo
 /* ---- terminal-repeat scan -----------------------------------------------------
  * Replaces the two parasail.sw_trace_scan_16 calls per contig of scan_for_terminal_repeats
  * (utils/termini.py:103-131): matrix_create("ACGT", 2, -100), gap open 100 / extend 5.
- * A job aligns query = bases [q0, q0+n) against reference = bases [r0, r0+n) (direct) or their
- * reverse complement (inverted), both taken from the packed contigs of jg_pack_bases.
+ * A job aligns query = bases [q0, q0+nq) (nq = 0 means n) against reference = bases [r0, r0+n) (direct) or their
+ * reverse complement (inverted), both taken from the packed contigs of jg_pack_bases.  Square jobs are the
+ * terminal-repeat scans; rectangular ones the att-site scans of prophage_report (postprocess/prophages.py:771-800,
+ * same parasail call and scores).
  * jg_sw_scan:  d_out[job] = {score, end_query, end_ref, length of the diagonal run ending there}.
  * jg_sw_trace: refills [0,end_i] x [0,end_j], one direction byte per cell at d_scratch + dirs_off
  *              ((end_i+1)*(end_j+1) bytes), and walks the traceback:
  *              d_out[job] = {alignment columns, gaps in query line, gaps in reference line, identities}
- *              (the counts get_alignment_summary takes from result.traceback, termini.py:43-46).
- * threads: CTA size, a multiple of 32 with threads * 16 >= max_n (largest n of the call), resp. >= max_rows
- * (largest end_i + 1); max_cols = largest end_j + 1. */
-typedef struct jg_sw_job { int64_t q0, r0; int32_t n, inverted; } jg_sw_job;
-typedef struct jg_sw_trace_job { jg_sw_job job; int32_t end_i, end_j; int64_t dirs_off; } jg_sw_trace_job;
+ *              (the counts get_alignment_summary takes from result.traceback, termini.py:43-46).  With
+ *              ops_off >= 0 it also writes one byte per alignment column at d_scratch + ops_off, last column
+ *              first (1 pair, 2 gap in the query line, 3 gap in the reference line; <= end_i + end_j + 2
+ *              bytes): what result.traceback.query / .ref (the `front` / `rear`, `attL` / `attR` strings) need.
+ * threads: CTA size, a multiple of 32 with threads * 16 >= max_rows (largest query length of the call, resp.
+ * largest end_i + 1); max_cols = largest reference length, resp. largest end_j + 1. */
+typedef struct jg_sw_job { int64_t q0, r0; int32_t n, inverted, nq, reserved; } jg_sw_job;
+typedef struct jg_sw_trace_job { jg_sw_job job; int32_t end_i, end_j; int64_t dirs_off, ops_off; } jg_sw_trace_job;
 int jg_sw_scan(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid, const jg_sw_job* d_jobs, int32_t n_jobs,
-               int32_t threads, int32_t max_n, int32_t* d_out);
+               int32_t threads, int32_t max_rows, int32_t max_cols, int32_t* d_out);
 int jg_sw_trace(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid, const jg_sw_trace_job* d_jobs, int32_t n_jobs,
                 int32_t threads, int32_t max_rows, int32_t max_cols, uint8_t* d_scratch, int32_t* d_out);
 

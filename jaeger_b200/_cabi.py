@@ -61,7 +61,7 @@ _SIGNATURES = {
     "jg_segment_scores": (c_int32, [c_void_p, _P, c_int32, c_int32, c_int32, _P, _P]),
     "jg_legacy_reliability": (c_int32, [c_void_p, _P, c_int64, c_int32, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                         _P, c_int32, _P, _P]),
-    "jg_sw_scan": (c_int32, [c_void_p, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
+    "jg_sw_scan": (c_int32, [c_void_p, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P]),
     "jg_sw_trace": (c_int32, [c_void_p, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "jg_viterbi_decode": (c_int32, [c_void_p, _P, _P, c_int32, c_int64, c_int32, _P, _P, _P]),
 }

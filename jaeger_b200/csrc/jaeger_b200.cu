@@ -915,14 +915,14 @@ static_assert(sizeof(jg_sw_job) == sizeof(jg::SwJob), "jg_sw_job layout");
 static_assert(sizeof(jg_sw_trace_job) == sizeof(jg::SwTraceJob), "jg_sw_trace_job layout");
 
 int jg_sw_scan(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_valid, const jg_sw_job* d_jobs, int32_t n_jobs,
-               int32_t threads, int32_t max_n, int32_t* d_out) {
+               int32_t threads, int32_t max_rows, int32_t max_cols, int32_t* d_out) {
   if (n_jobs <= 0) return 0;
-  if (threads < 32 || threads > 1024 || threads % 32 != 0 || static_cast<long long>(threads) * jg::kSwRows < max_n)
-    return fail("jg_sw_scan: threads must be a multiple of 32 with threads * 16 >= max_n");
+  if (threads < 32 || threads > 1024 || threads % 32 != 0 || static_cast<long long>(threads) * jg::kSwRows < max_rows)
+    return fail("jg_sw_scan: threads must be a multiple of 32 with threads * 16 >= max_rows");
   JG_CUDA(cudaSetDevice(ctx->device));
   const jg::SwSeq seq{d_codes, d_valid};
   const jg::SwScores sc{2, -100, 0, 100, 5};                       // utils/termini.py:113, 121-122
-  const size_t smem = static_cast<size_t>(10) * threads * 4 + ((max_n + 15) / 16) * 16;
+  const size_t smem = static_cast<size_t>(10) * threads * 4 + ((max_cols + 15) / 16) * 16;
   jg::sw_scan_kernel<<<n_jobs, threads, smem, ctx->stream>>>(seq, reinterpret_cast<const jg::SwJob*>(d_jobs), sc, d_out);
   ctx->launches += 1;
   JG_CUDA(cudaGetLastError());

@@ -41,9 +41,11 @@ __device__ __forceinline__ int sw_sub(int a, int b, const SwScores& sc) {
   return (a > 3 || b > 3) ? sc.wild : (a == b ? sc.match : sc.mismatch);
 }
 
-// job = (front start, rear start, n, inverted?): query[i] = seq[q0 + i];
-// ref[j] = seq[r0 + j] (direct) or complement(seq[r0 + n - 1 - j]) (inverted)
-struct SwJob { long long q0, r0; int n, inverted; };
+// job = (query start, reference start, n, inverted?, nq): query[i] = seq[q0 + i], i < nq (nq = 0 means n: the
+// square terminal-repeat jobs); ref[j] = seq[r0 + j] (direct) or complement(seq[r0 + n - 1 - j]) (inverted), j < n.
+// Rectangular jobs are the att-site scans around a prophage region (postprocess/prophages.py:771-800).
+struct SwJob { long long q0, r0; int n, inverted, nq, reserved; };
+__device__ __forceinline__ int sw_rows(const SwJob& jb) { return jb.nq > 0 ? jb.nq : jb.n; }
 
 __device__ __forceinline__ int sw_ref_base(const SwSeq& s, const SwJob& jb, int j) {
   if (!jb.inverted) return sw_base(s, jb.r0 + j);
@@ -124,7 +126,7 @@ __global__ void sw_scan_kernel(SwSeq seq, const SwJob* __restrict__ jobs, SwScor
   int* s_red = s_sw + 6 * T;                                 // 4 * T ints
   uint8_t* s_ref = reinterpret_cast<uint8_t*>(s_sw + 10 * T);
   int best[4];
-  sw_fill<false>(seq, jb, sc, jb.n, jb.n, s_ref, s_slot, nullptr, best);
+  sw_fill<false>(seq, jb, sc, sw_rows(jb), jb.n, s_ref, s_slot, nullptr, best);
   const int t = threadIdx.x;
   for (int k = 0; k < 4; ++k) s_red[k * T + t] = best[k];
   __syncthreads();
@@ -139,7 +141,9 @@ __global__ void sw_scan_kernel(SwSeq seq, const SwJob* __restrict__ jobs, SwScor
   }
 }
 
-struct SwTraceJob { SwJob job; int end_i, end_j; long long dirs_off; };
+// ops_off >= 0: the traceback also writes one byte per alignment column at scratch + ops_off, from the LAST column
+// backwards (1 = pair, 2 = gap in the query line, 3 = gap in the reference line); at most end_i + end_j + 2 bytes.
+struct SwTraceJob { SwJob job; int end_i, end_j; long long dirs_off, ops_off; };
 
 // out[job] = {alignment columns, gaps in the query line, gaps in the reference line, identities}
 __global__ void sw_trace_kernel(SwSeq seq, const SwTraceJob* __restrict__ jobs, SwScores sc, uint8_t* __restrict__ scratch,
@@ -157,6 +161,7 @@ __global__ void sw_trace_kernel(SwSeq seq, const SwTraceJob* __restrict__ jobs, 
   __syncthreads();
   if (threadIdx.x == 0) {
     int i = tj.end_i, j = tj.end_j, cols = 0, qgaps = 0, rgaps = 0, iden = 0, state = 0;   // 0 H, 1 E, 2 F
+    uint8_t* ops = tj.ops_off >= 0 ? scratch + tj.ops_off : nullptr;
     while (i >= 0 && j >= 0) {
       const uint32_t d = dirs[static_cast<long long>(i) * n_cols + j];
       if (state == 0) {
@@ -165,15 +170,18 @@ __global__ void sw_trace_kernel(SwSeq seq, const SwTraceJob* __restrict__ jobs, 
         if (src == 1u) {
           const int a = sw_base(seq, tj.job.q0 + i), b = s_ref[j];
           iden += (a < 4 && a == b) ? 1 : 0;
+          if (ops) ops[cols] = 1;
           ++cols; --i; --j;
         } else {
           state = src == 2u ? 1 : 2;
         }
       } else if (state == 1) {        // reference base against a gap in the query
+        if (ops) ops[cols] = 2;
         ++cols; ++qgaps;
         state = (d & 4u) ? 1 : 0;
         --j;
       } else {                        // query base against a gap in the reference
+        if (ops) ops[cols] = 3;
         ++cols; ++rgaps;
         state = (d & 8u) ? 2 : 0;
         --i;

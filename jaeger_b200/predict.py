@@ -214,6 +214,15 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                 rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
         (out_dir / f"{base}_prophage_regions.tsv").write_text("\n".join(rows) + "\n")
         result["prophage_regions"] = regions
+        # att sites at the region ends -> <base>_prophages/prophages_jaeger.tsv (predict.py:372-376, 430-437;
+        # postprocess/prophages.py:706-873 without the gene-call refinement)
+        from .termini import prophage_report_loaded, write_prophage_report
+        t_att = time.time()
+        full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
+        report = prophage_report_loaded(engine, full, regions, fsize, stride)
+        write_prophage_report(report, out_dir / f"{base}_prophages")
+        result["prophage_report"] = report
+        logger.info(f"prophage att-site report ({len(report)} regions) in {time.time() - t_att:.2f} s")
     if kwargs.get("getsequences"):                                        # predict.py:444-455
         from .postprocess import write_fasta_from_results
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()

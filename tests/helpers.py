@@ -33,3 +33,52 @@ def to_dyt(cfg: dict) -> dict:
         elif layer["name"] == "residual_block":
             layer["config"]["norm_type"] = "masked_dyt"
     return cfg
+
+
+_COMP = {"A": "T", "T": "A", "C": "G", "G": "C"}
+
+
+def _revcomp(s: str) -> str:
+    return "".join(_COMP[b] for b in reversed(s))
+
+
+def repeat_contigs():
+    """Contigs with planted terminal repeats: exact direct / inverted, one mismatch, a gap in either line, a long
+    (LTR) repeat, N runs, soft-masked letters, a header with a comma, one record below fsize."""
+    rng = np.random.default_rng(77)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    core, long_core = rnd(120), rnd(700)
+    mut = core[:60] + ("A" if core[60] != "A" else "C") + core[61:]
+    return [("plain", rnd(3000)), ("dtr", core + rnd(3000) + core), ("itr,comma", core + rnd(2500) + _revcomp(core)),
+            ("mismatch", core + rnd(2500) + mut), ("gap", core + rnd(2500) + core[:60] + core[62:]),
+            ("qgap", core[:58] + core[59:] + rnd(2600) + core), ("ltr", long_core + rnd(30000) + long_core),
+            ("short", rnd(900)), ("nrun", "N" * 30 + core + rnd(2200) + core + "n" * 10),
+            ("lower", core.lower() + rnd(2400) + core), ("long", rnd(20) + core + rnd(48000) + core + rnd(33)),
+            ("both", core + rnd(1200) + _revcomp(core[:80]) + rnd(900) + core[:100])]
+
+
+def prophage_genomes():
+    """(records, prophage coordinates) for the att-site search (fsize 2000, stride 1500): a 520 kbp genome with four
+    called regions -- an exact 30-bp direct repeat across the region ends, a 120-bp inverted repeat with one mismatch
+    (traced), a 160-bp direct repeat with a deleted base (traced, gap) around a region that is 23 % N (reject), a region at the contig start
+    without a planted repeat -- a second > 500 kbp genome without regions, and a 400 kbp contig whose regions the
+    500 000 bp rule skips.  Coordinates are window-index ranges + scores, as `segment` returns them."""
+    rng = np.random.default_rng(123)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    g = list(rnd(520_000))
+
+    def put(pos, s):
+        g[pos:pos + len(s)] = list(s)
+    a30, b120, c160 = rnd(30), rnd(120), rnd(160)
+    # region windows [100, 104): raw 150000 .. 156500, off_set 1625 -> left [146000, 151625), right [154875, 160500)
+    put(149_000, a30); put(157_000, a30)
+    # region windows [200, 221): raw 300000 .. 332000, off_set 2000 -> left [296000, 302000), right [330000, 336000)
+    mut = b120[:60] + ("A" if b120[60] != "A" else "C") + b120[61:]
+    put(297_500, b120); put(333_000, _revcomp(mut))
+    # region windows [300, 303): raw 450000 .. 455000, off_set 1250 -> left [446000, 451250), right [453750, 459000)
+    put(447_000, c160); put(457_100, c160[:70] + c160[71:]); put(451_300, "N" * 2400)
+    g[448_500] = "n"
+    recs = [("genome1,with,commas", "".join(g)), ("genome2", rnd(501_000)), ("plasmid", rnd(400_000))]
+    cords = {"genome1___with___commas": [[[100, 104], [200, 221], [300, 303], [0, 3]], np.array([4.25, 7.5, 2.125, 1.75])],
+             "plasmid": [[[10, 20]], np.array([3.0])]}
+    return recs, cords

@@ -477,6 +477,11 @@ def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
     assert got["ranges"] == want_r
     assert np.allclose(got["scores"], want_s, atol=1e-6)
     assert (tmp_path / "out" / "standin" / "genome_prophage_regions.tsv").exists()
+    # the att-site report: one row per called region, raw coordinates = [start*stride, (end-1)*stride + fsize]
+    rep = res["prophage_report"]
+    assert len(rep) == len(want_r)
+    assert rep["raw_start"].tolist() == [s * 1500 for s, _ in want_r] and rep["raw_end"].tolist() == [(e - 1) * 1500 + 2000 for _, e in want_r]
+    assert (tmp_path / "out" / "standin" / "genome_prophages" / "prophages_jaeger.tsv").exists() == (len(want_r) > 0)
 
 
 def test_crf_viterbi_decoding_vs_reference_golden(standin):
@@ -544,18 +549,8 @@ def test_legacy_postprocess_tables_vs_reference_golden(tmp_path):
 
 
 def _repeat_contigs():
-    from oracle import termini as ot
-    rng = np.random.default_rng(77)
-    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
-    core, long_core = rnd(120), rnd(700)
-    mut = core[:60] + ("A" if core[60] != "A" else "C") + core[61:]
-    recs = [("plain", rnd(3000)), ("dtr", core + rnd(3000) + core), ("itr,comma", core + rnd(2500) + ot.reverse_complement(core)),
-            ("mismatch", core + rnd(2500) + mut), ("gap", core + rnd(2500) + core[:60] + core[62:]),
-            ("qgap", core[:58] + core[59:] + rnd(2600) + core), ("ltr", long_core + rnd(30000) + long_core),
-            ("short", rnd(900)), ("nrun", "N" * 30 + core + rnd(2200) + core + "n" * 10),
-            ("lower", core.lower() + rnd(2400) + core), ("long", rnd(20) + core + rnd(48000) + core + rnd(33)),
-            ("both", core + rnd(1200) + ot.reverse_complement(core[:80]) + rnd(900) + core[:100])]
-    return recs
+    from tests.helpers import repeat_contigs
+    return repeat_contigs()
 
 
 def test_terminal_repeat_scan_vs_oracle(standin):
@@ -583,24 +578,88 @@ def test_terminal_repeat_scan_vs_oracle(standin):
                 assert gv == v, (w["contig_id"], k, gv, v)
         kinds.append(w["terminal_repeats"])
     assert kinds[:7] == [None, "DTR", "ITR", "DTR", "DTR", "DTR", "LTR_DTR"]
-    # raw scan parity on random pairs (ties between equal maxima resolved identically)
-    from jaeger_b200.termini import JOB, _run_scan
+    # raw scan parity on random pairs, square and rectangular (ties between equal maxima resolved identically)
+    from jaeger_b200.termini import JOB, TRACE_JOB, _run_scan, _run_trace, alignment_lines
     rng = np.random.default_rng(5)
     seq = "".join(rng.choice(list("ACGTN"), 6000, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
-    jobs = np.zeros(8, dtype=JOB)
-    spans = [(0, 400, 0), (0, 400, 1), (100, 517, 0), (100, 517, 1), (0, 1000, 0), (3, 33, 0), (2000, 1999, 1), (50, 1, 0)]
-    for k, (q0, n, inv) in enumerate(spans):
-        jobs[k] = (q0, 6000 - n - q0 // 2, n, inv)
+    # (q0, n, inverted, nq): nq = 0 -> square
+    spans = [(0, 400, 0, 0), (0, 400, 1, 0), (100, 517, 0, 0), (100, 517, 1, 0), (0, 1000, 0, 0), (3, 33, 0, 0), (2000, 1999, 1, 0),
+             (50, 1, 0, 0), (10, 700, 0, 300), (10, 300, 1, 900), (500, 1200, 1, 17), (0, 40, 0, 1500), (7, 1, 0, 5), (9, 5, 1, 1)]
+    jobs = np.zeros(len(spans), dtype=JOB)
+    for k, (q0, n, inv, nq) in enumerate(spans):
+        jobs[k] = (q0, 6000 - n - q0 // 2, n, inv, nq, 0)
     with torch.cuda.stream(eng._stream()):
         codes, valid = eng.pack(eng._h2d(np.frombuffer(seq.encode(), np.uint8).copy()))
     res = _run_scan(eng, codes, valid, jobs)
-    for k, (q0, n, inv) in enumerate(spans):
+    for k, (q0, n, inv, nq) in enumerate(spans):
         r0 = 6000 - n - q0 // 2
         ref = seq[r0:r0 + n]
-        a = ot.sw_align(seq[q0:q0 + n], ot.reverse_complement(ref) if inv else ref)
+        a = ot.sw_align(seq[q0:q0 + (nq or n)], ot.reverse_complement(ref) if inv else ref)
         assert (res[k, 0], res[k, 1], res[k, 2]) == (a["score"], a["end_query"], a["end_ref"]), (k, res[k], a)
         if a["score"] < 104:
             assert res[k, 3] == a["cols"], (k, res[k], a)
+
+
+def test_sw_trace_operations_give_the_alignment_lines(standin):
+    """Rectangular traced jobs: counts and the per-column operations of jg_sw_trace rebuild exactly the oracle's
+    traceback.query / traceback.ref lines (gaps in either line, mismatches, direct and inverted, lower-case letters)."""
+    from jaeger_b200.termini import JOB, TRACE_JOB, JOB_FIELDS, _run_scan, _run_trace, alignment_lines
+    from oracle import termini as ot
+    _, _, eng = standin
+    rng = np.random.default_rng(21)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    core = rnd(400)
+    mut = lambda s, i: s[:i] + ("A" if s[i] != "A" else "C") + s[i + 1:]
+    pairs = [(rnd(300) + core + rnd(200), rnd(100) + core[:150] + core[152:] + rnd(350), 0),               # gap in the ref line
+             (rnd(50) + core[:200] + core[203:] + rnd(700), rnd(900) + core + rnd(20), 0),                    # gap in the query line
+             (rnd(10) + mut(core, 199).lower() + rnd(10), rnd(400) + core + rnd(333), 1),                     # mismatch, inverted, lower-case query
+             (rnd(77) + core + rnd(5), rnd(31) + mut(core[:120], 60) + "GT" + core[120:250] + core[254:] + rnd(600), 1)]
+    parts, jobs, pos = [], np.zeros(len(pairs), dtype=JOB), 0
+    for k, (q, r, inv) in enumerate(pairs):
+        stored = ot.reverse_complement(r) if inv else r
+        jobs[k] = (pos, pos + len(q) + 5, len(r), inv, len(q), 0)
+        parts += [q, "NNNNN", stored, "N" * 7]
+        pos += len(q) + 5 + len(r) + 7
+    host = np.frombuffer("".join(parts).encode(), np.uint8).copy()
+    with torch.cuda.stream(eng._stream()):
+        codes, valid = eng.pack(eng._h2d(host))
+    res = _run_scan(eng, codes, valid, jobs)
+    tj = np.zeros(len(pairs), dtype=TRACE_JOB)
+    for f in JOB_FIELDS:
+        tj[f] = jobs[f]
+    tj["end_i"], tj["end_j"] = res[:, 1], res[:, 2]
+    counts, ops = _run_trace(eng, codes, valid, tj, want_ops=True)
+    counts2, none = _run_trace(eng, codes, valid, tj.copy())
+    assert none is None and np.array_equal(counts, counts2)
+    for k, (q, r, inv) in enumerate(pairs):
+        a = ot.sw_align(q, r)
+        assert a["score"] >= 104 and a["qgaps"] + a["rgaps"] + (a["cols"] - a["iden"]) >= 1
+        assert tuple(res[k, :3]) == (a["score"], a["end_query"], a["end_ref"]), (k, res[k])
+        assert tuple(counts[k]) == (a["cols"], a["qgaps"], a["rgaps"], a["iden"]), (k, counts[k], a)
+        assert alignment_lines(host, jobs[k], int(res[k, 1]), int(res[k, 2]), ops[k]) == (a["qline"], a["rline"]), k
+
+
+def test_prophage_att_report_vs_reference_golden(standin, tmp_path):
+    """SURVEY.md 8f-4 (att sites): the device att-site search + report for synthetic called regions equals, byte for
+    byte, the `prophages_jaeger.tsv` the reference's prophage_report wrote for the same genomes and coordinates with
+    its aligner stubbed by the oracle (tests/golden/make_termini_goldens.py) -- exact DTR, traced ITR with a mismatch,
+    traced DTR with a gap around a 23 %-N region (reject), a spontaneous 13-mer at the contig start."""
+    from jaeger_b200 import WindowSource
+    from jaeger_b200.termini import prophage_report_loaded, write_prophage_report
+    from tests.helpers import prophage_genomes
+    _, _, eng = standin
+    recs, cords = prophage_genomes()
+    regions = {k: {"ranges": v[0], "scores": v[1]} for k, v in cords.items()}
+    src = WindowSource(records=recs, fsize=2000, stride=1500)
+    rep = prophage_report_loaded(eng, src.load(), regions, 2000, 1500)
+    assert len(rep) == 4 and rep["att_type"].tolist() == ["DTR", "ITR", "DTR", "DTR"]
+    write_prophage_report(rep, tmp_path / "x_prophages")
+    assert (tmp_path / "x_prophages" / "prophages_jaeger.tsv").read_text() == (G / "prophages_jaeger.tsv").read_text()
+    # nothing on contigs <= 500 kbp, no file without rows (prophages.py:759, 866)
+    none = prophage_report_loaded(eng, src.load(), {"plasmid": regions["plasmid"]}, 2000, 1500)
+    assert len(none) == 0
+    write_prophage_report(none, tmp_path / "y_prophages")
+    assert not (tmp_path / "y_prophages").exists()
 
 
 def test_driver_tsv_carries_terminal_repeat_columns(standin, tmp_path):

@@ -126,3 +126,69 @@ def test_write_fasta_from_results(tmp_path):
             want += f">{name}\n" + "".join(seq[i:i + 70] + "\n" for i in range(0, len(seq), 70))
     assert n == 3 and (tmp_path / "o.fa").read_text() == want
     assert pp.write_fasta_from_results(WindowSource(records=recs).load(), tmp_path / "missing.tsv", tmp_path / "e.fa") == 0
+
+
+def _same(a, b):
+    if b is None:
+        return a is None or a != a
+    if isinstance(b, float):
+        return a is not None and abs(float(a) - b) < 1e-12
+    return a == b
+
+
+def test_termini_table_oracle_vs_reference_golden():
+    """The reference's scan_for_terminal_repeats (utils/termini.py:91-189) run with the aligner stubbed by the oracle's
+    sw_align (tests/golden/make_termini_goldens.py): the oracle's restatement of the flow around the aligner -- scan
+    length, ITR / DTR choice, > 12 column rule, coordinates, front / rear strings (rear reverse-complemented back
+    for an ITR) -- gives the same table."""
+    from oracle import termini as ot
+    from tests.helpers import repeat_contigs
+    want = json.loads((G / "termini_table.json").read_text())
+    got = sorted(ot.scan_for_terminal_repeats(repeat_contigs(), 2000), key=lambda r: r["contig_id"])
+    assert [r["contig_id"] for r in got] == [r["contig_id"] for r in want] and len(want) == 11
+    for g, w in zip(got, want):
+        for k, v in w.items():
+            assert _same(g[k], v), (w["contig_id"], k, g[k], v)
+    by = {r["contig_id"]: r for r in want}
+    itr = by["itr___comma"]                               # rear is given as the contig holds it: the reverse complement of front
+    assert itr["terminal_repeats"] == "ITR" and itr["rear"] == ot.reverse_complement(itr["front"]) and len(itr["front"]) == 120
+    assert by["gap"]["rear"].count("-") == 2 and by["qgap"]["front"].count("-") == 1
+
+
+def test_alignment_lines_from_traceback_operations():
+    """Host side of the `front` / `rear` / `attL` / `attR` strings: the letters are read off the loaded FASTA bytes
+    along the traceback operations the trace kernel writes (last column first)."""
+    from jaeger_b200.termini import JOB, alignment_lines, reverse_complement_bytes
+    from oracle import termini as ot
+    rng = np.random.default_rng(8)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    core = rnd(150)
+    left = rnd(40) + core + rnd(25)
+    right_plain = rnd(10) + core[:70] + core[72:] + rnd(60)               # two bases missing from the reference line
+    right_q = rnd(33) + core[:60] + "TG" + core[60:] + rnd(5)             # two extra bases: gap in the query line
+    for right, inverted in ((right_plain, 0), (right_q, 0), (right_plain, 1), ("acgtn" + right_q, 1)):
+        stored = ot.reverse_complement(right) if inverted else right      # what the contig holds at r0
+        host = np.frombuffer(("NN" + left + "NNN" + stored).encode(), np.uint8)
+        a = ot.sw_align(left, ot.reverse_complement(stored) if inverted else stored)
+        assert a["qgaps"] + a["rgaps"] >= 1 and a["cols"] > 140
+        ops = np.array([2 if q == "-" else 3 if r == "-" else 1 for q, r in zip(a["qline"], a["rline"])], np.uint8)[::-1]
+        job = np.array([(2, 2 + len(left) + 3, len(stored), inverted, len(left), 0)], dtype=JOB)[0]
+        ql, rl = alignment_lines(host, job, a["end_query"], a["end_ref"], ops)
+        assert (ql, rl) == (a["qline"], a["rline"])
+    assert reverse_complement_bytes(np.frombuffer(b"ACGTNacgtRYx-", np.uint8)).tobytes().decode() == ot.reverse_complement("ACGTNacgtRYx-")
+
+
+def test_prophage_report_oracle_vs_reference_golden(tmp_path):
+    """The reference's prophage_report (postprocess/prophages.py:706-873, refined_boundaries=None) run with the
+    aligner stubbed by the oracle's sw_align: the oracle's restatement of the flank coordinates, the ITR / DTR choice,
+    get_prophage_alignment_summary's arithmetic, n% / gc% / reject and the TSV formatting gives the same file."""
+    import pandas as pd
+    from oracle import termini as ot
+    from tests.helpers import prophage_genomes
+    recs, cords = prophage_genomes()
+    rows = ot.prophage_report(recs, cords, fsize=2000, stride=1500)
+    df = pd.DataFrame(rows)
+    df["contig_id"] = df["contig_id"].apply(lambda x: x.replace("___", ","))
+    df.to_csv(tmp_path / "p.tsv", sep="\t", index=False, float_format="%.3f")
+    assert (tmp_path / "p.tsv").read_text() == (G / "prophages_jaeger.tsv").read_text()
+    assert [r["att_type"] for r in rows] == ["DTR", "ITR", "DTR", "DTR"] and rows[2]["reject"] is True
