@@ -22,7 +22,8 @@
  *   jg_smooth_scores     postprocess/prophages.py:126-151 (softmax + width-4 box sum)
  *   jg_segment_scores    postprocess/prophages.py:554-595 (KernelCPD/PELT at pen 1..9)
  *   jg_viterbi_decode    postprocess/helpers.py:393-449 (--crf window decoding)
- *   jg_sw_scan / jg_sw_trace utils/termini.py:103-131 (terminal-repeat Smith-Waterman scans)
+ *   jg_refine_contigs    postprocess/refinement.py:39-213 (--refine window labels + per-contig aggregation)
+ *   jg_sw_scan / jg_sw_trace utils/termini.py:103-131 (terminal-repeat scans), postprocess/prophages.py:771-800 (att sites)
  *   jg_legacy_reliability postprocess/helpers.py:558-565 + collect.py:121-123 (legacy reliability_score)
  *
  * Conventions: every function returns 0 on success and a non-zero code on failure, with a
@@ -210,6 +211,18 @@ int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t mi
  * Outputs: d_path [n_windows] decoded class per window, d_counts [n_contigs][n_cls]. n_cls <= 8. */
 int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int32_t n_contigs, int64_t n_windows,
                       int32_t n_cls, const double* d_costs, int32_t* d_path, int32_t* d_counts);
+
+/* Post-hoc refinement (`jaeger predict --refine`): replaces add_score_features + refine + aggregate_contig
+ * (postprocess/refinement.py:39-73, 97-137, 140-213) as driven by _build_refined_contig_df
+ * (commands/predict.py:115-155).  Score columns are positional: 0 phage, 1 virus, 2 archaea, 3 bacteria,
+ * 4 plasmid, 5 eukarya (n_cls >= 6).  d_tau [12] float64: per-class logit thresholds, then margin thresholds
+ * (the calibration file's `taus`; -inf disables).  mode 0 gated / 1 weighted / 2 unweighted; merge_share 0.5
+ * ("half") or 1.0 ("full").  Outputs: d_label [n_windows] (0..5 class, 6 unknown, 7 bacteria_or_plasmid,
+ * 8 virus_any), d_margin [n_windows] float64, d_sums [n_contigs][6] float64, d_stats [n_contigs][2] =
+ * {windows used, merged-label windows}, d_total_weight [n_contigs] float64. */
+int jg_refine_contigs(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int64_t n_contigs, int64_t n_windows,
+                      int32_t n_cls, const double* d_tau, int32_t merge_bp, int32_t merge_pv, int32_t mode, double merge_share,
+                      uint8_t* d_label, double* d_margin, double* d_sums, int32_t* d_stats, double* d_total_weight);
 
 /* Legacy `default` model reliability: replaces ood_predict_default(..., type "sklearn")
  * (postprocess/helpers.py:558-565; parameters loaded at commands/predict_legacy.py:99-109) per

@@ -63,6 +63,7 @@ _SIGNATURES = {
                                         _P, c_int32, _P, _P]),
     "jg_sw_scan": (c_int32, [c_void_p, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P]),
     "jg_sw_trace": (c_int32, [c_void_p, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "jg_refine_contigs": (c_int32, [c_void_p, _P, _P, c_int64, c_int64, c_int32, _P, c_int32, c_int32, c_int32, c_double, _P, _P, _P, _P, _P]),
     "jg_viterbi_decode": (c_int32, [c_void_p, _P, _P, c_int32, c_int64, c_int32, _P, _P, _P]),
 }
 EXPORTED = tuple(_SIGNATURES)

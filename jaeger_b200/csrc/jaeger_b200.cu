@@ -893,6 +893,24 @@ int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offse
   return 0;
 }
 
+int jg_refine_contigs(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int64_t n_contigs, int64_t n_windows,
+                      int32_t n_cls, const double* d_tau, int32_t merge_bp, int32_t merge_pv, int32_t mode, double merge_share,
+                      uint8_t* d_label, double* d_margin, double* d_sums, int32_t* d_stats, double* d_total_weight) {
+  if (n_cls < jg::kRefineClasses) return fail("jg_refine_contigs: the refinement layer needs the 6 score columns");
+  if (mode < 0 || mode > 2) return fail("jg_refine_contigs: mode must be 0 (gated), 1 (weighted) or 2 (unweighted)");
+  if (n_contigs <= 0 || n_windows <= 0) return 0;
+  JG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  jg::refine_windows_kernel<<<grid_for(n_windows, 256, ctx->num_sms), 256, 0, st>>>(d_logits, n_windows, n_cls, d_tau, merge_bp,
+                                                                                   merge_pv, d_label, d_margin);
+  jg::refine_contigs_kernel<<<grid_for(n_contigs * 32, 256, ctx->num_sms, 16), 256, 0, st>>>(
+      d_logits, n_cls, d_label, d_margin, reinterpret_cast<const long long*>(d_offsets), n_contigs, mode, merge_share, d_sums,
+      d_stats, d_total_weight);
+  ctx->launches += 2;
+  JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int jg_legacy_reliability(jg_ctx* ctx, const float* d_embedding, int64_t n_windows, int32_t dim, const float* d_batch_mean,
                           const float* d_batch_std, const double* d_coef, double intercept, double cal_a, double cal_b,
                           const int64_t* d_offsets, int32_t n_contigs, double* d_window_p0, double* d_contig_mean) {

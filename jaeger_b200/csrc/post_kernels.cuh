@@ -335,4 +335,103 @@ __global__ void segment_mean_f64_kernel(const double* __restrict__ v, const long
   }
 }
 
+// ---- post-hoc refinement (`--refine`): postprocess/refinement.py:39-247 ---------------------------------------
+// Score columns are positional (commands/predict.py:140): 0 phage, 1 virus, 2 archaea, 3 bacteria, 4 plasmid,
+// 5 eukarya.  Window labels: 0..5 = class, 6 = unknown, 7 = bacteria_or_plasmid, 8 = virus_any.
+constexpr int kRefineClasses = 6;
+constexpr int kRefineUnknown = 6, kRefineBactPlasmid = 7, kRefineVirusAny = 8;
+
+// positions -1 / -2 of a stable ascending argsort of 6 values (np.argsort on a row; ties keep index order)
+__device__ __forceinline__ void refine_top2(const double (&z)[kRefineClasses], int& last, int& second) {
+  double v[kRefineClasses];
+  int id[kRefineClasses];
+#pragma unroll
+  for (int k = 0; k < kRefineClasses; ++k) { v[k] = z[k]; id[k] = k; }
+#pragma unroll
+  for (int a = 1; a < kRefineClasses; ++a) {          // insertion sort with a strict comparison: stable
+#pragma unroll
+    for (int b = a; b > 0; --b) {
+      if (v[b] < v[b - 1]) {
+        const double tv = v[b]; v[b] = v[b - 1]; v[b - 1] = tv;
+        const int ti = id[b]; id[b] = id[b - 1]; id[b - 1] = ti;
+      }
+    }
+  }
+  last = id[kRefineClasses - 1];
+  second = id[kRefineClasses - 2];
+}
+
+// add_score_features + refine (refinement.py:39-73, 97-137): one thread per window, float64 like the reference's
+// NumPy arithmetic on the widened logits.  tau[0..5] = per-class logit thresholds, tau[6..11] = margin thresholds.
+__global__ void refine_windows_kernel(const float* __restrict__ logits, long long n_windows, int n_cls,
+                                      const double* __restrict__ tau, int merge_bp, int merge_pv,
+                                      uint8_t* __restrict__ label, double* __restrict__ margin_out) {
+  for (long long w = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; w < n_windows;
+       w += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double z[kRefineClasses];
+#pragma unroll
+    for (int k = 0; k < kRefineClasses; ++k) z[k] = static_cast<double>(logits[w * n_cls + k]);
+    int top = 0;                                        // np.argmax: first maximum
+#pragma unroll
+    for (int k = 1; k < kRefineClasses; ++k) top = z[k] > z[top] ? k : top;
+    int last, second;
+    refine_top2(z, last, second);
+    const double top_logit = z[last], margin = z[last] - z[second];
+    const double tau_logit = tau[top], tau_margin = tau[kRefineClasses + top];
+    int lab = top;
+    const bool low_margin = margin < tau_margin;
+    if (merge_bp && low_margin && ((top == 3 && second == 4) || (top == 4 && second == 3))) lab = kRefineBactPlasmid;
+    if (merge_pv && low_margin && ((top == 0 && second == 1) || (top == 1 && second == 0))) lab = kRefineVirusAny;
+    if (lab < kRefineClasses && (top_logit < tau_logit || low_margin)) lab = kRefineUnknown;
+    label[w] = static_cast<uint8_t>(lab);
+    margin_out[w] = margin;
+  }
+}
+
+// aggregate_contig (refinement.py:140-213): one warp per contig, segmented float64 sums of score * weight *
+// class multiplier.  mode 0 gated (drop unknown, weight 1), 1 weighted (drop unknown, weight = max(margin, 0)),
+// 2 unweighted (all windows, weight 1).  sums [n][6], stats [n][2] = {windows used, merged-label windows},
+// total_weight [n].  Lanes add their strided partial sums, then a fixed butterfly: deterministic.
+__global__ void refine_contigs_kernel(const float* __restrict__ logits, int n_cls, const uint8_t* __restrict__ label,
+                                      const double* __restrict__ margin, const long long* __restrict__ offsets,
+                                      long long n_contigs, int mode, double merge_share, double* __restrict__ sums,
+                                      int* __restrict__ stats, double* __restrict__ total_weight) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long c = warp0; c < n_contigs; c += n_warps) {
+    double acc[kRefineClasses] = {0, 0, 0, 0, 0, 0};
+    double wsum = 0.0;
+    int used = 0, merged = 0;
+    for (long long w = offsets[c] + lane; w < offsets[c + 1]; w += 32) {
+      const int lab = label[w];
+      if (mode != 2 && lab == kRefineUnknown) continue;
+      const double m = margin[w];
+      const double wt = mode == 1 ? (m > 0.0 ? m : 0.0) : 1.0;
+      const bool is_merged = lab == kRefineBactPlasmid || lab == kRefineVirusAny;
+#pragma unroll
+      for (int k = 0; k < kRefineClasses; ++k) {
+        const bool member = lab == kRefineBactPlasmid ? (k == 3 || k == 4) : (k == 0 || k == 1);
+        const double mult = is_merged ? (member ? merge_share : 0.0) : 1.0;
+        acc[k] += static_cast<double>(logits[w * n_cls + k]) * wt * mult;
+      }
+      wsum += wt; ++used; merged += is_merged;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < kRefineClasses; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, off);
+      used += __shfl_xor_sync(0xffffffffu, used, off);
+      merged += __shfl_xor_sync(0xffffffffu, merged, off);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kRefineClasses; ++k) sums[c * kRefineClasses + k] = acc[k];
+      stats[c * 2] = used; stats[c * 2 + 1] = merged;
+      total_weight[c] = wsum;
+    }
+  }
+}
+
 }  // namespace jg

@@ -144,8 +144,9 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
     }
 
 
-def generate_summary(data: dict[str, Any], labels, indices):
-    """Column order of collect.py:472-518 (+ left join of the terminal-repeat columns, 527-532)."""
+def generate_summary(data: dict[str, Any], labels, indices, refined_contig=None):
+    """Column order of collect.py:472-518 (+ left join of the terminal-repeat columns, 527-532, and of the refined
+    contig calls of `--refine`, 534-550)."""
     import pandas as pd
     class_map = {int(k): v for k, v in zip(indices, labels)}
     n = len(data["headers"])
@@ -170,6 +171,9 @@ def generate_summary(data: dict[str, Any], labels, indices):
     if data.get("repeats") is not None:
         df = pd.merge(left=df, right=data["repeats"][["contig_id", "terminal_repeats", "repeat_length"]],
                       on="contig_id", how="left")
+    if refined_contig is not None:
+        from .refine import merge_into_summary
+        df = merge_into_summary(df, refined_contig)
     df["contig_id"] = df["contig_id"].str.replace("___", ",")
     return df
 

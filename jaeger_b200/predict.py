@@ -4,8 +4,7 @@ Mirrors the reference driver `commands/predict.py:488-861` for the options that 
 path (the option names and defaults are the reference CLI's, cli.py:122-371, including the experimental --crf family): same model
 registry (`config.json["model_paths"]`, scanned like `AvailableModels`, utils/misc.py:334-392),
 same output locations `<-o>/<model_id>/<base>.tsv` and `<base>_phages.tsv`, same `--overwrite`
-rule, same prophage table source.  Options outside the path (--refine, plots, --onnx ...)
-are not accepted.
+rule, same prophage table source, same `--refine` family.  Options outside the path (plots, --onnx ...) are not accepted.
 
     python -m jaeger_b200.predict -i contigs.fasta -o out -m jaeger_xxx_1.4M_fragment --config config.json
     python -m jaeger_b200.predict -i contigs.fasta -o out -m standin      # random-init stand-in architecture
@@ -175,7 +174,25 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     data = contig_table(engine, y_pred, fsize, term_repeats=term, crf_switch_cost=crf_cost,
                         crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix) if y_pred else None
     cm = engine.class_map
-    df = generate_summary(data, cm["class"], cm["index"]) if data else None
+    refined = None
+    if kwargs.get("refine") and data:                                          # predict.py:310-335
+        from .refine import load_refinement, refined_contig_table
+        refine_path = Path(kwargs["refine_file"]) if kwargs.get("refine_file") else (
+            Path(info[model_name]["graph"]).parent / f"{model_name}_refine.yaml" if model_name != "standin" else None)
+        if refine_path is not None and refine_path.exists():
+            try:
+                refine_cfg = load_refinement(refine_path, expect_model=model_name)
+                refined = refined_contig_table(engine, data["headers"], data["predictions"], data["offsets"], refine_cfg["taus"],
+                                               mode=kwargs.get("refine_mode", "gated"), min_windows=int(kwargs.get("refine_min_windows", 3)),
+                                               merge_split=kwargs.get("refine_merge_split", "half"),
+                                               allow_merged_contig_call=bool(kwargs.get("refine_allow_merged_contig_call", False)),
+                                               contig_hedge_margin=float(kwargs.get("refine_contig_hedge_margin", 1.0)))
+                logger.info(f"Applied refinement calibration from {refine_path}")
+            except Exception as e:
+                logger.warning(f"Refinement failed: {e}; using default predictions")
+        else:
+            logger.warning(f"No refinement calibration found at {refine_path}; using default predictions")
+    df = generate_summary(data, cm["class"], cm["index"], refined_contig=refined) if data else None
     regions = None
     if kwargs.get("prophage") and data:
         regions = call_regions(engine, data, cm, fsize, stride, lc=int(kwargs.get("lc", 500_000)),
@@ -254,6 +271,13 @@ def main(argv=None) -> int:
     ap.add_argument("--dynamic-stride-threshold", dest="dynamic_stride_threshold", type=float, default=10.0)
     ap.add_argument("--dustmask", dest="dustmask", action="store_true", default=True)
     ap.add_argument("--no-dustmask", dest="dustmask", action="store_false")
+    ap.add_argument("--refine", action="store_true", help="apply post-hoc refinement using the model's <model>_refine.yaml")
+    ap.add_argument("--refine-file", dest="refine_file", default=None, help="calibration file to use instead of the model's own")
+    ap.add_argument("--refine-mode", dest="refine_mode", choices=["gated", "weighted", "unweighted"], default="gated")
+    ap.add_argument("--refine-min-windows", dest="refine_min_windows", type=int, default=3)
+    ap.add_argument("--refine-merge-split", dest="refine_merge_split", choices=["half", "full"], default="half")
+    ap.add_argument("--refine-allow-merged-contig-call", dest="refine_allow_merged_contig_call", action="store_true")
+    ap.add_argument("--refine-contig-hedge-margin", dest="refine_contig_hedge_margin", type=float, default=1.0)
     ap.add_argument("--crf", action="store_true", help="(experimental) joint Viterbi decoding of window labels")
     ap.add_argument("--crf-switch-cost", dest="crf_switch_cost", type=float, default=2.0)
     ap.add_argument("--crf-prior", dest="crf_prior", choices=["biological", "uniform"], default="biological")

@@ -841,3 +841,91 @@ def test_dustmask_kernel_vs_sdust_oracle(standin):
     for i, w in enumerate(wins):
         assert [int(y[f"meta_{k}"][i]) for k in (5, 6, 7, 8)] == [w.g, w.c, w.a, w.t], i
         assert y["meta_9"][i].decode() == w.gc_skew
+
+
+def _refine_case(seed=11):
+    rng = np.random.default_rng(seed)
+    n_win = [1, 2, 3, 5, 40, 7, 3, 150, 4, 33]
+    W = sum(n_win)
+    z = rng.normal(0.0, 1.6, (W, 6)).astype(np.float32)
+    z[10:14] = z[9]                                    # identical windows
+    z[20, 3] = z[20, 4] = z[20].max() + 1.0            # exact tie between bacteria and plasmid at the top
+    z[21, :] = 0.0                                     # all equal
+    z[22, 0] = z[22, 1] = 2.5; z[22, 2:] = -1.0        # phage / virus tie
+    z[60:75, 3] += 3.0; z[60:75, 4] += 2.8             # bacteria ~ plasmid: merged labels
+    z[100:130, 0] += 4.0; z[100:130, 1] += 3.9         # phage ~ virus
+    offsets = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
+    headers = [f"ctg___{i}" for i in range(len(n_win))]
+    from oracle import refine as orf
+    taus = {c: {"logit": 0.4 + 0.15 * i, "margin": 0.2 + 0.1 * i, "n": 50} for i, c in enumerate(orf.CLASSES)}
+    taus["archaea"] = {"logit": float("-inf"), "margin": float("-inf"), "n": 2}
+    return z, offsets, headers, taus
+
+
+@pytest.mark.parametrize("mode,split,allow", [("gated", "half", False), ("weighted", "full", True), ("unweighted", "half", True)])
+def test_refinement_layer_vs_oracle(standin, mode, split, allow):
+    """`--refine` (postprocess/refinement.py:39-247): per-window refined labels identical to the oracle's (ties between
+    exactly equal logits included), per-contig aggregated scores / margins within 1e-9 relative (float64 sums in a
+    different order), used / merged window counts, contig calls and the min_windows filter identical."""
+    from jaeger_b200.refine import LABELS, refine_contigs, refined_contig_table
+    from oracle import refine as orf
+    _, _, eng = standin
+    z, offsets, headers, taus = _refine_case()
+    feat = orf.add_score_features(z)
+    want_lab = orf.refine(feat, taus)
+    r = refine_contigs(eng, z, offsets, taus, mode, split)
+    assert [LABELS[i] for i in r["label"]] == want_lab.tolist()
+    assert np.array_equal(r["margin"], feat["margin"])                   # float64 difference of widened float32 logits: exact
+    assert {"unknown", "bacteria_or_plasmid", "virus_any"} <= set(want_lab.tolist())
+    ids = np.repeat(np.array(headers, dtype=object), np.diff(offsets))
+    want = orf.aggregate_contig(ids, z, want_lab, feat["margin"], mode=mode, min_windows=3, merge_split=split,
+                                allow_merged_contig_call=allow, contig_hedge_margin=5.0)
+    got = refined_contig_table(eng, headers, z, offsets, taus, mode=mode, min_windows=3, merge_split=split,
+                               allow_merged_contig_call=allow, contig_hedge_margin=5.0)
+    assert got["contig_id"].tolist() == list(want)
+    for row in got.to_dict("records"):
+        w = want[row["contig_id"]]
+        for k, v in w.items():
+            if isinstance(v, float):
+                assert row[k] == pytest.approx(v, rel=1e-9, abs=1e-12), (row["contig_id"], k)
+            else:
+                assert row[k] == v, (row["contig_id"], k, row[k], v)
+    if mode == "unweighted":
+        assert set(got["contig_call"]) & {"bacteria_or_plasmid", "virus_any"}
+
+
+def test_driver_refine_option_adds_the_refined_columns(standin, tmp_path):
+    """run_core(refine=True): the summary TSV gains contig_call, contig_top_logit, contig_margin, n_windows_used,
+    n_merged_windows (collect.py:534-550) for contigs with >= 3 informative windows; a calibration file for another
+    model is rejected with a warning and the default table is written (predict.py:329-330)."""
+    import pandas as pd
+    import yaml
+    from jaeger_b200.predict import run_core
+    from oracle import refine as orf
+    from tests.helpers import random_contigs
+    recs = random_contigs(3, [2000, 9000, 30000, 5200, 2600])
+    fa = tmp_path / "c.fasta"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
+    taus = {c: {"logit": -0.5, "margin": 0.01, "n": 100} for c in orf.CLASSES}
+    cal = tmp_path / "standin_refine.yaml"
+    cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "standin", "quantile": 0.05, "taus": taus}, sort_keys=False))
+    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
+                   refine=True, refine_file=str(cal), window_scores=True, terminal_repeats=False)
+    tsv = pd.read_csv(res["table"], sep="\t")
+    for col in ("contig_call", "contig_top_logit", "contig_margin", "n_windows_used", "n_merged_windows"):
+        assert col in tsv.columns
+    z = np.load(tmp_path / "o" / "standin" / "c_window_scores.npz", allow_pickle=True)
+    want = orf.build_refined_contig([str(h) for h in z["headers"]], list(z["predictions"]), taus, mode="gated", min_windows=3)
+    tsv = tsv.set_index("contig_id")
+    assert len(want) >= 2
+    for cid in tsv.index:
+        if cid in want:
+            assert tsv.loc[cid, "contig_call"] == want[cid]["contig_call"]
+            assert int(tsv.loc[cid, "n_windows_used"]) == want[cid]["n_windows_used"]
+            assert abs(float(tsv.loc[cid, "contig_margin"]) - want[cid]["contig_margin"]) < 2e-3
+        else:
+            assert pd.isna(tsv.loc[cid, "contig_call"])
+    cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "other", "taus": taus}))
+    res = run_core(input=str(fa), output=str(tmp_path / "o2"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
+                   refine=True, refine_file=str(cal), terminal_repeats=False)
+    assert "contig_call" not in pd.read_csv(res["table"], sep="\t").columns

@@ -3,6 +3,7 @@ import json
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from jaeger_b200 import postprocess as pp
 from jaeger_b200 import prophage as ppro
@@ -192,3 +193,53 @@ def test_prophage_report_oracle_vs_reference_golden(tmp_path):
     df.to_csv(tmp_path / "p.tsv", sep="\t", index=False, float_format="%.3f")
     assert (tmp_path / "p.tsv").read_text() == (G / "prophages_jaeger.tsv").read_text()
     assert [r["att_type"] for r in rows] == ["DTR", "ITR", "DTR", "DTR"] and rows[2]["reject"] is True
+
+
+def test_refinement_oracle_on_reference_known_answers(tmp_path):
+    """The known answers of the reference's tests/unit/test_refinement.py (the module itself needs polars and cannot
+    be imported here), restated against oracle/refine.py; each block names the reference test."""
+    from oracle import refine as orf
+    C = orf.CLASSES
+    # test_add_score_features_basic
+    z = np.zeros((1, 6), np.float32); z[0, 0] = 3.0; z[0, 1] = 1.0
+    f = orf.add_score_features(z)
+    assert f["top_class"][0] == "phage" and f["second_class"][0] == "virus"
+    assert f["top_logit"][0] == pytest.approx(3.0) and f["margin"][0] == pytest.approx(2.0)
+    assert 0.0 < f["top_prob"][0] <= 1.0 and f["entropy"][0] >= 0.0
+    taus = {c: {"logit": 1.0, "margin": 0.5} for c in C}
+    # test_refine_merges_before_abstain
+    z = np.zeros((1, 6), np.float32); z[0, 3] = 0.6; z[0, 4] = 0.4
+    assert orf.refine(orf.add_score_features(z), taus)[0] == "bacteria_or_plasmid"
+    # test_refine_abstains_low_confidence
+    z = np.zeros((1, 6), np.float32); z[0, 3] = 0.3; z[0, 5] = 0.1
+    assert orf.refine(orf.add_score_features(z), taus)[0] == "unknown"
+    # test_aggregate_contig_gated_drops_unknown
+    S = np.array([[5.0, 0, 0, 0, 0, 0], [0.0, 0, 0, 0, 0, 0]])
+    out = orf.aggregate_contig(["c1", "c1"], S, np.array(["phage", "unknown"], dtype=object), np.array([5.0, 0.0]), mode="gated", min_windows=1)
+    assert out["c1"]["n_windows_used"] == 1 and out["c1"]["contig_call"] == "phage"
+    # test_aggregate_contig_weighted_uses_margin
+    S = np.array([[4.0, 0, 0, 0, 0, 0], [0.0, 2.0, 0, 0, 0, 0]])
+    out = orf.aggregate_contig(["c1", "c1"], S, np.array(["phage", "virus"], dtype=object), np.array([4.0, 2.0]), mode="weighted", min_windows=1)
+    assert out["c1"]["contig_call"] == "phage" and out["c1"]["total_weight"] == pytest.approx(6.0)
+    # test_aggregate_contig_merge_split_half / _full
+    S = np.array([[0.0, 0.0, 0.0, 2.0, 1.5, 0.0]])
+    out = orf.aggregate_contig(["c1"], S, np.array(["bacteria_or_plasmid"], dtype=object), np.array([0.5]), mode="gated", min_windows=1, merge_split="half")
+    assert out["c1"]["contig_call"] == "bacteria" and out["c1"]["bacteria_score"] == 1.0 and out["c1"]["plasmid_score"] == 0.75
+    S = np.array([[0.0, 0.0, 0.0, 1.0, 1.2, 0.0]])
+    out = orf.aggregate_contig(["c1"], S, np.array(["bacteria_or_plasmid"], dtype=object), np.array([0.5]), mode="gated", min_windows=1, merge_split="full")
+    assert out["c1"]["contig_call"] == "plasmid"
+    # default min_windows = 3 drops the one-window contig (refinement.py:214)
+    assert orf.aggregate_contig(["c1"], S, np.array(["plasmid"], dtype=object), np.array([0.5])) == {}
+    # test_save_and_load_refinement / test_load_refinement_rejects_wrong_model (the product's loader; file as save_refinement writes it)
+    import yaml
+    from jaeger_b200.refine import load_refinement, tau_vector
+    path = tmp_path / "refine.yaml"
+    full = {c: {"logit": 0.25 * i, "margin": 0.1 * i, "n": 40} for i, c in enumerate(C)}
+    full["eukarya"] = {"logit": float("-inf"), "margin": float("-inf"), "n": 3}
+    path.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "test_model", "quantile": 0.05, "classes": C, "taus": full}, sort_keys=False))
+    meta = load_refinement(path, expect_model="test_model")
+    assert meta["taus"]["virus"]["logit"] == pytest.approx(0.25)
+    tv = tau_vector(meta["taus"])
+    assert tv.shape == (12,) and tv[5] == -np.inf and tv[11] == -np.inf and tv[7] == pytest.approx(0.1)
+    with pytest.raises(ValueError):
+        load_refinement(path, expect_model="model_b")
