@@ -97,9 +97,12 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
         elif name == "nmd":
             layers.append(LayerSpec("nmd"))
         elif name == "masked_batchnorm":
-            if c.get("return_nmd"):
-                raise NotImplementedError("masked_batchnorm(return_nmd=True) is not supported; use an nmd layer")
-            layers.append(LayerSpec("norm", dict(type="bn", epsilon=float(c.get("epsilon", 1e-5)))))
+            # return_nmd (layers.py:943-954): besides the normalised tensor the layer returns the masked per-example
+            # channel mean of its INPUT minus its own moving mean -- an NMD tap in front of the norm
+            eps = float(c.get("epsilon", 1e-5))
+            if c.get("return_nmd") and eps != 1e-5:
+                raise NotImplementedError("masked_batchnorm(return_nmd=True) with epsilon != 1e-5 (the tap's count epsilon)")
+            layers.append(LayerSpec("norm", dict(type="bn", epsilon=eps, return_nmd=bool(c.get("return_nmd", False)))))
         elif name == "masked_dyt":          # nnlib/v2/layers.py:385-444: gamma * tanh(alpha * x) + beta, re-masked
             if c.get("return_nmd"):
                 raise NotImplementedError("masked_dyt(return_nmd=True) is rejected by the reference as well")
@@ -112,9 +115,10 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
             norm_type = str(c.get("norm_type", "masked_batchnorm")).lower()
             if norm_type not in ("masked_batchnorm", "masked_dyt"):
                 raise NotImplementedError(f"residual blocks with norm_type={norm_type!r} are not supported")
-            if c.get("return_nmd"):
-                raise NotImplementedError("residual_block(return_nmd=True) is not supported; use an nmd layer")
+            if c.get("return_nmd") and norm_type != "masked_batchnorm":
+                raise NotImplementedError("residual_block(return_nmd=True) needs masked_batchnorm (MaskedDYT rejects it, layers.py:396-400)")
             layers.append(LayerSpec("resblock", dict(
+                return_nmd=bool(c.get("return_nmd", False)),      # NMD of the LAST block's bn2 (layers.py:1897-1898, 2696-2704)
                 block_size=int(c.get("block_size", 1)), filters=int(c["filters"]),
                 kernel_size=int(c.get("kernel_size", 3)), dilation=int(c.get("dilation_rate", 1)),
                 use_bias=bool(c.get("use_bias", True)), activation=_act_name(c, model.get("activation", "gelu")) or "gelu",
@@ -246,13 +250,13 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
     w["classifier"] = [dict(kernel=_glorot(rng, (feat, spec.n_classes), feat, spec.n_classes),
                             bias=np.zeros(spec.n_classes, np.float32))]
     if spec.reliability is not None:
-        n_nmd = sum(1 for layer in spec.layers if layer.kind == "nmd")
+        n_nmd = sum(1 for layer in spec.layers if layer.kind == "nmd" or layer.cfg.get("return_nmd"))
         nmd_dim = 0
         chn = e if e > 0 else 64
         for layer in spec.layers:
             if layer.kind in ("conv", "resblock"):
                 chn = layer.cfg["filters"]
-            if layer.kind == "nmd":
+            if layer.kind == "nmd" or layer.cfg.get("return_nmd"):
                 nmd_dim += chn
         h = spec.reliability[0]["units"]
         w["reliability"] = [dict(kernel=_glorot(rng, (nmd_dim, h), nmd_dim, h), bias=np.zeros(h, np.float32)),

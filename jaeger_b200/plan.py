@@ -271,6 +271,11 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                 c2.act1, c2.stage = cfg["activation"], 2
                 cur = c2
                 cur_buf, cur_mask = x_buf, c2.mask_out
+            if cfg.get("return_nmd"):
+                # bn2 of the last block also returns mean(conv2 output) - its moving mean (layers.py:943-954): a tap on
+                # the raw conv output of that launch
+                cur.tap_mode, cur.tap_slot, cur.tap_mean = 1, n_taps, _np32(lw["blocks"][-1]["bn2"]["mean"])
+                n_taps += 1
             ch = cfg["filters"]
         elif layer.kind == "nmd":
             if cur is None or cur.tap_mode != 0:
@@ -287,6 +292,12 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             if cur is None:
                 raise NotImplementedError("norm before the first convolution")
             s, t, dg, db = _norm_fold(lw, cfg.get("epsilon", 1e-5))
+            if cfg.get("return_nmd"):          # masked_batchnorm(return_nmd=True): an NMD tap on this norm's input
+                if cur.tap_mode != 0 or cur.stage not in (0, 2):
+                    raise NotImplementedError("masked_batchnorm(return_nmd=True) placement cannot be fused (one tap per convolution)")
+                cur.tap_mode = 1 if cur.stage == 0 else 2
+                cur.tap_slot, cur.tap_mean = n_taps, _np32(lw["mean"])
+                n_taps += 1
             if cur.stage == 0:
                 cur.scale1, cur.shift1, cur.dyt_g1, cur.dyt_b1, cur.stage = s, t, dg, db, 1
             elif cur.stage == 2 and cur.scale2 is None:

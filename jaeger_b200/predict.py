@@ -119,15 +119,39 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         kwargs["physicalid"] = local_rank
-    if model_name == "standin":
-        engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=int(kwargs.get("physicalid") or 0))
+    if kwargs.get("cpu"):
+        raise RuntimeError("--cpu: this engine has no CPU path (use the reference's own engine for CPU runs)")
+    precision = kwargs.get("precision") or "fp16"                          # predict.py:604-613
+    if precision not in ("fp32", "fp16", "bf16"):
+        raise ValueError(f"--precision {precision!r} (use fp32, fp16 or bf16)")
+    if precision != "fp16":
+        logger.warning(f"--precision {precision}: the B200 engine always computes with fp16 activations / weights and fp32 "
+                       "accumulation (logits within 4e-3 of fp32); the option is accepted for CLI compatibility")
+    # --mem (GB, predict.py:544, 615-623) caps the device workspace the window chunks are sized from
+    workspace_gb = float(kwargs["mem"]) if kwargs.get("mem") else 16.0
+    device = int(kwargs.get("physicalid") or 0)
+    if model_name == "standin" and not kwargs.get("model_path"):
+        engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=device, workspace_gb=workspace_gb)
         model_id = "standin"
+    elif kwargs.get("model_path"):                                         # predict.py:503-542
+        info = available_models(kwargs["model_path"])
+        if not info:
+            raise ValueError(f"No model found in {kwargs['model_path']}")
+        cls_models = {n: m for n, m in info.items() if m.get("graph") is not None and m.get("classes") is not None}
+        if not cls_models:
+            raise ValueError(f"No classification model found in {kwargs['model_path']}. Expected a *_graph directory, "
+                             "*_classes.yaml, *_project.yaml, and *.weights.h5 files.")
+        if len(cls_models) > 1:
+            cls_models = {n: m for n, m in cls_models.items() if not n.endswith("_embedding")} or cls_models
+        model_name = next(iter(cls_models))
+        engine = B200Engine(cls_models[model_name], device=device, workspace_gb=workspace_gb)
+        model_id = get_model_id(model_name)
     else:
         cfg = json.loads(Path(kwargs["config"]).read_text()) if kwargs.get("config") else {}
         info = available_models(cfg.get("model_paths", []))
         if model_name not in info:
             raise ValueError(f"model {model_name!r} not found; available: {sorted(info)}")
-        engine = B200Engine(info[model_name], device=int(kwargs.get("physicalid") or 0))
+        engine = B200Engine(info[model_name], device=device, workspace_gb=workspace_gb)
         model_id = get_model_id(model_name)
     out_dir = Path(kwargs["output"]) / model_id                          # predict.py:551
     out_dir.mkdir(parents=True, exist_ok=True)
@@ -140,7 +164,9 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                        dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
                        dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
                        batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)),    # cli.py: --dustmask default on
-                       outputs=("prediction", "reliability"), lazy_meta=True)       # the tables need neither embeddings nor meta strings
+                       outputs=("prediction", "reliability") + (("embedding",) if kwargs.get("save_embedding") else ())
+                       + (("nmd",) if kwargs.get("save_nmd") else ()),          # the tables need neither embeddings nor NMD vectors
+                       lazy_meta=True)
     t_load = time.time()
     rec_off = src.load()[2]
     n_records = len(rec_off) - 1
@@ -245,6 +271,14 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
         n_seq = write_fasta_from_results(full, phage_table, out_dir / f"{base}_phages_jaeger.fasta")
         logger.info(f"{base}_phages_jaeger.fasta created ({n_seq} records)")
+    if y_pred and world == 1:                                             # _save_auxiliary_outputs, predict.py:66-112
+        headers = y_pred["meta_0"] if (kwargs.get("save_embedding") or kwargs.get("save_nmd")) else None
+        if kwargs.get("save_embedding") and "embedding" in y_pred:
+            np.savez(out_dir / f"{base}_embedding.npz", embedding=y_pred["embedding"], headers=headers)
+            logger.info(f"{base}_embedding.npz created")
+        if kwargs.get("save_nmd") and "nmd" in y_pred:
+            np.savez(out_dir / f"{base}_nmd.npz", embedding=y_pred["nmd"], headers=headers)   # the reference keeps the key name "embedding"
+            logger.info(f"{base}_nmd.npz created")
     if kwargs.get("window_scores") and data:                              # predict.py:458-470
         off = data["offsets"]
         np.savez(out_dir / f"{base}_window_scores.npz", headers=data["headers"], lengths=data["length"],
@@ -290,6 +324,12 @@ def main(argv=None) -> int:
     ap.add_argument("--lc", type=int, default=500_000)
     ap.add_argument("-s", "--sensitivity", type=float, default=1.5)
     ap.add_argument("--physicalid", type=int, default=0)
+    ap.add_argument("--model_path", dest="model_path", default=None, help="directory holding the model instead of the config's model_paths")
+    ap.add_argument("--mem", type=float, default=None, help="device workspace cap in GB (default 16)")
+    ap.add_argument("--precision", choices=["fp32", "fp16", "bf16"], default="fp16")
+    ap.add_argument("--cpu", action="store_true", help="rejected: there is no CPU path")
+    ap.add_argument("--save-embedding", dest="save_embedding", action="store_true", help="write <base>_embedding.npz")
+    ap.add_argument("--save-nmd", dest="save_nmd", action="store_true", help="write <base>_nmd.npz")
     ap.add_argument("--window-scores", dest="window_scores", action="store_true")
     ap.add_argument("--getsequences", action="store_true", help="write the records of the phage table to <base>_phages_jaeger.fasta")
     ap.add_argument("--overwrite", action="store_true")

@@ -155,17 +155,22 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
         elif layer.kind == "nmd":
             nmds.append(nmd_vector(x, mask, _t(lw["moving_mean"], dtype)))
         elif layer.kind == "norm":
-            x = _norm(x, {k: _t(v, dtype) for k, v in lw.items()}, mask if spec.use_masking else None, c.get("epsilon", 1e-5))
+            nw = {k: _t(v, dtype) for k, v in lw.items()}
+            if c.get("return_nmd"):               # layers.py:943-954: NMD of the norm's input against its own moving mean
+                nmds.append(nmd_vector(x, mask if spec.use_masking else None, nw["mean"], c.get("epsilon", 1e-5)))
+            x = _norm(x, nw, mask if spec.use_masking else None, c.get("epsilon", 1e-5))
         elif layer.kind == "act":
             x = _act(x, c.get("activation"))
         elif layer.kind == "resblock":
-            for blk in lw["blocks"]:
+            for bi, blk in enumerate(lw["blocks"]):
                 m_in = mask if c["use_masking"] else None
                 h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
                                       c["dilation"], "same")
                 h = _act(_norm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}, m1 if m_in is not None else None), c["activation"])
                 h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
                                        c["dilation"], "same")
+                if c.get("return_nmd") and bi == len(lw["blocks"]) - 1:          # layers.py:1897-1898, 2696-2704
+                    nmds.append(nmd_vector(h2, m2 if m_in is not None else None, _t(blk["bn2"]["mean"], dtype)))
                 h2 = _norm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()}, m2 if m_in is not None else None)
                 x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
                 mask = m2 if m_in is not None else mask

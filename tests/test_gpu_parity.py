@@ -910,7 +910,13 @@ def test_driver_refine_option_adds_the_refined_columns(standin, tmp_path):
     cal = tmp_path / "standin_refine.yaml"
     cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "standin", "quantile": 0.05, "taus": taus}, sort_keys=False))
     res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
-                   refine=True, refine_file=str(cal), window_scores=True, terminal_repeats=False)
+                   refine=True, refine_file=str(cal), window_scores=True, terminal_repeats=False, save_embedding=True, save_nmd=True,
+                   mem=2, precision="bf16")
+    emb, nmd = np.load(tmp_path / "o" / "standin" / "c_embedding.npz"), np.load(tmp_path / "o" / "standin" / "c_nmd.npz")
+    assert emb["embedding"].shape == (res["windows"], 128) and nmd["embedding"].shape == (res["windows"], 640)     # predict.py:66-112
+    assert len(emb["headers"]) == res["windows"] and emb["headers"][0] in (b"c0", "c0")
+    with pytest.raises(RuntimeError):
+        run_core(input=str(fa), output=str(tmp_path / "o3"), model="standin", cpu=True)
     tsv = pd.read_csv(res["table"], sep="\t")
     for col in ("contig_call", "contig_top_logit", "contig_margin", "n_windows_used", "n_merged_windows"):
         assert col in tsv.columns
@@ -929,3 +935,29 @@ def test_driver_refine_option_adds_the_refined_columns(standin, tmp_path):
     res = run_core(input=str(fa), output=str(tmp_path / "o2"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
                    refine=True, refine_file=str(cal), terminal_repeats=False)
     assert "contig_call" not in pd.read_csv(res["table"], sep="\t").columns
+
+
+@pytest.mark.parametrize("masking", [True, False])
+def test_return_nmd_taps_through_batchnorm_vs_oracle(masking):
+    """`return_nmd: true` on masked_batchnorm / residual_block (layers.py:943-954, 1897-1898; the way
+    train_config/nn_config_baseline.yaml:205 feeds its reliability head): the NMD vectors are taken on the raw output of
+    the stem conv, on the raw conv2 output of a residual stack's last block (a launch with a shortcut) and on a block
+    output -- logits, NMD vectors and reliability against the fp32 oracle on both kernel families."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import seqwin
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import return_nmd_config
+    spec = parse_project(return_nmd_config(masking))
+    w = init_random(spec, 5)
+    recs = random_contigs(17, [2000, 6500, 9000, 2300])
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    ref = ofw.forward(spec, w, oenc.encode_windows([x.seq for x in wins], 2000))
+    assert ref["nmd"].shape[1] == 384
+    for use_ref in (False, True):
+        eng = B200Engine(spec=spec, weights=w, use_ref_kernels=use_ref)
+        y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500))
+        eng.close()
+        for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
+            assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))

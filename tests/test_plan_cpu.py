@@ -86,6 +86,41 @@ def test_plan_equals_unfused_oracle(pooling, masking, rel, dyt):
         assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
 
 
+def return_nmd_config(masking=True):
+    """The NMD vectors taken through `return_nmd: true` (train_config/nn_config_baseline.yaml:205 style) instead of
+    stand-alone nmd layers: on the stem's masked_batchnorm, on a residual stack, and on a norm after an activation."""
+    cfg = small_config("max", masking, True)
+    hl = [l for l in cfg["model"]["representation_learner"]["hidden_layers"] if l["name"] != "nmd"]
+    hl = [dict(l, config=dict(l.get("config") or {})) for l in hl]
+    assert [l["name"] for l in hl] == ["masked_conv1d", "masked_batchnorm", "activation", "residual_block", "masked_batchnorm",
+                                       "activation", "residual_block", "masked_batchnorm", "activation"]
+    hl[1]["config"]["return_nmd"] = True          # NMD of the stem conv output
+    hl[3]["config"]["return_nmd"] = True          # NMD of the last block's conv2 output (before bn2)
+    hl[7]["config"]["return_nmd"] = True          # NMD of a block output (input of the stand-alone norm)
+    cfg["model"]["representation_learner"]["hidden_layers"] = hl
+    return cfg
+
+
+@pytest.mark.parametrize("masking", [True, False])
+def test_return_nmd_plan_equals_unfused_oracle(masking):
+    spec = parse_project(return_nmd_config(masking))
+    w = init_random(spec, 5)
+    rng = np.random.default_rng(2)
+    for lw in w["layers"]:
+        for part in ([lw] if "blocks" not in lw else [p for b in lw["blocks"] for p in b.values()]):
+            for k in ("bias", "beta"):
+                if k in part:
+                    part[k] = rng.normal(0, 0.3, part[k].shape).astype(np.float32)
+    plan = compile_plan(spec, w)
+    assert plan.n_taps == 3 and [c.tap_mode for c in plan.launches] == [1, 0, 0, 0, 1, 0, 0, 0, 2]
+    tok = _tokens(4, 3, 120, pad_from=70)
+    ref = ofw.forward(spec, w, tok, dtype=torch.float64)
+    got = run_plan(plan, tok)
+    assert ref["nmd"].shape == (3, 384)
+    for k in ref:
+        assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
+
+
 def test_unsupported_layers_fail_loudly():
     cfg = small_config()
     cfg["model"]["representation_learner"]["hidden_layers"].insert(1, {"name": "masked_bilstm", "config": {"units": 8}})
