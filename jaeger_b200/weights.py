@@ -5,8 +5,8 @@
   `variables.data-00000-of-00001`), which is how the reference stores a model next to its
   `*_project.yaml` (nnlib/builder.py:1495-1529).
 * `save_npz_weights` / `load_npz_weights`: the nested weights dict of `modelspec.py` flattened
-  into an `.npz` (`<name>.weights.npz` next to the project file).  `tools/export_weights_npz.py`
-  writes that file from a Keras model inside a reference environment.
+  into an `.npz` (`<name>.weights.npz` next to the project file; takes precedence when present).
+* `weights_from_bundle(spec, tensors)`: the bundle of a layer-list model mapped onto the project's layer list.
 * `load_saved_model_weights(path_dict, spec)`: what `B200Engine(path_dict)` calls.
 """
 from __future__ import annotations
@@ -142,7 +142,172 @@ def load_npz_weights(path: str | Path) -> dict[str, Any]:
     return w
 
 
+_ATTR = "/.ATTRIBUTES/VARIABLE_VALUE"
+_BLOCK_PARTS = ("conv1", "bn1", "conv2", "bn2", "conv3", "bn3")
+
+
+def _natural(path: str):
+    return [(0, int(c), "") if c.isdigit() else (1, 0, c) for c in path.split("/")]
+
+
+def group_bundle(tensors: dict[str, np.ndarray]) -> list[tuple[str, str, dict[str, np.ndarray]]]:
+    """The bundle's variables grouped by owning layer, in graph order: [(layer path, kind, {attribute: array})].
+    A Keras 3 export keys every variable by its object-graph path `_operations/<i>/.../<attribute>` (verified on the
+    reference's bundled data/models/test/jaeger_fragment_graph: `_operations/7/_kernel`, `_operations/9/moving_mean`);
+    `_operations` is the functional model's operation list in construction order, nested layers hang below their owner
+    by attribute name (ResidualBlockStack.blocks[i].conv1 ..., nnlib/v2/layers.py:1836-1872, 2680-2692).  Attribute
+    names: built-in layers `_kernel` / `bias` / `_embeddings` / `gamma` / `beta` / `moving_mean` / `moving_variance`;
+    MaskedConv1D `kernel` / `bias` (layers.py:1196-1210); MaskedBatchNorm (layers.py:828-855); MaskedDYT `alpha` /
+    `gamma` / `beta` (layers.py:412-427); NMDLayer `moving_mean` (nmd.py:34).  kind: emb | conv | dense | bn | dyt | nmd."""
+    groups: dict[str, dict[str, np.ndarray]] = {}
+    for key, arr in tensors.items():
+        if not key.endswith(_ATTR) or key.startswith("optimizer"):
+            continue
+        parent, _, attr = key[:-len(_ATTR)].rpartition("/")
+        groups.setdefault(parent, {})[attr.lstrip("_")] = arr
+    out = []
+    for path in sorted(groups, key=_natural):
+        g = groups[path]
+        if "embeddings" in g:
+            kind = "emb"
+        elif "kernel" in g and g["kernel"].ndim == 3:
+            kind = "conv"
+        elif "kernel" in g and g["kernel"].ndim == 2:
+            kind = "dense"
+        elif {"gamma", "beta", "moving_mean", "moving_variance"} <= set(g):
+            kind = "bn"
+        elif "alpha" in g and "gamma" in g:
+            kind = "dyt"
+        elif set(g) == {"moving_mean"}:
+            kind = "nmd"
+        else:
+            continue                       # seed-generator states, counters ...
+        out.append((path, kind, g))
+    return out
+
+
+def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
+    """The nested weights dict of `modelspec.py` from a SavedModel bundle of a layer-list model: the representation
+    learner's layers are consumed in graph order and checked by kind and shape against the project's layer list;
+    the heads are found by shape.  Anything that does not line up raises with the offending layer -- the mapping
+    cannot be validated against a real modern checkpoint offline (none is vendored), so it refuses rather than guesses."""
+    groups = group_bundle(tensors)
+    used = [False] * len(groups)
+    pos = 0
+
+    def fail(msg):
+        listing = "\n".join(f"  {p} [{k}] " + ", ".join(f"{a}{tuple(v.shape)}" for a, v in g.items()) for p, k, g in groups)
+        raise ValueError(f"SavedModel bundle does not match the project's layer list: {msg}\nvariables found:\n{listing}")
+
+    def take(kinds, what):
+        nonlocal pos
+        i = pos
+        while i < len(groups) and (used[i] or groups[i][1] not in kinds):
+            if not used[i] and groups[i][1] in ("conv", "bn", "dyt", "nmd"):
+                fail(f"expected {what}, found {groups[i][1]} at {groups[i][0]}")
+            i += 1
+        if i == len(groups):
+            fail(f"no variables left for {what}")
+        used[i] = True
+        pos = i + 1
+        return groups[i]
+
+    def conv_w(g, cin, cfg, what):
+        k = g["kernel"]
+        if k.shape != (cfg["kernel_size"], cin, cfg["filters"]):
+            fail(f"{what}: kernel {k.shape} != {(cfg['kernel_size'], cin, cfg['filters'])}")
+        return dict(kernel=k.astype(np.float32), bias=g["bias"].astype(np.float32) if "bias" in g else np.zeros(cfg["filters"], np.float32))
+
+    def norm_w(g, c, what):
+        if g["gamma"].shape != (c,):
+            fail(f"{what}: {g['gamma'].shape} channels, expected {c}")
+        if "alpha" in g:
+            return dict(alpha=g["alpha"].reshape(-1)[:1].astype(np.float32), gamma=g["gamma"].astype(np.float32), beta=g["beta"].astype(np.float32))
+        return dict(gamma=g["gamma"].astype(np.float32), beta=g["beta"].astype(np.float32), mean=g["moving_mean"].astype(np.float32),
+                    var=g["moving_variance"].astype(np.float32))
+
+    w: dict[str, Any] = {"layers": [], "embedding": None}
+    e = spec.embedding_size
+    ch = 64
+    if e > 0:
+        if spec.uses_token_input:
+            _, _, g = take(("emb",), "the Embedding table")
+            w["embedding"] = g["embeddings"].astype(np.float32)
+        else:                                   # Masking + Dense(E, use_bias=False) on the one-hot codons (builder.py:876-894)
+            _, _, g = take(("dense",), "the input Dense projection")
+            w["embedding"] = g["kernel"].astype(np.float32)
+        if w["embedding"].shape[1] != e:
+            fail(f"embedding width {w['embedding'].shape} != {e}")
+        ch = e
+    for li, layer in enumerate(spec.layers):
+        c = layer.cfg
+        what = f"hidden layer {li} ({layer.kind})"
+        if layer.kind == "conv":
+            w["layers"].append(conv_w(take(("conv",), what)[2], ch, c, what))
+            ch = c["filters"]
+        elif layer.kind == "norm":
+            w["layers"].append(norm_w(take(("dyt",) if c.get("type") == "dyt" else ("bn",), what)[2], ch, what))
+        elif layer.kind == "nmd":
+            g = take(("nmd",), what)[2]
+            if g["moving_mean"].shape != (ch,):
+                fail(f"{what}: moving_mean {g['moving_mean'].shape}, expected {(ch,)}")
+            w["layers"].append(dict(moving_mean=g["moving_mean"].astype(np.float32)))
+        elif layer.kind == "resblock":
+            blocks = []
+            for b in range(c["block_size"]):
+                while pos < len(groups) and (used[pos] or groups[pos][1] == "dense"):
+                    pos += 1
+                if pos == len(groups):
+                    fail(f"no variables left for {what} block {b}")
+                owner, _, leaf = groups[pos][0].rpartition("/")
+                if leaf not in _BLOCK_PARTS:
+                    fail(f"{what}: expected a residual block's conv1 / bn1 / conv2 / bn2, found {groups[pos][0]}")
+                parts: dict[str, dict] = {}
+                while pos < len(groups):
+                    parent, _, leaf = groups[pos][0].rpartition("/")
+                    if parent != owner or leaf not in _BLOCK_PARTS:
+                        break
+                    parts[leaf] = groups[pos][2]
+                    used[pos] = True
+                    pos += 1
+                if set(parts) != {"conv1", "bn1", "conv2", "bn2"}:
+                    fail(f"{what} block {b}: found {sorted(parts)} (strided / 1x1-bypass blocks are not supported)")
+                blocks.append(dict(conv1=conv_w(parts["conv1"], ch, c, what), bn1=norm_w(parts["bn1"], c["filters"], what),
+                                   conv2=conv_w(parts["conv2"], c["filters"], c, what), bn2=norm_w(parts["bn2"], c["filters"], what)))
+                ch = c["filters"]
+            w["layers"].append(dict(blocks=blocks))
+        else:
+            w["layers"].append({})
+    left = [p for i, (p, k, _) in enumerate(groups) if not used[i] and k in ("conv", "bn", "dyt", "nmd", "emb")]
+    if left:
+        fail(f"{len(left)} representation-learner variables are not in the project's layer list (first: {left[0]})")
+    dense = [(i, g) for i, (_, k, g) in enumerate(groups) if k == "dense" and not used[i]]
+
+    def pick(shape, what):
+        hits = [(i, g) for i, g in dense if g["kernel"].shape == shape and not used[i]]
+        if not hits:
+            fail(f"no Dense kernel of shape {shape} for {what}")
+        i, g = hits[0]
+        used[i] = True
+        return dict(kernel=g["kernel"].astype(np.float32), bias=g["bias"].astype(np.float32) if "bias" in g else np.zeros(shape[1], np.float32))
+
+    w["classifier"] = [pick((ch, spec.n_classes), "the classifier")]
+    if spec.reliability is not None:
+        nmd_dim = 0
+        chn = e if e > 0 else 64
+        for layer in spec.layers:
+            if layer.kind in ("conv", "resblock"):
+                chn = layer.cfg["filters"]
+            if layer.kind == "nmd" or layer.cfg.get("return_nmd"):
+                nmd_dim += chn
+        h = spec.reliability[0]["units"]
+        w["reliability"] = [pick((nmd_dim, h), "the reliability hidden layer"), pick((h, 1), "the reliability output")]
+    return w
+
+
 def load_saved_model_weights(path_dict: dict[str, Any], spec) -> dict[str, Any]:
+    """`<name>.weights.npz` next to the project file when present (written by `save_npz_weights`), else the
+    SavedModel bundle under `<name>_graph/variables/` (the artefact `InferModel` loads, nnlib/inference.py:311-339)."""
     project = Path(path_dict["project"])
     npz = project.with_name(project.name.replace("_project.yaml", ".weights.npz"))
     if npz.exists():
@@ -151,7 +316,7 @@ def load_saved_model_weights(path_dict: dict[str, Any], spec) -> dict[str, Any]:
         layers += [{} for _ in range(len(spec.layers) - len(layers))]     # trailing parameter-free layers
         w["layers"] = layers
         return w
-    raise NotImplementedError(
-        f"{npz.name} not found. The SavedModel / .weights.h5 key layout of layer-list models cannot be validated "
-        "offline (no such model is vendored by the reference); export the weights once inside a reference "
-        "environment with tools/export_weights_npz.py.")
+    graph = path_dict.get("graph")
+    if graph is not None and (Path(graph) / "variables" / "variables.index").exists():
+        return weights_from_bundle(spec, read_tf_bundle(Path(graph) / "variables"))
+    raise FileNotFoundError(f"neither {npz.name} nor {graph}/variables found for this model")

@@ -189,3 +189,51 @@ def test_500bp_baseline_config_with_narrow_layers_is_padded_correctly():
     got = run_plan(plan, tok)
     for k in ref:
         assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), k
+
+
+def _assert_same_weights(a, b, path=""):
+    if isinstance(a, dict):
+        assert set(a) == set(b), (path, set(a), set(b))
+        for k in a:
+            _assert_same_weights(a[k], b[k], f"{path}/{k}")
+    elif isinstance(a, list):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _assert_same_weights(x, y, f"{path}[{i}]")
+    elif a is None:
+        assert b is None, path
+    else:
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)), path
+
+
+@pytest.mark.parametrize("variant", ["standin", "dyt", "onehot_dense", "return_nmd"])
+def test_saved_model_bundle_maps_onto_the_layer_list(tmp_path, variant):
+    """`B200Engine(path_dict)` without an exported npz: the SavedModel `variables/` bundle is read by the pure-Python
+    reader and mapped onto the project's layer list by graph order, attribute name and shape (a bundle written by
+    tests/tf_bundle_writer.py with the key naming a Keras 3 export uses -- the naming verified on the reference's own
+    data/models/test bundle; a modern checkpoint is not vendored).  Misaligned bundles are refused."""
+    from jaeger_b200.weights import load_saved_model_weights, read_tf_bundle, weights_from_bundle
+    from tests.helpers import to_dyt
+    from tests.tf_bundle_writer import keras3_export_names, write_bundle
+    cfg = {"standin": standin_1p4m_config, "dyt": lambda: to_dyt(standin_1p4m_config()), "onehot_dense": standin_1p4m_config,
+           "return_nmd": return_nmd_config}[variant]()
+    if variant == "onehot_dense":
+        cfg["model"]["embedding"].update(use_embedding_layer=False, input_shape=[6, None, 64])
+        cfg["model"]["representation_learner"]["hidden_layers"][0]["config"]["use_bias"] = False
+    spec = parse_project(cfg)
+    w = init_random(spec, 11)
+    graph = tmp_path / "model" / "jaeger_x_1M_fragment_graph"
+    write_bundle(graph / "variables", keras3_export_names(spec, w))
+    tensors = read_tf_bundle(graph / "variables")
+    assert len(tensors) == len(keras3_export_names(spec, w))
+    project = tmp_path / "model" / "jaeger_x_1M_fragment_project.yaml"
+    project.write_text(yaml.safe_dump(cfg))
+    got = load_saved_model_weights({"graph": graph, "project": project}, spec)
+    _assert_same_weights(w, got)
+    ref = ofw.forward(spec, w, _tokens(1, 2, 90))
+    again = ofw.forward(spec, got, _tokens(1, 2, 90))
+    assert all(np.array_equal(ref[k], again[k]) for k in ref)
+    # a bundle of a different architecture is refused, not guessed
+    other = parse_project(small_config())
+    with pytest.raises(ValueError, match="does not match"):
+        weights_from_bundle(other, tensors)
