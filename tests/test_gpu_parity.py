@@ -961,3 +961,50 @@ def test_return_nmd_taps_through_batchnorm_vs_oracle(masking):
         eng.close()
         for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
             assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))
+
+
+def test_drop_in_model_directory_config_json_and_savedmodel_bundle(tmp_path):
+    """The drop-in boundary as a user meets it: a model directory laid out like the reference's
+    (`<root>/model/<name>_graph/variables/`, `<name>_classes.yaml`, `<name>_project.yaml`, `<name>_refine.yaml`;
+    utils/misc.py:346-392), found through config.json's `model_paths` (-m <name> --config) or through --model_path;
+    weights come from the SavedModel bundle.  Output lands in <-o>/<model_id>/ and equals the run with the same
+    weights handed over in memory."""
+    import pandas as pd
+    import yaml
+    from jaeger_b200 import init_random, parse_project, standin_1p4m_config
+    from jaeger_b200.predict import run_core
+    from jaeger_b200 import B200Engine, WindowSource
+    from jaeger_b200.postprocess import contig_table, generate_summary
+    from oracle import refine as orf
+    from tests.helpers import random_contigs
+    from tests.tf_bundle_writer import keras3_export_names, write_bundle
+    cfg = standin_1p4m_config()
+    spec = parse_project(cfg)
+    w = init_random(spec, 21)
+    name = "jaeger_38341_1.4M_fragment"
+    mdir = tmp_path / "models" / "nested" / "model"
+    write_bundle(mdir / f"{name}_graph" / "variables", keras3_export_names(spec, w))
+    (mdir / f"{name}_project.yaml").write_text(yaml.safe_dump(cfg))
+    classes = [{"class": c["class"], "label": c["label"]} for c in cfg["model"]["class_label_map"]]
+    (mdir / f"{name}_classes.yaml").write_text(yaml.safe_dump({"classes": classes}))
+    taus = {c: {"logit": -1.0, "margin": 0.0, "n": 100} for c in orf.CLASSES}
+    (mdir / f"{name}_refine.yaml").write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": name, "taus": taus}))
+    (tmp_path / "config.json").write_text(json.dumps({"model_paths": [str(tmp_path / "models")]}))
+    recs = random_contigs(5, [2000, 7000, 12000, 3100])
+    fa = tmp_path / "in.fasta"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
+    r1 = run_core(input=str(fa), output=str(tmp_path / "o1"), model=name, config=str(tmp_path / "config.json"), refine=True, dustmask=False)
+    r2 = run_core(input=str(fa), output=str(tmp_path / "o2"), model_path=str(tmp_path / "models"), dustmask=False)
+    assert r1["table"] == tmp_path / "o1" / "38341_1.4M" / "in.tsv" and r2["table"] == tmp_path / "o2" / "38341_1.4M" / "in.tsv"
+    t1, t2 = pd.read_csv(r1["table"], sep="\t"), pd.read_csv(r2["table"], sep="\t")
+    assert "contig_call" in t1.columns and "contig_call" not in t2.columns
+    assert t1[t2.columns].equals(t2)
+    eng = B200Engine(spec=spec, weights=w)
+    y = eng.predict(WindowSource(fasta=fa, fsize=2000, stride=1500, dustmask=False))
+    want = generate_summary(contig_table(eng, y, 2000), eng.class_map["class"], eng.class_map["index"])
+    eng.close()
+    for col in ("contig_id", "prediction", "length", "window_summary"):
+        assert t2[col].tolist() == want[col].tolist(), col
+    assert np.allclose(t2["phage_score"].to_numpy(), want["phage_score"].to_numpy(dtype=np.float64), atol=6e-4)
+    with pytest.raises(ValueError, match="not found"):
+        run_core(input=str(fa), output=str(tmp_path / "o3"), model="jaeger_0_none_fragment", config=str(tmp_path / "config.json"))
