@@ -141,10 +141,12 @@ typedef struct jg_head_desc {
   int32_t rel_hidden;       /* units of the reliability hidden dense (gelu) */
   int32_t mlp_hidden;       /* legacy head: two Dense(mlp_hidden, act) before the classifier (0 = none) */
   int32_t mlp_act;          /* activation code of those layers (3 = erf GELU) */
-  int32_t reserved[1];
+  int32_t reserved[1];      /* [0]: OOD signals appended to the NMD vector for the reliability head (reliability_model.mode
+                             * "nmd_plus_signals", builder.py:644-657): n | id0 << 3 | id1 << 6 ...; ids 1 max_prob, 2 entropy,
+                             * 3 energy, 4 margin, 5 nmd_norm (OODSignalLayer, nnlib/v2/layers.py:1632-1666); 0 = mode "nmd" */
   const float* cls_w;       /* [feat_dim][n_classes] */
   const float* cls_b;       /* [n_classes] */
-  const float* rel_w1;      /* [sum tap widths][rel_hidden] */
+  const float* rel_w1;      /* [sum tap widths + n signals][rel_hidden] */
   const float* rel_b1;      /* [rel_hidden] */
   const float* rel_w2;      /* [rel_hidden][1] */
   const float* rel_b2;      /* [1] */

@@ -555,7 +555,9 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
         std::memcpy(means.data() + static_cast<size_t>(layers[l].i[LF_TAP_SLOT]) * m->tap_width, layers[l].p[LP_TAP_MEAN], m->tap_width * 4);
     if (upload_f32(means.data(), means.size(), &m->tap_mean)) return 2;
     if (head->rel_w1) {
-      if (upload_f32(head->rel_w1, static_cast<size_t>(nmd_dim) * head->rel_hidden, &m->rel_w1)) return 2;
+      const int n_sig = head->reserved[0] & 7;       // nmd_plus_signals: the signals follow the NMD vector
+      if (n_sig > 5 || (n_sig && head->n_classes > jg::kMaxSignalClasses)) return fail("jg_model_create: at most 5 OOD signals over at most 16 classes");
+      if (upload_f32(head->rel_w1, static_cast<size_t>(nmd_dim + n_sig) * head->rel_hidden, &m->rel_w1)) return 2;
       if (upload_f32(head->rel_b1, head->rel_hidden, &m->rel_b1)) return 2;
       if (upload_f32(head->rel_w2, head->rel_hidden, &m->rel_w2)) return 2;
       if (upload_f32(head->rel_b2, 1, &m->rel_b2)) return 2;
@@ -782,6 +784,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   hp.mlp_hidden = m->head.mlp_hidden;
   hp.mlp_act = m->head.mlp_act;
   hp.pool_final = pool_final ? 1 : 0;
+  hp.signals = m->head.reserved[0];
   const int warps = 4;
   const size_t smem = static_cast<size_t>(warps) * (hp.feat + hp.n_taps * hp.tap_width) * 4;
   jg::heads_kernel<<<grid_for(n_windows, warps, ctx->num_sms, 16), warps * 32, smem, st>>>(hp);

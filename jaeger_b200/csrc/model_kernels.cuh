@@ -175,6 +175,8 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
        i += static_cast<long long>(gridDim.x) * blockDim.x) p[i] = v;
 }
 
+constexpr int kMaxSignalClasses = 16;
+
 struct HeadParams {
   const float* pool;        // [W][feat] masked max (sentinel -1e9) or masked sum
   const int* pool_count;    // [W] valid rows under the final mask
@@ -187,6 +189,8 @@ struct HeadParams {
   float* logits; float* rel; float* emb; float* nmd;
   int n_windows, feat, n_classes, pool_mode, n_taps, tap_width, rel_hidden, masking;
   int mlp_hidden, mlp_act, pool_final;   // pool_final: the pool buffer already holds finished features
+  int signals;   // reliability_model.mode "nmd_plus_signals" (builder.py:644-657): n | id0 << 3 | id1 << 6 ...; ids:
+                 // 1 max_prob, 2 entropy, 3 energy, 4 margin, 5 nmd_norm (OODSignalLayer, nnlib/v2/layers.py:1632-1666)
 };
 
 // One warp per window: finalise the pooled features, classifier dense, NMD vector,
@@ -239,18 +243,44 @@ __global__ void heads_kernel(const HeadParams p) {
       if (p.nmd) p.nmd[static_cast<long long>(w) * nmd_dim + i] = v;
     }
     __syncwarp();
+    // OOD signals of the window's logits (fp32 like the reference layer): running softmax statistics, all lanes alike
+    const int n_sig = p.signals & 7;
+    float z_max = -3.0e38f, z_second = -3.0e38f;
+    float zs[kMaxSignalClasses];
     for (int k = 0; k < p.n_classes; ++k) {
       float acc = 0.0f;
       for (int c = lane; c < p.feat; c += 32) acc = fmaf(feat[c], p.cls_w[c * p.n_classes + k], acc);
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) p.logits[static_cast<long long>(w) * p.n_classes + k] = acc + p.cls_b[k];
+      const float z = acc + p.cls_b[k];
+      if (lane == 0) p.logits[static_cast<long long>(w) * p.n_classes + k] = z;
+      if (n_sig && k < kMaxSignalClasses) {
+        zs[k] = z;
+        if (z > z_max) { z_second = z_max; z_max = z; } else if (z > z_second) { z_second = z; }
+      }
+    }
+    float sig[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (n_sig) {
+      float denom = 0.0f;
+      for (int k = 0; k < p.n_classes && k < kMaxSignalClasses; ++k) denom += expf(zs[k] - z_max);
+      float ent = 0.0f;
+      for (int k = 0; k < p.n_classes && k < kMaxSignalClasses; ++k) {
+        const float pr = fmaxf(expf(zs[k] - z_max) / denom, 1e-10f);
+        ent -= pr * logf(pr);
+      }
+      float nn = 0.0f;
+      for (int i = lane; i < nmd_dim; i += 32) nn = fmaf(nmdv[i], nmdv[i], nn);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
+      const float all[6] = {0.0f, 1.0f / denom, ent, z_max + logf(denom), (1.0f - expf(z_second - z_max)) / denom, sqrtf(nn)};
+      for (int i = 0; i < n_sig; ++i) sig[i] = all[(p.signals >> (3 * (i + 1))) & 7];
     }
     if (p.rel && p.n_taps > 0) {
       float out = 0.0f;
       for (int h = 0; h < p.rel_hidden; ++h) {
         float acc = 0.0f;
         for (int i = lane; i < nmd_dim; i += 32) acc = fmaf(nmdv[i], p.rel_w1[i * p.rel_hidden + h], acc);
+        if (lane < n_sig) acc = fmaf(sig[lane], p.rel_w1[(nmd_dim + lane) * p.rel_hidden + h], acc);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         const float a = acc + p.rel_b1[h];

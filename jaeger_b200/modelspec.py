@@ -24,6 +24,7 @@ import numpy as np
 import yaml
 
 CODON_TABLE_NAMES = ("CODON_ID", "AA_ID", "MURPHY10_ID", "PC5_ID")
+OOD_SIGNALS = ("max_prob", "entropy", "energy", "margin", "nmd_norm")     # builder.py:645-651 default order; ids 1..5 on the device
 
 
 @dataclass
@@ -43,6 +44,7 @@ class ModelSpec:
     classifier: list[dict[str, Any]]      # dense layer cfgs (units, activation)
     reliability: list[dict[str, Any]] | None
     use_masking: bool = True
+    reliability_signals: list[str] | None = None      # reliability_model.mode == "nmd_plus_signals" (builder.py:644-657)
 
     @property
     def n_classes(self) -> int:
@@ -140,20 +142,27 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
                 out.append(dict(units=int(c["units"]), activation=_act_name(c), use_bias=bool(c.get("use_bias", True))))
         return out
 
+    signals = None
     classifier = dense_stack(model["classifier"])
     if len(classifier) != 1 or classifier[0]["activation"] is not None:
         raise NotImplementedError("classifier head must be a single linear Dense layer")
     reliability = None
     if "reliability_model" in model:
         rm = model["reliability_model"]
-        if rm.get("mode", "nmd") != "nmd":
-            raise NotImplementedError("reliability_model.mode other than 'nmd' is not supported")
+        mode = rm.get("mode", "nmd")
+        if mode not in ("nmd", "nmd_plus_signals"):
+            raise ValueError(f"Unsupported reliability_model.mode: {mode!r}. Use 'nmd' or 'nmd_plus_signals'.")   # builder.py:628-632
+        if mode == "nmd_plus_signals":
+            signals = list(rm.get("signals", OOD_SIGNALS))
+            bad = sorted(set(signals) - set(OOD_SIGNALS))
+            if bad:
+                raise ValueError(f"Unsupported signal(s): {bad}. Supported: {sorted(OOD_SIGNALS)}")                # layers.py:1626-1631
         reliability = dense_stack(rm)
         if len(reliability) != 2 or reliability[1]["units"] != 1:
             raise NotImplementedError("reliability head must be Dense(h, act) -> Dense(1)")
     return ModelSpec(name=str(model.get("name", "jaeger")), classes=list(model.get("class_label_map", [])),
                      embedding=emb, string_processor=sp, layers=layers, pooling=pooling,
-                     classifier=classifier, reliability=reliability, use_masking=use_masking)
+                     classifier=classifier, reliability=reliability, use_masking=use_masking, reliability_signals=signals)
 
 
 def load_project(path: str | Path) -> ModelSpec:
@@ -259,6 +268,7 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
             if layer.kind == "nmd" or layer.cfg.get("return_nmd"):
                 nmd_dim += chn
         h = spec.reliability[0]["units"]
+        nmd_dim += len(spec.reliability_signals or [])
         w["reliability"] = [dict(kernel=_glorot(rng, (nmd_dim, h), nmd_dim, h), bias=np.zeros(h, np.float32)),
                             dict(kernel=_glorot(rng, (h, 1), h, 1), bias=np.zeros(1, np.float32))]
         assert n_nmd > 0, "reliability head needs at least one nmd layer"

@@ -108,6 +108,7 @@ class Plan:
     tok_offset: int = 1
     mlp: list[np.ndarray] | None = None        # legacy head: [w1, b1, w2, b2]
     mlp_act: str | None = None
+    rel_signals: list[str] | None = None       # OOD signals appended to the NMD vector (nmd_plus_signals)
     flops_per_window_formula: Any = None
     keep: list[Any] = field(default_factory=list)   # keeps ctypes-referenced arrays alive
 
@@ -367,7 +368,8 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
     cls_w[:real_feat] = weights["classifier"][0]["kernel"]
     return Plan(launches=launches, n_classes=spec.n_classes, feat_dim=ch, pool_mode=last.pool_mode, n_taps=n_taps,
                 tap_width=tap_width, cls_w=cls_w, cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel,
-                rel_hidden=rel_hidden, total_shrink=cum_shrink, real_feat_dim=real_feat)
+                rel_hidden=rel_hidden, total_shrink=cum_shrink, real_feat_dim=real_feat,
+                rel_signals=list(spec.reliability_signals) if (rel is not None and spec.reliability_signals) else None)
 
 
 def _fptr(a: np.ndarray | None):
@@ -400,6 +402,12 @@ def to_ctypes(plan: Plan):
     h.cls_w, h.cls_b = _fptr(plan.cls_w), _fptr(plan.cls_b)
     if plan.rel is not None:
         h.rel_w1, h.rel_b1, h.rel_w2, h.rel_b2 = (_fptr(a) for a in plan.rel)
+        if plan.rel_signals:
+            from .modelspec import OOD_SIGNALS
+            code = len(plan.rel_signals)
+            for i, name in enumerate(plan.rel_signals):
+                code |= (OOD_SIGNALS.index(name) + 1) << (3 * (i + 1))
+            h.reserved[0] = code
     if plan.mlp is not None:
         h.mlp_hidden, h.mlp_act = plan.mlp[0].shape[1], ACT[plan.mlp_act]
         h.mlp_w1, h.mlp_b1, h.mlp_w2, h.mlp_b2 = (_fptr(a) for a in plan.mlp)

@@ -301,6 +301,7 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
             if layer.kind == "nmd" or layer.cfg.get("return_nmd"):
                 nmd_dim += chn
         h = spec.reliability[0]["units"]
+        nmd_dim += len(spec.reliability_signals or [])
         w["reliability"] = [pick((nmd_dim, h), "the reliability hidden layer"), pick((h, 1), "the reliability output")]
     return w
 

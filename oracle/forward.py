@@ -126,6 +126,28 @@ def masked_global_avg(x, mask):
     return torch.where(n > 0, s / n, torch.zeros_like(s))
 
 
+def ood_signals(logits, nmd, signals, eps=1e-10):
+    """OODSignalLayer.call (layers.py:1632-1666)."""
+    probs = torch.softmax(logits, dim=-1)
+    out = []
+    for sname in signals:
+        if sname == "max_prob":
+            out.append(probs.amax(dim=-1, keepdim=True))
+        elif sname == "entropy":
+            sp = torch.clamp(probs, min=eps)
+            out.append(-(sp * torch.log(sp)).sum(dim=-1, keepdim=True))
+        elif sname == "energy":
+            out.append(torch.logsumexp(logits, dim=-1, keepdim=True))
+        elif sname == "margin":
+            top2 = torch.topk(probs, 2, dim=-1).values
+            out.append(top2[..., 0:1] - top2[..., 1:2])
+        elif sname == "nmd_norm":
+            out.append(torch.linalg.vector_norm(nmd, dim=-1, keepdim=True))
+        else:
+            raise ValueError(sname)
+    return torch.cat(out, dim=-1)
+
+
 def _t(a, dtype):
     return torch.as_tensor(np.asarray(a), dtype=dtype)
 
@@ -183,6 +205,9 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
         out["nmd"] = torch.cat(nmds, dim=-1)
         if spec.reliability is not None and "reliability" in weights:
             r = weights["reliability"]
-            h = _act(out["nmd"] @ _t(r[0]["kernel"], dtype) + _t(r[0]["bias"], dtype), spec.reliability[0]["activation"])
+            rel_in = out["nmd"]
+            if getattr(spec, "reliability_signals", None):          # builder.py:716-722: concat(nmd, OODSignalLayer(logits, nmd))
+                rel_in = torch.cat([rel_in, ood_signals(out["prediction"], out["nmd"], spec.reliability_signals)], dim=-1)
+            h = _act(rel_in @ _t(r[0]["kernel"], dtype) + _t(r[0]["bias"], dtype), spec.reliability[0]["activation"])
             out["reliability"] = h @ _t(r[1]["kernel"], dtype) + _t(r[1]["bias"], dtype)
     return {k: v.to(torch.float32).numpy() for k, v in out.items()}

@@ -77,5 +77,13 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
         out["nmd"] = torch.cat([taps[i] for i in range(len(taps))], dim=-1)
         if plan.rel is not None:
             w1, b1, w2, b2 = (torch.as_tensor(a, dtype=dt) for a in plan.rel)
-            out["reliability"] = _act(out["nmd"] @ w1 + b1, "gelu") @ w2 + b2
+            rel_in = out["nmd"]
+            if plan.rel_signals:
+                z, sig = out["prediction"], []
+                pr = torch.softmax(z, dim=-1)
+                top2 = torch.topk(pr, 2, dim=-1).values
+                vals = {"max_prob": pr.amax(dim=-1), "entropy": -(torch.clamp(pr, min=1e-10) * torch.log(torch.clamp(pr, min=1e-10))).sum(dim=-1),
+                        "energy": torch.logsumexp(z, dim=-1), "margin": top2[:, 0] - top2[:, 1], "nmd_norm": rel_in.norm(dim=-1)}
+                rel_in = torch.cat([rel_in] + [vals[n].unsqueeze(-1) for n in plan.rel_signals], dim=-1)
+            out["reliability"] = _act(rel_in @ w1 + b1, "gelu") @ w2 + b2
     return {k: v.numpy() for k, v in out.items()}

@@ -1008,3 +1008,32 @@ def test_drop_in_model_directory_config_json_and_savedmodel_bundle(tmp_path):
     assert np.allclose(t2["phage_score"].to_numpy(), want["phage_score"].to_numpy(dtype=np.float64), atol=6e-4)
     with pytest.raises(ValueError, match="not found"):
         run_core(input=str(fa), output=str(tmp_path / "o3"), model="jaeger_0_none_fragment", config=str(tmp_path / "config.json"))
+
+
+def test_reliability_head_with_ood_signals_vs_oracle():
+    """reliability_model.mode nmd_plus_signals (builder.py:644-657, 716-722; OODSignalLayer layers.py:1598-1683): the
+    reliability head reads concat(NMD vector, max_prob, entropy, energy, margin, nmd_norm) computed from the window's
+    own logits -- fp32 on the device, against the fp32 oracle (tolerance 4e-3 like the other head outputs)."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import seqwin
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import signals_config
+    recs = random_contigs(23, [2000, 6500, 9000, 2300])
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    tok = oenc.encode_windows([x.seq for x in wins], 2000)
+    for signals in (None, ["margin", "nmd_norm", "energy"]):
+        spec = parse_project(signals_config(signals))
+        w = init_random(spec, 9)
+        w["classifier"][0]["kernel"] *= 8.0
+        w["reliability"][0]["kernel"][384:] *= 3.0            # make the signal rows count
+        ref = ofw.forward(spec, w, tok)
+        plain = ofw.forward(parse_project(__import__("tests.test_plan_cpu", fromlist=["small_config"]).small_config()),
+                            dict(w, reliability=[dict(w["reliability"][0], kernel=w["reliability"][0]["kernel"][:384]), w["reliability"][1]]), tok)
+        assert np.abs(ref["reliability"] - plain["reliability"]).max() > 0.05        # the signals change the output
+        eng = B200Engine(spec=spec, weights=w)
+        y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500))
+        eng.close()
+        for k, tol in (("prediction", 4e-3), ("nmd", 4e-3), ("reliability", 4e-3)):
+            assert np.abs(ref[k] - y[k]).max() <= tol, (k, signals, float(np.abs(ref[k] - y[k]).max()))

@@ -121,6 +121,50 @@ def test_return_nmd_plan_equals_unfused_oracle(masking):
         assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
 
 
+def signals_config(signals=None):
+    """reliability_model.mode: nmd_plus_signals (the optional block of nn_config_1500bp_nmd_merge_6_class_zeus.yaml:158-165)."""
+    cfg = small_config()
+    rm = cfg["model"]["reliability_model"]
+    rm["mode"] = "nmd_plus_signals"
+    rm.pop("input_shape", None)
+    if signals is not None:
+        rm["signals"] = signals
+    return cfg
+
+
+@pytest.mark.parametrize("signals", [None, ["margin", "energy"], ["nmd_norm"]])
+def test_nmd_plus_signals_plan_equals_unfused_oracle(signals):
+    from jaeger_b200.plan import to_ctypes
+    spec = parse_project(signals_config(signals))
+    names = signals or ["max_prob", "entropy", "energy", "margin", "nmd_norm"]
+    assert spec.reliability_signals == names
+    w = init_random(spec, 9)
+    assert w["reliability"][0]["kernel"].shape == (384 + len(names), 8)
+    w["classifier"][0]["kernel"] *= 8.0                      # logits far enough apart for the softmax signals to matter
+    plan = compile_plan(spec, w)
+    _, head = to_ctypes(plan)
+    assert head.reserved[0] & 7 == len(names)
+    ids = ["max_prob", "entropy", "energy", "margin", "nmd_norm"]
+    assert [ids[((head.reserved[0] >> (3 * (i + 1))) & 7) - 1] for i in range(len(names))] == names
+    tok = _tokens(2, 3, 120, pad_from=70)
+    ref = ofw.forward(spec, w, tok, dtype=torch.float64)
+    got = run_plan(plan, tok)
+    for k in ref:
+        assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
+    with pytest.raises(ValueError, match="Unsupported signal"):
+        parse_project(signals_config(["max_prob", "bogus"]))
+
+
+def test_ood_signal_known_answers():
+    """OODSignalLayer (layers.py:1632-1666) on hand-checkable logits: uniform logits give max_prob 1/n, entropy ln n,
+    energy z + ln n, margin 0; a dominant logit gives max_prob ~ 1, entropy ~ 0, margin ~ 1; nmd_norm is the L2 norm."""
+    z = torch.tensor([[2.0] * 6, [30.0, 0, 0, 0, 0, 0]], dtype=torch.float64)
+    nmd = torch.tensor([[3.0, 4.0], [0.0, 0.0]], dtype=torch.float64)
+    s = ofw.ood_signals(z, nmd, ["max_prob", "entropy", "energy", "margin", "nmd_norm"]).numpy()
+    assert np.allclose(s[0], [1 / 6, np.log(6), 2 + np.log(6), 0.0, 5.0], atol=1e-12)
+    assert np.allclose(s[1], [1.0, 0.0, 30.0, 1.0, 0.0], atol=1e-7)          # entropy: 5 classes clamped at eps = 1e-10
+
+
 def test_unsupported_layers_fail_loudly():
     cfg = small_config()
     cfg["model"]["representation_learner"]["hidden_layers"].insert(1, {"name": "masked_bilstm", "config": {"units": 8}})
