@@ -178,6 +178,21 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
       for (int wd = lane; wd < words_per_frame; wd += 32) {
         const int j0 = wd * 4;
         uint32_t packed = 0;
+        if (j0 + 3 < nc) {
+          // four whole codons = 12 contiguous bases: one funnel shift brings their 24 code bits, one their 12
+          // validity bits; forward frames hold the word's first codon lowest, reverse frames highest
+          const int b0 = (f < 3) ? f + 3 * j0 : n - 3 - (f - 3) - 3 * (j0 + 3);
+          const int cb = 2 * b0, cw = cb >> 5, vw = b0 >> 5;
+          const uint32_t bits = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31);
+          const uint32_t vb = __funnelshift_r(s_valid[vw], s_valid[vw + 1], b0 & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int pos = (f < 3) ? e : 3 - e;
+            const uint32_t six = (bits >> (6 * pos)) & 63u;
+            const uint32_t t = (f < 3) ? s_lut_fwd[six] : s_lut[six ^ 0x2Au];
+            packed |= (((vb >> (3 * pos)) & 7u) == 7u ? t : 0u) << (8 * e);
+          }
+        } else
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = j0 + e;
