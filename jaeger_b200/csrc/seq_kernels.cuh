@@ -173,9 +173,11 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
     if (n - 5 + off <= 0) nc = 0;
     if (nc > lc) nc = lc;
     uint8_t* out = tokens + w * 6ll * pitch;
-    for (int f = 0; f < 6; ++f) {
+    // the 6 x words_per_frame token words of the window are one index space for the warp's lanes
+    for (int idx = lane, f = 0, wd = lane; idx < 6 * words_per_frame; idx += 32, wd += 32) {
+      while (wd >= words_per_frame) { wd -= words_per_frame; ++f; }
       uint8_t* frame = out + static_cast<long long>(f) * pitch;
-      for (int wd = lane; wd < words_per_frame; wd += 32) {
+      {
         const int j0 = wd * 4;
         uint32_t packed = 0;
         if (j0 + 3 < nc) {
@@ -183,15 +185,17 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
           // validity bits; forward frames hold the word's first codon lowest, reverse frames highest
           const int b0 = (f < 3) ? f + 3 * j0 : n - 3 - (f - 3) - 3 * (j0 + 3);
           const int cb = 2 * b0, cw = cb >> 5, vw = b0 >> 5;
-          const uint32_t bits = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31);
-          const uint32_t vb = __funnelshift_r(s_valid[vw], s_valid[vw + 1], b0 & 31);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int pos = (f < 3) ? e : 3 - e;
-            const uint32_t six = (bits >> (6 * pos)) & 63u;
-            const uint32_t t = (f < 3) ? s_lut_fwd[six] : s_lut[six ^ 0x2Au];
-            packed |= (((vb >> (3 * pos)) & 7u) == 7u ? t : 0u) << (8 * e);
-          }
+          uint32_t bits = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31);
+          const uint32_t vb = __funnelshift_r(s_valid[vw], s_valid[vw + 1], b0 & 31) & 0xFFFu;
+          const uint8_t* lut = (f < 3) ? s_lut_fwd : s_lut;
+          if (f >= 3) bits ^= 0xAAAAAAu;                   // complement of all 12 bases
+          const uint32_t t0 = lut[bits & 63u], t1 = lut[(bits >> 6) & 63u], t2 = lut[(bits >> 12) & 63u], t3 = lut[(bits >> 18) & 63u];
+          uint32_t m = 0xFFFFFFFFu;
+          if (vb != 0xFFFu)                                // an N / soft-masked base in the word: blank its codons
+            m = ((vb & 7u) == 7u ? 0xFFu : 0u) | ((vb & 0x38u) == 0x38u ? 0xFF00u : 0u) |
+                ((vb & 0x1C0u) == 0x1C0u ? 0xFF0000u : 0u) | ((vb & 0xE00u) == 0xE00u ? 0xFF000000u : 0u);
+          const uint32_t asc = t0 | (t1 << 8) | (t2 << 16) | (t3 << 24);       // codons in base order
+          packed = ((f < 3) ? asc : __byte_perm(asc, 0, 0x0123)) & ((f < 3) ? m : __byte_perm(m, 0, 0x0123));
         } else
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
