@@ -16,9 +16,11 @@ Pinning status (see DESIGN.md "Oracle"):
     summaries, CRF / Viterbi decoding and score smoothing are pinned against golden vectors produced
     by importing the reference's own Python modules in the build container
     (tests/golden/make_goldens.py) and against the reference tests' known answers.
-  * conv-stack logits: PARITY UNPINNED - TensorFlow/Keras cannot be installed here, so the
-    forward pass is a restatement of nnlib/v2/layers.py checked only against the reference
-    tests' mask / pooling known answers.
+  * legacy (`default`) conv-stack logits: pinned on the reference's serialized TensorFlow graph, executed by the
+    NumPy interpreter oracle/tfgraph.py (tests/golden/legacy_graph_outputs.npz, tests/test_legacy_graph_pin.py).
+  * layer-list (v2) conv-stack logits: PARITY UNPINNED - no such SavedModel is vendored and TensorFlow/Keras cannot
+    be installed here, so the forward pass is a restatement of nnlib/v2/layers.py checked against the reference
+    tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py).
   * change-point segmentation (ruptures KernelCPD + kneed): PARITY UNPINNED - restated from
     the published algorithms (PELT with L2 cost; Kneedle), libraries absent.
   * low-complexity soft-masking (pydustmasker): PARITY UNPINNED - restated from the published

@@ -4,7 +4,10 @@ Restates `WRes_model_embeddings(input_shape=(None,), dropout_active=False)`
 (nnlib/v1/layers.py:399-423) with `ConvolutionalTower(num_res_blocks=5, add_residual=False)`
 (:154-207) and `rc_resnet_block` (:90-151) in torch fp32; `tf.nn.gelu` default = exact erf GELU
 (:78-79), Keras BatchNormalization epsilon 1e-3, MaxPooling1D(2) floor semantics.
-PARITY UNPINNED against TensorFlow itself (not installable here); weights are the reference's.
+PINNED on the reference's own serialized TensorFlow graph: data/models/test/jaeger_fragment_graph/saved_model.pb
+interpreted op by op (oracle/tfgraph.py -> tests/golden/legacy_graph_outputs.npz); this restatement agrees with it to
+3e-6 in float64 / 3e-5 in float32 on the 135 health-FASTA windows and on masked random tokens
+(tests/test_legacy_graph_pin.py).  TensorFlow's own kernels (float32 rounding order) remain un-run.
 """
 from __future__ import annotations
 

@@ -715,6 +715,13 @@ def test_legacy_default_model_on_health_fasta_vs_oracle():
     margins = top2[:, -1] - top2[:, -2]
     assert len(differ) <= 2 and np.all(margins[differ] < 2 * d.max()), (differ, margins[differ], d.max())   # only near-ties may flip
     print(f"legacy: max|logit diff| {d.max():.4f}, windows with different argmax {len(differ)} (margins {margins[differ]})")
+    # ... and against the reference's own serialized TF graph, interpreted op by op (oracle/tfgraph.py -> golden)
+    gold = np.load(G / "legacy_graph_outputs.npz")
+    assert zlib.crc32(tok.tobytes()) == int(gold["health_token_crc"])
+    dg = np.abs(gold["health_output"] - y["prediction"])
+    assert dg.max() <= 0.15 and np.abs(gold["health_embedding"] - y["embedding"]).max() <= 0.15
+    flips = np.flatnonzero(gold["health_output"].argmax(1) != y["prediction"].argmax(1))
+    assert len(flips) <= 2 and np.all(margins[flips] < 2 * dg.max())
     data = contig_table(eng, y, 2000)
     agg = opp.aggregate_numeric(ref["output"], None, np.array([x.is_last for x in wins]))
     assert np.array_equal(data["consensus"], agg["consensus"])           # 9 / 9 contig labels
