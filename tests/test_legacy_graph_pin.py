@@ -83,3 +83,18 @@ def test_tf_op_restatements_known_answers():
     at = {"begin_mask": 1, "end_mask": 1, "shrink_axis_mask": 2}
     assert np.array_equal(SF._strided_slice([d, [0, 1], [0, 2], [1, 1]], at), d[:, 1])
     assert SF._strided_slice([np.array([7, 8, 9]), [1], [2], [1]], {"shrink_axis_mask": 1}) == 8
+
+
+def test_v2_oracle_conv_shares_the_graph_pinned_padding_rule():
+    """The TF SAME padding of dilated convolutions (k 5 / 9, dilations 1..7: total = d(k-1), left = total // 2) is what
+    the interpreted graph computes through SpaceToBatchND; oracle/legacy._conv_same reproduces it (pinned above) and the
+    v2 oracle's separate implementation (oracle/forward._conv1d_tf, used for every MaskedConv1D) equals it."""
+    from oracle import forward as ofw
+    from oracle import legacy as oleg
+    g = torch.Generator().manual_seed(0)
+    for k, d, length in [(5, 3, 40), (5, 1, 17), (9, 2, 33), (4, 1, 12), (4, 3, 25), (7, 7, 60)]:
+        x = torch.randn(3, length, 6, generator=g, dtype=torch.float64)
+        w = torch.randn(k, 6, 5, generator=g, dtype=torch.float64)
+        a = ofw._conv1d_tf(x, w, d, "same")
+        b = oleg._conv_same(x, w, None, d)
+        assert a.shape == (3, length, 5) and torch.allclose(a, b, atol=1e-12)
