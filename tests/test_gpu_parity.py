@@ -1026,7 +1026,7 @@ def test_reliability_head_with_ood_signals_vs_oracle():
     from oracle import forward as ofw
     from oracle import seqwin
     from tests.helpers import random_contigs
-    from tests.test_plan_cpu import signals_config
+    from tests.test_plan_cpu import signals_config, small_config
     recs = random_contigs(23, [2000, 6500, 9000, 2300])
     wins = list(seqwin.fragment_windows(recs, 2000, 1500))
     tok = oenc.encode_windows([x.seq for x in wins], 2000)
@@ -1036,7 +1036,7 @@ def test_reliability_head_with_ood_signals_vs_oracle():
         w["classifier"][0]["kernel"] *= 8.0
         w["reliability"][0]["kernel"][384:] *= 3.0            # make the signal rows count
         ref = ofw.forward(spec, w, tok)
-        plain = ofw.forward(parse_project(__import__("tests.test_plan_cpu", fromlist=["small_config"]).small_config()),
+        plain = ofw.forward(parse_project(small_config()),
                             dict(w, reliability=[dict(w["reliability"][0], kernel=w["reliability"][0]["kernel"][:384]), w["reliability"][1]]), tok)
         assert np.abs(ref["reliability"] - plain["reliability"]).max() > 0.05        # the signals change the output
         eng = B200Engine(spec=spec, weights=w)
