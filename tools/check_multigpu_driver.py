@@ -19,7 +19,11 @@ with open(fa, "w") as fh:
         fh.write(f">ctg{i} len={n}\n")
         for k in range(0, len(s), 80):
             fh.write(s[k:k + 80] + "\n")
-common = ["-i", str(fa), "--min-len", "500", "-p", "--lc", "500000", "--overwrite"]
+import yaml
+cal = tmp / "standin_refine.yaml"
+cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "standin", "taus": {
+    c: {"logit": -0.5, "margin": 0.01, "n": 100} for c in ("phage", "virus", "archaea", "bacteria", "plasmid", "eukarya")}}))
+common = ["-i", str(fa), "--min-len", "500", "-p", "--lc", "500000", "-s", "0.2", "--overwrite", "--refine", "--refine-file", str(cal)]
 subprocess.run([sys.executable, "-m", "jaeger_b200.predict", *common, "-o", str(tmp / "one")], check=True)
 subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_gpus}", "--master-addr", "127.0.0.1",
                 "--master-port", "29541", "-m", "jaeger_b200.predict", *common, "-o", str(tmp / "many")], check=True)
@@ -34,4 +38,8 @@ for col in a.columns:
 pa = (tmp / "one" / "standin" / "meta_prophage_regions.tsv").read_text()
 pb = (tmp / "many" / "standin" / "meta_prophage_regions.tsv").read_text()
 assert pa == pb, (pa, pb)
+assert "contig_call" in a.columns and (a["n_windows_used"] != "").sum() > 10
+ra, rb = (tmp / d / "standin" / "meta_prophages" / "prophages_jaeger.tsv" for d in ("one", "many"))
+assert ra.exists() == rb.exists() and (not ra.exists() or ra.read_text() == rb.read_text())
+print("att-site report rows:", len(ra.read_text().splitlines()) - 1 if ra.exists() else 0)
 print(f"multi-GPU driver check ok: {len(a)} rows identical on 1 and {n_gpus} GPUs; DTR rows: {(a['terminal_repeats'] != '').sum()}")
