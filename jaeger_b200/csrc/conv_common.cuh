@@ -61,7 +61,7 @@ struct ConvParams {
   // epilogue ------------------------------------------------------------
   int act1, act2;               // Act
   int has_affine2;
-  int tap_mode;                 // 0 none, 1 raw conv output (acc+bias), 2 after act1
+  int tap_mode;                 // 0 none, 1 raw conv output (acc+bias), 2 after act1, 3 after the second affine + act2
   int pool_mode;                // 0 none, 1 masked max, 2 masked sum
   // fused mask propagation (tensor-core kernels): when fuse_mask != 0 the epilogue derives the row's
   // validity itself -- in-frame test + OR over the taps of the INPUT mask (layers.py:1245-1252,

@@ -313,6 +313,13 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       if (p.dyt2) dyt_apply_h2(h, e.g2, e.b2, cb);
       act_apply_h2(h, p.act2);
     }
+    if (kGen && p.tap_mode == 3) {   // NMD tap on the launch output (after the stand-alone norm + activation)
+      __half2 tv[16];
+      const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
+    }
   }
   if (kMode == EPI_FINAL_POOL || (kGen && p.pool_mode != 0)) {
     __half2 tv[16];

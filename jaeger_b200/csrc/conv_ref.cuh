@@ -41,6 +41,7 @@ __global__ void conv_ref_kernel(const ConvParams p) {
       if (p.dyt2) v = fmaf(tanhf(v), p.dyt_g2[co], p.dyt_b2[co]);
       v = act_apply(v, p.act2);
     }
+    if (p.tap_mode == 3 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, v);
     if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * p.cout + co, v);
     if (p.y)

@@ -331,6 +331,8 @@ class B200Engine:
                 out["nmd"][b:e].data_ptr() if "nmd" in out else None, int(self.use_ref_kernels)))
         if p.real_feat_dim is not None and p.real_feat_dim != p.feat_dim:
             out["embedding"] = out["embedding"][:, :p.real_feat_dim]     # drop the zero padding channels
+        if p.nmd_cols is not None and "nmd" in out:
+            out["nmd"] = out["nmd"][:, torch.as_tensor(p.nmd_cols, device=self.tdev)]     # taps of layers narrower than 64 channels
         return out
 
     def aggregate(self, logits: torch.Tensor, rel: torch.Tensor | None, offsets: torch.Tensor) -> dict[str, torch.Tensor]:

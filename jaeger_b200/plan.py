@@ -109,6 +109,7 @@ class Plan:
     mlp: list[np.ndarray] | None = None        # legacy head: [w1, b1, w2, b2]
     mlp_act: str | None = None
     rel_signals: list[str] | None = None       # OOD signals appended to the NMD vector (nmd_plus_signals)
+    nmd_cols: np.ndarray | None = None         # columns of the padded device NMD vector that are the reference's NMD vector
     flops_per_window_formula: Any = None
     keep: list[Any] = field(default_factory=list)   # keeps ctypes-referenced arrays alive
 
@@ -285,6 +286,8 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                 cur.tap_mode = 1
             elif cur.stage == 2:
                 cur.tap_mode = 2
+            elif cur.stage == 4:
+                cur.tap_mode = 3                 # on the launch output: after the stand-alone norm and its activation
             else:
                 raise NotImplementedError("nmd layer between a norm and its activation cannot be fused")
             cur.tap_slot, cur.tap_mean = n_taps, _np32(lw["moving_mean"])
@@ -324,13 +327,16 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
     # 500 bp model) are zero-padded -- padded output channels stay exactly 0 through bias-free
     # affine / GELU / residual / pooling, padded input channels meet zero weights.
     real_feat = ch
+    tap_real_widths = {c.tap_slot: c.kernel.shape[2] for c in launches if c.tap_mode}
     for c in launches:
         k, cin, cout = c.kernel.shape
         cin_p, cout_p = -(-cin // 64) * 64, -(-cout // 64) * 64
         if (cin_p, cout_p) == (cin, cout):
             continue
-        if c.tap_mode:
-            raise NotImplementedError("NMD taps on layers narrower than a multiple of 64 channels")
+        if c.tap_mode:                   # padded channels tap to exactly 0 (zero sums, zero moving mean)
+            tm = np.zeros(cout_p, np.float32)
+            tm[:cout] = c.tap_mean
+            c.tap_mean = tm
         kp = np.zeros((k, cin_p, cout_p), np.float32)
         kp[:, :cin, :cout] = c.kernel
         c.kernel = kp
@@ -356,20 +362,31 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             if tap_width and tap_width != w:
                 raise NotImplementedError("NMD taps of different widths")
             tap_width = w
+    # NMD columns of the reference (real channels of every tap, tap order) inside the padded device layout
+    nmd_cols = np.concatenate([np.arange(real_w) + slot * tap_width for slot, real_w in sorted(tap_real_widths.items())]) \
+        if tap_real_widths else np.zeros(0, np.int64)
     rel = None
     rel_hidden = 0
     if spec.reliability is not None and "reliability" in weights:
         r = weights["reliability"]
         if spec.reliability[0]["activation"] != "gelu":
             raise NotImplementedError("reliability hidden activation other than gelu")
-        rel = [_np32(r[0]["kernel"]), _np32(r[0]["bias"]), _np32(r[1]["kernel"]), _np32(r[1]["bias"])]
+        k1 = _np32(r[0]["kernel"])
+        n_sig = len(spec.reliability_signals or [])
+        if len(nmd_cols) + n_sig != k1.shape[0]:
+            raise ValueError(f"reliability head expects {k1.shape[0]} inputs, the layer list provides {len(nmd_cols)} NMD values + {n_sig} signals")
+        k1p = np.zeros((n_taps * tap_width + n_sig, k1.shape[1]), np.float32)
+        k1p[nmd_cols] = k1[:len(nmd_cols)]
+        k1p[n_taps * tap_width:] = k1[len(nmd_cols):]
+        rel = [k1p, _np32(r[0]["bias"]), _np32(r[1]["kernel"]), _np32(r[1]["bias"])]
         rel_hidden = r[0]["kernel"].shape[1]
     cls_w = np.zeros((ch, spec.n_classes), np.float32)
     cls_w[:real_feat] = weights["classifier"][0]["kernel"]
     return Plan(launches=launches, n_classes=spec.n_classes, feat_dim=ch, pool_mode=last.pool_mode, n_taps=n_taps,
                 tap_width=tap_width, cls_w=cls_w, cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel,
                 rel_hidden=rel_hidden, total_shrink=cum_shrink, real_feat_dim=real_feat,
-                rel_signals=list(spec.reliability_signals) if (rel is not None and spec.reliability_signals) else None)
+                rel_signals=list(spec.reliability_signals) if (rel is not None and spec.reliability_signals) else None,
+                nmd_cols=nmd_cols if len(nmd_cols) != n_taps * tap_width else None)
 
 
 def _fptr(a: np.ndarray | None):

@@ -64,6 +64,9 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
             if c.dyt_g2 is not None:
                 v = torch.tanh(v) * torch.as_tensor(c.dyt_g2, dtype=dt) + torch.as_tensor(c.dyt_b2, dtype=dt)
             v = _act(v, c.act2)
+        if c.tap_mode == 3:
+            taps[c.tap_slot] = (v * mo).sum(dim=(1, 2)) / (m_out.sum(dim=(1, 2)).unsqueeze(-1) + 1e-5) \
+                - torch.as_tensor(c.tap_mean, dtype=dt)
         if c.pool_mode == 1:
             pm = torch.where(mo > 0, v, torch.tensor(-1e9, dtype=dt)).amax(dim=(1, 2))
             pooled = torch.where(m_out.amax(dim=(1, 2)).unsqueeze(-1) > 0, pm, torch.zeros_like(pm))
@@ -75,9 +78,12 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
     out = {"embedding": pooled[:, :real], "prediction": pooled @ torch.as_tensor(plan.cls_w, dtype=dt) + torch.as_tensor(plan.cls_b, dtype=dt)}
     if taps:
         out["nmd"] = torch.cat([taps[i] for i in range(len(taps))], dim=-1)
+        padded_nmd = out["nmd"]
+        if plan.nmd_cols is not None:
+            out["nmd"] = out["nmd"][:, torch.as_tensor(plan.nmd_cols)]
         if plan.rel is not None:
             w1, b1, w2, b2 = (torch.as_tensor(a, dtype=dt) for a in plan.rel)
-            rel_in = out["nmd"]
+            rel_in = padded_nmd
             if plan.rel_signals:
                 z, sig = out["prediction"], []
                 pr = torch.softmax(z, dim=-1)

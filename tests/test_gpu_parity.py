@@ -1044,3 +1044,28 @@ def test_reliability_head_with_ood_signals_vs_oracle():
         eng.close()
         for k, tol in (("prediction", 4e-3), ("nmd", 4e-3), ("reliability", 4e-3)):
             assert np.abs(ref[k] - y[k]).max() <= tol, (k, signals, float(np.abs(ref[k] - y[k]).max()))
+
+
+def test_500bp_nmd_merge_model_vs_oracle():
+    """train_config/nn_config_500bp_nmd_merge.yaml (restated in tests/test_plan_cpu.py): NMD taps on 32-channel layers
+    (zero-padded to 64 on the device, sliced back on return) and a tap on a launch's final output, average pooling,
+    reliability head -- 500-bp windows against the fp32 oracle, tensor-core and CUDA-core kernels."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import seqwin
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import nmd_merge_500bp_config
+    spec = parse_project(nmd_merge_500bp_config())
+    w = init_random(spec, 2)
+    recs = random_contigs(41, [500, 1700, 2600, 900, 500])
+    wins = list(seqwin.fragment_windows(recs, 500, 500))
+    ref = ofw.forward(spec, w, oenc.encode_windows([x.seq for x in wins], 500))
+    assert ref["nmd"].shape == (len(wins), 64)
+    for use_ref in (False, True):
+        eng = B200Engine(spec=spec, weights=w, use_ref_kernels=use_ref)
+        y = eng.predict(WindowSource(records=recs, fsize=500, stride=500))
+        eng.close()
+        assert y["nmd"].shape == ref["nmd"].shape and y["embedding"].shape == ref["embedding"].shape
+        for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
+            assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))

@@ -165,6 +165,55 @@ def test_ood_signal_known_answers():
     assert np.allclose(s[1], [1.0, 0.0, 30.0, 1.0, 0.0], atol=1e-7)          # entropy: 5 classes clamped at eps = 1e-10
 
 
+def nmd_merge_500bp_config():
+    """train_config/nn_config_500bp_nmd_merge.yaml restated (the reference checkout is not on the GPU box): E64 ->
+    conv(32, k7) -> BN -> GELU -> nmd -> 2 residual blocks (32, k3) -> BN -> GELU -> nmd, average pooling, 3 classes,
+    reliability head on the 2 x 32 NMD values.  Exercises taps on 32-channel layers (padded to 64 on the device) and a tap
+    on a launch's final output (after the stand-alone norm and its activation)."""
+    def conv(f, k):
+        return {"name": "masked_conv1d", "config": {"filters": f, "kernel_size": k, "strides": 1, "dilation_rate": 1,
+                                                    "use_bias": True, "activation": None}}
+    tail = [{"name": "masked_batchnorm", "config": {"return_nmd": False}}, {"name": "activation", "config": {"activation": "gelu"}},
+            {"name": "nmd", "config": {}}]
+    hidden = [conv(32, 7)] + tail + [{"name": "residual_block", "config": {"block_size": 2, "filters": 32, "kernel_size": 3,
+                                                                             "use_bias": True}}] + tail
+    classes = ["chromosome", "virus", "plasmid"]
+    return {"model": {
+        "name": "jaeger_500bp_nmd_merge", "activation": "gelu", "classifier_out_dim": 3,
+        "class_label_map": [{"class": c, "label": i} for i, c in enumerate(classes)],
+        "embedding": {"use_embedding_layer": True, "input_type": "translated", "frames": 6, "input_shape": [6, None], "embedding_size": 64},
+        "string_processor": {"seq_onehot": False, "codon": "CODON", "codon_id": "CODON_ID", "masking": False},
+        "representation_learner": {"hidden_layers": hidden, "pooling": "average"},
+        "classifier": {"input_shape": 32, "hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None, "use_bias": True}}]},
+        "reliability_model": {"input_shape": 64, "hidden_layers": [
+            {"name": "dense", "config": {"units": 8, "activation": "gelu", "use_bias": True}}, {"name": "dropout", "config": {"rate": 0.5}},
+            {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]}}}
+
+
+def test_500bp_nmd_merge_config_taps_on_narrow_layers():
+    spec = parse_project(nmd_merge_500bp_config())
+    if REF_CFG.exists():                                     # the restated config has the reference file's layer list
+        ref_spec = parse_project(yaml.safe_load((REF_CFG / "nn_config_500bp_nmd_merge.yaml").read_text()))
+        assert [(l.kind, l.cfg) for l in ref_spec.layers] == [(l.kind, l.cfg) for l in spec.layers]
+        assert ref_spec.pooling == spec.pooling and ref_spec.n_classes == spec.n_classes
+    w = init_random(spec, 0)
+    rng = np.random.default_rng(1)
+    for lw in w["layers"]:
+        for part in ([lw] if "blocks" not in lw else [p for b in lw["blocks"] for p in b.values()]):
+            for k in ("bias", "beta"):
+                if k in part:
+                    part[k] = rng.normal(0, 0.3, part[k].shape).astype(np.float32)
+    plan = compile_plan(spec, w)
+    assert [c.tap_mode for c in plan.launches] == [2, 0, 0, 0, 3] and plan.tap_width == 64 and plan.rel[0].shape == (128, 8)
+    assert plan.nmd_cols.tolist() == list(range(32)) + list(range(64, 96))
+    tok = _tokens(5, 3, 165, pad_from=100)
+    ref = ofw.forward(spec, w, tok, dtype=torch.float64)
+    got = run_plan(plan, tok)
+    assert ref["nmd"].shape == (3, 64) and ref["embedding"].shape == (3, 32)
+    for k in ref:
+        assert np.allclose(ref[k], got[k], rtol=1e-5, atol=2e-6), (k, np.abs(ref[k] - got[k]).max())
+
+
 def test_unsupported_layers_fail_loudly():
     cfg = small_config()
     cfg["model"]["representation_learner"]["hidden_layers"].insert(1, {"name": "masked_bilstm", "config": {"units": 8}})
