@@ -55,6 +55,21 @@ def test_reference_train_config_parses():
     assert plan.flops_per_window(665, algorithmic_stem_cin=128) == pytest.approx(8.68e9, rel=2e-3)
 
 
+@pytest.mark.skipif(not REF_CFG.exists(), reason="reference checkout not mounted")
+@pytest.mark.parametrize("name,launches,taps,params", [("nn_config_1500bp_nmd_merge_6_class_brain", 13, 4, 1_116_416),
+                                                       ("nn_config_1500bp_nmd_merge_6_class_zeus", 13, 4, 1_177_684),
+                                                       ("nn_config_500bp_baseline", 5, 0, 31_712), ("nn_config_500bp_nmd_merge", 5, 2, None)])
+def test_every_residual_cnn_train_config_of_the_reference_compiles(name, launches, taps, params):
+    """All plain-YAML residual-CNN configs the reference ships (the others are attention / hyena models or Jinja
+    templates of the strided pyramid, outside the supported family) parse, initialise and compile to a launch plan."""
+    spec = parse_project(yaml.safe_load((REF_CFG / f"{name}.yaml").read_text()))
+    w = init_random(spec, 0)
+    plan = compile_plan(spec, w)
+    assert len(plan.launches) == launches and plan.n_taps == taps
+    if params is not None:
+        assert count_params(spec, w) == params
+
+
 def _tokens(seed, b, lc, n_frac=0.02, pad_from=None):
     rng = np.random.default_rng(seed)
     t = rng.integers(1, 65, size=(b, 6, lc)).astype(np.uint8)
