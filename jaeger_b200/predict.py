@@ -328,13 +328,19 @@ def main(argv=None) -> int:
     ap.add_argument("--mem", type=float, default=None, help="device workspace cap in GB (default 16)")
     ap.add_argument("--precision", choices=["fp32", "fp16", "bf16"], default="fp16")
     ap.add_argument("--cpu", action="store_true", help="rejected: there is no CPU path")
+    ap.add_argument("--workers", type=int, default=4, help="accepted for CLI compatibility: windowing / encoding run on the device")
+    ap.add_argument("--plot-type", dest="plot_type", default="none", choices=["circular", "linear", "both", "none"],
+                    help="accepted for CLI compatibility: plots are outside the hot path and are not drawn")
+    ap.add_argument("-v", "--verbose", action="count", default=1, help="-vv debug, -v info")
     ap.add_argument("--save-embedding", dest="save_embedding", action="store_true", help="write <base>_embedding.npz")
     ap.add_argument("--save-nmd", dest="save_nmd", action="store_true", help="write <base>_nmd.npz")
     ap.add_argument("--window-scores", dest="window_scores", action="store_true")
     ap.add_argument("--getsequences", action="store_true", help="write the records of the phage table to <base>_phages_jaeger.fasta")
     ap.add_argument("--overwrite", action="store_true")
     args = ap.parse_args(argv)
-    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s [jaeger_b200] %(message)s")
+    logging.basicConfig(level=logging.DEBUG if args.verbose >= 2 else logging.INFO, format="%(asctime)s %(levelname)s [jaeger_b200] %(message)s")
+    if args.plot_type != "none" and args.prophage:
+        logger.warning(f"--plot-type {args.plot_type}: prophage plots are not drawn by this engine (tables only)")
     try:
         res = run_core(**vars(args))
     except Exception as e:                                               # predict.py:811-816
