@@ -131,6 +131,7 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
         else:
             raise NotImplementedError(f"layer {name!r} is outside the supported residual-CNN family")
     pooling = str(rep.get("pooling", "max")).lower()
+    pooling = {"masked_max": "max", "masked_average": "average"}.get(pooling, pooling)       # builder.py:1703-1713 aliases
     if pooling not in ("max", "average"):
         raise NotImplementedError(f"pooling {pooling!r} is not supported")
 
