@@ -100,8 +100,9 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
   uint32_t* s_codes = s_mem + warp * (words_c + 2 * words_b);
   uint32_t* s_valid = s_codes + words_c;   // valid for tokens (soft-masked removed if case_sensitive)
   uint32_t* s_count = s_valid + words_b;   // valid & ~soft (what the G/C/A/T counts see)
-  __shared__ uint8_t s_lut[64];       // index = (first base << 4) | (second << 2) | third
-  __shared__ uint8_t s_lut_fwd[64];   // index = first | (second << 2) | (third << 4)
+  __shared__ uint8_t s_lut2[128];     // [0, 64): forward frames, index = first | (second << 2) | (third << 4)
+  uint8_t* const s_lut_fwd = s_lut2;  // [64, 128): reverse frames, index = (first base << 4) | (second << 2) | third
+  uint8_t* const s_lut = s_lut2 + 64;
   if (threadIdx.x < 64) {
     const uint32_t i = threadIdx.x;
     s_lut[i] = lut64.v[i];
@@ -172,11 +173,10 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
     int nc = (n - 5 + off + 2) / 3;          // ceil((n - 5 + off) / 3)
     if (n - 5 + off <= 0) nc = 0;
     if (nc > lc) nc = lc;
-    uint8_t* out = tokens + w * 6ll * pitch;
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(tokens + w * 6ll * pitch);
     // the 6 x words_per_frame token words of the window are one index space for the warp's lanes
     for (int idx = lane, f = 0, wd = lane; idx < 6 * words_per_frame; idx += 32, wd += 32) {
       while (wd >= words_per_frame) { wd -= words_per_frame; ++f; }
-      uint8_t* frame = out + static_cast<long long>(f) * pitch;
       {
         const int j0 = wd * 4;
         uint32_t packed = 0;
@@ -187,7 +187,7 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
           const int cb = 2 * b0, cw = cb >> 5, vw = b0 >> 5;
           uint32_t bits = __funnelshift_r(s_codes[cw], s_codes[cw + 1], cb & 31);
           const uint32_t vb = __funnelshift_r(s_valid[vw], s_valid[vw + 1], b0 & 31) & 0xFFFu;
-          const uint8_t* lut = (f < 3) ? s_lut_fwd : s_lut;
+          const uint8_t* lut = s_lut2 + ((f < 3) ? 0 : 64);
           if (f >= 3) bits ^= 0xAAAAAAu;                   // complement of all 12 bases
           const uint32_t t0 = lut[bits & 63u], t1 = lut[(bits >> 6) & 63u], t2 = lut[(bits >> 12) & 63u], t3 = lut[(bits >> 18) & 63u];
           uint32_t m = 0xFFFFFFFFu;
@@ -215,7 +215,7 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
           }
           packed |= tok << (8 * e);
         }
-        *reinterpret_cast<uint32_t*>(frame + j0) = packed;
+        out_words[idx] = packed;                           // pitch = 4 * words_per_frame: word f * wpf + wd is word idx
       }
     }
     if (lane == 0) {
