@@ -408,6 +408,22 @@ class B200Engine:
             return self._predict_source(dataset)
         return self._predict_batches(dataset)
 
+    def evaluate(self, dataset, no_progress: bool = False) -> dict[str, float]:
+        """InferModel.evaluate (nnlib/inference.py:375-408): dataset yields (inputs_dict, y_true_onehot) batches;
+        returns the mean categorical cross-entropy of the logits (from_logits=True) and the accuracy."""
+        logits_acc, true_acc = [], []
+        for inputs, y_true in dataset:
+            logits_acc.append(self._predict_batches([(inputs,)])["prediction"])
+            true_acc.append(np.asarray(y_true, dtype=np.float32))
+        logits = np.concatenate(logits_acc, axis=0).astype(np.float32)
+        y_true = np.concatenate(true_acc, axis=0)
+        # keras.losses.categorical_crossentropy(from_logits=True): -sum(y * log_softmax(z)), float32
+        z = logits - logits.max(axis=1, keepdims=True)
+        log_sm = z - np.log(np.exp(z).sum(axis=1, keepdims=True))
+        loss = float(np.mean(-(y_true * log_sm).sum(axis=1)))
+        accuracy = float(np.mean(np.argmax(logits, axis=1) == np.argmax(y_true, axis=1)))
+        return {"loss": loss, "accuracy": accuracy}
+
     def _predict_batches(self, dataset: Iterable) -> dict[str, np.ndarray]:
         """Reference dataset protocol: (inputs_dict, meta_0..meta_9) batches (inference.py:341-373)."""
         acc: dict[str, list] = {}

@@ -1069,3 +1069,41 @@ def test_500bp_nmd_merge_model_vs_oracle():
         assert y["nmd"].shape == ref["nmd"].shape and y["embedding"].shape == ref["embedding"].shape
         for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
             assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))
+
+
+def test_reference_dataset_protocol_batches_and_evaluate(standin):
+    """The engine behind the reference's own data pipeline: `predict` fed with the
+    `(inputs_dict, meta_0..meta_9)` batches `process_string_inference` yields (float32 tokens [B, 6, Lc], or one-hot
+    [B, 6, Lc, 64]) returns the same logits as the engine's own FASTA path, meta columns passed through in window order
+    (inference.py:341-373); `evaluate` on `(inputs_dict, y_true_onehot)` batches gives Keras' from-logits categorical
+    cross-entropy and the accuracy (inference.py:375-408)."""
+    from jaeger_b200 import WindowSource
+    from oracle import encode as oenc
+    from oracle import seqwin
+    from tests.helpers import random_contigs
+    _, _, eng = standin
+    recs = random_contigs(12, [2000, 5200, 8000, 3500])
+    y_src = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500))
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    tok = oenc.encode_windows([x.seq for x in wins], 2000)
+    n = len(wins)
+
+    def batches(onehot):
+        for a in range(0, n, 4):
+            t = tok[a:a + 4]
+            x = (np.eye(65, dtype=np.float32)[t][..., 1:] if onehot else t.astype(np.float32))
+            meta = [np.array([f"{k}_{i}".encode() for i in range(a, min(a + 4, n))]) for k in range(10)]
+            yield ({"translated": x}, *meta)
+
+    for onehot in (False, True):
+        y = eng.predict(batches(onehot), no_progress=True)
+        assert y["prediction"].shape == (n, 6) and np.array_equal(y["prediction"], y_src["prediction"])
+        assert np.abs(y["reliability"] - y_src["reliability"]).max() <= 1e-6       # NMD sums are fp32 atomics: order-dependent last bit
+        assert [m.decode() for m in y["meta_3"]] == [f"3_{i}" for i in range(n)] and set(k for k in y if k.startswith("meta_")) == {f"meta_{i}" for i in range(10)}
+    labels = np.random.default_rng(0).integers(0, 6, n)
+    onehot_y = np.eye(6, dtype=np.float32)[labels]
+    res = eng.evaluate((({"translated": tok[a:a + 5].astype(np.float32)}, onehot_y[a:a + 5]) for a in range(0, n, 5)))
+    z = y_src["prediction"].astype(np.float64)
+    lse = np.log(np.exp(z - z.max(1, keepdims=True)).sum(1)) + z.max(1)
+    assert abs(res["loss"] - float(np.mean(lse - z[np.arange(n), labels]))) < 1e-5
+    assert res["accuracy"] == float(np.mean(z.argmax(1) == labels))
