@@ -243,3 +243,55 @@ def test_refinement_oracle_on_reference_known_answers(tmp_path):
     assert tv.shape == (12,) and tv[5] == -np.inf and tv[11] == -np.inf and tv[7] == pytest.approx(0.1)
     with pytest.raises(ValueError):
         load_refinement(path, expect_model="model_b")
+
+
+def _model_tree(root: Path):
+    """A model registry like the reference's data/models: nested `model` directories with graphs, class / project files,
+    an embedding-only graph, a legacy .h5 and unrelated files."""
+    for rel in ["a/model/jaeger_38341_1.4M_fragment_graph/variables", "a/model/jaeger_38341_1.4M_fragment_embedding_graph",
+                "b/deep/er/model/jaeger_57341_1.5M_fragment_graph", "c/not_model/jaeger_1_x_fragment_graph", "d/model"]:
+        (root / rel).mkdir(parents=True)
+    for rel in ["a/model/jaeger_38341_1.4M_fragment_classes.yaml", "a/model/jaeger_38341_1.4M_fragment_project.yaml",
+                "a/model/jaeger_38341_1.4M_fragment.weights.h5", "a/model/README.txt", "b/deep/er/model/jaeger_57341_1.5M_fragment_classes.yaml",
+                "c/not_model/jaeger_1_x_fragment_classes.yaml", "d/model/WRes_1024.h5"]:
+        (root / rel).write_text("x")
+
+
+def test_available_models_scan_matches_reference(tmp_path):
+    """`AvailableModels(path).info` and `get_model_id` (utils/misc.py:334-396) on a synthetic registry: same model names,
+    same graph / classes / project / weights paths.  Compared with the reference's own class when the checkout is mounted."""
+    import sys
+    from jaeger_b200.predict import available_models, get_model_id
+    _model_tree(tmp_path)
+    got = available_models([str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c"), str(tmp_path / "d")])
+    assert set(got) >= {"jaeger_38341_1.4M_fragment", "jaeger_38341_1.4M_fragment_embedding", "jaeger_57341_1.5M_fragment"}
+    assert "jaeger_1_x_fragment" not in got                                  # only directories named `model` are scanned
+    m = got["jaeger_38341_1.4M_fragment"]
+    assert m["graph"].name == "jaeger_38341_1.4M_fragment_graph" and m["classes"].name.endswith("_classes.yaml")
+    assert m["project"].name.endswith("_project.yaml") and m["weights"].name.endswith(".weights.h5")
+    assert get_model_id("jaeger_38341_1.4M_fragment") == "38341_1.4M"
+    ref_src = Path("/root/reference/src")
+    if not ref_src.exists():
+        return
+    sys.path.insert(0, str(ref_src))
+    try:
+        from jaeger.utils.misc import AvailableModels, get_model_id as ref_id
+    finally:
+        sys.path.remove(str(ref_src))
+    want = AvailableModels(path=[str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c"), str(tmp_path / "d")]).info
+    assert set(want) == set(got)
+    for name, parts in want.items():
+        assert {k: Path(v) for k, v in parts.items() if v is not None} == {k: Path(v) for k, v in got[name].items()}, name
+    for name in want:
+        if name.count("_") >= 2:
+            assert ref_id(name) == get_model_id(name)
+
+
+def test_driver_rejects_cpu_and_bad_precision_before_touching_a_device(tmp_path):
+    from jaeger_b200.predict import run_core
+    fa = tmp_path / "x.fasta"
+    fa.write_text(">a\n" + "ACGT" * 600 + "\n")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", cpu=True)
+    with pytest.raises(ValueError, match="precision"):
+        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", precision="int8")
