@@ -193,7 +193,43 @@ def string_processor_config(spec: ModelSpec) -> dict[str, Any]:
     if not cfg["seq_onehot"]:
         cfg["codon_depth"] = 1
     cfg["masking"] = bool(cfg.get("masking", False))
+    if "crop_size" in cfg:                          # nnlib/inference.py:466-482: the trained fragment length
+        cfg.setdefault("crop_units", "codon")
+        cfg["crop_size_codons"], cfg["crop_size_nt"] = resolve_crop(cfg)
     return cfg
+
+
+def resolve_crop(sp: dict[str, Any]) -> tuple[int, int]:
+    """seqops/crop.py:74-93: (codons, nucleotides) of a string_processor config; nt = 3 * codons + 5."""
+    if "crop_size" not in sp:
+        raise ValueError("string_processor config must define 'crop_size'")
+    size = sp["crop_size"]
+    if not isinstance(size, int) or isinstance(size, bool) or size <= 0:
+        raise ValueError(f"crop_size must be a positive integer, got {size!r}")
+    units = sp.get("crop_units", "codon")
+    if units == "codon":
+        return size, 3 * size + 5
+    if units == "nucleotide":
+        return (size - 5) // 3, size
+    raise ValueError(f"crop_units must be 'codon' or 'nucleotide', got {units!r}")
+
+
+def crop_length_warning(trained_codons: int | None, trained_nt: int | None, fsize: int) -> str | None:
+    """commands/predict.py:36-64: the warning `jaeger predict` logs when --fsize does not match the model's trained
+    fragment length (None when it matches or nothing is known)."""
+    if trained_codons is not None:
+        runtime_codons = (int(fsize) - 5) // 3
+        if runtime_codons == trained_codons:
+            return None
+        nt_hint = f" ({trained_nt} nt)" if trained_nt is not None else ""
+        prefer = trained_nt if trained_nt is not None else "used at training"
+        return (f"runtime --fsize {fsize} maps to {runtime_codons} codon frames, but the model was trained on {trained_codons} "
+                f"codons{nt_hint}. Fixed-length architectures (e.g. hyena) may degrade or collapse to a single class at a "
+                f"different length; prefer --fsize {prefer} for this model.")
+    if trained_nt is not None and int(fsize) != int(trained_nt):
+        return (f"runtime --fsize {fsize} differs from the model's trained fragment length ({trained_nt} nt). Fixed-length "
+                f"architectures (e.g. hyena) may degrade at a different length; prefer --fsize {trained_nt} for this model.")
+    return None
 
 
 # ---- weights ---------------------------------------------------------------------------------

@@ -153,6 +153,13 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
             raise ValueError(f"model {model_name!r} not found; available: {sorted(info)}")
         engine = B200Engine(info[model_name], device=device, workspace_gb=workspace_gb)
         model_id = get_model_id(model_name)
+    spc = getattr(engine, "string_processor_config", None) or {}        # predict.py:752-766
+    if spc.get("crop_size_nt") is not None:
+        logger.info(f"model trained fragment length: {spc.get('crop_size_codons')} codons ({spc['crop_size_nt']} nt)")
+    from .modelspec import crop_length_warning
+    crop_msg = crop_length_warning(spc.get("crop_size_codons"), spc.get("crop_size_nt"), fsize)
+    if crop_msg is not None:
+        logger.warning(crop_msg)
     out_dir = Path(kwargs["output"]) / model_id                          # predict.py:551
     out_dir.mkdir(parents=True, exist_ok=True)
     base = input_path.stem

@@ -345,3 +345,36 @@ def test_saved_model_bundle_maps_onto_the_layer_list(tmp_path, variant):
     other = parse_project(small_config())
     with pytest.raises(ValueError, match="does not match"):
         weights_from_bundle(other, tensors)
+
+
+def test_crop_resolution_and_fsize_warning_match_the_reference():
+    """seqops/crop.py (resolve_crop, the 3 * codons + 5 rule) and commands/predict.py:36-64 (_crop_length_warning):
+    the known answers of the reference's tests/unit/test_crop.py / test_predict_crop_warning.py, and -- when the checkout
+    is mounted -- the reference's own pure-Python functions over a sweep."""
+    import sys
+    from jaeger_b200.modelspec import crop_length_warning, resolve_crop
+    assert resolve_crop({"crop_size": 665}) == (665, 2000) and resolve_crop({"crop_size": 2000, "crop_units": "nucleotide"}) == (665, 2000)
+    assert resolve_crop({"crop_size": 498}) == (498, 1499) and resolve_crop({"crop_size": 1500, "crop_units": "nucleotide"}) == (498, 1500)
+    for bad in ({}, {"crop_size": 0}, {"crop_size": "665"}, {"crop_size": 10, "crop_units": "bp"}):
+        with pytest.raises(ValueError):
+            resolve_crop(bad)
+    assert crop_length_warning(665, 2000, 2000) is None and crop_length_warning(None, None, 1234) is None
+    assert "498 codon frames" in crop_length_warning(665, 2000, 1500) and "prefer --fsize 2000" in crop_length_warning(665, 2000, 1500)
+    assert crop_length_warning(None, 2000, 2000) is None and "differs from the model's trained fragment length (2000 nt)" in crop_length_warning(None, 2000, 1500)
+    cfg = standin_1p4m_config()
+    cfg["model"]["string_processor"]["crop_size"] = 665
+    sp = string_processor_config(parse_project(cfg))
+    assert (sp["crop_size_codons"], sp["crop_size_nt"], sp["crop_units"]) == (665, 2000, "codon")
+    ref_src = Path("/root/reference/src")
+    if not ref_src.exists():
+        return
+    sys.path.insert(0, str(ref_src))
+    try:
+        from jaeger.seqops import crop as rcrop
+    finally:
+        sys.path.remove(str(ref_src))
+    for size in (1, 5, 6, 165, 498, 665, 681, 2000, 2048):
+        for units in ("codon", "nucleotide"):
+            if units == "nucleotide" and size < 6:
+                continue
+            assert resolve_crop({"crop_size": size, "crop_units": units}) == rcrop.resolve_crop({"crop_size": size, "crop_units": units})
