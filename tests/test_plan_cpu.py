@@ -378,3 +378,41 @@ def test_crop_resolution_and_fsize_warning_match_the_reference():
             if units == "nucleotide" and size < 6:
                 continue
             assert resolve_crop({"crop_size": size, "crop_units": units}) == rcrop.resolve_crop({"crop_size": size, "crop_units": units})
+
+
+def test_host_window_planner_fuzz_vs_reference_window_indices():
+    """Property test (hypothesis): the native planner equals `_window_indices` (seqops/io.py:38-71) -- the reference's own
+    function when the checkout is mounted, else the oracle restatement -- for arbitrary lengths, window sizes, strides
+    and dynamic-stride thresholds, including the banker's-rounding ties of `round(i * (L - fsize) / (n - 1))`."""
+    import sys
+    import types
+    from hypothesis import given, settings, strategies as st
+    from oracle import seqwin
+    ref_fn = None
+    if Path("/root/reference/src").exists():
+        sys.path.insert(0, "/root/reference/src")
+        saved = sys.modules.get("pyfastx")
+        sys.modules.setdefault("pyfastx", types.ModuleType("pyfastx"))
+        sys.modules.setdefault("pydustmasker", types.ModuleType("pydustmasker"))
+        try:
+            from jaeger.seqops import io as rio
+            ref_fn = rio._window_indices
+        except Exception:
+            ref_fn = None
+        finally:
+            sys.path.remove("/root/reference/src")
+            if saved is None:
+                sys.modules.pop("pyfastx", None)
+        assert ref_fn is not None, "the reference's seqops.io did not import with the pyfastx / pydustmasker stubs"
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.integers(1, 4096), st.integers(0, 60000), st.integers(1, 5000), st.booleans(), st.sampled_from([1.0, 1.5, 3.0, 10.0, 25.0]))
+    def check(fsize, extra, stride, dyn, thr):
+        seqlen = fsize + extra
+        want = (ref_fn or seqwin.window_indices)(seqlen, fsize, stride, dyn, thr)
+        assert seqwin.window_indices(seqlen, fsize, stride, dyn, thr) == list(want)
+        _, start, nb, ordinal, last = B200Engine.plan_windows(np.array([seqlen]), fsize, stride, dyn, thr)
+        assert start.tolist() == list(want), (seqlen, fsize, stride, dyn, thr)
+        assert (nb == fsize).all() and last.tolist() == [0] * (len(want) - 1) + [1]
+
+    check()
