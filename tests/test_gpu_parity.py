@@ -91,6 +91,10 @@ def test_tokens_bit_exact_vs_reference_encoder_golden(standin):
     z = np.load(G / "tokens_2000.npz")
     tok, _, _ = _encode_seqs(eng, [str(s) for s in z["seqs"]], 2000)
     assert np.array_equal(tok, z["tokens"])
+    z = np.load(G / "tokens_more_crops.npz")                       # crops 2048 / 500 from the same reference encoder
+    for crop in (2048, 500):
+        tok, _, _ = _encode_seqs(eng, [str(s) for s in z[f"seqs_{crop}"]], crop)
+        assert np.array_equal(tok[:, :, :z[f"tokens_{crop}"].shape[2]], z[f"tokens_{crop}"]), crop
 
 
 @pytest.mark.parametrize("crop", [2000, 2048, 1500, 500, 301])

@@ -75,6 +75,17 @@ def test_encoder_matches_reference_numba_encoder():
     assert (tok == 0).any()          # the N / IUPAC window produced unknown codons
 
 
+@pytest.mark.parametrize("crop,lc", [(2048, 681), (500, 165)])
+def test_encoder_matches_reference_numba_encoder_other_crops(crop, lc):
+    """Crops 2048 / 500 (the `health` geometry and BASELINE config 3): tests/golden/tokens_more_crops.npz from the
+    reference's numba encoder (tests/golden/make_token_goldens_more_crops.py)."""
+    z = np.load(G / "tokens_more_crops.npz")
+    tok = oenc.encode_windows([str(s) for s in z[f"seqs_{crop}"]], crop)
+    assert tok.shape == z[f"tokens_{crop}"].shape == (len(z[f"seqs_{crop}"]), 6, lc)
+    assert np.array_equal(tok, z[f"tokens_{crop}"])
+    assert (tok == 0).any()
+
+
 def test_frame_lengths_known_answers():
     # reference tests/unit/test_crop.py, test_inference_crop.py: 2000 -> 665, 1500 -> 498; SURVEY: 2048 -> 681, 500 -> 165
     for n, lc in [(2000, 665), (1500, 498), (2048, 681), (500, 165)]:
