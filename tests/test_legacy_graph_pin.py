@@ -98,3 +98,46 @@ def test_v2_oracle_conv_shares_the_graph_pinned_padding_rule():
         a = ofw._conv1d_tf(x, w, d, "same")
         b = oleg._conv_same(x, w, None, d)
         assert a.shape == (3, length, 5) and torch.allclose(a, b, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["default", "all_labels"])
+def test_config1_tables_oracle_pipeline_vs_reference_end_to_end(tag):
+    """BASELINE config 1 end to end: tests/golden/config1_*_jaeger.tsv is what the reference's own fragment_generator +
+    serialized TF graph (interpreted) + pred_to_dict_legacy + generate_summary_legacy + bundled reliability model write for
+    the health FASTA (tests/golden/make_config1_goldens.py).  The oracle pipeline the GPU driver test is held against
+    (oracle windows -> legacy encoder -> oracle/legacy.forward -> oracle legacy tables) reproduces it: identical contig ids,
+    lengths, labels, second labels, window counts and run-length summaries; scores / entropy / reliability to 1.5e-3."""
+    import io
+    import pandas as pd
+    from jaeger_b200 import codon_tables as ct
+    from oracle import encode as oenc
+    from oracle import legacy as oleg
+    from oracle import seqwin
+    z = np.load(G / "legacy_default.npz")
+    recs = [(str(n), str(s)) for n, s in zip(z["names"], z["seqs"])]
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    ref = oleg.forward(_weights(), _health_tokens())
+    zp = np.load(G / "legacy_post.npz")
+    ood = {k[4:]: zp[k] for k in zp.files if k.startswith("ood_") and k != "ood_windows"}
+    meta = [np.array([str(v).encode() for v in col]) for col in zip(*[
+        (x.header, x.index, int(x.is_last), x.ordinal, x.seqlen, x.g, x.c, x.a, x.t, x.gc_skew) for x in wins])]
+    all_labels = {0: "bacteria", 1: "phage", 2: "eukarya", 3: "archaea"}
+    labels = ["non-phage", "phage", "non-phage", "non-phage"] if tag == "default" else [all_labels[i] for i in range(4)]
+    cols, _ = oleg.summary_legacy(ref["output"], ref["embedding"], tuple(meta), 2000, ood, labels, all_labels,
+                                  {1: "eukarya", 2: "archaea", 3: "bacteria", 0: ""}, 1)
+    got = pd.DataFrame(cols)
+    want = pd.read_csv(G / f"config1_{tag}_jaeger.tsv", sep="\t", keep_default_na=False)
+    assert len(want) == 9 and want["prediction"].tolist() == ["phage"] * 9        # the health contigs are phages
+    shared = [c for c in want.columns if c in got.columns]
+    assert {"contig_id", "length", "prediction", "entropy", "reliability_score", "phage_score", "phage_var", "#_phage_windows",
+            "window_summary", "G+C", "N%"} <= set(shared)
+    for c in shared:
+        w = want[c]
+        if c in ("terminal_repeats", "repeat_length"):
+            continue
+        try:
+            wf = w.to_numpy(dtype=np.float64)
+        except (ValueError, TypeError):
+            assert [str(v) for v in got[c]] == [str(v) for v in w], c
+            continue
+        assert np.allclose(got[c].to_numpy(dtype=np.float64), wf, atol=1.5e-3), (c, got[c].tolist(), w.tolist())
