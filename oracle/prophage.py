@@ -6,6 +6,8 @@ Restates
   * `merge_overlapping_ranges`  postprocess/helpers.py:604-632   (pinned: tests/golden/merge_ranges.json)
   * `scale_range`               postprocess/helpers.py:656-675
 
+The flow of `segment` around its two third-party calls is pinned on the reference's own function run with both calls
+stubbed by this file's restatements (tests/golden/make_segment_goldens.py -> segment_cases.json).
 PARITY UNPINNED for the two third-party calls inside `segment` (neither library is installed
 here, neither is vendored by the reference):
   * ruptures >= 1.1.9 `KernelCPD(kernel="linear", min_size=3, jump=1).predict(pen=p)`: restated

@@ -295,3 +295,27 @@ def test_driver_rejects_cpu_and_bad_precision_before_touching_a_device(tmp_path)
         run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", cpu=True)
     with pytest.raises(ValueError, match="precision"):
         run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", precision="int8")
+
+
+def test_segment_flow_vs_reference_golden():
+    """The reference's own `logits_to_df_v2` + `segment` (postprocess/prophages.py:99-153, 524-602) run with ruptures / kneed
+    replaced by stubs that return the oracle's restatements (tests/golden/make_segment_goldens.py): the oracle's `segment`
+    reproduces every range and score -- including the reference's quirks: the stretch before the first breakpoint is never a
+    range, scores are those of the ranges BEFORE the interval merge, contigs not longer than the cutoff are skipped."""
+    cases = json.loads((G / "segment_cases.json").read_text())
+    assert len(cases) == 7
+    for c in cases:
+        rng = np.random.default_rng(c["seed"])
+        z = rng.normal(0.0, 1.2, (c["t"], 6)).astype(np.float32)
+        z[:, 0] += 2.0
+        for a, b, lift in c["islands"]:
+            z[a:b, 1] += lift
+        if c["skipped"]:
+            assert c["ranges"] == [] and c.get("short")
+            continue
+        ranges, scores = opro.segment(opro.smooth_scores(z)[:, 1], c["sens"])
+        assert [list(map(int, r)) for r in ranges] == c["ranges"], (c["seed"], ranges, c["ranges"])
+        assert np.allclose(np.asarray(scores, dtype=np.float64), np.asarray(c["scores"]), atol=1e-9), c["seed"]
+    by = {c["seed"]: c for c in cases}
+    assert by[4]["ranges"] == [[470, 500]]                       # the island at the contig start is not reported
+    assert len(by[5]["ranges"]) == 2 and len(by[5]["scores"]) == 5
