@@ -82,3 +82,14 @@ def prophage_genomes():
     cords = {"genome1___with___commas": [[[100, 104], [200, 221], [300, 303], [0, 3]], np.array([4.25, 7.5, 2.125, 1.75])],
              "plasmid": [[[10, 20]], np.array([3.0])]}
     return recs, cords
+
+
+def dust_contigs():
+    """Contigs with low-complexity stretches (homopolymers, di- / tri-nucleotide repeats, a repeat that straddles a window
+    boundary, lower-case input, N runs) between random sequence, plus a short contig for the two-pass mode."""
+    rng = np.random.default_rng(64)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), n))
+    return [("lc1", rnd(700) + "A" * 90 + rnd(900) + "AC" * 60 + rnd(1500) + "GGT" * 40 + rnd(800)),
+            ("lc2,comma", rnd(1950) + "T" * 120 + rnd(2200) + "N" * 40 + rnd(300) + "CA" * 35 + rnd(1000)),
+            ("plain", rnd(2600)), ("lower", (rnd(400) + "G" * 70 + rnd(1700)).lower() + rnd(300)),
+            ("short", rnd(300) + "AT" * 50 + rnd(400)), ("tiny", rnd(120))]

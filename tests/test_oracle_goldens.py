@@ -173,3 +173,25 @@ def test_legacy_postprocess_vs_reference_golden():
         want = pd.read_csv(G / f"summary_legacy_{tag}.tsv", sep="\t", keep_default_na=False)
         for col in got.columns:
             assert got[col].tolist() == want[col].tolist(), (tag, col)
+
+
+def test_fragment_windows_with_dustmask_flow_vs_reference():
+    """fragment_generator(dustmask=True) of the reference with pydustmasker stubbed by the oracle's SDUST
+    (tests/golden/make_dust_flow_goldens.py): the oracle's window generator with the same soft-masks gives the same rows --
+    windows cut from the soft-masked, upper-cased record, case-sensitive base counts, gc_skew strings, the short pass."""
+    import zlib
+    from oracle import dust as odust
+    from tests.helpers import dust_contigs
+    gold = json.loads((G / "fragments_dustmask.json").read_text())
+    recs = dust_contigs()
+    masks = {n: odust.mask_bits(s.strip().upper()) for n, s in recs}
+    assert any(np.asarray(m).any() for m in masks.values())
+    for key, kw in {"2000_1500": dict(fragsize=2000, stride=1500), "2000_1500_short": dict(fragsize=2000, stride=1500, min_len=500, max_len=1999),
+                    "500_500": dict(fragsize=500, stride=500)}.items():
+        got = []
+        for w in seqwin.fragment_windows(recs, kw["fragsize"], kw["stride"], softmasks=masks, min_len=kw.get("min_len"), max_len=kw.get("max_len")):
+            f = w.csv().split(",")
+            got.append([zlib.crc32(f[0].encode()), len(f[0])] + f[1:])
+        assert got == gold[key], key
+    masked = [r for r in gold["500_500"] if int(r[7]) + int(r[8]) + int(r[9]) + int(r[10]) < r[1]]
+    assert len(masked) >= 8                                    # soft-masked bases do not count as A / C / G / T
