@@ -319,3 +319,20 @@ def test_segment_flow_vs_reference_golden():
     by = {c["seed"]: c for c in cases}
     assert by[4]["ranges"] == [[470, 500]]                       # the island at the contig start is not reported
     assert len(by[5]["ranges"]) == 2 and len(by[5]["scores"]) == 5
+
+
+def test_refined_columns_join_vs_reference_generate_summary(tmp_path):
+    """collect.py:534-550: the reference's own generate_summary(refined_contig=...) (tests/golden/make_refine_summary_golden.py)
+    against the product's join -- same six columns in the same order, NaN cells for contigs without a refined call (so the
+    integer counts print as floats), refined rows that match no contig dropped."""
+    import pandas as pd
+    from jaeger_b200.refine import MERGE_COLUMNS, merge_into_summary
+    base = pd.read_csv(G / "summary.tsv", sep="\t")
+    base["contig_id"] = base["contig_id"].str.replace(",", "___")            # the join runs before the ids are restored
+    refined = pd.DataFrame(json.loads((G / "refined_contig.json").read_text()))
+    out = merge_into_summary(base, refined)
+    out["contig_id"] = out["contig_id"].str.replace("___", ",")
+    out.to_csv(tmp_path / "s.tsv", sep="\t", index=False, float_format="%.3f")
+    want = (G / "summary_refined.tsv").read_text()
+    assert (tmp_path / "s.tsv").read_text() == want
+    assert want.splitlines()[0].split("\t")[-5:] == MERGE_COLUMNS[1:]
