@@ -93,3 +93,24 @@ def dust_contigs():
             ("lc2,comma", rnd(1950) + "T" * 120 + rnd(2200) + "N" * 40 + rnd(300) + "CA" * 35 + rnd(1000)),
             ("plain", rnd(2600)), ("lower", (rnd(400) + "G" * 70 + rnd(1700)).lower() + rnd(300)),
             ("short", rnd(300) + "AT" * 50 + rnd(400)), ("tiny", rnd(120))]
+
+
+def refine_case(seed=11):
+    """Seeded window logits of 10 contigs with exact ties, near-tied bacteria / plasmid and phage / virus stretches, plus
+    per-class thresholds (one class disabled with -inf): the `--refine` test case."""
+    rng = np.random.default_rng(seed)
+    n_win = [1, 2, 3, 5, 40, 7, 3, 150, 4, 33]
+    W = sum(n_win)
+    z = rng.normal(0.0, 1.6, (W, 6)).astype(np.float32)
+    z[10:14] = z[9]                                    # identical windows
+    z[20, 3] = z[20, 4] = z[20].max() + 1.0            # exact tie between bacteria and plasmid at the top
+    z[21, :] = 0.0                                     # all equal
+    z[22, 0] = z[22, 1] = 2.5; z[22, 2:] = -1.0        # phage / virus tie
+    z[60:75, 3] += 3.0; z[60:75, 4] += 2.8             # bacteria ~ plasmid: merged labels
+    z[100:130, 0] += 4.0; z[100:130, 1] += 3.9         # phage ~ virus
+    offsets = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
+    headers = [f"ctg___{i}" for i in range(len(n_win))]
+    classes = ["phage", "virus", "archaea", "bacteria", "plasmid", "eukarya"]
+    taus = {c: {"logit": 0.4 + 0.15 * i, "margin": 0.2 + 0.1 * i, "n": 50} for i, c in enumerate(classes)}
+    taus["archaea"] = {"logit": float("-inf"), "margin": float("-inf"), "n": 2}
+    return z, offsets, headers, taus

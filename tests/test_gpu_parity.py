@@ -855,22 +855,8 @@ def test_dustmask_kernel_vs_sdust_oracle(standin):
 
 
 def _refine_case(seed=11):
-    rng = np.random.default_rng(seed)
-    n_win = [1, 2, 3, 5, 40, 7, 3, 150, 4, 33]
-    W = sum(n_win)
-    z = rng.normal(0.0, 1.6, (W, 6)).astype(np.float32)
-    z[10:14] = z[9]                                    # identical windows
-    z[20, 3] = z[20, 4] = z[20].max() + 1.0            # exact tie between bacteria and plasmid at the top
-    z[21, :] = 0.0                                     # all equal
-    z[22, 0] = z[22, 1] = 2.5; z[22, 2:] = -1.0        # phage / virus tie
-    z[60:75, 3] += 3.0; z[60:75, 4] += 2.8             # bacteria ~ plasmid: merged labels
-    z[100:130, 0] += 4.0; z[100:130, 1] += 3.9         # phage ~ virus
-    offsets = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
-    headers = [f"ctg___{i}" for i in range(len(n_win))]
-    from oracle import refine as orf
-    taus = {c: {"logit": 0.4 + 0.15 * i, "margin": 0.2 + 0.1 * i, "n": 50} for i, c in enumerate(orf.CLASSES)}
-    taus["archaea"] = {"logit": float("-inf"), "margin": float("-inf"), "n": 2}
-    return z, offsets, headers, taus
+    from tests.helpers import refine_case
+    return refine_case(seed)
 
 
 @pytest.mark.parametrize("mode,split,allow", [("gated", "half", False), ("weighted", "full", True), ("unweighted", "half", True)])

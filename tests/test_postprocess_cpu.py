@@ -336,3 +336,21 @@ def test_refined_columns_join_vs_reference_generate_summary(tmp_path):
     want = (G / "summary_refined.tsv").read_text()
     assert (tmp_path / "s.tsv").read_text() == want
     assert want.splitlines()[0].split("\t")[-5:] == MERGE_COLUMNS[1:]
+
+
+def test_refine_window_labels_vs_reference_source():
+    """add_score_features + refine executed from the reference's own source (postprocess/refinement.py:39-137) behind a
+    four-method stand-in for polars (tests/golden/make_refine_window_goldens.py): top / second class -- exact ties between
+    logits included --, margins and refined labels of every window equal the oracle's, with and without the merge rules."""
+    from oracle import refine as orf
+    from tests.helpers import refine_case
+    gold = json.loads((G / "refine_windows.json").read_text())
+    z, _, _, taus = refine_case()
+    feat = orf.add_score_features(z)
+    for tag, tt, kw in (("case", taus, {}), ("no_merge", {c: {"logit": 0.0, "margin": 0.3} for c in orf.CLASSES}, dict(merge_bp=False, merge_pv=False))):
+        g = gold[tag]
+        assert feat["top_class"].tolist() == g["top_class"] and feat["second_class"].tolist() == g["second_class"]
+        assert np.array_equal(feat["margin"], np.asarray(g["margin"]))
+        assert orf.refine(feat, tt, **kw).tolist() == g["refined_prediction"], tag
+    assert {"unknown", "bacteria_or_plasmid", "virus_any"} <= set(gold["case"]["refined_prediction"])
+    assert gold["case"]["top_class"][21] == "phage" and gold["case"]["second_class"][21] == "plasmid"     # all-equal row: argmax first, argsort[-2]
