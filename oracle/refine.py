@@ -3,10 +3,9 @@
 NumPy restatement of postprocess/refinement.py:39-247 (`add_score_features`, `refine`, `aggregate_contig`) and of
 the driver glue commands/predict.py:115-155 (`_build_refined_contig_df`).  The reference implements these on polars
 (>= 1.0, not vendored, not installable here), so the module cannot be imported as it is.
-Pinned: the known answers of the reference's own tests/unit/test_refinement.py, and `add_score_features` + `refine` run from
-the reference's source behind a four-method polars stand-in (tests/golden/make_refine_window_goldens.py); both restated
-against this file in tests/test_postprocess_cpu.py.  PARITY UNPINNED for `aggregate_contig`'s polars expressions beyond
-those known answers.  Conventions fixed here where the libraries leave a choice:
+Pinned: the known answers of the reference's own tests/unit/test_refinement.py, and `add_score_features` + `refine` + `aggregate_contig`
+run from the reference's source behind a polars stand-in (tests/golden/make_refine_window_goldens.py); both restated
+against this file in tests/test_postprocess_cpu.py.  PARITY UNPINNED: polars' own expression evaluation (summation order).  Conventions fixed here where the libraries leave a choice:
   * window logits are widened to float64 before any arithmetic (polars builds the frame from Python row dicts);
   * top class = np.argmax (first maximum); second class = position -2 of a STABLE ascending argsort (NumPy's
     argsort on 6 elements; ties between exactly equal logits are the only case where the sort kind matters);

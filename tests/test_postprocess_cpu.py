@@ -354,3 +354,28 @@ def test_refine_window_labels_vs_reference_source():
         assert orf.refine(feat, tt, **kw).tolist() == g["refined_prediction"], tag
     assert {"unknown", "bacteria_or_plasmid", "virus_any"} <= set(gold["case"]["refined_prediction"])
     assert gold["case"]["top_class"][21] == "phage" and gold["case"]["second_class"][21] == "plasmid"     # all-equal row: argmax first, argsort[-2]
+
+
+def test_refine_contig_aggregation_vs_reference_source():
+    """aggregate_contig executed from the reference's own source (postprocess/refinement.py:140-247) behind a small evaluator
+    of the polars expressions it builds (tests/golden/make_refine_window_goldens.py): gating, margin weights, merged-label
+    multipliers, the min_windows filter, the contig-level top-2 and hedged calls equal the oracle's in all three modes."""
+    from oracle import refine as orf
+    from tests.helpers import refine_case
+    gold = json.loads((G / "refine_windows.json").read_text())["contigs"]
+    z, offsets, headers, taus = refine_case()
+    feat = orf.add_score_features(z)
+    lab = orf.refine(feat, taus)
+    ids = np.repeat(np.array(headers, dtype=object), np.diff(offsets))
+    for mode, split, allow in (("gated", "half", False), ("weighted", "full", True), ("unweighted", "half", True)):
+        want = gold[f"{mode}_{split}_{int(allow)}"]
+        got = orf.aggregate_contig(ids, z, lab, feat["margin"], mode=mode, min_windows=3, merge_split=split,
+                                   allow_merged_contig_call=allow, contig_hedge_margin=5.0)
+        assert list(got) == list(want), mode
+        for cid, w in want.items():
+            for k, v in w.items():
+                if isinstance(v, float):
+                    assert got[cid][k] == pytest.approx(v, rel=1e-12, abs=1e-12), (mode, cid, k)
+                else:
+                    assert got[cid][k] == v, (mode, cid, k, got[cid][k], v)
+    assert {"virus_any", "bacteria_or_plasmid"} <= {w["contig_call"] for w in gold["unweighted_half_1"].values()}
