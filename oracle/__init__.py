@@ -19,8 +19,10 @@ Pinning status (see DESIGN.md "Oracle"):
   * legacy (`default`) conv-stack logits: pinned on the reference's serialized TensorFlow graph, executed by the
     NumPy interpreter oracle/tfgraph.py (tests/golden/legacy_graph_outputs.npz, tests/test_legacy_graph_pin.py).
   * layer-list (v2) conv-stack logits: PARITY UNPINNED - no such SavedModel is vendored and TensorFlow/Keras cannot
-    be installed here, so the forward pass is a restatement of nnlib/v2/layers.py checked against the reference
-    tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py).
+    be installed here, so the forward pass is a restatement of nnlib/v2/layers.py.  Its layer functions are pinned one by one on the
+    reference's own `call` bodies executed on a NumPy stand-in for TensorFlow (tests/golden/v2_layers.npz) and on the
+    reference tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py); what stays unpinned is
+    Keras' mask hand-over between layers.
   * change-point segmentation (ruptures KernelCPD + kneed): PARITY UNPINNED - restated from
     the published algorithms (PELT with L2 cost; Kneedle), libraries absent.
   * low-complexity soft-masking (pydustmasker): PARITY UNPINNED - restated from the published

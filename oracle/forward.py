@@ -17,8 +17,12 @@ Mask carried out of a ResidualBlock: Keras 3 `Layer._set_mask_metadata` keeps a 
 inner layer already attached to the output tensor, so the block output carries conv2's
 (twice-dilated) mask, not the block input's mask.
 
-PARITY UNPINNED for logits: TensorFlow cannot be installed in the build container, so this
-restatement is checked only against the reference tests' mask / pooling known answers
+Pinned per layer: every layer function below equals, to 1e-12, the reference's own `call` body executed on a NumPy stand-in
+for TensorFlow (tests/golden/tf_standin.py, make_v2_layer_goldens.py -> v2_layers.npz: MaskedConv1D in all three mask modes,
+MaskedBatchNorm at inference incl. return_nmd, MaskedDYT, NMDLayer, GeLU, masked max / average pooling), and the reference
+tests' mask / pooling known answers.  PARITY UNPINNED for whole-model logits: TensorFlow / Keras cannot be installed in the
+build container, so how Keras hands masks from layer to layer (the block comment above) is this file's reading, checked only
+against the reference tests' mask / pooling known answers
 (tests/unit/test_mask_mode.py, test_masked_pooling.py, test_nnlib_v2_nmd.py, test_inference_crop.py) -- see
 tests/test_oracle_layer_known_answers.py.
 """

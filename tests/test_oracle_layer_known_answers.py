@@ -142,3 +142,43 @@ def test_mask_threshold_rule_on_random_masks(mode, thr):
         padded = np.concatenate([np.zeros(6, bool), m, np.zeros(6, bool)])     # total pad d*(k-1) = 12, left 6
         cnt = np.array([sum(padded[i + t * d] for t in range(k)) for i in range(length)])
         np.testing.assert_array_equal(_out_mask(m, mode, k, "same", d), cnt >= thr)
+
+
+def test_oracle_layers_vs_reference_call_bodies():
+    """tests/golden/v2_layers.npz = the reference's own `call` bodies (MaskedConv1D in all three mask modes, MaskedBatchNorm at
+    inference with return_nmd, MaskedDYT, NMDLayer, GeLU, masked global max / average pooling) executed on a NumPy stand-in
+    for TensorFlow (tests/golden/make_v2_layer_goldens.py): every oracle restatement equals them to 1e-12, masks exactly."""
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "v2_layers.npz")
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)   # noqa: E731
+    x, mask = T(z["x"]), T(z["mask"].astype(np.float64))
+    kernel, bias = T(z["conv_kernel"]), T(z["conv_bias"])
+    for padding in ("valid", "same"):
+        for dil in (1, 3):
+            for mode in ("any", "majority", "strict"):
+                tag = f"conv_{padding}_d{dil}_{mode}"
+                y, om = fwd.masked_conv1d(x, mask, kernel, bias, dil, padding, None, mask_mode=mode)
+                assert np.abs(y.numpy() - z[tag + "_y"]).max() < 1e-12, tag
+                assert np.array_equal(om.numpy() > 0, z[tag + "_mask"]), tag
+    y, om = fwd.masked_conv1d(x, None, kernel, None, 1, "valid", "gelu")
+    assert om is None and np.abs(y.numpy() - z["conv_nomask_gelu_y"]).max() < 1e-12
+    assert not np.array_equal(z["conv_same_d3_any_mask"], z["conv_same_d3_strict_mask"])
+    h, hm = T(z["h"]), T(z["h_mask"].astype(np.float64))
+    bn = {"gamma": T(z["bn_gamma"]), "beta": T(z["bn_beta"]), "mean": T(z["bn_moving_mean"]), "var": T(z["bn_moving_variance"])}
+    assert np.abs(fwd.batchnorm(h, bn).numpy() - z["bn_y"]).max() < 1e-12            # inference BN does not re-mask
+    assert np.abs(fwd.batchnorm(h, bn).numpy() - z["bn_y_nomask"]).max() < 1e-12
+    assert np.abs(fwd.nmd_vector(h, hm, bn["mean"]).numpy() - z["bn_nmd"]).max() < 1e-12       # return_nmd: NMD of the norm's input
+    assert np.abs(fwd.nmd_vector(h, None, bn["mean"]).numpy() - z["bn_nmd_nomask"]).max() < 1e-12
+    dw = {"alpha": T(z["dyt_alpha"]), "gamma": T(z["dyt_gamma"]), "beta": T(z["dyt_beta"])}
+    assert np.abs(fwd.dyt(h, dw, hm).numpy() - z["dyt_y"]).max() < 1e-12
+    assert np.abs(fwd.dyt(h, dw, None).numpy() - z["dyt_y_nomask"]).max() < 1e-12
+    mm = T(z["nmd_moving_mean"])
+    assert np.abs(fwd.nmd_vector(h, hm, mm).numpy() - z["nmd_y"]).max() < 1e-12
+    assert np.abs(fwd.nmd_vector(h, None, mm).numpy() - z["nmd_y_nomask"]).max() < 1e-12
+    assert np.abs(fwd.gelu_tanh(h).numpy() - z["gelu_y"]).max() < 1e-12
+    pm = T(z["pool_mask"].astype(np.float64))
+    assert np.abs(fwd.masked_global_max(h, pm).numpy() - z["maxpool_y"]).max() < 1e-12
+    assert np.abs(fwd.masked_global_max(h, None).numpy() - z["maxpool_y_nomask"]).max() < 1e-12
+    assert np.abs(fwd.masked_global_avg(h, pm).numpy() - z["avgpool_y"]).max() < 1e-12
+    assert np.abs(fwd.masked_global_avg(h, None).numpy() - z["avgpool_y_nomask"]).max() < 1e-12
+    assert np.all(z["maxpool_y"][1] == 0.0) and np.all(z["avgpool_y"][1] == 0.0)              # the fully masked sample
