@@ -1,6 +1,6 @@
 """Layer-level goldens of the fragment-model (v2) layers, computed by EXECUTING THE REFERENCE'S OWN `call` BODIES
 (nnlib/v2/layers.py: GeLU, MaskedConv1D in all three mask modes, MaskedBatchNorm at inference incl. return_nmd, MaskedDYT,
-MaskedGlobalMaxPooling, MaskedGlobalAvgPooling; nnlib/v2/nmd.py: NMDLayer) on top of tests/golden/tf_standin.py, a NumPy
+MaskedGlobalMaxPooling, MaskedGlobalAvgPooling, OODSignalLayer; nnlib/v2/nmd.py: NMDLayer) on top of tests/golden/tf_standin.py, a NumPy
 stand-in for the ~30 TensorFlow symbols those bodies use (TensorFlow / Keras are not installable here).  The layer math --
 what is masked, what the mask becomes, epsilons, which statistics, the NMD definition, pooling sentinels -- is the
 reference's code; the primitives (conv1d with TF SAME padding, reductions, tanh-GELU) are the stand-in's, the conv padding
@@ -89,6 +89,15 @@ def main():
     out["pool_mask"] = pm
     out["maxpool_y"], out["maxpool_y_nomask"] = np.asarray(L.MaskedGlobalMaxPooling().call(t(h), mask=t(pm))), np.asarray(L.MaskedGlobalMaxPooling().call(t(h), mask=None))
     out["avgpool_y"], out["avgpool_y_nomask"] = np.asarray(L.MaskedGlobalAvgPooling().call(t(h), mask=t(pm))), np.asarray(L.MaskedGlobalAvgPooling().call(t(h), mask=None))
+    # ---- OODSignalLayer (reliability_model.mode nmd_plus_signals) -----------------------------------------
+    logits = rng.normal(0, 2.5, (9, 6))
+    logits[0] = 1.0                                  # uniform
+    logits[1, 2] = logits[1, 4] = 7.0                # tie at the top
+    logits[2, 0] = 40.0                              # one dominant class
+    nmd_vec = rng.normal(0, 0.4, (9, 20))
+    out["ood_logits"], out["ood_nmd"] = logits, nmd_vec
+    signals = ["max_prob", "entropy", "energy", "margin", "nmd_norm"]
+    out["ood_y"] = np.asarray(L.OODSignalLayer(signals=signals).call({"logits": t(logits), "nmd": t(nmd_vec)}))
     np.savez_compressed(OUT / "v2_layers.npz", **out)
     print("written", OUT / "v2_layers.npz", len(out), "arrays")
 

@@ -164,9 +164,17 @@ def install():
     tf.reduce_mean = lambda x, axis=None, keepdims=False: t(np.mean(np.asarray(x), axis=_axes(axis), keepdims=keepdims))
     tf.reduce_max = lambda x, axis=None, keepdims=False: t(np.max(np.asarray(x), axis=_axes(axis), keepdims=keepdims))
     tf.stop_gradient = _passthrough
-    tf.math = _NS(rsqrt=lambda x: t(1.0 / np.sqrt(np.asarray(x))), tanh=lambda x: t(np.tanh(np.asarray(x))),
+    tf.reduce_logsumexp = lambda x, axis=None, keepdims=False: t(torch.logsumexp(torch.as_tensor(np.asarray(x, dtype=np.float64)), dim=_axes(axis), keepdim=keepdims).numpy())
+    tf.norm = lambda x, ord="euclidean", axis=None, keepdims=False: t(np.sqrt(np.sum(np.square(np.asarray(x)), axis=_axes(axis), keepdims=keepdims)))
+    tf.math = _NS(log=lambda x: t(np.log(np.asarray(x))), rsqrt=lambda x: t(1.0 / np.sqrt(np.asarray(x))), tanh=lambda x: t(np.tanh(np.asarray(x))),
                                     divide_no_nan=lambda a, b: t(np.where(np.asarray(b) == 0, 0.0, np.asarray(a) / np.where(np.asarray(b) == 0, 1.0, np.asarray(b)))))
-    tf.nn = _NS(conv1d=conv1d, gelu=gelu, bias_add=lambda x, b, data_format=None: t(np.asarray(x) + np.asarray(b)),
+    def _top_k(x, k=1):
+        v = -np.sort(-np.asarray(x), axis=-1)[..., :k]
+        return _NS(values=t(v))
+
+    def _softmax(x, axis=-1):
+        return t(torch.softmax(torch.as_tensor(np.asarray(x, dtype=np.float64)), dim=int(axis)).numpy())
+    tf.nn = _NS(softmax=_softmax, top_k=_top_k, conv1d=conv1d, gelu=gelu, bias_add=lambda x, b, data_format=None: t(np.asarray(x) + np.asarray(b)),
                                   moments=lambda x, axes, keepdims=False: (t(np.mean(np.asarray(x), axis=_axes(axes), keepdims=keepdims)),
                                                                            t(np.var(np.asarray(x), axis=_axes(axes), keepdims=keepdims))))
     ker = types.ModuleType("tensorflow.keras")

@@ -182,3 +182,6 @@ def test_oracle_layers_vs_reference_call_bodies():
     assert np.abs(fwd.masked_global_avg(h, pm).numpy() - z["avgpool_y"]).max() < 1e-12
     assert np.abs(fwd.masked_global_avg(h, None).numpy() - z["avgpool_y_nomask"]).max() < 1e-12
     assert np.all(z["maxpool_y"][1] == 0.0) and np.all(z["avgpool_y"][1] == 0.0)              # the fully masked sample
+    sig = fwd.ood_signals(T(z["ood_logits"]), T(z["ood_nmd"]), ["max_prob", "entropy", "energy", "margin", "nmd_norm"])
+    assert np.abs(sig.numpy() - z["ood_y"]).max() < 1e-12                                      # OODSignalLayer (layers.py:1632-1666)
+    assert z["ood_y"][1, 3] == 0.0 and abs(z["ood_y"][0, 0] - 1 / 6) < 1e-12                   # tie: margin 0; uniform: max_prob 1/6
