@@ -19,7 +19,8 @@ inner layer already attached to the output tensor, so the block output carries c
 
 Pinned per layer: every layer function below equals, to 1e-12, the reference's own `call` body executed on a NumPy stand-in
 for TensorFlow (tests/golden/tf_standin.py, make_v2_layer_goldens.py -> v2_layers.npz: MaskedConv1D in all three mask modes,
-MaskedBatchNorm at inference incl. return_nmd, MaskedDYT, NMDLayer, GeLU, masked max / average pooling), and the reference
+MaskedBatchNorm at inference incl. return_nmd, MaskedDYT, NMDLayer, GeLU, masked max / average pooling, OODSignalLayer, and
+ResidualBlockStack / ResidualBlock.call = `residual_stack` below under the stand-in's Keras 3 `__call__` mask rules), and the reference
 tests' mask / pooling known answers.  PARITY UNPINNED for whole-model logits: TensorFlow / Keras cannot be installed in the
 build container, so how Keras hands masks from layer to layer (the block comment above) is this file's reading, checked only
 against the reference tests' mask / pooling known answers
@@ -156,6 +157,25 @@ def _t(a, dtype):
     return torch.as_tensor(np.asarray(a), dtype=dtype)
 
 
+def residual_stack(x, mask, blocks, c, dtype=torch.float32):
+    """ResidualBlockStack / ResidualBlock.call (layers.py:2696-2704, 1882-1915) on x [B,6,L,C] carrying `mask` (or None):
+    returns (output, the mask it carries, NMD vector of the last block's bn2 when c["return_nmd"] else None)."""
+    block_nmd = None
+    for bi, blk in enumerate(blocks):
+        m_in = mask if c["use_masking"] else None
+        h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
+                              c["dilation"], "same")
+        h = _act(_norm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}, m1 if m_in is not None else None), c["activation"])
+        h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
+                               c["dilation"], "same")
+        if c.get("return_nmd") and bi == len(blocks) - 1:          # layers.py:1897-1898, 2696-2704
+            block_nmd = nmd_vector(h2, m2 if m_in is not None else None, _t(blk["bn2"]["mean"], dtype))
+        h2 = _norm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()}, m2 if m_in is not None else None)
+        x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
+        mask = m2 if m_in is not None else mask
+    return x, mask, block_nmd
+
+
 def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str, np.ndarray]:
     """tokens [B, 6, L] uint8 (0 = unknown / padding) -> prediction, embedding, nmd, reliability."""
     tok = torch.as_tensor(np.asarray(tokens).astype(np.int64))
@@ -188,18 +208,9 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
         elif layer.kind == "act":
             x = _act(x, c.get("activation"))
         elif layer.kind == "resblock":
-            for bi, blk in enumerate(lw["blocks"]):
-                m_in = mask if c["use_masking"] else None
-                h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
-                                      c["dilation"], "same")
-                h = _act(_norm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}, m1 if m_in is not None else None), c["activation"])
-                h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
-                                       c["dilation"], "same")
-                if c.get("return_nmd") and bi == len(lw["blocks"]) - 1:          # layers.py:1897-1898, 2696-2704
-                    nmds.append(nmd_vector(h2, m2 if m_in is not None else None, _t(blk["bn2"]["mean"], dtype)))
-                h2 = _norm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()}, m2 if m_in is not None else None)
-                x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
-                mask = m2 if m_in is not None else mask
+            x, mask, block_nmd = residual_stack(x, mask, lw["blocks"], c, dtype)
+            if block_nmd is not None:
+                nmds.append(block_nmd)
         else:
             raise NotImplementedError(layer.kind)
     feat = masked_global_max(x, mask) if spec.pooling == "max" else masked_global_avg(x, mask)

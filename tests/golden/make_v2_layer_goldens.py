@@ -4,8 +4,10 @@ MaskedGlobalMaxPooling, MaskedGlobalAvgPooling, OODSignalLayer; nnlib/v2/nmd.py:
 stand-in for the ~30 TensorFlow symbols those bodies use (TensorFlow / Keras are not installable here).  The layer math --
 what is masked, what the mask becomes, epsilons, which statistics, the NMD definition, pooling sentinels -- is the
 reference's code; the primitives (conv1d with TF SAME padding, reductions, tanh-GELU) are the stand-in's, the conv padding
-rule being pinned separately on the reference's serialized TF graph (tests/test_legacy_graph_pin.py).  Keras' mask
-propagation BETWEEN layers is not exercised: every layer is called alone with an explicit mask.
+rule being pinned separately on the reference's serialized TF graph (tests/test_legacy_graph_pin.py).  The single layers are called
+alone with explicit masks.  The last section runs ResidualBlockStack / ResidualBlock.call from the reference source; there the
+mask hand-over between the inner layers follows the stand-in's restatement of Keras 3's `Layer.__call__` rules (see
+tf_standin.Layer) -- the block's CODE is the reference's, those four rules are not executed from Keras.
 Writes tests/golden/v2_layers.npz (inputs are seeded and stored, outputs float64).
 
 usage:  python tests/golden/make_v2_layer_goldens.py
@@ -98,6 +100,52 @@ def main():
     out["ood_logits"], out["ood_nmd"] = logits, nmd_vec
     signals = ["max_prob", "entropy", "energy", "margin", "nmd_norm"]
     out["ood_y"] = np.asarray(L.OODSignalLayer(signals=signals).call({"logits": t(logits), "nmd": t(nmd_vec)}))
+    # ---- ResidualBlockStack: the reference's block code under the stand-in's Keras-3 __call__ mask rules -------------------
+    from tf_standin import get_keras_mask
+    cb, kb, db = 8, 5, 3
+    xb = rng.normal(size=(2, 6, 41, cb))
+    mb = rng.random((2, 6, 41)) < 0.75
+    mb[0, :, 8:25] = False
+    mb[1, :, 30:] = False
+    out["block_x"], out["block_mask"] = xb, mb
+    for norm in ("masked_batchnorm", "masked_dyt"):
+        for masking in (True, False):
+            kw = dict(filters=cb, kernel_size=kb, dilation_rate=db, use_bias=True, norm_type=norm, use_masking=masking, name="resblock_1")
+            if norm == "masked_batchnorm":
+                kw["return_nmd"] = True
+            stack = L.ResidualBlockStack(2, (6, None, cb), **kw)
+            xin = t(xb)
+            if masking:
+                xin._keras_mask = t(mb)
+            stack(xin)                                           # builds the sub-layers
+            tag = f"block_{'bn' if norm == 'masked_batchnorm' else 'dyt'}_{int(masking)}"
+            for bi, blk in enumerate(stack.blocks):
+                for cname in ("conv1", "conv2"):
+                    conv = getattr(blk, cname)
+                    conv.kernel, conv.bias = t(rng.normal(size=(kb, cb, cb)) * 0.25), t(rng.normal(size=cb) * 0.2)
+                    out[f"{tag}_b{bi}_{cname}_kernel"], out[f"{tag}_b{bi}_{cname}_bias"] = np.asarray(conv.kernel), np.asarray(conv.bias)
+                for nname in ("bn1", "bn2"):
+                    nl_ = getattr(blk, nname)
+                    if norm == "masked_batchnorm":
+                        nl_.gamma, nl_.beta = t(rng.uniform(0.5, 1.5, cb)), t(rng.normal(0, 0.2, cb))
+                        nl_.moving_mean, nl_.moving_variance = t(rng.normal(0, 0.3, cb)), t(rng.uniform(0.4, 1.6, cb))
+                        names = ("gamma", "beta", "moving_mean", "moving_variance")
+                    else:
+                        nl_.alpha, nl_.gamma, nl_.beta = t(np.array([rng.uniform(0.3, 0.7)])), t(rng.uniform(0.5, 1.5, cb)), t(rng.normal(0, 0.2, cb))
+                        names = ("alpha", "gamma", "beta")
+                    for a in names:
+                        out[f"{tag}_b{bi}_{nname}_{a}"] = np.asarray(getattr(nl_, a))
+            xin = t(xb)
+            if masking:
+                xin._keras_mask = t(mb)
+            res = stack(xin)
+            y = res[0] if isinstance(res, (list, tuple)) else res
+            out[tag + "_y"] = np.asarray(y)
+            if isinstance(res, (list, tuple)):
+                out[tag + "_nmd"] = np.asarray(res[1])
+            m = get_keras_mask(y)
+            out[tag + "_outmask"] = np.zeros(0, bool) if m is None else np.asarray(m).astype(bool)
+            print(tag, np.asarray(y).shape, "outgoing mask:", None if m is None else int(np.asarray(m).sum()), "of", mb.size, "(input", int(mb.sum()), ")")
     np.savez_compressed(OUT / "v2_layers.npz", **out)
     print("written", OUT / "v2_layers.npz", len(out), "arrays")
 

@@ -89,11 +89,30 @@ def _axes(axis):
     return None if axis is None else (tuple(int(a) for a in axis) if np.ndim(axis) else int(axis))
 
 
+def get_keras_mask(x):
+    if isinstance(x, (list, tuple)):
+        return [get_keras_mask(v) for v in x]
+    return getattr(x, "_keras_mask", None)
+
+
 class Layer:
-    """keras.layers.Layer as far as the layers' __init__ / build / call need it."""
+    """keras.layers.Layer as far as the layers' __init__ / build / call need it, plus Keras 3's `__call__` mask rules
+    (keras/src/layers/layer.py, restated from the library's documented behaviour -- Keras itself is not installable here):
+      1. a `mask` argument of `call` that was not passed explicitly is filled from the `_keras_mask` of the first argument;
+      2. after `call`, if the layer `supports_masking`, every output that does not ALREADY carry a mask (one set by an inner
+         layer is kept: `_set_mask_metadata` returns early when all outputs have one) gets
+         `compute_mask(first argument, mask of the first argument)`, outputs and masks paired in order and an existing mask
+         never overwritten; the default `compute_mask` passes the incoming mask through;
+      3. a layer that does not support masking leaves its outputs without a mask;
+      4. `supports_masking` defaults to "the class overrides compute_mask" (`not utils.is_default(self.compute_mask)` in
+         Layer.__init__), so the reference's MaskedAdd -- which overrides compute_mask without setting the flag -- propagates
+         the mask of its first input.
+    Rules 2 and 4 decide which mask leaves a ResidualBlock (conv2's, attached by the inner layers, rather than the block
+    input's); they are written down from the Keras 3 sources as remembered, not executed from them."""
 
     def __init__(self, name=None, dtype=None, trainable=True, **kwargs):
-        self.name, self.trainable, self.supports_masking, self.built = name, trainable, False, False
+        self.name, self.trainable, self.built = name, trainable, False
+        self.supports_masking = type(self).compute_mask is not Layer.compute_mask
         self.compute_dtype = self.variable_dtype = "float32"
 
     def add_weight(self, name=None, shape=(), initializer="zeros", trainable=True, dtype=None, **kw):
@@ -105,8 +124,62 @@ class Layer:
     def build(self, input_shape):
         self.built = True
 
+    def compute_mask(self, inputs, previous_mask=None):
+        return previous_mask
+
     def get_config(self):
         return {}
+
+    def __call__(self, inputs, *args, **kwargs):
+        import inspect
+        if not self.built:
+            first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+            self.build(tuple(np.ndarray.shape.__get__(np.asarray(first))))
+            self.built = True
+        params = inspect.signature(self.call).parameters
+        previous_mask = get_keras_mask(inputs)
+        if "mask" in params and kwargs.get("mask") is None:
+            kwargs["mask"] = previous_mask
+        if "training" in params and "training" not in kwargs:
+            kwargs["training"] = False
+        kwargs = {k: v for k, v in kwargs.items() if k in params or any(p.kind == p.VAR_KEYWORD for p in params.values())}
+        outputs = self.call(inputs, *args, **kwargs)
+        if self.supports_masking:                       # Layer._set_mask_metadata
+            flat = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
+            if not all(get_keras_mask(o) is not None for o in flat):
+                m = self.compute_mask(inputs, previous_mask)
+                if m is not None:
+                    masks = list(m) if isinstance(m, (list, tuple)) else [m]
+                    for o, mk in zip(flat, masks):           # pairs outputs with masks in order; never overwrites
+                        if get_keras_mask(o) is None and mk is not None:
+                            o._keras_mask = mk
+        return outputs
+
+
+class Add(Layer):
+    """keras.layers.Add (used by ResidualBlock when use_masking is off: no masks are around)."""
+
+    def call(self, inputs):
+        return t(sum(np.asarray(v) for v in inputs))
+
+
+class Activation(Layer):
+    """keras.layers.Activation: supports masking, applies keras.activations.get(name) (gelu = the tanh approximation)."""
+
+    def __init__(self, activation, **kwargs):
+        super().__init__(**kwargs)
+        self.supports_masking = True
+        self.activation = activation
+
+    def call(self, inputs):
+        x = np.asarray(inputs)
+        if self.activation == "gelu":
+            return gelu(x, approximate=True)
+        if self.activation == "relu":
+            return t(np.maximum(x, 0.0))
+        if self.activation in (None, "linear"):
+            return t(x)
+        raise NotImplementedError(self.activation)
 
 
 def _passthrough(*a, **k):
@@ -166,7 +239,7 @@ def install():
     tf.stop_gradient = _passthrough
     tf.reduce_logsumexp = lambda x, axis=None, keepdims=False: t(torch.logsumexp(torch.as_tensor(np.asarray(x, dtype=np.float64)), dim=_axes(axis), keepdim=keepdims).numpy())
     tf.norm = lambda x, ord="euclidean", axis=None, keepdims=False: t(np.sqrt(np.sum(np.square(np.asarray(x)), axis=_axes(axis), keepdims=keepdims)))
-    tf.math = _NS(log=lambda x: t(np.log(np.asarray(x))), rsqrt=lambda x: t(1.0 / np.sqrt(np.asarray(x))), tanh=lambda x: t(np.tanh(np.asarray(x))),
+    tf.math = _NS(add_n=lambda xs: t(sum(np.asarray(v) for v in xs)), log=lambda x: t(np.log(np.asarray(x))), rsqrt=lambda x: t(1.0 / np.sqrt(np.asarray(x))), tanh=lambda x: t(np.tanh(np.asarray(x))),
                                     divide_no_nan=lambda a, b: t(np.where(np.asarray(b) == 0, 0.0, np.asarray(a) / np.where(np.asarray(b) == 0, 1.0, np.asarray(b)))))
     def _top_k(x, k=1):
         v = -np.sort(-np.asarray(x), axis=-1)[..., :k]
@@ -178,7 +251,7 @@ def install():
                                   moments=lambda x, axes, keepdims=False: (t(np.mean(np.asarray(x), axis=_axes(axes), keepdims=keepdims)),
                                                                            t(np.var(np.asarray(x), axis=_axes(axes), keepdims=keepdims))))
     ker = types.ModuleType("tensorflow.keras")
-    ker.layers = _NS(Layer=Layer, Add=_Anything, Activation=_Anything)
+    ker.layers = _NS(Layer=Layer, Add=Add, Activation=Activation)
     ker.Model = Layer
     ker.activations = _NS(get=lambda a: None if a in (None, "linear") else (lambda x: gelu(x, approximate=True)) if a == "gelu" else _Anything(),
                                             serialize=lambda a: a)

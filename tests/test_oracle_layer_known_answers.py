@@ -185,3 +185,39 @@ def test_oracle_layers_vs_reference_call_bodies():
     sig = fwd.ood_signals(T(z["ood_logits"]), T(z["ood_nmd"]), ["max_prob", "entropy", "energy", "margin", "nmd_norm"])
     assert np.abs(sig.numpy() - z["ood_y"]).max() < 1e-12                                      # OODSignalLayer (layers.py:1632-1666)
     assert z["ood_y"][1, 3] == 0.0 and abs(z["ood_y"][0, 0] - 1 / 6) < 1e-12                   # tie: margin 0; uniform: max_prob 1/6
+
+
+@pytest.mark.parametrize("norm", ["bn", "dyt"])
+@pytest.mark.parametrize("masking", [1, 0])
+def test_oracle_residual_stack_vs_reference_block_code(norm, masking):
+    """ResidualBlockStack / ResidualBlock.call executed from the reference's source (two blocks, k5, dilation 3; BatchNorm with
+    return_nmd, MaskedDYT; masking on and off) on the NumPy stand-in, whose `Layer.__call__` restates Keras 3's mask rules
+    (tests/golden/tf_standin.py): oracle.forward.residual_stack gives the same block output (1e-12), the same NMD vector and
+    the same outgoing mask -- conv2's, not the block input's."""
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "v2_layers.npz")
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)   # noqa: E731
+    tag = f"block_{norm}_{masking}"
+    blocks = []
+    for bi in range(2):
+        blk = {}
+        for cname in ("conv1", "conv2"):
+            blk[cname] = {"kernel": z[f"{tag}_b{bi}_{cname}_kernel"], "bias": z[f"{tag}_b{bi}_{cname}_bias"]}
+        for nname in ("bn1", "bn2"):
+            if norm == "bn":
+                blk[nname] = {"gamma": z[f"{tag}_b{bi}_{nname}_gamma"], "beta": z[f"{tag}_b{bi}_{nname}_beta"],
+                              "mean": z[f"{tag}_b{bi}_{nname}_moving_mean"], "var": z[f"{tag}_b{bi}_{nname}_moving_variance"]}
+            else:
+                blk[nname] = {a: z[f"{tag}_b{bi}_{nname}_{a}"] for a in ("alpha", "gamma", "beta")}
+        blocks.append(blk)
+    cfg = {"use_masking": bool(masking), "dilation": 3, "activation": "gelu", "return_nmd": norm == "bn"}
+    mask = T(z["block_mask"].astype(np.float64)) if masking else None
+    y, m_out, nmd = fwd.residual_stack(T(z["block_x"]), mask, blocks, cfg, torch.float64)
+    assert np.abs(y.numpy() - z[tag + "_y"]).max() < 1e-12
+    if norm == "bn":
+        assert np.abs(nmd.numpy() - z[tag + "_nmd"]).max() < 1e-12
+    if masking:
+        assert np.array_equal(m_out.numpy() > 0, z[tag + "_outmask"])
+        assert z[tag + "_outmask"].sum() > z["block_mask"].sum()            # two `any` convolutions validate rows next to valid ones
+    else:
+        assert m_out is None and z[tag + "_outmask"].size == 0
