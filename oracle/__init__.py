@@ -23,8 +23,11 @@ Pinning status (see DESIGN.md "Oracle"):
     reference's own `call` bodies executed on a NumPy stand-in for TensorFlow (tests/golden/v2_layers.npz) and on the
     reference tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py); what stays unpinned is
     Keras' mask hand-over between layers.
-  * change-point segmentation (ruptures KernelCPD + kneed): PARITY UNPINNED - restated from
-    the published algorithms (PELT with L2 cost; Kneedle), libraries absent.
-  * low-complexity soft-masking (pydustmasker): PARITY UNPINNED - restated from the published
-    SDUST algorithm (oracle/dust.py), library absent.
+  * flows around un-installable third-party calls are pinned by running the reference's own functions with the call
+    stubbed by this package's restatement: scan_for_terminal_repeats / prophage_report (parasail), segment (ruptures,
+    kneed), fragment_generator(dustmask=True) (pydustmasker), add_score_features / refine / aggregate_contig (polars)
+    -- generators under tests/golden/make_*_goldens.py.
+  * the third-party algorithms themselves stay PARITY UNPINNED: ruptures KernelCPD + kneed (restated from the published
+    PELT / Kneedle algorithms), pydustmasker (published SDUST, oracle/dust.py), parasail's Smith-Waterman tie-breaking
+    (oracle/termini.py), polars' summation order.
 """
