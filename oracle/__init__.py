@@ -21,8 +21,9 @@ Pinning status (see DESIGN.md "Oracle"):
   * layer-list (v2) conv-stack logits: PARITY UNPINNED - no such SavedModel is vendored and TensorFlow/Keras cannot
     be installed here, so the forward pass is a restatement of nnlib/v2/layers.py.  Its layer functions are pinned one by one on the
     reference's own `call` bodies executed on a NumPy stand-in for TensorFlow (tests/golden/v2_layers.npz) and on the
-    reference tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py); what stays unpinned is
-    Keras' mask hand-over between layers.
+    reference tests' mask / pooling / NMD known answers (tests/test_oracle_layer_known_answers.py); the whole representation
+    learner equals the reference's DynamicModelBuilder._build_block run eagerly on that stand-in (tests/golden/v2_model.npz).
+    What stays unpinned is Keras' own `__call__` mask hand-over (four rules restated in tests/golden/tf_standin.py).
   * flows around un-installable third-party calls are pinned by running the reference's own functions with the call
     stubbed by this package's restatement: scan_for_terminal_repeats / prophage_report (parasail), segment (ruptures,
     kneed), fragment_generator(dustmask=True) (pydustmasker), add_score_features / refine / aggregate_contig (polars)

@@ -20,10 +20,11 @@ inner layer already attached to the output tensor, so the block output carries c
 Pinned per layer: every layer function below equals, to 1e-12, the reference's own `call` body executed on a NumPy stand-in
 for TensorFlow (tests/golden/tf_standin.py, make_v2_layer_goldens.py -> v2_layers.npz: MaskedConv1D in all three mask modes,
 MaskedBatchNorm at inference incl. return_nmd, MaskedDYT, NMDLayer, GeLU, masked max / average pooling, OODSignalLayer, and
-ResidualBlockStack / ResidualBlock.call = `residual_stack` below under the stand-in's Keras 3 `__call__` mask rules), and the reference
-tests' mask / pooling known answers.  PARITY UNPINNED for whole-model logits: TensorFlow / Keras cannot be installed in the
-build container, so how Keras hands masks from layer to layer (the block comment above) is this file's reading, checked only
-against the reference tests' mask / pooling known answers
+ResidualBlockStack / ResidualBlock.call = `residual_stack` below under the stand-in's Keras 3 `__call__` mask rules; the whole
+representation learner = the reference's DynamicModelBuilder._build_block run eagerly on the stand-in, v2_model.npz), and the reference
+tests' mask / pooling known answers.  PARITY UNPINNED: TensorFlow / Keras themselves cannot be installed in the
+build container, so the stand-in's four Keras `__call__` mask rules (the block comment above depends on them) are a reading of
+Keras 3, and TF's float32 kernels are not run; the reference tests' mask / pooling known answers are also restated
 (tests/unit/test_mask_mode.py, test_masked_pooling.py, test_nnlib_v2_nmd.py, test_inference_crop.py) -- see
 tests/test_oracle_layer_known_answers.py.
 """

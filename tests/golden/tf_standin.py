@@ -89,6 +89,10 @@ def _axes(axis):
     return None if axis is None else (tuple(int(a) for a in axis) if np.ndim(axis) else int(axis))
 
 
+WEIGHT_PROVIDER = None      # callable(layer name, weight name, shape) -> array; set by a golden generator
+WEIGHT_LOG: list = []
+
+
 def get_keras_mask(x):
     if isinstance(x, (list, tuple)):
         return [get_keras_mask(v) for v in x]
@@ -117,6 +121,10 @@ class Layer:
 
     def add_weight(self, name=None, shape=(), initializer="zeros", trainable=True, dtype=None, **kw):
         shape = tuple(int(s) for s in shape)
+        if WEIGHT_PROVIDER is not None:                      # seeded values, logged in creation order
+            arr = t(np.asarray(WEIGHT_PROVIDER(self.name, name, shape), dtype=np.float64))
+            WEIGHT_LOG.append((self.name, name, arr))
+            return arr
         if callable(initializer) and not isinstance(initializer, str):
             return t(np.asarray(initializer(shape), dtype=np.float64))
         return t(np.ones(shape) if str(initializer) == "ones" else np.zeros(shape))
@@ -161,6 +169,15 @@ class Add(Layer):
 
     def call(self, inputs):
         return t(sum(np.asarray(v) for v in inputs))
+
+
+class Concatenate(Layer):
+    def __init__(self, axis=-1, **kwargs):
+        super().__init__(**kwargs)
+        self.axis = axis
+
+    def call(self, inputs):
+        return t(np.concatenate([np.asarray(v) for v in inputs], axis=self.axis))
 
 
 class Activation(Layer):
@@ -251,7 +268,7 @@ def install():
                                   moments=lambda x, axes, keepdims=False: (t(np.mean(np.asarray(x), axis=_axes(axes), keepdims=keepdims)),
                                                                            t(np.var(np.asarray(x), axis=_axes(axes), keepdims=keepdims))))
     ker = types.ModuleType("tensorflow.keras")
-    ker.layers = _NS(Layer=Layer, Add=Add, Activation=Activation)
+    ker.layers = _NS(Layer=Layer, Add=Add, Activation=Activation, Concatenate=Concatenate)
     ker.Model = Layer
     ker.activations = _NS(get=lambda a: None if a in (None, "linear") else (lambda x: gelu(x, approximate=True)) if a == "gelu" else _Anything(),
                                             serialize=lambda a: a)

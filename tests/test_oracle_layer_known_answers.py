@@ -221,3 +221,67 @@ def test_oracle_residual_stack_vs_reference_block_code(norm, masking):
         assert z[tag + "_outmask"].sum() > z["block_mask"].sum()            # two `any` convolutions validate rows next to valid ones
     else:
         assert m_out is None and z[tag + "_outmask"].size == 0
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_oracle_forward_vs_reference_builder_code(case):
+    """tests/golden/v2_model.npz: the reference's `DynamicModelBuilder._build_block` (nnlib/builder.py:982-1193) run eagerly on the
+    NumPy stand-in -- the reference's layer order, config hand-over, NMD collection / concatenation and pooling over the
+    reference's layer classes.  oracle.forward.forward on the same tokens and weights returns the same pooled features and NMD
+    vector (BatchNorm + max pooling, MaskedDYT + average pooling, masking off), to float32 rounding."""
+    from pathlib import Path
+    from jaeger_b200.modelspec import parse_project
+    z = np.load(Path(__file__).resolve().parent / "golden" / "v2_model.npz")
+    tag = f"m{case}"
+    norm, masking, pooling = z[tag + "_cfg"].tolist()
+    nname = "masked_batchnorm" if norm == "bn" else "masked_dyt"
+    tail = [{"name": "nmd"}, {"name": nname, "config": {}}, {"name": "activation", "config": {"activation": "gelu"}}]
+    block = {"name": "residual_block", "config": {"block_size": 2, "filters": 16, "kernel_size": 5, "dilation_rate": 3, "use_bias": True,
+                                                  **({"norm_type": "masked_dyt"} if norm == "dyt" else {})}}
+    hidden = [{"name": "masked_conv1d", "config": {"filters": 16, "kernel_size": 7, "use_bias": True, "activation": None}}] + tail + [block] + tail + [block] + tail
+    cfg = {"model": {"name": "m", "use_masking": bool(int(masking)), "class_label_map": [{"class": c, "label": i} for i, c in enumerate("abc")],
+                     "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 12},
+                     "string_processor": {"codon": "CODON", "codon_id": "CODON_ID"},
+                     "representation_learner": {"hidden_layers": hidden, "pooling": pooling},
+                     "classifier": {"hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None}}]}}}
+    spec = parse_project(cfg)
+    names = z[tag + "_wnames"].tolist()
+    pos = [0]
+
+    def take(*expected):
+        out = {}
+        for e in expected:
+            assert names[pos[0]].endswith("/" + e), (names[pos[0]], e)
+            out[e] = z[f"{tag}_w{pos[0]:03d}_{e}"]
+            pos[0] += 1
+        return out
+
+    def norm_w():
+        if norm == "dyt":
+            return take("alpha", "gamma", "beta")
+        w = take("gamma", "beta", "moving_mean", "moving_variance")
+        return {"gamma": w["gamma"], "beta": w["beta"], "mean": w["moving_mean"], "var": w["moving_variance"]}
+
+    layers = []
+    for layer in spec.layers:
+        if layer.kind == "conv":
+            layers.append(take("kernel", "bias"))
+        elif layer.kind == "nmd":
+            layers.append(take("moving_mean"))
+        elif layer.kind == "norm":
+            layers.append(norm_w())
+        elif layer.kind == "resblock":
+            blocks = []
+            for _ in range(layer.cfg["block_size"]):
+                c1 = take("kernel", "bias"); b1 = norm_w(); c2 = take("kernel", "bias"); b2 = norm_w()
+                blocks.append({"conv1": c1, "bn1": b1, "conv2": c2, "bn2": b2})
+            layers.append({"blocks": blocks})
+        else:
+            layers.append({})
+    assert pos[0] == len(names)
+    weights = {"embedding": z["embedding_table"], "layers": layers,
+               "classifier": [{"kernel": np.zeros((16, 3)), "bias": np.zeros(3)}]}
+    ref = fwd.forward(spec, weights, z["tokens"], dtype=torch.float64)
+    # forward() hands back float32 arrays: agreement to float32 rounding of the float64 computation
+    assert np.allclose(ref["embedding"], z[tag + "_feat"], rtol=3e-7, atol=1e-6), np.abs(ref["embedding"] - z[tag + "_feat"]).max()
+    assert np.allclose(ref["nmd"], z[tag + "_nmd"], rtol=3e-7, atol=1e-6), np.abs(ref["nmd"] - z[tag + "_nmd"]).max()
