@@ -223,12 +223,9 @@ def test_oracle_residual_stack_vs_reference_block_code(norm, masking):
         assert m_out is None and z[tag + "_outmask"].size == 0
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
-def test_oracle_forward_vs_reference_builder_code(case):
-    """tests/golden/v2_model.npz: the reference's `DynamicModelBuilder._build_block` (nnlib/builder.py:982-1193) run eagerly on the
-    NumPy stand-in -- the reference's layer order, config hand-over, NMD collection / concatenation and pooling over the
-    reference's layer classes.  oracle.forward.forward on the same tokens and weights returns the same pooled features and NMD
-    vector (BatchNorm + max pooling, MaskedDYT + average pooling, masking off), to float32 rounding."""
+def v2_model_case(case: int):
+    """(spec, weights, tokens, golden features, golden NMD) of case `case` of tests/golden/v2_model.npz: the weights the stand-in's
+    seeded provider handed to the reference's layers, re-assembled in creation order into the nested weights dict."""
     from pathlib import Path
     from jaeger_b200.modelspec import parse_project
     z = np.load(Path(__file__).resolve().parent / "golden" / "v2_model.npz")
@@ -281,7 +278,17 @@ def test_oracle_forward_vs_reference_builder_code(case):
     assert pos[0] == len(names)
     weights = {"embedding": z["embedding_table"], "layers": layers,
                "classifier": [{"kernel": np.zeros((16, 3)), "bias": np.zeros(3)}]}
-    ref = fwd.forward(spec, weights, z["tokens"], dtype=torch.float64)
+    return spec, weights, z["tokens"], z[tag + "_feat"], z[tag + "_nmd"]
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_oracle_forward_vs_reference_builder_code(case):
+    """tests/golden/v2_model.npz: the reference's `DynamicModelBuilder._build_block` (nnlib/builder.py:982-1193) run eagerly on the
+    NumPy stand-in -- the reference's layer order, config hand-over, NMD collection / concatenation and pooling over the
+    reference's layer classes.  oracle.forward.forward on the same tokens and weights returns the same pooled features and NMD
+    vector (BatchNorm + max pooling, MaskedDYT + average pooling, masking off), to float32 rounding."""
+    spec, weights, tokens, feat, nmd = v2_model_case(case)
+    ref = fwd.forward(spec, weights, tokens, dtype=torch.float64)
     # forward() hands back float32 arrays: agreement to float32 rounding of the float64 computation
-    assert np.allclose(ref["embedding"], z[tag + "_feat"], rtol=3e-7, atol=1e-6), np.abs(ref["embedding"] - z[tag + "_feat"]).max()
-    assert np.allclose(ref["nmd"], z[tag + "_nmd"], rtol=3e-7, atol=1e-6), np.abs(ref["nmd"] - z[tag + "_nmd"]).max()
+    assert np.allclose(ref["embedding"], feat, rtol=3e-7, atol=1e-6), np.abs(ref["embedding"] - feat).max()
+    assert np.allclose(ref["nmd"], nmd, rtol=3e-7, atol=1e-6), np.abs(ref["nmd"] - nmd).max()

@@ -416,3 +416,17 @@ def test_host_window_planner_fuzz_vs_reference_window_indices():
         assert (nb == fsize).all() and last.tolist() == [0] * (len(want) - 1) + [1]
 
     check()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_plan_compiler_vs_reference_builder_code(case):
+    """The PRODUCT's plan compiler against the reference's own builder + layer code: tests/golden/v2_model.npz is
+    `DynamicModelBuilder._build_block` run eagerly on a NumPy stand-in for TensorFlow (tests/golden/make_v2_model_goldens.py);
+    the fused launch plan compiled from the same weights, executed by the float64 plan interpreter with the kernels' storage
+    semantics (masked storage, masked-row constants, folded norms, embedding folded into the stem), gives the same pooled
+    features and NMD vector."""
+    from tests.test_oracle_layer_known_answers import v2_model_case
+    spec, weights, tokens, feat, nmd = v2_model_case(case)
+    got = run_plan(compile_plan(spec, weights), tokens)
+    assert np.allclose(got["embedding"], feat, rtol=2e-5, atol=2e-5), np.abs(got["embedding"] - feat).max()
+    assert np.allclose(got["nmd"], nmd, rtol=2e-5, atol=2e-5), np.abs(got["nmd"] - nmd).max()
