@@ -268,11 +268,15 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         # postprocess/prophages.py:706-873 without the gene-call refinement)
         from .termini import prophage_report_loaded, write_prophage_report
         t_att = time.time()
-        full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
-        report = prophage_report_loaded(engine, full, regions, fsize, stride)
-        write_prophage_report(report, out_dir / f"{base}_prophages")
-        result["prophage_report"] = report
-        logger.info(f"prophage att-site report ({len(report)} regions) in {time.time() - t_att:.2f} s")
+        result["prophage_report"] = None
+        try:                                              # the reference logs and carries on (predict.py:440-442)
+            full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
+            report = prophage_report_loaded(engine, full, regions, fsize, stride)
+            write_prophage_report(report, out_dir / f"{base}_prophages")
+            result["prophage_report"] = report
+            logger.info(f"prophage att-site report ({len(report)} regions) in {time.time() - t_att:.2f} s")
+        except (ArithmeticError, ValueError, KeyError, IndexError) as e:
+            logger.error(f"an error {e!r} occurred during the prophage report step")
     if kwargs.get("getsequences"):                                        # predict.py:444-455
         from .postprocess import write_fasta_from_results
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
