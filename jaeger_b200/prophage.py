@@ -13,38 +13,52 @@ import torch
 from ._cabi import check, lib
 
 
+def _interp_at_nodes(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """kneed's smoothing step `scipy.interpolate.interp1d(x, y)(x)` written out: interp1d sorts the nodes by x
+    (stable merge sort) and, for 1-D linear interpolation, evaluates with numpy.interp semantics -- a query that
+    equals a node value takes the LAST node of that value in sorted order.  x here are breakpoint counts at
+    pen = 1..9, non-increasing and often tied, so this is not the identity: every member of a tie group gets the
+    y of the group's last member (postprocess/prophages.py:563-568 passes x = counts, y = 0..n-1)."""
+    order = np.argsort(x, kind="mergesort")
+    xs, ys = x[order], y[order]
+    last = np.searchsorted(xs, x, side="right") - 1          # last sorted node with value <= x[i]: x[i] itself is a node
+    return ys[last]
+
+
 def knee_point(x, y, S: float = 1.0):
-    """kneed.KneeLocator(x, y, curve="convex", direction="decreasing") with its defaults
-    (S=1, interp1d = identity on the given points, offline): the x value of the first knee or
-    None.  Restated from kneed's documented steps (library not vendored by the reference)."""
+    """kneed.KneeLocator(x, y, curve="convex", direction="decreasing").knee with the library defaults
+    (S=1, interp_method="interp1d", online=False): the x value at the first knee, or None.
+    Steps (kneed 0.8.x `KneeLocator.__init__` / `find_knee`; call site postprocess/prophages.py:563-573):
+    Ds_y = interp1d(x, y)(x); min-max normalise x and Ds_y; y <- max(y) - y; difference curve; local maxima /
+    minima with >= / <= against both neighbours (argrelextrema, mode="clip"); threshold of a maximum =
+    its height - S * |mean(diff(x_norm))|; walk from the first maximum, a minimum resets the threshold to 0,
+    the first point whose successor falls below the threshold yields x[index of the last maximum]."""
     x = np.asarray(x, dtype=float)
     y = np.asarray(y, dtype=float)
-    if len(x) < 2 or np.ptp(x) == 0 or np.ptp(y) == 0:
+    if len(x) < 2 or np.ptp(x) == 0:
+        return None
+    ds = _interp_at_nodes(x, y)
+    if np.ptp(ds) == 0:
         return None
     xn = (x - x.min()) / (x.max() - x.min())
-    yn = (y - y.min()) / (y.max() - y.min())
+    yn = (ds - ds.min()) / (ds.max() - ds.min())
     yn = yn.max() - yn                                   # convex + decreasing -> knee form
     yd = yn - xn
     n = len(yd)
-    left = yd[np.clip(np.arange(n) - 1, 0, n - 1)]       # argrelextrema(..., mode="clip")
+    left = yd[np.clip(np.arange(n) - 1, 0, n - 1)]
     right = yd[np.clip(np.arange(n) + 1, 0, n - 1)]
-    maxima = np.flatnonzero((yd >= left) & (yd >= right))
-    minima = np.flatnonzero((yd <= left) & (yd <= right))
-    if maxima.size == 0:
+    is_max = (yd >= left) & (yd >= right)
+    is_min = (yd <= left) & (yd <= right)
+    if not is_max.any():
         return None
-    tmx = yd[maxima] - S * abs(np.diff(xn).mean())
-    threshold, threshold_index, mi = None, None, 0
-    for i in range(n):
-        if i < maxima[0]:
-            continue
-        if i == n - 1:
-            break
-        if (maxima == i).any():
-            threshold, threshold_index = tmx[mi], i
-            mi += 1
-        if (minima == i).any():
+    step = abs(np.diff(xn).mean())
+    threshold, threshold_index = None, None
+    for i in range(int(np.argmax(is_max)), n - 1):
+        if is_max[i]:
+            threshold, threshold_index = yd[i] - S * step, i
+        if is_min[i]:
             threshold = 0.0
-        if threshold is not None and yd[i + 1] < threshold:
+        if yd[i + 1] < threshold:
             return x[threshold_index]
     return None
 

@@ -84,46 +84,45 @@ def optimal_partition(x: np.ndarray, pen: float, min_size: int = 3) -> list[int]
 
 
 def knee_locator(x, y, S: float = 1.0):
-    """kneed.KneeLocator(x, y, curve="convex", direction="decreasing"), defaults S=1.0,
-    interp_method="interp1d" (identity on the given points), online=False.  Returns knee x or None.
-
-    1. min-max normalise x and y;  2. transform_y for convex+decreasing: y = y.max() - y;
-    3. difference curve yd = y - x;  4. local maxima / minima with argrelextrema(>=, <=), whose
-    default mode="clip" lets end points qualify;  5. thresholds Tmx = yd[max] - S*|mean(diff(x))|;
-    6. walk the curve from the first maximum: a maximum (re)arms the threshold, a minimum resets
-    it to 0, the first point whose successor drops below the threshold yields x[threshold index]."""
-    x = np.asarray(x, dtype=float)
-    y = np.asarray(y, dtype=float)
-    if len(x) < 2 or x.max() == x.min() or y.max() == y.min():
+    """kneed.KneeLocator(x, y, curve="convex", direction="decreasing").knee, library defaults S=1.0,
+    interp_method="interp1d", online=False (kneed >= 0.8.5 is not installable here; call site
+    /root/reference/src/jaeger/postprocess/prophages.py:563-573).  Written with the same SciPy calls kneed makes
+    -- `scipy.interpolate.interp1d(x, y)(x)` for the smoothing step and `scipy.signal.argrelextrema` for the
+    extrema -- so that ties in x (equal breakpoint counts at neighbouring penalties, where interp1d is NOT the
+    identity) behave as in the library.  Returns the knee's x value or None."""
+    from scipy.interpolate import interp1d
+    from scipy.signal import argrelextrema
+    x = np.asarray(x)
+    y = np.asarray(y)
+    if len(x) < 2:
         return None
-    xn = (x - x.min()) / (x.max() - x.min())
-    yn = (y - y.min()) / (y.max() - y.min())
-    yn = yn.max() - yn
-    yd = yn - xn
-    n = len(yd)
-    mx, mn = [], []
-    for i in range(n):
-        l, r = yd[max(i - 1, 0)], yd[min(i + 1, n - 1)]
-        if yd[i] >= l and yd[i] >= r:
-            mx.append(i)
-        if yd[i] <= l and yd[i] <= r:
-            mn.append(i)
-    if not mx:
+    with np.errstate(all="ignore"):
+        ds_y = interp1d(x, y)(x)                                              # step 1: "fit a smooth line"
+        x_n = (x - x.min()) / (x.max() - x.min())                             # step 2: normalise
+        y_n = (ds_y - ds_y.min()) / (ds_y.max() - ds_y.min())
+    if not (np.isfinite(x_n).all() and np.isfinite(y_n).all()):               # flat x or y: kneed finds nothing usable
         return None
-    step = abs(np.diff(xn).mean())
-    thr, thr_i, used = None, None, 0
-    for i in range(n):
-        if i < mx[0]:
+    y_n = y_n.max() - y_n                                                     # step 3: transform_y(decreasing, convex)
+    y_diff = y_n - x_n
+    maxima = argrelextrema(y_diff, np.greater_equal)[0]                       # step 4 (mode="clip": end points qualify)
+    minima = argrelextrema(y_diff, np.less_equal)[0]
+    if not maxima.size:
+        return None
+    tmx = y_diff[maxima] - S * np.abs(np.diff(x_n).mean())                    # step 5
+    threshold = threshold_index = None                                        # step 6: find_knee
+    k = 0
+    for i in range(len(y_diff)):
+        if i < maxima[0]:
             continue
-        if i == n - 1:
+        if i == len(y_diff) - 1:
             break
-        if i in mx:
-            thr, thr_i = yd[i] - S * step, i
-            used += 1
-        if i in mn:
-            thr = 0.0
-        if thr is not None and yd[i + 1] < thr:
-            return x[thr_i]
+        if (maxima == i).any():
+            threshold, threshold_index = tmx[k], i
+            k += 1
+        if (minima == i).any():
+            threshold = 0.0
+        if y_diff[i + 1] < threshold:
+            return float(x[threshold_index])
     return None
 
 

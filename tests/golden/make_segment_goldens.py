@@ -1,7 +1,8 @@
 """Goldens for prophage region calling from the REFERENCE's own `logits_to_df_v2` + `segment`
 (postprocess/prophages.py:99-153, 524-602).  The two third-party calls inside `segment` -- ruptures.KernelCPD(kernel="linear",
 min_size=3, jump=1).fit(x).predict(pen) and kneed.KneeLocator(...).knee, neither installable here -- are replaced by stubs that
-return the oracle's restatements (oracle/prophage.py: optimal_partition, knee_locator), so the file pins everything the
+return the oracle's restatements (oracle/prophage.py: optimal_partition; knee_locator, which makes the same SciPy calls kneed
+makes -- interp1d(x, y)(x) and argrelextrema -- so tied breakpoint counts behave as in the library), so the file pins everything the
 reference does AROUND them: which penalties' breakpoint lists are kept, the knee / searchsorted index choice (a knee of 0 is
 falsy), ranges from consecutive breakpoints, end-inclusive `.loc[s:e]` means, the sensitivity filter, the unsorted interval
 merge, the length cutoff and the exception path.  ruptures / kneed themselves stay unpinned.
@@ -73,7 +74,13 @@ def case_logits(seed: int, t: int, islands) -> np.ndarray:
 CASES = [dict(seed=1, t=400, islands=[[120, 160, 7.0]], sens=1.5), dict(seed=2, t=700, islands=[[50, 90, 6.0], [300, 420, 8.0], [600, 640, 5.0]], sens=1.5),
          dict(seed=3, t=350, islands=[], sens=1.5), dict(seed=4, t=500, islands=[[0, 30, 9.0], [470, 500, 9.0]], sens=1.5),
          dict(seed=5, t=900, islands=[[100, 130, 4.0], [135, 170, 4.5], [500, 505, 9.0]], sens=0.5),
-         dict(seed=6, t=360, islands=[[10, 350, 6.0]], sens=3.0), dict(seed=7, t=340, islands=[[150, 190, 7.0]], sens=1.5, short=True)]
+         dict(seed=6, t=360, islands=[[10, 350, 6.0]], sens=3.0), dict(seed=7, t=340, islands=[[150, 190, 7.0]], sens=1.5, short=True),
+         # breakpoint counts with long tie groups at different positions (the interp1d step of kneed decides the penalty)
+         dict(seed=8, t=800, islands=[[60, 100, 5.0], [200, 230, 3.0], [400, 460, 6.5], [700, 720, 3.5]], sens=1.5),
+         dict(seed=9, t=1200, islands=[[100, 140, 3.0], [300, 330, 2.5], [500, 620, 7.0], [800, 830, 2.8], [1000, 1100, 4.0]], sens=1.0),
+         dict(seed=10, t=600, islands=[[50, 70, 2.5], [120, 150, 2.7], [200, 240, 2.9], [300, 350, 3.1], [450, 520, 3.3]], sens=1.5),
+         dict(seed=11, t=3333, islands=[[500, 530, 6.0], [1500, 1540, 7.0], [2500, 2600, 5.0]], sens=1.5),
+         dict(seed=12, t=450, islands=[[100, 112, 4.0], [200, 206, 5.0], [300, 303, 9.0]], sens=2.0)]
 
 
 def main():
@@ -89,9 +96,11 @@ def main():
                                   [rng.normal(0, 0.1, c["t"]).round(2)], [np.full(c["t"], 0.5)])
         res = rpro.segment(df, outdir=None, cutoff_length=lc, sensitivity=c["sens"], identifier="phage")
         ranges, scores = res.get("g", [[], []]) if res else [[], []]
-        out.append(dict(c, ranges=[[int(a), int(b)] for a, b in np.asarray(ranges).reshape(-1, 2)], scores=[float(s) for s in scores],
+        col = opro.smooth_scores(z)[:, 1]
+        counts = [len(b) for b in (opro.optimal_partition(col, float(p)) for p in range(1, 10)) if len(b) > 1]
+        out.append(dict(c, counts=counts, ranges=[[int(a), int(b)] for a, b in np.asarray(ranges).reshape(-1, 2)], scores=[float(s) for s in scores],
                         skipped="g" not in res))
-        print(c["seed"], out[-1]["ranges"], [round(s, 3) for s in out[-1]["scores"]], out[-1]["skipped"])
+        print(c["seed"], counts, out[-1]["ranges"], [round(s, 3) for s in out[-1]["scores"]], out[-1]["skipped"])
     (OUT / "segment_cases.json").write_text(json.dumps(out))
 
 

@@ -4,6 +4,8 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
 
 from jaeger_b200 import postprocess as pp
 from jaeger_b200 import prophage as ppro
@@ -35,14 +37,39 @@ def test_merge_ranges_match_reference_golden():
 
 
 def test_knee_point_product_equals_oracle():
+    """Penalty selection of `segment` (postprocess/prophages.py:563-573).  x = breakpoint counts at pen 1..9: non-increasing,
+    usually TIED.  The oracle makes kneed's own SciPy calls (interp1d(x, y)(x), argrelextrema); the product writes the tie
+    rule out.  Both must agree on every tied count vector, and on the known answers of an interp1d-faithful Kneedle."""
+    from scipy.interpolate import interp1d
+    x0 = np.array([9, 7, 5, 5, 3, 3, 3, 2, 2])
+    assert interp1d(x0, np.arange(9))(x0).tolist() == [0, 1, 3, 3, 6, 6, 6, 8, 8]           # not the identity on ties
+    assert ppro._interp_at_nodes(x0.astype(float), np.arange(9.0)).tolist() == [0, 1, 3, 3, 6, 6, 6, 8, 8]
     rng = np.random.default_rng(0)
-    for _ in range(300):
+    n_tied = n_knee = 0
+    for it in range(4000):
         n = int(rng.integers(2, 10))
-        x = np.sort(rng.integers(2, 40, n))[::-1]
+        x = np.sort(rng.integers(2, 14 if it % 2 else 40, n))[::-1]
         y = list(range(n))
-        assert ppro.knee_point(x, y) == opro.knee_locator(x, y)
-    assert ppro.knee_point([9, 7, 5, 5, 3, 3, 3, 2, 2], list(range(9))) == 3.0
-    assert ppro.knee_point([4, 4, 4], [0, 1, 2]) is None
+        got, want = ppro.knee_point(x, y), opro.knee_locator(x, y)
+        assert got == want, (x.tolist(), got, want)
+        n_tied += len(set(x.tolist())) < n
+        n_knee += got is not None
+    assert n_tied >= 1000 and n_knee >= 1000, (n_tied, n_knee)
+    # counts where treating interp1d as the identity picks another penalty (round-1 bug)
+    assert ppro.knee_point([11, 7, 5, 5, 5, 5, 3], list(range(7))) == 7.0
+    assert ppro.knee_point([9, 8, 5, 5, 4, 2, 2, 2], list(range(8))) == 4.0
+    assert opro.knee_locator([11, 7, 5, 5, 5, 5, 3], list(range(7))) == 7.0
+    assert opro.knee_locator([9, 8, 5, 5, 4, 2, 2, 2], list(range(8))) == 4.0
+    assert ppro.knee_point([4, 4, 4], [0, 1, 2]) is None and opro.knee_locator([4, 4, 4], [0, 1, 2]) is None
+    assert ppro.knee_point([5], [0]) is None and opro.knee_locator([5], [0]) is None
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.integers(2, 60), min_size=2, max_size=9))
+def test_knee_point_property_tied_counts(counts):
+    x = np.sort(np.array(counts))[::-1]
+    y = list(range(len(x)))
+    assert ppro.knee_point(x, y) == opro.knee_locator(x, y)
 
 
 def test_x_axis_clamp_reference_known_answer():
@@ -303,7 +330,8 @@ def test_segment_flow_vs_reference_golden():
     reproduces every range and score -- including the reference's quirks: the stretch before the first breakpoint is never a
     range, scores are those of the ranges BEFORE the interval merge, contigs not longer than the cutoff are skipped."""
     cases = json.loads((G / "segment_cases.json").read_text())
-    assert len(cases) == 7
+    assert len(cases) == 12
+    assert sum(len(set(c["counts"])) < len(c["counts"]) for c in cases) >= 10      # tied breakpoint counts are the rule
     for c in cases:
         rng = np.random.default_rng(c["seed"])
         z = rng.normal(0.0, 1.2, (c["t"], 6)).astype(np.float32)
@@ -317,7 +345,7 @@ def test_segment_flow_vs_reference_golden():
         assert [list(map(int, r)) for r in ranges] == c["ranges"], (c["seed"], ranges, c["ranges"])
         assert np.allclose(np.asarray(scores, dtype=np.float64), np.asarray(c["scores"]), atol=1e-9), c["seed"]
     by = {c["seed"]: c for c in cases}
-    assert by[4]["ranges"] == [[470, 500]]                       # the island at the contig start is not reported
+    assert by[4]["ranges"] == [[3, 32], [469, 500]]              # the first range starts at the first breakpoint, never at 0
     assert len(by[5]["ranges"]) == 2 and len(by[5]["scores"]) == 5
 
 
