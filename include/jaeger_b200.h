@@ -179,6 +179,8 @@ double jg_model_flops_per_window(jg_model* m, int32_t lc);
  * jg_model_get_profile synchronises the stream and returns, per layer of the plan, the summed
  * kernel milliseconds, the number of launches and the number of windows they covered. */
 int jg_model_set_profiling(jg_model* m, int32_t on);
+/* "12 x jg::tc2::conv_tc2_kernel<2> + 4 x ..." : the conv kernel the last forward pass launched for every conv layer */
+int jg_model_kernel_names(jg_model* m, char* buf, int32_t n);
 int jg_model_get_profile(jg_model* m, int32_t n_layers, double* ms, int64_t* launches, double* windows);
 
 /* ---- stage 4: per-contig aggregation ------------------------------------------------------
@@ -206,6 +208,13 @@ int jg_smooth_scores(jg_ctx* ctx, const float* d_logits, const int64_t* d_offset
  * d_bkps [n_pen][n] int32: ascending segment ends for each penalty (last = n), d_nbkps [n_pen]. */
 int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size,
                       int32_t n_pen, int32_t* d_bkps, int32_t* d_nbkps);
+/* The same search for every contig of a prophage-mode run in ONE launch pair (the reference loops over the
+ * contigs in Python, postprocess/prophages.py:546-552): contig c owns points [d_offsets[c], d_offsets[c+1]) of the
+ * concatenated signal (total_points in all).  d_bkps [n_pen][total_points]: contig c's list for penalty p starts at
+ * d_bkps[p][d_offsets[c]]; d_nbkps [n_contigs][n_pen]. */
+int jg_segment_scores_batched(jg_ctx* ctx, const double* d_signal, const int64_t* d_offsets, int32_t n_contigs,
+                              int64_t total_points, int32_t min_size, int32_t n_pen, int32_t* d_bkps,
+                              int32_t* d_nbkps);
 
 /* Linear-chain CRF (Viterbi) decoding of every contig's window labels: replaces viterbi_decode
  * (postprocess/helpers.py:393-449) as called per contig from pred_to_dict (collect.py:343-346,

@@ -55,9 +55,11 @@ _SIGNATURES = {
     "jg_model_workspace_bytes": (c_int64, [c_void_p]),
     "jg_model_flops_per_window": (c_double, [c_void_p, c_int32]),
     "jg_model_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "jg_model_kernel_names": (c_int32, [c_void_p, ctypes.c_char_p, c_int32]),
     "jg_model_get_profile": (c_int32, [c_void_p, c_int32, POINTER(c_double), POINTER(c_int64), POINTER(c_double)]),
     "jg_aggregate_contigs": (c_int32, [c_void_p, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "jg_smooth_scores": (c_int32, [c_void_p, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "jg_segment_scores_batched": (c_int32, [c_void_p, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P]),
     "jg_segment_scores": (c_int32, [c_void_p, _P, c_int32, c_int32, c_int32, _P, _P]),
     "jg_legacy_reliability": (c_int32, [c_void_p, _P, c_int64, c_int32, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                         _P, c_int32, _P, _P]),

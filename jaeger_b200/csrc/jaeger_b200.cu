@@ -81,6 +81,7 @@ struct Layer {
   float* w_tap = nullptr;      // stem with an NMD tap on one-hot input: fp16-rounded weights [k][64][cout] + their tap sum [64][cout]
   int shifts_h[jg::kMaxTaps];
   int halo_l = 0, halo_r = 0;
+  const char* last_kernel = "";  // which conv kernel the last forward pass launched for this layer
 };
 
 struct jg_model {
@@ -736,6 +737,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
                        jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
     const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
     if (pair) p.w = L.w2;
+    L.last_kernel = layer_ref ? "jg::conv_ref_kernel" : (pair3 ? "jg::tc2::conv_tc2_kernel<3>" : (pair ? "jg::tc2::conv_tc2_kernel<2>" : "jg::tc::conv_tc_kernel"));
     cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
                             : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
@@ -790,6 +792,21 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   jg::heads_kernel<<<grid_for(n_windows, warps, ctx->num_sms, 16), warps * 32, smem, st>>>(hp);
   ctx->launches++;
   JG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int jg_model_kernel_names(jg_model* m, char* buf, int32_t n) {
+  if (!buf || n <= 0) return fail("jg_model_kernel_names: no buffer");
+  std::vector<std::pair<std::string, int>> seen;
+  for (const Layer& L : m->layers) {
+    if (L.f[LF_KIND] != 1 || !L.last_kernel[0]) continue;
+    bool found = false;
+    for (auto& pr : seen) if (pr.first == L.last_kernel) { pr.second++; found = true; }
+    if (!found) seen.emplace_back(L.last_kernel, 1);
+  }
+  std::string out;
+  for (auto& pr : seen) out += (out.empty() ? "" : " + ") + std::to_string(pr.second) + " x " + pr.first;
+  std::snprintf(buf, static_cast<size_t>(n), "%s", out.c_str());
   return 0;
 }
 
@@ -863,21 +880,38 @@ int jg_smooth_scores(jg_ctx* ctx, const float* d_logits, const int64_t* d_offset
   return 0;
 }
 
-int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size, int32_t n_pen,
-                      int32_t* d_bkps, int32_t* d_nbkps) {
-  if (n <= 0 || n_pen <= 0) return 0;
+namespace {
+int segment_launch(jg_ctx* ctx, const double* d_signal, const long long* d_offsets, int32_t n_single, int64_t total_points,
+                   int32_t n_contigs, int32_t min_size, int32_t n_pen, int32_t* d_bkps, int32_t* d_nbkps) {
   JG_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   double* work = nullptr;
-  const size_t doubles = 2ull * (n + 1) + static_cast<size_t>(n_pen) * (n + 1);
-  const size_t bytes = doubles * 8 + static_cast<size_t>(n_pen) * (n + 1) * 4 + 16;
+  const size_t slots = static_cast<size_t>(total_points) + static_cast<size_t>(n_contigs);
+  const size_t bytes = (2 + static_cast<size_t>(n_pen)) * slots * 8 + static_cast<size_t>(n_pen) * slots * 4 + 16;
   JG_CUDA(cudaMallocAsync(&work, bytes, st));
-  jg::prefix_sums_kernel<<<1, 32, 0, st>>>(d_signal, n, work);
-  jg::segment_scores_kernel<<<n_pen, 256, 32 * 8 + 32 * 4, st>>>(d_signal, n, min_size, n_pen, work, d_bkps, d_nbkps);
+  jg::prefix_sums_kernel<<<n_contigs, 32, 0, st>>>(d_signal, d_offsets, n_single, static_cast<long long>(slots), work);
+  jg::segment_scores_kernel<<<dim3(n_pen, n_contigs), 256, 32 * 8 + 32 * 4, st>>>(d_offsets, n_single, total_points,
+                                                                                static_cast<long long>(slots), min_size, n_pen,
+                                                                                work, d_bkps, d_nbkps);
   ctx->launches += 2;
   JG_CUDA(cudaGetLastError());
   JG_CUDA(cudaFreeAsync(work, st));
   return 0;
+}
+}  // namespace
+
+int jg_segment_scores(jg_ctx* ctx, const double* d_signal, int32_t n, int32_t min_size, int32_t n_pen,
+                      int32_t* d_bkps, int32_t* d_nbkps) {
+  if (n <= 0 || n_pen <= 0) return 0;
+  return segment_launch(ctx, d_signal, nullptr, n, n, 1, min_size, n_pen, d_bkps, d_nbkps);
+}
+
+int jg_segment_scores_batched(jg_ctx* ctx, const double* d_signal, const int64_t* d_offsets, int32_t n_contigs,
+                              int64_t total_points, int32_t min_size, int32_t n_pen, int32_t* d_bkps, int32_t* d_nbkps) {
+  if (n_contigs <= 0 || total_points <= 0 || n_pen <= 0) return 0;
+  if (n_contigs > 65535) return fail("jg_segment_scores_batched: at most 65535 contigs per call");
+  return segment_launch(ctx, d_signal, reinterpret_cast<const long long*>(d_offsets), 0, total_points, n_contigs, min_size,
+                        n_pen, d_bkps, d_nbkps);
 }
 
 int jg_viterbi_decode(jg_ctx* ctx, const float* d_logits, const int64_t* d_offsets, int32_t n_contigs, int64_t n_windows,

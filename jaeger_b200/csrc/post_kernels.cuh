@@ -168,28 +168,44 @@ __global__ void smooth_scores_kernel(const float* __restrict__ logits, const lon
 // every segment >= min_size, total = sum cost + pen * (#segments - 1)... ruptures adds `pen`
 // per change point.  One CTA per penalty; the inner minimisation over the last change point
 // is a block-wide min-reduction (warp shuffles), the outer loop over t is sequential.
-__global__ void prefix_sums_kernel(const double* __restrict__ x, int n, double* __restrict__ work) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double* S1 = work;
-    double* S2 = work + (n + 1);
+// Batched over contigs (blockIdx.y): contig c owns signal points [offsets[c], offsets[c+1]) of the concatenated signal and
+// the work / output slots at the same positions (+ c for the n + 1 sized arrays).  offsets == nullptr: one signal of n points.
+struct SegSlot { long long base, wbase; int n; };
+__device__ __forceinline__ SegSlot seg_slot(const long long* offsets, int n_single, int c) {
+  SegSlot s;
+  if (offsets) { s.base = offsets[c]; s.n = static_cast<int>(offsets[c + 1] - offsets[c]); s.wbase = s.base + c; }
+  else { s.base = 0; s.n = n_single; s.wbase = 0; }
+  return s;
+}
+// work layout for N = total points, C contigs, P penalties, T = N + C:  S1 [T] | S2 [T] | F [P][T] doubles | prev [P][T] ints
+__global__ void prefix_sums_kernel(const double* __restrict__ x, const long long* __restrict__ offsets, int n_single,
+                                   long long total_slots, double* __restrict__ work) {
+  if (threadIdx.x == 0) {
+    const SegSlot sl = seg_slot(offsets, n_single, blockIdx.x);
+    double* S1 = work + sl.wbase;
+    double* S2 = work + total_slots + sl.wbase;
+    const double* xs = x + sl.base;
     double a = 0.0, b = 0.0;
     S1[0] = 0.0; S2[0] = 0.0;
-    for (int i = 0; i < n; ++i) { a += x[i]; b += x[i] * x[i]; S1[i + 1] = a; S2[i + 1] = b; }
+    for (int i = 0; i < sl.n; ++i) { a += xs[i]; b += xs[i] * xs[i]; S1[i + 1] = a; S2[i + 1] = b; }
   }
 }
 
-__global__ void segment_scores_kernel(const double* __restrict__ x, int n, int min_size, int n_pen,
+__global__ void segment_scores_kernel(const long long* __restrict__ offsets, int n_single, long long total_points,
+                                      long long total_slots, int min_size, int n_pen,
                                       double* __restrict__ work, int* __restrict__ bkps, int* __restrict__ nbkps) {
   extern __shared__ double s_red[];
   int* s_idx = reinterpret_cast<int*>(s_red + 32);
   const int pen_i = blockIdx.x;
   if (pen_i >= n_pen) return;
+  const SegSlot sl = seg_slot(offsets, n_single, blockIdx.y);
+  const int n = sl.n;
   const double pen = static_cast<double>(pen_i + 1);
-  const double* S1 = work;                 // prefix sums from prefix_sums_kernel
-  const double* S2 = work + (n + 1);
-  double* F = work + 2 * (n + 1) + static_cast<long long>(pen_i) * (n + 1);
-  int* prev = reinterpret_cast<int*>(work + 2 * (n + 1) + static_cast<long long>(n_pen) * (n + 1)) +
-              static_cast<long long>(pen_i) * (n + 1);
+  const double* S1 = work + sl.wbase;                 // prefix sums from prefix_sums_kernel
+  const double* S2 = work + total_slots + sl.wbase;
+  double* F = work + 2 * total_slots + static_cast<long long>(pen_i) * total_slots + sl.wbase;
+  int* prev = reinterpret_cast<int*>(work + 2 * total_slots + static_cast<long long>(n_pen) * total_slots) +
+              static_cast<long long>(pen_i) * total_slots + sl.wbase;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int t = 0; t <= n; ++t) {
     if (threadIdx.x == 0) { if (t == 0) { F[0] = -pen; prev[0] = 0; } }
@@ -227,13 +243,13 @@ __global__ void segment_scores_kernel(const double* __restrict__ x, int n, int m
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    // backtrack: segment ends in ascending order, last = n
+    // backtrack: segment ends in ascending order, last = n.  Contig c's list for penalty p starts at bkps[p][offsets[c]].
     int cnt = 0;
     int t = n;
-    int* out = bkps + static_cast<long long>(pen_i) * n;
+    int* out = bkps + static_cast<long long>(pen_i) * total_points + sl.base;
     while (t > 0 && prev[t] >= 0) { out[cnt++] = t; t = prev[t]; }
     for (int i = 0; i < cnt / 2; ++i) { const int tmp = out[i]; out[i] = out[cnt - 1 - i]; out[cnt - 1 - i] = tmp; }
-    nbkps[pen_i] = cnt;
+    nbkps[static_cast<long long>(blockIdx.y) * n_pen + pen_i] = cnt;
   }
 }
 

@@ -121,18 +121,23 @@ encode_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __rest
     // re-based copies: code word j holds bases [16j, 16j+16) of the window
     const int sh_c = static_cast<int>(base & 15) * 2;
     const long long w0_c = base >> 4;
+    // loads are bounded by the window's own length (a short contig at the end of the packed buffer must not read
+    // crop bases past it): word j is only fetched when it holds a base of the window, the rest is zero-filled
     for (int j = lane; j < words_c; j += 32) {
-      const uint32_t a = codes[w0_c + j], b = codes[w0_c + j + 1];
+      uint32_t a = 0u, b = 0u;
+      if (j * 16 < n) { a = codes[w0_c + j]; if (sh_c) b = codes[w0_c + j + 1]; }
       s_codes[j] = sh_c ? ((a >> sh_c) | (b << (32 - sh_c))) : a;
     }
     const int sh_b = static_cast<int>(base & 31);
     const long long w0_b = base >> 5;
     for (int j = lane; j < words_b; j += 32) {
-      const uint32_t a = valid[w0_b + j], b = valid[w0_b + j + 1];
+      const bool in_window = j * 32 < n;
+      uint32_t a = 0u, b = 0u;
+      if (in_window) { a = valid[w0_b + j]; if (sh_b) b = valid[w0_b + j + 1]; }
       uint32_t v = sh_b ? ((a >> sh_b) | (b << (32 - sh_b))) : a;
       uint32_t sm = 0;
-      if (soft) {
-        const uint32_t c = soft[w0_b + j], d = soft[w0_b + j + 1];
+      if (soft && in_window) {
+        const uint32_t c = soft[w0_b + j], d = sh_b ? soft[w0_b + j + 1] : 0u;
         sm = sh_b ? ((c >> sh_b) | (d << (32 - sh_b))) : c;
       }
       // clip to the window length

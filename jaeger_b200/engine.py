@@ -87,6 +87,17 @@ class WindowSource:
     outputs: tuple[str, ...] | None = None   # model outputs to bring back (None = all: prediction, reliability, embedding, nmd)
     lazy_meta: bool = False              # build the meta_0..9 byte-string arrays only when they are read
 
+    @classmethod
+    def from_host(cls, names: list[str], bases, offsets: np.ndarray, **kw) -> "WindowSource":
+        """Contigs that already sit in ONE host buffer (`bases`: uint8 NumPy array or CPU torch tensor, all records
+        back to back; `offsets`: n + 1 record starts).  The buffer is used as the H2D source as it is -- pin it
+        (torch `pin_memory()`) for an asynchronous copy."""
+        src = cls(**kw)
+        host = bases if isinstance(bases, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bases, dtype=np.uint8))
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        src._loaded = (list(names), host[:int(off[-1])], off)
+        return src
+
     def load(self) -> tuple[list[str], torch.Tensor, np.ndarray]:
         """(names, bases in one pinned host buffer, record offsets); read once and kept."""
         if getattr(self, "_loaded", None) is not None:
@@ -111,6 +122,7 @@ class PredictResult(dict):
     """The dict `engine.predict` returns.  With lazy meta the ten `meta_i` byte-string arrays of the
     reference protocol (encode.py:304-316) are built from the numeric window table on first access."""
     window_table = None
+    device_outputs = None        # the model outputs as they still sit in HBM (stage 4 reads them there, no re-upload)
 
     def _build(self, key):
         t = self.window_table
@@ -400,7 +412,14 @@ class B200Engine:
         woff = np.concatenate([[0], ends]).astype(np.int64)
         agg = self.aggregate(out["prediction"], out.get("reliability"), self._h2d(woff))
         agg["gc_counts"] = counts
+        agg["_logits"], agg["_window_offsets"] = out["prediction"], woff       # for stage 4b (region calling) on the device
         return agg, w, len(ends)
+
+    def conv_kernel_names(self) -> str:
+        """Which conv kernel the library picked for the launches of the plan (jg_model_kernel_names)."""
+        buf = ctypes.create_string_buffer(4096)
+        check(lib.jg_model_kernel_names(self.model, buf, len(buf)))
+        return buf.value.decode()
 
     # ---- the engine contract --------------------------------------------------------------------
     def predict(self, dataset, no_progress: bool = False) -> dict[str, np.ndarray]:
@@ -516,6 +535,9 @@ class B200Engine:
         # meta_0..meta_9 exactly as process_string_inference forwards them (encode.py:304-316)
         res = PredictResult(y)
         res.window_table = self.windows
+        with torch.cuda.stream(self._stream()):
+            res.device_outputs = {k: (results[0][k] if len(results) == 1 else torch.cat([r[k] for r in results], dim=0))
+                                  for k in ("prediction", "reliability") if k in results[0]}
         if not src.lazy_meta:
             for i in range(10):
                 res[f"meta_{i}"]

@@ -363,3 +363,20 @@ def standin_1p4m_config() -> dict[str, Any]:
             {"name": "dropout", "config": {"rate": 0.1}},
             {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]},
     }}
+
+
+def baseline_500bp_config() -> dict[str, Any]:
+    """train_config/nn_config_500bp_baseline.yaml:17-100 (BASELINE config 3): E64 -> conv(32, k7, VALID) -> BN -> GELU ->
+    2 residual stacks (block_size 2, 32 filters, k3, SAME) -> BN -> GELU -> average pool -> Dense 3; no reliability head."""
+    def conv(f, k):
+        return {"name": "masked_conv1d", "config": {"filters": f, "kernel_size": k, "strides": 1, "dilation_rate": 1,
+                                                    "use_bias": True, "activation": None}}
+    bn_act = [{"name": "masked_batchnorm", "config": {"return_nmd": False}}, {"name": "activation", "config": {"activation": "gelu"}}]
+    block = {"name": "residual_block", "config": {"use_1x1conv": False, "block_size": 2, "filters": 32, "kernel_size": 3, "use_bias": True}}
+    return {"model": {
+        "name": "jaeger_500bp_baseline", "activation": "gelu",
+        "class_label_map": [{"class": c, "label": i} for i, c in enumerate(["chromosome", "virus", "plasmid"])],
+        "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 64},
+        "string_processor": {"seq_onehot": False, "codon": "CODON", "codon_id": "CODON_ID", "crop_size": 500, "masking": False},
+        "representation_learner": {"hidden_layers": [conv(32, 7)] + bn_act + [block, block] + bn_act, "pooling": "average"},
+        "classifier": {"input_shape": 32, "hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None, "use_bias": True}}]}}}

@@ -37,36 +37,30 @@ def shard_contigs(lens: np.ndarray, world: int, fsize: int, stride: int) -> list
     return [np.flatnonzero(owner == r) for r in range(world)]
 
 
-def gather_contig_records(records: torch.Tensor, contig_ids: torch.Tensor, n_total: int, dst: int = 0,
+def gather_contig_records(records: torch.Tensor, shards: list[np.ndarray], n_total: int, dst: int = 0,
                           group=None) -> torch.Tensor | None:
-    """records [n_local, width] (any float/int dtype), contig_ids [n_local] int64 = positions in the
-    global contig list.  Returns on `dst` the [n_total, width] table in global order (rows of
-    contigs nobody reported stay zero), None elsewhere."""
+    """records [len(shards[rank]), width] (any float/int dtype): this rank's per-contig records, row k belonging to
+    global contig shards[rank][k].  `shards` is the partition every rank computed for itself with `shard_contigs`
+    (it is deterministic), so all sizes and destinations are known up front: ONE pre-sized gather, no size
+    exchange, no device-to-host read, nothing that blocks the host.  Returns on `dst` the [n_total, width] table
+    in global contig order (rows nobody owns stay zero), None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if len(shards) != world or records.shape[0] != len(shards[rank]):
+        raise ValueError(f"rank {rank}: {records.shape[0]} records for a shard of {len(shards[rank])} contigs ({len(shards)} shards, world {world})")
     dev = records.device
-    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    m = max(int(s.item()) for s in sizes)
+    m = max(len(s) for s in shards)
     width = records.shape[1]
-    pad_r = torch.zeros((m, width), dtype=records.dtype, device=dev)
-    pad_i = torch.full((m,), -1, dtype=torch.int64, device=dev)
-    pad_r[:records.shape[0]] = records
-    pad_i[:records.shape[0]] = contig_ids
-    if rank == dst:
-        out_r = [torch.zeros_like(pad_r) for _ in range(world)]
-        out_i = [torch.zeros_like(pad_i) for _ in range(world)]
-    else:
-        out_r = out_i = None
-    dist.gather(pad_r, out_r, dst=dst, group=group)
-    dist.gather(pad_i, out_i, dst=dst, group=group)
+    pad = torch.zeros((m, width), dtype=records.dtype, device=dev)
+    pad[:records.shape[0]] = records
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst, group=group)
     if rank != dst:
         return None
     table = torch.zeros((n_total, width), dtype=records.dtype, device=dev)
-    for r_, i_ in zip(out_r, out_i):
-        keep = i_ >= 0
-        table[i_[keep]] = r_[keep]
+    for r_, ids in zip(out, shards):
+        if len(ids):
+            table[torch.as_tensor(np.asarray(ids), dtype=torch.int64, device=dev)] = r_[:len(ids)]
     return table
 
 

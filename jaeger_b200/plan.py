@@ -89,6 +89,8 @@ class ConvLaunch:
     stage: int = 0                        # epilogue fill state while compiling
     kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool
     halvings: int = 0                     # MaxPool(2) stages applied to the frame length before this layer
+    real_cin: int = 0                     # channel counts of the reference layer (before padding to multiples of 64)
+    real_cout: int = 0
 
 
 @dataclass
@@ -330,6 +332,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
     tap_real_widths = {c.tap_slot: c.kernel.shape[2] for c in launches if c.tap_mode}
     for c in launches:
         k, cin, cout = c.kernel.shape
+        c.real_cin, c.real_cout = cin, cout
         cin_p, cout_p = -(-cin // 64) * 64, -(-cout // 64) * 64
         if (cin_p, cout_p) == (cin, cout):
             continue

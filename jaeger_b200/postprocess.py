@@ -110,9 +110,14 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
     wn = _window_numbers(y_pred)
     offsets = _split_points(wn["is_last"])
     rel = y_pred.get("reliability")
+    on_dev = getattr(y_pred, "device_outputs", None) or {}      # the engine's own result: logits are still in HBM
     with torch.cuda.stream(engine._stream()):
-        pred_dev, off_dev = engine._h2d(pred), engine._h2d(offsets)
-        agg = engine.aggregate(pred_dev, engine._h2d(np.ascontiguousarray(rel, np.float32)) if rel is not None else None, off_dev)
+        off_dev = engine._h2d(offsets)
+        pred_dev = on_dev["prediction"] if "prediction" in on_dev else engine._h2d(pred)
+        rel_dev = None
+        if rel is not None:
+            rel_dev = on_dev["reliability"] if "reliability" in on_dev else engine._h2d(np.ascontiguousarray(rel, np.float32))
+        agg = engine.aggregate(pred_dev, rel_dev, off_dev)
         if crf_switch_cost is not None:
             cm = engine.class_map
             names = [n for _, n in sorted(zip(cm["index"], cm["class"]), key=lambda t: int(t[0]))]
@@ -141,6 +146,7 @@ def contig_table(engine, y_pred: dict[str, np.ndarray], fsize: int, term_repeats
         "repeats": term_repeats,
         "gc_mean": np.add.reduceat(gcs, first) / n_win, "ns_mean": np.add.reduceat(ns, first) / n_win,
         "predictions": pred, "gc_skews": wn["gc_skew"], "gcs": gcs,
+        "_pred_dev": pred_dev,                     # the same logits, still in HBM (stage 4b reads them there)
     }
 
 

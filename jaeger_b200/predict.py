@@ -65,7 +65,14 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
     if min_len < fsize:                                                  # predict_legacy.py:57-64
         logger.warning(f"--min-len < --fsize is not supported in legacy prediction mode; using --min-len={fsize}.")
         min_len = fsize
+    if not kwargs.get("legacy_weights"):
+        raise ValueError("-m default needs --legacy-weights: the bundled model's SavedModel variables/ directory "
+                         "(<jaeger>/data/models/test/jaeger_fragment_graph/variables) or an .npz written by jaeger_b200.weights.save_npz_weights")
     wpath = Path(kwargs["legacy_weights"])
+    if not wpath.exists():
+        raise ValueError(f"--legacy-weights {wpath} does not exist")
+    if int(__import__("os").environ.get("WORLD_SIZE", "1")) > 1:
+        raise ValueError("-m default runs in one process (the legacy path is not sharded): launch it without torchrun")
     weights = load_npz_weights(wpath) if wpath.suffix == ".npz" else legacy.weights_from_bundle(read_tf_bundle(wpath))
     ood = legacy.load_ood_params(kwargs["legacy_ood_dir"]) if kwargs.get("legacy_ood_dir") else None
     engine = B200Engine(legacy_weights=weights, all_labels=bool(kwargs.get("getalllabels")), device=int(kwargs.get("physicalid") or 0))
@@ -99,7 +106,7 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
 
 
 def run_core(**kwargs: Any) -> dict[str, Any]:
-    if (kwargs.get("model") or "") == "default":
+    if (kwargs.get("model") or "default") == "default":
         return run_core_legacy(**kwargs)
     from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
     from .parallel import dist_env, merge_rank_frames, shard_contigs, shard_loaded
@@ -108,7 +115,10 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
 
     t0 = time.time()
     input_path = Path(kwargs["input"])
-    model_name = kwargs.get("model") or "standin"
+    model_name = kwargs.get("model") or "default"                           # cli.py: the reference's default model
+    if model_name == "standin" and not kwargs.get("model_path") and not kwargs.get("allow_random_weights"):
+        raise ValueError("-m standin is a RANDOM-INITIALISED network (the benchmark architecture): its tables are meaningless. "
+                         "Pass --allow-random-weights to run it anyway.")
     fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
     # one process per GPU under torchrun: contigs are sharded over the ranks, rank 0 writes
     world, rank, local_rank = dist_env()
@@ -125,12 +135,14 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if precision not in ("fp32", "fp16", "bf16"):
         raise ValueError(f"--precision {precision!r} (use fp32, fp16 or bf16)")
     if precision != "fp16":
-        logger.warning(f"--precision {precision}: the B200 engine always computes with fp16 activations / weights and fp32 "
-                       "accumulation (logits within 4e-3 of fp32); the option is accepted for CLI compatibility")
+        # not silently ignored: this engine has ONE numeric mode (fp16 activations / weights, fp32 accumulation and heads)
+        raise ValueError(f"--precision {precision} is not available on the B200 engine: it computes with fp16 activations and "
+                         "weights, fp32 accumulation and fp32 heads (logits within the tolerance stated in DESIGN.md). Use --precision fp16.")
     # --mem (GB, predict.py:544, 615-623) caps the device workspace the window chunks are sized from
     workspace_gb = float(kwargs["mem"]) if kwargs.get("mem") else 16.0
     device = int(kwargs.get("physicalid") or 0)
     if model_name == "standin" and not kwargs.get("model_path"):
+        logger.warning("RANDOM-INITIALISED stand-in network (--allow-random-weights): the classifications below carry no meaning")
         engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=device, workspace_gb=workspace_gb)
         model_id = "standin"
     elif kwargs.get("model_path"):                                         # predict.py:503-542
@@ -303,7 +315,9 @@ def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="jaeger_b200 predict", description=__doc__.split("\n")[0])
     ap.add_argument("-i", "--input", required=True)
     ap.add_argument("-o", "--output", required=True)
-    ap.add_argument("-m", "--model", default="standin")
+    ap.add_argument("-m", "--model", default="default", help="model name from the config's model_paths; `default` = the bundled legacy model")
+    ap.add_argument("--allow-random-weights", dest="allow_random_weights", action="store_true",
+                    help="required for -m standin: the random-initialised benchmark architecture (meaningless tables)")
     ap.add_argument("--config", default=None, help="config.json with model_paths (utils/misc.py:309-331)")
     ap.add_argument("--legacy-weights", dest="legacy_weights", default=None, help="-m default: SavedModel variables/ dir or .npz")
     ap.add_argument("--legacy-ood-dir", dest="legacy_ood_dir", default=None, help="-m default: dir with the reliability model files")

@@ -95,14 +95,9 @@ def breakpoints(engine, signal_dev: torch.Tensor, min_size: int = 3, n_pen: int 
     return [bk[p, :nb[p]].tolist() for p in range(n_pen)]
 
 
-def segment_contig(engine, logits: np.ndarray, phage_index: int, sensitivity: float = 1.5):
-    """prophages.py:554-595 for one contig: (merged window-index ranges, scores of the kept ranges)."""
-    with torch.cuda.stream(engine._stream()):
-        sm = smooth(engine, engine._h2d(np.ascontiguousarray(logits, np.float32)))
-        col_dev = sm[:, phage_index].contiguous()
-        preds = breakpoints(engine, col_dev)
-        col = col_dev.cpu().numpy()
-    engine.ctx.sync()
+def _select_ranges(preds: list[list[int]], col: np.ndarray, sensitivity: float):
+    """prophages.py:554-595 after the change-point search: keep the penalties with > 1 segment end, pick one by the knee of
+    the breakpoint counts (searchsorted fallback), ranges = consecutive ends, end-inclusive means, sensitivity filter, merge."""
     bkpts = [b for b in preds if len(b) > 1]
     if not bkpts:
         return [], np.array([])
@@ -121,20 +116,70 @@ def segment_contig(engine, logits: np.ndarray, phage_index: int, sensitivity: fl
         return [], np.array([])
 
 
+def segment_device(engine, logits_dev: torch.Tensor, offsets: np.ndarray, phage_index: int, sensitivity: float = 1.5,
+                   n_pen: int = 9, min_size: int = 3):
+    """Stage 4b for ALL contigs of a run at once: logits_dev [W, n_cls] fp32 in HBM, contig c = windows
+    offsets[c]:offsets[c+1].  One smoothing launch and one change-point launch pair cover every contig (jg_smooth_scores,
+    jg_segment_scores_batched: grid = penalties x contigs); one D2H brings the segment ends and the phage column back for the
+    scalar knee / filter / merge logic.  Returns [(ranges, scores)] per contig."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    nc, w = len(offsets) - 1, int(offsets[-1])
+    if nc <= 0 or w <= 0:
+        return [([], np.array([]))] * max(nc, 0)
+    n_cls = logits_dev.shape[1]
+    with torch.cuda.stream(engine._stream()):
+        off_dev = engine._h2d(offsets)
+        sm = torch.empty((w, n_cls), dtype=torch.float64, device=engine.tdev)
+        check(lib.jg_smooth_scores(engine.ctx.handle, logits_dev.data_ptr(), off_dev.data_ptr(), nc, n_cls, 4, sm.data_ptr()))
+        col_dev = sm[:, phage_index].contiguous()
+        bk = torch.zeros((n_pen, w), dtype=torch.int32, device=engine.tdev)
+        nb = torch.zeros((nc, n_pen), dtype=torch.int32, device=engine.tdev)
+        check(lib.jg_segment_scores_batched(engine.ctx.handle, col_dev.data_ptr(), off_dev.data_ptr(), nc, w, min_size, n_pen,
+                                            bk.data_ptr(), nb.data_ptr()))
+        bk_h, nb_h, col_h = bk.cpu(), nb.cpu(), col_dev.cpu()
+    engine.ctx.sync()
+    bk_h, nb_h, col_h = bk_h.numpy(), nb_h.numpy(), col_h.numpy()
+    out = []
+    for c in range(nc):
+        a, b = int(offsets[c]), int(offsets[c + 1])
+        preds = [bk_h[p, a:a + nb_h[c, p]].tolist() for p in range(n_pen)]
+        out.append(_select_ranges(preds, col_h[a:b], sensitivity))
+    return out
+
+
+def segment_contig(engine, logits: np.ndarray, phage_index: int, sensitivity: float = 1.5):
+    """prophages.py:554-595 for one contig: (merged window-index ranges, scores of the kept ranges)."""
+    logits = np.ascontiguousarray(logits, np.float32)
+    with torch.cuda.stream(engine._stream()):
+        dev = engine._h2d(logits)
+    return segment_device(engine, dev, np.array([0, len(logits)], dtype=np.int64), phage_index, sensitivity)[0]
+
+
 def call_regions(engine, data: dict, class_map: dict, fsize: int, stride: int, lc: int = 500_000,
                  sensitivity: float = 1.5, identifier: str = "phage") -> dict[str, dict]:
     """All contigs longer than `lc`: window-index ranges, scores and bp coordinates
-    [start*stride, (end-1)*stride + fsize] (prophages.py:765-766)."""
+    [start*stride, (end-1)*stride + fsize] (prophages.py:765-766).  The selected contigs' window logits are taken from the
+    copy that is still in HBM when `data` comes from `contig_table` of this engine's own result."""
     names = [c.lower() for c in class_map["class"]]
     if identifier not in names:
         return {}
     k = class_map["index"][names.index(identifier)]
+    off = np.asarray(data["offsets"], dtype=np.int64)
+    sel = [ci for ci, length in enumerate(data["length"]) if not (length < lc or length <= lc)]   # logits_to_df_v2 keeps >= lc, segment drops <= cutoff
+    if not sel:
+        return {}
+    n_win = np.array([off[ci + 1] - off[ci] for ci in sel], dtype=np.int64)
+    sub_off = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
+    rows = np.concatenate([np.arange(off[ci], off[ci + 1]) for ci in sel])
+    with torch.cuda.stream(engine._stream()):
+        pred_dev = data.get("_pred_dev")
+        if pred_dev is not None:
+            logits_dev = pred_dev if len(rows) == pred_dev.shape[0] else pred_dev[engine._h2d(rows)]
+        else:
+            logits_dev = engine._h2d(np.ascontiguousarray(data["predictions"][rows], np.float32))
+    res = segment_device(engine, logits_dev, sub_off, int(k), sensitivity)
     out = {}
-    off = data["offsets"]
-    for ci, (name, length) in enumerate(zip(data["headers"], data["length"])):
-        if length < lc or length <= lc:                  # logits_to_df_v2 keeps >= lc, segment drops <= cutoff
-            continue
-        ranges, scores = segment_contig(engine, data["predictions"][off[ci]:off[ci + 1]], int(k), sensitivity)
-        out[str(name)] = {"ranges": ranges, "scores": scores,
-                          "coords": [(s * stride, (e - 1) * stride + fsize) for s, e in ranges]}
+    for ci, (ranges, scores) in zip(sel, res):
+        out[str(data["headers"][ci])] = {"ranges": ranges, "scores": scores,
+                                         "coords": [(s * stride, (e - 1) * stride + fsize) for s, e in ranges]}
     return out

@@ -411,13 +411,13 @@ def test_predict_driver_tsv_equals_oracle_pipeline(standin, tmp_path):
     from jaeger_b200.predict import run_core
     from oracle import postprocess as opp
     spec, weights, eng = standin
-    res = run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin", fsize=2000, stride=1500,
+    res = run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin", allow_random_weights=True, fsize=2000, stride=1500,
                    min_len=500, overwrite=True)
     gold = json.loads((G / "fragments_synthetic.json").read_text())
     assert res["table"].exists()
     assert res["windows"] == len(gold["2000_1500_None_None_0"]) + len(gold["2000_1500_500_1999_0"])   # long + short pass
     with pytest.raises(FileExistsError):
-        run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin")
+        run_core(input=str(G / "synthetic_contigs.fasta"), output=str(tmp_path), model="standin", allow_random_weights=True)
     y = eng.predict(WindowSource(fasta=G / "synthetic_contigs.fasta", fsize=2000, stride=1500, min_len=500))
     data = contig_table(eng, y, 2000)
     got = generate_summary(data, eng.class_map["class"], eng.class_map["index"])
@@ -449,7 +449,8 @@ def test_prophage_region_calling_vs_oracle(standin):
         assert ranges == want_r, (T, ranges, want_r)
         assert np.allclose(scores, want_s, atol=1e-6)
         if islands:
-            assert len(ranges) >= 1 and all(any(abs(r[0] - a) <= 12 and abs(r[1] - b) <= 12 for a, b in islands) for r in ranges)
+            # every planted island is called (noise may add short ranges, depending on the penalty the knee selects)
+            assert all(any(abs(r[0] - a) <= 12 and abs(r[1] - b) <= 12 for r in ranges) for a, b in islands), (ranges, islands)
 
 
 def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
@@ -467,7 +468,7 @@ def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
         fh.write(b">chr1 synthetic genome\n")
         for i in range(0, n, 80):
             fh.write(seq[i:i + 80].tobytes() + b"\n")
-    res = run_core(input=str(fa), output=str(tmp_path / "out"), model="standin", fsize=2000, stride=1500,
+    res = run_core(input=str(fa), output=str(tmp_path / "out"), model="standin", allow_random_weights=True, fsize=2000, stride=1500,
                    prophage=True, lc=500_000, sensitivity=1.5, overwrite=True, window_scores=True)
     assert res["num"] == 1 and res["num_written"] == 1
     assert res["windows"] == (n - 2000) // 1500 + 1
@@ -672,7 +673,7 @@ def test_driver_tsv_carries_terminal_repeat_columns(standin, tmp_path):
     recs = _repeat_contigs()
     fa = tmp_path / "rep.fasta"
     fa.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
-    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False)
+    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, fsize=2000, stride=1500, overwrite=True, dustmask=False)
     tsv = pd.read_csv(res["table"], sep="\t", keep_default_na=False).set_index("contig_id")
     assert tsv.loc["dtr", "terminal_repeats"] == "DTR" and int(float(tsv.loc["dtr", "repeat_length"])) == 120
     assert tsv.loc["itr,comma", "terminal_repeats"] == "ITR"
@@ -906,14 +907,14 @@ def test_driver_refine_option_adds_the_refined_columns(standin, tmp_path):
     taus = {c: {"logit": -0.5, "margin": 0.01, "n": 100} for c in orf.CLASSES}
     cal = tmp_path / "standin_refine.yaml"
     cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "standin", "quantile": 0.05, "taus": taus}, sort_keys=False))
-    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
+    res = run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, fsize=2000, stride=1500, overwrite=True, dustmask=False,
                    refine=True, refine_file=str(cal), window_scores=True, terminal_repeats=False, save_embedding=True, save_nmd=True,
-                   mem=2, precision="bf16")
+                   mem=2, precision="fp16")
     emb, nmd = np.load(tmp_path / "o" / "standin" / "c_embedding.npz"), np.load(tmp_path / "o" / "standin" / "c_nmd.npz")
     assert emb["embedding"].shape == (res["windows"], 128) and nmd["embedding"].shape == (res["windows"], 640)     # predict.py:66-112
     assert len(emb["headers"]) == res["windows"] and emb["headers"][0] in (b"c0", "c0")
     with pytest.raises(RuntimeError):
-        run_core(input=str(fa), output=str(tmp_path / "o3"), model="standin", cpu=True)
+        run_core(input=str(fa), output=str(tmp_path / "o3"), model="standin", allow_random_weights=True, cpu=True)
     tsv = pd.read_csv(res["table"], sep="\t")
     for col in ("contig_call", "contig_top_logit", "contig_margin", "n_windows_used", "n_merged_windows"):
         assert col in tsv.columns
@@ -929,7 +930,7 @@ def test_driver_refine_option_adds_the_refined_columns(standin, tmp_path):
         else:
             assert pd.isna(tsv.loc[cid, "contig_call"])
     cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "other", "taus": taus}))
-    res = run_core(input=str(fa), output=str(tmp_path / "o2"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=False,
+    res = run_core(input=str(fa), output=str(tmp_path / "o2"), model="standin", allow_random_weights=True, fsize=2000, stride=1500, overwrite=True, dustmask=False,
                    refine=True, refine_file=str(cal), terminal_repeats=False)
     assert "contig_call" not in pd.read_csv(res["table"], sep="\t").columns
 

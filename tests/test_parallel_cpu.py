@@ -33,10 +33,11 @@ def _worker(rank, world, port, n_total):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(1)
     lens = rng.integers(2000, 50001, size=n_total)
-    mine = shard_contigs(lens, world, 2000, 1500)[rank]
+    shards = shard_contigs(lens, world, 2000, 1500)
+    mine = shards[rank]
     # a stand-in for the per-contig records every rank computes on its own GPU
     rec = torch.tensor(np.stack([mine * 3.0 + 1.0, lens[mine].astype(np.float64)], axis=1))
-    table = gather_contig_records(rec, torch.tensor(mine), n_total, dst=0)
+    table = gather_contig_records(rec, shards, n_total, dst=0)
     if rank == 0:
         want = np.stack([np.arange(n_total) * 3.0 + 1.0, lens.astype(np.float64)], axis=1)
         assert np.array_equal(table.numpy(), want)

@@ -319,9 +319,16 @@ def test_driver_rejects_cpu_and_bad_precision_before_touching_a_device(tmp_path)
     fa = tmp_path / "x.fasta"
     fa.write_text(">a\n" + "ACGT" * 600 + "\n")
     with pytest.raises(RuntimeError, match="no CPU path"):
-        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", cpu=True)
+        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, cpu=True)
     with pytest.raises(ValueError, match="precision"):
-        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", precision="int8")
+        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, precision="int8")
+    for prec in ("fp32", "bf16"):            # one numeric mode: another precision is refused, not silently ignored
+        with pytest.raises(ValueError, match="not available on the B200 engine"):
+            run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, precision=prec)
+    with pytest.raises(ValueError, match="RANDOM-INITIALISED"):
+        run_core(input=str(fa), output=str(tmp_path / "o"), model="standin")
+    with pytest.raises(ValueError, match="--legacy-weights"):
+        run_core(input=str(fa), output=str(tmp_path / "o"))            # default model is `default`, which needs its weights
 
 
 def test_segment_flow_vs_reference_golden():

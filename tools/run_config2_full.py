@@ -27,7 +27,7 @@ logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
 from jaeger_b200.predict import run_core
 for dust in (False, True):
     t = time.time()
-    res = run_core(input=str(fa), output=str(tmp / f"out{int(dust)}"), model="standin", fsize=2000, stride=1500, overwrite=True, dustmask=dust)
+    res = run_core(input=str(fa), output=str(tmp / f"out{int(dust)}"), model="standin", allow_random_weights=True, fsize=2000, stride=1500, overwrite=True, dustmask=dust)
     dt = time.time() - t
     print(f"dustmask={dust}: {res['windows']} windows, {res['num_written']} contigs written; predict stage {res['predict_seconds']:.1f} s, "
           f"whole run {dt:.1f} s -> {gbp * 1e3 / dt:.1f} Mbp/s end to end from the file", flush=True)

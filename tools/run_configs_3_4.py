@@ -49,7 +49,7 @@ with open(fa, "wb") as fh:
         fh.write(b">genome%d\n" % g); fh.write(s.tobytes()); fh.write(b"\n")
 for rep in range(2):
     t = time.time()
-    res = run_core(input=str(fa), output=str(tmp / f"o{rep}"), model="standin", fsize=2000, stride=1500, prophage=True, lc=500_000,
+    res = run_core(input=str(fa), output=str(tmp / f"o{rep}"), model="standin", allow_random_weights=True, fsize=2000, stride=1500, prophage=True, lc=500_000,
                    sensitivity=1.5, overwrite=True)
     dt = time.time() - t
     print(f"config 4: 8 x 5 Mbp genomes, {res['windows']} windows, {sum(len(r['ranges']) for r in res['prophage_regions'].values())} regions; "
