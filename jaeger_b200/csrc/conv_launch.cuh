@@ -3,6 +3,7 @@
 #include "conv_ref.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_ws.cuh"
 
 namespace jg {
 
@@ -63,6 +64,49 @@ inline cudaError_t launch_conv_tc2(const ConvParams& p, int num_sms, cudaStream_
     tc2::conv_tc2_kernel<3><<<2 * pairs, tc2::kThreads2H, L.total, stream>>>(p);
   }
   return cudaGetLastError();
+}
+
+// Weights-stationary kernel (conv_ws.cuh): 128 output channels, weights within 320 TMEM columns, and one of the epilogue
+// shapes it is specialised for.  Returns the ws::WsMode, or -1 when the layer has to run on another kernel.
+inline int conv_ws_mode(const ConvParams& p) {
+  if (p.cout != 128 || (p.cin != 64 && p.cin != 128) || p.ntaps * p.cin / 2 > ws::kWColsMax || p.ntaps > kMaxTaps) return -1;
+  if (!p.folded || p.dyt1 || p.dyt2 || p.act1 != ACT_GELU_TANH || p.rows_per_window % ws::kSubRows != 0 || p.n_tiles < 1) return -1;
+  if (p.halo_l > 56 || p.halo_r > 56) return -1;
+  if (ws::smem_layout_ws(p.cin, p.halo_l, p.halo_r).total > kMaxSmem) return -1;
+  const bool has_sc = p.sc != nullptr;
+  if (p.tap_mode == 0 && p.pool_mode == 0 && !p.has_affine2 && p.y != nullptr) return has_sc ? ws::WS_LIGHT_SC : ws::WS_LIGHT;
+  if (has_sc && p.tap_mode == 2 && p.has_affine2 && p.act2 == ACT_GELU_TANH && p.tap_sum != nullptr) {
+    if (p.pool_mode == 0 && p.y != nullptr) return ws::WS_FINAL;
+    if (p.pool_mode == 1 && p.pool != nullptr) return ws::WS_FINAL_POOL;
+  }
+  return -1;
+}
+
+template <int kMode, int kTaps, int kGroups>
+inline cudaError_t launch_conv_ws_inst(const ConvParams& p, int grid, unsigned smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(ws::conv_ws_kernel<kMode, kTaps, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  ws::conv_ws_kernel<kMode, kTaps, kGroups><<<grid, ws::kThreadsWs, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_conv_ws(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  const int mode = conv_ws_mode(p);
+  if (mode < 0) return cudaErrorInvalidConfiguration;
+  const ws::SmemLayoutWs L = ws::smem_layout_ws(p.cin, p.halo_l, p.halo_r);
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  // the shapes that carry the time get an unrolled MMA issue loop: k5 x 128 channels (residual convs), k7 x 64 (stem)
+  if (p.ntaps == 5 && p.cin == 128) {
+    if (mode == ws::WS_LIGHT) return launch_conv_ws_inst<ws::WS_LIGHT, 5, 2>(p, grid, L.total, stream);
+    if (mode == ws::WS_LIGHT_SC) return launch_conv_ws_inst<ws::WS_LIGHT_SC, 5, 2>(p, grid, L.total, stream);
+    if (mode == ws::WS_FINAL) return launch_conv_ws_inst<ws::WS_FINAL, 5, 2>(p, grid, L.total, stream);
+    return launch_conv_ws_inst<ws::WS_FINAL_POOL, 5, 2>(p, grid, L.total, stream);
+  }
+  if (p.ntaps == 7 && p.cin == 64 && mode == ws::WS_LIGHT) return launch_conv_ws_inst<ws::WS_LIGHT, 7, 1>(p, grid, L.total, stream);
+  if (mode == ws::WS_LIGHT) return launch_conv_ws_inst<ws::WS_LIGHT, 0, 0>(p, grid, L.total, stream);
+  if (mode == ws::WS_LIGHT_SC) return launch_conv_ws_inst<ws::WS_LIGHT_SC, 0, 0>(p, grid, L.total, stream);
+  if (mode == ws::WS_FINAL) return launch_conv_ws_inst<ws::WS_FINAL, 0, 0>(p, grid, L.total, stream);
+  return launch_conv_ws_inst<ws::WS_FINAL_POOL, 0, 0>(p, grid, L.total, stream);
 }
 
 inline cudaError_t launch_conv_ref(const ConvParams& p, cudaStream_t stream) {

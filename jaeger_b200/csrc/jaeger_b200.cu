@@ -75,6 +75,7 @@ struct Layer {
   int32_t f[JG_LAYER_INT_FIELDS];
   jg::act_t* w = nullptr;      // weights image of the single-CTA kernel (w_index)
   jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
+  jg::act_t* w3 = nullptr;     // weights image of the weights-stationary kernel (ws::w3_index), 128-output-channel layers only
   float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const, dyt gamma1, beta1, gamma2, beta2  (10 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
   bool folded = false;         // scale1 folded into the weights (par scale1 == 1)
@@ -95,7 +96,8 @@ struct jg_model {
         *rel_b2 = nullptr, *tap_mean = nullptr, *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr,
         *mlp_b2 = nullptr;
   int final_mask = 0;
-  int conv_impl = 0;            // 0 auto, 1 single-CTA kernel only, 2 CTA-pair kernel wherever eligible, 3 = 0 (JG_CONV_IMPL)
+  int conv_impl = 0;            // JG_CONV_IMPL: 0 auto (weights-stationary kernel where eligible), 1 single-CTA kernel only,
+                                // 2 CTA-pair kernel wherever eligible, 3 the round-1 choice (no weights-stationary kernel)
   std::vector<int> tap_mask_slot;
   // workspace -------------------------------------------------------------------------------
   long long cap_rows = 0, cap_windows = 0;
@@ -491,6 +493,14 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
           img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
     JG_CUDA(cudaMalloc(&L.w2, img.size() * 2));
     JG_CUDA(cudaMemcpy(L.w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    if (cout == 128 && k * cin / 2 <= jg::ws::kWColsMax) {       // transposed image for the tensor-memory resident A operand
+      for (int t = 0; t < k; ++t)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int co = 0; co < cout; ++co)
+            img[jg::ws::w3_index(t, ci, co, cin, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
+      JG_CUDA(cudaMalloc(&L.w3, img.size() * 2));
+      JG_CUDA(cudaMemcpy(L.w3, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    }
     if (linear_tap_layer) {   // linear stem tap (stem_tap_kernel): the raw conv output from the unscaled fp32 weights
       std::vector<float> wt(static_cast<size_t>(k + 1) * 64 * cout, 0.0f);
       for (int t = 0; t < k; ++t)
@@ -578,7 +588,7 @@ int jg_model_destroy(jg_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->ctx->device);
   free_workspace(m);
-  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.w_tap); cudaFree(L.par); cudaFree(L.shifts); }
+  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.w3); cudaFree(L.w_tap); cudaFree(L.par); cudaFree(L.shifts); }
   for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
                    m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
@@ -737,9 +747,16 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
                        jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
     const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
     if (pair) p.w = L.w2;
-    L.last_kernel = layer_ref ? "jg::conv_ref_kernel" : (pair3 ? "jg::tc2::conv_tc2_kernel<3>" : (pair ? "jg::tc2::conv_tc2_kernel<2>" : "jg::tc::conv_tc_kernel"));
+    // 128-output-channel layers with one of the specialised epilogue shapes: the weights-stationary kernel (weights resident in
+    // tensor memory, transposed accumulators; profiles/conv_kernel_r2.md).  JG_CONV_IMPL=1|2|3 keeps the round-1 kernels.
+    const bool ws = !layer_ref && L.w3 != nullptr && (m->conv_impl == 0 || m->conv_impl == 4) && jg::conv_ws_mode(p) >= 0;
+    if (ws) p.w = L.w3;
+    L.last_kernel = layer_ref ? "jg::conv_ref_kernel"
+                  : ws ? "jg::ws::conv_ws_kernel"
+                  : (pair3 ? "jg::tc2::conv_tc2_kernel<3>" : (pair ? "jg::tc2::conv_tc2_kernel<2>" : "jg::tc::conv_tc_kernel"));
     cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
-                            : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
+                  : ws ? jg::launch_conv_ws(p, ctx->num_sms, st)
+                  : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(e, "conv launch");
     if (linear_tap) {

@@ -3,7 +3,7 @@
 // shape:   0 = residual conv (Cin 128, Cout 128, k5 d3, SAME, shortcut + taps + pool)
 //          1 = stem conv     (Cin 64,  Cout 128, k7 d1, VALID, raw tap)
 //          2 = wide-dilation conv (Cin 64, Cout 64, k5 d8, SAME)
-// variant: 0 = single-CTA kernel (conv_tc.cuh), 2 = CTA-pair kernel (conv_tc2.cuh)
+// variant: 0 = single-CTA kernel (conv_tc.cuh), 2 / 3 = CTA-pair kernel (conv_tc2.cuh), 4 = weights-stationary kernel (conv_ws.cuh)
 // Compares conv_tc_kernel against conv_ref_kernel on the same random inputs and prints
 // max |diff|; with time_iters > 0 also times the tensor-core kernel with CUDA events.
 #include <cstdio>
@@ -85,7 +85,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dmask, R)); CK(cudaMalloc(&dscmask, R)); CK(cudaMalloc(&dpar, hpar.size() * 4));
   CK(cudaMalloc(&dtap_ref, n_win * cout * 4)); CK(cudaMalloc(&dtap_tc, n_win * cout * 4));
   CK(cudaMalloc(&dpool_ref, n_win * cout * 4)); CK(cudaMalloc(&dpool_tc, n_win * cout * 4));
-  CK(cudaMalloc(&derr, 4)); CK(cudaMemset(derr, 0, 4));
+  CK(cudaMalloc(&derr, 64)); CK(cudaMemset(derr, 0, 64));
   CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dsc, hsc.data(), hsc.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
@@ -130,6 +130,7 @@ int main(int argc, char** argv) {
   if (strip & 2) { p.act1 = jg::ACT_NONE; p.act2 = jg::ACT_NONE; p.has_affine2 = 0; }
   if (strip & 4) { p.sc = nullptr; p.sc_mask = nullptr; }
   if (strip & 16) { p.has_affine2 = 0; p.act2 = jg::ACT_NONE; }
+  if (strip & 32) { p.pool_mode = 0; }
   p.err = derr;
   p.folded = getenv("JG_PROBE_FOLDED") ? 1 : 0;   // with it, scale1 must be 1 (set below) and the specialised epilogues run
   (void)variant;
@@ -145,8 +146,23 @@ int main(int argc, char** argv) {
   jg::ConvParams pt = p;
   pt.y = reinterpret_cast<jg::act_t*>(dy_tc) + jg::kGuardRows * 64; pt.tap_sum = dtap_tc; pt.pool = dpool_tc;
   if (strip & 8) { pt.y = nullptr; }
-  auto launch = [&](const jg::ConvParams& q) { return variant >= 2 ? jg::launch_conv_tc2(q, dev_sms, 0, variant) : jg::launch_conv_tc(q, dev_sms, 0); };
+  auto launch = [&](const jg::ConvParams& q) {
+    return variant == 4 ? jg::launch_conv_ws(q, dev_sms, 0) : (variant >= 2 ? jg::launch_conv_tc2(q, dev_sms, 0, variant) : jg::launch_conv_tc(q, dev_sms, 0));
+  };
   if (variant >= 2) pt.w = reinterpret_cast<const jg::act_t*>(dw2);
+  if (variant == 4) {      // weights-stationary image: Wt[cout][tap * cin + ci]
+    std::vector<uint16_t> hw3(hw.size());
+    for (int t = 0; t < k; ++t)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          hw3[jg::ws::w3_index(t, ci, co, cin, k)] = hw[jg::w_index(t, ci, co, cin, cout)];
+    uint16_t* dw3; CK(cudaMalloc(&dw3, hw3.size() * 2));
+    CK(cudaMemcpy(dw3, hw3.data(), hw3.size() * 2, cudaMemcpyHostToDevice));
+    pt.w = reinterpret_cast<const jg::act_t*>(dw3);
+    if (strip & 8) pt.y = nullptr;
+    printf("ws mode %d\n", jg::conv_ws_mode(pt));
+    if (jg::conv_ws_mode(pt) < 0) { printf("layer not eligible for the weights-stationary kernel\n"); return 4; }
+  }
   CK(launch(pt));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
@@ -188,7 +204,23 @@ int main(int argc, char** argv) {
   const bool ok = nbad == 0 && tapdiff <= 1e-3 * (1.0 + tapmax) * 4 && pooldiff < 0.05;
   printf("RESULT shape %d variant %d: %s\n", shape, variant, ok ? "MATCH" : "MISMATCH");
 
-  if (getenv("JG_TRACE")) {
+  if (getenv("JG_TRACE") && variant == 4) {
+    long long* ddbg; CK(cudaMalloc(&ddbg, 1024 * 8));
+    jg::ConvParams pd = pt; pd.dbg = ddbg;
+    for (int i = 0; i < 3; ++i) CK(launch(pt));
+    CK(cudaMemset(ddbg, 0, 1024 * 8));
+    CK(launch(pd));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(32);
+    CK(cudaMemcpy(h.data(), ddbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    const double ns = double(h[15]);
+    const double own = ns / 3.0;       // sub-tiles of epilogue group 0
+    printf("ws CTA0: %lld cycles in %lld ns (%.0f MHz), %lld sub-tiles (%.0f / sub-tile; MMA floor %d)\n", h[0], h[16], 1e3 * h[0] / double(h[16]),
+           h[15], h[0] / ns, 4 * k * (cin / 64) * 32);
+    printf("  MMA warp per sub-tile: wait free acc %.0f, wait operands %.0f, issue %.0f | epilogue group 0 per own sub-tile: validity %.0f, slot %.0f, accumulator %.0f, math %.0f, pair barrier %.0f, other %.0f\n",
+           h[1] / ns, h[2] / ns, h[13] / ns, h[7] / own, h[5] / own, h[3] / own, h[9] / own, h[11] / own,
+           (h[14] - h[7] - h[5] - h[3] - h[9] - h[11]) / own);
+  } else if (getenv("JG_TRACE")) {
     long long* ddbg; CK(cudaMalloc(&ddbg, 1024 * 8)); CK(cudaMemset(ddbg, 0, 1024 * 8));
     jg::ConvParams pd = pt; pd.dbg = ddbg;
     for (int i = 0; i < 3; ++i) CK(launch(pt));
@@ -222,6 +254,8 @@ int main(int argc, char** argv) {
       while (wms < 1500.0f) {
         for (int i = 0; i < 20; ++i) CK(launch(pt));
         CK(cudaEventRecord(w1)); CK(cudaEventSynchronize(w1));
+        { int herr[8]; CK(cudaMemcpy(herr, derr, 32, cudaMemcpyDeviceToHost));
+          if (herr[0]) { printf("STUCK WAIT code %d it %d cta %d parity %d warp %d (1 producer/EMPTY 2 MMA/TEMPTY 3 MMA/FULL 4 helper/SFREE 5 helper/VEMPTY 6 epi/VFULL 7 epi/SFULL 8 epi/SFREE 9 epi/TFULL)\n", herr[0], herr[1], herr[2], herr[3], herr[4]); return 5; } }
         cudaEventElapsedTime(&wms, w0, w1);
       }
     }

@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, ".")
 import numpy as np, torch
 from jaeger_b200 import B200Engine, parse_project, standin_1p4m_config
-from bench import synth_batch, FSIZE, STRIDE
+from bench import synth_batch
+FSIZE, STRIDE = 2000, 1500
 cfg = standin_1p4m_config()
 if os.environ.get("JG_DYT"):            # the MaskedDYT variant of the architecture
     sys.path.insert(0, "tests")

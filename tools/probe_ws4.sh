@@ -1,0 +1,14 @@
+#!/bin/bash
+export JG_PROBE_FOLDED=1
+mkdir -p gpurun_out
+{
+for cfg in "0 4 2 0 21" "0 4 2 0 17" "1 4 2 0 1" "0 4 2 0 32" "0 4 3 0 0" "0 4 37 0 0"; do
+  echo "== conv_probe $cfg"; timeout 120 ./build/conv_probe $cfg 2>&1 | grep -E "RESULT|bad|error|failed|y:"
+done
+for strip in 21 17 32 0; do
+  echo "== trace variant 4 strip $strip"; JG_TRACE=1 timeout 300 ./build/conv_probe 0 4 592 10 $strip 2>&1 | grep -E "TIMING|RESULT|error|failed|ws CTA0|per sub-tile"
+  for v in 2 3; do timeout 300 ./build/conv_probe 0 $v 592 10 $strip 2>&1 | grep -E "TIMING|error|failed"; done
+done
+echo "== stem"; JG_TRACE=1 timeout 300 ./build/conv_probe 1 4 592 10 1 2>&1 | grep -E "TIMING|RESULT|error|failed|ws CTA0|per sub-tile"; timeout 300 ./build/conv_probe 1 2 592 10 1 2>&1 | grep -E "TIMING|error|failed"
+} > gpurun_out/probe_ws4.log 2>&1
+cat gpurun_out/probe_ws4.log
