@@ -106,7 +106,7 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
 
 
 def run_core(**kwargs: Any) -> dict[str, Any]:
-    if (kwargs.get("model") or "default") == "default":
+    if (kwargs.get("model") or "default") == "default" and not kwargs.get("model_path"):     # --model_path picks the model itself (predict.py:503-542)
         return run_core_legacy(**kwargs)
     from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
     from .parallel import dist_env, merge_rank_frames, shard_contigs, shard_loaded
