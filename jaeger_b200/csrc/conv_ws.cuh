@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
   tc_fence_after();
 
   if (warp == 0) {
-    // ===== TMA producer: one halo'd [lead + 128 + tail][64] slab per channel group per tile =====
+    // ===== TMA producer: per tile, one halo'd [lead + 128 + tail][64] slab per channel group, then (layers with a
+    // shortcut) the block-input rows of the tile's two sub-tiles into their staging slots =====
     const bool leader = elect_one();
     int cnt = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -295,6 +296,22 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
           mbar_expect_tx(FULL(s), L.stage_bytes);
           const act_t* src = p.x + (static_cast<long long>(g) * p.x_plane + r_first) * 64;
           bulk_g2s(st_base + s * L.stage_pitch, src, L.stage_bytes, FULL(s));
+        }
+      }
+      if (kSc) {
+        const int it = 2 * (tile - tile_begin);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int slot = (it + h) % kSlotsWs;
+          const uint32_t use = static_cast<uint32_t>((it + h) / kSlotsWs);
+          WS_WAIT(SFREE(slot), (use & 1u) ^ 1u, 4, it + h);
+          if (leader) {
+            mbar_expect_tx(SFULL(slot), kSlotBytes);
+            for (int cg = 0; cg < 2; ++cg)
+              bulk_g2s(slot_base + slot * kSlotBytes + cg * (kSlotBytes / 2),
+                       p.sc + (static_cast<long long>(cg) * p.y_plane + static_cast<long long>(tile) * kTileM + h * kSubRows) * 64,
+                       kSlotBytes / 2, SFULL(slot));
+          }
         }
       }
     }
@@ -372,25 +389,9 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
     }
     if (dbg0 && leader && sub == 0) { p.dbg[1] = d_wacc; p.dbg[2] = d_wfull; p.dbg[13] = d_issue; }
   } else if (warp == 2) {
-    // ===== helper: per tile, the shortcut rows of its two sub-tiles (bulk loads into their staging slots) and the row
-    // masks / window counts, a few sub-tiles ahead of the epilogue =====
-    const bool leader = elect_one();
+    // ===== helper: row masks / window counts of a tile's two sub-tiles, up to kVSlotsWs sub-tiles ahead of the epilogue =====
     for (int it = 0; it < n_sub; it += 2) {                       // one 128-row tile = sub-tiles it, it + 1 per iteration
       const long long row0 = static_cast<long long>(tile_begin + (it >> 1)) * kTileM;
-      if (kSc) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int slot = (it + h) % kSlotsWs;
-          const uint32_t use = static_cast<uint32_t>((it + h) / kSlotsWs);
-          WS_WAIT(SFREE(slot), (use & 1u) ^ 1u, 4, it + h);
-          if (leader) {
-            mbar_expect_tx(SFULL(slot), kSlotBytes);
-            for (int cg = 0; cg < 2; ++cg)
-              bulk_g2s(slot_base + slot * kSlotBytes + cg * (kSlotBytes / 2),
-                       p.sc + (static_cast<long long>(cg) * p.y_plane + row0 + h * kSubRows) * 64, kSlotBytes / 2, SFULL(slot));
-          }
-        }
-      }
       const int va = it & (kVSlotsWs - 1), vb = (it + 1) & (kVSlotsWs - 1);
       const uint32_t vph = ((static_cast<uint32_t>(it) / kVSlotsWs) & 1u) ^ 1u;      // it is even and the ring size even: same phase for both
       WS_WAIT(VEMPTY(va), vph, 5, it);
@@ -405,7 +406,9 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
     const int grp = (warp - 4) >> 2;
     const int cg = q >> 1;                              // 64-channel group this warp's channels belong to
     const int t4 = lane >> 2, tq = lane & 3;
-    const bool issuer = (q & 1) == 0 && lane == 0;      // issues the bulk store of (grp, cg)
+    // the bulk stores of (grp, cg) are issued by lanes 0..3 of the even warp in turn: a lane only ever waits for a store
+    // of its own that is two sub-tiles of this group old (bulk groups are per thread), never for the most recent one
+    const bool issuer_warp = (q & 1) == 0;
     const int bar_id = 1 + grp * 2 + cg;
     // channel of (slab s, half h): 32 q + 16 s + 8 h + t4
     float sh1[2][2];
@@ -464,8 +467,9 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
       }
       // this group's stores before the most recent one have finished reading their slots: hand the oldest slot on
       // (it is the one this group uses after the next sub-tile, so the shortcut loader runs a whole period ahead)
-      if (issuer && p.y && it >= 2 * kEpiGroupsWs) {
-        bulk_wait_read<1>();
+      const int k_it = it / kEpiGroupsWs;                     // this group's iteration index
+      if (issuer_warp && p.y && k_it >= 2 && lane == ((k_it - 2) & 3)) {
+        bulk_wait_read<0>();
         mbar_arrive(SFREE((it + kEpiGroupsWs) % kSlotsWs));
       }
       const int vslot = it & (kVSlotsWs - 1);
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
       const long long tb0 = dbgw ? clock64() : 0;
       named_bar_sync(bar_id, 64);
       if (dbgw) { e_b += clock64() - tb0; e_m += tb0 - ts2; }
-      if (issuer) {
+      if (issuer_warp && lane == (k_it & 3)) {
         if (p.y) {
           bulk_s2g(p.y + (static_cast<long long>(cg) * p.y_plane + row0) * 64, slot_addr, kSlotBytes / 2);
           bulk_commit();
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
       }
     }
     if (kFinal && cur_win >= 0) flush(cur_win);
-    if (issuer && p.y) bulk_wait_all();
+    if (issuer_warp && lane < 4 && p.y) bulk_wait_all();
     if (dbg0 && q == 0 && lane == 0 && grp == 0) {
       p.dbg[3] = e_t; p.dbg[5] = e_s; p.dbg[7] = e_v; p.dbg[9] = e_m; p.dbg[11] = e_b;
       p.dbg[14] = clock64() - p.dbg[0];
