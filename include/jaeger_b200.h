@@ -126,7 +126,7 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
  * per-channel affine (MaskedBatchNorm folded, nnlib/v2/layers.py:918-941) or, with i[22] / i[23] set,
  * a MaskedDYT (layers.py:385-444): gamma * tanh(scale * x + shift) + beta with gamma / beta in
  * p[8..11]. */
-#define JG_LAYER_INT_FIELDS 24
+#define JG_LAYER_INT_FIELDS 32
 #define JG_LAYER_PTR_FIELDS 12
 typedef struct jg_layer_desc {
   int32_t i[JG_LAYER_INT_FIELDS];

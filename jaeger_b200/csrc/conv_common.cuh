@@ -74,6 +74,9 @@ struct ConvParams {
   const float *dyt_g1, *dyt_b1, *dyt_g2, *dyt_b2;   // MaskedDYT gamma / beta after the tanh (alpha rides in scale1 / scale2)
   int dyt1, dyt2;          // the first / second norm is a MaskedDYT: y = gamma * tanh(scale * x + shift) + beta
   int folded;              // scale1 is folded into the weights (== 1): the specialised epilogues add shift1 only
+  int epi_f32;             // generic epilogue entirely in fp32 with ONE rounding at the store (conv_epilogue.cuh): for graphs
+                           // whose norm FOLLOWS the activation with a large scale (the legacy `default` model: BatchNorm after
+                           // GELU with gamma / sigma up to 26), where a half-precision activation would be amplified
   int* err;                     // device int, set non-zero on a barrier time-out
   long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)
 };

@@ -119,6 +119,12 @@ __device__ __forceinline__ void epi_params_fill(float* s_par, const ConvParams& 
     s_par[i] = p.scale1[i];
     s_par[p.cout + i] = p.shift1[i];
     s_par[2 * p.cout + i] = p.bias ? p.bias[i] : 0.0f;
+    if (p.epi_f32) {        // the fp32 epilogue keeps the second affine and the shortcut constant in fp32 (same slots, full width)
+      s_par[3 * p.cout + i] = p.has_affine2 ? p.scale2[i] : 1.0f;
+      s_par[4 * p.cout + i] = p.has_affine2 ? p.shift2[i] : 0.0f;
+      s_par[5 * p.cout + i] = p.sc_const ? p.sc_const[i] : 0.0f;
+      continue;
+    }
     h2[i] = __float2half_rn(p.has_affine2 ? p.scale2[i] : 1.0f);
     t2[i] = __float2half_rn(p.has_affine2 ? p.shift2[i] : 0.0f);
     sc[i] = __float2half_rn(p.sc_const ? p.sc_const[i] : 0.0f);
@@ -211,6 +217,85 @@ __device__ __forceinline__ void dyt_apply_h2(__half2 (&h)[16], const uint4* g, c
   }
 }
 
+// The generic epilogue in fp32 from the accumulator to the store (p.epi_f32): conv + bias -> [tap] -> affine -> [+ shortcut] ->
+// activation -> [tap] -> [affine -> activation] -> [tap] -> [pool] -> ONE rounding to fp16.  No MaskedDYT on this path.
+__device__ __forceinline__ void epilogue_batch_f32(const ConvParams& p, const float* s_par, int cb, const uint32_t (&raw)[32],
+                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane, int win,
+                                                uint4 (&out)[4]) {
+  const float* sc1 = s_par + cb * 32;
+  const float* sh1 = s_par + p.cout + cb * 32;
+  const float* bias = s_par + 2 * p.cout + cb * 32;
+  const float* sc2 = s_par + 3 * p.cout + cb * 32;
+  const float* sh2 = s_par + 4 * p.cout + cb * 32;
+  const float* scc_const = s_par + 5 * p.cout + cb * 32;
+  float v[32];
+  if (p.tap_mode == 1) {
+    float tv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tv[j] = valid ? __uint_as_float(raw[j]) + bias[j] : 0.0f;
+    warp_cols_reduce<false>(tv, lane);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), sc1[j], sh1[j]);
+  if (has_sc) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const __half2* s2 = reinterpret_cast<const __half2*>(&scc[j4]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(s2[k]);
+        v[j4 * 8 + 2 * k] += sc_valid ? f.x : scc_const[j4 * 8 + 2 * k];
+        v[j4 * 8 + 2 * k + 1] += sc_valid ? f.y : scc_const[j4 * 8 + 2 * k + 1];
+      }
+    }
+  }
+  act_apply_vec(v, p.act1);
+  if (p.tap_mode == 2) {
+    float tv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
+    warp_cols_reduce<false>(tv, lane);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+  }
+  if (p.has_affine2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sc2[j], sh2[j]);
+    act_apply_vec(v, p.act2);
+  }
+  if (p.tap_mode == 3) {
+    float tv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
+    warp_cols_reduce<false>(tv, lane);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+  }
+  if (p.pool_mode != 0) {
+    float tv[32];
+    const bool pool_max = p.pool_mode == 1;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : (pool_max ? -3.0e38f : 0.0f);
+    if (pool_max) {
+      warp_cols_reduce<true>(tv, lane);
+      if (tv[0] > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    } else {
+      warp_cols_reduce<false>(tv, lane);
+      atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    const __half2 a = cvt_sat_h2(valid ? v[j * 8 + 0] : 0.0f, valid ? v[j * 8 + 1] : 0.0f);
+    const __half2 b = cvt_sat_h2(valid ? v[j * 8 + 2] : 0.0f, valid ? v[j * 8 + 3] : 0.0f);
+    const __half2 c = cvt_sat_h2(valid ? v[j * 8 + 4] : 0.0f, valid ? v[j * 8 + 5] : 0.0f);
+    const __half2 d = cvt_sat_h2(valid ? v[j * 8 + 6] : 0.0f, valid ? v[j * 8 + 7] : 0.0f);
+    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    o.z = *reinterpret_cast<const uint32_t*>(&c); o.w = *reinterpret_cast<const uint32_t*>(&d);
+    out[j] = o;
+  }
+}
+
 // kMode specialises the epilogue at compile time for the layer shapes that carry the time, so that
 // the flag tests disappear and the whole batch is one scheduling region (the runtime-flag version
 // splits it into basic blocks the compiler cannot overlap):
@@ -229,6 +314,10 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane,
                                                int win, uint4 (&out)[4]) {
   constexpr bool kGen = kMode == EPI_GENERIC, kFinal = kMode == EPI_FINAL || kMode == EPI_FINAL_POOL;
+  if (kGen && p.epi_f32) {
+    epilogue_batch_f32(p, reinterpret_cast<const float*>(e.scale1), cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
+    return;
+  }
   if (kGen && p.tap_mode == 1) {   // NMD tap on the raw conv output (acc + bias), stem only
     float tv[32];
 #pragma unroll

@@ -65,7 +65,7 @@ struct jg_ctx {
 enum LayerField {
   LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
   LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
-  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2
+  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL
 };
 // layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
 enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
@@ -720,6 +720,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     p.pool_mode = L.f[LF_POOL_MODE];
     p.fuse_mask = layer_ref ? 0 : 1;
     p.folded = L.folded ? 1 : 0;
+    p.epi_f32 = L.f[LF_EPI_F32];
     p.in_mask = mask_row0(L.f[LF_MASK_IN]);
     p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
     p.lpad = d_lpad;

@@ -115,7 +115,9 @@ def compile_legacy_plan(w: dict[str, Any]) -> Plan:
         c = ConvLaunch(kernel=_np32(k), bias=_np32(w["convs"][i]["bias"]), dilation=d, pad_left=span // 2, shrink=0,
                        in_buf=in_buf, out_buf=out_buf, mask_in=mask_in, mask_out=new_mask(), masking=0,
                        scale1=_np32(np.ones(128)), shift1=_np32(w["convs"][i]["bias"]), act1="gelu_erf",
-                       scale2=s2, shift2=t2, act2="gelu_erf" if outer_gelu else None, halvings=halvings)
+                       scale2=s2, shift2=t2, act2="gelu_erf" if outer_gelu else None, halvings=halvings,
+                       epi_f32=1)      # BatchNorm FOLLOWS the GELU here with gamma / sigma up to 26 (first layer): everything up to
+                                       # the store stays in fp32, a half-precision GELU output would be amplified by that scale
         launches.append(c)
         return c
 

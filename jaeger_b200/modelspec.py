@@ -78,8 +78,12 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
     if emb.get("input_type", emb.get("type", "translated")) != "translated":
         raise NotImplementedError("only the translated (six-frame codon) input is on the hot path")
     rep = model.get("representation_learner")
+    if rep is not None and "hidden_layers" not in rep and "block_sizes" in rep:
+        model = flat_schema_to_layer_list(model)              # first-generation project files
+        emb = dict(model.get("embedding", {}))
+        rep = model["representation_learner"]
     if rep is None or "hidden_layers" not in rep:
-        raise NotImplementedError("flat (pre-layer-list) project schema is not supported yet")
+        raise NotImplementedError("project.yaml has no representation_learner.hidden_layers (and is not the flat first-generation schema)")
     use_masking = bool(model.get("use_masking", True))
     layers: list[LayerSpec] = []
     for lc in rep["hidden_layers"]:
@@ -112,8 +116,14 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
         elif name in ("activation", "gelu", "relu"):
             layers.append(LayerSpec("act", dict(activation=_act_name(c, name if name != "activation" else None))))
         elif name == "residual_block":
-            if int(c.get("strides", 1)) != 1 or c.get("use_1x1conv", False):
-                raise NotImplementedError("strided / 1x1-bypass residual blocks are not supported")
+            strides = int(c.get("strides", 1))
+            if strides not in (1, 2):
+                raise NotImplementedError(f"residual_block strides={strides}: only 1 and 2 are supported")
+            if strides > 1 and bool(c.get("use_masking", use_masking)):
+                # layers.py:1884-1888: the block forwards the pre-stride mask, which has the wrong length after a strided
+                # conv -- strided architectures are only well-defined without masking
+                raise ValueError("residual_block with strides > 1 needs model.use_masking: false (the reference forwards a mask "
+                                 "of the pre-stride length past a strided block)")
             norm_type = str(c.get("norm_type", "masked_batchnorm")).lower()
             if norm_type not in ("masked_batchnorm", "masked_dyt"):
                 raise NotImplementedError(f"residual blocks with norm_type={norm_type!r} are not supported")
@@ -125,6 +135,7 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
                 kernel_size=int(c.get("kernel_size", 3)), dilation=int(c.get("dilation_rate", 1)),
                 use_bias=bool(c.get("use_bias", True)), activation=_act_name(c, model.get("activation", "gelu")) or "gelu",
                 use_masking=bool(c.get("use_masking", use_masking)),
+                strides=strides, use_1x1conv=bool(c.get("use_1x1conv", False)),      # layers.py:1855-1864: bypass conv when asked for or strided
                 norm="dyt" if norm_type == "masked_dyt" else "bn", alpha_init=float(c.get("alpha_init", 0.5)))))
         elif name == "dropout":
             continue
@@ -145,8 +156,10 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
 
     signals = None
     classifier = dense_stack(model["classifier"])
-    if len(classifier) != 1 or classifier[0]["activation"] is not None:
-        raise NotImplementedError("classifier head must be a single linear Dense layer")
+    if not classifier or classifier[-1]["activation"] is not None:
+        raise NotImplementedError("classifier head must end in a linear Dense layer (logits)")
+    if len(classifier) > 3 or len({d["activation"] for d in classifier[:-1]}) > 1:
+        raise NotImplementedError("classifier head: at most two hidden Dense layers with one activation")
     reliability = None
     if "reliability_model" in model:
         rm = model["reliability_model"]
@@ -164,6 +177,62 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
     return ModelSpec(name=str(model.get("name", "jaeger")), classes=list(model.get("class_label_map", [])),
                      embedding=emb, string_processor=sp, layers=layers, pooling=pooling,
                      classifier=classifier, reliability=reliability, use_masking=use_masking, reliability_signals=signals)
+
+
+def flat_schema_to_layer_list(model: dict[str, Any]) -> dict[str, Any]:
+    """First-generation (G1) project files -- `jaeger_57341_1.5M_fragment`, `jaeger_38341_1.4M_fragment`, template
+    commands/configs/nn_config.yaml:36-66 -- describe the network with flat keys instead of a layer list.  This rewrites them
+    as the layer list the current builder would need for the same network, following the one place the reference still reads
+    those keys (nnlib/inference.py:184-260, DynamicInferenceModelBuilder._build_representation_learner):
+        masked_conv1d_1_* (SAME)  -> activation
+        per stack i: block_sizes[i] residual blocks (block_filters / block_kernel_size / block_kernel_dilation; the stride of
+        block_kernel_strides[i] on the first block only, which also gets the 1x1 bypass)
+        masked_conv1d_final_* (SAME, block_filters[-1] filters) -> activation -> global pooling
+        classifier: Dense(dense_1_units, activation) -> Dense(classes);  reliability: Dense(dense_1_units, activation) -> Dense(1)
+    One-hot input [6, L, 64] through Dense(embedding_size, no bias); no mask propagation (these models were traced without
+    it, docs/_source/optimizations.md; scripts/convert_legacy_classifier_checkpoint.py:57-60).  The per-stack MaxPooling2D of
+    that vestigial builder is NOT reproduced: it applies the heads to a 4-D map and is no specification of the shipped graphs
+     -- the tensor shapes of the model's SavedModel bundle are checked against this layer list at load."""
+    rep = model["representation_learner"]
+    act = str(model.get("activation", "gelu")).lower()
+    n = len(rep.get("block_sizes", []))
+    get = lambda key, default: list(rep.get(key, [default] * n))     # noqa: E731
+    sizes, filters = get("block_sizes", 2), get("block_filters", 128)
+    ksize, dil, strides = get("block_kernel_size", 5), get("block_kernel_dilation", 3), get("block_kernel_strides", 1)
+
+    def conv(prefix, f):
+        return {"name": "masked_conv1d", "config": {
+            "filters": int(f), "kernel_size": int(rep.get(f"{prefix}_kernel_size", 7 if prefix.endswith("_1") else 5)),
+            "strides": int(rep.get(f"{prefix}_strides", 1)), "dilation_rate": int(rep.get(f"{prefix}_dilation_rate", 1)),
+            "padding": "same", "use_bias": True, "activation": None}}
+    hidden = [conv("masked_conv1d_1", rep.get("masked_conv1d_1_filters", 128)), {"name": "activation", "config": {"activation": act}}]
+    for i in range(n):
+        for j in range(int(sizes[i])):
+            st = int(strides[i]) if j == 0 else 1
+            hidden.append({"name": "residual_block", "config": {
+                "block_size": 1, "filters": int(filters[i]), "kernel_size": int(ksize[i]), "dilation_rate": int(dil[i]),
+                "strides": st, "use_1x1conv": st > 1, "use_bias": True, "activation": act}})
+    hidden += [conv("masked_conv1d_final", filters[-1] if n else rep.get("masked_conv1d_1_filters", 128)),
+               {"name": "activation", "config": {"activation": act}}]
+    pooling = str(rep.get("pooling", "max")).lower()
+    out = dict(model)
+    emb = dict(model.get("embedding", {}))
+    emb.setdefault("input_type", emb.get("type", "translated"))
+    emb["use_embedding_layer"] = False                 # one-hot [6, L, 64] input, Dense(embedding_size, use_bias=False)
+    out["embedding"] = emb
+    out["use_masking"] = False
+    out["representation_learner"] = {"hidden_layers": hidden, "pooling": {"avg": "average"}.get(pooling, pooling)}
+
+    def head(section, units_out):
+        h = int(section.get("dense_1_units", 128))
+        return {"hidden_layers": [{"name": "dense", "config": {"units": h, "activation": act, "use_bias": True}},
+                                  {"name": "dense", "config": {"units": int(units_out), "activation": None, "use_bias": True}}]}
+    cls = model.get("classifier", {})
+    n_cls = int(cls.get("classes", len(model.get("class_label_map", [])) or 6))
+    out["classifier"] = head(cls, n_cls)
+    # the G1 reliability head reads pooled features, not NMD vectors: that graph is not built here, the head is left out
+    out.pop("reliability_model", None)
+    return out
 
 
 def load_project(path: str | Path) -> ModelSpec:
@@ -285,16 +354,27 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
             blocks = []
             for _ in range(c["block_size"]):
                 norm = (lambda n: _dyt(rng, n, c.get("alpha_init", 0.5))) if c.get("norm") == "dyt" else (lambda n: _bn(rng, n))
-                blocks.append(dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=norm(c["filters"]),
-                                   conv2=_conv(rng, c["kernel_size"], c["filters"], c["filters"]),
-                                   bn2=norm(c["filters"])))
+                blk = dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=norm(c["filters"]),
+                           conv2=_conv(rng, c["kernel_size"], c["filters"], c["filters"]),
+                           bn2=norm(c["filters"]))
+                if block_has_bypass(c, len(blocks)):
+                    blk["conv3"], blk["bn3"] = _conv(rng, 1, ch, c["filters"]), norm(c["filters"])
+                if not c.get("use_bias", True):
+                    for name in ("conv1", "conv2", "conv3"):
+                        if name in blk:
+                            blk[name]["bias"] = np.zeros_like(blk[name]["bias"])
+                blocks.append(blk)
                 ch = c["filters"]
             w["layers"].append(dict(blocks=blocks))
         else:
             w["layers"].append({})
     feat = ch
-    w["classifier"] = [dict(kernel=_glorot(rng, (feat, spec.n_classes), feat, spec.n_classes),
-                            bias=np.zeros(spec.n_classes, np.float32))]
+    w["classifier"], width = [], feat
+    for d in spec.classifier:
+        w["classifier"].append(dict(kernel=_glorot(rng, (width, d["units"]), width, d["units"]),
+                                    bias=(rng.normal(0.0, 0.05, d["units"]).astype(np.float32) if len(spec.classifier) > 1
+                                          else np.zeros(d["units"], np.float32))))
+        width = d["units"]
     if spec.reliability is not None:
         n_nmd = sum(1 for layer in spec.layers if layer.kind == "nmd" or layer.cfg.get("return_nmd"))
         nmd_dim = 0
@@ -310,6 +390,12 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
                             dict(kernel=_glorot(rng, (h, 1), h, 1), bias=np.zeros(1, np.float32))]
         assert n_nmd > 0, "reliability head needs at least one nmd layer"
     return w
+
+
+def block_has_bypass(cfg: dict[str, Any], block_index: int) -> bool:
+    """layers.py:1855-1864 + 2680-2682: a block gets the 1x1 bypass conv when it is strided (every block of a strided stack
+    is) or when `use_1x1conv` is set, which ResidualBlockStack hands to the FIRST block of the stack only."""
+    return int(cfg.get("strides", 1)) > 1 or (bool(cfg.get("use_1x1conv", False)) and block_index == 0)
 
 
 def count_params(spec: ModelSpec, weights: dict[str, Any], representation_only: bool = True) -> int:

@@ -26,12 +26,12 @@ import numpy as np
 from .modelspec import ModelSpec
 
 ACT = {None: 0, "gelu": 1, "relu": 2, "gelu_erf": 3}
-LAYER_INT_FIELDS = 24
+LAYER_INT_FIELDS = 32
 LAYER_PTR_FIELDS = 12
 # int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
- LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2) = range(24)
+ LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL) = range(26)
 (LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
  LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2) = range(12)
 
@@ -87,7 +87,9 @@ class ConvLaunch:
     dyt_b2: np.ndarray | None = None
     out_const: np.ndarray | None = None   # value of this launch's output at rows its mask zeroed
     stage: int = 0                        # epilogue fill state while compiling
-    kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool
+    kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool, 4 rows -> (even, odd) planes
+    epi_f32: int = 0                      # epilogue in fp32 with one rounding at the store (norm after the activation, large scales)
+    len_ceil: int = 0                     # the frame length is halved with ceil (SAME stride-2 convs), not floor (MaxPool(2))
     halvings: int = 0                     # MaxPool(2) stages applied to the frame length before this layer
     real_cin: int = 0                     # channel counts of the reference layer (before padding to multiples of 64)
     real_cout: int = 0
@@ -408,7 +410,8 @@ def to_ctypes(plan: Plan):
                 LF_ACT1: ACT[c.act1], LF_HAS_AFF2: int(c.scale2 is not None), LF_ACT2: ACT[c.act2],
                 LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
                 LF_MASK_OUT: c.mask_out, LF_SC_MASK: c.sc_mask, LF_MASKING: c.masking,
-                LF_CUM_SHRINK_IN: c.cum_shrink_in, LF_DYT1: int(c.dyt_g1 is not None), LF_DYT2: int(c.dyt_g2 is not None)}
+                LF_CUM_SHRINK_IN: c.cum_shrink_in, LF_DYT1: int(c.dyt_g1 is not None), LF_DYT2: int(c.dyt_g2 is not None),
+                LF_EPI_F32: c.epi_f32, LF_LEN_CEIL: c.len_ceil}
         for i, v in vals.items():
             d.i[i] = int(v)
         ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,

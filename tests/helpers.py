@@ -114,3 +114,46 @@ def refine_case(seed=11):
     taus = {c: {"logit": 0.4 + 0.15 * i, "margin": 0.2 + 0.1 * i, "n": 50} for i, c in enumerate(classes)}
     taus["archaea"] = {"logit": float("-inf"), "margin": float("-inf"), "n": 2}
     return z, offsets, headers, taus
+
+
+def agreement_stats(got: np.ndarray, ref: np.ndarray, is_last: np.ndarray) -> dict:
+    """Label agreement between device logits `got` and oracle logits `ref` [W, n_cls]:
+    per window (argmax) and per contig (argmax of the float16 mean logits, postprocess/collect.py:332-342),
+    plus the logit error in absolute terms and relative to the oracle's top-2 margin."""
+    got, ref = np.asarray(got, np.float32), np.asarray(ref, np.float32)
+    err = np.abs(got - ref).max(axis=1)
+    top2 = np.sort(ref, axis=1)
+    margin = top2[:, -1] - top2[:, -2]
+    win_same = got.argmax(1) == ref.argmax(1)
+    ends = np.flatnonzero(np.asarray(is_last).astype(bool)) + 1
+    starts = np.concatenate([[0], ends[:-1]])
+    cg = np.array([np.float16(got[a:b].mean(axis=0)) for a, b in zip(starts, ends)])
+    cr = np.array([np.float16(ref[a:b].mean(axis=0)) for a, b in zip(starts, ends)])
+    contig_same = cg.argmax(1) == cr.argmax(1)
+    flips = np.flatnonzero(~win_same)
+    return {"windows": int(len(got)), "contigs": int(len(ends)),
+            "window_label_agreement": float(win_same.mean()), "contig_label_agreement": float(contig_same.mean()),
+            "max_abs_logit_err": float(err.max()), "mean_abs_logit_err": float(err.mean()),
+            "median_top2_margin": float(np.median(margin)), "mean_abs_logit": float(np.abs(ref).mean()),
+            "max_err_over_margin_at_flips": float((err[flips] / np.maximum(margin[flips], 1e-9)).min()) if len(flips) else None,
+            "p999_err_over_margin": float(np.quantile(err / np.maximum(margin, 1e-9), 0.999)),
+            "flipped_windows": int(len(flips)), "flipped_contigs": int((~contig_same).sum()),
+            "largest_margin_among_flips": float(margin[flips].max()) if len(flips) else 0.0}
+
+
+def agreement_contigs(seed: int, n_contigs: int):
+    """Many short contigs (1-4 windows at fsize 2000 / stride 1500) with varied composition: i.i.d. bases with a per-contig
+    GC content in [0.25, 0.75], a tenth of them with a low-complexity stretch or an N run."""
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n_contigs):
+        n = int(rng.integers(2000, 6600))
+        gc = rng.uniform(0.25, 0.75)
+        pr = np.array([(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])
+        s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n, p=pr).copy()
+        if i % 10 == 3:
+            a = int(rng.integers(0, n - 200)); s[a:a + int(rng.integers(10, 150))] = ord("N")
+        if i % 10 == 7:
+            a = int(rng.integers(0, n - 200)); s[a:a + 90] = np.frombuffer(b"ACA", dtype=np.uint8)[np.arange(90) % 3]
+        recs.append((f"k{i}", s.tobytes().decode()))
+    return recs

@@ -695,8 +695,9 @@ def _legacy_fixture():
 
 def test_legacy_default_model_on_health_fasta_vs_oracle():
     """BASELINE config 1: the bundled `default` weights on the reference's health FASTA
-    (135 windows at the CLI defaults).  Tolerance: fp16 activations vs the fp32 oracle with real
-    weights, |logit| ~ 3-10: max |diff| <= 0.15 and identical per-window / per-contig labels."""
+    (135 windows at the CLI defaults).  Tolerance: fp16-stored activations (fp32 epilogues: this graph's BatchNorm follows the
+    GELU with scales up to 26) vs the fp32 oracle with real weights, |logit| ~ 3-10: max |diff| <= 0.03 (observed 0.009)
+    and identical per-window / per-contig labels."""
     from jaeger_b200 import B200Engine, WindowSource
     from jaeger_b200 import codon_tables as ct
     from jaeger_b200.postprocess import contig_table
@@ -713,8 +714,8 @@ def test_legacy_default_model_on_health_fasta_vs_oracle():
     tok = np.stack([oenc.encode_window_legacy(x.seq, 2000, table) for x in wins]).astype(np.uint8)
     ref = oleg.forward(w, tok)
     d = np.abs(ref["output"] - y["prediction"])
-    assert d.max() <= 0.15, d.max()
-    assert np.abs(ref["embedding"] - y["embedding"]).max() <= 0.15
+    assert d.max() <= 0.03, d.max()
+    assert np.abs(ref["embedding"] - y["embedding"]).max() <= 0.03
     differ = np.flatnonzero(ref["output"].argmax(1) != y["prediction"].argmax(1))
     top2 = np.sort(ref["output"], axis=1)
     margins = top2[:, -1] - top2[:, -2]
@@ -724,7 +725,7 @@ def test_legacy_default_model_on_health_fasta_vs_oracle():
     gold = np.load(G / "legacy_graph_outputs.npz")
     assert zlib.crc32(tok.tobytes()) == int(gold["health_token_crc"])
     dg = np.abs(gold["health_output"] - y["prediction"])
-    assert dg.max() <= 0.15 and np.abs(gold["health_embedding"] - y["embedding"]).max() <= 0.15
+    assert dg.max() <= 0.03 and np.abs(gold["health_embedding"] - y["embedding"]).max() <= 0.03
     flips = np.flatnonzero(gold["health_output"].argmax(1) != y["prediction"].argmax(1))
     assert len(flips) <= 2 and np.all(margins[flips] < 2 * dg.max())
     data = contig_table(eng, y, 2000)
@@ -1098,3 +1099,54 @@ def test_reference_dataset_protocol_batches_and_evaluate(standin):
     lse = np.log(np.exp(z - z.max(1, keepdims=True)).sum(1)) + z.max(1)
     assert abs(res["loss"] - float(np.mean(lse - z[np.arange(n), labels]))) < 1e-5
     assert res["accuracy"] == float(np.mean(z.argmax(1) == labels))
+
+
+@pytest.mark.gpu
+def test_label_agreement_at_scale_real_weights_and_scaled_standin():
+    """North-star target: >= 99.9 % per-contig label agreement with the reference's path on the same inputs
+    (contig label = argmax of the float16 mean logits, postprocess/collect.py:332-342).
+    (A) the reference's REAL `default` weights on 5 000 synthetic contigs (about 12 000 windows): device vs oracle/legacy.py.
+    (B) the stand-in architecture with the classifier kernel scaled x25 (|logit| ~ 5-10, so the fp16-activation error is
+        no longer small against the logits) on 700 contigs: device vs oracle/forward.py (fp32).
+    Also bounds the logit error against the top-2 margin: a window may only flip where the oracle's own margin is within
+    twice the observed error.  tools/label_agreement.py runs the same at larger sizes and writes profiles/label_agreement_r2.json."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project, standin_1p4m_config
+    from jaeger_b200 import codon_tables as ct
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from oracle import legacy as oleg
+    from oracle import seqwin
+    from tests.helpers import agreement_contigs, agreement_stats
+    w, _ = _legacy_fixture()
+    recs = agreement_contigs(101, 5000)
+    eng = B200Engine(legacy_weights=w)
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500, outputs=("prediction",), lazy_meta=True))
+    eng.close()
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    table = dict(zip(oenc.CODONS, ct.LEGACY_AA_ID))
+    tok = np.stack([oenc.encode_window_legacy(x.seq, 2000, table) for x in wins]).astype(np.uint8)
+    ref = np.concatenate([oleg.forward(w, tok[b:b + 256])["output"] for b in range(0, len(tok), 256)])
+    st = agreement_stats(y["prediction"], ref, np.array([x.is_last for x in wins]))
+    print("legacy real weights:", st)
+    assert st["contigs"] == 5000 and st["windows"] >= 10000
+    assert st["contig_label_agreement"] >= 0.999, st
+    assert st["window_label_agreement"] >= 0.995, st
+    assert st["max_abs_logit_err"] <= 0.03, st                      # fp16-stored activations, real weights, |logit| up to ~10 (observed 0.013)
+    assert st["largest_margin_among_flips"] <= 2 * st["max_abs_logit_err"], st   # only near-ties flip
+
+    spec = parse_project(standin_1p4m_config())
+    wt = init_random(spec, 0)
+    wt["classifier"][0]["kernel"] = wt["classifier"][0]["kernel"] * 25.0
+    recs = agreement_contigs(202, 700)
+    eng = B200Engine(spec=spec, weights=wt)
+    y = eng.predict(WindowSource(records=recs, fsize=2000, stride=1500, outputs=("prediction",), lazy_meta=True))
+    eng.close()
+    wins = list(seqwin.fragment_windows(recs, 2000, 1500))
+    tok = oenc.encode_windows([x.seq for x in wins], 2000)
+    ref = np.concatenate([ofw.forward(spec, wt, tok[b:b + 96])["prediction"] for b in range(0, len(tok), 96)])
+    st = agreement_stats(y["prediction"], ref, np.array([x.is_last for x in wins]))
+    print("stand-in, classifier x25:", st)
+    assert st["mean_abs_logit"] >= 1.0, st                           # the logits are no longer tiny
+    assert st["contig_label_agreement"] >= 0.999, st
+    assert st["max_abs_logit_err"] <= 0.1, st                        # 25 x the 4e-3 bound of the unscaled stand-in
+    assert st["largest_margin_among_flips"] <= 2 * st["max_abs_logit_err"], st
