@@ -127,7 +127,7 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
  * a MaskedDYT (layers.py:385-444): gamma * tanh(scale * x + shift) + beta with gamma / beta in
  * p[8..11]. */
 #define JG_LAYER_INT_FIELDS 32
-#define JG_LAYER_PTR_FIELDS 12
+#define JG_LAYER_PTR_FIELDS 16
 typedef struct jg_layer_desc {
   int32_t i[JG_LAYER_INT_FIELDS];
   const float* p[JG_LAYER_PTR_FIELDS];

@@ -71,6 +71,10 @@ struct ConvParams {
   const int* lpad;              // [n_windows] padded frame length of every window
   int* count;                   // [n_windows] valid output rows
   int fuse_mask, masking, period, frames, shrink_in, halvings, shrink;
+  int len_round;           // frame length = (lpad - shrink_in + len_round) >> halvings: 0 = floor (MaxPool(2) stages), 2^halvings - 1 =
+                           // ceil (SAME stride-2 convs, layers.py:1318-1320)
+  int red_pitch;           // channel pitch of tap_sum / pool when this launch computes a SLICE of a wider layer's output channels
+                           // (0 = cout); tap_sum / pool then point at the slice's first channel
   const float *dyt_g1, *dyt_b1, *dyt_g2, *dyt_b2;   // MaskedDYT gamma / beta after the tanh (alpha rides in scale1 / scale2)
   int dyt1, dyt2;          // the first / second norm is a MaskedDYT: y = gamma * tanh(scale * x + shift) + beta
   int folded;              // scale1 is folded into the weights (== 1): the specialised epilogues add shift1 only
@@ -160,6 +164,8 @@ __device__ __forceinline__ void act_apply_vec(float (&v)[N], int act) {
     for (int j = 0; j < N; ++j) v[j] = act_apply(v[j], ACT_GELU_ERF);
   }
 }
+
+__host__ __device__ __forceinline__ int red_pitch_of(const ConvParams& p) { return p.red_pitch ? p.red_pitch : p.cout; }
 
 // float atomic max through the sign-split integer trick (no NaNs on this path)
 __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {

@@ -179,7 +179,7 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
   const bool has_scm = p.sc != nullptr && p.sc_mask != nullptr;
 #pragma unroll
   for (int c = 0; c < 4; ++c) scm[c] = has_scm ? p.sc_mask[tile_row0 + c * 32 + lane] : (p.sc != nullptr ? 1u : 0u);
-  const int limit = ((lp - p.shrink_in) >> p.halvings) - p.shrink;
+  const int limit = ((lp - p.shrink_in + p.len_round) >> p.halvings) - p.shrink;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const long long row = tile_row0 + c * 32 + lane;
@@ -234,7 +234,7 @@ __device__ __forceinline__ void epilogue_batch_f32(const ConvParams& p, const fl
 #pragma unroll
     for (int j = 0; j < 32; ++j) tv[j] = valid ? __uint_as_float(raw[j]) + bias[j] : 0.0f;
     warp_cols_reduce<false>(tv, lane);
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), sc1[j], sh1[j]);
@@ -256,7 +256,7 @@ __device__ __forceinline__ void epilogue_batch_f32(const ConvParams& p, const fl
 #pragma unroll
     for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
     warp_cols_reduce<false>(tv, lane);
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
   }
   if (p.has_affine2) {
 #pragma unroll
@@ -268,7 +268,7 @@ __device__ __forceinline__ void epilogue_batch_f32(const ConvParams& p, const fl
 #pragma unroll
     for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : 0.0f;
     warp_cols_reduce<false>(tv, lane);
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
   }
   if (p.pool_mode != 0) {
     float tv[32];
@@ -277,10 +277,10 @@ __device__ __forceinline__ void epilogue_batch_f32(const ConvParams& p, const fl
     for (int j = 0; j < 32; ++j) tv[j] = valid ? v[j] : (pool_max ? -3.0e38f : 0.0f);
     if (pool_max) {
       warp_cols_reduce<true>(tv, lane);
-      if (tv[0] > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+      if (tv[0] > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
     } else {
       warp_cols_reduce<false>(tv, lane);
-      atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+      atomicAdd(p.pool + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
     }
   }
 #pragma unroll
@@ -329,7 +329,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       tv[j4 * 4 + 3] = valid ? __uint_as_float(raw[j4 * 4 + 3]) + b.w : 0.0f;
     }
     warp_cols_reduce<false>(tv, lane);
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, tv[0]);
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
   }
   __half2 h[16];
   if (kGen) {
@@ -378,7 +378,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = valid ? h[i] : zero;
     }
-    atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(h, lane));
+    atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, warp_cols_reduce_h2<false>(h, lane));
 #pragma unroll
     for (int i = 0; i < 16; ++i) h[i] = x3[i];
     act_apply_h2(h, ACT_GELU_TANH);
@@ -388,7 +388,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
       for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
-      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
     }
     if (kGen && p.has_affine2) {
 #pragma unroll
@@ -407,7 +407,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
       const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
       for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : zero;
-      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
     }
   }
   if (kMode == EPI_FINAL_POOL || (kGen && p.pool_mode != 0)) {
@@ -419,9 +419,9 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     for (int i = 0; i < 16; ++i) tv[i] = valid ? h[i] : fill;
     if (pool_max) {
       const float m = warp_cols_reduce_h2<true>(tv, lane);
-      if (m > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, m);
+      if (m > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, m);
     } else {
-      atomicAdd(p.pool + static_cast<long long>(win) * p.cout + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
+      atomicAdd(p.pool + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, warp_cols_reduce_h2<false>(tv, lane));
     }
   }
 #pragma unroll

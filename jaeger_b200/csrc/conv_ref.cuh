@@ -26,7 +26,7 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     const bool valid = p.out_mask[row] != 0;
     const int win = static_cast<int>(row / p.rows_per_window);
     if (p.tap_mode == 1 && valid)
-      atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, acc + p.bias[co]);
+      atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + co, acc + p.bias[co]);
     float v = fmaf(acc, p.scale1[co], p.shift1[co]);
     if (p.dyt1) v = fmaf(tanhf(v), p.dyt_g1[co], p.dyt_b1[co]);
     if (p.sc) {
@@ -35,15 +35,15 @@ __global__ void conv_ref_kernel(const ConvParams p) {
                : (p.sc_const ? p.sc_const[co] : 0.0f);
     }
     v = act_apply(v, p.act1);
-    if (p.tap_mode == 2 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, v);
+    if (p.tap_mode == 2 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + co, v);
     if (p.has_affine2) {
       v = fmaf(v, p.scale2[co], p.shift2[co]);
       if (p.dyt2) v = fmaf(tanhf(v), p.dyt_g2[co], p.dyt_b2[co]);
       v = act_apply(v, p.act2);
     }
-    if (p.tap_mode == 3 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * p.cout + co, v);
-    if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * p.cout + co, v);
-    if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * p.cout + co, v);
+    if (p.tap_mode == 3 && valid) atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + co, v);
+    if (p.pool_mode == 1 && valid) atomic_max_f32(p.pool + static_cast<long long>(win) * red_pitch_of(p) + co, v);
+    if (p.pool_mode == 2 && valid) atomicAdd(p.pool + static_cast<long long>(win) * red_pitch_of(p) + co, v);
     if (p.y)
       p.y[act_index(row, co, p.y_plane)] = __float2half_rn(valid ? v : 0.0f);
   }

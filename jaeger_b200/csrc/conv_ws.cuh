@@ -173,7 +173,7 @@ __device__ __forceinline__ void tile_validity_bits(const ConvParams& p, long lon
   const bool has_scm = p.sc != nullptr && p.sc_mask != nullptr;
 #pragma unroll
   for (int c = 0; c < 4; ++c) scm[c] = has_scm ? p.sc_mask[row0 + c * 32 + lane] : (p.sc != nullptr ? 1u : 0u);
-  const int limit = ((lp - p.shrink_in) >> p.halvings) - p.shrink;
+  const int limit = ((lp - p.shrink_in + p.len_round) >> p.halvings) - p.shrink;
   int n_valid = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -440,14 +440,14 @@ __global__ void __launch_bounds__(kThreadsWs, 1) conv_ws_kernel(const __grid_con
             float v = tapacc[s][h];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (tq == 0) atomicAdd(p.tap_sum + static_cast<long long>(w) * p.cout + ch, v);
+            if (tq == 0) atomicAdd(p.tap_sum + static_cast<long long>(w) * red_pitch_of(p) + ch, v);
             tapacc[s][h] = 0.0f;
           }
           if (kPool) {
             float v = poolacc[s][h];
             v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
             v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-            if (tq == 0 && v > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(w) * p.cout + ch, v);
+            if (tq == 0 && v > -1.0e38f) atomic_max_f32(p.pool + static_cast<long long>(w) * red_pitch_of(p) + ch, v);
             poolacc[s][h] = -3.0e38f;
           }
         }

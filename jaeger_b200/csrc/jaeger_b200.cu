@@ -69,13 +69,25 @@ enum LayerField {
 };
 // layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
 enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
-                LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2 };
+                LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2, LP_KERNEL_ODD };
+
+// The device weight images of one convolution (or of one slice of its output channels)
+struct WeightImages {
+  jg::act_t* w = nullptr;      // single-CTA kernel (w_index)
+  jg::act_t* w2 = nullptr;     // CTA-pair kernel (w2_index)
+  jg::act_t* w3 = nullptr;     // weights-stationary kernel (ws::w3_index), 128-output-channel layers only
+};
 
 struct Layer {
   int32_t f[JG_LAYER_INT_FIELDS];
   jg::act_t* w = nullptr;      // weights image of the single-CTA kernel (w_index)
   jg::act_t* w2 = nullptr;     // weights image of the CTA-pair kernel (w2_index)
   jg::act_t* w3 = nullptr;     // weights image of the weights-stationary kernel (ws::w3_index), 128-output-channel layers only
+  WeightImages odd;            // strided convs: the images of the kernel for an odd input frame length (plan.py:split_phases)
+  // A layer whose weights fit no kernel's shared memory (e.g. 256 -> 256 channels, k5) runs as slices of 64 output
+  // channels on the CTA-pair kernel: one launch per slice, each reading the whole input.  [parity][slice]
+  std::vector<WeightImages> slices[2];
+  int slice_width = 0;
   float* par = nullptr;   // bias, scale1, shift1, scale2, shift2, sc_const, dyt gamma1, beta1, gamma2, beta2  (10 x cout)
   int* shifts = nullptr;  // device copy for the mask kernel
   bool folded = false;         // scale1 folded into the weights (par scale1 == 1)
@@ -120,11 +132,15 @@ struct jg_model {
 
 namespace {
 
+// frame length a layer sees: floor halving after MaxPool(2) stages, ceil halving after SAME stride-2 convs
+inline int len_round_of(const Layer& L) { return L.f[LF_LEN_CEIL] ? (1 << L.f[LF_HALVINGS]) - 1 : 0; }
+inline int layer_len(const Layer& L, int lc) { return (lc - L.f[LF_CUM_SHRINK_IN] + len_round_of(L)) >> L.f[LF_HALVINGS]; }
+
 void model_geometry(const jg_model* m, int lc, int* period, int* rpw) {
   int p = lc;
   for (const Layer& L : m->layers) {
     if (L.f[LF_KIND] != 1) continue;
-    const int l_in = (lc - L.f[LF_CUM_SHRINK_IN]) >> L.f[LF_HALVINGS];
+    const int l_in = layer_len(L, lc);
     const int halo = L.halo_l > L.halo_r ? L.halo_l : L.halo_r;
     const int need = l_in + (L.f[LF_SHRINK] == 0 ? halo : 0);
     if (need > p) p = need;
@@ -191,6 +207,31 @@ int ensure_workspace(jg_model* m, long long n_windows, long long rows) {
   m->ws_bytes = total;
   return 0;
 }
+
+// fp32 TF-layout kernel [k][cin][cout_total] (output channels [co0, co0 + cout)) -> the device images of the conv kernels
+int build_weight_images(const float* wk, int k, int cin, int cout_total, int co0, int cout, bool want_w3, WeightImages* out) {
+  std::vector<uint16_t> img(static_cast<size_t>(k) * cin * cout);
+  auto at = [&](int t, int ci, int co) { return f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout_total + co0 + co]); };
+  for (int t = 0; t < k; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) img[jg::w_index(t, ci, co, cin, cout)] = at(t, ci, co);
+  JG_CUDA(cudaMalloc(&out->w, img.size() * 2));
+  JG_CUDA(cudaMemcpy(out->w, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  for (int t = 0; t < k; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = at(t, ci, co);
+  JG_CUDA(cudaMalloc(&out->w2, img.size() * 2));
+  JG_CUDA(cudaMemcpy(out->w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  if (want_w3) {       // transposed image for the tensor-memory resident A operand
+    for (int t = 0; t < k; ++t)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co) img[jg::ws::w3_index(t, ci, co, cin, k)] = at(t, ci, co);
+    JG_CUDA(cudaMalloc(&out->w3, img.size() * 2));
+    JG_CUDA(cudaMemcpy(out->w3, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+void free_weight_images(WeightImages& w) { cudaFree(w.w); cudaFree(w.w2); cudaFree(w.w3); w = WeightImages{}; }
 
 int upload_f32(const float* h, size_t n, float** d) {
   JG_CUDA(cudaMalloc(d, n * 4));
@@ -444,8 +485,8 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     Layer L;
     std::memcpy(L.f, layers[l].i, sizeof(L.f));
     const int cin = L.f[LF_CIN], cout = L.f[LF_COUT], k = L.f[LF_K];
-    if (L.f[LF_KIND] == 2 || L.f[LF_KIND] == 3) {
-      if (cin % 64 != 0) { delete m; return fail("pooling layers need a channel count that is a multiple of 64"); }
+    if (L.f[LF_KIND] == 2 || L.f[LF_KIND] == 3 || L.f[LF_KIND] == 4) {
+      if (cin % 64 != 0) { delete m; return fail("pooling / row-phase layers need a channel count that is a multiple of 64"); }
       for (int b : {L.f[LF_IN_BUF], L.f[LF_OUT_BUF]}) max_buf = b > max_buf ? b : max_buf;
       for (int sl : {L.f[LF_MASK_IN], L.f[LF_MASK_OUT]}) max_mask = sl > max_mask ? sl : max_mask;
       m->layers.push_back(L);
@@ -465,41 +506,48 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     L.halo_l = -mn;
     L.halo_r = mx;
     if (L.halo_l > jg::kGuardRows - 8 || L.halo_r > jg::kGuardRows - 8) { delete m; return fail("conv halo exceeds guard rows"); }
-    // weights: TF layout [k][cin][cout] fp32 -> swizzled fp16 shared-memory image
-    std::vector<uint16_t> img(static_cast<size_t>(k) * cin * cout);
+    // weights: TF layout [k][cin][cout] fp32 -> swizzled fp16 shared-memory images
     const float* wk = layers[l].p[LP_KERNEL];
     // The first affine's per-channel scale (BatchNorm gamma / sigma) is folded into the fp16 weights, so
     // the epilogue adds the shift only.  Not for a layer whose NMD tap reads the raw conv output in the
     // epilogue (tap mode 1 without the linear stem tap): that needs the unscaled accumulator.
     const bool linear_tap_layer = l == 0 && L.f[LF_TAP_MODE] == 1 && cin == 64;
     L.folded = (L.f[LF_TAP_MODE] != 1 || linear_tap_layer) && layers[l].p[LP_SCALE1] != nullptr && !std::getenv("JG_NO_BN_FOLD");
-    std::vector<float> wfold;
-    if (L.folded) {
-      wfold.resize(static_cast<size_t>(k) * cin * cout);
-      const float* sc1 = layers[l].p[LP_SCALE1];
-      for (size_t i = 0; i < wfold.size(); ++i) wfold[i] = wk[i] * sc1[i % cout];
-    }
     const float* wk_raw = wk;
-    if (L.folded) wk = wfold.data();
-    for (int t = 0; t < k; ++t)
-      for (int ci = 0; ci < cin; ++ci)
-        for (int co = 0; co < cout; ++co)
-          img[jg::w_index(t, ci, co, cin, cout)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
-    JG_CUDA(cudaMalloc(&L.w, img.size() * 2));
-    JG_CUDA(cudaMemcpy(L.w, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    for (int t = 0; t < k; ++t)
-      for (int ci = 0; ci < cin; ++ci)
-        for (int co = 0; co < cout; ++co)
-          img[jg::tc2::w2_index(t, ci, co, cin, cout, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
-    JG_CUDA(cudaMalloc(&L.w2, img.size() * 2));
-    JG_CUDA(cudaMemcpy(L.w2, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    if (cout == 128 && k * cin / 2 <= jg::ws::kWColsMax) {       // transposed image for the tensor-memory resident A operand
-      for (int t = 0; t < k; ++t)
-        for (int ci = 0; ci < cin; ++ci)
-          for (int co = 0; co < cout; ++co)
-            img[jg::ws::w3_index(t, ci, co, cin, k)] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
-      JG_CUDA(cudaMalloc(&L.w3, img.size() * 2));
-      JG_CUDA(cudaMemcpy(L.w3, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    const float* wk_odd = layers[l].p[LP_KERNEL_ODD];
+    std::vector<float> wfold, wfold_odd;
+    if (L.folded) {
+      const float* sc1 = layers[l].p[LP_SCALE1];
+      wfold.resize(static_cast<size_t>(k) * cin * cout);
+      for (size_t i = 0; i < wfold.size(); ++i) wfold[i] = wk[i] * sc1[i % cout];
+      wk = wfold.data();
+      if (wk_odd) {
+        wfold_odd.resize(wfold.size());
+        for (size_t i = 0; i < wfold_odd.size(); ++i) wfold_odd[i] = wk_odd[i] * sc1[i % cout];
+        wk_odd = wfold_odd.data();
+      }
+    }
+    // does the layer fit one of the kernels as a whole?  If not and it is wide, it runs as slices of 64 output channels
+    jg::ConvParams geo{};
+    geo.cin = cin; geo.cout = cout; geo.ntaps = k; geo.halo_l = L.halo_l; geo.halo_r = L.halo_r; geo.n_tiles = 2;
+    const bool fits_whole = jg::conv_tc_stages(geo) >= 0 || jg::conv_tc2_eligible(geo);
+    jg::ConvParams geo_s = geo;
+    geo_s.cout = 64;
+    if (!fits_whole && cout > 64 && jg::conv_tc2_eligible(geo_s) && !std::getenv("JG_NO_SLICES")) L.slice_width = 64;
+    for (int par = 0; par < 2; ++par) {
+      const float* src = par == 0 ? wk : wk_odd;
+      if (!src) continue;
+      if (L.slice_width) {
+        for (int co0 = 0; co0 < cout; co0 += L.slice_width) {
+          WeightImages wi;
+          if (build_weight_images(src, k, cin, cout, co0, L.slice_width, false, &wi)) { delete m; return 2; }
+          L.slices[par].push_back(wi);
+        }
+      } else {
+        WeightImages wi;
+        if (build_weight_images(src, k, cin, cout, 0, cout, cout == 128 && k * cin / 2 <= jg::ws::kWColsMax, &wi)) { delete m; return 2; }
+        if (par == 0) { L.w = wi.w; L.w2 = wi.w2; L.w3 = wi.w3; } else { L.odd = wi; }
+      }
     }
     if (linear_tap_layer) {   // linear stem tap (stem_tap_kernel): the raw conv output from the unscaled fp32 weights
       std::vector<float> wt(static_cast<size_t>(k + 1) * 64 * cout, 0.0f);
@@ -555,8 +603,10 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     if (head->mlp_hidden != feat || feat > 256) { delete m; return fail("MLP head needs hidden width == feature width <= 256"); }
     if (upload_f32(head->mlp_w1, static_cast<size_t>(feat) * feat, &m->mlp_w1)) return 2;
     if (upload_f32(head->mlp_b1, feat, &m->mlp_b1)) return 2;
-    if (upload_f32(head->mlp_w2, static_cast<size_t>(feat) * feat, &m->mlp_w2)) return 2;
-    if (upload_f32(head->mlp_b2, feat, &m->mlp_b2)) return 2;
+    if (head->mlp_w2) {
+      if (upload_f32(head->mlp_w2, static_cast<size_t>(feat) * feat, &m->mlp_w2)) return 2;
+      if (upload_f32(head->mlp_b2, feat, &m->mlp_b2)) return 2;
+    }
   }
   if (m->n_taps > 0) {
     const int nmd_dim = m->n_taps * m->tap_width;
@@ -588,7 +638,11 @@ int jg_model_destroy(jg_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->ctx->device);
   free_workspace(m);
-  for (Layer& L : m->layers) { cudaFree(L.w); cudaFree(L.w2); cudaFree(L.w3); cudaFree(L.w_tap); cudaFree(L.par); cudaFree(L.shifts); }
+  for (Layer& L : m->layers) {
+    cudaFree(L.w); cudaFree(L.w2); cudaFree(L.w3); cudaFree(L.w_tap); cudaFree(L.par); cudaFree(L.shifts);
+    free_weight_images(L.odd);
+    for (auto& v : L.slices) for (auto& wi : v) free_weight_images(wi);
+  }
   for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
                    m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
@@ -608,7 +662,7 @@ double jg_model_flops_per_window(jg_model* m, int32_t lc) {
   double f = 0.0;
   for (const Layer& L : m->layers) {
     if (L.f[LF_KIND] != 1) continue;
-    const int l_out = ((lc - L.f[LF_CUM_SHRINK_IN]) >> L.f[LF_HALVINGS]) - L.f[LF_SHRINK];
+    const int l_out = layer_len(L, lc) - L.f[LF_SHRINK];
     f += 2.0 * m->frames * l_out * L.f[LF_K] * static_cast<double>(L.f[LF_CIN]) * L.f[LF_COUT];
   }
   return f;
@@ -669,97 +723,127 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       pool_final = true;
       continue;
     }
-    // A layer whose weights do not fit either tensor-core kernel's shared memory (e.g. 128 -> 256
-    // channels with k >= 3) runs on the CUDA-core kernel, like the whole model does under use_ref.
+    if (L.f[LF_KIND] == 4) {     // rows -> (even, odd) row planes in front of the strided convs of a residual block
+      const int groups = L.f[LF_CIN] / 64;
+      jg::rows_to_phases_kernel<<<grid_for(rows * 16 * groups, 256, ctx->num_sms, 16), 256, 0, st>>>(
+          buf_row0(L.f[LF_IN_BUF]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], len_round_of(L), groups, plane,
+          buf_row0(L.f[LF_OUT_BUF]));
+      ctx->launches++;
+      JG_CUDA(cudaGetLastError());
+      continue;
+    }
+    // Weight images: a strided conv (plan.py:split_phases) has one kernel per parity of its pre-stride frame length, which is
+    // uniform over a forward call except in the padded short pass -- there the plan compiler's caller refuses strided models.
+    int par = 0;
+    if (L.odd.w != nullptr || !L.slices[1].empty()) {
+      const int l_prev = (lc - L.f[LF_CUM_SHRINK_IN] + (1 << (L.f[LF_HALVINGS] - 1)) - 1) >> (L.f[LF_HALVINGS] - 1);
+      par = l_prev & 1;
+    }
+    const jg::act_t* img_w = par ? L.odd.w : L.w;
+    const jg::act_t* img_w2 = par ? L.odd.w2 : L.w2;
+    const jg::act_t* img_w3 = par ? L.odd.w3 : L.w3;
+    const int n_slices = L.slice_width ? cout / L.slice_width : 1;
+    const int lcout = L.slice_width ? L.slice_width : cout;       // output channels of one launch
+    // A layer whose weights fit no tensor-core kernel's shared memory even in slices runs on the CUDA-core kernel, like the
+    // whole model does under use_ref.
     jg::ConvParams geo{};
-    geo.cin = L.f[LF_CIN]; geo.cout = cout; geo.ntaps = L.f[LF_K]; geo.halo_l = L.halo_l; geo.halo_r = L.halo_r;
+    geo.cin = L.f[LF_CIN]; geo.cout = lcout; geo.ntaps = L.f[LF_K]; geo.halo_l = L.halo_l; geo.halo_r = L.halo_r;
     geo.n_tiles = static_cast<int>(rows / jg::kTileM);
     const bool fits_tc = jg::conv_tc_stages(geo) >= 0, fits_tc2 = jg::conv_tc2_eligible(geo);
     const bool layer_ref = use_ref || (!fits_tc && !fits_tc2);
     if (layer_ref) {   // the CUDA-core path keeps the stand-alone mask kernel
       jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
-          mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], L.f[LF_SHRINK], L.f[LF_K],
+          mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], len_round_of(L), L.f[LF_SHRINK], L.f[LF_K],
           L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
       ctx->launches++;
     }
-    jg::ConvParams p{};
-    p.x = buf_row0(L.f[LF_IN_BUF]);
-    p.y = L.f[LF_OUT_BUF] >= 0 ? buf_row0(L.f[LF_OUT_BUF]) : nullptr;
-    p.sc = L.f[LF_SC_BUF] >= 0 ? buf_row0(L.f[LF_SC_BUF]) : nullptr;
-    p.sc_mask = (L.f[LF_SC_BUF] >= 0 && L.f[LF_SC_MASK] >= 0) ? mask_row0(L.f[LF_SC_MASK]) : nullptr;
-    p.out_mask = mask_row0(L.f[LF_MASK_OUT]);
-    p.w = L.w;
-    p.bias = L.par;
-    p.scale1 = L.par + cout;
-    p.shift1 = L.par + 2 * cout;
-    p.scale2 = L.par + 3 * cout;
-    p.shift2 = L.par + 4 * cout;
-    p.sc_const = L.par + 5 * cout;
-    p.dyt_g1 = L.par + 6 * cout; p.dyt_b1 = L.par + 7 * cout; p.dyt_g2 = L.par + 8 * cout; p.dyt_b2 = L.par + 9 * cout;
-    p.dyt1 = L.f[LF_DYT1]; p.dyt2 = L.f[LF_DYT2];
-    p.tap_sum = L.f[LF_TAP_MODE] != 0 ? m->tap_sum + static_cast<long long>(L.f[LF_TAP_SLOT]) * n_windows * m->tap_width : nullptr;
-    p.pool = L.f[LF_POOL_MODE] != 0 ? m->pool : nullptr;
-    p.x_plane = plane;
-    p.y_plane = plane;
-    p.n_tiles = static_cast<int>(rows / jg::kTileM);
-    p.rows_per_window = rpw;
-    p.cin = L.f[LF_CIN];
-    p.cout = cout;
-    p.ntaps = L.f[LF_K];
-    for (int t = 0; t < L.f[LF_K]; ++t) p.shifts[t] = L.shifts_h[t];
-    p.halo_l = L.halo_l;
-    p.halo_r = L.halo_r;
-    p.act1 = L.f[LF_ACT1];
-    p.act2 = L.f[LF_ACT2];
-    p.has_affine2 = L.f[LF_HAS_AFF2];
-    p.tap_mode = L.f[LF_TAP_MODE];
-    // The stem's tap is linear in its one-hot input: it is taken from token counts after the conv
-    // (stem_tap_kernel), which leaves the stem a light layer for the CTA-pair kernel.
-    const bool linear_tap = L.w_tap != nullptr && L.f[LF_SHRINK] >= 0 && L.f[LF_CUM_SHRINK_IN] == 0 && L.f[LF_HALVINGS] == 0;
-    if (linear_tap) { p.tap_mode = 0; p.tap_sum = nullptr; }
-    p.pool_mode = L.f[LF_POOL_MODE];
-    p.fuse_mask = layer_ref ? 0 : 1;
-    p.folded = L.folded ? 1 : 0;
-    p.epi_f32 = L.f[LF_EPI_F32];
-    p.in_mask = mask_row0(L.f[LF_MASK_IN]);
-    p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
-    p.lpad = d_lpad;
-    p.count = m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows;
-    p.masking = L.f[LF_MASKING];
-    p.period = period;
-    p.frames = m->frames;
-    p.shrink_in = L.f[LF_CUM_SHRINK_IN];
-    p.halvings = L.f[LF_HALVINGS];
-    p.shrink = L.f[LF_SHRINK];
-    p.err = m->err;
-    p.dbg = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (m->profiling) {
       JG_CUDA(cudaEventCreate(&ev0));
       JG_CUDA(cudaEventCreate(&ev1));
       JG_CUDA(cudaEventRecord(ev0, st));
     }
-    // Kernel choice (profiles/conv_kernel_r1.md): light epilogues -> CTA-pair kernel with two epilogue
-    // groups and staged bulk stores; layers with an NMD tap / second affine / pool are bound by epilogue
-    // instruction issue -> three epilogue groups: the pair kernel's 3-group variant when Cin >= 128
-    // (+13 % over the single-CTA kernel in the forward pass), else the single-CTA kernel (stem).
-    const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
-    const bool pair3 = !layer_ref && heavy && p.cin >= 128 && (m->conv_impl == 0 || m->conv_impl == 3) &&
-                       jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
-    const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
-    if (pair) p.w = L.w2;
-    // 128-output-channel layers with one of the specialised epilogue shapes: the weights-stationary kernel (weights resident in
-    // tensor memory, transposed accumulators; profiles/conv_kernel_r2.md).  JG_CONV_IMPL=1|2|3 keeps the round-1 kernels.
-    const bool ws = !layer_ref && L.w3 != nullptr && (m->conv_impl == 0 || m->conv_impl == 4) && jg::conv_ws_mode(p) >= 0;
-    if (ws) p.w = L.w3;
-    L.last_kernel = layer_ref ? "jg::conv_ref_kernel"
-                  : ws ? "jg::ws::conv_ws_kernel"
-                  : (pair3 ? "jg::tc2::conv_tc2_kernel<3>" : (pair ? "jg::tc2::conv_tc2_kernel<2>" : "jg::tc::conv_tc_kernel"));
-    cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
-                  : ws ? jg::launch_conv_ws(p, ctx->num_sms, st)
-                  : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
-    ctx->launches++;
-    if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+    bool linear_tap = false;
+    jg::ConvParams p{};
+    for (int sl = 0; sl < n_slices; ++sl) {
+      const int c0 = sl * lcout;                                  // first output channel of this launch
+      const long long g0 = static_cast<long long>(c0 / 64) * plane * 64;      // its channel-group offset in a g64sw tensor
+      p = jg::ConvParams{};
+      p.x = buf_row0(L.f[LF_IN_BUF]);
+      p.y = L.f[LF_OUT_BUF] >= 0 ? buf_row0(L.f[LF_OUT_BUF]) + g0 : nullptr;
+      p.sc = L.f[LF_SC_BUF] >= 0 ? buf_row0(L.f[LF_SC_BUF]) + g0 : nullptr;
+      p.sc_mask = (L.f[LF_SC_BUF] >= 0 && L.f[LF_SC_MASK] >= 0) ? mask_row0(L.f[LF_SC_MASK]) : nullptr;
+      p.out_mask = mask_row0(L.f[LF_MASK_OUT]);
+      p.w = L.slice_width ? L.slices[par][sl].w : img_w;
+      p.bias = L.par + c0;
+      p.scale1 = L.par + cout + c0;
+      p.shift1 = L.par + 2 * cout + c0;
+      p.scale2 = L.par + 3 * cout + c0;
+      p.shift2 = L.par + 4 * cout + c0;
+      p.sc_const = L.par + 5 * cout + c0;
+      p.dyt_g1 = L.par + 6 * cout + c0; p.dyt_b1 = L.par + 7 * cout + c0; p.dyt_g2 = L.par + 8 * cout + c0; p.dyt_b2 = L.par + 9 * cout + c0;
+      p.dyt1 = L.f[LF_DYT1]; p.dyt2 = L.f[LF_DYT2];
+      p.tap_sum = L.f[LF_TAP_MODE] != 0 ? m->tap_sum + static_cast<long long>(L.f[LF_TAP_SLOT]) * n_windows * m->tap_width + c0 : nullptr;
+      p.pool = L.f[LF_POOL_MODE] != 0 ? m->pool + c0 : nullptr;
+      p.red_pitch = L.slice_width ? cout : 0;
+      p.x_plane = plane;
+      p.y_plane = plane;
+      p.n_tiles = static_cast<int>(rows / jg::kTileM);
+      p.rows_per_window = rpw;
+      p.cin = L.f[LF_CIN];
+      p.cout = lcout;
+      p.ntaps = L.f[LF_K];
+      for (int t = 0; t < L.f[LF_K]; ++t) p.shifts[t] = L.shifts_h[t];
+      p.halo_l = L.halo_l;
+      p.halo_r = L.halo_r;
+      p.act1 = L.f[LF_ACT1];
+      p.act2 = L.f[LF_ACT2];
+      p.has_affine2 = L.f[LF_HAS_AFF2];
+      p.tap_mode = L.f[LF_TAP_MODE];
+      // The stem's tap is linear in its one-hot input: it is taken from token counts after the conv
+      // (stem_tap_kernel), which leaves the stem a light layer for the tensor-core kernels.
+      linear_tap = L.w_tap != nullptr && L.f[LF_SHRINK] >= 0 && L.f[LF_CUM_SHRINK_IN] == 0 && L.f[LF_HALVINGS] == 0;
+      if (linear_tap) { p.tap_mode = 0; p.tap_sum = nullptr; }
+      p.pool_mode = L.f[LF_POOL_MODE];
+      // the first slice (or the only launch) derives and publishes the layer's row mask / window counts; further slices read it
+      p.fuse_mask = (layer_ref || sl > 0) ? 0 : 1;
+      p.folded = L.folded ? 1 : 0;
+      p.epi_f32 = L.f[LF_EPI_F32];
+      p.in_mask = mask_row0(L.f[LF_MASK_IN]);
+      p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
+      p.lpad = d_lpad;
+      p.count = m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows;
+      p.masking = L.f[LF_MASKING];
+      p.period = period;
+      p.frames = m->frames;
+      p.shrink_in = L.f[LF_CUM_SHRINK_IN];
+      p.halvings = L.f[LF_HALVINGS];
+      p.len_round = len_round_of(L);
+      p.shrink = L.f[LF_SHRINK];
+      p.err = m->err;
+      p.dbg = nullptr;
+      // Kernel choice (profiles/conv_kernel_r1.md): light epilogues -> CTA-pair kernel with two epilogue
+      // groups and staged bulk stores; layers with an NMD tap / second affine / pool are bound by epilogue
+      // instruction issue -> three epilogue groups: the pair kernel's 3-group variant when Cin >= 128
+      // (+13 % over the single-CTA kernel in the forward pass), else the single-CTA kernel (stem).
+      const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
+      const bool pair3 = !layer_ref && heavy && p.cin >= 128 && (m->conv_impl == 0 || m->conv_impl == 3) &&
+                         jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
+      const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
+      if (pair) p.w = L.slice_width ? L.slices[par][sl].w2 : img_w2;
+      // 128-output-channel layers with one of the specialised epilogue shapes: the weights-stationary kernel (weights resident in
+      // tensor memory, transposed accumulators; profiles/conv_kernel_r2.md).  JG_CONV_IMPL=1|2|3 keeps the round-1 kernels.
+      const bool ws = !layer_ref && !L.slice_width && img_w3 != nullptr && (m->conv_impl == 0 || m->conv_impl == 4) && jg::conv_ws_mode(p) >= 0;
+      if (ws) p.w = img_w3;
+      L.last_kernel = layer_ref ? "jg::conv_ref_kernel"
+                    : ws ? "jg::ws::conv_ws_kernel"
+                    : (pair3 ? "jg::tc2::conv_tc2_kernel<3>" : (pair ? "jg::tc2::conv_tc2_kernel<2>" : "jg::tc::conv_tc_kernel"));
+      cudaError_t e = layer_ref ? jg::launch_conv_ref(p, st)
+                    : ws ? jg::launch_conv_ws(p, ctx->num_sms, st)
+                    : (pair ? jg::launch_conv_tc2(p, ctx->num_sms, st, pair3 ? 3 : 2) : jg::launch_conv_tc(p, ctx->num_sms, st));
+      ctx->launches++;
+      if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+    }
     if (linear_tap) {
       jg::StemTapParams tp{};
       tp.tokens = d_tokens; tp.lpad = d_lpad; tp.count = p.count;

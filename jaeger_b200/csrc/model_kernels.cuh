@@ -63,7 +63,7 @@ __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const i
 // (nnlib/v2/layers.py:1245-1252, mask_mode "any").  Also accumulates the per-window count of
 // valid rows that the NMD taps and the pooling need.
 __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const int* __restrict__ lpad,
-                                      long long n_rows, RowGeom g, int shrink_in, int halvings, int shrink,
+                                      long long n_rows, RowGeom g, int shrink_in, int halvings, int len_round, int shrink,
                                       int ntaps, const int* __restrict__ shifts, int masking,
                                       uint8_t* __restrict__ out_mask, int* __restrict__ count) {
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
@@ -71,7 +71,7 @@ __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const
     const long long w = row / g.rpw;
     const int rw = static_cast<int>(row - w * g.rpw);
     const int f = rw / g.period, j = rw - f * g.period;
-    int ok = (f < g.frames) && (j < ((lpad[w] - shrink_in) >> halvings) - shrink);
+    int ok = (f < g.frames) && (j < ((lpad[w] - shrink_in + len_round) >> halvings) - shrink);
     if (ok && masking) {
       int any = 0;
       for (int t = 0; t < ntaps; ++t) any |= in_mask[row + shifts[t]];
@@ -86,6 +86,36 @@ __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const
     } else if (ok) {
       atomicAdd(count + w, 1);
     }
+  }
+}
+
+// Rows -> (even, odd) row planes inside every frame: out[w,f,j] = (in[w,f,2j] | in[w,f,2j+1]) along the channel axis for
+// j < ceil(L_in / 2), zero elsewhere (a missing odd row of an odd-length frame is zero = the SAME padding of the strided conv).
+// A stride-2 conv over `in` is then a stride-1 conv over `out` with twice the input channels (plan.py:split_phases;
+// reference: the strided conv1 / bypass conv of a ResidualBlock, nnlib/v2/layers.py:1840-1864).  One thread per 16-byte chunk of
+// an output row; both tensors are g64sw.  groups = channel groups of the INPUT; output group p * groups + g = phase p, group g.
+__global__ void rows_to_phases_kernel(const act_t* __restrict__ x, const int* __restrict__ lpad, long long n_rows, RowGeom g,
+                                      int shrink_in, int halvings, int len_round, int groups, long long plane,
+                                      act_t* __restrict__ y) {
+  const long long total = n_rows * 8 * groups * 2;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pc = static_cast<int>(idx & 7);
+    const long long t = idx >> 3;
+    const long long row = t % n_rows;
+    const int og = static_cast<int>(t / n_rows);               // output group
+    const int phase = og / groups, grp = og - phase * groups;
+    const long long w = row / g.rpw;
+    const int rw = static_cast<int>(row - w * g.rpw);
+    const int f = rw / g.period, j = rw - f * g.period;
+    const int l_in = (lpad[w] - shrink_in + len_round) >> halvings;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (f < g.frames && 2 * j + phase < l_in) {
+      const int chunk = pc ^ static_cast<int>(row & 7);        // logical chunk held at this position of the output row
+      const long long r = w * g.rpw + static_cast<long long>(f) * g.period + 2 * j + phase;
+      o = *reinterpret_cast<const uint4*>(x + (grp * plane + r) * 64 + ((chunk ^ static_cast<int>(r & 7)) * 8));
+    }
+    *reinterpret_cast<uint4*>(y + (og * plane + row) * 64 + pc * 8) = o;
   }
 }
 
@@ -202,6 +232,8 @@ __global__ void heads_kernel(const HeadParams p) {
   const int nmd_dim = p.n_taps * p.tap_width;
   float* feat = s_feat + static_cast<size_t>(warp) * (p.feat + nmd_dim);
   float* nmdv = feat + p.feat;
+  const int mlp_layers = ((p.signals >> 20) & 3) ? ((p.signals >> 20) & 3) : 2;
+  const bool emb_pooled = ((p.signals >> 22) & 1) != 0;
   for (int w = blockIdx.x * warps_per_block + warp; w < p.n_windows; w += gridDim.x * warps_per_block) {
     const int cnt = p.pool_final ? 1 : p.pool_count[w];
     for (int c = lane; c < p.feat; c += 32) {
@@ -211,13 +243,14 @@ __global__ void heads_kernel(const HeadParams p) {
       else v = p.masking ? (cnt > 0 ? v / fmaxf(static_cast<float>(cnt), 1e-7f) : 0.0f)
                          : v / static_cast<float>(cnt);
       feat[c] = v;
-      if (p.emb && p.mlp_hidden == 0) p.emb[static_cast<long long>(w) * p.feat + c] = v;
+      if (p.emb && (p.mlp_hidden == 0 || emb_pooled)) p.emb[static_cast<long long>(w) * p.feat + c] = v;
     }
     if (p.mlp_hidden > 0) {
-      // legacy head: Dense(h, gelu) -> Dense(h, gelu) = "embedding" (nnlib/v1/layers.py:414-419);
-      // requires mlp_hidden == feat so the buffers can be reused
+      // hidden Dense layers in front of the classifier, zero-padded to mlp_hidden == feat so the buffer can be reused:
+      // the legacy head Dense(h, gelu) -> Dense(h, gelu) = "embedding" (nnlib/v1/layers.py:414-419), or the one / two hidden
+      // layers of a v2 classification head (builder.py:589-596), whose "embedding" stays the pooled features
       __syncwarp();
-      for (int layer = 0; layer < 2; ++layer) {
+      for (int layer = 0; layer < mlp_layers; ++layer) {
         const float* W = layer == 0 ? p.mlp_w1 : p.mlp_w2;
         const float* B = layer == 0 ? p.mlp_b1 : p.mlp_b2;
         float outv[8];                                   // up to 256 hidden units per warp
@@ -230,7 +263,7 @@ __global__ void heads_kernel(const HeadParams p) {
         for (int h = lane, i = 0; h < p.mlp_hidden; h += 32, ++i) feat[h] = outv[i];
         __syncwarp();
       }
-      if (p.emb)
+      if (p.emb && !emb_pooled)
         for (int c = lane; c < p.feat; c += 32) p.emb[static_cast<long long>(w) * p.feat + c] = feat[c];
     }
     for (int i = lane; i < nmd_dim; i += 32) {

@@ -473,6 +473,10 @@ class B200Engine:
         lens = np.diff(offsets)
         total = int(offsets[-1])
         two_pass = src.min_len is not None and src.min_len < fsize      # commands/predict.py:771-810
+        if two_pass and any(c.kind == 4 for c in self.plan.launches):
+            # TF's SAME padding of a strided conv depends on the parity of the (padded) batch length, which varies between the
+            # padded batches of the short pass; the row-plane kernels are picked once per forward call
+            raise NotImplementedError("--min-len < --fsize (the padded short-contig pass) is not available for models with strided residual blocks")
         passes = [self.plan_windows(lens, fsize, stride, src.dynamic_stride, src.dynamic_stride_threshold,
                                     min_len=fsize, short_pass=False)]
         if two_pass:

@@ -124,6 +124,8 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
                 # conv -- strided architectures are only well-defined without masking
                 raise ValueError("residual_block with strides > 1 needs model.use_masking: false (the reference forwards a mask "
                                  "of the pre-stride length past a strided block)")
+            if strides > 1 and int(c.get("dilation_rate", 1)) != 1:
+                raise NotImplementedError("a strided residual block with dilation_rate > 1 (tf.nn.conv1d refuses the combination too)")
             norm_type = str(c.get("norm_type", "masked_batchnorm")).lower()
             if norm_type not in ("masked_batchnorm", "masked_dyt"):
                 raise NotImplementedError(f"residual blocks with norm_type={norm_type!r} are not supported")

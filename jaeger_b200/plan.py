@@ -27,13 +27,13 @@ from .modelspec import ModelSpec
 
 ACT = {None: 0, "gelu": 1, "relu": 2, "gelu_erf": 3}
 LAYER_INT_FIELDS = 32
-LAYER_PTR_FIELDS = 12
+LAYER_PTR_FIELDS = 16
 # int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
  LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL) = range(26)
 (LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
- LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2) = range(12)
+ LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2, LP_KERNEL_ODD) = range(13)
 
 
 class LayerDesc(ctypes.Structure):
@@ -88,6 +88,8 @@ class ConvLaunch:
     out_const: np.ndarray | None = None   # value of this launch's output at rows its mask zeroed
     stage: int = 0                        # epilogue fill state while compiling
     kind: int = 1                         # 1 conv, 2 maxpool(2) per frame, 3 frame-sum + global max pool, 4 rows -> (even, odd) planes
+    kernel_odd: np.ndarray | None = None  # strided convs: the kernel to use when the layer's INPUT frame length is odd (TF SAME
+                                          # padding of a stride-2 conv depends on the parity of the length); `kernel` = even
     epi_f32: int = 0                      # epilogue in fp32 with one rounding at the store (norm after the activation, large scales)
     len_ceil: int = 0                     # the frame length is halved with ceil (SAME stride-2 convs), not floor (MaxPool(2))
     halvings: int = 0                     # MaxPool(2) stages applied to the frame length before this layer
@@ -110,8 +112,10 @@ class Plan:
     total_shrink: int
     real_feat_dim: int | None = None           # feature width before padding to a multiple of 64
     tok_offset: int = 1
-    mlp: list[np.ndarray] | None = None        # legacy head: [w1, b1, w2, b2]
+    mlp: list[np.ndarray] | None = None        # hidden Dense layers in front of the classifier: [w1, b1(, w2, b2)], width = feat_dim
     mlp_act: str | None = None
+    mlp_layers: int = 2                        # how many of them (the legacy head has two)
+    emb_pooled: bool = False                   # "embedding" output = the pooled features (v2 models); legacy: the last hidden layer
     rel_signals: list[str] | None = None       # OOD signals appended to the NMD vector (nmd_plus_signals)
     nmd_cols: np.ndarray | None = None         # columns of the padded device NMD vector that are the reference's NMD vector
     flops_per_window_formula: Any = None
@@ -180,25 +184,55 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         return n_masks - 1
 
     def other_buf(*used):
-        for b in (1, 2, 3):
+        for b in (1, 2, 3, 4, 5):
             if b not in used:
                 return b
         raise AssertionError
 
-    def add_conv(kernel, bias, dilation, padding, use_masking, in_buf, in_mask, out_buf, sc_buf=-1, sc_mask=-1, sc_const=None):
+    halvings = 0          # stride-2 stages passed so far (frame length = ceil(L / 2^halvings))
+
+    def add_conv(kernel, bias, dilation, padding, use_masking, in_buf, in_mask, out_buf, sc_buf=-1, sc_mask=-1, sc_const=None,
+                 pad_left=None, kernel_odd=None):
         nonlocal cum_shrink
         k = kernel.shape[0]
         span = dilation * (k - 1)
-        if padding == "same":
+        if pad_left is not None:
+            shrink = 0
+        elif padding == "same":
             pad_left, shrink = span // 2, 0
         else:
             pad_left, shrink = 0, span
+        if shrink and halvings:
+            raise NotImplementedError("a VALID convolution after a strided block")
         c = ConvLaunch(kernel=_np32(kernel), bias=_np32(bias), dilation=dilation, pad_left=pad_left, shrink=shrink,
                        in_buf=in_buf, out_buf=out_buf, sc_buf=sc_buf, mask_in=in_mask, mask_out=new_mask(),
-                       sc_mask=sc_mask, masking=int(use_masking), cum_shrink_in=cum_shrink, sc_const=sc_const)
+                       sc_mask=sc_mask, masking=int(use_masking), cum_shrink_in=cum_shrink, sc_const=sc_const,
+                       halvings=halvings, len_ceil=int(halvings > 0), kernel_odd=None if kernel_odd is None else _np32(kernel_odd))
         cum_shrink += shrink
         launches.append(c)
         return c
+
+    def split_phases(kernel, dilation, cin_pad):
+        """A stride-2 SAME conv over rows x[.] as a stride-1 conv over the (even, odd) row planes S[j] = (x[2j], x[2j+1]):
+        x[2j + o] = S[j + o // 2][o % 2], so tap t (offset o = t * dilation - pad_left) lands on shift o // 2, phase o % 2.
+        TF's SAME padding of the strided conv depends on the parity of the input length L (pad_total = (k-1)d - 1 for even L,
+        (k-1)d for odd L): returns (kernel for even L, kernel for odd L, pad_left of the phase conv), both kernels
+        [k', 2 * cin_pad, cout] over one common shift range."""
+        k, cin, cout = kernel.shape
+        span = dilation * (k - 1)
+        variants = []
+        for total in (max(span - 1, 0), span):                  # even L, odd L
+            pl = total // 2
+            variants.append([(t, (t * dilation - pl) // 2, (t * dilation - pl) % 2) for t in range(k)])
+        lo = min(s for v in variants for _, s, _ in v)
+        hi = max(s for v in variants for _, s, _ in v)
+        out = []
+        for v in variants:
+            kk = np.zeros((hi - lo + 1, 2 * cin_pad, cout), np.float64)
+            for t, sft, ph in v:
+                kk[sft - lo, ph * cin_pad:ph * cin_pad + cin] = kernel[t]
+            out.append(kk)
+        return out[0], out[1], -lo
 
     def finish(c: ConvLaunch):
         """Fold bias into shift1 and compute the masked-row constant of the launch output."""
@@ -258,21 +292,52 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             cur_buf, cur_mask, ch = out_buf, cur.mask_out, kernel.shape[2]
         elif layer.kind == "resblock":
             masking = cfg["use_masking"] and spec.use_masking
+            stride = int(cfg.get("strides", 1))
+            zero_bias = lambda cw: cw["bias"] if cfg.get("use_bias", True) else np.zeros_like(cw["bias"])      # noqa: E731
             for blk in lw["blocks"]:
                 x_buf, x_mask = cur_buf, cur_mask
                 if cur is not None and cur.out_const is None:
                     finish(cur)
                 x_const = launches[-1].out_const if launches else None
-                h_buf = other_buf(x_buf)
-                c1 = add_conv(blk["conv1"]["kernel"], blk["conv1"]["bias"], cfg["dilation"], "same", masking,
-                              x_buf, x_mask, h_buf)
+                src_buf, cin_pad = x_buf, -(-blk["conv1"]["kernel"].shape[1] // 64) * 64
+                if stride == 2:
+                    # rows -> (even, odd) row planes with twice the channels and half the length (kind 4), so that the strided
+                    # convs of the block run on the stride-1 kernels (layers.py:1840-1864 conv1 / bypass conv of a strided block)
+                    src_buf = other_buf(x_buf)
+                    launches.append(ConvLaunch(kernel=np.zeros((1, cin_pad, 2 * cin_pad), np.float32), bias=np.zeros(2 * cin_pad, np.float32),
+                                               dilation=1, pad_left=0, shrink=0, in_buf=x_buf, out_buf=src_buf, mask_in=x_mask,
+                                               mask_out=x_mask, masking=0, kind=4, halvings=halvings, len_ceil=int(halvings > 0),
+                                               cum_shrink_in=cum_shrink))
+                    halvings += 1
+                h_buf = other_buf(x_buf, src_buf)
+                if stride == 2:
+                    k_even, k_odd, pl = split_phases(blk["conv1"]["kernel"].astype(np.float64), cfg["dilation"], cin_pad)
+                    c1 = add_conv(k_even, zero_bias(blk["conv1"]), 1, "same", masking, src_buf, x_mask, h_buf, pad_left=pl, kernel_odd=k_odd)
+                else:
+                    c1 = add_conv(blk["conv1"]["kernel"], zero_bias(blk["conv1"]), cfg["dilation"], "same", masking, x_buf, x_mask, h_buf)
                 c1.scale1, c1.shift1, c1.dyt_g1, c1.dyt_b1 = _norm_fold(blk["bn1"], 1e-5)
                 c1.act1, c1.stage = cfg["activation"], 2
                 finish(c1)
-                # conv2 writes the block output in place over the block input (same rows, same thread)
-                c2 = add_conv(blk["conv2"]["kernel"], blk["conv2"]["bias"], cfg["dilation"], "same", masking,
-                              h_buf, c1.mask_out, x_buf, sc_buf=x_buf, sc_mask=x_mask if masking else -1,
-                              sc_const=x_const)
+                sc_buf, sc_mask, sc_const = x_buf, (x_mask if masking else -1), x_const
+                if "conv3" in blk:
+                    # 1x1 bypass conv + norm on the block input (layers.py:1855-1864, 1903-1909): its own launch, no activation;
+                    # conv2 adds it as the shortcut.  Strided: tap (shift 0, even phase) of the row-plane tensor.
+                    b_buf = other_buf(x_buf, src_buf, h_buf)
+                    k3 = blk["conv3"]["kernel"].astype(np.float64)
+                    if stride == 2:
+                        k3p = np.zeros((1, 2 * cin_pad, k3.shape[2]), np.float64)
+                        k3p[0, :k3.shape[1]] = k3[0]
+                        c3 = add_conv(k3p, zero_bias(blk["conv3"]), 1, "same", masking, src_buf, x_mask, b_buf, pad_left=0)
+                    else:
+                        c3 = add_conv(k3, zero_bias(blk["conv3"]), 1, "same", masking, x_buf, x_mask, b_buf)
+                    c3.scale1, c3.shift1, c3.dyt_g1, c3.dyt_b1 = _norm_fold(blk["bn3"], 1e-5)
+                    c3.stage = 2
+                    finish(c3)
+                    sc_buf, sc_mask, sc_const = b_buf, (c3.mask_out if masking else -1), c3.out_const
+                # conv2 writes the block output in place over the block input when that IS the shortcut (same rows, same
+                # thread); with a bypass the block input is dead after conv1 / conv3 and its buffer is reused all the same
+                c2 = add_conv(blk["conv2"]["kernel"], zero_bias(blk["conv2"]), cfg["dilation"], "same", masking,
+                              h_buf, c1.mask_out, x_buf, sc_buf=sc_buf, sc_mask=sc_mask, sc_const=sc_const)
                 c2.scale1, c2.shift1, c2.dyt_g1, c2.dyt_b1 = _norm_fold(blk["bn2"], 1e-5)
                 c2.act1, c2.stage = cfg["activation"], 2
                 cur = c2
@@ -345,6 +410,12 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         kp = np.zeros((k, cin_p, cout_p), np.float32)
         kp[:, :cin, :cout] = c.kernel
         c.kernel = kp
+        if c.kernel_odd is not None:
+            ko = np.zeros((k, cin_p, cout_p), np.float32)
+            ko[:, :cin, :cout] = c.kernel_odd
+            c.kernel_odd = ko
+        if c.kind == 4:
+            continue
 
         def pad(a, fill):
             if a is None:
@@ -385,13 +456,33 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         k1p[n_taps * tap_width:] = k1[len(nmd_cols):]
         rel = [k1p, _np32(r[0]["bias"]), _np32(r[1]["kernel"]), _np32(r[1]["bias"])]
         rel_hidden = r[0]["kernel"].shape[1]
+    # classification head (builder.py:589-596): Dense stack; hidden layers are zero-padded to the feature width so that the
+    # heads kernel can reuse one buffer (a padded hidden unit is act(0) = 0 for gelu / relu and meets zero weights)
+    dense = weights["classifier"]
+    if len(dense) != len(spec.classifier):
+        raise ValueError(f"classifier head: {len(spec.classifier)} Dense layers in the project, {len(dense)} in the weights")
+    mlp, mlp_act, width = None, None, real_feat
+    if len(dense) > 1:
+        mlp_act = spec.classifier[0]["activation"]
+        mlp = []
+        for d in dense[:-1]:
+            kin, kout = d["kernel"].shape
+            if kin != width or kout > ch:
+                raise NotImplementedError(f"classifier hidden layer {kin} -> {kout}: input must match, width must not exceed the feature width {ch}")
+            wp, bp = np.zeros((ch, ch), np.float32), np.zeros(ch, np.float32)
+            wp[:kin, :kout], bp[:kout] = d["kernel"], d["bias"]
+            mlp += [wp, bp]
+            width = kout
+    if dense[-1]["kernel"].shape[0] != width:
+        raise ValueError(f"classifier output layer expects {dense[-1]['kernel'].shape[0]} inputs, the head provides {width}")
     cls_w = np.zeros((ch, spec.n_classes), np.float32)
-    cls_w[:real_feat] = weights["classifier"][0]["kernel"]
+    cls_w[:width] = dense[-1]["kernel"]
     return Plan(launches=launches, n_classes=spec.n_classes, feat_dim=ch, pool_mode=last.pool_mode, n_taps=n_taps,
-                tap_width=tap_width, cls_w=cls_w, cls_b=_np32(weights["classifier"][0]["bias"]), rel=rel,
+                tap_width=tap_width, cls_w=cls_w, cls_b=_np32(dense[-1]["bias"]), rel=rel,
                 rel_hidden=rel_hidden, total_shrink=cum_shrink, real_feat_dim=real_feat,
                 rel_signals=list(spec.reliability_signals) if (rel is not None and spec.reliability_signals) else None,
-                nmd_cols=nmd_cols if len(nmd_cols) != n_taps * tap_width else None)
+                nmd_cols=nmd_cols if len(nmd_cols) != n_taps * tap_width else None,
+                mlp=mlp, mlp_act=mlp_act, mlp_layers=len(dense) - 1, emb_pooled=True)
 
 
 def _fptr(a: np.ndarray | None):
@@ -416,7 +507,7 @@ def to_ctypes(plan: Plan):
             d.i[i] = int(v)
         ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,
                 LP_SHIFT2: c.shift2, LP_SC_CONST: c.sc_const, LP_TAP_MEAN: c.tap_mean,
-                LP_DYT_G1: c.dyt_g1, LP_DYT_B1: c.dyt_b1, LP_DYT_G2: c.dyt_g2, LP_DYT_B2: c.dyt_b2}
+                LP_DYT_G1: c.dyt_g1, LP_DYT_B1: c.dyt_b1, LP_DYT_G2: c.dyt_g2, LP_DYT_B2: c.dyt_b2, LP_KERNEL_ODD: c.kernel_odd}
         for i, a in ptrs.items():
             d.p[i] = _fptr(a)
     h = HeadDesc()
@@ -433,6 +524,8 @@ def to_ctypes(plan: Plan):
             h.reserved[0] = code
     if plan.mlp is not None:
         h.mlp_hidden, h.mlp_act = plan.mlp[0].shape[1], ACT[plan.mlp_act]
-        h.mlp_w1, h.mlp_b1, h.mlp_w2, h.mlp_b2 = (_fptr(a) for a in plan.mlp)
+        ptrs4 = [_fptr(a) for a in plan.mlp] + [_fptr(None)] * (4 - len(plan.mlp))
+        h.mlp_w1, h.mlp_b1, h.mlp_w2, h.mlp_b2 = ptrs4
+        h.reserved[0] |= (int(plan.mlp_layers) << 20) | (int(bool(plan.emb_pooled)) << 22)
     plan.keep = [arr, h]
     return arr, h

@@ -49,19 +49,22 @@ def _act(x, name):
     return x
 
 
-def _conv1d_tf(x, kernel, dilation, padding):
-    """x [N, L, Cin], kernel [k, Cin, Cout] (TF layout) -> [N, L', Cout] with TF padding rules."""
+def _conv1d_tf(x, kernel, dilation, padding, stride=1):
+    """x [N, L, Cin], kernel [k, Cin, Cout] (TF layout) -> [N, L', Cout] with TF padding rules: SAME gives
+    L' = ceil(L / stride) with max((L' - 1) * stride + dilation * (k - 1) + 1 - L, 0) zeros, the smaller half in front."""
     k = kernel.shape[0]
     xt = x.transpose(1, 2)
     if padding == "same":
-        total = dilation * (k - 1)
+        l_in = x.shape[1]
+        l_out = -(-l_in // stride)
+        total = max((l_out - 1) * stride + dilation * (k - 1) + 1 - l_in, 0)
         left = total // 2
         xt = F.pad(xt, (left, total - left))
     w = kernel.permute(2, 1, 0).contiguous()      # [Cout, Cin, k]
-    return F.conv1d(xt, w, dilation=dilation).transpose(1, 2)
+    return F.conv1d(xt, w, dilation=dilation, stride=stride).transpose(1, 2)
 
 
-def masked_conv1d(x, mask, kernel, bias, dilation=1, padding="valid", activation=None, mask_mode="any"):
+def masked_conv1d(x, mask, kernel, bias, dilation=1, padding="valid", activation=None, mask_mode="any", stride=1):
     """layers.py:1217-1280.  x [B,6,L,C]; mask [B,6,L] float or None."""
     b, f, l, c = x.shape
     out_mask = None
@@ -69,7 +72,7 @@ def masked_conv1d(x, mask, kernel, bias, dilation=1, padding="valid", activation
         x = x * mask.unsqueeze(-1)
         k = kernel.shape[0]
         ones = torch.ones(k, 1, 1, dtype=x.dtype)
-        mc = _conv1d_tf(mask.reshape(b * f, l, 1), ones, dilation, padding)
+        mc = _conv1d_tf(mask.reshape(b * f, l, 1), ones, dilation, padding, stride)
         if mask_mode == "any":
             om = mc > 0
         elif mask_mode == "majority":
@@ -77,7 +80,7 @@ def masked_conv1d(x, mask, kernel, bias, dilation=1, padding="valid", activation
         else:
             om = mc == float(k)
         out_mask = om.squeeze(-1).reshape(b, f, -1).to(x.dtype)
-    y = _conv1d_tf(x.reshape(b * f, l, c), kernel, dilation, padding)
+    y = _conv1d_tf(x.reshape(b * f, l, c), kernel, dilation, padding, stride)
     if bias is not None:
         y = y + bias
     y = _act(y, activation)
@@ -162,17 +165,22 @@ def residual_stack(x, mask, blocks, c, dtype=torch.float32):
     """ResidualBlockStack / ResidualBlock.call (layers.py:2696-2704, 1882-1915) on x [B,6,L,C] carrying `mask` (or None):
     returns (output, the mask it carries, NMD vector of the last block's bn2 when c["return_nmd"] else None)."""
     block_nmd = None
+    stride = int(c.get("strides", 1))                 # ResidualBlockStack hands `strides` to EVERY block (layers.py:2676-2690)
     for bi, blk in enumerate(blocks):
         m_in = mask if c["use_masking"] else None
-        h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), _t(blk["conv1"]["bias"], dtype),
-                              c["dilation"], "same")
-        h = _act(_norm(h, {k: _t(v, dtype) for k, v in blk["bn1"].items()}, m1 if m_in is not None else None), c["activation"])
-        h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), _t(blk["conv2"]["bias"], dtype),
-                               c["dilation"], "same")
+        tw = lambda d: {k: _t(v, dtype) for k, v in d.items()}     # noqa: E731
+        bias = lambda d: _t(d["bias"], dtype) if c.get("use_bias", True) else None     # noqa: E731
+        h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), bias(blk["conv1"]), c["dilation"], "same", stride=stride)
+        h = _act(_norm(h, tw(blk["bn1"]), m1 if m_in is not None else None), c["activation"])
+        h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), bias(blk["conv2"]), c["dilation"], "same")
         if c.get("return_nmd") and bi == len(blocks) - 1:          # layers.py:1897-1898, 2696-2704
             block_nmd = nmd_vector(h2, m2 if m_in is not None else None, _t(blk["bn2"]["mean"], dtype))
-        h2 = _norm(h2, {k: _t(v, dtype) for k, v in blk["bn2"].items()}, m2 if m_in is not None else None)
-        x = _act(h2 + x, c["activation"])            # MaskedAdd: no re-masking (layers.py:60-76)
+        h2 = _norm(h2, tw(blk["bn2"]), m2 if m_in is not None else None)
+        shortcut = x
+        if "conv3" in blk:                            # layers.py:1855-1864, 1903-1909: 1x1 conv (same stride) + norm on the block input
+            sc, m3 = masked_conv1d(x, m_in, _t(blk["conv3"]["kernel"], dtype), bias(blk["conv3"]), c["dilation"], "same", stride=stride)
+            shortcut = _norm(sc, tw(blk["bn3"]), m3 if m_in is not None else None)
+        x = _act(h2 + shortcut, c["activation"])      # MaskedAdd: no re-masking (layers.py:60-76)
         mask = m2 if m_in is not None else mask
     return x, mask, block_nmd
 
@@ -215,8 +223,10 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
         else:
             raise NotImplementedError(layer.kind)
     feat = masked_global_max(x, mask) if spec.pooling == "max" else masked_global_avg(x, mask)
-    cls = weights["classifier"][0]
-    out = {"prediction": feat @ _t(cls["kernel"], dtype) + _t(cls["bias"], dtype), "embedding": feat}
+    z = feat                                          # classification head: Dense stack, dropout is the identity (builder.py:589-596)
+    for d, dw in zip(spec.classifier, weights["classifier"]):
+        z = _act(z @ _t(dw["kernel"], dtype) + _t(dw["bias"], dtype), d.get("activation"))
+    out = {"prediction": z, "embedding": feat}
     if nmds:
         out["nmd"] = torch.cat(nmds, dim=-1)
         if spec.reliability is not None and "reliability" in weights:

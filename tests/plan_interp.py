@@ -26,13 +26,23 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
     taps = {}
     pooled = None
     final_mask = None
+    odd_len = False                                            # parity of the frame length in front of the last stride
     for c in plan.launches:
         x = bufs[c.in_buf]                                     # stored (already masked) input
+        if c.kind == 4:                                        # rows -> (even, odd) row planes: twice the channels, ceil(L / 2) rows
+            l_in = x.shape[2]
+            odd_len = bool(l_in & 1)
+            ev, od = x[:, :, 0::2], x[:, :, 1::2]
+            if od.shape[2] < ev.shape[2]:
+                od = F.pad(od, (0, 0, 0, 1))
+            bufs[c.out_buf] = torch.cat([ev, od], dim=-1)
+            continue
+        kern = c.kernel_odd if (c.kernel_odd is not None and odd_len) else c.kernel
         k = c.kernel.shape[0]
         xt = x.reshape(b * f, x.shape[2], x.shape[3]).transpose(1, 2)
         span = c.dilation * (k - 1)
         xt = F.pad(xt, (c.pad_left, span - c.pad_left - c.shrink)) if c.shrink == 0 else xt
-        w = torch.as_tensor(c.kernel, dtype=dt).permute(2, 1, 0).contiguous()
+        w = torch.as_tensor(kern, dtype=dt).permute(2, 1, 0).contiguous()
         acc = F.conv1d(xt, w, dilation=c.dilation).transpose(1, 2).reshape(b, f, -1, c.kernel.shape[2])
         m_in = masks[c.mask_in]
         if c.masking:
@@ -75,7 +85,11 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
         if c.out_buf >= 0:
             bufs[c.out_buf] = v * mo
     real = plan.real_feat_dim or plan.feat_dim
-    out = {"embedding": pooled[:, :real], "prediction": pooled @ torch.as_tensor(plan.cls_w, dtype=dt) + torch.as_tensor(plan.cls_b, dtype=dt)}
+    z = pooled
+    if plan.mlp is not None:                                   # hidden Dense layers, zero-padded to the feature width
+        for i in range(plan.mlp_layers):
+            z = _act(z @ torch.as_tensor(plan.mlp[2 * i], dtype=dt) + torch.as_tensor(plan.mlp[2 * i + 1], dtype=dt), plan.mlp_act)
+    out = {"embedding": pooled[:, :real], "prediction": z @ torch.as_tensor(plan.cls_w, dtype=dt) + torch.as_tensor(plan.cls_b, dtype=dt)}
     if taps:
         out["nmd"] = torch.cat([taps[i] for i in range(len(taps))], dim=-1)
         padded_nmd = out["nmd"]

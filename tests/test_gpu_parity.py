@@ -1150,3 +1150,41 @@ def test_label_agreement_at_scale_real_weights_and_scaled_standin():
     assert st["contig_label_agreement"] >= 0.999, st
     assert st["max_abs_logit_err"] <= 0.1, st                        # 25 x the 4e-3 bound of the unscaled stand-in
     assert st["largest_margin_among_flips"] <= 2 * st["max_abs_logit_err"], st
+
+
+@pytest.mark.parametrize("which,lc", [("small", 665), ("small", 498), ("small_wide", 665), ("baseline_3p4m", 665), ("flat_g1", 341)])
+def test_strided_bypass_blocks_and_mlp_heads_vs_oracle(which, lc):
+    """Residual blocks with strides = 2 / a 1x1 bypass conv + norm (nnlib/v2/layers.py:1840-1864, 1903-1909), layers of 256
+    channels (run as slices of 64 output channels on the CTA-pair kernel) and multi-layer classification heads
+    (builder.py:589-596) on the device against the fp32 oracle: a small network with every variant (odd and even frame
+    lengths), the reference's train_config/nn_config_baseline.yaml (3.4 M) and the flat first-generation schema of
+    commands/configs/nn_config.yaml.  Tolerance: fp16 activations / weights vs fp32, |logit| <~ 0.5: 6e-3 absolute."""
+    import yaml
+    from jaeger_b200 import B200Engine, init_random, parse_project
+    from oracle import forward as ofw
+    from tests.test_plan_cpu import _baseline_3p4m_config, flat_g1_config, small_strided_config
+    if which == "small":
+        cfg = small_strided_config()
+    elif which == "small_wide":                               # 128 -> 256 channels: the wide layers run as slices of 64 output channels
+        cfg = small_strided_config(filters=(128, 256))
+    elif which == "baseline_3p4m":
+        if not Path("/root/reference/train_config/nn_config_baseline.yaml").exists():
+            pytest.skip("the reference tree is not on this box: the configuration is exercised by the CPU suite")
+        cfg = _baseline_3p4m_config()
+    else:
+        cfg = flat_g1_config()
+    spec = parse_project(cfg)
+    w = init_random(spec, 7)
+    rng = np.random.default_rng(lc)
+    tok = rng.integers(0, 65, (5, 6, lc)).astype(np.uint8)
+    tok[1, :, lc - 40:] = 0                                   # unknown codons are ordinary zero rows when masking is off
+    eng = B200Engine(spec=spec, weights=w)
+    got = eng.predict([({"translated": tok},)])
+    ref = ofw.forward(spec, w, tok)
+    names = eng.conv_kernel_names()
+    eng.close()
+    for key in ("prediction", "embedding") + (("nmd",) if "nmd" in ref else ()):
+        d = np.abs(got[key] - ref[key]).max()
+        assert d < 6e-3 * max(1.0, np.abs(ref[key]).max()), (which, key, d, names)
+    assert "conv_ref_kernel" not in names, names             # every conv runs on a tensor-core kernel
+    print(which, lc, names, "max |logit diff|", np.abs(got["prediction"] - ref["prediction"]).max())

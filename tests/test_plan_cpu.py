@@ -430,3 +430,106 @@ def test_plan_compiler_vs_reference_builder_code(case):
     got = run_plan(compile_plan(spec, weights), tokens)
     assert np.allclose(got["embedding"], feat, rtol=2e-5, atol=2e-5), np.abs(got["embedding"] - feat).max()
     assert np.allclose(got["nmd"], nmd, rtol=2e-5, atol=2e-5), np.abs(got["nmd"] - nmd).max()
+
+
+def _baseline_3p4m_config():
+    """train_config/nn_config_baseline.yaml as a dict (the broken quote of its data_dir line repaired), masking off: strided
+    architectures are only well-defined without it."""
+    import re
+    import yaml
+    txt = (Path("/root/reference/train_config/nn_config_baseline.yaml")).read_text()
+    cfg = yaml.safe_load(re.sub(r'"/path/to/data directory""', '"x"', txt))
+    cfg["model"]["use_masking"] = False
+    return cfg
+
+
+def small_strided_config(filters=(64, 128), bypass_first=True):
+    """A small network with every new block variant: a stride-1 block with a 1x1 bypass, strided blocks (channel growth,
+    k5 and k3), a block after the stride with dilation 2, return_nmd on the last block, and a two-hidden-layer classifier."""
+    def blk(f, k, s=1, d=1, n=1, one=False, nmd=False):
+        return {"name": "residual_block", "config": {"block_size": n, "filters": f, "kernel_size": k, "strides": s, "dilation_rate": d,
+                                                      "use_1x1conv": one, "use_bias": True, "activation": "gelu", "return_nmd": nmd}}
+    hidden = [{"name": "masked_conv1d", "config": {"filters": filters[0], "kernel_size": 7, "use_bias": True, "activation": None}},
+              {"name": "masked_batchnorm", "config": {}}, {"name": "activation", "config": {"activation": "gelu"}},
+              blk(filters[0], 5, one=bypass_first), blk(filters[1], 5, s=2), blk(filters[1], 3, d=2, n=2), blk(filters[1], 3, s=2, nmd=True)]
+    return {"model": {"name": "strided_small", "activation": "gelu", "use_masking": False,
+                      "class_label_map": [{"class": c, "label": i} for i, c in enumerate("abcd")],
+                      "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 16},
+                      "string_processor": {"seq_onehot": False, "codon": "CODON", "codon_id": "CODON_ID", "masking": False},
+                      "representation_learner": {"hidden_layers": hidden, "pooling": "max"},
+                      "classifier": {"input_shape": filters[1], "hidden_layers": [
+                          {"name": "dense", "config": {"units": 48, "activation": "gelu", "use_bias": True}},
+                          {"name": "dropout", "config": {"rate": 0.5}},
+                          {"name": "dense", "config": {"units": 32, "activation": "gelu", "use_bias": True}},
+                          {"name": "dense", "config": {"units": 4, "activation": None, "use_bias": True}}]},
+                      "reliability_model": {"hidden_layers": [{"name": "dense", "config": {"units": 8, "activation": "gelu", "use_bias": True}},
+                                                              {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]}}}
+
+
+def flat_g1_config():
+    """A first-generation (flat schema) project: the keys of commands/configs/nn_config.yaml:36-66 with the shape of the
+    `jaeger_1.5M` template -- one-hot input, conv k7, three single-block stacks 64 / 128 / 256 with stride 2, final conv k5,
+    max pooling, Dense(128) -> Dense(5) classifier."""
+    return {"model": {
+        "name": "jaeger_flat_g1", "activation": "gelu",
+        "class_label_map": [{"class": c, "label": i} for i, c in enumerate(["bacteria", "phage", "archaea", "virus", "eukarya"])],
+        "embedding": {"type": "translated", "strands": 2, "frames": 6, "length": None, "input_shape": [6, None, 64], "embedding_size": 4},
+        "string_processor": {"codon": "CODON", "codon_id": "CODON_ID", "crop_size": 1024},
+        "representation_learner": {
+            "masked_conv1d_1_filters": 64, "masked_conv1d_1_kernel_size": 7, "masked_conv1d_1_strides": 1, "masked_conv1d_1_dilation_rate": 1,
+            "block_sizes": [1, 1, 1], "block_filters": [64, 128, 256], "block_kernel_size": [5, 5, 5], "block_kernel_dilation": [1, 1, 1],
+            "block_kernel_strides": [2, 2, 2],
+            "masked_conv1d_final_kernel_size": 5, "masked_conv1d_final_strides": 1, "masked_conv1d_final_dilation_rate": 1, "pooling": "max"},
+        "classifier": {"dense_1_units": 128, "classes": 5},
+        "reliability_model": {"dense_1_units": 128}}}
+
+
+@pytest.mark.parametrize("lc", [665, 498, 166, 165])
+def test_strided_and_bypass_blocks_plan_equals_unfused_oracle(lc):
+    """ResidualBlock with strides = 2 and / or a 1x1 bypass conv + norm (nnlib/v2/layers.py:1840-1864, 1903-1909), compiled to
+    row-plane launches + stride-1 convs (plan.py:split_phases), against the un-fused oracle whose strided convs use TF's SAME
+    padding rule -- for even and odd frame lengths (lc - 6 = 659, 492, 160, 159: the padding differs with the parity) -- and a
+    classifier head with two hidden Dense layers."""
+    spec = parse_project(small_strided_config())
+    w = init_random(spec, 5)
+    rng = np.random.default_rng(lc)
+    tok = rng.integers(0, 65, (3, 6, lc)).astype(np.uint8)
+    plan = compile_plan(spec, w)
+    assert sum(c.kind == 4 for c in plan.launches) == 2 and any(c.kernel_odd is not None for c in plan.launches)
+    got, want = run_plan(plan, tok), ofw.forward(spec, w, tok, dtype=torch.float64)
+    for key in ("prediction", "embedding", "nmd", "reliability"):
+        assert np.abs(got[key] - want[key]).max() < 1e-6, (key, np.abs(got[key] - want[key]).max())     # the oracle returns float32
+
+
+def test_reference_baseline_3p4m_and_flat_g1_configs_compile_and_match_the_oracle():
+    """The reference's own strided configurations: train_config/nn_config_baseline.yaml (3.4 M parameters: stride-2 blocks with
+    bypass, dilations up to 8, 256 channels, MLP head) and the flat first-generation schema of commands/configs/nn_config.yaml
+    (the `jaeger_1.5M` template of the G1 models, translated to a layer list by modelspec.flat_schema_to_layer_list)."""
+    import yaml
+    ref_flat = Path("/root/reference/src/jaeger/commands/configs/nn_config.yaml")
+    cases = [(flat_g1_config(), 3)]
+    if ref_flat.exists():
+        cases += [(_baseline_3p4m_config(), 3), (yaml.safe_load(ref_flat.read_text()), 3)]
+    for cfg, n_kind4 in cases:
+        spec = parse_project(cfg)
+        w = init_random(spec, 1)
+        plan = compile_plan(spec, w)
+        assert sum(c.kind == 4 for c in plan.launches) == n_kind4
+        tok = np.random.default_rng(3).integers(0, 65, (2, 6, 165)).astype(np.uint8)
+        got, want = run_plan(plan, tok), ofw.forward(spec, w, tok, dtype=torch.float64)
+        for key in want:
+            assert np.abs(got[key] - want[key]).max() < 1e-6, (spec.name, key)
+    if not ref_flat.exists():
+        return
+    spec = parse_project(_baseline_3p4m_config())
+    n_bias_free = sum(v.size for lw in init_random(spec, 0)["layers"] if "blocks" in lw for b in lw["blocks"]
+                      for name in ("conv1", "conv2", "conv3") if name in b and not np.any(b[name]["bias"]) and b[name]["kernel"].shape[2] == 256
+                      for v in [b[name]["bias"]])
+    assert count_params(spec, init_random(spec, 0)) - n_bias_free == 3_384_352          # SURVEY.md 3.2b: "3.4M"
+
+
+def test_strided_blocks_need_masking_off():
+    cfg = small_strided_config()
+    cfg["model"]["use_masking"] = True
+    with pytest.raises(ValueError, match="use_masking: false"):
+        parse_project(cfg)
