@@ -59,6 +59,21 @@ def model_cfg(norm: str, masking: bool, pooling: str):
     return {"hidden_layers": hidden, "pooling": pooling}, masking
 
 
+def strided_cfg():
+    """Strided / bypass residual blocks (nnlib/v2/layers.py:1840-1864, 1903-1909; train_config/nn_config_baseline.yaml family): a
+    stride-1 block with use_1x1conv, a stride-2 block that grows the channels, a two-block stack with dilation 2 whose last bn2
+    returns its NMD vector.  Masking off (strided blocks are only well-defined without it)."""
+    def blk(**kw):
+        return {"name": "residual_block", "config": {"use_bias": True, "activation": "gelu", **kw}}
+    tail = [{"name": "nmd"}, {"name": "masked_batchnorm", "config": {"return_nmd": False}}, {"name": "activation", "config": {"activation": "gelu"}}]
+    hidden = [{"name": "masked_conv1d", "config": {"filters": 16, "kernel_size": 7, "strides": 1, "dilation_rate": 1, "use_bias": True,
+                                                   "activation": None}}] + tail + [
+        blk(use_1x1conv=True, block_size=1, filters=16, kernel_size=5, strides=1, dilation_rate=1),
+        blk(use_1x1conv=False, block_size=1, filters=24, kernel_size=5, strides=2, dilation_rate=1),
+        blk(use_1x1conv=False, block_size=2, filters=24, kernel_size=3, strides=1, dilation_rate=2, return_nmd=True)]
+    return {"hidden_layers": hidden, "pooling": "max"}, False
+
+
 def main():
     from jaeger.nnlib import builder as B
     out = {}
@@ -69,8 +84,8 @@ def main():
     tok[1, :, 50:] = 0
     emb = rng.normal(size=(65, 12)) * 0.5
     out["tokens"], out["embedding_table"] = tok.astype(np.uint8), emb
-    for ci, (norm, masking, pooling) in enumerate([("bn", True, "max"), ("dyt", True, "average"), ("bn", False, "max")]):
-        cfg, use_masking = model_cfg(norm, masking, pooling)
+    for ci, (norm, masking, pooling) in enumerate([("bn", True, "max"), ("dyt", True, "average"), ("bn", False, "max"), ("strided", False, "max")]):
+        cfg, use_masking = strided_cfg() if norm == "strided" else model_cfg(norm, masking, pooling)
         fake = types.SimpleNamespace(use_masking=use_masking, model_cfg={}, input_shape=(6, None), _make_regularizer=lambda *a, **k: None)
         real = B.DynamicModelBuilder.__new__(B.DynamicModelBuilder)
         fake._layers = {"masked_conv1d": B.MaskedConv1D, "masked_batchnorm": B.MaskedBatchNorm, "masked_dyt": B.MaskedDYT, "nmd": B.NMDLayer,

@@ -236,6 +236,14 @@ def v2_model_case(case: int):
     block = {"name": "residual_block", "config": {"block_size": 2, "filters": 16, "kernel_size": 5, "dilation_rate": 3, "use_bias": True,
                                                   **({"norm_type": "masked_dyt"} if norm == "dyt" else {})}}
     hidden = [{"name": "masked_conv1d", "config": {"filters": 16, "kernel_size": 7, "use_bias": True, "activation": None}}] + tail + [block] + tail + [block] + tail
+    if norm == "strided":          # make_v2_model_goldens.py:strided_cfg -- bypass / stride-2 / return_nmd blocks, masking off
+        def blk(**kw):
+            return {"name": "residual_block", "config": {"use_bias": True, "activation": "gelu", **kw}}
+        tail = [{"name": "nmd"}, {"name": "masked_batchnorm", "config": {}}, {"name": "activation", "config": {"activation": "gelu"}}]
+        hidden = [{"name": "masked_conv1d", "config": {"filters": 16, "kernel_size": 7, "use_bias": True, "activation": None}}] + tail + [
+            blk(use_1x1conv=True, block_size=1, filters=16, kernel_size=5, strides=1, dilation_rate=1),
+            blk(use_1x1conv=False, block_size=1, filters=24, kernel_size=5, strides=2, dilation_rate=1),
+            blk(use_1x1conv=False, block_size=2, filters=24, kernel_size=3, strides=1, dilation_rate=2, return_nmd=True)]
     cfg = {"model": {"name": "m", "use_masking": bool(int(masking)), "class_label_map": [{"class": c, "label": i} for i, c in enumerate("abc")],
                      "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 12},
                      "string_processor": {"codon": "CODON", "codon_id": "CODON_ID"},
@@ -269,19 +277,22 @@ def v2_model_case(case: int):
             layers.append(norm_w())
         elif layer.kind == "resblock":
             blocks = []
-            for _ in range(layer.cfg["block_size"]):
+            from jaeger_b200.modelspec import block_has_bypass
+            for bi in range(layer.cfg["block_size"]):
                 c1 = take("kernel", "bias"); b1 = norm_w(); c2 = take("kernel", "bias"); b2 = norm_w()
                 blocks.append({"conv1": c1, "bn1": b1, "conv2": c2, "bn2": b2})
+                if block_has_bypass(layer.cfg, bi):            # created (first called) after bn2: layers.py:1903-1909
+                    blocks[-1]["conv3"], blocks[-1]["bn3"] = take("kernel", "bias"), norm_w()
             layers.append({"blocks": blocks})
         else:
             layers.append({})
     assert pos[0] == len(names)
     weights = {"embedding": z["embedding_table"], "layers": layers,
-               "classifier": [{"kernel": np.zeros((16, 3)), "bias": np.zeros(3)}]}
+               "classifier": [{"kernel": np.zeros((z[tag + "_feat"].shape[1], 3)), "bias": np.zeros(3)}]}
     return spec, weights, z["tokens"], z[tag + "_feat"], z[tag + "_nmd"]
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_oracle_forward_vs_reference_builder_code(case):
     """tests/golden/v2_model.npz: the reference's `DynamicModelBuilder._build_block` (nnlib/builder.py:982-1193) run eagerly on the
     NumPy stand-in -- the reference's layer order, config hand-over, NMD collection / concatenation and pooling over the

@@ -418,7 +418,7 @@ def test_host_window_planner_fuzz_vs_reference_window_indices():
     check()
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_plan_compiler_vs_reference_builder_code(case):
     """The PRODUCT's plan compiler against the reference's own builder + layer code: tests/golden/v2_model.npz is
     `DynamicModelBuilder._build_block` run eagerly on a NumPy stand-in for TensorFlow (tests/golden/make_v2_model_goldens.py);
