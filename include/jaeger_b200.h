@@ -67,6 +67,19 @@ int64_t jg_ctx_launch_count(jg_ctx* ctx);
 int jg_fasta_scan(const char* path, int64_t* n_records, int64_t* n_bases, int64_t* name_bytes);
 int jg_fasta_load(const char* path, uint8_t* h_bases, int64_t* h_offsets, char* h_names);
 
+/* Chunked ingest for inputs that must not be held whole (BASELINE config 5, 100 Gbp; replaces the reference's record
+ * iteration seqops/io.py:97-104).  jg_fasta_open: byte_begin / byte_end (-1 = to the end) give the reader exactly the records
+ * whose '>' lies in [byte_begin, byte_end) of an UNCOMPRESSED file, so N ranks parse N disjoint byte slices (a gzip stream
+ * can only be read from offset 0).  jg_fasta_next: the next run of whole records holding at most max_bases bases and
+ * max_records records (at least one record); outputs as for jg_fasta_load.  *n_records == 0 marks the end.  Returns 3 with
+ * *need_bases set when the next record alone does not fit cap_bases (it is kept for the next call). */
+typedef struct jg_fasta_reader jg_fasta_reader;
+int jg_fasta_open(const char* path, int64_t byte_begin, int64_t byte_end, jg_fasta_reader** out);
+int jg_fasta_next(jg_fasta_reader* reader, int64_t max_bases, int64_t cap_bases, int64_t max_records,
+                  int64_t cap_name_bytes, uint8_t* h_bases, int64_t* h_offsets, char* h_names,
+                  int64_t* n_records, int64_t* n_bases, int64_t* name_bytes, int64_t* need_bases);
+int jg_fasta_close(jg_fasta_reader* reader);
+
 /* ---- stage 1: pack ---------------------------------------------------------------------
  * d_ascii: n bases (contigs concatenated, no separators).  d_codes: ceil(n/16) uint32, base i
  * in bits [2(i%16), 2(i%16)+2) with A=0 C=1 T=2 G=3 (complement = code ^ 2).  d_valid:

@@ -40,6 +40,10 @@ _SIGNATURES = {
     "jg_ctx_launch_count": (c_int64, [c_void_p]),
     "jg_fasta_scan": (c_int32, [ctypes.c_char_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "jg_fasta_load": (c_int32, [ctypes.c_char_p, _P, POINTER(c_int64), ctypes.c_char_p]),
+    "jg_fasta_open": (c_int32, [ctypes.c_char_p, c_int64, c_int64, POINTER(c_void_p)]),
+    "jg_fasta_next": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_int64), ctypes.c_char_p,
+                                POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "jg_fasta_close": (c_int32, [c_void_p]),
     "jg_pack_bases": (c_int32, [c_void_p, _P, c_int64, _P, _P]),
     "jg_dust_mask": (c_int32, [c_void_p, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "jg_plan_windows": (c_int32, [POINTER(c_int64), c_int64, c_int32, c_int32, c_int32, c_double, c_int32, c_int64,

@@ -369,6 +369,158 @@ int jg_fasta_load(const char* path, uint8_t* h_bases, int64_t* h_offsets, char* 
   return fasta_walk(path, &sc, h_bases, h_offsets, h_names);
 }
 
+// ---- stage 0b: chunked FASTA ingest (host) --------------------------------------------------------------
+// A resumable reader: every call hands back the next run of WHOLE records holding at most max_bases bases (one record when
+// a single record is longer), so a file of any size streams through two fixed pinned buffers while the previous chunk is
+// on the device.  A byte range [begin, end) makes the reader own exactly the records whose '>' lies inside it: N ranks
+// parse N disjoint slices of one plain file, nothing is read twice.
+struct jg_fasta_reader {
+  gzFile fh = nullptr;
+  std::vector<char> buf;
+  int64_t buf_pos = 0, buf_len = 0;      // unread part of buf
+  int64_t file_pos = 0;                  // uncompressed offset of buf[buf_pos]
+  int64_t byte_end = -1;                 // records starting at or after this offset belong to the next reader (-1: none)
+  bool at_line_start = true, eof = false, done = false;
+  // the record under construction when a call ran out of room (its header is parsed, some of its bases may be buffered)
+  bool have_pending = false;
+  std::string pend_name;
+  std::vector<uint8_t> pend_bases;
+  bool in_header = false, header_name_done = false;
+
+  bool fill() {
+    if (eof) return false;
+    const int got = gzread(fh, buf.data(), static_cast<unsigned>(buf.size()));
+    if (got <= 0) { eof = true; return false; }
+    buf_pos = 0; buf_len = got;
+    return true;
+  }
+};
+
+int jg_fasta_open(const char* path, int64_t byte_begin, int64_t byte_end, jg_fasta_reader** out) {
+  jg_fasta_reader* r = new jg_fasta_reader();
+  r->fh = gzopen(path, "rb");
+  if (!r->fh) { delete r; return fail(std::string("cannot open ") + path); }
+  gzbuffer(r->fh, 1 << 20);
+  r->buf.resize(1 << 22);
+  r->byte_end = byte_end;
+  if (byte_begin > 0) {
+    if (!gzdirect(r->fh)) { gzclose(r->fh); delete r; return fail("byte ranges need an uncompressed FASTA file"); }
+    // start one byte early: a '>' at byte_begin only opens a record when the byte before it ends a line
+    if (gzseek(r->fh, byte_begin - 1, SEEK_SET) < 0) { gzclose(r->fh); delete r; return fail("seek failed"); }
+    r->file_pos = byte_begin - 1;
+    r->at_line_start = false;
+    // skip to the first record start inside the range
+    bool found = false;
+    while (!found) {
+      if (r->buf_pos >= r->buf_len && !r->fill()) break;
+      while (r->buf_pos < r->buf_len) {
+        const char c = r->buf[r->buf_pos];
+        if (r->at_line_start && c == '>' && r->file_pos >= byte_begin) { found = true; break; }
+        r->at_line_start = c == '\n';
+        ++r->buf_pos; ++r->file_pos;
+      }
+    }
+    if (!found) r->done = true;
+  }
+  *out = r;
+  return 0;
+}
+
+int jg_fasta_close(jg_fasta_reader* r) {
+  if (!r) return 0;
+  if (r->fh) gzclose(r->fh);
+  delete r;
+  return 0;
+}
+
+// Next chunk: up to max_records whole records with at most max_bases bases in total (always at least one record if any is
+// left and it fits cap_bases).  h_offsets gets n + 1 entries, h_names the NUL-terminated names back to back.
+// Returns 0 and *n_records = 0 at the end of the reader's range; 3 when the next record alone exceeds cap_bases (the caller
+// grows its buffer to *need_bases and calls again: the record is kept).
+int jg_fasta_next(jg_fasta_reader* r, int64_t max_bases, int64_t cap_bases, int64_t max_records, int64_t cap_name_bytes,
+                  uint8_t* h_bases, int64_t* h_offsets, char* h_names, int64_t* n_records, int64_t* n_bases,
+                  int64_t* name_bytes, int64_t* need_bases) {
+  int64_t nrec = 0, nb = 0, nn = 0;
+  *n_records = *n_bases = *name_bytes = 0;
+  if (need_bases) *need_bases = 0;
+  h_offsets[0] = 0;
+  auto emit_pending = [&]() -> int {        // move the finished pending record into the caller's buffers
+    const int64_t len = static_cast<int64_t>(r->pend_bases.size());
+    if (len > cap_bases) { if (need_bases) *need_bases = len; return 3; }
+    if (nrec > 0 && (nb + len > max_bases || nb + len > cap_bases || nrec >= max_records ||
+                     nn + static_cast<int64_t>(r->pend_name.size()) + 1 > cap_name_bytes)) return 1;      // chunk is full: keep it for the next call
+    if (nn + static_cast<int64_t>(r->pend_name.size()) + 1 > cap_name_bytes) return fail("record name longer than the name buffer");
+    std::memcpy(h_bases + nb, r->pend_bases.data(), static_cast<size_t>(len));
+    nb += len;
+    std::memcpy(h_names + nn, r->pend_name.c_str(), r->pend_name.size() + 1);
+    nn += static_cast<int64_t>(r->pend_name.size()) + 1;
+    ++nrec;
+    h_offsets[nrec] = nb;
+    r->have_pending = false;
+    r->pend_name.clear();
+    r->pend_bases.clear();
+    return 0;
+  };
+  bool record_complete = false;      // the pending record has seen its last line
+  for (;;) {
+    if (r->done && !r->have_pending) break;
+    if (r->done || record_complete) {
+      const int rc = emit_pending();
+      record_complete = false;
+      if (rc == 1) break;
+      if (rc != 0) { *n_records = nrec; *n_bases = nb; *name_bytes = nn; return rc; }
+      if (r->done) break;
+      continue;
+    }
+    if (r->buf_pos >= r->buf_len && !r->fill()) { r->done = true; if (r->in_header) r->in_header = false; continue; }
+    const char* base = r->buf.data();
+    const char* p = base + r->buf_pos;
+    const char* end = base + r->buf_len;
+    while (p < end) {
+      if (r->at_line_start && *p == '>') {
+        const int64_t here = r->file_pos + (p - (base + r->buf_pos));
+        if (r->have_pending) { record_complete = true; break; }          // the previous record is finished: emit it first
+        if (r->byte_end >= 0 && here >= r->byte_end) { r->done = true; break; }
+        r->have_pending = true;
+        r->in_header = true; r->header_name_done = false; r->at_line_start = false;
+        ++p;
+        continue;
+      }
+      const char* nl = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(end - p)));
+      const char* seg_end = nl ? nl : end;
+      if (r->in_header) {
+        for (const char* q = p; q < seg_end && !r->header_name_done; ++q) {
+          if (*q == ' ' || *q == '\t' || *q == '\r') r->header_name_done = true;
+          else r->pend_name.push_back(*q);
+        }
+      } else if (r->have_pending && seg_end > p) {
+        const char* last = seg_end;
+        if (nl && last[-1] == '\r') --last;
+        const size_t len = static_cast<size_t>(last - p);
+        if (!std::memchr(p, ' ', len) && !std::memchr(p, '\t', len) && !std::memchr(p, '\r', len)) {
+          r->pend_bases.insert(r->pend_bases.end(), reinterpret_cast<const uint8_t*>(p), reinterpret_cast<const uint8_t*>(last));
+        } else {
+          for (const char* q = p; q < last; ++q)
+            if (*q != ' ' && *q != '\t' && *q != '\r') r->pend_bases.push_back(static_cast<uint8_t>(*q));
+        }
+      }
+      if (seg_end > p) r->at_line_start = false;
+      if (nl) {
+        if (r->in_header) r->in_header = false;
+        r->at_line_start = true;
+        p = nl + 1;
+      } else {
+        p = end;
+      }
+    }
+    const int64_t consumed = p - (base + r->buf_pos);
+    r->buf_pos += consumed;
+    r->file_pos += consumed;
+  }
+  *n_records = nrec; *n_bases = nb; *name_bytes = nn;
+  return 0;
+}
+
 // ---- stage 1 -----------------------------------------------------------------------------------
 int jg_pack_bases(jg_ctx* ctx, const uint8_t* d_ascii, int64_t n, uint32_t* d_codes, uint32_t* d_valid) {
   if (n <= 0) return 0;

@@ -87,7 +87,17 @@ def shard_loaded(loaded, mine: np.ndarray):
     return [names[c] for c in mine], buf[:int(sub_off[-1])], sub_off
 
 
-def merge_rank_frames(frames):
+def normalise_joined_columns(df):
+    """Per-rank / per-chunk summary frames are concatenated.  The left-joined terminal-repeat columns (collect.py:527-532)
+    must come out as ONE whole-file join gives them: `repeat_length` float64 with NaN where no repeat was found (the TSV then
+    shows "15.000", as the reference's does) -- also when a part had a repeat on every contig (an int column) or on none."""
+    if "repeat_length" in df.columns:
+        import pandas as pd
+        df["repeat_length"] = pd.to_numeric(df["repeat_length"], errors="coerce").astype("float64")
+    return df
+
+
+def merge_rank_frames(frames, keep_order_columns: bool = False):
     """Per-rank summary tables (each with helper columns `_pass`, `_gid` = pass of the contig's windows
     and its index in the FASTA) -> one table in the single-process row order: long-pass contigs in
     FASTA order, then short-pass contigs in FASTA order."""
@@ -95,6 +105,6 @@ def merge_rank_frames(frames):
     frames = [f for f in frames if f is not None and len(f)]
     if not frames:
         return pd.DataFrame()
-    df = pd.concat(frames, ignore_index=True)
+    df = normalise_joined_columns(pd.concat(frames, ignore_index=True))
     df = df.sort_values(["_pass", "_gid"], kind="stable").reset_index(drop=True)
-    return df.drop(columns=["_pass", "_gid"])
+    return df if keep_order_columns else df.drop(columns=["_pass", "_gid"])

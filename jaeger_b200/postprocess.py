@@ -291,7 +291,7 @@ def write_output_legacy(data: dict[str, Any], labels: list[str], output_table_pa
     return len(df)
 
 
-def write_fasta_from_results(loaded, output_tsv, output_fasta, width: int = 70) -> int:
+def write_fasta_from_results(loaded, output_tsv, output_fasta, width: int = 70, append: bool = False) -> int:
     """write_fasta_from_results (collect.py:611-639) from the records already in memory (`loaded` =
     WindowSource.load(): names, bases, offsets) instead of a further pass over the input file:
     the records whose name is in the phage table, 70 letters per line.  Returns the record count."""
@@ -303,7 +303,7 @@ def write_fasta_from_results(loaded, output_tsv, output_fasta, width: int = 70) 
     names, host, offsets = loaded
     data = host.numpy()
     n = 0
-    with open(str(output_fasta), "wb") as fh:
+    with open(str(output_fasta), "ab" if append else "wb") as fh:
         for i, name in enumerate(names):
             if name not in phages:
                 continue

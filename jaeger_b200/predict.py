@@ -105,30 +105,13 @@ def run_core_legacy(**kwargs: Any) -> dict[str, Any]:
             "windows": int(y_pred["prediction"].shape[0]), "predict_seconds": t1 - t0, "data": data}
 
 
-def run_core(**kwargs: Any) -> dict[str, Any]:
-    if (kwargs.get("model") or "default") == "default" and not kwargs.get("model_path"):     # --model_path picks the model itself (predict.py:503-542)
-        return run_core_legacy(**kwargs)
-    from . import B200Engine, WindowSource, parse_project, standin_1p4m_config
-    from .parallel import dist_env, merge_rank_frames, shard_contigs, shard_loaded
-    from .postprocess import contig_table, generate_summary, write_tables
-    from .prophage import call_regions
-
-    t0 = time.time()
-    input_path = Path(kwargs["input"])
+def _make_engine(kwargs: dict[str, Any]):
+    """Model lookup (commands/predict.py:494-551) -> (engine, model_id, model_name, registry entry or None)."""
+    from . import B200Engine, parse_project, standin_1p4m_config
     model_name = kwargs.get("model") or "default"                           # cli.py: the reference's default model
     if model_name == "standin" and not kwargs.get("model_path") and not kwargs.get("allow_random_weights"):
         raise ValueError("-m standin is a RANDOM-INITIALISED network (the benchmark architecture): its tables are meaningless. "
                          "Pass --allow-random-weights to run it anyway.")
-    fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
-    # one process per GPU under torchrun: contigs are sharded over the ranks, rank 0 writes
-    world, rank, local_rank = dist_env()
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        kwargs["physicalid"] = local_rank
     if kwargs.get("cpu"):
         raise RuntimeError("--cpu: this engine has no CPU path (use the reference's own engine for CPU runs)")
     precision = kwargs.get("precision") or "fp16"                          # predict.py:604-613
@@ -141,6 +124,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     # --mem (GB, predict.py:544, 615-623) caps the device workspace the window chunks are sized from
     workspace_gb = float(kwargs["mem"]) if kwargs.get("mem") else 16.0
     device = int(kwargs.get("physicalid") or 0)
+    info = None
     if model_name == "standin" and not kwargs.get("model_path"):
         logger.warning("RANDOM-INITIALISED stand-in network (--allow-random-weights): the classifications below carry no meaning")
         engine = B200Engine(spec=parse_project(standin_1p4m_config()), device=device, workspace_gb=workspace_gb)
@@ -166,56 +150,49 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         engine = B200Engine(info[model_name], device=device, workspace_gb=workspace_gb)
         model_id = get_model_id(model_name)
     spc = getattr(engine, "string_processor_config", None) or {}        # predict.py:752-766
+    fsize = int(kwargs.get("fsize", 2000))
     if spc.get("crop_size_nt") is not None:
         logger.info(f"model trained fragment length: {spc.get('crop_size_codons')} codons ({spc['crop_size_nt']} nt)")
     from .modelspec import crop_length_warning
     crop_msg = crop_length_warning(spc.get("crop_size_codons"), spc.get("crop_size_nt"), fsize)
     if crop_msg is not None:
         logger.warning(crop_msg)
-    out_dir = Path(kwargs["output"]) / model_id                          # predict.py:551
-    out_dir.mkdir(parents=True, exist_ok=True)
-    base = input_path.stem
-    table, phage_table = out_dir / f"{base}.tsv", out_dir / f"{base}_phages.tsv"      # predict.py:571-572
-    if table.exists() and not kwargs.get("overwrite"):
-        raise FileExistsError(f"{table} exists; use --overwrite")                     # predict.py:574-578
-    min_len = kwargs.get("min_len")
-    src = WindowSource(fasta=input_path, fsize=fsize, stride=stride, min_len=min_len,
-                       dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
-                       dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
-                       batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)),    # cli.py: --dustmask default on
-                       outputs=("prediction", "reliability") + (("embedding",) if kwargs.get("save_embedding") else ())
-                       + (("nmd",) if kwargs.get("save_nmd") else ()),          # the tables need neither embeddings nor NMD vectors
-                       lazy_meta=True)
-    t_load = time.time()
-    rec_off = src.load()[2]
-    n_records = len(rec_off) - 1
-    logger.info(f"read {n_records} records, {int(rec_off[-1])} bases in {time.time() - t_load:.2f} s")
-    if not (np.diff(rec_off) >= (min_len or fsize)).any():
-        raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
-    mine = np.arange(n_records)
-    if world > 1:
-        # balance on long-pass window counts; a short contig of the two-pass mode is one window
-        lens = np.diff(rec_off)
-        eff = np.where((lens < fsize) & (lens >= (min_len or fsize)), fsize, lens)
-        mine = shard_contigs(eff, world, fsize, stride)[rank]
-        src._loaded = shard_loaded(src.load(), mine)
-    t_pred = time.time()
+    return engine, model_id, model_name, info
+
+
+def _window_source(kwargs: dict[str, Any], fsize: int, stride: int, **where):
+    from . import WindowSource
+    make = WindowSource.from_host if "names" in where else WindowSource
+    return make(**where, fsize=fsize, stride=stride, min_len=kwargs.get("min_len"),
+                dynamic_stride=bool(kwargs.get("dynamic_stride", False)),
+                dynamic_stride_threshold=float(kwargs.get("dynamic_stride_threshold", 10.0)),
+                batch=int(kwargs.get("batch", 96)), dustmask=bool(kwargs.get("dustmask", True)),    # cli.py: --dustmask default on
+                outputs=("prediction", "reliability") + (("embedding",) if kwargs.get("save_embedding") else ())
+                + (("nmd",) if kwargs.get("save_nmd") else ()),          # the tables need neither embeddings nor NMD vectors
+                lazy_meta=True)
+
+
+def _classify_source(engine, src, kwargs: dict[str, Any], fsize: int, stride: int, model_name: str, info) -> dict[str, Any]:
+    """One set of records through stages 1-4 (+ terminal repeats, --refine, -p): the per-contig summary frame and what hangs
+    off it.  Shared by the whole-file run and by every chunk of a streamed run."""
+    from .postprocess import contig_table, generate_summary
+    from .prophage import call_regions
+    t0 = time.time()
     y_pred = engine.predict(src)
     t1 = time.time()
-    logger.info(f"classified {int(y_pred['prediction'].shape[0]) if y_pred else 0} windows in {t1 - t_pred:.2f} s")
+    n_windows = int(y_pred["prediction"].shape[0]) if y_pred else 0
+    logger.info(f"classified {n_windows} windows in {t1 - t0:.2f} s")
     crf_cost, crf_matrix = None, kwargs.get("crf_transition_matrix")          # predict.py:288-307
     if kwargs.get("crf"):
-        logger.warning("CRF window decoding is experimental; results may change between releases")
         crf_cost = float(kwargs.get("crf_switch_cost", 2.0))
         if isinstance(crf_matrix, (str, Path)):
             crf_matrix = json.loads(Path(crf_matrix).read_text())
     term = None
-    if kwargs.get("terminal_repeats", True):                                  # predict.py:679-685 (always on in the reference)
+    if kwargs.get("terminal_repeats", True) and y_pred:                       # predict.py:679-685 (always on in the reference)
         from .termini import scan_source
         t_term = time.time()
         term = scan_source(engine, src, fsize)
         logger.info(f"terminal-repeat scan in {time.time() - t_term:.2f} s")
-    t_post = time.time()
     data = contig_table(engine, y_pred, fsize, term_repeats=term, crf_switch_cost=crf_cost,
                         crf_prior=kwargs.get("crf_prior", "biological"), crf_transition_matrix=crf_matrix) if y_pred else None
     cm = engine.class_map
@@ -223,7 +200,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if kwargs.get("refine") and data:                                          # predict.py:310-335
         from .refine import load_refinement, refined_contig_table
         refine_path = Path(kwargs["refine_file"]) if kwargs.get("refine_file") else (
-            Path(info[model_name]["graph"]).parent / f"{model_name}_refine.yaml" if model_name != "standin" else None)
+            Path(info[model_name]["graph"]).parent / f"{model_name}_refine.yaml" if (info and model_name in info) else None)
         if refine_path is not None and refine_path.exists():
             try:
                 refine_cfg = load_refinement(refine_path, expect_model=model_name)
@@ -242,7 +219,88 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if kwargs.get("prophage") and data:
         regions = call_regions(engine, data, cm, fsize, stride, lc=int(kwargs.get("lc", 500_000)),
                                sensitivity=float(kwargs.get("sensitivity", 1.5)))
-    n_windows = int(y_pred["prediction"].shape[0]) if y_pred else 0
+    return {"y_pred": y_pred, "data": data, "df": df, "regions": regions, "windows": n_windows, "predict_seconds": t1 - t0}
+
+
+def _write_prophage_outputs(engine, loaded, regions, out_dir: Path, base: str, fsize: int, stride: int, result: dict, append: bool = False):
+    """<base>_prophage_regions.tsv and the att-site report <base>_prophages/prophages_jaeger.tsv (predict.py:372-376, 430-437;
+    postprocess/prophages.py:706-873 without the gene-call refinement)."""
+    rows = [] if append else ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
+    for name, r in regions.items():
+        for (ws, we), (s, e), sc in zip(r["ranges"], r["coords"], r["scores"]):
+            rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
+    with open(out_dir / f"{base}_prophage_regions.tsv", "a" if append else "w") as fh:
+        fh.write("\n".join(rows) + ("\n" if rows else ""))
+    result.setdefault("prophage_regions", {}).update(regions)
+    from .termini import prophage_report_loaded, write_prophage_report
+    t_att = time.time()
+    try:                                              # the reference logs and carries on (predict.py:440-442)
+        report = prophage_report_loaded(engine, loaded, regions, fsize, stride)
+        if append and result.get("prophage_report") is not None:
+            import pandas as pd
+            report = pd.concat([result["prophage_report"], report], ignore_index=True)
+        write_prophage_report(report, out_dir / f"{base}_prophages")
+        result["prophage_report"] = report
+        logger.info(f"prophage att-site report ({len(report)} regions) in {time.time() - t_att:.2f} s")
+    except (ArithmeticError, ValueError, KeyError, IndexError) as e:
+        result.setdefault("prophage_report", None)
+        logger.error(f"an error {e!r} occurred during the prophage report step")
+
+
+def run_core(**kwargs: Any) -> dict[str, Any]:
+    if (kwargs.get("model") or "default") == "default" and not kwargs.get("model_path"):     # --model_path picks the model itself (predict.py:503-542)
+        return run_core_legacy(**kwargs)
+    from . import WindowSource
+    from .parallel import dist_env, merge_rank_frames, shard_contigs, shard_loaded
+    from .postprocess import write_tables
+
+    t0 = time.time()
+    input_path = Path(kwargs["input"])
+    fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
+    # one process per GPU under torchrun: contigs are sharded over the ranks (SURVEY.md 8e), rank 0 writes
+    world, rank, local_rank = dist_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        kwargs["physicalid"] = local_rank
+    # inputs that should not be held whole are streamed in chunks of whole records (ingest.py)
+    stream_mbp = kwargs.get("stream_mbp")
+    if stream_mbp is None and input_path.exists() and input_path.stat().st_size > int(kwargs.get("stream_above_gb", 2.0) * 1e9):
+        stream_mbp = 512.0
+    if stream_mbp:
+        return _run_core_streaming(kwargs, float(stream_mbp), world, rank, t0)
+    engine, model_id, model_name, info = _make_engine(kwargs)
+    out_dir = Path(kwargs["output"]) / model_id                          # predict.py:551
+    out_dir.mkdir(parents=True, exist_ok=True)
+    base = input_path.stem
+    table, phage_table = out_dir / f"{base}.tsv", out_dir / f"{base}_phages.tsv"      # predict.py:571-572
+    if table.exists() and not kwargs.get("overwrite"):
+        raise FileExistsError(f"{table} exists; use --overwrite")                     # predict.py:574-578
+    min_len = kwargs.get("min_len")
+    src = _window_source(kwargs, fsize, stride, fasta=input_path)
+    t_load = time.time()
+    rec_off = src.load()[2]
+    n_records = len(rec_off) - 1
+    logger.info(f"read {n_records} records, {int(rec_off[-1])} bases in {time.time() - t_load:.2f} s")
+    if not (np.diff(rec_off) >= (min_len or fsize)).any():
+        raise ValueError(f"all records in {input_path} are < {min_len or fsize}bp")   # utils/fs.py:99-115
+    mine = np.arange(n_records)
+    if world > 1:
+        # balance on long-pass window counts; a short contig of the two-pass mode is one window
+        lens = np.diff(rec_off)
+        eff = np.where((lens < fsize) & (lens >= (min_len or fsize)), fsize, lens)
+        mine = shard_contigs(eff, world, fsize, stride)[rank]
+        src._loaded = shard_loaded(src.load(), mine)
+    if kwargs.get("crf"):
+        logger.warning("CRF window decoding is experimental; results may change between releases")
+    t_post = time.time()
+    res = _classify_source(engine, src, kwargs, fsize, stride, model_name, info)
+    y_pred, data, df, regions, n_windows = res["y_pred"], res["data"], res["df"], res["regions"], res["windows"]
+    t1 = t_post + res["predict_seconds"]
+    cm = engine.class_map
     if world > 1:
         if df is not None:       # row -> (pass, index of the contig in the FASTA), the single-process row order
             first = data["offsets"][:-1]
@@ -255,7 +313,8 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
             off = data["offsets"]
             np.savez(out_dir / f"{base}_window_scores.rank{rank}.npz", headers=data["headers"], lengths=data["length"],
                      predictions=np.array([data["predictions"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
-                     allow_pickle=True)
+                     gc_skews=np.array([data["gc_skews"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
+                     gcs=np.array([data["gcs"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object), allow_pickle=True)
             kwargs["window_scores"] = False
         if rank != 0:
             return {"table": table, "phage_table": phage_table, "rank": rank, "windows": n_windows, "predict_seconds": t1 - t0}
@@ -267,28 +326,11 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                              reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
     result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
               "windows": n_windows, "predict_seconds": t1 - t0}
-    logger.info(f"aggregation + tables in {time.time() - t_post:.2f} s")
+    logger.info(f"aggregation + tables in {time.time() - t_post - res['predict_seconds']:.2f} s")
     logger.info(f"processed {n_written}/{n_records} sequences")
     if kwargs.get("prophage"):
-        rows = ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
-        for name, r in regions.items():
-            for (ws, we), (s, e), sc in zip(r["ranges"], r["coords"], r["scores"]):
-                rows.append(f"{name}\t{s}\t{e}\t{ws}\t{we}\t{sc:.3f}")
-        (out_dir / f"{base}_prophage_regions.tsv").write_text("\n".join(rows) + "\n")
-        result["prophage_regions"] = regions
-        # att sites at the region ends -> <base>_prophages/prophages_jaeger.tsv (predict.py:372-376, 430-437;
-        # postprocess/prophages.py:706-873 without the gene-call refinement)
-        from .termini import prophage_report_loaded, write_prophage_report
-        t_att = time.time()
-        result["prophage_report"] = None
-        try:                                              # the reference logs and carries on (predict.py:440-442)
-            full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
-            report = prophage_report_loaded(engine, full, regions, fsize, stride)
-            write_prophage_report(report, out_dir / f"{base}_prophages")
-            result["prophage_report"] = report
-            logger.info(f"prophage att-site report ({len(report)} regions) in {time.time() - t_att:.2f} s")
-        except (ArithmeticError, ValueError, KeyError, IndexError) as e:
-            logger.error(f"an error {e!r} occurred during the prophage report step")
+        full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
+        _write_prophage_outputs(engine, full, regions or {}, out_dir, base, fsize, stride, result)
     if kwargs.get("getsequences"):                                        # predict.py:444-455
         from .postprocess import write_fasta_from_results
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
@@ -308,6 +350,94 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
                  predictions=np.array([data["predictions"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
                  gc_skews=np.array([data["gc_skews"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object),
                  gcs=np.array([data["gcs"][off[i]:off[i + 1]] for i in range(len(off) - 1)], dtype=object), allow_pickle=True)
+    return result
+
+
+def _run_core_streaming(kwargs: dict[str, Any], stream_mbp: float, world: int, rank: int, t0: float) -> dict[str, Any]:
+    """`jaeger predict` over an input that is never held whole (BASELINE config 5): chunks of whole records stream through two
+    pinned host buffers (ingest.FastaChunks: the next chunk is parsed while the current one is on the device), every chunk goes
+    through stages 1-4 and leaves only its per-contig rows behind, so host and device memory are bounded by the chunk size,
+    not by the file.  Under torchrun every rank streams its own byte slice of a plain-text file (a gzip stream is read by every
+    rank, which keeps every world-th chunk); rank 0 gathers the per-contig tables and writes them in the single-process row
+    order (long-pass contigs in file order, then short-pass contigs)."""
+    import pandas as pd
+    from .ingest import FastaChunks, is_gzip, rank_byte_range
+    from .parallel import merge_rank_frames, normalise_joined_columns
+    from .postprocess import write_tables
+    for opt in ("window_scores", "save_embedding", "save_nmd"):
+        if kwargs.get(opt):
+            raise NotImplementedError(f"--{opt.replace('_', '-')} keeps per-window arrays of the whole run in memory and is not available "
+                                      "when the input is streamed (pass --stream-mbp 0 to load the file whole)")
+    input_path = Path(kwargs["input"])
+    fsize, stride = int(kwargs.get("fsize", 2000)), int(kwargs.get("stride", 1500))
+    min_len = kwargs.get("min_len") or fsize
+    engine, model_id, model_name, info = _make_engine(kwargs)
+    out_dir = Path(kwargs["output"]) / model_id
+    out_dir.mkdir(parents=True, exist_ok=True)
+    base = input_path.stem
+    table, phage_table = out_dir / f"{base}.tsv", out_dir / f"{base}_phages.tsv"
+    if table.exists() and not kwargs.get("overwrite"):
+        raise FileExistsError(f"{table} exists; use --overwrite")
+    gz = is_gzip(input_path)
+    byte_range = (0, -1) if (world == 1 or gz) else rank_byte_range(input_path, rank, world)
+    chunks = FastaChunks(input_path, chunk_bases=int(stream_mbp * 1e6), byte_range=byte_range)
+    frames, n_windows, n_records, n_eligible, predict_s, gid0, n_chunks = [], 0, 0, 0, 0.0, 0, 0
+    rank_term = 0 if (gz or world == 1) else (rank << 40)          # byte slices are in file order: rank-major row order
+    result: dict[str, Any] = {"table": table, "phage_table": phage_table}
+    cm = engine.class_map
+    has_rel = True
+    first_prophage = True
+    for k, (names, bases, offsets) in enumerate(chunks):
+        lens = np.diff(offsets)
+        n_here = len(names)
+        mine_chunk = world == 1 or not gz or (k % world == rank)
+        if mine_chunk:
+            n_records += n_here
+            n_eligible += int((lens >= min_len).sum())
+        if mine_chunk and (lens >= min_len).any():
+            src = _window_source(kwargs, fsize, stride, names=names, bases=bases, offsets=offsets)
+            res = _classify_source(engine, src, kwargs, fsize, stride, model_name, info)
+            predict_s += res["predict_seconds"]
+            n_windows += res["windows"]
+            if res["df"] is not None:
+                data, df = res["data"], res["df"]
+                first = data["offsets"][:-1]
+                df["_pass"] = (engine.windows.seqlen[first] < fsize).astype(np.int64)
+                df["_gid"] = rank_term + gid0 + engine.windows.contig[first].astype(np.int64)
+                frames.append(df)
+                has_rel = bool(data.get("has_reliability", True))
+            if kwargs.get("prophage") and res["regions"]:
+                _write_prophage_outputs(engine, src.load(), res["regions"], out_dir, base, fsize, stride, result, append=not first_prophage)
+                first_prophage = False
+            logger.info(f"chunk {k}: {n_here} records, {int(offsets[-1])} bases, {res['windows']} windows")
+        gid0 += n_here
+        n_chunks += 1
+    df = normalise_joined_columns(pd.concat(frames, ignore_index=True)) if frames else None
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object({"df": df, "windows": n_windows, "records": n_records, "eligible": n_eligible}, gathered, dst=0)
+        if rank != 0:
+            return {"table": table, "phage_table": phage_table, "rank": rank, "windows": n_windows, "predict_seconds": predict_s}
+        df = merge_rank_frames([g["df"] for g in gathered], keep_order_columns=True)
+        n_windows, n_records, n_eligible = (sum(g[key] for g in gathered) for key in ("windows", "records", "eligible"))
+    if n_eligible == 0:
+        raise ValueError(f"all records in {input_path} are < {min_len}bp")            # utils/fs.py:99-115
+    if df is not None and len(df):
+        df = df.sort_values(["_pass", "_gid"], kind="stable").reset_index(drop=True).drop(columns=["_pass", "_gid"])
+    n_written = write_tables(df, cm["class"], has_rel, table, phage_table, reliability_cutoff=float(kwargs.get("rc", 0.1)),
+                             phage_score=float(kwargs.get("pc", 3))) if df is not None else 0
+    result.update({"num_written": n_written, "num": n_records, "windows": n_windows, "predict_seconds": predict_s,
+                   "streamed_chunks": n_chunks, "wall_seconds": time.time() - t0})
+    logger.info(f"processed {n_written}/{n_records} sequences in {result['streamed_chunks']} chunks")
+    if kwargs.get("getsequences"):           # a second streaming pass over the input picks the records of the phage table
+        from .postprocess import write_fasta_from_results
+        n_seq = 0
+        out_fa = out_dir / f"{base}_phages_jaeger.fasta"
+        out_fa.write_bytes(b"")
+        for names, bases, offsets in FastaChunks(input_path, chunk_bases=int(stream_mbp * 1e6)):
+            n_seq += write_fasta_from_results((names, bases, offsets), phage_table, out_fa, append=True)
+        logger.info(f"{base}_phages_jaeger.fasta created ({n_seq} records)")
     return result
 
 
@@ -362,6 +492,8 @@ def main(argv=None) -> int:
     ap.add_argument("--window-scores", dest="window_scores", action="store_true")
     ap.add_argument("--getsequences", action="store_true", help="write the records of the phage table to <base>_phages_jaeger.fasta")
     ap.add_argument("--overwrite", action="store_true")
+    ap.add_argument("--stream-mbp", dest="stream_mbp", type=float, default=None,
+                    help="stream the input in chunks of this many Mbp of whole records (bounded memory); default: 512 for inputs above 2 GB, 0 = never")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose >= 2 else logging.INFO, format="%(asctime)s %(levelname)s [jaeger_b200] %(message)s")
     if args.plot_type != "none" and args.prophage:

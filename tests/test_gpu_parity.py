@@ -1188,3 +1188,25 @@ def test_strided_bypass_blocks_and_mlp_heads_vs_oracle(which, lc):
         assert d < 6e-3 * max(1.0, np.abs(ref[key]).max()), (which, key, d, names)
     assert "conv_ref_kernel" not in names, names             # every conv runs on a tensor-core kernel
     print(which, lc, names, "max |logit diff|", np.abs(got["prediction"] - ref["prediction"]).max())
+
+
+def test_streamed_run_equals_whole_file_run(standin, tmp_path):
+    """f3: `run_core` with the input streamed in chunks of whole records (two pinned buffers, the next chunk parsed while the
+    current one is on the device) writes byte-identical tables to the whole-file run -- long pass and padded short pass,
+    dust-masking, terminal repeats -- and a second streaming pass writes the same phage FASTA."""
+    from jaeger_b200.predict import run_core
+    from tests.helpers import random_contigs
+    recs = random_contigs(11, [2600, 900, 14000, 2000, 700, 31000, 5200, 1200, 8000, 2100, 600, 45000, 3000])
+    fa = tmp_path / "meta.fasta"
+    fa.write_text("".join(f">{n} len={len(s)}\n" + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n" for n, s in recs))
+    common = dict(input=str(fa), model="standin", allow_random_weights=True, fsize=2000, stride=1500, min_len=500, overwrite=True,
+                  getsequences=True, pc=-100.0, rc=-1.0)
+    a = run_core(output=str(tmp_path / "whole"), stream_mbp=0, **common)
+    b = run_core(output=str(tmp_path / "streamed"), stream_mbp=0.02, **common)
+    assert b["streamed_chunks"] >= 4 and a["windows"] == b["windows"] and a["num_written"] == b["num_written"]
+    assert a["table"].read_text() == b["table"].read_text()
+    assert a["phage_table"].exists() == b["phage_table"].exists()      # only written when a contig is called phage (collect.py:601-607)
+    if a["phage_table"].exists():
+        assert a["phage_table"].read_text() == b["phage_table"].read_text()
+    fa_a, fa_b = (tmp_path / d / "standin" / "meta_phages_jaeger.fasta" for d in ("whole", "streamed"))
+    assert fa_a.read_bytes() == fa_b.read_bytes()

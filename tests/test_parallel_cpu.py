@@ -104,3 +104,44 @@ def test_driver_sharding_helpers_round_trip():
     merged = merge_rank_frames(frames + [None])
     want = [f"c{c}" for c in range(len(lens)) if lens[c] >= 2000] + [f"c{c}" for c in range(len(lens)) if lens[c] < 2000]
     assert merged["contig_id"].tolist() == want and list(merged.columns) == ["contig_id"]
+
+
+def test_chunked_fasta_reader_equals_whole_file_loader_and_partitions_by_byte_range(tmp_path):
+    """jg_fasta_open / jg_fasta_next (ingest.FastaChunks): chunks of whole records -- any chunk size, records longer than a chunk,
+    empty records, CRLF and blank lines, gzip -- concatenate to exactly what the one-pass loader returns, and the byte ranges of
+    `rank_byte_range` give every record to exactly one rank, in file order (a record belongs to the slice holding its '>')."""
+    import gzip
+    from jaeger_b200.engine import load_fasta
+    from jaeger_b200.ingest import FastaChunks, rank_byte_range
+    rng = np.random.default_rng(0)
+    p = tmp_path / "x.fa"
+    with open(p, "w", newline="") as fh:
+        for i in range(400):
+            n = int(rng.integers(0, 4000)) if i % 50 else 60_000
+            s = "".join(rng.choice(list("ACGTNacgt"), n))
+            fh.write(f">rec{i} description {i}\n")
+            for k in range(0, n, 70):
+                fh.write(s[k:k + 70] + ("\r\n" if i % 7 == 0 else "\n"))
+            if i % 11 == 0:
+                fh.write("\n")
+    names, host, off = load_fasta(p)
+    whole = bytes(host.numpy())
+    for chunk in (1000, 25_000, 10 ** 9):
+        got_names, got, lens = [], b"", []
+        for nm, b, o in FastaChunks(p, chunk_bases=chunk, pin=False):
+            assert int(o[-1]) <= max(chunk, 60_000) and int(o[-1]) == b.numel()
+            got_names += nm; got += bytes(b.numpy()); lens += np.diff(o).tolist()
+        assert got_names == names and got == whole and lens == np.diff(off).tolist(), chunk
+    for world in (2, 3, 8):
+        seen = []
+        for r in range(world):
+            for nm, _, _ in FastaChunks(p, chunk_bases=50_000, byte_range=rank_byte_range(p, r, world), pin=False, prefetch=False):
+                seen += nm
+        assert seen == names, world
+    gz = tmp_path / "x.fa.gz"
+    gz.write_bytes(gzip.compress(p.read_bytes()))
+    assert [n for nm, _, _ in FastaChunks(gz, chunk_bases=30_000, pin=False) for n in nm] == names
+    import pytest
+    from jaeger_b200._cabi import JaegerB200Error
+    with pytest.raises(JaegerB200Error, match="uncompressed"):
+        FastaChunks(gz, byte_range=(100, -1), pin=False)

@@ -23,7 +23,7 @@ import yaml
 cal = tmp / "standin_refine.yaml"
 cal.write_text(yaml.safe_dump({"schema_version": 1, "jaeger_model": "standin", "taus": {
     c: {"logit": -0.5, "margin": 0.01, "n": 100} for c in ("phage", "virus", "archaea", "bacteria", "plasmid", "eukarya")}}))
-common = ["-i", str(fa), "--min-len", "500", "-p", "--lc", "500000", "-s", "0.2", "--overwrite", "--refine", "--refine-file", str(cal)]
+common = ["-m", "standin", "--allow-random-weights", "-i", str(fa), "--min-len", "500", "-p", "--lc", "500000", "-s", "0.2", "--overwrite", "--refine", "--refine-file", str(cal)]
 subprocess.run([sys.executable, "-m", "jaeger_b200.predict", *common, "-o", str(tmp / "one")], check=True)
 subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_gpus}", "--master-addr", "127.0.0.1",
                 "--master-port", "29541", "-m", "jaeger_b200.predict", *common, "-o", str(tmp / "many")], check=True)
