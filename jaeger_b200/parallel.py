@@ -97,6 +97,24 @@ def normalise_joined_columns(df):
     return df
 
 
+def exchange_errors(err: BaseException | None, world: int, rank: int) -> None:
+    """Called by every rank right before the result gather: a rank that failed in its own work (engine.predict,
+    contig_table ...) tells the others instead of leaving them blocked in the collective.  Re-raises the local error
+    on the rank that failed and a RuntimeError naming the failed ranks everywhere else."""
+    if world <= 1:
+        if err is not None:
+            raise err
+        return
+    import torch.distributed as dist
+    msgs: list = [None] * world
+    dist.all_gather_object(msgs, None if err is None else f"{type(err).__name__}: {err}")
+    if err is not None:
+        raise err
+    bad = [f"rank {r}: {m}" for r, m in enumerate(msgs) if m]
+    if bad:
+        raise RuntimeError("another rank failed before the gather -- " + "; ".join(bad))
+
+
 def merge_rank_frames(frames, keep_order_columns: bool = False):
     """Per-rank summary tables (each with helper columns `_pass`, `_gid` = pass of the contig's windows
     and its index in the FASTA) -> one table in the single-process row order: long-pass contigs in
@@ -104,7 +122,7 @@ def merge_rank_frames(frames, keep_order_columns: bool = False):
     import pandas as pd
     frames = [f for f in frames if f is not None and len(f)]
     if not frames:
-        return pd.DataFrame()
+        return None                      # no rank produced a row: the callers write no table, like the single-process run
     df = normalise_joined_columns(pd.concat(frames, ignore_index=True))
     df = df.sort_values(["_pass", "_gid"], kind="stable").reset_index(drop=True)
     return df if keep_order_columns else df.drop(columns=["_pass", "_gid"])

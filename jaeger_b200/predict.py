@@ -297,7 +297,12 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     if kwargs.get("crf"):
         logger.warning("CRF window decoding is experimental; results may change between releases")
     t_post = time.time()
-    res = _classify_source(engine, src, kwargs, fsize, stride, model_name, info)
+    from .parallel import exchange_errors
+    try:
+        res, failure = _classify_source(engine, src, kwargs, fsize, stride, model_name, info), None
+    except Exception as e:              # told to the other ranks before anybody enters the gather
+        res, failure = None, e
+    exchange_errors(failure, world, rank)
     y_pred, data, df, regions, n_windows = res["y_pred"], res["data"], res["df"], res["regions"], res["windows"]
     t1 = t_post + res["predict_seconds"]
     cm = engine.class_map
@@ -323,7 +328,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
         if kwargs.get("prophage"):
             regions = {k: v for g in gathered if g["regions"] for k, v in g["regions"].items()}
     n_written = write_tables(df, cm["class"], bool(data.get("has_reliability", True)) if data else True, table, phage_table,
-                             reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3)))
+                             reliability_cutoff=float(kwargs.get("rc", 0.1)), phage_score=float(kwargs.get("pc", 3))) if df is not None else 0
     result = {"table": table, "phage_table": phage_table, "num_written": n_written, "num": n_records,
               "windows": n_windows, "predict_seconds": t1 - t0}
     logger.info(f"aggregation + tables in {time.time() - t_post - res['predict_seconds']:.2f} s")
@@ -387,7 +392,10 @@ def _run_core_streaming(kwargs: dict[str, Any], stream_mbp: float, world: int, r
     cm = engine.class_map
     has_rel = True
     first_prophage = True
+    failure = None
     for k, (names, bases, offsets) in enumerate(chunks):
+        if failure is not None:
+            break
         lens = np.diff(offsets)
         n_here = len(names)
         mine_chunk = world == 1 or not gz or (k % world == rank)
@@ -396,7 +404,11 @@ def _run_core_streaming(kwargs: dict[str, Any], stream_mbp: float, world: int, r
             n_eligible += int((lens >= min_len).sum())
         if mine_chunk and (lens >= min_len).any():
             src = _window_source(kwargs, fsize, stride, names=names, bases=bases, offsets=offsets)
-            res = _classify_source(engine, src, kwargs, fsize, stride, model_name, info)
+            try:
+                res = _classify_source(engine, src, kwargs, fsize, stride, model_name, info)
+            except Exception as e:      # kept until every rank reaches the exchange below (no collective inside the loop)
+                failure = e
+                continue
             predict_s += res["predict_seconds"]
             n_windows += res["windows"]
             if res["df"] is not None:
@@ -412,6 +424,8 @@ def _run_core_streaming(kwargs: dict[str, Any], stream_mbp: float, world: int, r
             logger.info(f"chunk {k}: {n_here} records, {int(offsets[-1])} bases, {res['windows']} windows")
         gid0 += n_here
         n_chunks += 1
+    from .parallel import exchange_errors
+    exchange_errors(failure, world, rank)
     df = normalise_joined_columns(pd.concat(frames, ignore_index=True)) if frames else None
     if world > 1:
         import torch.distributed as dist

@@ -17,6 +17,8 @@ from typing import Any
 
 import numpy as np
 
+from .modelspec import block_has_bypass
+
 _DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 9: np.int64, 19: np.float16, 10: np.bool_}
 
 
@@ -56,6 +58,8 @@ def _parse_proto(buf: bytes) -> dict[int, list]:
 def _read_block(data: bytes, offset: int, size: int) -> list[tuple[bytes, bytes]]:
     """Entries of one uncompressed SSTable block (prefix-compressed keys + restart array)."""
     block = data[offset:offset + size]
+    if len(data) > offset + size and data[offset + size] != 0:
+        raise ValueError(f"variables.index: block at {offset} is compressed (type {data[offset + size]}); only uncompressed bundles are read")
     n_restarts = struct.unpack("<I", block[-4:])[0]
     end = len(block) - 4 - 4 * n_restarts
     pos, key, out = 0, b"", []
@@ -87,9 +91,14 @@ def read_tf_bundle(variables_dir: str | Path) -> dict[str, np.ndarray]:
         off, p = _varint(handle, p)
         size, p = _varint(handle, p)
         for key, val in _read_block(index, off, size):
-            if not key:
-                continue                      # bundle header
+            if not key:                       # BundleHeaderProto: field 1 = num_shards
+                shards = _parse_proto(val).get(1, [1])[0]
+                if shards != 1:
+                    raise ValueError(f"variables bundle has {shards} data shards; only single-shard bundles are read")
+                continue
             e = _parse_proto(val)
+            if e.get(3, [0])[0] != 0:
+                raise ValueError(f"variable {key.decode()} lives in data shard {e[3][0]}; only shard 0 is read")
             dtype = _DTYPES.get(e.get(1, [0])[0])
             if dtype is None:
                 continue
@@ -270,10 +279,16 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
                     parts[leaf] = groups[pos][2]
                     used[pos] = True
                     pos += 1
-                if set(parts) != {"conv1", "bn1", "conv2", "bn2"}:
-                    fail(f"{what} block {b}: found {sorted(parts)} (strided / 1x1-bypass blocks are not supported)")
-                blocks.append(dict(conv1=conv_w(parts["conv1"], ch, c, what), bn1=norm_w(parts["bn1"], c["filters"], what),
-                                   conv2=conv_w(parts["conv2"], c["filters"], c, what), bn2=norm_w(parts["bn2"], c["filters"], what)))
+                bypass = block_has_bypass(c, b)
+                want = {"conv1", "bn1", "conv2", "bn2"} | ({"conv3", "bn3"} if bypass else set())
+                if set(parts) != want:
+                    fail(f"{what} block {b}: found {sorted(parts)}, the project's block has {sorted(want)}")
+                blk = dict(conv1=conv_w(parts["conv1"], ch, c, what), bn1=norm_w(parts["bn1"], c["filters"], what),
+                           conv2=conv_w(parts["conv2"], c["filters"], c, what), bn2=norm_w(parts["bn2"], c["filters"], what))
+                if bypass:                      # layers.py:1855-1864: Conv1D(filters, 1, strides) + BatchNorm on the shortcut
+                    blk["conv3"] = conv_w(parts["conv3"], ch, dict(c, kernel_size=1), what)
+                    blk["bn3"] = norm_w(parts["bn3"], c["filters"], what)
+                blocks.append(blk)
                 ch = c["filters"]
             w["layers"].append(dict(blocks=blocks))
         else:
@@ -287,11 +302,17 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
         hits = [(i, g) for i, g in dense if g["kernel"].shape == shape and not used[i]]
         if not hits:
             fail(f"no Dense kernel of shape {shape} for {what}")
+        if len(hits) > 1:       # the object-graph path of a functional model (`_operations/<i>`) carries no layer name to decide by
+            fail(f"{len(hits)} unused Dense kernels of shape {shape} could be {what} ({', '.join(groups[i][0] for i, _ in hits)}): "
+                 "ambiguous, export the weights with save_npz_weights instead")
         i, g = hits[0]
         used[i] = True
         return dict(kernel=g["kernel"].astype(np.float32), bias=g["bias"].astype(np.float32) if "bias" in g else np.zeros(shape[1], np.float32))
 
-    w["classifier"] = [pick((ch, spec.n_classes), "the classifier")]
+    w["classifier"], width = [], ch
+    for di, d in enumerate(spec.classifier):
+        w["classifier"].append(pick((width, d["units"]), f"classifier Dense {di}"))
+        width = d["units"]
     if spec.reliability is not None:
         nmd_dim = 0
         chn = e if e > 0 else 64

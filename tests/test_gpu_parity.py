@@ -399,6 +399,19 @@ def test_smoothing_vs_reference_golden_and_segmentation_vs_oracle(standin):
         want = opro.optimal_partition(col, float(p + 1), 3)
         assert bk[p, :nb[p]].tolist() == want, p
         assert want[-1] == T and all(b - a >= 3 for a, b in zip([0] + want[:-1], want))
+    # exact ties (integer-valued and constant tracks): the kernel keeps the earliest last change point, like the oracle
+    rng = np.random.default_rng(3)
+    for track in (np.zeros(40), np.round(rng.normal(size=60) * 2.0), np.repeat([0.0, 3.0, 0.0, 3.0], 6)):
+        n = len(track)
+        with torch.cuda.stream(eng._stream()):
+            sig = eng._h2d(track.astype(np.float64))
+            bk = torch.zeros((9, n), dtype=torch.int32, device=eng.tdev)
+            nb = torch.zeros((9,), dtype=torch.int32, device=eng.tdev)
+            check(lib.jg_segment_scores(eng.ctx.handle, sig.data_ptr(), n, 3, 9, bk.data_ptr(), nb.data_ptr()))
+            bk, nb = bk.cpu().numpy(), nb.cpu().numpy()
+        eng.ctx.sync()
+        for p in range(9):
+            assert bk[p, :nb[p]].tolist() == opro.optimal_partition(track, float(p + 1), 3), (n, p)
 
 
 def test_predict_driver_tsv_equals_oracle_pipeline(standin, tmp_path):

@@ -145,3 +145,41 @@ def test_chunked_fasta_reader_equals_whole_file_loader_and_partitions_by_byte_ra
     from jaeger_b200._cabi import JaegerB200Error
     with pytest.raises(JaegerB200Error, match="uncompressed"):
         FastaChunks(gz, byte_range=(100, -1), pin=False)
+
+
+def _error_exchange_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from jaeger_b200.parallel import exchange_errors
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        exchange_errors(None, world, rank)                                   # nobody failed: returns on every rank
+        try:
+            exchange_errors(ValueError("bad shard") if rank == 1 else None, world, rank)
+            q.put((rank, "no error"))
+        except ValueError as e:
+            q.put((rank, f"own:{e}"))
+        except RuntimeError as e:
+            q.put((rank, f"peer:{e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_failure_is_exchanged_before_the_gather():
+    """A rank that fails in its own work must not leave the others blocked in the result gather (world size 2, gloo)."""
+    import torch.multiprocessing as mp
+    from jaeger_b200.parallel import merge_rank_frames
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 37
+    procs = [ctx.Process(target=_error_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[1] == "own:bad shard"
+    assert got[0].startswith("peer:") and "rank 1: ValueError: bad shard" in got[0]
+    assert merge_rank_frames([None, None]) is None                           # no rows anywhere: no table, no KeyError

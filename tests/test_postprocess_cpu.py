@@ -414,3 +414,50 @@ def test_refine_contig_aggregation_vs_reference_source():
                 else:
                     assert got[cid][k] == v, (mode, cid, k, got[cid][k], v)
     assert {"virus_any", "bacteria_or_plasmid"} <= {w["contig_call"] for w in gold["unweighted_half_1"].values()}
+
+
+def _all_partitions(n: int, min_size: int):
+    """Every list of segment ends (ascending, last = n) whose segments are all >= min_size long."""
+    def rec(start):
+        if n - start >= min_size:
+            yield [n]
+        for end in range(start + min_size, n - min_size + 1):
+            for rest in rec(end):
+                yield [end] + rest
+    return list(rec(0))
+
+
+def _objective(x, ends, pen):
+    tot, a = 0.0, 0
+    for b in ends:
+        seg = x[a:b]
+        tot += float(((seg - seg.mean()) ** 2).sum())
+        a = b
+    return tot + pen * (len(ends) - 1)
+
+
+def test_optimal_partition_is_the_exact_optimum_on_short_signals():
+    """ruptures' KernelCPD(kernel="linear", min_size=3).predict(pen=p) (prophages.py:540-556) minimises
+    sum of within-segment squared deviations + pen per change point; the library is not installable, so the
+    restatement is held against a brute force over every admissible partition of short signals.
+    Tie-break of the restatement (and of the device kernel, tests/test_gpu_parity.py): the dynamic programme
+    keeps, for every prefix, the EARLIEST last change point among equal objectives (first arg-min), i.e. the
+    longest last segment; exact ties have measure zero on real score tracks."""
+    rng = np.random.default_rng(11)
+    for case in range(120):
+        n = int(rng.integers(3, 15))
+        x = rng.normal(size=n) + (rng.random(n) < 0.3) * rng.normal(scale=4.0)
+        if case % 4 == 0:
+            x = np.round(x)                                  # integer signals: many exact ties
+        pen = float(rng.choice([0.0, 0.25, 1.0, 2.0, 9.0]))
+        parts = _all_partitions(n, 3)
+        objs = np.array([_objective(x, p, pen) for p in parts])
+        got = opro.optimal_partition(x, pen, 3)
+        assert got in parts
+        assert _objective(x, got, pen) <= objs.min() + 1e-9, (case, got, parts[int(objs.argmin())])
+        best = [p for p, o in zip(parts, objs) if o <= objs.min() + 1e-9]
+        if len(best) == 1:
+            assert got == best[0]
+    # the stated tie-break on an all-tie signal: no change point at pen 0 on a constant track
+    assert opro.optimal_partition(np.zeros(9), 0.0, 3) == [9]
+    assert opro.optimal_partition(np.zeros(9), 1.0, 3) == [9]
