@@ -444,6 +444,29 @@ def roofline(eng, wl: Workload, prof, ms: float, tot_windows: float, world: int)
     peaks = measured_peaks()
     lc = eng.codons_per_frame(wl.fsize, wl.fsize)
     conv_ms_total = sum(p[0] for p in prof)
+    if "stack_resident_kernel" in eng.conv_kernel_names():
+        # ONE launch runs the whole conv stack with every window resident in shared memory (csrc/conv_resident.cuh): its HBM traffic
+        # is the tokens in and 32 floats out, so the kernel is bounded by the SM (tensor pipe at N = 32 + epilogue issue), not HBM.
+        ms_k = sum(p[0] for p in prof)
+        n_launch = max(1.0, sum(p[1] for p in prof))
+        windows = prof[-1][2]
+        flop = 0.0
+        for c in plan.launches:
+            if c.kind != 1:
+                continue
+            k = c.kernel.shape[0]
+            l_out = ((lc - c.cum_shrink_in) >> c.halvings) - c.shrink
+            flop += 2.0 * 6 * l_out * k * c.real_cin * c.real_cout
+        tflops = flop * windows / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
+        byts = (6.0 * ((lc + 3) // 4 * 4) + 4.0 * plan.real_feat_dim) * windows
+        return {"bound": "tensor", "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["tflops"],
+                "kernel": eng.conv_kernel_names(), "traffic": None, "peak_source": peaks["source"],
+                "avg_launch_ms": ms_k / n_launch, "kernel_share_of_step": conv_ms_total / ms,
+                "algorithmic_flop_per_launch": flop * windows / n_launch, "algorithmic_bytes_per_launch": byts / n_launch,
+                "hbm_gbs_algorithmic": byts / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0, "hbm_peak_gbs": peaks["hbm_gbs"],
+                "windows_per_launch": windows / n_launch,
+                "note": "window-resident kernel: activations never leave the SM, so neither roofline binds; the SS-mode N = 32 MMAs are "
+                        "shared-memory-bandwidth limited and the epilogue warps are issue limited (DESIGN.md section 4)"}
     res_ms = res_launch = res_flop = res_bytes = res_windows = 0.0
     for li, (c, (pms, pl, pw)) in enumerate(zip(plan.launches, prof)):
         if li == 0 or c.kind != 1:

@@ -138,7 +138,9 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
  * activation 1 -> [NMD tap] -> [norm 2 -> activation 2] -> [masked global pool]; a norm is a
  * per-channel affine (MaskedBatchNorm folded, nnlib/v2/layers.py:918-941) or, with i[22] / i[23] set,
  * a MaskedDYT (layers.py:385-444): gamma * tanh(scale * x + shift) + beta with gamma / beta in
- * p[8..11]. */
+ * p[8..11].  i[26] / i[27]: the layer's channel counts before the plan padded them to multiples of 64 (0 = not given).  A model
+ * whose conv stack is at most 32 channels wide everywhere (BASELINE config 3) runs as ONE kernel that keeps each window in shared
+ * memory through all layers (csrc/conv_resident.cuh); JG_RESIDENT=0 in the environment keeps the per-layer kernels. */
 #define JG_LAYER_INT_FIELDS 32
 #define JG_LAYER_PTR_FIELDS 16
 typedef struct jg_layer_desc {

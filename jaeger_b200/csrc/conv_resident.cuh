@@ -1,0 +1,401 @@
+// Window-resident conv stack for NARROW models (every activation tensor <= 32 channels; BASELINE config 3: the 500 bp / 32-filter
+// baseline, train_config/nn_config_500bp_baseline.yaml; graph = nnlib/builder.py:982-1193 over nnlib/v2/layers.py:1110-1265,
+// 1836-1915).
+//
+// The per-layer kernels stream every activation tensor through HBM with its 32 channels zero-padded to a 64-channel group; at
+// 32 channels a whole window (6 frames x ~166 codons = 1 024 rows x 64 B) is only 64 KB per tensor, so here ONE CTA keeps the
+// window in shared memory through ALL layers of the stack:
+//
+//   tokens (1 KB per window, the only HBM read)  ->  one-hot stem operand built per 128-row tile in shared memory
+//   ->  stem conv  ->  conv1 / conv2 of every residual block (shortcut added in place)  ->  trailing norm + activation
+//   ->  masked sum / max pool  ->  32 floats per window (the only HBM write)
+//
+// Layout of an activation tensor in shared memory: fp16 [4 channel chunks of 8][guard + rows + guard][8] ("chunk planes"): the
+// canonical K-major NO-SWIZZLE operand layout of tcgen05.mma with core matrices of consecutive row groups contiguous (SBO = 128 B)
+// and the two K chunks of one MMA a plane apart (LBO = plane bytes).  Rows are linear inside a plane, so a conv tap is the
+// descriptor's start address advanced by `shift` x 16 B, an MMA operand fetch reads 8 rows x 16 B = 128 contiguous bytes, and the
+// epilogue's thread-per-row 16-byte accesses are conflict-free.  Guard rows stay zero = the SAME padding at the window ends; the
+// gap rows between frames are stored as zeros by the epilogue like in the HBM layout (conv_common.cuh).
+//
+// MMA: M = 128 rows (A, shared memory), N = 32 output channels (B = the layer's weights, resident in shared memory for the CTA's
+// lifetime), K = 16, fp32 accumulators of all 8 tiles of a layer in tensor memory (8 x 32 columns), two sets alternating between
+// layers.  Dependencies are per 128-row tile, not per layer: the MMAs of layer l+1, tile i wait for the epilogues of layer l, tiles
+// i-1 .. i+1 (mbarrier TILE_DONE), so the tensor pipe and the epilogue warps overlap across the layer boundary, and the next
+// window's stem overlaps the last layer's epilogue.
+//
+// Roles (576 threads, one persistent CTA per SM): warps 0-15 epilogue (group g = warp / 4 owns tiles g and g + 4; thread = row, the
+// same two rows of the window for every layer, so frame / position are computed once), warp 16 MMA issuer (+ TMEM allocation),
+// warp 17 builder (tokens -> token mask + one-hot tiles; prefetches the next window's tokens into registers).
+// The epilogue arithmetic is the generic epilogue of conv_epilogue.cuh (fp32 affine, packed fp16 from there on), so the numerics
+// equal the per-layer kernels'.
+#pragma once
+#include "conv_ws.cuh"
+
+namespace jg {
+namespace rs {
+
+using namespace jg::tc;
+using jg::tc2::fence_async_smem;
+using jg::ws::h2u;
+
+constexpr int kMaxLayersRs = 12;
+constexpr int kMaxTapsRs = 8;
+constexpr int kGuardRs = 8;                              // zero rows before / after a window's rows in every chunk plane
+constexpr int kEpiWarpsRs = 16;
+constexpr int kThreadsRs = (kEpiWarpsRs + 2) * 32;
+constexpr int kMaxTilesRs = 8;                           // 8 tiles x 32 columns x 2 sets = 512 TMEM columns
+constexpr int kParBytesRs = 512;                         // per layer: shift1 f32[32] | scale1 f32[32] | scale2 h[32] | shift2 h[32] | scc h[32]
+constexpr int kTokWordsRs = 12;                          // token words a builder lane prefetches: frames x pitch <= 32 x 12 x 4 bytes
+
+struct LayerRs {
+  int ntaps;
+  int shifts[kMaxTapsRs];
+  int in_arr;              // 0 = tokens (stem: one-hot operand), 1 = X, 2 = H
+  int out_arr;             // 1 = X, 2 = H, 0 = none (pool-only last layer)
+  int has_sc;              // residual shortcut
+  int sc_arr;              // the buffer it is read from (1 = X, 2 = H): the output buffer's current content (added in place), or X / H
+                           // for the pool-only last layer
+  int sc_all_valid;        // the shortcut tensor carries no mask
+  int act1, act2, has_aff2, pool_mode, masking, folded;
+  int shrink_in, shrink;
+  int kc;                  // input channel chunks of 8: 8 for the one-hot stem operand, 4 otherwise
+  uint32_t w_off;          // byte offset of the layer's weight image in the weights block: [tap][kc][32 out channels][8] fp16
+};
+
+struct ResidentParams {
+  const uint8_t* tokens;   // [n_windows][frames][pitch]
+  const int* lpad;         // [n_windows] padded frame length
+  long long n_windows;
+  int lc, pitch, tok_offset, period, frames, rpw, n_layers;
+  const uint8_t* wblock;   // all weight images, then kParBytesRs per layer
+  uint32_t w_bytes;
+  float* pool;             // [n_windows][pool_pitch], pre-filled (0 for the sum, -1e9 for the max)
+  int pool_pitch;
+  int* count;              // [n_windows] valid rows of the final mask, pre-zeroed
+  int* err;
+  int desc_swap;           // probe switch: exchange the LBO / SBO fields of the no-swizzle descriptors
+  LayerRs layer[kMaxLayersRs];
+};
+
+struct SmemRs {
+  uint32_t plane_bytes, buf_bytes, buf_off[2], w_off, par_off, mask_bytes, mask_off[3], tok_off, bar_off, total;
+  uint32_t slot_rows, slot_plane, slot_bytes;
+};
+
+__host__ __device__ inline SmemRs smem_rs(int rpw, int n_layers, uint32_t w_bytes, int frames, int pitch, int stem_span) {
+  SmemRs S;
+  S.plane_bytes = static_cast<uint32_t>(rpw + 2 * kGuardRs) * 16u;
+  S.buf_bytes = 4u * S.plane_bytes;
+  S.buf_off[0] = 0;
+  S.buf_off[1] = S.buf_bytes;
+  S.w_off = 2u * S.buf_bytes;
+  S.par_off = S.w_off + ((w_bytes + 127u) & ~127u);
+  S.mask_bytes = (static_cast<uint32_t>(rpw + 2 * kGuardRs) + 15u) & ~15u;
+  S.mask_off[0] = S.par_off + static_cast<uint32_t>(n_layers) * kParBytesRs;
+  S.mask_off[1] = S.mask_off[0] + S.mask_bytes;
+  S.mask_off[2] = S.mask_off[1] + S.mask_bytes;
+  S.tok_off = S.mask_off[2] + S.mask_bytes;
+  S.bar_off = S.tok_off + ((static_cast<uint32_t>(frames * pitch) + 15u) & ~15u);
+  S.total = S.bar_off + 256u + 128u;                       // barriers + TMEM pointer, + slack to align the base to 128 B
+  S.slot_rows = static_cast<uint32_t>(128 + stem_span + 7) / 8u * 8u;
+  S.slot_plane = S.slot_rows * 16u;
+  S.slot_bytes = 8u * S.slot_plane;
+  return S;
+}
+
+// K-major no-swizzle matrix descriptor (cute/arch/mma_sm100_desc.hpp; canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units)
+__device__ __forceinline__ uint64_t desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+  return desc_pack(lo, hi);
+}
+
+__global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __grid_constant__ ResidentParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.rpw / kTileM;
+  const int n_layers = p.n_layers;
+  int stem_min = 0, stem_max = 0;
+  for (int t = 0; t < p.layer[0].ntaps; ++t) {
+    stem_min = min(stem_min, p.layer[0].shifts[t]);
+    stem_max = max(stem_max, p.layer[0].shifts[t]);
+  }
+  const SmemRs S = smem_rs(p.rpw, n_layers, p.w_bytes, p.frames, p.pitch, stem_max - stem_min);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + S.bar_off);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 24);
+  auto ACC_FULL = [&](int i) { return smem_u32(s_bar + i); };
+  auto TILE_DONE = [&](int i) { return smem_u32(s_bar + 8 + i); };
+  auto OH_FULL = [&](int s) { return smem_u32(s_bar + 16 + s); };
+  auto OH_FREE = [&](int s) { return smem_u32(s_bar + 18 + s); };
+  const uint32_t WIN_DONE = smem_u32(s_bar + 20);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxTilesRs; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(TILE_DONE(i), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(OH_FULL(s), 1); mbar_init(OH_FREE(s), 1); }
+    mbar_init(WIN_DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarpsRs) tmem_alloc(smem_u32(s_tmem), 512u);
+  {   // zero the activation buffers and masks, bring in the weights and per-layer parameters
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = threadIdx.x; i < 2u * S.buf_bytes / 16u; i += kThreadsRs) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* mz = reinterpret_cast<uint4*>(smem + S.mask_off[0]);
+    for (uint32_t i = threadIdx.x; i < 3u * S.mask_bytes / 16u; i += kThreadsRs) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* src = reinterpret_cast<const uint4*>(p.wblock);
+    uint4* wd = reinterpret_cast<uint4*>(smem + S.w_off);
+    for (uint32_t i = threadIdx.x; i < p.w_bytes / 16u; i += kThreadsRs) wd[i] = src[i];
+    const uint4* psrc = reinterpret_cast<const uint4*>(p.wblock + p.w_bytes);
+    uint4* pd = reinterpret_cast<uint4*>(smem + S.par_off);
+    for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(n_layers) * kParBytesRs / 16u; i += kThreadsRs) pd[i] = psrc[i];
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const long long w0 = blockIdx.x, wstep = gridDim.x;
+
+  if (warp < kEpiWarpsRs) {
+    // ------------------------------------------------------------------ epilogue: thread = row ------------------------------
+    const int q = warp & 3, g = warp >> 2;
+    const int rw0 = g * kTileM + q * 32 + lane, rw1 = rw0 + 4 * kTileM;       // the two rows of the window this thread owns
+    const int fr0 = rw0 / p.period, fr1 = rw1 / p.period;
+    const int jj0 = rw0 - fr0 * p.period, jj1 = rw1 - fr1 * p.period;
+    uint32_t gl = 0;
+    int lp_next = w0 < p.n_windows ? p.lpad[w0] : 0;
+    for (long long w = w0; w < p.n_windows; w += wstep) {
+      const int lp = lp_next;
+      if (w + wstep < p.n_windows) lp_next = p.lpad[w + wstep];
+      for (int l = 0; l < n_layers; ++l, ++gl) {
+        const LayerRs& L = p.layer[l];
+        const uint8_t* par = smem + S.par_off + l * kParBytesRs;
+        const float4* shift1 = reinterpret_cast<const float4*>(par);
+        const float4* scale1 = reinterpret_cast<const float4*>(par + 128);
+        const uint4* scale2 = reinterpret_cast<const uint4*>(par + 256);
+        const uint4* shift2 = reinterpret_cast<const uint4*>(par + 320);
+        const uint4* scc = reinterpret_cast<const uint4*>(par + 384);
+        const uint8_t* mask_in = smem + S.mask_off[L.in_arr] + kGuardRs;
+        uint8_t* mask_out = L.out_arr ? smem + S.mask_off[L.out_arr] + kGuardRs : nullptr;
+        uint8_t* out = L.out_arr ? smem + S.buf_off[L.out_arr - 1] : nullptr;
+        const uint8_t* scb = L.sc_arr ? smem + S.buf_off[L.sc_arr - 1] : nullptr;
+        const uint8_t* sc_mask = L.sc_arr ? smem + S.mask_off[L.sc_arr] + kGuardRs : nullptr;
+        const int limit = lp - L.shrink_in - L.shrink;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int i = g + 4 * h;
+          if (i >= n_tiles) break;
+          mbar_wait(ACC_FULL(i), gl & 1u);
+          tc_fence_after();
+          uint32_t raw[32];
+          tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u, raw);
+          const int r = h ? rw1 : rw0;
+          bool valid = (h ? fr1 : fr0) < p.frames && (h ? jj1 : jj0) < limit;
+          if (L.masking) {
+            uint32_t any = 0u;
+            for (int t = 0; t < L.ntaps; ++t) any |= mask_in[r + L.shifts[t]];
+            valid = valid && any != 0u;
+          }
+          const uint32_t row_off = static_cast<uint32_t>(kGuardRs + r) * 16u;
+          uint4 sv[4];
+          bool sc_valid = false;
+          if (L.has_sc) {
+            sc_valid = L.sc_all_valid || sc_mask[r] != 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sv[c] = sc_valid ? *reinterpret_cast<const uint4*>(scb + c * S.plane_bytes + row_off) : scc[c];
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          __half2 hv[16];
+          if (L.folded) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = shift1[j4];
+              hv[j4 * 2 + 0] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 0]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y);
+              hv[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 a = scale1[j4], b = shift1[j4];
+              hv[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
+              hv[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
+            }
+          }
+          if (L.has_sc) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const __half2* s2 = reinterpret_cast<const __half2*>(&sv[c]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hadd2(hv[c * 4 + k], s2[k]);
+            }
+          }
+          act_apply_h2(hv, L.act1);
+          if (L.has_aff2) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 a = scale2[c], b = shift2[c];
+              const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+              const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hfma2(hv[c * 4 + k], a2[k], b2[k]);
+            }
+            act_apply_h2(hv, L.act2);
+          }
+          if (L.pool_mode != 0) {
+            __half2 tv[16];
+            const bool pool_max = L.pool_mode == 1;
+            const uint32_t fill_bits = pool_max ? 0xFC00FC00u : 0u;
+            const __half2 fill = *reinterpret_cast<const __half2*>(&fill_bits);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tv[k] = valid ? hv[k] : fill;
+            if (pool_max) {
+              const float m = warp_cols_reduce_h2<true>(tv, lane);
+              if (m > -1.0e38f) atomic_max_f32(p.pool + w * p.pool_pitch + lane, m);
+            } else {
+              atomicAdd(p.pool + w * p.pool_pitch + lane, warp_cols_reduce_h2<false>(tv, lane));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0 && bal) atomicAdd(p.count + w, __popc(bal));
+          }
+          if (out != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              o.x = h2u(hv[c * 4 + 0]); o.y = h2u(hv[c * 4 + 1]); o.z = h2u(hv[c * 4 + 2]); o.w = h2u(hv[c * 4 + 3]);
+              if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(out + c * S.plane_bytes + row_off) = o;
+            }
+            mask_out[r] = static_cast<uint8_t>(valid);
+            // the window's guard rows: H doubles as the staging area of the one-hot stem tiles, so they are re-zeroed by every layer
+            if (r < kGuardRs || r >= p.rpw - kGuardRs) {
+              const uint32_t goff = static_cast<uint32_t>(r < kGuardRs ? r : r + 2 * kGuardRs) * 16u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(out + c * S.plane_bytes + goff) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(TILE_DONE(i));
+        }
+      }
+    }
+  } else if (warp == kEpiWarpsRs) {
+    // ------------------------------------------------------------------ MMA issuer -------------------------------------------
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+    const uint32_t w_base = smem_u32(smem + S.w_off);
+    uint32_t gl = 0, nstem = 0;
+    for (long long w = w0; w < p.n_windows; w += wstep) {
+      for (int l = 0; l < n_layers; ++l, ++gl) {
+        const LayerRs& L = p.layer[l];
+        const bool stem = L.in_arr == 0;
+        const uint32_t prev = (gl - 1u) & 1u;
+        for (int i = 0; i < n_tiles; ++i) {
+          // Every phase of every TILE_DONE barrier is awaited exactly once, in order (a parity wait cannot tell phase u from
+          // u + 2, so no phase may be skipped -- the stem waits for the previous window's last layer too, although it only
+          // needs it for the accumulator set it is about to overwrite).  Tile i needs tiles i-1 .. i+1 of the layer before;
+          // i-1 and i were awaited for the tiles before this one.
+          if (gl > 0u) {
+            if (i == 0) {
+              mbar_wait(TILE_DONE(0), prev);
+              if (n_tiles > 1) mbar_wait(TILE_DONE(1), prev);
+            } else if (i + 1 < n_tiles) {
+              mbar_wait(TILE_DONE(i + 1), prev);
+            }
+          }
+          uint32_t slot = 0;
+          if (stem) {
+            slot = nstem & 1u;
+            mbar_wait(OH_FULL(slot), (nstem >> 1) & 1u);
+          }
+          tc_fence_after();
+          if (leader) {
+            const uint32_t d = tmem + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u;
+            const uint32_t plane = stem ? S.slot_plane : S.plane_bytes;
+            const uint32_t a_base = stem ? smem_u32(smem + S.buf_off[1]) + slot * S.slot_bytes
+                                         : smem_u32(smem + S.buf_off[L.in_arr - 1]) + static_cast<uint32_t>(kGuardRs + i * kTileM) * 16u;
+            const uint32_t a_lbo = p.desc_swap ? 128u : plane, a_sbo = p.desc_swap ? plane : 128u;
+            const uint32_t b_lbo = p.desc_swap ? 128u : 512u, b_sbo = p.desc_swap ? 512u : 128u;
+            for (int t = 0; t < L.ntaps; ++t) {
+              const int rs = stem ? L.shifts[t] - stem_min : L.shifts[t];
+              const uint32_t a_tap = a_base + static_cast<uint32_t>(rs * 16);
+              const uint32_t b_tap = w_base + L.w_off + static_cast<uint32_t>(t * L.kc) * 512u;
+              for (int kk = 0; kk < L.kc / 2; ++kk)
+                umma_bf16(d, desc_ns(a_tap + static_cast<uint32_t>(2 * kk) * plane, a_lbo, a_sbo),
+                          desc_ns(b_tap + static_cast<uint32_t>(2 * kk) * 512u, b_lbo, b_sbo), idesc, (t | kk) != 0);
+            }
+            umma_commit(ACC_FULL(i));
+            if (stem) umma_commit(OH_FREE(slot));
+            if (l == n_layers - 1 && i == n_tiles - 1) umma_commit(WIN_DONE);
+          }
+          __syncwarp();
+          if (stem) ++nstem;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ builder: tokens -> mask + one-hot stem tiles ----------
+    const int n_words = p.frames * p.pitch / 4;
+    uint32_t tk[kTokWordsRs];
+    auto fetch = [&](long long w) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tokens + w * p.frames * p.pitch);
+#pragma unroll
+      for (int u = 0; u < kTokWordsRs; ++u) tk[u] = (u * 32 + lane < n_words) ? src[u * 32 + lane] : 0u;
+    };
+    if (w0 < p.n_windows) fetch(w0);
+    uint8_t* tok = smem + S.tok_off;
+    uint8_t* mask_t = smem + S.mask_off[0] + kGuardRs;
+    uint8_t* stage = smem + S.buf_off[1];
+    uint32_t nstem = 0, it = 0;
+    int lp_next = w0 < p.n_windows ? p.lpad[w0] : 0;
+    for (long long w = w0; w < p.n_windows; w += wstep, ++it) {
+      // the previous window's last MMAs (the last readers of H) and, transitively, every reader of the token mask are done
+      if (it > 0) mbar_wait(WIN_DONE, (it - 1u) & 1u);
+#pragma unroll
+      for (int u = 0; u < kTokWordsRs; ++u)
+        if (u * 32 + lane < n_words) reinterpret_cast<uint32_t*>(tok)[u * 32 + lane] = tk[u];
+      int lim = lp_next < p.lc ? lp_next : p.lc;
+      if (w + wstep < p.n_windows) { fetch(w + wstep); lp_next = p.lpad[w + wstep]; }
+      __syncwarp();
+      for (int r = lane; r < p.rpw; r += 32) {
+        const int f = r / p.period, j = r - f * p.period;
+        const bool on = f < p.frames && j < lim && static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset >= 0;
+        mask_t[r] = static_cast<uint8_t>(on);
+      }
+      for (int i = 0; i < n_tiles; ++i, ++nstem) {
+        const uint32_t slot = nstem & 1u;
+        if (nstem >= 2u) mbar_wait(OH_FREE(slot), ((nstem >> 1) - 1u) & 1u);
+        uint8_t* sl = stage + slot * S.slot_bytes;
+        for (int s = lane; s < static_cast<int>(S.slot_rows); s += 32) {
+          const int r = i * kTileM + stem_min + s;
+          int ch = -1;
+          if (r >= 0 && r < p.rpw) {
+            const int f = r / p.period, j = r - f * p.period;
+            if (f < p.frames && j < lim) ch = static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset;
+          }
+          const uint32_t one = ch >= 0 ? (0x3C00u << (16 * (ch & 1))) : 0u;      // fp16 1.0 in the channel's half of its word
+          const int word = ch >= 0 ? (ch & 7) >> 1 : -1, chunk = ch >= 0 ? ch >> 3 : -1;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (c == chunk) { o.x = word == 0 ? one : 0u; o.y = word == 1 ? one : 0u; o.z = word == 2 ? one : 0u; o.w = word == 3 ? one : 0u; }
+            *reinterpret_cast<uint4*>(sl + c * S.slot_plane + s * 16) = o;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(OH_FULL(slot));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarpsRs) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512u);
+  }
+}
+
+}  // namespace rs
+}  // namespace jg

@@ -12,6 +12,7 @@
 #include <zlib.h>
 
 #include "conv_launch.cuh"
+#include "conv_resident.cuh"
 #include "dust_kernels.cuh"
 #include "model_kernels.cuh"
 #include "post_kernels.cuh"
@@ -65,7 +66,8 @@ struct jg_ctx {
 enum LayerField {
   LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
   LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
-  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL
+  LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL,
+  LF_REAL_CIN, LF_REAL_COUT      // channel counts before the plan's padding to 64 (0 = not given)
 };
 // layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
 enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
@@ -121,6 +123,13 @@ struct jg_model {
   const int** tap_count_ptrs = nullptr;
   int* err = nullptr;
   int64_t ws_bytes = 0;
+  // window-resident kernel for narrow stacks (conv_resident.cuh): candidate decided at model creation, geometry checked per call
+  bool rs_ok = true;                  // every layer so far fits the resident kernel's envelope
+  std::vector<uint8_t> rs_w, rs_p;    // host images: weights [layer][tap][kc][32][8] fp16, parameters 512 B per layer
+  uint8_t* rs_block = nullptr;        // device copy: weights, then parameters
+  jg::rs::ResidentParams rs_par{};
+  int rs_stem_span = 0;
+  bool last_resident = false;         // the last forward pass ran the resident kernel
   // per-conv-launch CUDA-event timing (jg_model_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // pending (start, stop) pairs
@@ -236,6 +245,57 @@ void free_weight_images(WeightImages& w) { cudaFree(w.w); cudaFree(w.w2); cudaFr
 int upload_f32(const float* h, size_t n, float** d) {
   JG_CUDA(cudaMalloc(d, n * 4));
   JG_CUDA(cudaMemcpy(*d, h, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Window-resident kernel: wire the layers' buffers / masks (the plan's buffer ids -> the kernel's X / H arrays) and upload the images.
+// Leaves m->rs_ok false when the plan's dataflow is not the in-place two-buffer chain the kernel implements.
+int finish_resident(jg_model* m, const jg_head_desc* head) {
+  const int n = static_cast<int>(m->layers.size());
+  bool ok = m->rs_ok && n >= 2 && m->n_taps == 0 && head->feat_dim == 64 && !std::getenv("JG_NO_RESIDENT");
+  if (const char* e = std::getenv("JG_RESIDENT")) ok = ok && std::atoi(e) != 0;
+  int arr_of[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mask_of[3] = {-2, -2, -2}, next_arr = 1;
+  for (int l = 0; ok && l < n; ++l) {
+    const Layer& L = m->layers[l];
+    jg::rs::LayerRs& R = m->rs_par.layer[l];
+    const int ib = L.f[LF_IN_BUF], ob = L.f[LF_OUT_BUF], sb = L.f[LF_SC_BUF];
+    if (ib < 0 || ib >= 8 || ob >= 8 || sb >= 8) { ok = false; break; }
+    if (l == 0) {
+      mask_of[0] = L.f[LF_MASK_IN];
+      R.in_arr = 0;
+    } else {
+      if (ib == 0 || arr_of[ib] == 0) { ok = false; break; }
+      R.in_arr = arr_of[ib];
+    }
+    if (mask_of[R.in_arr] != L.f[LF_MASK_IN]) { ok = false; break; }
+    R.has_sc = sb >= 0 ? 1 : 0;
+    R.sc_arr = 0;
+    if (sb >= 0) {
+      if (sb == 0 || arr_of[sb] == 0 || arr_of[sb] == R.in_arr) { ok = false; break; }
+      R.sc_arr = arr_of[sb];
+      R.sc_all_valid = L.f[LF_SC_MASK] < 0 ? 1 : 0;
+      if (L.f[LF_SC_MASK] >= 0 && mask_of[R.sc_arr] != L.f[LF_SC_MASK]) { ok = false; break; }
+    }
+    R.out_arr = 0;
+    if (ob >= 0) {
+      if (ob == 0) { ok = false; break; }
+      if (arr_of[ob] == 0) {
+        if (next_arr > 2) { ok = false; break; }
+        arr_of[ob] = next_arr++;
+      }
+      R.out_arr = arr_of[ob];
+      if (R.out_arr == R.in_arr || (R.sc_arr != 0 && R.sc_arr != R.out_arr)) { ok = false; break; }
+      mask_of[R.out_arr] = L.f[LF_MASK_OUT];
+    }
+    if ((L.f[LF_POOL_MODE] != 0) != (l == n - 1) || (ob < 0) != (l == n - 1)) { ok = false; break; }
+  }
+  m->rs_ok = ok;
+  if (!ok) { m->rs_w.clear(); m->rs_p.clear(); return 0; }
+  m->rs_par.n_layers = n;
+  m->rs_par.w_bytes = static_cast<uint32_t>(m->rs_w.size());
+  JG_CUDA(cudaMalloc(&m->rs_block, m->rs_w.size() + m->rs_p.size()));
+  JG_CUDA(cudaMemcpy(m->rs_block, m->rs_w.data(), m->rs_w.size(), cudaMemcpyHostToDevice));
+  JG_CUDA(cudaMemcpy(m->rs_block + m->rs_w.size(), m->rs_p.data(), m->rs_p.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -641,6 +701,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
       if (cin % 64 != 0) { delete m; return fail("pooling / row-phase layers need a channel count that is a multiple of 64"); }
       for (int b : {L.f[LF_IN_BUF], L.f[LF_OUT_BUF]}) max_buf = b > max_buf ? b : max_buf;
       for (int sl : {L.f[LF_MASK_IN], L.f[LF_MASK_OUT]}) max_mask = sl > max_mask ? sl : max_mask;
+      m->rs_ok = false;                 // pooling / row-phase layers are outside the resident kernel's envelope
       m->layers.push_back(L);
       continue;
     }
@@ -722,6 +783,46 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     if (L.folded)
       for (int c = 0; c < cout; ++c) par[1 * cout + c] = 1.0f;        // scale1 now lives in the weights
     if (upload_f32(par.data(), par.size(), &L.par)) { delete m; return 2; }
+    {   // window-resident kernel: does this layer fit its envelope?  (<= 32 real channels, <= 8 taps within the guard rows, plain
+        // affine + tanh-GELU / ReLU epilogue, no NMD tap, no stride)  If so, append its weight image and parameter block.
+      const int n_prev = static_cast<int>(m->layers.size());
+      const int rcin = L.f[LF_REAL_CIN] > 0 ? L.f[LF_REAL_CIN] : cin, rcout = L.f[LF_REAL_COUT] > 0 ? L.f[LF_REAL_COUT] : cout;
+      const bool stem = n_prev == 0;
+      bool ok = m->rs_ok && n_prev < jg::rs::kMaxLayersRs && cout == 64 && rcout <= 32 && k <= jg::rs::kMaxTapsRs &&
+                (stem ? (cin == 64 && L.f[LF_IN_BUF] == 0) : (cin == 64 && rcin <= 32)) && L.f[LF_TAP_MODE] == 0 && L.f[LF_DYT1] == 0 &&
+                L.f[LF_DYT2] == 0 && L.f[LF_EPI_F32] == 0 && L.f[LF_HALVINGS] == 0 && L.f[LF_LEN_CEIL] == 0 && wk_odd == nullptr &&
+                L.f[LF_ACT1] <= 2 && L.f[LF_ACT2] <= 2 && (stem || (L.halo_l <= jg::rs::kGuardRs && L.halo_r <= jg::rs::kGuardRs));
+      if (ok) {
+        const int kc = stem ? 8 : 4;
+        const size_t off = m->rs_w.size();
+        m->rs_w.resize(off + static_cast<size_t>(k) * kc * 512);
+        uint16_t* img = reinterpret_cast<uint16_t*>(m->rs_w.data() + off);
+        for (int t = 0; t < k; ++t)
+          for (int ci = 0; ci < kc * 8; ++ci)
+            for (int co = 0; co < 32; ++co)
+              img[((static_cast<size_t>(t) * kc + ci / 8) * 32 + co) * 8 + ci % 8] = f32_to_f16(wk[(static_cast<size_t>(t) * cin + ci) * cout + co]);
+        const size_t poff = m->rs_p.size();
+        m->rs_p.resize(poff + jg::rs::kParBytesRs);
+        float* pf = reinterpret_cast<float*>(m->rs_p.data() + poff);
+        uint16_t* ph = reinterpret_cast<uint16_t*>(m->rs_p.data() + poff + 256);
+        for (int c = 0; c < 32; ++c) {
+          pf[c] = par[2 * cout + c];                                                  // shift1
+          pf[32 + c] = par[1 * cout + c];                                             // scale1 (1 when folded)
+          ph[c] = f32_to_f16(L.f[LF_HAS_AFF2] ? par[3 * cout + c] : 1.0f);            // scale2
+          ph[32 + c] = f32_to_f16(L.f[LF_HAS_AFF2] ? par[4 * cout + c] : 0.0f);       // shift2
+          ph[64 + c] = f32_to_f16(par[5 * cout + c]);                                 // shortcut value at masked rows
+        }
+        jg::rs::LayerRs& R = m->rs_par.layer[n_prev];
+        R = jg::rs::LayerRs{};
+        R.ntaps = k;
+        for (int t = 0; t < k; ++t) R.shifts[t] = L.shifts_h[t];
+        R.act1 = L.f[LF_ACT1]; R.act2 = L.f[LF_ACT2]; R.has_aff2 = L.f[LF_HAS_AFF2]; R.pool_mode = L.f[LF_POOL_MODE];
+        R.masking = L.f[LF_MASKING]; R.folded = L.folded ? 1 : 0; R.shrink_in = L.f[LF_CUM_SHRINK_IN]; R.shrink = L.f[LF_SHRINK];
+        R.kc = kc; R.w_off = static_cast<uint32_t>(off);
+        if (stem) m->rs_stem_span = L.halo_l + L.halo_r;
+      }
+      m->rs_ok = ok;
+    }
     JG_CUDA(cudaMalloc(&L.shifts, sizeof(int) * jg::kMaxTaps));
     JG_CUDA(cudaMemcpy(L.shifts, L.shifts_h, sizeof(int) * k, cudaMemcpyHostToDevice));
     for (int b : {L.f[LF_IN_BUF], L.f[LF_OUT_BUF], L.f[LF_SC_BUF]}) max_buf = b > max_buf ? b : max_buf;
@@ -778,6 +879,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
   }
   JG_CUDA(cudaMalloc(&m->err, 4));
   JG_CUDA(cudaMemset(m->err, 0, 4));
+  if (finish_resident(m, head)) { delete m; return 2; }
   if (const char* impl = std::getenv("JG_CONV_IMPL")) m->conv_impl = std::atoi(impl);
   m->prof_ms.assign(m->layers.size(), 0.0);
   m->prof_launches.assign(m->layers.size(), 0);
@@ -798,6 +900,7 @@ int jg_model_destroy(jg_model* m) {
   for (float* p : {m->cls_w, m->cls_b, m->rel_w1, m->rel_b1, m->rel_w2, m->rel_b2, m->tap_mean, m->mlp_w1, m->mlp_b1,
                    m->mlp_w2, m->mlp_b2}) cudaFree(p);
   cudaFree(m->err);
+  cudaFree(m->rs_block);
   delete m;
   return 0;
 }
@@ -849,6 +952,42 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   auto buf_row0 = [&](int b) { return m->bufs[b] + static_cast<long long>(jg::kGuardRows) * 64; };
   auto mask_row0 = [&](int s) { return m->masks[s] + jg::kGuardRows; };
 
+  // Narrow stacks: ONE launch keeps every window in shared memory through all conv layers (conv_resident.cuh); it reads the
+  // tokens and writes the pooled features + the valid-row counts of the final mask, nothing else.
+  m->last_resident = false;
+  if (m->rs_ok && !use_ref && rpw / jg::kTileM <= jg::rs::kMaxTilesRs && m->frames * pitch <= 128 * jg::rs::kTokWordsRs && pitch % 4 == 0) {
+    const jg::rs::SmemRs S = jg::rs::smem_rs(rpw, m->rs_par.n_layers, m->rs_par.w_bytes, m->frames, pitch, m->rs_stem_span);
+    if (S.total <= jg::kMaxSmem && 2u * S.slot_bytes <= S.buf_bytes) {
+      jg::rs::ResidentParams rp = m->rs_par;
+      rp.tokens = d_tokens; rp.lpad = d_lpad; rp.n_windows = n_windows; rp.lc = lc; rp.pitch = pitch; rp.tok_offset = m->tok_offset;
+      rp.period = period; rp.frames = m->frames; rp.rpw = rpw;
+      rp.wblock = m->rs_block;
+      rp.pool = m->pool; rp.pool_pitch = m->head.feat_dim;
+      rp.count = m->counts + static_cast<long long>(m->final_mask) * m->cap_windows;
+      rp.err = m->err;
+      rp.desc_swap = std::getenv("JG_RS_DESC_SWAP") ? 1 : 0;
+      JG_CUDA(cudaFuncSetAttribute(jg::rs::stack_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (m->profiling) {
+        JG_CUDA(cudaEventCreate(&ev0));
+        JG_CUDA(cudaEventCreate(&ev1));
+        JG_CUDA(cudaEventRecord(ev0, st));
+      }
+      const int grid = n_windows < ctx->num_sms ? static_cast<int>(n_windows) : ctx->num_sms;
+      jg::rs::stack_resident_kernel<<<grid, jg::rs::kThreadsRs, S.total, st>>>(rp);
+      ctx->launches++;
+      JG_CUDA(cudaGetLastError());
+      if (m->profiling) {     // the one launch is booked on the last conv layer; every layer gets the windows it covered
+        JG_CUDA(cudaEventRecord(ev1, st));
+        m->prof_events.emplace_back(ev0, ev1);
+        m->prof_layer.push_back(static_cast<int>(m->layers.size()) - 1);
+        for (size_t l = 0; l < m->layers.size(); ++l) m->prof_rows[l] += static_cast<double>(n_windows);
+      }
+      m->last_resident = true;
+    }
+  }
+  bool pool_final = false;
+  if (!m->last_resident) {
   // stem operand: one-hot rows + token mask
   jg::expand_tokens_kernel<<<grid_for(n_windows * (m->frames + 1), 1, ctx->num_sms, 8), 256, 0, st>>>(
       d_tokens, d_lpad, n_windows, lc, pitch, geom, m->tok_offset, buf_row0(m->layers[0].f[LF_IN_BUF]), mask_row0(m->layers[0].f[LF_MASK_IN]),
@@ -856,7 +995,6 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
   ctx->launches++;
   JG_CUDA(cudaGetLastError());
 
-  bool pool_final = false;
   for (Layer& L : m->layers) {
     const int cout = L.f[LF_COUT];
     if (L.f[LF_KIND] == 2) {
@@ -1015,6 +1153,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       m->prof_rows[&L - m->layers.data()] += static_cast<double>(n_windows);
     }
   }
+  }   // per-layer path
 
   jg::HeadParams hp{};
   hp.pool = m->pool;
@@ -1052,6 +1191,10 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
 int jg_model_kernel_names(jg_model* m, char* buf, int32_t n) {
   if (!buf || n <= 0) return fail("jg_model_kernel_names: no buffer");
   std::vector<std::pair<std::string, int>> seen;
+  if (m->last_resident) {
+    std::snprintf(buf, static_cast<size_t>(n), "1 x jg::rs::stack_resident_kernel (%d conv layers)", static_cast<int>(m->layers.size()));
+    return 0;
+  }
   for (const Layer& L : m->layers) {
     if (L.f[LF_KIND] != 1 || !L.last_kernel[0]) continue;
     bool found = false;

@@ -31,7 +31,8 @@ LAYER_PTR_FIELDS = 16
 # int field indices (mirror enum LayerField in csrc/jaeger_b200.cu)
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
- LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL) = range(26)
+ LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL, LF_REAL_CIN,
+ LF_REAL_COUT) = range(28)
 (LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
  LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2, LP_KERNEL_ODD) = range(13)
 
@@ -502,7 +503,7 @@ def to_ctypes(plan: Plan):
                 LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
                 LF_MASK_OUT: c.mask_out, LF_SC_MASK: c.sc_mask, LF_MASKING: c.masking,
                 LF_CUM_SHRINK_IN: c.cum_shrink_in, LF_DYT1: int(c.dyt_g1 is not None), LF_DYT2: int(c.dyt_g2 is not None),
-                LF_EPI_F32: c.epi_f32, LF_LEN_CEIL: c.len_ceil}
+                LF_EPI_F32: c.epi_f32, LF_LEN_CEIL: c.len_ceil, LF_REAL_CIN: c.real_cin, LF_REAL_COUT: c.real_cout}
         for i, v in vals.items():
             d.i[i] = int(v)
         ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,

@@ -819,6 +819,62 @@ def test_500bp_baseline_model_config3():
     ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 500))
     assert np.abs(ref["prediction"] - y["prediction"]).max() <= 4e-3
     assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2
+    assert "stack_resident_kernel" in eng.conv_kernel_names()        # narrow stacks run window-resident (csrc/conv_resident.cuh)
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", ["baseline", "max_relu", "no_masking", "k3_dilated"])
+def test_window_resident_kernel_vs_per_layer_kernels_and_oracle(variant, monkeypatch):
+    """The window-resident kernel (one launch, every window kept in shared memory through all conv layers) against the
+    per-layer kernels it replaces (JG_RESIDENT=0) and the fp32 oracle: the full config-3 graph (2 residual stacks), max pooling
+    + ReLU, masking off, dilated taps; windows with N runs (masked codons), a short last window and a frame-length mix."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from jaeger_b200.modelspec import baseline_500bp_config
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    cfg = baseline_500bp_config()
+    rl = cfg["model"]["representation_learner"]
+    if variant == "max_relu":
+        rl["pooling"] = "max"
+        cfg["model"]["activation"] = "relu"
+        for layer in rl["hidden_layers"]:
+            if layer["name"] == "activation":
+                layer["config"]["activation"] = "relu"
+    elif variant == "no_masking":
+        cfg["model"]["use_masking"] = False
+    elif variant == "k3_dilated":
+        for layer in rl["hidden_layers"]:
+            if layer["name"] == "residual_block":
+                layer["config"].update(kernel_size=3, dilation_rate=3)
+    spec = parse_project(cfg)
+    w = init_random(spec, 5)
+    recs = random_contigs(4, [500] * 200 + [499, 1700, 512, 640, 2100], n_run_every=5, lower_every=0)
+    seqs = [s[i:i + 500] for _, s in recs for i in range(0, len(s) - 499, 500)]
+    ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 500))
+    got = {}
+    for resident in ("1", "0"):
+        monkeypatch.setenv("JG_RESIDENT", resident)
+        eng = B200Engine(spec=spec, weights=w)
+        got[resident] = eng.predict(WindowSource(records=recs, fsize=500, stride=500))
+        assert ("stack_resident_kernel" in eng.conv_kernel_names()) == (resident == "1")
+        eng.close()
+    for resident, y in got.items():
+        assert y["prediction"].shape == (len(seqs), 3)
+        assert np.abs(ref["prediction"] - y["prediction"]).max() <= 4e-3, resident
+        assert np.abs(ref["embedding"] - y["embedding"]).max() <= 1e-2, resident
+    # same arithmetic in both paths (fp32 accumulation order inside the MMA aside)
+    assert np.abs(got["1"]["prediction"] - got["0"]["prediction"]).max() <= 2e-3
+    # window independence: a window's logits do not depend on its neighbours in the batch
+    monkeypatch.setenv("JG_RESIDENT", "1")
+    eng = B200Engine(spec=spec, weights=w)
+    some = recs[::7]
+    y2 = eng.predict(WindowSource(records=some, fsize=500, stride=500))
+    names = list(got["1"]["meta_0"])
+    for i, nm in enumerate(y2["meta_0"]):
+        j = names.index(nm) if nm in names else -1
+        if j >= 0 and list(names).count(nm) == 1:
+            assert np.array_equal(y2["prediction"][i], got["1"]["prediction"][j])
     eng.close()
 
 
