@@ -58,6 +58,7 @@ struct LayerRs {
   int sc_all_valid;        // the shortcut tensor carries no mask
   int act1, act2, has_aff2, pool_mode, masking, folded;
   int shrink_in, shrink;
+  int zero_tap;            // one of the taps has shift 0: in a window without masked codons every in-frame output row is then valid
   int kc;                  // input channel chunks of 8: 8 for the one-hot stem operand, 4 otherwise
   uint32_t w_off;          // byte offset of the layer's weight image in the weights block: [tap][kc][32 out channels][8] fp16
 };
@@ -73,7 +74,6 @@ struct ResidentParams {
   int pool_pitch;
   int* count;              // [n_windows] valid rows of the final mask, pre-zeroed
   int* err;
-  int desc_swap;           // probe switch: exchange the LBO / SBO fields of the no-swizzle descriptors
   LayerRs layer[kMaxLayersRs];
 };
 
@@ -110,6 +110,32 @@ __device__ __forceinline__ uint64_t desc_ns(uint32_t saddr, uint32_t lbo, uint32
   return desc_pack(lo, hi);
 }
 
+// tcgen05.mma issue, SS mode.  No "memory" clobber: the instruction touches no memory the compiler knows about, and its ordering
+// against the barrier waits / commits around it is that of the volatile asm statements themselves.
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+// The MMAs of one 128-row tile, fully unrolled for the layer shapes that carry the time (the rolled version spends ~180 cycles per
+// MMA in a dependent chain of uniform-datapath address arithmetic; an MMA is ~40).  a_lo / b_lo: low descriptor words (start
+// address and LBO) of the tile's first row, tap 0, K chunk 0; `dil`: tap-to-tap row shift, `a_kk`: two chunk planes, both in
+// 16-byte units.  The weight image is contiguous in (tap, K chunk pair): 1 KB per MMA.
+template <int kT, int kK>
+__device__ __forceinline__ void issue_tile(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t dil, uint32_t a_kk, uint32_t hi, uint32_t idesc) {
+#pragma unroll
+  for (int t = 0; t < kT; ++t) {
+#pragma unroll
+    for (int kk = 0; kk < kK; ++kk)
+      umma_ss(d, desc_pack(a_lo + static_cast<uint32_t>(t) * dil + static_cast<uint32_t>(kk) * a_kk, hi),
+              desc_pack(b_lo + static_cast<uint32_t>(t * kK + kk) * 64u, hi), idesc, (t | kk) != 0);
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __grid_constant__ ResidentParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -124,6 +150,7 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
   const SmemRs S = smem_rs(p.rpw, n_layers, p.w_bytes, p.frames, p.pitch, stem_max - stem_min);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + S.bar_off);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 24);
+  volatile int* s_clean = reinterpret_cast<volatile int*>(s_bar + 25);   // [2], by window parity: no in-frame codon of the window is masked
   auto ACC_FULL = [&](int i) { return smem_u32(s_bar + i); };
   auto TILE_DONE = [&](int i) { return smem_u32(s_bar + 8 + i); };
   auto OH_FULL = [&](int s) { return smem_u32(s_bar + 16 + s); };
@@ -162,9 +189,9 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     const int rw0 = g * kTileM + q * 32 + lane, rw1 = rw0 + 4 * kTileM;       // the two rows of the window this thread owns
     const int fr0 = rw0 / p.period, fr1 = rw1 / p.period;
     const int jj0 = rw0 - fr0 * p.period, jj1 = rw1 - fr1 * p.period;
-    uint32_t gl = 0;
+    uint32_t gl = 0, itw = 0;
     int lp_next = w0 < p.n_windows ? p.lpad[w0] : 0;
-    for (long long w = w0; w < p.n_windows; w += wstep) {
+    for (long long w = w0; w < p.n_windows; w += wstep, ++itw) {
       const int lp = lp_next;
       if (w + wstep < p.n_windows) lp_next = p.lpad[w + wstep];
       for (int l = 0; l < n_layers; ++l, ++gl) {
@@ -175,11 +202,11 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         const uint4* scale2 = reinterpret_cast<const uint4*>(par + 256);
         const uint4* shift2 = reinterpret_cast<const uint4*>(par + 320);
         const uint4* scc = reinterpret_cast<const uint4*>(par + 384);
-        const uint8_t* mask_in = smem + S.mask_off[L.in_arr] + kGuardRs;
-        uint8_t* mask_out = L.out_arr ? smem + S.mask_off[L.out_arr] + kGuardRs : nullptr;
-        uint8_t* out = L.out_arr ? smem + S.buf_off[L.out_arr - 1] : nullptr;
-        const uint8_t* scb = L.sc_arr ? smem + S.buf_off[L.sc_arr - 1] : nullptr;
-        const uint8_t* sc_mask = L.sc_arr ? smem + S.mask_off[L.sc_arr] + kGuardRs : nullptr;
+        const uint8_t* mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr) * S.mask_bytes + kGuardRs;
+        uint8_t* mask_out = L.out_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.out_arr) * S.mask_bytes + kGuardRs : nullptr;
+        uint8_t* out = L.out_arr ? smem + static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : nullptr;
+        const uint8_t* scb = L.sc_arr ? smem + static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : nullptr;
+        const uint8_t* sc_mask = L.sc_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.sc_arr) * S.mask_bytes + kGuardRs : nullptr;
         const int limit = lp - L.shrink_in - L.shrink;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -191,19 +218,15 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
           tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u, raw);
           const int r = h ? rw1 : rw0;
           bool valid = (h ? fr1 : fr0) < p.frames && (h ? jj1 : jj0) < limit;
-          if (L.masking) {
+          // Keras mask propagation, mode "any" (layers.py:1245-1252).  In a window without masked codons (the flag is the builder's)
+          // every in-frame row of every layer is valid as soon as the layer has a tap at shift 0, so the tap loop is skipped.
+          if (L.masking && !(L.zero_tap && s_clean[itw & 1u])) {
             uint32_t any = 0u;
             for (int t = 0; t < L.ntaps; ++t) any |= mask_in[r + L.shifts[t]];
             valid = valid && any != 0u;
           }
           const uint32_t row_off = static_cast<uint32_t>(kGuardRs + r) * 16u;
-          uint4 sv[4];
-          bool sc_valid = false;
-          if (L.has_sc) {
-            sc_valid = L.sc_all_valid || sc_mask[r] != 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sv[c] = sc_valid ? *reinterpret_cast<const uint4*>(scb + c * S.plane_bytes + row_off) : scc[c];
-          }
+          const bool sc_valid = L.has_sc && (L.sc_all_valid || sc_mask[r] != 0);
           tmem_ld_wait();
           tc_fence_before();
           __half2 hv[16];
@@ -225,7 +248,8 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
           if (L.has_sc) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const __half2* s2 = reinterpret_cast<const __half2*>(&sv[c]);
+              const uint4 sv = sc_valid ? *reinterpret_cast<const uint4*>(scb + c * S.plane_bytes + row_off) : scc[c];
+              const __half2* s2 = reinterpret_cast<const __half2*>(&sv);
 #pragma unroll
               for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hadd2(hv[c * 4 + k], s2[k]);
             }
@@ -310,24 +334,35 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
             mbar_wait(OH_FULL(slot), (nstem >> 1) & 1u);
           }
           tc_fence_after();
-          if (leader) {
+          {
             const uint32_t d = tmem + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u;
             const uint32_t plane = stem ? S.slot_plane : S.plane_bytes;
-            const uint32_t a_base = stem ? smem_u32(smem + S.buf_off[1]) + slot * S.slot_bytes
-                                         : smem_u32(smem + S.buf_off[L.in_arr - 1]) + static_cast<uint32_t>(kGuardRs + i * kTileM) * 16u;
-            const uint32_t a_lbo = p.desc_swap ? 128u : plane, a_sbo = p.desc_swap ? plane : 128u;
-            const uint32_t b_lbo = p.desc_swap ? 128u : 512u, b_sbo = p.desc_swap ? 512u : 128u;
-            for (int t = 0; t < L.ntaps; ++t) {
-              const int rs = stem ? L.shifts[t] - stem_min : L.shifts[t];
-              const uint32_t a_tap = a_base + static_cast<uint32_t>(rs * 16);
-              const uint32_t b_tap = w_base + L.w_off + static_cast<uint32_t>(t * L.kc) * 512u;
-              for (int kk = 0; kk < L.kc / 2; ++kk)
-                umma_bf16(d, desc_ns(a_tap + static_cast<uint32_t>(2 * kk) * plane, a_lbo, a_sbo),
-                          desc_ns(b_tap + static_cast<uint32_t>(2 * kk) * 512u, b_lbo, b_sbo), idesc, (t | kk) != 0);
+            const int rs0 = stem ? L.shifts[0] - stem_min : L.shifts[0];
+            const uint32_t a_base = (stem ? smem_u32(smem + S.buf_off[1]) + slot * S.slot_bytes
+                                          : smem_u32(smem + static_cast<uint32_t>(L.in_arr - 1) * S.buf_bytes) + static_cast<uint32_t>(kGuardRs + i * kTileM) * 16u) +
+                                    static_cast<uint32_t>(rs0 * 16);
+            const uint32_t b_base = w_base + L.w_off;
+            const uint32_t dil = L.ntaps > 1 ? static_cast<uint32_t>(L.shifts[1] - L.shifts[0]) : 0u;   // taps are equally spaced
+            // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
+            // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous
+            const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
+            const uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+            const uint32_t hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_kk = 2u * (plane >> 4);
+            if (leader) {
+              if (L.ntaps == 3 && L.kc == 4) issue_tile<3, 2>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
+              else if (L.ntaps == 7 && L.kc == 8) issue_tile<7, 4>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
+              else if (L.ntaps == 5 && L.kc == 4) issue_tile<5, 2>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
+              else {
+                for (int t = 0; t < L.ntaps; ++t)
+                  for (int kk = 0; kk < L.kc / 2; ++kk)
+                    umma_ss(d, desc_pack(a_lo + static_cast<uint32_t>(t) * dil + static_cast<uint32_t>(kk) * a_kk, hi),
+                            desc_pack(b_lo + static_cast<uint32_t>(t * (L.kc / 2) + kk) * 64u, hi), idesc, (t | kk) != 0);
+              }
+              umma_commit(ACC_FULL(i));
+              if (stem) umma_commit(OH_FREE(slot));
+              if (l == n_layers - 1 && i == n_tiles - 1) umma_commit(WIN_DONE);
             }
-            umma_commit(ACC_FULL(i));
-            if (stem) umma_commit(OH_FREE(slot));
-            if (l == n_layers - 1 && i == n_tiles - 1) umma_commit(WIN_DONE);
           }
           __syncwarp();
           if (stem) ++nstem;
@@ -358,11 +393,16 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
       int lim = lp_next < p.lc ? lp_next : p.lc;
       if (w + wstep < p.n_windows) { fetch(w + wstep); lp_next = p.lpad[w + wstep]; }
       __syncwarp();
+      bool clean = true;
       for (int r = lane; r < p.rpw; r += 32) {
         const int f = r / p.period, j = r - f * p.period;
-        const bool on = f < p.frames && j < lim && static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset >= 0;
+        const bool in = f < p.frames && j < lim;
+        const bool on = in && static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset >= 0;
         mask_t[r] = static_cast<uint8_t>(on);
+        clean = clean && (on || !in);
       }
+      clean = __all_sync(0xffffffffu, clean);
+      if (lane == 0) s_clean[it & 1u] = clean ? 1 : 0;      // published by the OH_FULL arrive of the window's first stem tile
       for (int i = 0; i < n_tiles; ++i, ++nstem) {
         const uint32_t slot = nstem & 1u;
         if (nstem >= 2u) mbar_wait(OH_FREE(slot), ((nstem >> 1) - 1u) & 1u);

@@ -815,7 +815,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
         jg::rs::LayerRs& R = m->rs_par.layer[n_prev];
         R = jg::rs::LayerRs{};
         R.ntaps = k;
-        for (int t = 0; t < k; ++t) R.shifts[t] = L.shifts_h[t];
+        for (int t = 0; t < k; ++t) { R.shifts[t] = L.shifts_h[t]; if (L.shifts_h[t] == 0) R.zero_tap = 1; }
         R.act1 = L.f[LF_ACT1]; R.act2 = L.f[LF_ACT2]; R.has_aff2 = L.f[LF_HAS_AFF2]; R.pool_mode = L.f[LF_POOL_MODE];
         R.masking = L.f[LF_MASKING]; R.folded = L.folded ? 1 : 0; R.shrink_in = L.f[LF_CUM_SHRINK_IN]; R.shrink = L.f[LF_SHRINK];
         R.kc = kc; R.w_off = static_cast<uint32_t>(off);
@@ -965,7 +965,6 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       rp.pool = m->pool; rp.pool_pitch = m->head.feat_dim;
       rp.count = m->counts + static_cast<long long>(m->final_mask) * m->cap_windows;
       rp.err = m->err;
-      rp.desc_swap = std::getenv("JG_RS_DESC_SWAP") ? 1 : 0;
       JG_CUDA(cudaFuncSetAttribute(jg::rs::stack_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (m->profiling) {
