@@ -136,6 +136,59 @@ __device__ __forceinline__ void issue_tile(uint32_t d, uint32_t a_lo, uint32_t b
   }
 }
 
+// barrier slots (8 bytes each) behind SmemRs::bar_off
+constexpr uint32_t kBarAccFull = 0, kBarTileDone = 8, kBarOhFull = 16, kBarOhFree = 18, kBarWinDone = 20;
+
+struct LayerIssue {
+  uint32_t idesc, hi, bar0, slot_step;
+  uint32_t a_lo, b_lo, dil, a_kk, d0, prev;
+  int n_tiles, ntaps, kk;
+  bool wait_prev, last;
+};
+
+// The MMA warp's work for one layer of one window: per 128-row tile the barrier waits, the tile's MMAs and the commits.
+// kT, kK > 0: taps / K-chunk pairs known at compile time (unrolled issue); 0: generic loops.
+template <int kT, int kK, bool kStem>
+__device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, uint32_t& nstem) {
+  for (int i = 0; i < I.n_tiles; ++i) {
+    // Every phase of every TILE_DONE barrier is awaited exactly once, in order (a parity wait cannot tell phase u from u + 2, so
+    // no phase may be skipped -- the stem waits for the previous window's last layer too, although it only needs it for the
+    // accumulator set it is about to overwrite).  Tile i needs tiles i-1 .. i+1 of the layer before; i-1 and i were awaited for
+    // the tiles before this one.
+    if (I.wait_prev) {
+      if (i == 0) {
+        mbar_wait(I.bar0 + (kBarTileDone + 0) * 8u, I.prev);
+        if (I.n_tiles > 1) mbar_wait(I.bar0 + (kBarTileDone + 1) * 8u, I.prev);
+      } else if (i + 1 < I.n_tiles) {
+        mbar_wait(I.bar0 + (kBarTileDone + static_cast<uint32_t>(i) + 1u) * 8u, I.prev);
+      }
+    }
+    uint32_t slot = 0;
+    if (kStem) {
+      slot = nstem & 1u;
+      mbar_wait(I.bar0 + (kBarOhFull + slot) * 8u, (nstem >> 1) & 1u);
+      ++nstem;
+    }
+    tc_fence_after();
+    const uint32_t d = I.d0 + static_cast<uint32_t>(i) * 32u;
+    const uint32_t a_lo = I.a_lo + (kStem ? slot * I.slot_step : static_cast<uint32_t>(i) * (kTileM * 16u >> 4));
+    if (leader) {
+      if (kT > 0) {
+        issue_tile<kT, kK>(d, a_lo, I.b_lo, I.dil, I.a_kk, I.hi, I.idesc);
+      } else {
+        for (int t = 0; t < I.ntaps; ++t)
+          for (int kk = 0; kk < I.kk; ++kk)
+            umma_ss(d, desc_pack(a_lo + static_cast<uint32_t>(t) * I.dil + static_cast<uint32_t>(kk) * I.a_kk, I.hi),
+                    desc_pack(I.b_lo + static_cast<uint32_t>(t * I.kk + kk) * 64u, I.hi), I.idesc, (t | kk) != 0);
+      }
+      umma_commit(I.bar0 + (kBarAccFull + static_cast<uint32_t>(i)) * 8u);
+      if (kStem) umma_commit(I.bar0 + (kBarOhFree + slot) * 8u);
+      if (I.last && i == I.n_tiles - 1) umma_commit(I.bar0 + kBarWinDone * 8u);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __grid_constant__ ResidentParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -307,65 +360,43 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
   } else if (warp == kEpiWarpsRs) {
     // ------------------------------------------------------------------ MMA issuer -------------------------------------------
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+    LayerIssue I;
+    I.idesc = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+    I.hi = (128u >> 4) | (1u << 14);
+    I.n_tiles = n_tiles;
+    I.bar0 = smem_u32(s_bar);
+    I.slot_step = S.slot_bytes >> 4;
     const uint32_t w_base = smem_u32(smem + S.w_off);
     uint32_t gl = 0, nstem = 0;
     for (long long w = w0; w < p.n_windows; w += wstep) {
       for (int l = 0; l < n_layers; ++l, ++gl) {
+        // everything that is constant over the layer's tiles is computed here, once (the per-tile code of this one warp is the
+        // serial section of the whole kernel)
         const LayerRs& L = p.layer[l];
         const bool stem = L.in_arr == 0;
-        const uint32_t prev = (gl - 1u) & 1u;
-        for (int i = 0; i < n_tiles; ++i) {
-          // Every phase of every TILE_DONE barrier is awaited exactly once, in order (a parity wait cannot tell phase u from
-          // u + 2, so no phase may be skipped -- the stem waits for the previous window's last layer too, although it only
-          // needs it for the accumulator set it is about to overwrite).  Tile i needs tiles i-1 .. i+1 of the layer before;
-          // i-1 and i were awaited for the tiles before this one.
-          if (gl > 0u) {
-            if (i == 0) {
-              mbar_wait(TILE_DONE(0), prev);
-              if (n_tiles > 1) mbar_wait(TILE_DONE(1), prev);
-            } else if (i + 1 < n_tiles) {
-              mbar_wait(TILE_DONE(i + 1), prev);
-            }
-          }
-          uint32_t slot = 0;
-          if (stem) {
-            slot = nstem & 1u;
-            mbar_wait(OH_FULL(slot), (nstem >> 1) & 1u);
-          }
-          tc_fence_after();
-          {
-            const uint32_t d = tmem + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u;
-            const uint32_t plane = stem ? S.slot_plane : S.plane_bytes;
-            const int rs0 = stem ? L.shifts[0] - stem_min : L.shifts[0];
-            const uint32_t a_base = (stem ? smem_u32(smem + S.buf_off[1]) + slot * S.slot_bytes
-                                          : smem_u32(smem + static_cast<uint32_t>(L.in_arr - 1) * S.buf_bytes) + static_cast<uint32_t>(kGuardRs + i * kTileM) * 16u) +
-                                    static_cast<uint32_t>(rs0 * 16);
-            const uint32_t b_base = w_base + L.w_off;
-            const uint32_t dil = L.ntaps > 1 ? static_cast<uint32_t>(L.shifts[1] - L.shifts[0]) : 0u;   // taps are equally spaced
-            // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
-            // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous
-            const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
-            const uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
-            const uint32_t hi = (128u >> 4) | (1u << 14);
-            const uint32_t a_kk = 2u * (plane >> 4);
-            if (leader) {
-              if (L.ntaps == 3 && L.kc == 4) issue_tile<3, 2>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
-              else if (L.ntaps == 7 && L.kc == 8) issue_tile<7, 4>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
-              else if (L.ntaps == 5 && L.kc == 4) issue_tile<5, 2>(d, a_lo, b_lo, dil, a_kk, hi, idesc);
-              else {
-                for (int t = 0; t < L.ntaps; ++t)
-                  for (int kk = 0; kk < L.kc / 2; ++kk)
-                    umma_ss(d, desc_pack(a_lo + static_cast<uint32_t>(t) * dil + static_cast<uint32_t>(kk) * a_kk, hi),
-                            desc_pack(b_lo + static_cast<uint32_t>(t * (L.kc / 2) + kk) * 64u, hi), idesc, (t | kk) != 0);
-              }
-              umma_commit(ACC_FULL(i));
-              if (stem) umma_commit(OH_FREE(slot));
-              if (l == n_layers - 1 && i == n_tiles - 1) umma_commit(WIN_DONE);
-            }
-          }
-          __syncwarp();
-          if (stem) ++nstem;
+        const uint32_t plane = stem ? S.slot_plane : S.plane_bytes;
+        const int rs0 = stem ? L.shifts[0] - stem_min : L.shifts[0];
+        const uint32_t a_base = (stem ? smem_u32(smem + S.buf_off[1]) : smem_u32(smem + static_cast<uint32_t>(L.in_arr - 1) * S.buf_bytes) + kGuardRs * 16u) +
+                                static_cast<uint32_t>(rs0 * 16);
+        // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
+        // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous
+        I.a_lo = ((a_base >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
+        I.b_lo = (((w_base + L.w_off) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+        I.dil = L.ntaps > 1 ? static_cast<uint32_t>(L.shifts[1] - L.shifts[0]) : 0u;      // taps are equally spaced
+        I.a_kk = 2u * (plane >> 4);
+        I.d0 = tmem + (gl & 1u) * 256u;
+        I.prev = (gl - 1u) & 1u;
+        I.wait_prev = gl > 0u;
+        I.last = l == n_layers - 1;
+        I.ntaps = L.ntaps;
+        I.kk = L.kc / 2;
+        if (stem) {
+          if (L.ntaps == 7 && L.kc == 8) layer_tiles<7, 4, true>(I, leader, nstem);
+          else layer_tiles<0, 0, true>(I, leader, nstem);
+        } else {
+          if (L.ntaps == 3 && L.kc == 4) layer_tiles<3, 2, false>(I, leader, nstem);
+          else if (L.ntaps == 5 && L.kc == 4) layer_tiles<5, 2, false>(I, leader, nstem);
+          else layer_tiles<0, 0, false>(I, leader, nstem);
         }
       }
     }
