@@ -58,6 +58,7 @@ struct LayerRs {
   int sc_all_valid;        // the shortcut tensor carries no mask
   int act1, act2, has_aff2, pool_mode, masking, folded;
   int shrink_in, shrink;
+  int mode;                // EpiModeRs: the compile-time epilogue shape this layer matches (0 = generic)
   int zero_tap;            // one of the taps has shift 0: in a window without masked codons every in-frame output row is then valid
   int kc;                  // input channel chunks of 8: 8 for the one-hot stem operand, 4 otherwise
   uint32_t w_off;          // byte offset of the layer's weight image in the weights block: [tap][kc][32 out channels][8] fp16
@@ -145,6 +146,145 @@ struct LayerIssue {
   int n_tiles, ntaps, kk;
   bool wait_prev, last;
 };
+
+// Epilogue shapes specialised at compile time (the runtime-flag version spends most of its issue slots on flag loads and branches):
+//   LIGHT      folded affine -> tanh-GELU -> store                        (stem, conv1 of a residual block)
+//   LIGHT_SC   folded affine -> + shortcut -> tanh-GELU -> store          (conv2 of a residual block)
+//   FINAL_SUM  folded affine -> + shortcut -> tanh-GELU -> second affine -> tanh-GELU -> masked sum pool, no store
+//   GENERIC    every feature behind its runtime flag
+enum EpiModeRs { EPI_RS_GENERIC = 0, EPI_RS_LIGHT = 1, EPI_RS_LIGHT_SC = 2, EPI_RS_FINAL_SUM = 3 };
+
+struct EpiLayer {
+  const uint8_t* par;
+  const uint8_t* mask_in;
+  uint8_t* mask_out;
+  uint8_t* out;
+  const uint8_t* scb;
+  const uint8_t* sc_mask;      // nullptr: the shortcut tensor carries no mask
+  float* pool;
+  int* count;
+  uint32_t plane_bytes, acc, parity, bar0;
+  int limit, frames, rpw, n_tiles;
+  bool slow_mask;              // masked codons in this window (or no tap at shift 0): evaluate the "any" rule per row
+};
+
+// The clean-window flag is the builder's; it is published by the barrier chain that ends in the window's first ACC_FULL, which this
+// thread has not waited for yet at the top of the stem layer -- so the stem layer waits for its first tile's accumulator here (the
+// wait is repeated, already satisfied, inside epi_layer).
+__device__ __forceinline__ bool s_clean_of(volatile int* s_clean, uint32_t itw, uint32_t bar0, int g, uint32_t gl) {
+  mbar_wait(bar0 + (kBarAccFull + static_cast<uint32_t>(g)) * 8u, gl & 1u);
+  return s_clean[itw & 1u] != 0;
+}
+
+template <int kMode>
+__device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, int g, int lane, int rw0, int fr0, int jj0, int rw1, int fr1, int jj1) {
+  constexpr bool kGen = kMode == EPI_RS_GENERIC;
+  const bool folded = kGen ? L.folded != 0 : true;
+  const bool has_sc = kGen ? L.has_sc != 0 : (kMode == EPI_RS_LIGHT_SC || kMode == EPI_RS_FINAL_SUM);
+  const bool has_aff2 = kGen ? L.has_aff2 != 0 : kMode == EPI_RS_FINAL_SUM;
+  const int pool_mode = kGen ? L.pool_mode : (kMode == EPI_RS_FINAL_SUM ? 2 : 0);
+  const bool has_out = kGen ? E.out != nullptr : kMode != EPI_RS_FINAL_SUM;
+  const int act1 = kGen ? L.act1 : ACT_GELU_TANH, act2 = kGen ? L.act2 : ACT_GELU_TANH;
+  const float4* shift1 = reinterpret_cast<const float4*>(E.par);
+  const float4* scale1 = reinterpret_cast<const float4*>(E.par + 128);
+  const uint4* scale2 = reinterpret_cast<const uint4*>(E.par + 256);
+  const uint4* shift2 = reinterpret_cast<const uint4*>(E.par + 320);
+  const uint4* scc = reinterpret_cast<const uint4*>(E.par + 384);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int i = g + 4 * h;
+    if (i >= E.n_tiles) break;
+    mbar_wait(E.bar0 + (kBarAccFull + static_cast<uint32_t>(i)) * 8u, E.parity);
+    tc_fence_after();
+    uint32_t raw[32];
+    tmem_ld32(E.acc + static_cast<uint32_t>(i) * 32u, raw);
+    const int r = h ? rw1 : rw0;
+    bool valid = (h ? fr1 : fr0) < E.frames && (h ? jj1 : jj0) < E.limit;
+    // Keras mask propagation, mode "any" (layers.py:1245-1252).  In a window without masked codons every in-frame row of every layer
+    // is valid as soon as the layer has a tap at shift 0, so the tap loop only runs for windows with N runs.
+    if (E.slow_mask) {
+      uint32_t any = 0u;
+      for (int t = 0; t < L.ntaps; ++t) any |= E.mask_in[r + L.shifts[t]];
+      valid = valid && any != 0u;
+    }
+    const uint32_t row_off = static_cast<uint32_t>(kGuardRs + r) * 16u;
+    const bool sc_valid = has_sc && (E.sc_mask == nullptr || E.sc_mask[r] != 0);
+    tmem_ld_wait();
+    tc_fence_before();
+    __half2 hv[16];
+    if (folded) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = shift1[j4];
+        hv[j4 * 2 + 0] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 0]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y);
+        hv[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 a = scale1[j4], b = shift1[j4];
+        hv[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
+        hv[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
+      }
+    }
+    if (has_sc) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 sv = sc_valid ? *reinterpret_cast<const uint4*>(E.scb + c * E.plane_bytes + row_off) : scc[c];
+        const __half2* s2 = reinterpret_cast<const __half2*>(&sv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hadd2(hv[c * 4 + k], s2[k]);
+      }
+    }
+    if (kGen) act_apply_h2(hv, act1); else act_apply_h2(hv, ACT_GELU_TANH);
+    if (has_aff2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = scale2[c], b = shift2[c];
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hfma2(hv[c * 4 + k], a2[k], b2[k]);
+      }
+      if (kGen) act_apply_h2(hv, act2); else act_apply_h2(hv, ACT_GELU_TANH);
+    }
+    if (pool_mode != 0) {
+      __half2 tv[16];
+      const bool pool_max = pool_mode == 1;
+      const uint32_t fill_bits = pool_max ? 0xFC00FC00u : 0u;
+      const __half2 fill = *reinterpret_cast<const __half2*>(&fill_bits);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tv[k] = valid ? hv[k] : fill;
+      if (pool_max) {
+        const float m = warp_cols_reduce_h2<true>(tv, lane);
+        if (m > -1.0e38f) atomic_max_f32(E.pool, m);
+      } else {
+        atomicAdd(E.pool, warp_cols_reduce_h2<false>(tv, lane));
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0 && bal) atomicAdd(E.count, __popc(bal));
+    }
+    if (has_out) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = h2u(hv[c * 4 + 0]); o.y = h2u(hv[c * 4 + 1]); o.z = h2u(hv[c * 4 + 2]); o.w = h2u(hv[c * 4 + 3]);
+        if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(E.out + c * E.plane_bytes + row_off) = o;
+      }
+      E.mask_out[r] = static_cast<uint8_t>(valid);
+      // the window's guard rows: H doubles as the staging area of the one-hot stem tiles, so they are re-zeroed by every layer
+      if (r < kGuardRs || r >= E.rpw - kGuardRs) {
+        const uint32_t goff = static_cast<uint32_t>(r < kGuardRs ? r : r + 2 * kGuardRs) * 16u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(E.out + c * E.plane_bytes + goff) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(E.bar0 + (kBarTileDone + static_cast<uint32_t>(i)) * 8u);
+  }
+}
 
 // The MMA warp's work for one layer of one window: per 128-row tile the barrier waits, the tile's MMAs and the commits.
 // kT, kK > 0: taps / K-chunk pairs known at compile time (unrolled issue); 0: generic loops.
@@ -244,116 +384,34 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     const int jj0 = rw0 - fr0 * p.period, jj1 = rw1 - fr1 * p.period;
     uint32_t gl = 0, itw = 0;
     int lp_next = w0 < p.n_windows ? p.lpad[w0] : 0;
-    for (long long w = w0; w < p.n_windows; w += wstep, ++itw) {
+    for (long long w = w0; w < p.n_windows && g < n_tiles; w += wstep, ++itw) {      // a group beyond the tile count has no rows
       const int lp = lp_next;
       if (w + wstep < p.n_windows) lp_next = p.lpad[w + wstep];
       for (int l = 0; l < n_layers; ++l, ++gl) {
         const LayerRs& L = p.layer[l];
-        const uint8_t* par = smem + S.par_off + l * kParBytesRs;
-        const float4* shift1 = reinterpret_cast<const float4*>(par);
-        const float4* scale1 = reinterpret_cast<const float4*>(par + 128);
-        const uint4* scale2 = reinterpret_cast<const uint4*>(par + 256);
-        const uint4* shift2 = reinterpret_cast<const uint4*>(par + 320);
-        const uint4* scc = reinterpret_cast<const uint4*>(par + 384);
-        const uint8_t* mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr) * S.mask_bytes + kGuardRs;
-        uint8_t* mask_out = L.out_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.out_arr) * S.mask_bytes + kGuardRs : nullptr;
-        uint8_t* out = L.out_arr ? smem + static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : nullptr;
-        const uint8_t* scb = L.sc_arr ? smem + static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : nullptr;
-        const uint8_t* sc_mask = L.sc_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.sc_arr) * S.mask_bytes + kGuardRs : nullptr;
-        const int limit = lp - L.shrink_in - L.shrink;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int i = g + 4 * h;
-          if (i >= n_tiles) break;
-          mbar_wait(ACC_FULL(i), gl & 1u);
-          tc_fence_after();
-          uint32_t raw[32];
-          tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u + static_cast<uint32_t>(i) * 32u, raw);
-          const int r = h ? rw1 : rw0;
-          bool valid = (h ? fr1 : fr0) < p.frames && (h ? jj1 : jj0) < limit;
-          // Keras mask propagation, mode "any" (layers.py:1245-1252).  In a window without masked codons (the flag is the builder's)
-          // every in-frame row of every layer is valid as soon as the layer has a tap at shift 0, so the tap loop is skipped.
-          if (L.masking && !(L.zero_tap && s_clean[itw & 1u])) {
-            uint32_t any = 0u;
-            for (int t = 0; t < L.ntaps; ++t) any |= mask_in[r + L.shifts[t]];
-            valid = valid && any != 0u;
-          }
-          const uint32_t row_off = static_cast<uint32_t>(kGuardRs + r) * 16u;
-          const bool sc_valid = L.has_sc && (L.sc_all_valid || sc_mask[r] != 0);
-          tmem_ld_wait();
-          tc_fence_before();
-          __half2 hv[16];
-          if (L.folded) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = shift1[j4];
-              hv[j4 * 2 + 0] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 0]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y);
-              hv[j4 * 2 + 1] = cvt_sat_h2(__uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
-            }
-          } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 a = scale1[j4], b = shift1[j4];
-              hv[j4 * 2 + 0] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 0]), a.x, b.x), fmaf(__uint_as_float(raw[j4 * 4 + 1]), a.y, b.y));
-              hv[j4 * 2 + 1] = cvt_sat_h2(fmaf(__uint_as_float(raw[j4 * 4 + 2]), a.z, b.z), fmaf(__uint_as_float(raw[j4 * 4 + 3]), a.w, b.w));
-            }
-          }
-          if (L.has_sc) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 sv = sc_valid ? *reinterpret_cast<const uint4*>(scb + c * S.plane_bytes + row_off) : scc[c];
-              const __half2* s2 = reinterpret_cast<const __half2*>(&sv);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hadd2(hv[c * 4 + k], s2[k]);
-            }
-          }
-          act_apply_h2(hv, L.act1);
-          if (L.has_aff2) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 a = scale2[c], b = shift2[c];
-              const __half2* a2 = reinterpret_cast<const __half2*>(&a);
-              const __half2* b2 = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hfma2(hv[c * 4 + k], a2[k], b2[k]);
-            }
-            act_apply_h2(hv, L.act2);
-          }
-          if (L.pool_mode != 0) {
-            __half2 tv[16];
-            const bool pool_max = L.pool_mode == 1;
-            const uint32_t fill_bits = pool_max ? 0xFC00FC00u : 0u;
-            const __half2 fill = *reinterpret_cast<const __half2*>(&fill_bits);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) tv[k] = valid ? hv[k] : fill;
-            if (pool_max) {
-              const float m = warp_cols_reduce_h2<true>(tv, lane);
-              if (m > -1.0e38f) atomic_max_f32(p.pool + w * p.pool_pitch + lane, m);
-            } else {
-              atomicAdd(p.pool + w * p.pool_pitch + lane, warp_cols_reduce_h2<false>(tv, lane));
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0 && bal) atomicAdd(p.count + w, __popc(bal));
-          }
-          if (out != nullptr) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 o;
-              o.x = h2u(hv[c * 4 + 0]); o.y = h2u(hv[c * 4 + 1]); o.z = h2u(hv[c * 4 + 2]); o.w = h2u(hv[c * 4 + 3]);
-              if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(out + c * S.plane_bytes + row_off) = o;
-            }
-            mask_out[r] = static_cast<uint8_t>(valid);
-            // the window's guard rows: H doubles as the staging area of the one-hot stem tiles, so they are re-zeroed by every layer
-            if (r < kGuardRs || r >= p.rpw - kGuardRs) {
-              const uint32_t goff = static_cast<uint32_t>(r < kGuardRs ? r : r + 2 * kGuardRs) * 16u;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(out + c * S.plane_bytes + goff) = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(TILE_DONE(i));
+        EpiLayer E;
+        E.par = smem + S.par_off + l * kParBytesRs;
+        E.mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr) * S.mask_bytes + kGuardRs;
+        E.mask_out = L.out_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.out_arr) * S.mask_bytes + kGuardRs : nullptr;
+        E.out = L.out_arr ? smem + static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : nullptr;
+        E.scb = L.sc_arr ? smem + static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : nullptr;
+        E.sc_mask = (L.sc_arr && !L.sc_all_valid) ? smem + S.mask_off[0] + static_cast<uint32_t>(L.sc_arr) * S.mask_bytes + kGuardRs : nullptr;
+        E.limit = lp - L.shrink_in - L.shrink;
+        E.plane_bytes = S.plane_bytes;
+        E.acc = tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u;
+        E.parity = gl & 1u;
+        E.bar0 = smem_u32(s_bar);
+        E.slow_mask = L.masking && !(L.zero_tap && s_clean_of(s_clean, itw, smem_u32(s_bar), g, gl));
+        E.pool = p.pool + w * p.pool_pitch + lane;
+        E.count = p.count + w;
+        E.frames = p.frames;
+        E.rpw = p.rpw;
+        E.n_tiles = n_tiles;
+        switch (L.mode) {
+          case EPI_RS_LIGHT: epi_layer<EPI_RS_LIGHT>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
+          case EPI_RS_LIGHT_SC: epi_layer<EPI_RS_LIGHT_SC>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
+          case EPI_RS_FINAL_SUM: epi_layer<EPI_RS_FINAL_SUM>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
+          default: epi_layer<EPI_RS_GENERIC>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
         }
       }
     }

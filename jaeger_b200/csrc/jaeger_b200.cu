@@ -288,6 +288,12 @@ int finish_resident(jg_model* m, const jg_head_desc* head) {
       mask_of[R.out_arr] = L.f[LF_MASK_OUT];
     }
     if ((L.f[LF_POOL_MODE] != 0) != (l == n - 1) || (ob < 0) != (l == n - 1)) { ok = false; break; }
+    // the compile-time epilogue shape, if the layer has one (conv_resident.cuh:EpiModeRs)
+    const bool gelu1 = R.folded && R.act1 == jg::ACT_GELU_TANH;
+    R.mode = jg::rs::EPI_RS_GENERIC;
+    if (gelu1 && !R.has_aff2 && R.pool_mode == 0 && R.out_arr != 0) R.mode = R.has_sc ? jg::rs::EPI_RS_LIGHT_SC : jg::rs::EPI_RS_LIGHT;
+    else if (gelu1 && R.has_sc && R.has_aff2 && R.act2 == jg::ACT_GELU_TANH && R.pool_mode == 2 && R.out_arr == 0) R.mode = jg::rs::EPI_RS_FINAL_SUM;
+    if (std::getenv("JG_RS_GENERIC")) R.mode = jg::rs::EPI_RS_GENERIC;
   }
   m->rs_ok = ok;
   if (!ok) { m->rs_w.clear(); m->rs_p.clear(); return 0; }
