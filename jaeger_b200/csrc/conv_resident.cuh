@@ -79,8 +79,8 @@ struct ResidentParams {
 };
 
 struct SmemRs {
-  uint32_t plane_bytes, buf_bytes, buf_off[2], w_off, par_off, mask_bytes, mask_off[3], tok_off, bar_off, total;
-  uint32_t slot_rows, slot_plane, slot_bytes;
+  uint32_t plane_bytes, buf_bytes, buf_off[2], w_off, par_off, mask_bytes, mask_off[4], tok_off, tok_bytes, bar_off, total;
+  uint32_t slot_rows, slot_plane, slot_bytes, n_slots;
 };
 
 __host__ __device__ inline SmemRs smem_rs(int rpw, int n_layers, uint32_t w_bytes, int frames, int pitch, int stem_span) {
@@ -95,12 +95,15 @@ __host__ __device__ inline SmemRs smem_rs(int rpw, int n_layers, uint32_t w_byte
   S.mask_off[0] = S.par_off + static_cast<uint32_t>(n_layers) * kParBytesRs;
   S.mask_off[1] = S.mask_off[0] + S.mask_bytes;
   S.mask_off[2] = S.mask_off[1] + S.mask_bytes;
-  S.tok_off = S.mask_off[2] + S.mask_bytes;
-  S.bar_off = S.tok_off + ((static_cast<uint32_t>(frames * pitch) + 15u) & ~15u);
+  S.mask_off[3] = S.mask_off[2] + S.mask_bytes;             // token masks are double-buffered by window parity: arrays 0 and 3
+  S.tok_off = S.mask_off[3] + S.mask_bytes;
+  S.tok_bytes = (static_cast<uint32_t>(frames * pitch) + 15u) & ~15u;
+  S.bar_off = S.tok_off + 2u * S.tok_bytes;
   S.total = S.bar_off + 256u + 128u;                       // barriers + TMEM pointer, + slack to align the base to 128 B
   S.slot_rows = static_cast<uint32_t>(128 + stem_span + 7) / 8u * 8u;
   S.slot_plane = S.slot_rows * 16u;
   S.slot_bytes = 8u * S.slot_plane;
+  S.n_slots = S.buf_bytes / S.slot_bytes >= 3u ? 3u : 2u;    // one-hot stem tiles staged in H
   return S;
 }
 
@@ -138,10 +141,10 @@ __device__ __forceinline__ void issue_tile(uint32_t d, uint32_t a_lo, uint32_t b
 }
 
 // barrier slots (8 bytes each) behind SmemRs::bar_off
-constexpr uint32_t kBarAccFull = 0, kBarTileDone = 8, kBarOhFull = 16, kBarOhFree = 18, kBarWinDone = 20;
+constexpr uint32_t kBarAccFull = 0, kBarTileDone = 8, kBarOhFull = 16, kBarOhFree = 19, kBarWinDone = 22;
 
 struct LayerIssue {
-  uint32_t idesc, hi, bar0, slot_step;
+  uint32_t idesc, hi, bar0, slot_step, n_slots;
   uint32_t a_lo, b_lo, dil, a_kk, d0, prev;
   int n_tiles, ntaps, kk;
   bool wait_prev, last;
@@ -289,7 +292,7 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
 // The MMA warp's work for one layer of one window: per 128-row tile the barrier waits, the tile's MMAs and the commits.
 // kT, kK > 0: taps / K-chunk pairs known at compile time (unrolled issue); 0: generic loops.
 template <int kT, int kK, bool kStem>
-__device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, uint32_t& nstem) {
+__device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, uint32_t& oh_slot, uint32_t& oh_phase) {
   for (int i = 0; i < I.n_tiles; ++i) {
     // Every phase of every TILE_DONE barrier is awaited exactly once, in order (a parity wait cannot tell phase u from u + 2, so
     // no phase may be skipped -- the stem waits for the previous window's last layer too, although it only needs it for the
@@ -305,9 +308,9 @@ __device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, ui
     }
     uint32_t slot = 0;
     if (kStem) {
-      slot = nstem & 1u;
-      mbar_wait(I.bar0 + (kBarOhFull + slot) * 8u, (nstem >> 1) & 1u);
-      ++nstem;
+      slot = oh_slot;
+      mbar_wait(I.bar0 + (kBarOhFull + slot) * 8u, oh_phase);
+      if (++oh_slot == I.n_slots) { oh_slot = 0; oh_phase ^= 1u; }
     }
     tc_fence_after();
     const uint32_t d = I.d0 + static_cast<uint32_t>(i) * 32u;
@@ -346,13 +349,13 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
   volatile int* s_clean = reinterpret_cast<volatile int*>(s_bar + 25);   // [2], by window parity: no in-frame codon of the window is masked
   auto ACC_FULL = [&](int i) { return smem_u32(s_bar + i); };
   auto TILE_DONE = [&](int i) { return smem_u32(s_bar + 8 + i); };
-  auto OH_FULL = [&](int s) { return smem_u32(s_bar + 16 + s); };
-  auto OH_FREE = [&](int s) { return smem_u32(s_bar + 18 + s); };
-  const uint32_t WIN_DONE = smem_u32(s_bar + 20);
+  auto OH_FULL = [&](int s) { return smem_u32(s_bar + kBarOhFull + s); };
+  auto OH_FREE = [&](int s) { return smem_u32(s_bar + kBarOhFree + s); };
+  const uint32_t WIN_DONE = smem_u32(s_bar + kBarWinDone);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxTilesRs; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(TILE_DONE(i), 4); }
-    for (int s = 0; s < 2; ++s) { mbar_init(OH_FULL(s), 1); mbar_init(OH_FREE(s), 1); }
+    for (int s = 0; s < 3; ++s) { mbar_init(OH_FULL(s), 1); mbar_init(OH_FREE(s), 1); }
     mbar_init(WIN_DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (uint32_t i = threadIdx.x; i < 2u * S.buf_bytes / 16u; i += kThreadsRs) z[i] = make_uint4(0u, 0u, 0u, 0u);
     uint4* mz = reinterpret_cast<uint4*>(smem + S.mask_off[0]);
-    for (uint32_t i = threadIdx.x; i < 3u * S.mask_bytes / 16u; i += kThreadsRs) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < 4u * S.mask_bytes / 16u; i += kThreadsRs) mz[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint4* src = reinterpret_cast<const uint4*>(p.wblock);
     uint4* wd = reinterpret_cast<uint4*>(smem + S.w_off);
     for (uint32_t i = threadIdx.x; i < p.w_bytes / 16u; i += kThreadsRs) wd[i] = src[i];
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         const LayerRs& L = p.layer[l];
         EpiLayer E;
         E.par = smem + S.par_off + l * kParBytesRs;
-        E.mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr) * S.mask_bytes + kGuardRs;
+        E.mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr ? L.in_arr : (itw & 1u) * 3u) * S.mask_bytes + kGuardRs;
         E.mask_out = L.out_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.out_arr) * S.mask_bytes + kGuardRs : nullptr;
         E.out = L.out_arr ? smem + static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : nullptr;
         E.scb = L.sc_arr ? smem + static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : nullptr;
@@ -424,8 +427,9 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     I.n_tiles = n_tiles;
     I.bar0 = smem_u32(s_bar);
     I.slot_step = S.slot_bytes >> 4;
+    I.n_slots = S.n_slots;
     const uint32_t w_base = smem_u32(smem + S.w_off);
-    uint32_t gl = 0, nstem = 0;
+    uint32_t gl = 0, oh_slot = 0, oh_phase = 0;
     for (long long w = w0; w < p.n_windows; w += wstep) {
       for (int l = 0; l < n_layers; ++l, ++gl) {
         // everything that is constant over the layer's tiles is computed here, once (the per-tile code of this one warp is the
@@ -449,12 +453,12 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         I.ntaps = L.ntaps;
         I.kk = L.kc / 2;
         if (stem) {
-          if (L.ntaps == 7 && L.kc == 8) layer_tiles<7, 4, true>(I, leader, nstem);
-          else layer_tiles<0, 0, true>(I, leader, nstem);
+          if (L.ntaps == 7 && L.kc == 8) layer_tiles<7, 4, true>(I, leader, oh_slot, oh_phase);
+          else layer_tiles<0, 0, true>(I, leader, oh_slot, oh_phase);
         } else {
-          if (L.ntaps == 3 && L.kc == 4) layer_tiles<3, 2, false>(I, leader, nstem);
-          else if (L.ntaps == 5 && L.kc == 4) layer_tiles<5, 2, false>(I, leader, nstem);
-          else layer_tiles<0, 0, false>(I, leader, nstem);
+          if (L.ntaps == 3 && L.kc == 4) layer_tiles<3, 2, false>(I, leader, oh_slot, oh_phase);
+          else if (L.ntaps == 5 && L.kc == 4) layer_tiles<5, 2, false>(I, leader, oh_slot, oh_phase);
+          else layer_tiles<0, 0, false>(I, leader, oh_slot, oh_phase);
         }
       }
     }
@@ -467,54 +471,73 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
 #pragma unroll
       for (int u = 0; u < kTokWordsRs; ++u) tk[u] = (u * 32 + lane < n_words) ? src[u * 32 + lane] : 0u;
     };
-    if (w0 < p.n_windows) fetch(w0);
-    uint8_t* tok = smem + S.tok_off;
-    uint8_t* mask_t = smem + S.mask_off[0] + kGuardRs;
-    uint8_t* stage = smem + S.buf_off[1];
-    uint32_t nstem = 0, it = 0;
-    int lp_next = w0 < p.n_windows ? p.lpad[w0] : 0;
-    for (long long w = w0; w < p.n_windows; w += wstep, ++it) {
-      // the previous window's last MMAs (the last readers of H) and, transitively, every reader of the token mask are done
-      if (it > 0) mbar_wait(WIN_DONE, (it - 1u) & 1u);
+    // tokens (from the prefetch registers) + token mask + clean flag of window number `itp` into the buffers of its parity; runs
+    // while the window before it is still in its conv layers, so only the one-hot tiles are built after WIN_DONE
+    auto prepare = [&](uint32_t itp, int lim) {
+      uint8_t* tok = smem + S.tok_off + (itp & 1u) * S.tok_bytes;
+      uint8_t* mask_t = smem + S.mask_off[0] + (itp & 1u) * 3u * S.mask_bytes + kGuardRs;
 #pragma unroll
       for (int u = 0; u < kTokWordsRs; ++u)
         if (u * 32 + lane < n_words) reinterpret_cast<uint32_t*>(tok)[u * 32 + lane] = tk[u];
-      int lim = lp_next < p.lc ? lp_next : p.lc;
-      if (w + wstep < p.n_windows) { fetch(w + wstep); lp_next = p.lpad[w + wstep]; }
       __syncwarp();
       bool clean = true;
+      int f = lane / p.period, j = lane - f * p.period;
       for (int r = lane; r < p.rpw; r += 32) {
-        const int f = r / p.period, j = r - f * p.period;
         const bool in = f < p.frames && j < lim;
         const bool on = in && static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset >= 0;
         mask_t[r] = static_cast<uint8_t>(on);
         clean = clean && (on || !in);
+        j += 32;
+        while (j >= p.period) { j -= p.period; ++f; }
       }
       clean = __all_sync(0xffffffffu, clean);
-      if (lane == 0) s_clean[it & 1u] = clean ? 1 : 0;      // published by the OH_FULL arrive of the window's first stem tile
-      for (int i = 0; i < n_tiles; ++i, ++nstem) {
-        const uint32_t slot = nstem & 1u;
-        if (nstem >= 2u) mbar_wait(OH_FREE(slot), ((nstem >> 1) - 1u) & 1u);
+      if (lane == 0) s_clean[itp & 1u] = clean ? 1 : 0;     // published by the OH_FULL arrive of the window's first stem tile
+    };
+    uint8_t* stage = smem + S.buf_off[1];
+    uint32_t it = 0, slot = 0, sphase = 0;
+    bool first_lap = true;
+    int lim_next = 0;
+    if (w0 < p.n_windows) {
+      fetch(w0);
+      const int lp0 = p.lpad[w0];
+      lim_next = lp0 < p.lc ? lp0 : p.lc;
+      prepare(0u, lim_next);
+      if (w0 + wstep < p.n_windows) fetch(w0 + wstep);
+    }
+    for (long long w = w0; w < p.n_windows; w += wstep, ++it) {
+      const int lim = lim_next;
+      const uint8_t* tok = smem + S.tok_off + (it & 1u) * S.tok_bytes;
+      // the previous window's last MMAs (the last readers of H, where the one-hot tiles are staged) are done
+      if (it > 0) mbar_wait(WIN_DONE, (it - 1u) & 1u);
+      for (int i = 0; i < n_tiles; ++i) {
+        if (!first_lap) mbar_wait(OH_FREE(slot), sphase ^ 1u);
         uint8_t* sl = stage + slot * S.slot_bytes;
-        for (int s = lane; s < static_cast<int>(S.slot_rows); s += 32) {
-          const int r = i * kTileM + stem_min + s;
+        int r = i * kTileM + stem_min + lane;
+        int f = r >= 0 ? r / p.period : 0, j = r >= 0 ? r - f * p.period : r;      // j < 0: a row before the window
+        for (int sr = lane; sr < static_cast<int>(S.slot_rows); sr += 32) {
           int ch = -1;
-          if (r >= 0 && r < p.rpw) {
-            const int f = r / p.period, j = r - f * p.period;
-            if (f < p.frames && j < lim) ch = static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset;
-          }
+          if (j >= 0 && r < p.rpw && f < p.frames && j < lim) ch = static_cast<int>(tok[f * p.pitch + j]) - p.tok_offset;
           const uint32_t one = ch >= 0 ? (0x3C00u << (16 * (ch & 1))) : 0u;      // fp16 1.0 in the channel's half of its word
           const int word = ch >= 0 ? (ch & 7) >> 1 : -1, chunk = ch >= 0 ? ch >> 3 : -1;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (c == chunk) { o.x = word == 0 ? one : 0u; o.y = word == 1 ? one : 0u; o.z = word == 2 ? one : 0u; o.w = word == 3 ? one : 0u; }
-            *reinterpret_cast<uint4*>(sl + c * S.slot_plane + s * 16) = o;
+            *reinterpret_cast<uint4*>(sl + c * S.slot_plane + sr * 16) = o;
           }
+          r += 32; j += 32;
+          while (j >= p.period) { j -= p.period; ++f; }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(OH_FULL(slot));
+        if (++slot == S.n_slots) { slot = 0; sphase ^= 1u; first_lap = false; }
+      }
+      if (w + wstep < p.n_windows) {       // the next window's tokens, mask and flag, while this one runs through its layers
+        const int lpn = p.lpad[w + wstep];
+        lim_next = lpn < p.lc ? lpn : p.lc;
+        prepare(it + 1u, lim_next);
+        if (w + 2 * wstep < p.n_windows) fetch(w + 2 * wstep);
       }
     }
   }
