@@ -62,7 +62,12 @@ struct LayerRs {
   int zero_tap;            // one of the taps has shift 0: in a window without masked codons every in-frame output row is then valid
   int kc;                  // input channel chunks of 8: 8 for the one-hot stem operand, 4 otherwise
   uint32_t w_off;          // byte offset of the layer's weight image in the weights block: [tap][kc][32 out channels][8] fp16
+  // byte offsets from the (aligned) shared-memory base, filled by the launcher from smem_rs() so that the epilogue warps' per-layer
+  // setup is a handful of independent constant loads; kNoneRs = absent.  e_mask_in of the stem is that of even windows
+  // (odd windows: + 3 mask arrays).
+  uint32_t e_par, e_mask_in, e_mask_out, e_out, e_sc, e_sc_mask;
 };
+constexpr uint32_t kNoneRs = 0xFFFFFFFFu;
 
 struct ResidentParams {
   const uint8_t* tokens;   // [n_windows][frames][pitch]
@@ -105,6 +110,20 @@ __host__ __device__ inline SmemRs smem_rs(int rpw, int n_layers, uint32_t w_byte
   S.slot_bytes = 8u * S.slot_plane;
   S.n_slots = S.buf_bytes / S.slot_bytes >= 3u ? 3u : 2u;    // one-hot stem tiles staged in H
   return S;
+}
+
+// The launcher's half of the per-layer setup: shared-memory byte offsets of everything a layer's epilogue touches.
+inline void fill_layer_offsets(ResidentParams& p, const SmemRs& S) {
+  for (int l = 0; l < p.n_layers; ++l) {
+    LayerRs& L = p.layer[l];
+    auto mask = [&](int arr) { return S.mask_off[0] + static_cast<uint32_t>(arr) * S.mask_bytes + kGuardRs; };
+    L.e_par = S.par_off + static_cast<uint32_t>(l) * kParBytesRs;
+    L.e_mask_in = mask(L.in_arr);
+    L.e_mask_out = L.out_arr ? mask(L.out_arr) : kNoneRs;
+    L.e_out = L.out_arr ? static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : kNoneRs;
+    L.e_sc = L.sc_arr ? static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : kNoneRs;
+    L.e_sc_mask = (L.sc_arr && !L.sc_all_valid) ? mask(L.sc_arr) : kNoneRs;
+  }
 }
 
 // K-major no-swizzle matrix descriptor (cute/arch/mma_sm100_desc.hpp; canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units)
@@ -393,12 +412,12 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
       for (int l = 0; l < n_layers; ++l, ++gl) {
         const LayerRs& L = p.layer[l];
         EpiLayer E;
-        E.par = smem + S.par_off + l * kParBytesRs;
-        E.mask_in = smem + S.mask_off[0] + static_cast<uint32_t>(L.in_arr ? L.in_arr : (itw & 1u) * 3u) * S.mask_bytes + kGuardRs;
-        E.mask_out = L.out_arr ? smem + S.mask_off[0] + static_cast<uint32_t>(L.out_arr) * S.mask_bytes + kGuardRs : nullptr;
-        E.out = L.out_arr ? smem + static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : nullptr;
-        E.scb = L.sc_arr ? smem + static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : nullptr;
-        E.sc_mask = (L.sc_arr && !L.sc_all_valid) ? smem + S.mask_off[0] + static_cast<uint32_t>(L.sc_arr) * S.mask_bytes + kGuardRs : nullptr;
+        E.par = smem + L.e_par;
+        E.mask_in = smem + L.e_mask_in + ((l == 0 && (itw & 1u)) ? 3u * S.mask_bytes : 0u);
+        E.mask_out = L.e_mask_out != kNoneRs ? smem + L.e_mask_out : nullptr;
+        E.out = L.e_out != kNoneRs ? smem + L.e_out : nullptr;
+        E.scb = L.e_sc != kNoneRs ? smem + L.e_sc : nullptr;
+        E.sc_mask = L.e_sc_mask != kNoneRs ? smem + L.e_sc_mask : nullptr;
         E.limit = lp - L.shrink_in - L.shrink;
         E.plane_bytes = S.plane_bytes;
         E.acc = tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u;

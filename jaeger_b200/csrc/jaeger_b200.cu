@@ -971,6 +971,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       rp.pool = m->pool; rp.pool_pitch = m->head.feat_dim;
       rp.count = m->counts + static_cast<long long>(m->final_mask) * m->cap_windows;
       rp.err = m->err;
+      jg::rs::fill_layer_offsets(rp, S);
       JG_CUDA(cudaFuncSetAttribute(jg::rs::stack_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (m->profiling) {
