@@ -459,8 +459,16 @@ def roofline(eng, wl: Workload, prof, ms: float, tot_windows: float, world: int)
             flop += 2.0 * 6 * l_out * k * c.real_cin * c.real_cout
         tflops = flop * windows / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
         byts = (6.0 * ((lc + 3) // 4 * 4) + 4.0 * plan.real_feat_dim) * windows
+        traffic = None
+        summ = ROOT / "profiles" / f"ncu_summary_r2_config{wl.cfg}.json"
+        if summ.exists():
+            try:
+                per_window = json.loads(summ.read_text()).get("dram_bytes_per_window")
+                traffic = per_window * windows / n_launch if per_window else None
+            except Exception:
+                traffic = None
         return {"bound": "tensor", "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["tflops"],
-                "kernel": eng.conv_kernel_names(), "traffic": None, "peak_source": peaks["source"],
+                "kernel": eng.conv_kernel_names(), "traffic": traffic, "peak_source": peaks["source"],
                 "avg_launch_ms": ms_k / n_launch, "kernel_share_of_step": conv_ms_total / ms,
                 "algorithmic_flop_per_launch": flop * windows / n_launch, "algorithmic_bytes_per_launch": byts / n_launch,
                 "hbm_gbs_algorithmic": byts / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0, "hbm_peak_gbs": peaks["hbm_gbs"],
