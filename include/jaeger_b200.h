@@ -138,7 +138,9 @@ int jg_encode_windows(jg_ctx* ctx, const uint32_t* d_codes, const uint32_t* d_va
  * activation 1 -> [NMD tap] -> [norm 2 -> activation 2] -> [masked global pool]; a norm is a
  * per-channel affine (MaskedBatchNorm folded, nnlib/v2/layers.py:918-941) or, with i[22] / i[23] set,
  * a MaskedDYT (layers.py:385-444): gamma * tanh(scale * x + shift) + beta with gamma / beta in
- * p[8..11].  i[26] / i[27]: the layer's channel counts before the plan padded them to multiples of 64 (0 = not given).  A model
+ * p[8..11].  i[28] != 0: the first norm is a MaskedLayerNormalization (layers.py:293-367) -- p[2] = gamma, p[3] = beta, p[1] the conv
+ * bias (kept apart), i[29] = epsilon as float bits, statistics over the i[27] real channels.  i[30]: valid taps an output row needs
+ * under mask propagation (layers.py:1245-1252): 0 / 1 "any", (k + 1) / 2 "majority", k "strict".  i[26] / i[27]: the layer's channel counts before the plan padded them to multiples of 64 (0 = not given).  A model
  * whose conv stack is at most 32 channels wide everywhere (BASELINE config 3) runs as ONE kernel that keeps each window in shared
  * memory through all layers (csrc/conv_resident.cuh); JG_RESIDENT=0 in the environment keeps the per-layer kernels. */
 #define JG_LAYER_INT_FIELDS 32

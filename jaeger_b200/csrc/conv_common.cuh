@@ -81,6 +81,11 @@ struct ConvParams {
   int epi_f32;             // generic epilogue entirely in fp32 with ONE rounding at the store (conv_epilogue.cuh): for graphs
                            // whose norm FOLLOWS the activation with a large scale (the legacy `default` model: BatchNorm after
                            // GELU with gamma / sigma up to 26), where a half-precision activation would be amplified
+  int mask_thr;            // valid taps an output row needs under mask propagation: <= 1 "any", (k + 1) / 2 "majority", k "strict"
+                           // (layers.py:1245-1252); honoured by the single-CTA / CTA-pair kernels and the CUDA-core path
+  int ln1;                 // the first norm is a MaskedLayerNormalization (layers.py:337-367): per ROW, v = acc + bias is normalised over
+                           // the layer's real channels, then scale1 (gamma) / shift1 (beta); single-CTA kernel, generic epilogue only
+  float ln_eps, ln_inv_c;  // its epsilon and 1 / (real channel count): padded channels carry acc = bias = gamma = beta = 0
   int* err;                     // device int, set non-zero on a barrier time-out
   long long* dbg;               // optional per-tile clock64 trace of CTA 0 (probe only)
 };

@@ -169,7 +169,7 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) any[c] |= m[c][u];
+          for (int c = 0; c < 4; ++c) any[c] += m[c][u];         // mask bytes are 0 / 1: the number of valid taps
       }
     }
   } else {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void tile_validity(const ConvParams& p, long long til
     if (p.fuse_mask) {
       const int rw = static_cast<int>(row - static_cast<long long>(win) * p.rows_per_window);
       const int f = rw / p.period, j = rw - f * p.period;
-      ok = f < p.frames && j < limit && (!p.masking || any[c] != 0u);
+      ok = f < p.frames && j < limit && (!p.masking || any[c] >= static_cast<uint32_t>(p.mask_thr > 1 ? p.mask_thr : 1));
       p.out_mask_w[row] = static_cast<uint8_t>(ok);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
       if (lane == 0 && bal) atomicAdd(p.count + win, __popc(bal));
@@ -312,7 +312,7 @@ struct EpiTag { static constexpr int kMode = kMode_; static constexpr bool kD1 =
 template <int kMode = EPI_GENERIC, bool kD1 = false, bool kD2 = false>
 __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiParams& e, int cb, const uint32_t (&raw)[32],
                                                const uint4 (&scc)[4], bool has_sc, bool sc_valid, bool valid, int lane,
-                                               int win, uint4 (&out)[4]) {
+                                               int win, uint4 (&out)[4], float ln_mu = 0.0f, float ln_rs = 1.0f) {
   constexpr bool kGen = kMode == EPI_GENERIC, kFinal = kMode == EPI_FINAL || kMode == EPI_FINAL_POOL;
   if (kGen && p.epi_f32) {
     epilogue_batch_f32(p, reinterpret_cast<const float*>(e.scale1), cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
@@ -332,7 +332,16 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const EpiPar
     atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + cb * 32 + lane, tv[0]);
   }
   __half2 h[16];
-  if (kGen) {
+  if (kGen && p.ln1) {       // MaskedLayerNormalization: (acc + bias - mean) / sqrt(var + eps) * gamma + beta, row statistics from the caller
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 a = e.scale1[cb * 8 + j4], b = e.shift1[cb * 8 + j4], c = e.bias[cb * 8 + j4];
+      h[j4 * 2 + 0] = cvt_sat_h2(fmaf((__uint_as_float(raw[j4 * 4 + 0]) + c.x - ln_mu) * ln_rs, a.x, b.x),
+                                 fmaf((__uint_as_float(raw[j4 * 4 + 1]) + c.y - ln_mu) * ln_rs, a.y, b.y));
+      h[j4 * 2 + 1] = cvt_sat_h2(fmaf((__uint_as_float(raw[j4 * 4 + 2]) + c.z - ln_mu) * ln_rs, a.z, b.z),
+                                 fmaf((__uint_as_float(raw[j4 * 4 + 3]) + c.w - ln_mu) * ln_rs, a.w, b.w));
+    }
+  } else if (kGen) {
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
       const float4 a = e.scale1[cb * 8 + j4], b = e.shift1[cb * 8 + j4];

@@ -69,6 +69,8 @@ inline cudaError_t launch_conv_tc2(const ConvParams& p, int num_sms, cudaStream_
 // Weights-stationary kernel (conv_ws.cuh): 128 output channels, weights within 320 TMEM columns, and one of the epilogue
 // shapes it is specialised for.  Returns the ws::WsMode, or -1 when the layer has to run on another kernel.
 inline int conv_ws_mode(const ConvParams& p) {
+  if (p.ln1) return -1;      // MaskedLayerNormalization runs on the single-CTA kernel's generic epilogue
+  if (p.mask_thr > 1) return -1;      // mask modes strict / majority: the round-1 kernels' validity helper counts the taps
   if (p.cout != 128 || (p.cin != 64 && p.cin != 128) || p.ntaps * p.cin / 2 > ws::kWColsMax || p.ntaps > kMaxTaps) return -1;
   if (!p.folded || p.dyt1 || p.dyt2 || p.act1 != ACT_GELU_TANH || p.rows_per_window % ws::kSubRows != 0 || p.n_tiles < 1) return -1;
   if (p.halo_l > 56 || p.halo_r > 56) return -1;

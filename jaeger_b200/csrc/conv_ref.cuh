@@ -28,6 +28,23 @@ __global__ void conv_ref_kernel(const ConvParams p) {
     if (p.tap_mode == 1 && valid)
       atomicAdd(p.tap_sum + static_cast<long long>(win) * red_pitch_of(p) + co, acc + p.bias[co]);
     float v = fmaf(acc, p.scale1[co], p.shift1[co]);
+    if (p.ln1) {      // MaskedLayerNormalization: the row's channel statistics, recomputed by every thread of the row (test path only)
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int c2 = 0; c2 < p.cout; ++c2) {
+        float a2 = 0.0f;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const long long r = row + p.shifts[t];
+          for (int ci = 0; ci < p.cin; ++ci)
+            a2 = fmaf(__half2float(p.x[act_index(r, ci, p.x_plane)]), __half2float(p.w[w_index(t, ci, c2, p.cin, p.cout)]), a2);
+        }
+        a2 += p.bias[c2];
+        s1 += a2;
+        s2 = fmaf(a2, a2, s2);
+      }
+      const float mu = s1 * p.ln_inv_c;
+      const float rs = 1.0f / sqrtf(fmaxf(s2 * p.ln_inv_c - mu * mu, 0.0f) + p.ln_eps);
+      v = fmaf((acc + p.bias[co] - mu) * rs, p.scale1[co], p.shift1[co]);
+    }
     if (p.dyt1) v = fmaf(tanhf(v), p.dyt_g1[co], p.dyt_b1[co]);
     if (p.sc) {
       const bool scv = p.sc_mask ? p.sc_mask[row] != 0 : true;

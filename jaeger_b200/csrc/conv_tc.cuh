@@ -369,6 +369,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0) p.dbg[524 + grp] += clock64() - tw3;   // epilogue group: wait for MMAs
       if (p.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
+      float ln_mu = 0.0f, ln_rs = 1.0f;
+      if (p.ln1) {     // MaskedLayerNormalization: a first pass over the row's accumulators for the channel mean / variance
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int cb = 0; cb < n_cb; ++cb) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.cout + cb * 32), raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c = ep.bias[cb * 8 + j4];
+            const float v0 = __uint_as_float(raw[j4 * 4 + 0]) + c.x, v1 = __uint_as_float(raw[j4 * 4 + 1]) + c.y;
+            const float v2 = __uint_as_float(raw[j4 * 4 + 2]) + c.z, v3 = __uint_as_float(raw[j4 * 4 + 3]) + c.w;
+            s1 += (v0 + v1) + (v2 + v3);
+            s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
+          }
+        }
+        ln_mu = s1 * p.ln_inv_c;
+        const float var = fmaxf(s2 * p.ln_inv_c - ln_mu * ln_mu, 0.0f);
+        ln_rs = 1.0f / sqrtf(var + p.ln_eps);
+      }
       for (int cb = 0; cb < n_cb; ++cb) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_arrive(TEMPTY(as));
         }
         uint4 out[4];
-        epilogue_batch(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out);
+        epilogue_batch(p, ep, cb, raw, scc, has_sc, sc_valid, valid, lane, win, out, ln_mu, ln_rs);
         if (p.y) {
           act_t* yrow = p.y + (static_cast<long long>(cb >> 1) * p.y_plane + row) * 64;
 #pragma unroll

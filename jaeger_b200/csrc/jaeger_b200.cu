@@ -67,7 +67,10 @@ enum LayerField {
   LF_KIND = 0, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF,
   LF_SC_BUF, LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN,
   LF_MASK_OUT, LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL,
-  LF_REAL_CIN, LF_REAL_COUT      // channel counts before the plan's padding to 64 (0 = not given)
+  LF_REAL_CIN, LF_REAL_COUT,     // channel counts before the plan's padding to 64 (0 = not given)
+  LF_LN1, LF_LN_EPS,             // the first norm is a MaskedLayerNormalization (scale1 = gamma, shift1 = beta, bias kept apart); its
+                                 // epsilon as float bits
+  LF_MASK_THR                    // valid taps an output row needs: 0 / 1 "any", (k + 1) / 2 "majority", k "strict" (layers.py:1245-1252)
 };
 // layer kinds: 1 = conv (fused epilogue), 2 = MaxPooling1D(2) per frame, 3 = frame sum + global max pool
 enum LayerPtr { LP_KERNEL = 0, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
@@ -731,7 +734,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
     // the epilogue adds the shift only.  Not for a layer whose NMD tap reads the raw conv output in the
     // epilogue (tap mode 1 without the linear stem tap): that needs the unscaled accumulator.
     const bool linear_tap_layer = l == 0 && L.f[LF_TAP_MODE] == 1 && cin == 64;
-    L.folded = (L.f[LF_TAP_MODE] != 1 || linear_tap_layer) && layers[l].p[LP_SCALE1] != nullptr && !std::getenv("JG_NO_BN_FOLD");
+    L.folded = (L.f[LF_TAP_MODE] != 1 || linear_tap_layer) && layers[l].p[LP_SCALE1] != nullptr && !L.f[LF_LN1] && !std::getenv("JG_NO_BN_FOLD");
     const float* wk_raw = wk;
     const float* wk_odd = layers[l].p[LP_KERNEL_ODD];
     std::vector<float> wfold, wfold_odd;
@@ -796,7 +799,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
       const bool stem = n_prev == 0;
       bool ok = m->rs_ok && n_prev < jg::rs::kMaxLayersRs && cout == 64 && rcout <= 32 && k <= jg::rs::kMaxTapsRs &&
                 (stem ? (cin == 64 && L.f[LF_IN_BUF] == 0) : (cin == 64 && rcin <= 32)) && L.f[LF_TAP_MODE] == 0 && L.f[LF_DYT1] == 0 &&
-                L.f[LF_DYT2] == 0 && L.f[LF_EPI_F32] == 0 && L.f[LF_HALVINGS] == 0 && L.f[LF_LEN_CEIL] == 0 && wk_odd == nullptr &&
+                L.f[LF_DYT2] == 0 && L.f[LF_LN1] == 0 && L.f[LF_MASK_THR] <= 1 && L.f[LF_EPI_F32] == 0 && L.f[LF_HALVINGS] == 0 && L.f[LF_LEN_CEIL] == 0 && wk_odd == nullptr &&
                 L.f[LF_ACT1] <= 2 && L.f[LF_ACT2] <= 2 && (stem || (L.halo_l <= jg::rs::kGuardRs && L.halo_r <= jg::rs::kGuardRs));
       if (ok) {
         const int kc = stem ? 8 : 4;
@@ -1050,7 +1053,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
     if (layer_ref) {   // the CUDA-core path keeps the stand-alone mask kernel
       jg::propagate_mask_kernel<<<grid_for(rows, 256, ctx->num_sms, 16), 256, 0, st>>>(
           mask_row0(L.f[LF_MASK_IN]), d_lpad, rows, geom, L.f[LF_CUM_SHRINK_IN], L.f[LF_HALVINGS], len_round_of(L), L.f[LF_SHRINK], L.f[LF_K],
-          L.shifts, L.f[LF_MASKING], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
+          L.shifts, L.f[LF_MASKING], L.f[LF_MASK_THR], mask_row0(L.f[LF_MASK_OUT]), m->counts + static_cast<long long>(L.f[LF_MASK_OUT]) * m->cap_windows);
       ctx->launches++;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1105,6 +1108,13 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       p.fuse_mask = (layer_ref || sl > 0) ? 0 : 1;
       p.folded = L.folded ? 1 : 0;
       p.epi_f32 = L.f[LF_EPI_F32];
+      p.ln1 = L.f[LF_LN1];
+      p.mask_thr = L.f[LF_MASK_THR];
+      if (p.ln1) {
+        std::memcpy(&p.ln_eps, &L.f[LF_LN_EPS], 4);
+        p.ln_inv_c = 1.0f / static_cast<float>(L.f[LF_REAL_COUT] > 0 ? L.f[LF_REAL_COUT] : cout);
+        if (L.slice_width || (!layer_ref && !fits_tc)) return fail("MaskedLayerNormalization needs a layer that fits the single-CTA tensor-core kernel");
+      }
       p.in_mask = mask_row0(L.f[LF_MASK_IN]);
       p.out_mask_w = mask_row0(L.f[LF_MASK_OUT]);
       p.lpad = d_lpad;
@@ -1125,7 +1135,7 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       const bool heavy = p.tap_mode != 0 || p.has_affine2 != 0 || p.pool_mode != 0;
       const bool pair3 = !layer_ref && heavy && p.cin >= 128 && (m->conv_impl == 0 || m->conv_impl == 3) &&
                          jg::conv_tc2_eligible(p, 3);                                       // pair kernel, 3 epilogue groups
-      const bool pair = pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy))));
+      const bool pair = !p.ln1 && (pair3 || (!layer_ref && fits_tc2 && (!fits_tc || (m->conv_impl != 1 && (m->conv_impl == 2 || !heavy)))));
       if (pair) p.w = L.slice_width ? L.slices[par][sl].w2 : img_w2;
       // 128-output-channel layers with one of the specialised epilogue shapes: the weights-stationary kernel (weights resident in
       // tensor memory, transposed accumulators; profiles/conv_kernel_r2.md).  JG_CONV_IMPL=1|2|3 keeps the round-1 kernels.

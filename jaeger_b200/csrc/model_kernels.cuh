@@ -64,7 +64,7 @@ __global__ void expand_tokens_kernel(const uint8_t* __restrict__ tokens, const i
 // valid rows that the NMD taps and the pooling need.
 __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const int* __restrict__ lpad,
                                       long long n_rows, RowGeom g, int shrink_in, int halvings, int len_round, int shrink,
-                                      int ntaps, const int* __restrict__ shifts, int masking,
+                                      int ntaps, const int* __restrict__ shifts, int masking, int mask_thr,
                                       uint8_t* __restrict__ out_mask, int* __restrict__ count) {
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
        row += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -74,8 +74,8 @@ __global__ void propagate_mask_kernel(const uint8_t* __restrict__ in_mask, const
     int ok = (f < g.frames) && (j < ((lpad[w] - shrink_in + len_round) >> halvings) - shrink);
     if (ok && masking) {
       int any = 0;
-      for (int t = 0; t < ntaps; ++t) any |= in_mask[row + shifts[t]];
-      ok = any;
+      for (int t = 0; t < ntaps; ++t) any += in_mask[row + shifts[t]];
+      ok = any >= (mask_thr > 1 ? mask_thr : 1);
     }
     out_mask[row] = static_cast<uint8_t>(ok);
     // warp-aggregated count (rows of a warp almost always share the window)

@@ -92,10 +92,11 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
         if name == "masked_conv1d":
             if int(c.get("strides", 1)) != 1:
                 raise NotImplementedError("strided convolutions are not supported")
-            mode = c.get("mask_mode", "any")
-            if c.get("use_masking", use_masking) and mode != "any":
-                raise NotImplementedError(f"mask_mode={mode!r}: only 'any' (the default) is supported")
+            mode = str(c.get("mask_mode", "any")).lower()
+            if mode not in ("any", "majority", "strict"):
+                raise ValueError(f"Invalid mask_mode: {mode!r} (use 'any', 'majority' or 'strict')")       # layers.py:1170-1173
             layers.append(LayerSpec("conv", dict(
+                mask_mode=mode,
                 filters=int(c["filters"]), kernel_size=int(c["kernel_size"]),
                 dilation=int(c.get("dilation_rate", 1)), padding=str(c.get("padding", "valid")).lower(),
                 use_bias=bool(c.get("use_bias", True)), activation=_act_name(c),
@@ -113,6 +114,11 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
             if c.get("return_nmd"):
                 raise NotImplementedError("masked_dyt(return_nmd=True) is rejected by the reference as well")
             layers.append(LayerSpec("norm", dict(type="dyt", alpha_init=float(c.get("alpha_init", 0.5)))))
+        elif name == "masked_layernorm":    # nnlib/v2/layers.py:293-367: per-position normalisation over the channels, re-masked
+            if c.get("return_nmd"):
+                raise ValueError("return_nmd=True is not supported by MaskedLayerNormalization (the reference raises too, layers.py:307-311)")
+            layers.append(LayerSpec("norm", dict(type="ln", epsilon=float(c.get("epsilon", 1e-3)), center=bool(c.get("center", True)),
+                                                 scale=bool(c.get("scale", True)))))
         elif name in ("activation", "gelu", "relu"):
             layers.append(LayerSpec("act", dict(activation=_act_name(c, name if name != "activation" else None))))
         elif name == "residual_block":
@@ -127,7 +133,7 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
             if strides > 1 and int(c.get("dilation_rate", 1)) != 1:
                 raise NotImplementedError("a strided residual block with dilation_rate > 1 (tf.nn.conv1d refuses the combination too)")
             norm_type = str(c.get("norm_type", "masked_batchnorm")).lower()
-            if norm_type not in ("masked_batchnorm", "masked_dyt"):
+            if norm_type not in ("masked_batchnorm", "masked_dyt", "masked_layernorm"):
                 raise NotImplementedError(f"residual blocks with norm_type={norm_type!r} are not supported")
             if c.get("return_nmd") and norm_type != "masked_batchnorm":
                 raise NotImplementedError("residual_block(return_nmd=True) needs masked_batchnorm (MaskedDYT rejects it, layers.py:396-400)")
@@ -138,7 +144,8 @@ def parse_project(cfg: dict[str, Any]) -> ModelSpec:
                 use_bias=bool(c.get("use_bias", True)), activation=_act_name(c, model.get("activation", "gelu")) or "gelu",
                 use_masking=bool(c.get("use_masking", use_masking)),
                 strides=strides, use_1x1conv=bool(c.get("use_1x1conv", False)),      # layers.py:1855-1864: bypass conv when asked for or strided
-                norm="dyt" if norm_type == "masked_dyt" else "bn", alpha_init=float(c.get("alpha_init", 0.5)))))
+                norm={"masked_dyt": "dyt", "masked_layernorm": "ln"}.get(norm_type, "bn"), alpha_init=float(c.get("alpha_init", 0.5)),
+                ln_epsilon=1e-3)))                                # ResidualBlock._make_norm: MaskedLayerNormalization(name=...), default epsilon
         elif name == "dropout":
             continue
         else:
@@ -322,6 +329,11 @@ def _dyt(rng, c, alpha_init=0.5):
                 beta=rng.normal(0.0, 0.1, c).astype(np.float32))
 
 
+def _ln(rng, c):
+    """MaskedLayerNormalization variables (layers.py:318-335); randomised away from the initialisers so tests see them."""
+    return dict(gamma=rng.uniform(0.5, 1.5, c).astype(np.float32), beta=rng.normal(0.0, 0.1, c).astype(np.float32))
+
+
 def _conv(rng, k, cin, cout):
     return dict(kernel=_glorot(rng, (k, cin, cout), k * cin, k * cout), bias=np.zeros(cout, np.float32))
 
@@ -349,13 +361,13 @@ def init_random(spec: ModelSpec, seed: int = 0) -> dict[str, Any]:
             w["layers"].append(_conv(rng, c["kernel_size"], ch, c["filters"]))
             ch = c["filters"]
         elif layer.kind == "norm":
-            w["layers"].append(_dyt(rng, ch, c.get("alpha_init", 0.5)) if c.get("type") == "dyt" else _bn(rng, ch))
+            w["layers"].append(_dyt(rng, ch, c.get("alpha_init", 0.5)) if c.get("type") == "dyt" else _ln(rng, ch) if c.get("type") == "ln" else _bn(rng, ch))
         elif layer.kind == "nmd":
             w["layers"].append(dict(moving_mean=rng.normal(0.0, 0.1, ch).astype(np.float32)))
         elif layer.kind == "resblock":
             blocks = []
             for _ in range(c["block_size"]):
-                norm = (lambda n: _dyt(rng, n, c.get("alpha_init", 0.5))) if c.get("norm") == "dyt" else (lambda n: _bn(rng, n))
+                norm = (lambda n: _dyt(rng, n, c.get("alpha_init", 0.5))) if c.get("norm") == "dyt" else (lambda n: _ln(rng, n)) if c.get("norm") == "ln" else (lambda n: _bn(rng, n))
                 blk = dict(conv1=_conv(rng, c["kernel_size"], ch, c["filters"]), bn1=norm(c["filters"]),
                            conv2=_conv(rng, c["kernel_size"], c["filters"], c["filters"]),
                            bn2=norm(c["filters"]))

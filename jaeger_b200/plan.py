@@ -32,7 +32,7 @@ LAYER_PTR_FIELDS = 16
 (LF_KIND, LF_CIN, LF_COUT, LF_K, LF_DIL, LF_PAD_LEFT, LF_SHRINK, LF_IN_BUF, LF_OUT_BUF, LF_SC_BUF,
  LF_ACT1, LF_HAS_AFF2, LF_ACT2, LF_TAP_MODE, LF_TAP_SLOT, LF_POOL_MODE, LF_MASK_IN, LF_MASK_OUT,
  LF_SC_MASK, LF_MASKING, LF_CUM_SHRINK_IN, LF_HALVINGS, LF_DYT1, LF_DYT2, LF_EPI_F32, LF_LEN_CEIL, LF_REAL_CIN,
- LF_REAL_COUT) = range(28)
+ LF_REAL_COUT, LF_LN1, LF_LN_EPS, LF_MASK_THR) = range(31)
 (LP_KERNEL, LP_BIAS, LP_SCALE1, LP_SHIFT1, LP_SCALE2, LP_SHIFT2, LP_SC_CONST, LP_TAP_MEAN,
  LP_DYT_G1, LP_DYT_B1, LP_DYT_G2, LP_DYT_B2, LP_KERNEL_ODD) = range(13)
 
@@ -96,6 +96,9 @@ class ConvLaunch:
     halvings: int = 0                     # MaxPool(2) stages applied to the frame length before this layer
     real_cin: int = 0                     # channel counts of the reference layer (before padding to multiples of 64)
     real_cout: int = 0
+    mask_thr: int = 1                     # valid taps an output row needs (layers.py:1245-1252): 1 = "any", (k + 1) // 2 = "majority", k = "strict"
+    ln1: int = 0                          # the first norm is a MaskedLayerNormalization: scale1 = gamma, shift1 = beta, bias kept apart
+    ln_eps: float = 1e-3
 
 
 @dataclass
@@ -157,6 +160,22 @@ def _bn_fold(bn: dict[str, np.ndarray], eps: float):
     scale = bn["gamma"].astype(np.float64) / np.sqrt(bn["var"].astype(np.float64) + eps)
     shift = bn["beta"].astype(np.float64) - scale * bn["mean"].astype(np.float64)
     return scale, shift
+
+
+def _is_ln(nw: dict[str, np.ndarray]) -> bool:
+    """A MaskedLayerNormalization owns gamma / beta only (no moving statistics, no alpha)."""
+    return "alpha" not in nw and "mean" not in nw
+
+
+def _attach_norm1(c: "ConvLaunch", nw: dict[str, np.ndarray], eps: float, ln_eps: float = 1e-3) -> None:
+    """The norm right after a convolution, into the launch's first-norm slot."""
+    if _is_ln(nw):
+        cout = c.kernel.shape[2]
+        c.scale1 = np.asarray(nw.get("gamma", np.ones(cout)), np.float64)
+        c.shift1 = np.asarray(nw.get("beta", np.zeros(cout)), np.float64)
+        c.ln1, c.ln_eps = 1, float(ln_eps)
+        return
+    c.scale1, c.shift1, c.dyt_g1, c.dyt_b1 = _norm_fold(nw, eps)
 
 
 def _norm_fold(nw: dict[str, np.ndarray], eps: float):
@@ -241,8 +260,12 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         s1 = np.ones(cout) if c.scale1 is None else c.scale1
         t1 = np.zeros(cout) if c.shift1 is None else c.shift1
         c.scale1 = _np32(s1)
-        c.shift1 = _np32(t1 + s1 * c.bias.astype(np.float64))     # acc*s1 + (t1 + s1*bias)
-        v = c.shift1.astype(np.float64)
+        if c.ln1:                         # LayerNorm normalises acc + bias before gamma / beta: the bias stays a separate vector;
+            c.shift1 = _np32(t1)          # the layer re-masks its output (layers.py:363-365): exactly 0 at masked rows
+            c.bias = _np32(c.bias)
+        else:
+            c.shift1 = _np32(t1 + s1 * c.bias.astype(np.float64))     # acc*s1 + (t1 + s1*bias)
+        v = np.zeros(cout) if c.ln1 else c.shift1.astype(np.float64)
         if c.dyt_g1 is not None:          # MaskedDYT multiplies its output by the mask: exactly 0 at masked rows
             c.dyt_g1, c.dyt_b1 = _np32(c.dyt_g1), _np32(c.dyt_b1)
             v = np.zeros(cout)
@@ -260,6 +283,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         c.out_const = _np32(v)
 
     cur: ConvLaunch | None = None
+    thresholded = False                   # a convolution with mask_mode strict / majority has been compiled
     for layer, lw in zip(spec.layers, weights["layers"]):
         cfg = layer.cfg
         if layer.kind == "conv":
@@ -290,8 +314,18 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                            cur_buf, cur_mask, out_buf)
             if cfg.get("activation"):
                 cur.act1, cur.stage = cfg["activation"], 2
+            if cur.masking and cfg.get("mask_mode", "any") != "any":
+                k_ = kernel.shape[0]
+                cur.mask_thr = k_ if cfg["mask_mode"] == "strict" else (k_ + 1) // 2
+                thresholded = True
             cur_buf, cur_mask, ch = out_buf, cur.mask_out, kernel.shape[2]
         elif layer.kind == "resblock":
+            if thresholded:
+                # Under "strict" / "majority" a masked output row may have seen valid taps, so its un-masked value is not a
+                # per-channel constant; a residual shortcut (MaskedAdd adds the UN-masked tensor, layers.py:60-76, 1910) would need
+                # that value at rows a later `any` convolution re-validates, and the stored tensors keep masked rows at zero.
+                raise NotImplementedError("a residual block after a masked_conv1d with mask_mode 'strict' / 'majority' is not supported "
+                                          "(the shortcut would need the un-masked tensor); stand-alone convolution stacks are")
             masking = cfg["use_masking"] and spec.use_masking
             stride = int(cfg.get("strides", 1))
             zero_bias = lambda cw: cw["bias"] if cfg.get("use_bias", True) else np.zeros_like(cw["bias"])      # noqa: E731
@@ -316,7 +350,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                     c1 = add_conv(k_even, zero_bias(blk["conv1"]), 1, "same", masking, src_buf, x_mask, h_buf, pad_left=pl, kernel_odd=k_odd)
                 else:
                     c1 = add_conv(blk["conv1"]["kernel"], zero_bias(blk["conv1"]), cfg["dilation"], "same", masking, x_buf, x_mask, h_buf)
-                c1.scale1, c1.shift1, c1.dyt_g1, c1.dyt_b1 = _norm_fold(blk["bn1"], 1e-5)
+                _attach_norm1(c1, blk["bn1"], 1e-5, cfg.get("ln_epsilon", 1e-3))
                 c1.act1, c1.stage = cfg["activation"], 2
                 finish(c1)
                 sc_buf, sc_mask, sc_const = x_buf, (x_mask if masking else -1), x_const
@@ -331,7 +365,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                         c3 = add_conv(k3p, zero_bias(blk["conv3"]), 1, "same", masking, src_buf, x_mask, b_buf, pad_left=0)
                     else:
                         c3 = add_conv(k3, zero_bias(blk["conv3"]), 1, "same", masking, x_buf, x_mask, b_buf)
-                    c3.scale1, c3.shift1, c3.dyt_g1, c3.dyt_b1 = _norm_fold(blk["bn3"], 1e-5)
+                    _attach_norm1(c3, blk["bn3"], 1e-5, cfg.get("ln_epsilon", 1e-3))
                     c3.stage = 2
                     finish(c3)
                     sc_buf, sc_mask, sc_const = b_buf, (c3.mask_out if masking else -1), c3.out_const
@@ -339,7 +373,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
                 # thread); with a bypass the block input is dead after conv1 / conv3 and its buffer is reused all the same
                 c2 = add_conv(blk["conv2"]["kernel"], zero_bias(blk["conv2"]), cfg["dilation"], "same", masking,
                               h_buf, c1.mask_out, x_buf, sc_buf=sc_buf, sc_mask=sc_mask, sc_const=sc_const)
-                c2.scale1, c2.shift1, c2.dyt_g1, c2.dyt_b1 = _norm_fold(blk["bn2"], 1e-5)
+                _attach_norm1(c2, blk["bn2"], 1e-5, cfg.get("ln_epsilon", 1e-3))
                 c2.act1, c2.stage = cfg["activation"], 2
                 cur = c2
                 cur_buf, cur_mask = x_buf, c2.mask_out
@@ -365,6 +399,13 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
         elif layer.kind == "norm":
             if cur is None:
                 raise NotImplementedError("norm before the first convolution")
+            if _is_ln(lw):
+                if cur.stage != 0:
+                    raise NotImplementedError("masked_layernorm is fused as the norm right after a convolution only (per-row channel "
+                                              "statistics of the accumulator); after an activation it is not supported")
+                _attach_norm1(cur, lw, 1e-5, cfg.get("epsilon", 1e-3))
+                cur.stage = 1
+                continue
             s, t, dg, db = _norm_fold(lw, cfg.get("epsilon", 1e-5))
             if cfg.get("return_nmd"):          # masked_batchnorm(return_nmd=True): an NMD tap on this norm's input
                 if cur.tap_mode != 0 or cur.stage not in (0, 2):
@@ -425,7 +466,7 @@ def compile_plan(spec: ModelSpec, weights: dict[str, Any]) -> Plan:
             out[:cout] = a
             return out
         c.bias, c.shift1, c.shift2 = pad(c.bias, 0.0), pad(c.shift1, 0.0), pad(c.shift2, 0.0)
-        c.scale1, c.scale2 = pad(c.scale1, 1.0), pad(c.scale2, 1.0)
+        c.scale1, c.scale2 = pad(c.scale1, 0.0 if c.ln1 else 1.0), pad(c.scale2, 1.0)    # LayerNorm: a padded channel normalises to (0 - mean) / sigma and must stay 0
         c.sc_const, c.out_const = pad(c.sc_const, 0.0), pad(c.out_const, 0.0)
         c.dyt_g1, c.dyt_b1, c.dyt_g2, c.dyt_b2 = pad(c.dyt_g1, 0.0), pad(c.dyt_b1, 0.0), pad(c.dyt_g2, 0.0), pad(c.dyt_b2, 0.0)
     ch = -(-ch // 64) * 64
@@ -503,7 +544,8 @@ def to_ctypes(plan: Plan):
                 LF_TAP_MODE: c.tap_mode, LF_TAP_SLOT: c.tap_slot, LF_POOL_MODE: c.pool_mode, LF_MASK_IN: c.mask_in,
                 LF_MASK_OUT: c.mask_out, LF_SC_MASK: c.sc_mask, LF_MASKING: c.masking,
                 LF_CUM_SHRINK_IN: c.cum_shrink_in, LF_DYT1: int(c.dyt_g1 is not None), LF_DYT2: int(c.dyt_g2 is not None),
-                LF_EPI_F32: c.epi_f32, LF_LEN_CEIL: c.len_ceil, LF_REAL_CIN: c.real_cin, LF_REAL_COUT: c.real_cout}
+                LF_EPI_F32: c.epi_f32, LF_LEN_CEIL: c.len_ceil, LF_REAL_CIN: c.real_cin, LF_REAL_COUT: c.real_cout,
+                LF_LN1: c.ln1, LF_LN_EPS: int(np.float32(c.ln_eps).view(np.int32)), LF_MASK_THR: c.mask_thr}
         for i, v in vals.items():
             d.i[i] = int(v)
         ptrs = {LP_KERNEL: c.kernel, LP_BIAS: c.bias, LP_SCALE1: c.scale1, LP_SHIFT1: c.shift1, LP_SCALE2: c.scale2,

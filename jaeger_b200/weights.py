@@ -189,6 +189,8 @@ def group_bundle(tensors: dict[str, np.ndarray]) -> list[tuple[str, str, dict[st
             kind = "dyt"
         elif set(g) == {"moving_mean"}:
             kind = "nmd"
+        elif set(g) <= {"gamma", "beta"} and g:
+            kind = "ln"                    # MaskedLayerNormalization: gamma / beta only (layers.py:318-335)
         else:
             continue                       # seed-generator states, counters ...
         out.append((path, kind, g))
@@ -212,7 +214,7 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
         nonlocal pos
         i = pos
         while i < len(groups) and (used[i] or groups[i][1] not in kinds):
-            if not used[i] and groups[i][1] in ("conv", "bn", "dyt", "nmd"):
+            if not used[i] and groups[i][1] in ("conv", "bn", "dyt", "ln", "nmd"):
                 fail(f"expected {what}, found {groups[i][1]} at {groups[i][0]}")
             i += 1
         if i == len(groups):
@@ -228,6 +230,12 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
         return dict(kernel=k.astype(np.float32), bias=g["bias"].astype(np.float32) if "bias" in g else np.zeros(cfg["filters"], np.float32))
 
     def norm_w(g, c, what):
+        if "moving_mean" not in g and "alpha" not in g:       # MaskedLayerNormalization; scale / center may be switched off
+            for a in ("gamma", "beta"):
+                if a in g and g[a].shape != (c,):
+                    fail(f"{what}: {a} {g[a].shape}, expected {(c,)}")
+            return dict(gamma=g["gamma"].astype(np.float32) if "gamma" in g else np.ones(c, np.float32),
+                        beta=g["beta"].astype(np.float32) if "beta" in g else np.zeros(c, np.float32))
         if g["gamma"].shape != (c,):
             fail(f"{what}: {g['gamma'].shape} channels, expected {c}")
         if "alpha" in g:
@@ -255,7 +263,7 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
             w["layers"].append(conv_w(take(("conv",), what)[2], ch, c, what))
             ch = c["filters"]
         elif layer.kind == "norm":
-            w["layers"].append(norm_w(take(("dyt",) if c.get("type") == "dyt" else ("bn",), what)[2], ch, what))
+            w["layers"].append(norm_w(take(("dyt",) if c.get("type") == "dyt" else ("ln",) if c.get("type") == "ln" else ("bn",), what)[2], ch, what))
         elif layer.kind == "nmd":
             g = take(("nmd",), what)[2]
             if g["moving_mean"].shape != (ch,):
@@ -293,7 +301,7 @@ def weights_from_bundle(spec, tensors: dict[str, np.ndarray]) -> dict[str, Any]:
             w["layers"].append(dict(blocks=blocks))
         else:
             w["layers"].append({})
-    left = [p for i, (p, k, _) in enumerate(groups) if not used[i] and k in ("conv", "bn", "dyt", "nmd", "emb")]
+    left = [p for i, (p, k, _) in enumerate(groups) if not used[i] and k in ("conv", "bn", "dyt", "ln", "nmd", "emb")]
     if left:
         fail(f"{len(left)} representation-learner variables are not in the project's layer list (first: {left[0]})")
     dense = [(i, g) for i, (_, k, g) in enumerate(groups) if k == "dense" and not used[i]]

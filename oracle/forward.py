@@ -99,8 +99,24 @@ def dyt(x, w, mask):
     return out * mask.unsqueeze(-1) if mask is not None else out
 
 
-def _norm(x, w, mask, eps=1e-5):
-    return dyt(x, w, mask) if "alpha" in w else batchnorm(x, w, eps)
+def layernorm(x, w, mask, eps=1e-3):
+    """MaskedLayerNormalization.call (layers.py:337-367): the input is multiplied by the mask, the moments run over the channel
+    axis (population variance, tf.nn.moments), gamma / beta, and the mask once more."""
+    xm = x * mask.unsqueeze(-1) if mask is not None else x
+    mean = xm.mean(dim=-1, keepdim=True)
+    var = ((xm - mean) ** 2).mean(dim=-1, keepdim=True)
+    out = (xm - mean) / torch.sqrt(var + eps) * w["gamma"] + w["beta"]
+    return out * mask.unsqueeze(-1) if mask is not None else out
+
+
+def _norm(x, w, mask, eps=1e-5, ln_eps=1e-3):
+    """Dispatch on the weights a norm layer owns: alpha -> MaskedDYT, moving statistics -> BatchNorm, gamma / beta only ->
+    MaskedLayerNormalization."""
+    if "alpha" in w:
+        return dyt(x, w, mask)
+    if "mean" in w:
+        return batchnorm(x, w, eps)
+    return layernorm(x, w, mask, ln_eps)
 
 
 def nmd_vector(x, mask, moving_mean, eps=1e-5):
@@ -171,15 +187,15 @@ def residual_stack(x, mask, blocks, c, dtype=torch.float32):
         tw = lambda d: {k: _t(v, dtype) for k, v in d.items()}     # noqa: E731
         bias = lambda d: _t(d["bias"], dtype) if c.get("use_bias", True) else None     # noqa: E731
         h, m1 = masked_conv1d(x, m_in, _t(blk["conv1"]["kernel"], dtype), bias(blk["conv1"]), c["dilation"], "same", stride=stride)
-        h = _act(_norm(h, tw(blk["bn1"]), m1 if m_in is not None else None), c["activation"])
+        h = _act(_norm(h, tw(blk["bn1"]), m1 if m_in is not None else None, ln_eps=c.get("ln_epsilon", 1e-3)), c["activation"])
         h2, m2 = masked_conv1d(h, m1, _t(blk["conv2"]["kernel"], dtype), bias(blk["conv2"]), c["dilation"], "same")
         if c.get("return_nmd") and bi == len(blocks) - 1:          # layers.py:1897-1898, 2696-2704
             block_nmd = nmd_vector(h2, m2 if m_in is not None else None, _t(blk["bn2"]["mean"], dtype))
-        h2 = _norm(h2, tw(blk["bn2"]), m2 if m_in is not None else None)
+        h2 = _norm(h2, tw(blk["bn2"]), m2 if m_in is not None else None, ln_eps=c.get("ln_epsilon", 1e-3))
         shortcut = x
         if "conv3" in blk:                            # layers.py:1855-1864, 1903-1909: 1x1 conv (same stride) + norm on the block input
             sc, m3 = masked_conv1d(x, m_in, _t(blk["conv3"]["kernel"], dtype), bias(blk["conv3"]), c["dilation"], "same", stride=stride)
-            shortcut = _norm(sc, tw(blk["bn3"]), m3 if m_in is not None else None)
+            shortcut = _norm(sc, tw(blk["bn3"]), m3 if m_in is not None else None, ln_eps=c.get("ln_epsilon", 1e-3))
         x = _act(h2 + shortcut, c["activation"])      # MaskedAdd: no re-masking (layers.py:60-76)
         mask = m2 if m_in is not None else mask
     return x, mask, block_nmd
@@ -206,14 +222,14 @@ def forward(spec, weights, tokens: np.ndarray, dtype=torch.float32) -> dict[str,
             m_in = mask if c["use_masking"] else None
             x, mask = masked_conv1d(x, m_in, _t(lw["kernel"], dtype),
                                     _t(lw["bias"], dtype) if c["use_bias"] else None,
-                                    c["dilation"], c["padding"], c.get("activation"))
+                                    c["dilation"], c["padding"], c.get("activation"), mask_mode=c.get("mask_mode", "any"))
         elif layer.kind == "nmd":
             nmds.append(nmd_vector(x, mask, _t(lw["moving_mean"], dtype)))
         elif layer.kind == "norm":
             nw = {k: _t(v, dtype) for k, v in lw.items()}
             if c.get("return_nmd"):               # layers.py:943-954: NMD of the norm's input against its own moving mean
                 nmds.append(nmd_vector(x, mask if spec.use_masking else None, nw["mean"], c.get("epsilon", 1e-5)))
-            x = _norm(x, nw, mask if spec.use_masking else None, c.get("epsilon", 1e-5))
+            x = _norm(x, nw, mask if spec.use_masking else None, c.get("epsilon", 1e-5), ln_eps=c.get("epsilon", 1e-3))
         elif layer.kind == "act":
             x = _act(x, c.get("activation"))
         elif layer.kind == "resblock":

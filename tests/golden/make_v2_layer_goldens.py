@@ -80,6 +80,11 @@ def main():
     dyt.alpha, dyt.gamma, dyt.beta = t(np.array([0.37])), t(rng.uniform(0.5, 1.5, c)), t(rng.normal(0, 0.2, c))
     out["dyt_alpha"], out["dyt_gamma"], out["dyt_beta"] = (np.asarray(getattr(dyt, a)) for a in ("alpha", "gamma", "beta"))
     out["dyt_y"], out["dyt_y_nomask"] = np.asarray(dyt.call(t(h), mask=t(hm))), np.asarray(dyt.call(t(h), mask=None))
+    ln = L.MaskedLayerNormalization(epsilon=1e-3)                   # layers.py:293-367
+    ln.build((b, f, length, c))
+    ln.gamma, ln.beta = t(rng.uniform(0.5, 1.5, c)), t(rng.normal(0, 0.2, c))
+    out["ln_gamma"], out["ln_beta"] = np.asarray(ln.gamma), np.asarray(ln.beta)
+    out["ln_y"], out["ln_y_nomask"] = np.asarray(ln.call(t(h), mask=t(hm))), np.asarray(ln.call(t(h), mask=None))
     nl = N.NMDLayer()
     nl.build((b, f, length, c))
     nl.moving_mean = t(rng.normal(0, 0.3, c))
@@ -108,7 +113,7 @@ def main():
     mb[0, :, 8:25] = False
     mb[1, :, 30:] = False
     out["block_x"], out["block_mask"] = xb, mb
-    for norm in ("masked_batchnorm", "masked_dyt"):
+    for norm in ("masked_batchnorm", "masked_dyt", "masked_layernorm"):
         for masking in (True, False):
             kw = dict(filters=cb, kernel_size=kb, dilation_rate=db, use_bias=True, norm_type=norm, use_masking=masking, name="resblock_1")
             if norm == "masked_batchnorm":
@@ -118,7 +123,7 @@ def main():
             if masking:
                 xin._keras_mask = t(mb)
             stack(xin)                                           # builds the sub-layers
-            tag = f"block_{'bn' if norm == 'masked_batchnorm' else 'dyt'}_{int(masking)}"
+            tag = f"block_{ {'masked_batchnorm': 'bn', 'masked_dyt': 'dyt', 'masked_layernorm': 'ln'}[norm] }_{int(masking)}"
             for bi, blk in enumerate(stack.blocks):
                 for cname in ("conv1", "conv2"):
                     conv = getattr(blk, cname)
@@ -130,6 +135,9 @@ def main():
                         nl_.gamma, nl_.beta = t(rng.uniform(0.5, 1.5, cb)), t(rng.normal(0, 0.2, cb))
                         nl_.moving_mean, nl_.moving_variance = t(rng.normal(0, 0.3, cb)), t(rng.uniform(0.4, 1.6, cb))
                         names = ("gamma", "beta", "moving_mean", "moving_variance")
+                    elif norm == "masked_layernorm":
+                        nl_.gamma, nl_.beta = t(rng.uniform(0.5, 1.5, cb)), t(rng.normal(0, 0.2, cb))
+                        names = ("gamma", "beta")
                     else:
                         nl_.alpha, nl_.gamma, nl_.beta = t(np.array([rng.uniform(0.3, 0.7)])), t(rng.uniform(0.5, 1.5, cb)), t(rng.normal(0, 0.2, cb))
                         names = ("alpha", "gamma", "beta")

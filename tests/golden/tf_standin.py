@@ -250,6 +250,7 @@ def install():
     tf.where = lambda c, a, b: t(np.where(np.asarray(c), np.asarray(a), np.asarray(b)))
     tf.maximum = lambda a, b: t(np.maximum(np.asarray(a), np.asarray(b)))
     tf.square = lambda x: t(np.square(np.asarray(x)))
+    tf.sqrt = lambda x: t(np.sqrt(np.asarray(x)))
     tf.reduce_sum = lambda x, axis=None, keepdims=False: t(np.sum(np.asarray(x), axis=_axes(axis), keepdims=keepdims))
     tf.reduce_mean = lambda x, axis=None, keepdims=False: t(np.mean(np.asarray(x), axis=_axes(axis), keepdims=keepdims))
     tf.reduce_max = lambda x, axis=None, keepdims=False: t(np.max(np.asarray(x), axis=_axes(axis), keepdims=keepdims))

@@ -48,7 +48,7 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
         if c.masking:
             mt = m_in.reshape(b * f, 1, -1)
             mt = F.pad(mt, (c.pad_left, span - c.pad_left)) if c.shrink == 0 else mt
-            m_out = (F.conv1d(mt, torch.ones(1, 1, k, dtype=dt), dilation=c.dilation) > 0).to(dt).reshape(b, f, -1)
+            m_out = (F.conv1d(mt, torch.ones(1, 1, k, dtype=dt), dilation=c.dilation) >= c.mask_thr).to(dt).reshape(b, f, -1)
         else:
             m_out = torch.ones(acc.shape[:3], dtype=dt)
         masks[c.mask_out] = m_out
@@ -56,7 +56,14 @@ def run_plan(plan, tokens: np.ndarray, lpad=None):
         if c.tap_mode == 1:
             taps[c.tap_slot] = ((acc + torch.as_tensor(c.bias, dtype=dt)) * mo).sum(dim=(1, 2)) / (m_out.sum(dim=(1, 2)).unsqueeze(-1) + 1e-5) \
                 - torch.as_tensor(c.tap_mean, dtype=dt)
-        v = acc * torch.as_tensor(c.scale1, dtype=dt) + torch.as_tensor(c.shift1, dtype=dt)
+        if c.ln1:          # MaskedLayerNormalization over the layer's real channels (padded ones carry acc = bias = gamma = beta = 0)
+            u = acc + torch.as_tensor(c.bias, dtype=dt)
+            n_real = c.real_cout or u.shape[-1]
+            mu = u.sum(-1, keepdim=True) / n_real
+            var = (u * u).sum(-1, keepdim=True) / n_real - mu * mu
+            v = (u - mu) / torch.sqrt(var.clamp_min(0) + c.ln_eps) * torch.as_tensor(c.scale1, dtype=dt) + torch.as_tensor(c.shift1, dtype=dt)
+        else:
+            v = acc * torch.as_tensor(c.scale1, dtype=dt) + torch.as_tensor(c.shift1, dtype=dt)
         if c.dyt_g1 is not None:
             v = torch.tanh(v) * torch.as_tensor(c.dyt_g1, dtype=dt) + torch.as_tensor(c.dyt_b1, dtype=dt)
         if c.sc_buf >= 0:

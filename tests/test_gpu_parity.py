@@ -1279,3 +1279,55 @@ def test_streamed_run_equals_whole_file_run(standin, tmp_path):
         assert a["phage_table"].read_text() == b["phage_table"].read_text()
     fa_a, fa_b = (tmp_path / d / "standin" / "meta_phages_jaeger.fasta" for d in ("whole", "streamed"))
     assert fa_a.read_bytes() == fa_b.read_bytes()
+
+
+@pytest.mark.parametrize("standalone_ln,masking,bypass", [(True, True, False), (False, True, True), (True, False, False)])
+def test_masked_layernorm_vs_oracle(standalone_ln, masking, bypass):
+    """MaskedLayerNormalization (nnlib/v2/layers.py:293-367) as the norm of the residual blocks and as a stand-alone layer after the
+    stem: row statistics over the real channels in the single-CTA tensor-core kernel's epilogue (and in the CUDA-core kernel), against
+    the fp32 oracle whose LayerNorm is pinned on the reference's own layer code (tests/golden/v2_layers.npz)."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import layernorm_config
+    for filters in (24, 128):
+        spec = parse_project(layernorm_config(standalone_ln, masking, filters=filters, bypass=bypass))
+        w = init_random(spec, 4)
+        recs = random_contigs(6, [300] * 40 + [299, 900, 310], n_run_every=3, lower_every=0)
+        seqs = [s[i:i + 300] for _, s in recs for i in range(0, len(s) - 299, 300)]
+        ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 300))
+        for use_ref in (False, True):
+            eng = B200Engine(spec=spec, weights=w, use_ref_kernels=use_ref)
+            y = eng.predict(WindowSource(records=recs, fsize=300, stride=300))
+            # random-init LayerNorm models have logits of magnitude 10-20: fp16 activations -> a tolerance relative to the scale
+            # (the stand-in with a scaled classifier shows the same 1e-3 of the logit scale, profiles/label_agreement_r2.json)
+            for k, tol in (("prediction", 3e-3), ("embedding", 4e-3), ("nmd", 4e-3), ("reliability", 4e-3)):
+                bound = tol * max(4.0, float(np.abs(ref[k]).max()))
+                assert np.abs(ref[k] - y[k]).max() <= bound, (k, filters, use_ref, float(np.abs(ref[k] - y[k]).max()), bound)
+            if not use_ref:
+                assert "conv_tc_kernel" in eng.conv_kernel_names()
+            eng.close()
+
+
+@pytest.mark.parametrize("modes", [("strict", "strict", "strict"), ("majority", "majority", "majority"), ("strict", "majority", "any")])
+def test_mask_modes_strict_and_majority_vs_oracle(modes):
+    """mask_mode strict / majority on stand-alone MaskedConv1D layers (nnlib/v2/layers.py:1245-1252): the validity helper of the
+    tensor-core kernels counts the valid taps of every output row and thresholds them (and so does the CUDA-core path); windows
+    with N runs, isolated Ns and a masked tail, against the fp32 oracle."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import conv_stack_config
+    spec = parse_project(conv_stack_config(modes))
+    w = init_random(spec, 6)
+    recs = random_contigs(9, [300] * 60 + [299, 900, 310], n_run_every=2, lower_every=0)
+    seqs = [s[i:i + 300] for _, s in recs for i in range(0, len(s) - 299, 300)]
+    ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 300))
+    for use_ref in (False, True):
+        eng = B200Engine(spec=spec, weights=w, use_ref_kernels=use_ref)
+        y = eng.predict(WindowSource(records=recs, fsize=300, stride=300))
+        for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 1e-2), ("reliability", 1e-2)):
+            assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))
+        eng.close()

@@ -169,6 +169,10 @@ def test_oracle_layers_vs_reference_call_bodies():
     assert np.abs(fwd.batchnorm(h, bn).numpy() - z["bn_y_nomask"]).max() < 1e-12
     assert np.abs(fwd.nmd_vector(h, hm, bn["mean"]).numpy() - z["bn_nmd"]).max() < 1e-12       # return_nmd: NMD of the norm's input
     assert np.abs(fwd.nmd_vector(h, None, bn["mean"]).numpy() - z["bn_nmd_nomask"]).max() < 1e-12
+    lw = {"gamma": T(z["ln_gamma"]), "beta": T(z["ln_beta"])}                       # MaskedLayerNormalization (layers.py:337-367)
+    assert np.abs(fwd.layernorm(h, lw, hm, 1e-3).numpy() - z["ln_y"]).max() < 1e-12
+    assert np.abs(fwd.layernorm(h, lw, None, 1e-3).numpy() - z["ln_y_nomask"]).max() < 1e-12
+    assert np.all(z["ln_y"][~z["h_mask"]] == 0.0)                                   # re-masked: exactly zero at masked rows
     dw = {"alpha": T(z["dyt_alpha"]), "gamma": T(z["dyt_gamma"]), "beta": T(z["dyt_beta"])}
     assert np.abs(fwd.dyt(h, dw, hm).numpy() - z["dyt_y"]).max() < 1e-12
     assert np.abs(fwd.dyt(h, dw, None).numpy() - z["dyt_y_nomask"]).max() < 1e-12
@@ -187,7 +191,7 @@ def test_oracle_layers_vs_reference_call_bodies():
     assert z["ood_y"][1, 3] == 0.0 and abs(z["ood_y"][0, 0] - 1 / 6) < 1e-12                   # tie: margin 0; uniform: max_prob 1/6
 
 
-@pytest.mark.parametrize("norm", ["bn", "dyt"])
+@pytest.mark.parametrize("norm", ["bn", "dyt", "ln"])
 @pytest.mark.parametrize("masking", [1, 0])
 def test_oracle_residual_stack_vs_reference_block_code(norm, masking):
     """ResidualBlockStack / ResidualBlock.call executed from the reference's source (two blocks, k5, dilation 3; BatchNorm with
@@ -207,6 +211,8 @@ def test_oracle_residual_stack_vs_reference_block_code(norm, masking):
             if norm == "bn":
                 blk[nname] = {"gamma": z[f"{tag}_b{bi}_{nname}_gamma"], "beta": z[f"{tag}_b{bi}_{nname}_beta"],
                               "mean": z[f"{tag}_b{bi}_{nname}_moving_mean"], "var": z[f"{tag}_b{bi}_{nname}_moving_variance"]}
+            elif norm == "ln":
+                blk[nname] = {a: z[f"{tag}_b{bi}_{nname}_{a}"] for a in ("gamma", "beta")}
             else:
                 blk[nname] = {a: z[f"{tag}_b{bi}_{nname}_{a}"] for a in ("alpha", "gamma", "beta")}
         blocks.append(blk)

@@ -533,3 +533,105 @@ def test_strided_blocks_need_masking_off():
     cfg["model"]["use_masking"] = True
     with pytest.raises(ValueError, match="use_masking: false"):
         parse_project(cfg)
+
+
+def layernorm_config(standalone_ln: bool, masking: bool = True, filters: int = 24, bypass: bool = False):
+    """A residual CNN whose norms are MaskedLayerNormalization (nnlib/v2/layers.py:293-367): every norm of the residual blocks
+    (`norm_type: masked_layernorm`, ResidualBlock._make_norm, layers.py:1826-1834) and, with `standalone_ln`, the stand-alone norm
+    after the stem conv; the trailing norm after the stack stays a BatchNorm (a LayerNorm there follows an activation)."""
+    conv = {"name": "masked_conv1d", "config": {"filters": filters, "kernel_size": 7, "use_bias": True, "activation": None}}
+    n1 = {"name": "masked_layernorm", "config": {"epsilon": 2e-3}} if standalone_ln else {"name": "masked_batchnorm", "config": {}}
+    act = {"name": "activation", "config": {"activation": "gelu"}}
+    blk = {"name": "residual_block", "config": {"block_size": 2, "filters": filters, "kernel_size": 5, "dilation_rate": 2, "use_bias": True,
+                                                "norm_type": "masked_layernorm", "use_1x1conv": bypass}}
+    return {"model": {"name": "ln_model", "activation": "gelu", "use_masking": masking,
+                      "class_label_map": [{"class": c, "label": i} for i, c in enumerate("abc")],
+                      "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 16},
+                      "string_processor": {"codon": "CODON", "codon_id": "CODON_ID", "crop_size": 300},
+                      "representation_learner": {"hidden_layers": [conv, n1, act, blk, {"name": "nmd"}, {"name": "masked_batchnorm", "config": {}}, act],
+                                                 "pooling": "max"},
+                      "classifier": {"hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None}}]},
+                      "reliability_model": {"hidden_layers": [{"name": "dense", "config": {"units": 8, "activation": "gelu", "use_bias": True}},
+                                                              {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]}}}
+
+
+@pytest.mark.parametrize("standalone_ln,masking,bypass", [(True, True, False), (False, True, True), (True, False, False)])
+def test_masked_layernorm_plan_equals_unfused_oracle(standalone_ln, masking, bypass):
+    """MaskedLayerNormalization compiled into the conv launch's first-norm slot (row statistics of acc + bias over the REAL channels,
+    gamma / beta, exactly 0 at masked rows) against the un-fused oracle, whose LayerNorm is pinned on the reference's own
+    `MaskedLayerNormalization.call` and `ResidualBlock.call` (tests/golden/v2_layers.npz: ln_*, block_ln_*)."""
+    spec = parse_project(layernorm_config(standalone_ln, masking, bypass=bypass))
+    w = init_random(spec, 4)
+    plan = compile_plan(spec, w)
+    assert sum(c.ln1 for c in plan.launches) == (5 if bypass else 4) + int(standalone_ln)
+    rng = np.random.default_rng(8)
+    tok = rng.integers(1, 65, (3, 6, 100)).astype(np.uint8)
+    tok[0, :, 20:31] = 0
+    tok[1, :, ::9] = 0
+    got, want = run_plan(plan, tok), ofw.forward(spec, w, tok, dtype=torch.float64)
+    for key in ("prediction", "embedding", "nmd", "reliability"):
+        assert np.abs(got[key] - want[key]).max() < 1e-6, (key, np.abs(got[key] - want[key]).max())
+
+
+def test_masked_layernorm_placements_that_are_refused():
+    cfg = layernorm_config(True)
+    hl = cfg["model"]["representation_learner"]["hidden_layers"]
+    hl[-2] = {"name": "masked_layernorm", "config": {}}           # after the residual stack's activation: not a first norm
+    spec = parse_project(cfg)
+    with pytest.raises(NotImplementedError, match="right after a convolution"):
+        compile_plan(spec, init_random(spec, 0))
+    cfg = layernorm_config(True)
+    cfg["model"]["representation_learner"]["hidden_layers"][1]["config"]["return_nmd"] = True
+    with pytest.raises(ValueError, match="return_nmd"):
+        parse_project(cfg)
+
+
+def conv_stack_config(modes=("strict", "majority", "any"), masking=True):
+    """A plain MaskedConv1D stack (no residual blocks) with a mask_mode per convolution (nnlib/v2/layers.py:1134-1146, 1245-1252):
+    k7 VALID, k5 SAME dilation 2, k3 SAME, each followed by BatchNorm + GELU + an NMD tap."""
+    def conv(f, k, mode, padding="valid", d=1):
+        return {"name": "masked_conv1d", "config": {"filters": f, "kernel_size": k, "dilation_rate": d, "padding": padding, "use_bias": True,
+                                                    "activation": None, "mask_mode": mode}}
+    tail = [{"name": "masked_batchnorm", "config": {}}, {"name": "activation", "config": {"activation": "gelu"}}, {"name": "nmd"}]
+    hidden = [conv(24, 7, modes[0])] + tail + [conv(24, 5, modes[1], "same", 2)] + tail + [conv(24, 3, modes[2], "same")] + tail
+    return {"model": {"name": "conv_stack", "activation": "gelu", "use_masking": masking,
+                      "class_label_map": [{"class": c, "label": i} for i, c in enumerate("abc")],
+                      "embedding": {"use_embedding_layer": True, "input_type": "translated", "input_shape": [6, None], "embedding_size": 16},
+                      "string_processor": {"codon": "CODON", "codon_id": "CODON_ID", "crop_size": 300},
+                      "representation_learner": {"hidden_layers": hidden, "pooling": "average"},
+                      "classifier": {"hidden_layers": [{"name": "dense", "config": {"units": 3, "activation": None}}]},
+                      "reliability_model": {"hidden_layers": [{"name": "dense", "config": {"units": 8, "activation": "gelu", "use_bias": True}},
+                                                              {"name": "dense", "config": {"units": 1, "activation": None, "use_bias": True}}]}}}
+
+
+@pytest.mark.parametrize("modes", [("strict", "strict", "strict"), ("majority", "majority", "majority"), ("strict", "majority", "any")])
+def test_mask_modes_strict_and_majority_plan_equals_unfused_oracle(modes):
+    """mask_mode strict / majority on stand-alone MaskedConv1D layers: the launch plan (a tap-count threshold per launch) against the
+    un-fused oracle, whose three modes are pinned on the reference's own MaskedConv1D.call (v2_layers.npz: conv_*_{any,majority,
+    strict}_mask) and on tests/unit/test_mask_mode.py's known answers."""
+    spec = parse_project(conv_stack_config(modes))
+    w = init_random(spec, 6)
+    plan = compile_plan(spec, w)
+    thr = {"any": lambda k: 1, "majority": lambda k: (k + 1) // 2, "strict": lambda k: k}
+    assert [c.mask_thr for c in plan.launches] == [thr[m](k) for m, k in zip(modes, (7, 5, 3))]
+    rng = np.random.default_rng(5)
+    tok = rng.integers(1, 65, (4, 6, 100)).astype(np.uint8)
+    tok[0, :, 20:31] = 0
+    tok[1, :, ::9] = 0
+    tok[2, :, 97:] = 0
+    got, want = run_plan(plan, tok), ofw.forward(spec, w, tok, dtype=torch.float64)
+    for key in ("prediction", "embedding", "nmd", "reliability"):
+        assert np.abs(got[key] - want[key]).max() < 1e-6, (key, np.abs(got[key] - want[key]).max())
+    base = ofw.forward(parse_project(conv_stack_config(("any", "any", "any"))), w, tok, dtype=torch.float64)
+    assert np.abs(base["embedding"] - want["embedding"]).max() > 1e-4 or modes == ("any",) * 3     # the modes do change the result
+
+
+def test_residual_block_after_a_thresholded_conv_is_refused():
+    cfg = conv_stack_config(("strict", "any", "any"))
+    cfg["model"]["representation_learner"]["hidden_layers"].append(
+        {"name": "residual_block", "config": {"block_size": 1, "filters": 24, "kernel_size": 3, "use_bias": True}})
+    spec = parse_project(cfg)
+    with pytest.raises(NotImplementedError, match="un-masked tensor"):
+        compile_plan(spec, init_random(spec, 0))
+    with pytest.raises(ValueError, match="Invalid mask_mode"):
+        parse_project(conv_stack_config(("most", "any", "any")))
