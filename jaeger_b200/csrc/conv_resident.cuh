@@ -44,7 +44,7 @@ constexpr int kGuardRs = 8;                              // zero rows before / a
 constexpr int kEpiWarpsRs = 16;
 constexpr int kThreadsRs = (kEpiWarpsRs + 2) * 32;
 constexpr int kMaxTilesRs = 8;                           // 8 tiles x 32 columns x 2 sets = 512 TMEM columns
-constexpr int kParBytesRs = 512;                         // per layer: shift1 f32[32] | scale1 f32[32] | scale2 h[32] | shift2 h[32] | scc h[32]
+constexpr int kParBytesRs = 640;                         // per layer: shift1 f32[32] | scale1 f32[32] | scale2 h[32] | shift2 h[32] | scc h[32] | pad | bias f32[32] @ 512
 constexpr int kTokWordsRs = 12;                          // token words a builder lane prefetches: frames x pitch <= 32 x 12 x 4 bytes
 
 struct LayerRs {
@@ -58,6 +58,10 @@ struct LayerRs {
   int sc_all_valid;        // the shortcut tensor carries no mask
   int act1, act2, has_aff2, pool_mode, masking, folded;
   int shrink_in, shrink;
+  int tap_mode;            // NMD tap taken by this kernel: 0 none, 1 raw conv output (acc + bias), 2 after the first activation, 3 on the
+                           // launch output (nmd.py:52-77); a stem whose tap is taken from token counts (stem_tap_kernel) has 0 here
+  int tap_slot;
+  int count_id;            // >= 0: add the layer's valid rows to count[count_id][window] (layers with a tap or the pool)
   int mode;                // EpiModeRs: the compile-time epilogue shape this layer matches (0 = generic)
   int zero_tap;            // one of the taps has shift 0: in a window without masked codons every in-frame output row is then valid
   int kc;                  // input channel chunks of 8: 8 for the one-hot stem operand, 4 otherwise
@@ -78,7 +82,10 @@ struct ResidentParams {
   uint32_t w_bytes;
   float* pool;             // [n_windows][pool_pitch], pre-filled (0 for the sum, -1e9 for the max)
   int pool_pitch;
-  int* count;              // [n_windows] valid rows of the final mask, pre-zeroed
+  int* count;              // [n_masks][cap_windows] valid rows per mask and window, pre-zeroed
+  long long cap_windows;
+  float* tap_sum;          // [n_taps][n_windows][tap_width] masked column sums, pre-zeroed
+  int tap_width;
   int* err;
   LayerRs layer[kMaxLayersRs];
 };
@@ -184,7 +191,8 @@ struct EpiLayer {
   const uint8_t* scb;
   const uint8_t* sc_mask;      // nullptr: the shortcut tensor carries no mask
   float* pool;
-  int* count;
+  float* tap;                  // this window's row of the layer's tap slot, at the thread's lane (nullptr: no tap)
+  int* count;                  // this window's counter of the layer's mask (nullptr: nobody needs it)
   uint32_t plane_bytes, acc, parity, bar0;
   int limit, frames, rpw, n_tiles;
   bool slow_mask;              // masked codons in this window (or no tap at shift 0): evaluate the "any" rule per row
@@ -207,6 +215,8 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
   const int pool_mode = kGen ? L.pool_mode : (kMode == EPI_RS_FINAL_SUM ? 2 : 0);
   const bool has_out = kGen ? E.out != nullptr : kMode != EPI_RS_FINAL_SUM;
   const int act1 = kGen ? L.act1 : ACT_GELU_TANH, act2 = kGen ? L.act2 : ACT_GELU_TANH;
+  const int tap_mode = kGen ? L.tap_mode : 0;
+  const float4* bias = reinterpret_cast<const float4*>(E.par + 512);
   const float4* shift1 = reinterpret_cast<const float4*>(E.par);
   const float4* scale1 = reinterpret_cast<const float4*>(E.par + 128);
   const uint4* scale2 = reinterpret_cast<const uint4*>(E.par + 256);
@@ -233,6 +243,19 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
     const bool sc_valid = has_sc && (E.sc_mask == nullptr || E.sc_mask[r] != 0);
     tmem_ld_wait();
     tc_fence_before();
+    if (kGen && tap_mode == 1) {      // NMD tap on the raw conv output
+      float tv[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = bias[j4];
+        tv[j4 * 4 + 0] = valid ? __uint_as_float(raw[j4 * 4 + 0]) + b.x : 0.0f;
+        tv[j4 * 4 + 1] = valid ? __uint_as_float(raw[j4 * 4 + 1]) + b.y : 0.0f;
+        tv[j4 * 4 + 2] = valid ? __uint_as_float(raw[j4 * 4 + 2]) + b.z : 0.0f;
+        tv[j4 * 4 + 3] = valid ? __uint_as_float(raw[j4 * 4 + 3]) + b.w : 0.0f;
+      }
+      warp_cols_reduce<false>(tv, lane);
+      atomicAdd(E.tap, tv[0]);
+    }
     __half2 hv[16];
     if (folded) {
 #pragma unroll
@@ -259,6 +282,13 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
       }
     }
     if (kGen) act_apply_h2(hv, act1); else act_apply_h2(hv, ACT_GELU_TANH);
+    if (kGen && tap_mode == 2) {      // NMD tap after the first activation
+      __half2 tv[16];
+      const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tv[k] = valid ? hv[k] : zero;
+      atomicAdd(E.tap, warp_cols_reduce_h2<false>(tv, lane));
+    }
     if (has_aff2) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -269,6 +299,17 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
         for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hfma2(hv[c * 4 + k], a2[k], b2[k]);
       }
       if (kGen) act_apply_h2(hv, act2); else act_apply_h2(hv, ACT_GELU_TANH);
+    }
+    if (kGen && tap_mode == 3) {      // NMD tap on the launch output
+      __half2 tv[16];
+      const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tv[k] = valid ? hv[k] : zero;
+      atomicAdd(E.tap, warp_cols_reduce_h2<false>(tv, lane));
+    }
+    if (E.count != nullptr) {
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0 && bal) atomicAdd(E.count, __popc(bal));
     }
     if (pool_mode != 0) {
       __half2 tv[16];
@@ -283,8 +324,6 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
       } else {
         atomicAdd(E.pool, warp_cols_reduce_h2<false>(tv, lane));
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, valid);
-      if (lane == 0 && bal) atomicAdd(E.count, __popc(bal));
     }
     if (has_out) {
 #pragma unroll
@@ -425,7 +464,8 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         E.bar0 = smem_u32(s_bar);
         E.slow_mask = L.masking && !(L.zero_tap && s_clean_of(s_clean, itw, smem_u32(s_bar), g, gl));
         E.pool = p.pool + w * p.pool_pitch + lane;
-        E.count = p.count + w;
+        E.count = L.count_id >= 0 ? p.count + static_cast<long long>(L.count_id) * p.cap_windows + w : nullptr;
+        E.tap = L.tap_mode ? p.tap_sum + (static_cast<long long>(L.tap_slot) * p.n_windows + w) * p.tap_width + lane : nullptr;
         E.frames = p.frames;
         E.rpw = p.rpw;
         E.n_tiles = n_tiles;

@@ -255,7 +255,7 @@ int upload_f32(const float* h, size_t n, float** d) {
 // Leaves m->rs_ok false when the plan's dataflow is not the in-place two-buffer chain the kernel implements.
 int finish_resident(jg_model* m, const jg_head_desc* head) {
   const int n = static_cast<int>(m->layers.size());
-  bool ok = m->rs_ok && n >= 2 && m->n_taps == 0 && head->feat_dim == 64 && !std::getenv("JG_NO_RESIDENT");
+  bool ok = m->rs_ok && n >= 2 && (m->n_taps == 0 || m->tap_width == 64) && head->feat_dim == 64 && !std::getenv("JG_NO_RESIDENT");
   if (const char* e = std::getenv("JG_RESIDENT")) ok = ok && std::atoi(e) != 0;
   int arr_of[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mask_of[3] = {-2, -2, -2}, next_arr = 1;
   for (int l = 0; ok && l < n; ++l) {
@@ -294,7 +294,8 @@ int finish_resident(jg_model* m, const jg_head_desc* head) {
     // the compile-time epilogue shape, if the layer has one (conv_resident.cuh:EpiModeRs)
     const bool gelu1 = R.folded && R.act1 == jg::ACT_GELU_TANH;
     R.mode = jg::rs::EPI_RS_GENERIC;
-    if (gelu1 && !R.has_aff2 && R.pool_mode == 0 && R.out_arr != 0) R.mode = R.has_sc ? jg::rs::EPI_RS_LIGHT_SC : jg::rs::EPI_RS_LIGHT;
+    if (R.tap_mode != 0) R.mode = jg::rs::EPI_RS_GENERIC;
+    else if (gelu1 && !R.has_aff2 && R.pool_mode == 0 && R.out_arr != 0) R.mode = R.has_sc ? jg::rs::EPI_RS_LIGHT_SC : jg::rs::EPI_RS_LIGHT;
     else if (gelu1 && R.has_sc && R.has_aff2 && R.act2 == jg::ACT_GELU_TANH && R.pool_mode == 2 && R.out_arr == 0) R.mode = jg::rs::EPI_RS_FINAL_SUM;
     if (std::getenv("JG_RS_GENERIC")) R.mode = jg::rs::EPI_RS_GENERIC;
   }
@@ -798,7 +799,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
       const int rcin = L.f[LF_REAL_CIN] > 0 ? L.f[LF_REAL_CIN] : cin, rcout = L.f[LF_REAL_COUT] > 0 ? L.f[LF_REAL_COUT] : cout;
       const bool stem = n_prev == 0;
       bool ok = m->rs_ok && n_prev < jg::rs::kMaxLayersRs && cout == 64 && rcout <= 32 && k <= jg::rs::kMaxTapsRs &&
-                (stem ? (cin == 64 && L.f[LF_IN_BUF] == 0) : (cin == 64 && rcin <= 32)) && L.f[LF_TAP_MODE] == 0 && L.f[LF_DYT1] == 0 &&
+                (stem ? (cin == 64 && L.f[LF_IN_BUF] == 0) : (cin == 64 && rcin <= 32)) && L.f[LF_DYT1] == 0 &&
                 L.f[LF_DYT2] == 0 && L.f[LF_LN1] == 0 && L.f[LF_MASK_THR] <= 1 && L.f[LF_EPI_F32] == 0 && L.f[LF_HALVINGS] == 0 && L.f[LF_LEN_CEIL] == 0 && wk_odd == nullptr &&
                 L.f[LF_ACT1] <= 2 && L.f[LF_ACT2] <= 2 && (stem || (L.halo_l <= jg::rs::kGuardRs && L.halo_r <= jg::rs::kGuardRs));
       if (ok) {
@@ -820,6 +821,7 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
           ph[c] = f32_to_f16(L.f[LF_HAS_AFF2] ? par[3 * cout + c] : 1.0f);            // scale2
           ph[32 + c] = f32_to_f16(L.f[LF_HAS_AFF2] ? par[4 * cout + c] : 0.0f);       // shift2
           ph[64 + c] = f32_to_f16(par[5 * cout + c]);                                 // shortcut value at masked rows
+          pf[128 + c] = par[0 * cout + c];                                            // conv bias (raw-output NMD tap)
         }
         jg::rs::LayerRs& R = m->rs_par.layer[n_prev];
         R = jg::rs::LayerRs{};
@@ -828,6 +830,10 @@ int jg_model_create(jg_ctx* ctx, const jg_layer_desc* layers, int32_t n_layers, 
         R.act1 = L.f[LF_ACT1]; R.act2 = L.f[LF_ACT2]; R.has_aff2 = L.f[LF_HAS_AFF2]; R.pool_mode = L.f[LF_POOL_MODE];
         R.masking = L.f[LF_MASKING]; R.folded = L.folded ? 1 : 0; R.shrink_in = L.f[LF_CUM_SHRINK_IN]; R.shrink = L.f[LF_SHRINK];
         R.kc = kc; R.w_off = static_cast<uint32_t>(off);
+        // NMD taps: summed in the kernel, except a stem tap on the raw conv output, which stem_tap_kernel takes from token counts
+        R.tap_mode = linear_tap_layer ? 0 : L.f[LF_TAP_MODE];
+        R.tap_slot = L.f[LF_TAP_SLOT];
+        R.count_id = (L.f[LF_TAP_MODE] != 0 || L.f[LF_POOL_MODE] != 0) ? L.f[LF_MASK_OUT] : -1;
         if (stem) m->rs_stem_span = L.halo_l + L.halo_r;
       }
       m->rs_ok = ok;
@@ -972,7 +978,8 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       rp.period = period; rp.frames = m->frames; rp.rpw = rpw;
       rp.wblock = m->rs_block;
       rp.pool = m->pool; rp.pool_pitch = m->head.feat_dim;
-      rp.count = m->counts + static_cast<long long>(m->final_mask) * m->cap_windows;
+      rp.count = m->counts; rp.cap_windows = m->cap_windows;
+      rp.tap_sum = m->tap_sum; rp.tap_width = m->tap_width;
       rp.err = m->err;
       jg::rs::fill_layer_offsets(rp, S);
       JG_CUDA(cudaFuncSetAttribute(jg::rs::stack_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
@@ -986,6 +993,22 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       jg::rs::stack_resident_kernel<<<grid, jg::rs::kThreadsRs, S.total, st>>>(rp);
       ctx->launches++;
       JG_CUDA(cudaGetLastError());
+      {   // a stem tap on the raw conv output is linear in the one-hot input: taken from token counts, like on the per-layer path
+        Layer& L0 = m->layers[0];
+        if (L0.w_tap != nullptr && L0.f[LF_TAP_MODE] == 1) {
+          const int cout0 = L0.f[LF_COUT];
+          jg::StemTapParams tp{};
+          tp.tokens = d_tokens; tp.lpad = d_lpad; tp.count = m->counts + static_cast<long long>(L0.f[LF_MASK_OUT]) * m->cap_windows;
+          tp.w = L0.w_tap; tp.wsum = L0.w_tap + static_cast<size_t>(L0.f[LF_K]) * 64 * cout0; tp.bias = L0.par;
+          tp.tap = m->tap_sum + static_cast<long long>(L0.f[LF_TAP_SLOT]) * n_windows * m->tap_width;
+          tp.n_windows = n_windows; tp.lc = lc; tp.pitch = pitch; tp.frames = m->frames; tp.tok_offset = m->tok_offset;
+          tp.ntaps = L0.f[LF_K]; tp.shrink = L0.f[LF_SHRINK]; tp.cout = cout0;
+          for (int t = 0; t < L0.f[LF_K]; ++t) tp.shifts[t] = L0.shifts_h[t];
+          jg::stem_tap_kernel<<<grid_for(n_windows, 1, ctx->num_sms, 16), 128, 0, st>>>(tp);
+          ctx->launches++;
+          JG_CUDA(cudaGetLastError());
+        }
+      }
       if (m->profiling) {     // the one launch is booked on the last conv layer; every layer gets the windows it covered
         JG_CUDA(cudaEventRecord(ev1, st));
         m->prof_events.emplace_back(ev0, ev1);

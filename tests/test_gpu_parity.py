@@ -1126,10 +1126,49 @@ def test_500bp_nmd_merge_model_vs_oracle():
     for use_ref in (False, True):
         eng = B200Engine(spec=spec, weights=w, use_ref_kernels=use_ref)
         y = eng.predict(WindowSource(records=recs, fsize=500, stride=500))
+        if not use_ref:                                   # narrow stack: the window-resident kernel, NMD taps included
+            assert "stack_resident_kernel" in eng.conv_kernel_names()
         eng.close()
         assert y["nmd"].shape == ref["nmd"].shape and y["embedding"].shape == ref["embedding"].shape
         for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
             assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))
+
+
+@pytest.mark.parametrize("tap", ["raw_stem", "after_act", "return_nmd"])
+def test_window_resident_kernel_nmd_taps_vs_per_layer_kernels(tap, monkeypatch):
+    """NMD taps inside the window-resident kernel -- on the raw stem output (taken from token counts by stem_tap_kernel on both
+    paths), after an activation, on the launch output, and `masked_batchnorm(return_nmd=True)` in front of a norm -- against the
+    per-layer kernels (JG_RESIDENT=0) and the fp32 oracle, with N runs in the windows (masked sums and counts)."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    from tests.test_plan_cpu import nmd_merge_500bp_config
+    import copy
+    cfg = copy.deepcopy(nmd_merge_500bp_config())        # the two tails of the config share their layer dicts
+    hl = cfg["model"]["representation_learner"]["hidden_layers"]
+    if tap == "raw_stem":            # conv -> nmd -> norm -> act: the tap reads the raw conv output
+        hl.insert(1, {"name": "nmd", "config": {}})
+        del hl[4]
+    elif tap == "return_nmd":        # the stem's BatchNorm returns the NMD of its input
+        hl[1] = {"name": "masked_batchnorm", "config": {"return_nmd": True}}
+        del hl[3]
+    spec = parse_project(cfg)
+    w = init_random(spec, 3)
+    recs = random_contigs(43, [500] * 90 + [1700, 2600, 900], n_run_every=4, lower_every=0)
+    seqs = [s[i:i + 500] for _, s in recs for i in range(0, len(s) - 499, 500)]
+    ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 500))
+    got = {}
+    for resident in ("1", "0"):
+        monkeypatch.setenv("JG_RESIDENT", resident)
+        eng = B200Engine(spec=spec, weights=w)
+        got[resident] = eng.predict(WindowSource(records=recs, fsize=500, stride=500))
+        assert ("stack_resident_kernel" in eng.conv_kernel_names()) == (resident == "1")
+        eng.close()
+        for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 4e-3), ("reliability", 4e-3)):
+            assert np.abs(ref[k] - got[resident][k]).max() <= tol, (k, resident, float(np.abs(ref[k] - got[resident][k]).max()))
+    for k in ("prediction", "nmd", "reliability"):
+        assert np.abs(got["1"][k] - got["0"][k]).max() <= 2e-3, k
 
 
 def test_reference_dataset_protocol_batches_and_evaluate(standin):
