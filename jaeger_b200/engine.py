@@ -469,7 +469,6 @@ class B200Engine:
     def _predict_source(self, src: WindowSource) -> dict[str, np.ndarray]:
         raw_names, host, offsets = src.load()
         fsize, stride = int(src.fsize), int(src.stride)
-        names = [n.strip().replace(",", "___") for n in raw_names]        # seqops/io.py:109
         lens = np.diff(offsets)
         total = int(offsets[-1])
         two_pass = src.min_len is not None and src.min_len < fsize      # commands/predict.py:771-810
@@ -522,6 +521,8 @@ class B200Engine:
                 out["_counts"], out["_skew"] = counts, skew
                 results.append(out)
                 tables.append((contig, start, nb, ordinal, last))
+            # header clean-up (seqops/io.py:109) on the host while the device works through the launches queued above
+            names = [n.strip().replace(",", "___") for n in raw_names]
             keep = None if src.outputs is None else set(src.outputs)
             host_out = [{k: v.cpu() for k, v in r.items() if keep is None or k in keep or k.startswith("_")} for r in results]
         self.ctx.sync()

@@ -87,7 +87,8 @@ def _window_numbers(y_pred) -> dict[str, np.ndarray]:
     result carries one (no round trip through the meta byte strings), else parsed from meta_0..9."""
     t = getattr(y_pred, "window_table", None)
     if t is not None and t.contig is not None:
-        names = np.array(t.headers, dtype=str)
+        names = np.empty(len(t.headers), dtype=object)      # object array: no copy of a million header strings into a fixed-width buffer
+        names[:] = t.headers
         skew = np.where(t.skew100 == (1 << 14), 0, t.skew100).astype(float) / 100.0
         return {"is_last": t.is_last, "headers": names[t.contig], "seqlen": t.seqlen.astype(np.int32),
                 "g": t.counts[:, 0].astype(float), "c": t.counts[:, 1].astype(float), "a": t.counts[:, 2].astype(float),

@@ -236,8 +236,9 @@ def test_unsupported_layers_fail_loudly():
         parse_project(cfg)
     cfg = small_config()
     cfg["model"]["representation_learner"]["hidden_layers"][0]["config"]["mask_mode"] = "strict"
-    with pytest.raises(NotImplementedError):
-        parse_project(cfg)
+    spec = parse_project(cfg)             # the mode itself is supported; residual blocks behind it are not (plan.py)
+    with pytest.raises(NotImplementedError, match="un-masked tensor"):
+        compile_plan(spec, init_random(spec, 0))
 
 
 def test_cabi_exports_every_declared_symbol():
