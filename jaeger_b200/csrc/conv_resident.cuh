@@ -37,12 +37,14 @@ namespace rs {
 using namespace jg::tc;
 using jg::tc2::fence_async_smem;
 using jg::ws::h2u;
+using jg::ws::named_bar_sync;
 
 constexpr int kMaxLayersRs = 12;
 constexpr int kMaxTapsRs = 8;
 constexpr int kGuardRs = 8;                              // zero rows before / after a window's rows in every chunk plane
 constexpr int kEpiWarpsRs = 16;
-constexpr int kThreadsRs = (kEpiWarpsRs + 2) * 32;
+constexpr int kBuildersRs = 2;                           // builder warps: stem tile i is built by builder i % 2
+constexpr int kThreadsRs = (kEpiWarpsRs + 1 + kBuildersRs) * 32;
 constexpr int kMaxTilesRs = 8;                           // 8 tiles x 32 columns x 2 sets = 512 TMEM columns
 constexpr int kParBytesRs = 640;                         // per layer: shift1 f32[32] | scale1 f32[32] | scale2 h[32] | shift2 h[32] | scc h[32] | pad | bias f32[32] @ 512
 constexpr int kTokWordsRs = 12;                          // token words a builder lane prefetches: frames x pitch <= 32 x 12 x 4 bytes
@@ -70,6 +72,10 @@ struct LayerRs {
   // setup is a handful of independent constant loads; kNoneRs = absent.  e_mask_in of the stem is that of even windows
   // (odd windows: + 3 mask arrays).
   uint32_t e_par, e_mask_in, e_mask_out, e_out, e_sc, e_sc_mask;
+  // the MMA warp's per-layer constants, also from the launcher: byte offset of the A operand of tile 0 / tap 0 (guard rows and the
+  // first tap's shift included; stem: of staging slot 0), its chunk-plane pitch, byte offset of the weight image, tap-to-tap row
+  // step, and which unrolled issue routine fits (0 generic, 1 = 3 taps x 2 K pairs, 2 = 5 x 2, 3 = stem 7 x 4)
+  uint32_t i_a_off, i_plane, i_b_off, i_dil, i_shape;
 };
 constexpr uint32_t kNoneRs = 0xFFFFFFFFu;
 
@@ -87,6 +93,7 @@ struct ResidentParams {
   float* tap_sum;          // [n_taps][n_windows][tap_width] masked column sums, pre-zeroed
   int tap_width;
   int* err;
+  long long* dbg;          // probe only (JG_RS_TRACE=1): clock64 timeline of CTA 0's fourth window, [layer][tile][4] + [1024..) misc
   LayerRs layer[kMaxLayersRs];
 };
 
@@ -130,6 +137,15 @@ inline void fill_layer_offsets(ResidentParams& p, const SmemRs& S) {
     L.e_out = L.out_arr ? static_cast<uint32_t>(L.out_arr - 1) * S.buf_bytes : kNoneRs;
     L.e_sc = L.sc_arr ? static_cast<uint32_t>(L.sc_arr - 1) * S.buf_bytes : kNoneRs;
     L.e_sc_mask = (L.sc_arr && !L.sc_all_valid) ? mask(L.sc_arr) : kNoneRs;
+    const bool stem = L.in_arr == 0;
+    int smin = 0;
+    for (int t = 0; t < L.ntaps; ++t) smin = L.shifts[t] < smin ? L.shifts[t] : smin;
+    const int rs0 = stem ? L.shifts[0] - smin : L.shifts[0];
+    L.i_plane = stem ? S.slot_plane : S.plane_bytes;
+    L.i_a_off = (stem ? S.buf_off[1] : static_cast<uint32_t>(L.in_arr - 1) * S.buf_bytes + kGuardRs * 16u) + static_cast<uint32_t>(rs0 * 16);
+    L.i_b_off = S.w_off + L.w_off;
+    L.i_dil = L.ntaps > 1 ? static_cast<uint32_t>(L.shifts[1] - L.shifts[0]) : 0u;      // taps are equally spaced
+    L.i_shape = stem ? ((L.ntaps == 7 && L.kc == 8) ? 3u : 0u) : (L.ntaps == 3 && L.kc == 4) ? 1u : (L.ntaps == 5 && L.kc == 4) ? 2u : 0u;
   }
 }
 
@@ -170,6 +186,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d, uint32_t a_lo, uint32_t b
 constexpr uint32_t kBarAccFull = 0, kBarTileDone = 8, kBarOhFull = 16, kBarOhFree = 19, kBarWinDone = 22;
 
 struct LayerIssue {
+  long long* dbg;
   uint32_t idesc, hi, bar0, slot_step, n_slots;
   uint32_t a_lo, b_lo, dil, a_kk, d0, prev;
   int n_tiles, ntaps, kk;
@@ -194,6 +211,7 @@ struct EpiLayer {
   float* tap;                  // this window's row of the layer's tap slot, at the thread's lane (nullptr: no tap)
   int* count;                  // this window's counter of the layer's mask (nullptr: nobody needs it)
   uint32_t plane_bytes, acc, parity, bar0;
+  long long* dbg;              // trace slot of this layer (nullptr = off)
   int limit, frames, rpw, n_tiles;
   bool slow_mask;              // masked codons in this window (or no tap at shift 0): evaluate the "any" rule per row
 };
@@ -227,6 +245,7 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
     const int i = g + 4 * h;
     if (i >= E.n_tiles) break;
     mbar_wait(E.bar0 + (kBarAccFull + static_cast<uint32_t>(i)) * 8u, E.parity);
+    if (E.dbg && (threadIdx.x & 127) == 0) E.dbg[i * 4 + 2] = clock64();
     tc_fence_after();
     uint32_t raw[32];
     tmem_ld32(E.acc + static_cast<uint32_t>(i) * 32u, raw);
@@ -344,6 +363,7 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(E.bar0 + (kBarTileDone + static_cast<uint32_t>(i)) * 8u);
+    if (E.dbg && (threadIdx.x & 127) == 0) E.dbg[i * 4 + 3] = clock64();
   }
 }
 
@@ -371,6 +391,7 @@ __device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, ui
       if (++oh_slot == I.n_slots) { oh_slot = 0; oh_phase ^= 1u; }
     }
     tc_fence_after();
+    if (I.dbg && (threadIdx.x & 31) == 0) I.dbg[i * 4 + 0] = clock64();
     const uint32_t d = I.d0 + static_cast<uint32_t>(i) * 32u;
     const uint32_t a_lo = I.a_lo + (kStem ? slot * I.slot_step : static_cast<uint32_t>(i) * (kTileM * 16u >> 4));
     if (leader) {
@@ -387,6 +408,7 @@ __device__ __forceinline__ void layer_tiles(const LayerIssue& I, bool leader, ui
       if (I.last && i == I.n_tiles - 1) umma_commit(I.bar0 + kBarWinDone * 8u);
     }
     __syncwarp();
+    if (I.dbg && (threadIdx.x & 31) == 0) I.dbg[i * 4 + 1] = clock64();
   }
 }
 
@@ -469,6 +491,7 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         E.frames = p.frames;
         E.rpw = p.rpw;
         E.n_tiles = n_tiles;
+        E.dbg = (p.dbg != nullptr && blockIdx.x == 0 && itw == 3) ? p.dbg + l * 32 : nullptr;
         switch (L.mode) {
           case EPI_RS_LIGHT: epi_layer<EPI_RS_LIGHT>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
           case EPI_RS_LIGHT_SC: epi_layer<EPI_RS_LIGHT_SC>(E, L, g, lane, rw0, fr0, jj0, rw1, fr1, jj1); break;
@@ -487,38 +510,33 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     I.bar0 = smem_u32(s_bar);
     I.slot_step = S.slot_bytes >> 4;
     I.n_slots = S.n_slots;
-    const uint32_t w_base = smem_u32(smem + S.w_off);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
     uint32_t gl = 0, oh_slot = 0, oh_phase = 0;
     for (long long w = w0; w < p.n_windows; w += wstep) {
       for (int l = 0; l < n_layers; ++l, ++gl) {
-        // everything that is constant over the layer's tiles is computed here, once (the per-tile code of this one warp is the
-        // serial section of the whole kernel)
-        const LayerRs& L = p.layer[l];
-        const bool stem = L.in_arr == 0;
-        const uint32_t plane = stem ? S.slot_plane : S.plane_bytes;
-        const int rs0 = stem ? L.shifts[0] - stem_min : L.shifts[0];
-        const uint32_t a_base = (stem ? smem_u32(smem + S.buf_off[1]) : smem_u32(smem + static_cast<uint32_t>(L.in_arr - 1) * S.buf_bytes) + kGuardRs * 16u) +
-                                static_cast<uint32_t>(rs0 * 16);
+        // Everything that is constant over the layer's tiles comes ready-made from the launcher (fill_layer_offsets): the per-layer
+        // and per-tile code of this one warp is the serial section of the whole kernel (a layer's period = its eight tiles here).
         // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
-        // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous
-        I.a_lo = ((a_base >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
-        I.b_lo = (((w_base + L.w_off) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
-        I.dil = L.ntaps > 1 ? static_cast<uint32_t>(L.shifts[1] - L.shifts[0]) : 0u;      // taps are equally spaced
-        I.a_kk = 2u * (plane >> 4);
+        // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous.
+        const LayerRs& L = p.layer[l];
+        const uint32_t plane16 = L.i_plane >> 4, shape = L.i_shape;
+        const bool stem = L.in_arr == 0;
+        I.a_lo = ((smem16 + (L.i_a_off >> 4)) & 0x3FFFu) | ((plane16 & 0x3FFFu) << 16);
+        I.b_lo = ((smem16 + (L.i_b_off >> 4)) & 0x3FFFu) | ((512u >> 4) << 16);
+        I.dil = L.i_dil;
+        I.a_kk = 2u * plane16;
         I.d0 = tmem + (gl & 1u) * 256u;
         I.prev = (gl - 1u) & 1u;
         I.wait_prev = gl > 0u;
         I.last = l == n_layers - 1;
         I.ntaps = L.ntaps;
         I.kk = L.kc / 2;
-        if (stem) {
-          if (L.ntaps == 7 && L.kc == 8) layer_tiles<7, 4, true>(I, leader, oh_slot, oh_phase);
-          else layer_tiles<0, 0, true>(I, leader, oh_slot, oh_phase);
-        } else {
-          if (L.ntaps == 3 && L.kc == 4) layer_tiles<3, 2, false>(I, leader, oh_slot, oh_phase);
-          else if (L.ntaps == 5 && L.kc == 4) layer_tiles<5, 2, false>(I, leader, oh_slot, oh_phase);
-          else layer_tiles<0, 0, false>(I, leader, oh_slot, oh_phase);
-        }
+        I.dbg = (p.dbg != nullptr && blockIdx.x == 0 && w == w0 + 3 * wstep) ? p.dbg + l * 32 : nullptr;
+        if (shape == 1u) layer_tiles<3, 2, false>(I, leader, oh_slot, oh_phase);
+        else if (shape == 3u) layer_tiles<7, 4, true>(I, leader, oh_slot, oh_phase);
+        else if (shape == 2u) layer_tiles<5, 2, false>(I, leader, oh_slot, oh_phase);
+        else if (stem) layer_tiles<0, 0, true>(I, leader, oh_slot, oh_phase);
+        else layer_tiles<0, 0, false>(I, leader, oh_slot, oh_phase);
       }
     }
   } else {
@@ -552,23 +570,31 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
       clean = __all_sync(0xffffffffu, clean);
       if (lane == 0) s_clean[itp & 1u] = clean ? 1 : 0;     // published by the OH_FULL arrive of the window's first stem tile
     };
+    // Two builder warps (one 128-row one-hot tile takes a single warp ~2 000 cycles, the stem's MMAs of a tile ~1 200): builder b
+    // builds the tiles of parity b; builder 0 also prepares the next window.  Both walk the same slot ring over ALL tiles.
+    const int bld = warp - (kEpiWarpsRs + 1);
     uint8_t* stage = smem + S.buf_off[1];
     uint32_t it = 0, slot = 0, sphase = 0;
     bool first_lap = true;
-    int lim_next = 0;
-    if (w0 < p.n_windows) {
+    if (bld == 0 && w0 < p.n_windows) {
       fetch(w0);
       const int lp0 = p.lpad[w0];
-      lim_next = lp0 < p.lc ? lp0 : p.lc;
-      prepare(0u, lim_next);
+      prepare(0u, lp0 < p.lc ? lp0 : p.lc);
       if (w0 + wstep < p.n_windows) fetch(w0 + wstep);
     }
     for (long long w = w0; w < p.n_windows; w += wstep, ++it) {
-      const int lim = lim_next;
+      // builder 0 has written this window's tokens / mask / flag (at the end of its previous iteration); builder 1 reads the tokens
+      named_bar_sync(1, 32 * kBuildersRs);
+      const int lpw = p.lpad[w];
+      const int lim = lpw < p.lc ? lpw : p.lc;
       const uint8_t* tok = smem + S.tok_off + (it & 1u) * S.tok_bytes;
       // the previous window's last MMAs (the last readers of H, where the one-hot tiles are staged) are done
       if (it > 0) mbar_wait(WIN_DONE, (it - 1u) & 1u);
       for (int i = 0; i < n_tiles; ++i) {
+        if ((i & 1) != bld) {            // the other builder's tile: only advance the ring
+          if (++slot == S.n_slots) { slot = 0; sphase ^= 1u; first_lap = false; }
+          continue;
+        }
         if (!first_lap) mbar_wait(OH_FREE(slot), sphase ^ 1u);
         uint8_t* sl = stage + slot * S.slot_bytes;
         int r = i * kTileM + stem_min + lane;
@@ -592,10 +618,9 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         if (lane == 0) mbar_arrive(OH_FULL(slot));
         if (++slot == S.n_slots) { slot = 0; sphase ^= 1u; first_lap = false; }
       }
-      if (w + wstep < p.n_windows) {       // the next window's tokens, mask and flag, while this one runs through its layers
+      if (bld == 0 && w + wstep < p.n_windows) {       // the next window's tokens, mask and flag, while this one runs through its layers
         const int lpn = p.lpad[w + wstep];
-        lim_next = lpn < p.lc ? lpn : p.lc;
-        prepare(it + 1u, lim_next);
+        prepare(it + 1u, lpn < p.lc ? lpn : p.lc);
         if (w + 2 * wstep < p.n_windows) fetch(w + 2 * wstep);
       }
     }

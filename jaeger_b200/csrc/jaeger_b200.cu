@@ -982,6 +982,12 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       rp.tap_sum = m->tap_sum; rp.tap_width = m->tap_width;
       rp.err = m->err;
       jg::rs::fill_layer_offsets(rp, S);
+      long long* d_trace = nullptr;
+      if (std::getenv("JG_RS_TRACE")) {          // probe only: per-tile clock64 timeline of CTA 0's fourth window, printed to stderr
+        JG_CUDA(cudaMalloc(&d_trace, 2048 * 8));
+        JG_CUDA(cudaMemsetAsync(d_trace, 0, 2048 * 8, st));
+      }
+      rp.dbg = d_trace;
       JG_CUDA(cudaFuncSetAttribute(jg::rs::stack_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (m->profiling) {
@@ -993,6 +999,21 @@ int jg_model_forward(jg_ctx* ctx, jg_model* m, const uint8_t* d_tokens, const in
       jg::rs::stack_resident_kernel<<<grid, jg::rs::kThreadsRs, S.total, st>>>(rp);
       ctx->launches++;
       JG_CUDA(cudaGetLastError());
+      if (d_trace) {
+        std::vector<long long> h(2048);
+        JG_CUDA(cudaStreamSynchronize(st));
+        JG_CUDA(cudaMemcpy(h.data(), d_trace, 2048 * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        long long t0 = h[0];
+        for (int i = 0; i < m->rs_par.n_layers * 32; ++i) if (h[i] > 0 && h[i] < t0) t0 = h[i];
+        std::fprintf(stderr, "resident trace (cycles from the window's first event; per tile: mma wait-done, mma issued, epi acc-ready, epi done)\n");
+        for (int l = 0; l < m->rs_par.n_layers; ++l) {
+          std::fprintf(stderr, "L%d:", l);
+          for (int i = 0; i < rpw / jg::kTileM; ++i)
+            std::fprintf(stderr, "  t%d[%lld %lld | %lld %lld]", i, h[l * 32 + i * 4] - t0, h[l * 32 + i * 4 + 1] - t0, h[l * 32 + i * 4 + 2] - t0, h[l * 32 + i * 4 + 3] - t0);
+          std::fprintf(stderr, "\n");
+        }
+      }
       {   // a stem tap on the raw conv output is linear in the one-hot input: taken from token counts, like on the per-layer path
         Layer& L0 = m->layers[0];
         if (L0.w_tap != nullptr && L0.f[LF_TAP_MODE] == 1) {
