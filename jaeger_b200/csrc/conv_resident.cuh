@@ -118,7 +118,8 @@ __host__ __device__ inline SmemRs smem_rs(int rpw, int n_layers, uint32_t w_byte
   S.tok_off = S.mask_off[3] + S.mask_bytes;
   S.tok_bytes = (static_cast<uint32_t>(frames * pitch) + 15u) & ~15u;
   S.bar_off = S.tok_off + 2u * S.tok_bytes;
-  S.total = S.bar_off + 256u + 128u;                       // barriers + TMEM pointer, + slack to align the base to 128 B
+  S.total = S.bar_off + 256u + static_cast<uint32_t>(kMaxLayersRs) * 32u + 128u;   // barriers + TMEM pointer, the MMA warp's per-layer
+                                                                                    // table, + slack to align the base to 128 B
   S.slot_rows = static_cast<uint32_t>(128 + stem_span + 7) / 8u * 8u;
   S.slot_plane = S.slot_rows * 16u;
   S.slot_bytes = 8u * S.slot_plane;
@@ -452,6 +453,18 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     uint4* pd = reinterpret_cast<uint4*>(smem + S.par_off);
     for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(n_layers) * kParBytesRs / 16u; i += kThreadsRs) pd[i] = psrc[i];
   }
+  // the MMA warp's per-layer constants as a shared-memory table (two 16-byte loads per layer instead of a chain of indexed constant
+  // loads: the gap between the last tile of a layer and the first of the next was ~800 cycles of this one warp's serial time)
+  uint4* s_lay = reinterpret_cast<uint4*>(smem + S.bar_off + 256u);
+  if (threadIdx.x < static_cast<unsigned>(n_layers)) {
+    const LayerRs& L = p.layer[threadIdx.x];
+    const uint32_t smem16 = smem_u32(smem) >> 4, plane16 = L.i_plane >> 4;
+    // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
+    // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous.
+    s_lay[threadIdx.x * 2 + 0] = make_uint4(((smem16 + (L.i_a_off >> 4)) & 0x3FFFu) | ((plane16 & 0x3FFFu) << 16),
+                                            ((smem16 + (L.i_b_off >> 4)) & 0x3FFFu) | ((512u >> 4) << 16), L.i_dil, 2u * plane16);
+    s_lay[threadIdx.x * 2 + 1] = make_uint4(static_cast<uint32_t>(L.ntaps), static_cast<uint32_t>(L.kc / 2), L.i_shape, L.in_arr == 0 ? 1u : 0u);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -510,7 +523,6 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     I.bar0 = smem_u32(s_bar);
     I.slot_step = S.slot_bytes >> 4;
     I.n_slots = S.n_slots;
-    const uint32_t smem16 = smem_u32(smem) >> 4;
     uint32_t gl = 0, oh_slot = 0, oh_phase = 0;
     for (long long w = w0; w < p.n_windows; w += wstep) {
       for (int l = 0; l < n_layers; ++l, ++gl) {
@@ -518,19 +530,19 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         // and per-tile code of this one warp is the serial section of the whole kernel (a layer's period = its eight tiles here).
         // K-major no-swizzle descriptors: LBO (bits 16-29 of the low word) = distance of the two K chunks of an MMA = one chunk
         // plane (A) / 512 B (B); SBO (high word) = 128 B: consecutive 8-row core matrices are contiguous.
-        const LayerRs& L = p.layer[l];
-        const uint32_t plane16 = L.i_plane >> 4, shape = L.i_shape;
-        const bool stem = L.in_arr == 0;
-        I.a_lo = ((smem16 + (L.i_a_off >> 4)) & 0x3FFFu) | ((plane16 & 0x3FFFu) << 16);
-        I.b_lo = ((smem16 + (L.i_b_off >> 4)) & 0x3FFFu) | ((512u >> 4) << 16);
-        I.dil = L.i_dil;
-        I.a_kk = 2u * plane16;
+        const uint4 q0 = s_lay[l * 2], q1 = s_lay[l * 2 + 1];
+        const uint32_t shape = q1.z;
+        const bool stem = q1.w != 0u;
+        I.a_lo = q0.x;
+        I.b_lo = q0.y;
+        I.dil = q0.z;
+        I.a_kk = q0.w;
         I.d0 = tmem + (gl & 1u) * 256u;
         I.prev = (gl - 1u) & 1u;
         I.wait_prev = gl > 0u;
         I.last = l == n_layers - 1;
-        I.ntaps = L.ntaps;
-        I.kk = L.kc / 2;
+        I.ntaps = static_cast<int>(q1.x);
+        I.kk = static_cast<int>(q1.y);
         I.dbg = (p.dbg != nullptr && blockIdx.x == 0 && w == w0 + 3 * wstep) ? p.dbg + l * 32 : nullptr;
         if (shape == 1u) layer_tiles<3, 2, false>(I, leader, oh_slot, oh_phase);
         else if (shape == 3u) layer_tiles<7, 4, true>(I, leader, oh_slot, oh_phase);
