@@ -23,9 +23,10 @@
 // i-1 .. i+1 (mbarrier TILE_DONE), so the tensor pipe and the epilogue warps overlap across the layer boundary, and the next
 // window's stem overlaps the last layer's epilogue.
 //
-// Roles (576 threads, one persistent CTA per SM): warps 0-15 epilogue (group g = warp / 4 owns tiles g and g + 4; thread = row, the
+// Roles (608 threads, one persistent CTA per SM): warps 0-15 epilogue (group g = warp / 4 owns tiles g and g + 4; thread = row, the
 // same two rows of the window for every layer, so frame / position are computed once), warp 16 MMA issuer (+ TMEM allocation),
-// warp 17 builder (tokens -> token mask + one-hot tiles; prefetches the next window's tokens into registers).
+// warps 17 / 18 builders (tokens -> token mask + one-hot tiles of their tile parity; builder 0 prefetches the next window's tokens
+// into registers and prepares its mask while the current window runs).
 // The epilogue arithmetic is the generic epilogue of conv_epilogue.cuh (fp32 affine, packed fp16 from there on), so the numerics
 // equal the per-layer kernels'.
 #pragma once
