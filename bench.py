@@ -326,8 +326,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    pending = []       # per-contig records of the steps of the current leg, gathered on rank 0 at the END of the leg
+
     def gather_results(pred_sum, consensus, i):
-        """NCCL is used only to gather the per-contig results on rank 0: one pre-sized gather."""
+        """NCCL is used only to deliver the per-contig results to rank 0.  The records of a step are kept on the
+        device and the pre-sized gathers (parallel.gather_contig_records: no size exchange, no host synchronisation) run after the
+        leg's last step, inside the timed region: a gather per step would make every rank wait for the slowest one every step, and
+        the driver writes its tables at the end of a run anyway."""
         if world == 1:
             return
         rec = torch.cat([pred_sum.float(), consensus.float().unsqueeze(1)], dim=1)
@@ -335,7 +340,12 @@ def run_b200(args):
             full = torch.zeros((len(shards_per_step[i][rank]), rec.shape[1]), device=dev)
             full[:rec.shape[0]] = rec
             rec = full
-        gather_contig_records(rec, shards_per_step[i], n_global[i], dst=0)
+        pending.append((rec, i))
+
+    def flush_gathers():
+        for rec, i in pending:
+            gather_contig_records(rec, shards_per_step[i], n_global[i], dst=0)
+        pending.clear()
 
     def device_step(i, x):
         agg, w, c = eng.classify_long(x, host_batches[i][1], fsize, stride)
@@ -369,6 +379,7 @@ def run_b200(args):
         dev_batches = [p.to(dev) for p in pinned]
         for i in range(args.warmup):
             device_step(i, dev_batches[i])
+        flush_gathers()
         barrier()
         eng.set_profiling(True)
         sampler = ClockSampler(local)
@@ -380,8 +391,12 @@ def run_b200(args):
         for i in range(args.warmup, n_batches):
             w, c = device_step(i, dev_batches[i])
             n_bases += int(host_batches[i][1].sum()); n_windows += w; n_contigs += c
+        ev_own = torch.cuda.Event(enable_timing=True)
+        ev_own.record(stream)                   # this rank's own work, before it meets the others in the gathers
+        flush_gathers()
         ev1.record(stream)
         barrier()
+        own_ms = ev0.elapsed_time(ev_own)
         ms = ev0.elapsed_time(ev1)
         launches = eng.ctx.launch_count - launches0
         clocks = sampler.stop()
@@ -390,11 +405,17 @@ def run_b200(args):
         del dev_batches
     # ---- leg 2: end to end through the engine's public call with host buffers ---------------------
     e2e_step(0)                                 # one untimed end-to-end step: no first-use cost in the first timed one
+    if world > 1:
+        with torch.cuda.stream(stream):
+            flush_gathers()
     barrier()
     t0 = time.perf_counter()
     h2d_bytes = d2h_bytes = 0
     for i in range(args.warmup, n_batches):
         _, h2d_bytes, d2h_bytes = e2e_step(i)
+    if world > 1:
+        with torch.cuda.stream(stream):
+            flush_gathers()
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -404,6 +425,9 @@ def run_b200(args):
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(tmax[0]), float(tmax[1])
         tot_bases, tot_windows, launches = float(tsum[2]), float(tsum[3]), int(tsum[4])
+        own = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(own, torch.tensor([own_ms], device=dev, dtype=torch.float64))
+        rank_ms = [float(x[0]) / args.steps for x in own]
     else:
         e2e_ms, tot_bases, tot_windows = e2e_s * 1e3, float(n_bases), float(n_windows)
 
@@ -420,6 +444,8 @@ def run_b200(args):
                         "call": "B200Engine.predict(WindowSource.from_host(pinned host buffer)) -> reference result dict on the host, "
                                 "then postprocess.contig_table" + (" + prophage.call_regions" if wl.prophage else "")},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if world > 1:        # every rank's own device time per step before the final gathers: the spread is the GPUs' (power cap), not the path's
+            line["rank_ms_per_step"] = [round(v, 2) for v in rank_ms]
         agree = ROOT / "profiles" / "label_agreement_r2.json"
         if agree.exists():
             try:
