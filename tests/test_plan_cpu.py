@@ -636,3 +636,46 @@ def test_residual_block_after_a_thresholded_conv_is_refused():
         compile_plan(spec, init_random(spec, 0))
     with pytest.raises(ValueError, match="Invalid mask_mode"):
         parse_project(conv_stack_config(("most", "any", "any")))
+
+
+@pytest.mark.parametrize("variant", ["strided_bypass_mlp", "layernorm"])
+def test_saved_model_bundle_with_bypass_blocks_mlp_head_and_layernorm(tmp_path, variant):
+    """The bundle -> weights mapping for the round-2 layer variants: residual blocks with the conv3 / bn3 bypass (strided or
+    use_1x1conv), a classifier with two hidden Dense layers (picked by chaining the widths), MaskedLayerNormalization groups
+    (gamma / beta only).  Also what the reader refuses: several data shards, compressed index blocks, ambiguous Dense shapes."""
+    from jaeger_b200 import weights as W
+    from tests.tf_bundle_writer import keras3_export_names, write_bundle
+    cfg = small_strided_config() if variant == "strided_bypass_mlp" else layernorm_config(True, bypass=True)
+    spec = parse_project(cfg)
+    w = init_random(spec, 13)
+    graph = tmp_path / "model" / "jaeger_y_1M_fragment_graph"
+    names = keras3_export_names(spec, w)
+    write_bundle(graph / "variables", names)
+    tensors = W.read_tf_bundle(graph / "variables")
+    assert len(tensors) == len(names)
+    got = W.weights_from_bundle(spec, tensors)
+    _assert_same_weights({k: w[k] for k in ("layers", "classifier", "reliability") if k in w}, {k: got[k] for k in ("layers", "classifier", "reliability") if k in w})
+    tok = _tokens(2, 2, 120)
+    ref, again = ofw.forward(spec, w, tok), ofw.forward(spec, {**got, "embedding": w["embedding"]}, tok)
+    assert all(np.array_equal(ref[k], again[k]) for k in ref)
+    # two unused Dense kernels of the same shape cannot be told apart by shape: refused, not guessed
+    dup = dict(tensors)
+    k_cls = [k for k, v in tensors.items() if v.ndim == 2 and v.shape == np.asarray(w["classifier"][0]["kernel"]).shape][0]
+    dup[k_cls.replace("_operations/", "_operations/9")] = tensors[k_cls]
+    with pytest.raises(ValueError, match="ambiguous"):
+        W.weights_from_bundle(spec, dup)
+    # compressed index block / several data shards
+    idx = bytearray((graph / "variables" / "variables.index").read_bytes())
+    bad = tmp_path / "bad" / "variables"
+    bad.mkdir(parents=True)
+    (bad / "variables.data-00000-of-00001").write_bytes((graph / "variables" / "variables.data-00000-of-00001").read_bytes())
+    footer = bytes(idx[-48:])
+    pos = 0
+    for _ in range(2):
+        _, pos = W._varint(footer, pos)
+    idx_off, pos = W._varint(footer, pos)
+    idx_size, pos = W._varint(footer, pos)
+    idx[idx_off + idx_size] = 1                      # compression type byte of the index block: snappy
+    (bad / "variables.index").write_bytes(bytes(idx))
+    with pytest.raises(ValueError, match="compressed"):
+        W.read_tf_bundle(bad)

@@ -63,6 +63,15 @@ def write_bundle(variables_dir: str | Path, tensors: dict[str, np.ndarray], per_
     (d / "variables.data-00000-of-00001").write_bytes(bytes(data))
 
 
+def _norm_attrs(nw: dict):
+    """(bundle attribute, weights key) pairs of a norm layer: MaskedDYT, MaskedLayerNormalization (gamma / beta only), BatchNorm."""
+    if "alpha" in nw:
+        return (("alpha", "alpha"), ("gamma", "gamma"), ("beta", "beta"))
+    if "mean" not in nw:
+        return (("gamma", "gamma"), ("beta", "beta"))
+    return (("gamma", "gamma"), ("beta", "beta"), ("moving_mean", "mean"), ("moving_variance", "var"))
+
+
 def keras3_export_names(spec, weights: dict) -> dict[str, np.ndarray]:
     """The nested weights of `modelspec.init_random` keyed the way a Keras 3 `model.export()` keys them:
     `_operations/<i>/<attribute>` with built-in layers using `_kernel` / `_embeddings`, the reference's custom layers
@@ -80,21 +89,23 @@ def keras3_export_names(spec, weights: dict) -> dict[str, np.ndarray]:
             if layer.cfg["use_bias"]:
                 put(f"{op}/bias", lw["bias"])
         elif layer.kind == "norm":
-            for a, b in ((("alpha", "alpha"), ("gamma", "gamma"), ("beta", "beta")) if "alpha" in lw else
-                         (("gamma", "gamma"), ("beta", "beta"), ("moving_mean", "mean"), ("moving_variance", "var"))):
+            for a, b in _norm_attrs(lw):
                 put(f"{op}/{a}", lw[b])
         elif layer.kind == "nmd":
             put(f"{op}/moving_mean", lw["moving_mean"])
         elif layer.kind == "resblock":
             for j, blk in enumerate(lw["blocks"]):
-                for part in ("conv1", "conv2"):
+                for part in ("conv1", "conv2", "conv3"):            # conv3 / bn3: the bypass of a strided or use_1x1conv block
+                    if part not in blk:
+                        continue
                     put(f"{op}/blocks/{j}/{part}/kernel", blk[part]["kernel"])
                     if layer.cfg["use_bias"]:
                         put(f"{op}/blocks/{j}/{part}/bias", blk[part]["bias"])
-                for part in ("bn1", "bn2"):
+                for part in ("bn1", "bn2", "bn3"):
+                    if part not in blk:
+                        continue
                     nw = blk[part]
-                    for a, b in ((("alpha", "alpha"), ("gamma", "gamma"), ("beta", "beta")) if "alpha" in nw else
-                                 (("gamma", "gamma"), ("beta", "beta"), ("moving_mean", "mean"), ("moving_variance", "var"))):
+                    for a, b in _norm_attrs(nw):
                         put(f"{op}/blocks/{j}/{part}/{a}", nw[b])
         op += 1
     op += 2                                                    # pooling, dropout
