@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), str(SRC), "-lz"]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("JG_EXTRA_NVCC_FLAGS", "").split(), "-o", str(LIB), str(SRC), "-lz"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
