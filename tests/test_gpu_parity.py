@@ -1370,3 +1370,36 @@ def test_mask_modes_strict_and_majority_vs_oracle(modes):
         for k, tol in (("prediction", 4e-3), ("embedding", 1e-2), ("nmd", 1e-2), ("reliability", 1e-2)):
             assert np.abs(ref[k] - y[k]).max() <= tol, (k, use_ref, float(np.abs(ref[k] - y[k]).max()))
         eng.close()
+
+
+def test_window_resident_kernel_other_geometries(monkeypatch):
+    """The window-resident kernel away from the 500 bp / 8-tile geometry: 300 bp windows (6 tiles: two epilogue groups own one tile
+    only), the padded short-contig pass (--min-len < --fsize: per-window frame lengths below the buffer's, batches padded to their
+    longest member) and a single-window call (one CTA), against the per-layer kernels and the oracle."""
+    from jaeger_b200 import B200Engine, WindowSource, init_random, parse_project
+    from jaeger_b200.modelspec import baseline_500bp_config
+    from oracle import encode as oenc
+    from oracle import forward as ofw
+    from tests.helpers import random_contigs
+    cfg = baseline_500bp_config()
+    cfg["model"]["string_processor"]["crop_size"] = 300
+    spec = parse_project(cfg)
+    w = init_random(spec, 7)
+    recs = random_contigs(12, [300] * 50 + [150, 180, 299, 240, 200, 900, 1000], n_run_every=4, lower_every=0)
+    got = {}
+    for resident in ("1", "0"):
+        monkeypatch.setenv("JG_RESIDENT", resident)
+        eng = B200Engine(spec=spec, weights=w)
+        got[resident] = eng.predict(WindowSource(records=recs, fsize=300, stride=300, min_len=150, batch=8))
+        assert ("stack_resident_kernel" in eng.conv_kernel_names()) == (resident == "1")
+        one = eng.predict(WindowSource(records=recs[:1], fsize=300, stride=300))
+        assert one["prediction"].shape == (1, 3)
+        got[resident + "_one"] = one
+        eng.close()
+    assert got["1"]["prediction"].shape == got["0"]["prediction"].shape and got["1"]["prediction"].shape[0] > 55
+    assert np.abs(got["1"]["prediction"] - got["0"]["prediction"]).max() <= 2e-3
+    assert np.abs(got["1_one"]["prediction"] - got["0_one"]["prediction"]).max() <= 2e-3
+    # the long pass against the oracle (full 300-bp windows, in the engine's window order: long pass first)
+    seqs = [s[i:i + 300] for _, s in recs if len(s) >= 300 for i in range(0, len(s) - 299, 300)]
+    ref = ofw.forward(spec, w, oenc.encode_windows(seqs, 300))
+    assert np.abs(ref["prediction"] - got["1"]["prediction"][:len(seqs)]).max() <= 4e-3
