@@ -226,6 +226,19 @@ __device__ __forceinline__ bool s_clean_of(volatile int* s_clean, uint32_t itw, 
   return s_clean[itw & 1u] != 0;
 }
 
+// runtime-selected activation of the generic epilogue shape: tanh-GELU, ReLU or none (the launcher admits nothing else), without the
+// erf-GELU branch of act_apply_h2 -- the kernel's code size matters, the roles and epilogue shapes share one instruction cache
+__device__ __forceinline__ void act_rs(__half2 (&h)[16], int act) {
+  if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = gelu_tanh_h2(h[j]);
+  } else if (act == ACT_RELU) {
+    const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = __hmax2(h[j], z);
+  }
+}
+
 template <int kMode>
 __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, int g, int lane, int rw0, int fr0, int jj0, int rw1, int fr1, int jj1) {
   constexpr bool kGen = kMode == EPI_RS_GENERIC;
@@ -302,7 +315,7 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
         for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hadd2(hv[c * 4 + k], s2[k]);
       }
     }
-    if (kGen) act_apply_h2(hv, act1); else act_apply_h2(hv, ACT_GELU_TANH);
+    if (kGen) act_rs(hv, act1); else act_rs(hv, ACT_GELU_TANH);
     if (kGen && tap_mode == 2) {      // NMD tap after the first activation
       __half2 tv[16];
       const __half2 zero = __float2half2_rn(0.0f);
@@ -319,7 +332,7 @@ __device__ __forceinline__ void epi_layer(const EpiLayer& E, const LayerRs& L, i
 #pragma unroll
         for (int k = 0; k < 4; ++k) hv[c * 4 + k] = __hfma2(hv[c * 4 + k], a2[k], b2[k]);
       }
-      if (kGen) act_apply_h2(hv, act2); else act_apply_h2(hv, ACT_GELU_TANH);
+      if (kGen) act_rs(hv, act2); else act_rs(hv, ACT_GELU_TANH);
     }
     if (kGen && tap_mode == 3) {      // NMD tap on the launch output
       __half2 tv[16];
