@@ -222,9 +222,11 @@ def _classify_source(engine, src, kwargs: dict[str, Any], fsize: int, stride: in
     return {"y_pred": y_pred, "data": data, "df": df, "regions": regions, "windows": n_windows, "predict_seconds": t1 - t0}
 
 
-def _write_prophage_outputs(engine, loaded, regions, out_dir: Path, base: str, fsize: int, stride: int, result: dict, append: bool = False):
-    """<base>_prophage_regions.tsv and the att-site report <base>_prophages/prophages_jaeger.tsv (predict.py:372-376, 430-437;
-    postprocess/prophages.py:706-873 without the gene-call refinement)."""
+def _write_prophage_outputs(engine, loaded, regions, out_dir: Path, base: str, fsize: int, stride: int, result: dict, append: bool = False,
+                            genes: str | None = None):
+    """<base>_prophage_regions.tsv and the att-site report <base>_prophages/prophages_jaeger.tsv (predict.py:372-376, 386-394,
+    430-437; postprocess/prophages.py:706-873).  Region ends are snapped out of coding genes first (prophage_boundaries.py) when
+    gene calls are available: the `--genes` table, or pyrodigal-gv when that package is installed; else the raw ends are used."""
     rows = [] if append else ["contig_id\tstart\tend\twindow_start\twindow_end\tscore"]
     for name, r in regions.items():
         for (ws, we), (s, e), sc in zip(r["ranges"], r["coords"], r["scores"]):
@@ -235,7 +237,15 @@ def _write_prophage_outputs(engine, loaded, regions, out_dir: Path, base: str, f
     from .termini import prophage_report_loaded, write_prophage_report
     t_att = time.time()
     try:                                              # the reference logs and carries on (predict.py:440-442)
-        report = prophage_report_loaded(engine, loaded, regions, fsize, stride)
+        from . import prophage_boundaries as pb
+        refined = None
+        genes_of = pb.gene_source(pb.load_gene_table(genes) if genes else None, loaded)
+        if genes_of is not None:
+            refined = pb.refine_regions(regions, loaded[0], np.diff(loaded[2]), fsize, stride, genes_of)
+            moved = sum(1 for rows in refined.values() for r in rows if (r[0], r[1]) != (r[2], r[3]))
+            logger.info(f"gene-aware boundaries: {moved} of {sum(len(v) for v in refined.values())} regions moved")
+            result.setdefault("refined_boundaries", {}).update(refined)
+        report = prophage_report_loaded(engine, loaded, regions, fsize, stride, refined_boundaries=refined)
         if append and result.get("prophage_report") is not None:
             import pandas as pd
             report = pd.concat([result["prophage_report"], report], ignore_index=True)
@@ -335,7 +345,7 @@ def run_core(**kwargs: Any) -> dict[str, Any]:
     logger.info(f"processed {n_written}/{n_records} sequences")
     if kwargs.get("prophage"):
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
-        _write_prophage_outputs(engine, full, regions or {}, out_dir, base, fsize, stride, result)
+        _write_prophage_outputs(engine, full, regions or {}, out_dir, base, fsize, stride, result, genes=kwargs.get("genes"))
     if kwargs.get("getsequences"):                                        # predict.py:444-455
         from .postprocess import write_fasta_from_results
         full = WindowSource(fasta=input_path).load() if world > 1 else src.load()
@@ -419,7 +429,8 @@ def _run_core_streaming(kwargs: dict[str, Any], stream_mbp: float, world: int, r
                 frames.append(df)
                 has_rel = bool(data.get("has_reliability", True))
             if kwargs.get("prophage") and res["regions"]:
-                _write_prophage_outputs(engine, src.load(), res["regions"], out_dir, base, fsize, stride, result, append=not first_prophage)
+                _write_prophage_outputs(engine, src.load(), res["regions"], out_dir, base, fsize, stride, result, append=not first_prophage,
+                                        genes=kwargs.get("genes"))
                 first_prophage = False
             logger.info(f"chunk {k}: {n_here} records, {int(offsets[-1])} bases, {res['windows']} windows")
         gid0 += n_here
@@ -491,6 +502,8 @@ def main(argv=None) -> int:
     ap.add_argument("--pc", type=float, default=3)
     ap.add_argument("-p", "--prophage", action="store_true")
     ap.add_argument("--lc", type=int, default=500_000)
+    ap.add_argument("--genes", default=None, help="gene calls (GFF3 / BED / TSV contig,begin,end) used to snap prophage ends out of "
+                                                  "coding genes (the reference calls pyrodigal-gv itself; used here too when installed)")
     ap.add_argument("-s", "--sensitivity", type=float, default=1.5)
     ap.add_argument("--physicalid", type=int, default=0)
     ap.add_argument("--model_path", dest="model_path", default=None, help="directory holding the model instead of the config's model_paths")

@@ -229,9 +229,10 @@ def _gc_and_n(contig: np.ndarray, s: int, e: int) -> tuple[float, float]:
 
 
 def prophage_report(engine, codes: torch.Tensor, valid: torch.Tensor, host: np.ndarray, offsets: np.ndarray, names: list[str],
-                    regions: dict, fsize: int, stride: int | None = None):
-    """The att-site search of `prophage_report` for the called regions (no gene-call refinement: refined = raw
-    boundaries): per region of a contig longer than 500 000 bp, the left flank [start - scan, start + off_set) is
+                    regions: dict, fsize: int, stride: int | None = None, refined_boundaries: dict | None = None):
+    """The att-site search of `prophage_report` for the called regions.  `refined_boundaries` (header ->
+    [(raw_start, raw_end, refined_start, refined_end)], prophage_boundaries.refine_regions): the gene-aware ends the search and
+    the reported coordinates use instead of the window-grid ones (prophages.py:759-772); None = raw boundaries.  Per region of a contig longer than 500 000 bp, the left flank [start - scan, start + off_set) is
     aligned against the right flank [end - off_set, end + scan) directly and against its reverse complement -- the
     same Smith-Waterman as the terminal-repeat scan, run as rectangular `jg_sw_scan` / `jg_sw_trace` jobs on the packed
     contigs -- and the better one, if either is longer than 12 columns, gives attL / attR and the region coordinates
@@ -246,20 +247,25 @@ def prophage_report(engine, codes: torch.Tensor, valid: torch.Tensor, host: np.n
         if not reg or len(reg["ranges"]) == 0 or len(reg["scores"]) == 0:
             continue
         L, base = int(lens[ci]), int(offsets[ci])
-        for (start, end), sc in zip(reg["ranges"], reg["scores"]):
+        header = names[ci].replace(",", "___")
+        contig_refined = (refined_boundaries.get(header) or refined_boundaries.get(names[ci])) if refined_boundaries else None
+        for idx, ((start, end), sc) in enumerate(zip(reg["ranges"], reg["scores"])):
             raw_start, raw_end = int(start * step), int((end - 1) * step + fsize)                    # prophages.py:765-766
-            region_len = raw_end - raw_start
+            ref_start, ref_end = raw_start, raw_end
+            if contig_refined is not None and idx < len(contig_refined):                              # prophages.py:767-770
+                ref_start, ref_end = int(contig_refined[idx][2]), int(contig_refined[idx][3])
+            region_len = ref_end - ref_start
             scan_length = min(max(int(L * 0.04), 400), 4000)
             off_set = 2000 if region_len // 2 >= 14000 else region_len // 4
-            search_start, search_end = max(raw_start - scan_length, 0), min(raw_end + scan_length, L)
-            l0, l1, _ = slice(search_start, raw_start + off_set).indices(L)
-            r0, r1, _ = slice(raw_end - off_set, search_end).indices(L)
+            search_start, search_end = max(ref_start - scan_length, 0), min(ref_end + scan_length, L)
+            l0, l1, _ = slice(search_start, ref_start + off_set).indices(L)
+            r0, r1, _ = slice(ref_end - off_set, search_end).indices(L)
             nl, nr = max(l1 - l0, 0), max(r1 - r0, 0)
             job_id = -1
             if nl > 0 and nr > 0:
                 job_id = len(jobs)
                 jobs += [(base + l0, base + r0, nr, 0, nl, 0), (base + l0, base + r0, nr, 1, nl, 0)]
-            items.append(dict(ci=ci, L=L, base=base, score=sc, raw_start=raw_start, raw_end=raw_end, off_set=off_set,
+            items.append(dict(ci=ci, L=L, base=base, score=sc, raw_start=raw_start, raw_end=raw_end, ref_start=ref_start, ref_end=ref_end, off_set=off_set,
                               search_start=search_start, search_end=search_end, job=job_id))
     if not items:
         return pd.DataFrame(columns=PROPHAGE_COLUMNS)
@@ -291,7 +297,7 @@ def prophage_report(engine, codes: torch.Tensor, valid: torch.Tensor, host: np.n
         contig = host[it["base"]:it["base"] + it["L"]]
         name = names[it["ci"]]
         if k not in winner:                                                     # result_object is None, prophages.py:624-650
-            s, e = it["raw_start"], it["raw_end"]
+            s, e = it["ref_start"], it["ref_end"]
             row = {"contig_id": name, "seq_len": it["L"], "region_len": e - s, "phage_score": it["score"], "n%": None,
                    "gc%": _gc_and_n(contig, s, e)[0], "reject": None, "sstart": s, "send": None, "estart": None, "eend": e,
                    **{c: None for c in PROPHAGE_COLUMNS[11:20]}}
@@ -309,7 +315,7 @@ def prophage_report(engine, codes: torch.Tensor, valid: torch.Tensor, host: np.n
             else:                                                               # prophages.py:668-675
                 s_end = it["search_start"] + end_q
                 s_start = s_end - alig_len + 1
-                e_end = (it["raw_end"] - it["off_set"]) + end_r
+                e_end = (it["ref_end"] - it["off_set"]) + end_r
                 e_start = e_end - alig_len + 1
                 if (s_end - s_start) >= 250:
                     type_ = f"LTR_{type_}"
@@ -323,7 +329,7 @@ def prophage_report(engine, codes: torch.Tensor, valid: torch.Tensor, host: np.n
     return pd.DataFrame(rows, columns=PROPHAGE_COLUMNS)
 
 
-def prophage_report_loaded(engine, loaded, regions: dict, fsize: int, stride: int | None = None):
+def prophage_report_loaded(engine, loaded, regions: dict, fsize: int, stride: int | None = None, refined_boundaries: dict | None = None):
     """`prophage_report` for a loaded FASTA (`WindowSource.load()`: names, pinned ASCII bases, offsets): H2D + pack, then
     the att-site scans.  Nothing is copied when no called region lies on a contig longer than 500 000 bp."""
     names, host, offsets = loaded
@@ -335,7 +341,7 @@ def prophage_report_loaded(engine, loaded, regions: dict, fsize: int, stride: in
         return pd.DataFrame(columns=PROPHAGE_COLUMNS)
     with torch.cuda.stream(engine._stream()):
         codes, valid = engine.pack(host.to(engine.tdev, non_blocking=True))
-    return prophage_report(engine, codes, valid, host.numpy(), offsets, names, regions, fsize, stride)
+    return prophage_report(engine, codes, valid, host.numpy(), offsets, names, regions, fsize, stride, refined_boundaries)
 
 
 def write_prophage_report(df, outdir) -> None:

@@ -182,9 +182,10 @@ def prophage_alignment_summary(res, seq_len: int, name: str, seq: str, cordinate
             "attL": res["qline"], "attR": res["rline"]}
 
 
-def prophage_report(records, prophage_cordinates: dict, fsize: int, stride: int | None = None) -> list[dict]:
-    """prophage_report (prophages.py:706-873) without gene-call refinement (refined_boundaries=None): one row per
-    called region of every contig longer than 500 000 bp.  `prophage_cordinates`: header -> (window-index ranges,
+def prophage_report(records, prophage_cordinates: dict, fsize: int, stride: int | None = None, refined_boundaries: dict | None = None) -> list[dict]:
+    """prophage_report (prophages.py:706-873): one row per called region of every contig longer than 500 000 bp; with
+    `refined_boundaries` (header -> [(raw_start, raw_end, refined_start, refined_end)]) the search and the coordinates use the
+    gene-aware ends (prophages.py:759-772).  `prophage_cordinates`: header -> (window-index ranges,
     scores) as `segment` returns them."""
     step = stride or fsize
     rows = []
@@ -197,9 +198,12 @@ def prophage_report(records, prophage_cordinates: dict, fsize: int, stride: int 
         cords, scores = prophage_cordinates.get(header, [[], []])
         if not (len(cords) > 0 and len(scores) > 0):
             continue
-        for (start, end), j in zip(cords, scores):
+        contig_refined = refined_boundaries.get(header) if refined_boundaries else None
+        for idx, ((start, end), j) in enumerate(zip(cords, scores)):
             raw_start, raw_end = int(start * step), int((end - 1) * step + fsize)
             r_start, r_end = raw_start, raw_end
+            if contig_refined is not None and idx < len(contig_refined):
+                _, _, r_start, r_end = contig_refined[idx]
             region_len = r_end - r_start
             scan_length = min(max(int(seq_len * 0.04), 400), 4000)
             off_set = 2000 if region_len // 2 >= 14000 else region_len // 4

@@ -78,10 +78,22 @@ def prophage_genomes():
     # region windows [300, 303): raw 450000 .. 455000, off_set 1250 -> left [446000, 451250), right [453750, 459000)
     put(447_000, c160); put(457_100, c160[:70] + c160[71:]); put(451_300, "N" * 2400)
     g[448_500] = "n"
+    # region windows [340, 341): raw 510000 .. 512000; a 40-bp direct repeat just OUTSIDE the raw search windows
+    # ([506000, 510500) / [511500, 516000)) that only the gene-refined ends (508500 .. 512700) bring into reach
+    d40 = rnd(40)
+    put(505_500, d40); put(516_200, d40)
     recs = [("genome1,with,commas", "".join(g)), ("genome2", rnd(501_000)), ("plasmid", rnd(400_000))]
-    cords = {"genome1___with___commas": [[[100, 104], [200, 221], [300, 303], [0, 3]], np.array([4.25, 7.5, 2.125, 1.75])],
+    cords = {"genome1___with___commas": [[[100, 104], [200, 221], [300, 303], [0, 3], [340, 341]], np.array([4.25, 7.5, 2.125, 1.75, 1.5])],
              "plasmid": [[[10, 20]], np.array([3.0])]}
     return recs, cords
+
+
+def prophage_gene_calls():
+    """Gene intervals (0-based half-open, as the reference's `find_genes` returns them) for `prophage_genomes()`: ends inside genes
+    on either side, an intergenic end, extensions beyond 2 * fsize (capped), a gene at the contig start, overlapping genes."""
+    return {"genome1___with___commas": [(0, 300), (149_800, 150_400), (150_100, 150_900), (156_200, 156_900), (299_000, 301_000),
+                                        (445_000, 452_000), (454_000, 460_000), (508_500, 510_300), (511_900, 512_700)],
+            "plasmid": [(14_000, 16_000)]}
 
 
 def dust_contigs():

@@ -500,6 +500,18 @@ def test_config4_genome_with_prophage_option_end_to_end(standin, tmp_path):
     assert len(rep) == len(want_r)
     assert rep["raw_start"].tolist() == [s * 1500 for s, _ in want_r] and rep["raw_end"].tolist() == [(e - 1) * 1500 + 2000 for _, e in want_r]
     assert (tmp_path / "out" / "standin" / "genome_prophages" / "prophages_jaeger.tsv").exists() == (len(want_r) > 0)
+    # --genes: a gene across every region end moves the reported ends out of it (prophage_boundaries.py), raw_* columns stay
+    if want_r:
+        genes = tmp_path / "genes.bed"
+        with open(genes, "w") as fh:
+            for s, e in want_r:
+                fh.write(f"chr1\t{s * 1500 - 700}\t{s * 1500 + 300}\n")
+                fh.write(f"chr1\t{(e - 1) * 1500 + 2000 - 100}\t{(e - 1) * 1500 + 2000 + 900}\n")
+        res2 = run_core(input=str(fa), output=str(tmp_path / "out2"), model="standin", allow_random_weights=True, fsize=2000, stride=1500,
+                        prophage=True, lc=500_000, sensitivity=1.5, overwrite=True, genes=str(genes))
+        ref_b = res2["refined_boundaries"]["chr1"]
+        assert [(r[2], r[3]) for r in ref_b] == [(max(r[0] - 700, 0), min(r[1] + 900, n)) for r in ref_b]
+        assert res2["prophage_report"]["raw_start"].tolist() == rep["raw_start"].tolist()
 
 
 def test_crf_viterbi_decoding_vs_reference_golden(standin):
@@ -670,9 +682,21 @@ def test_prophage_att_report_vs_reference_golden(standin, tmp_path):
     regions = {k: {"ranges": v[0], "scores": v[1]} for k, v in cords.items()}
     src = WindowSource(records=recs, fsize=2000, stride=1500)
     rep = prophage_report_loaded(eng, src.load(), regions, 2000, 1500)
-    assert len(rep) == 4 and rep["att_type"].tolist() == ["DTR", "ITR", "DTR", "DTR"]
+    assert len(rep) == 5 and rep["att_type"].tolist() == ["DTR", "ITR", "DTR", "DTR", "DTR"]
     write_prophage_report(rep, tmp_path / "x_prophages")
     assert (tmp_path / "x_prophages" / "prophages_jaeger.tsv").read_text() == (G / "prophages_jaeger.tsv").read_text()
+    # gene-aware ends (prophage_boundaries.py): the ends the reference's own refine_prophage_boundaries produced for a fixed gene
+    # table, the report the reference wrote on them -- the refined ends bring a planted 40-bp repeat into reach
+    from jaeger_b200 import prophage_boundaries as pb
+    from tests.helpers import prophage_gene_calls
+    calls = prophage_gene_calls()
+    names, _, offsets = src.load()
+    refined = pb.refine_regions(regions, names, np.diff(offsets), 2000, 1500, lambda header, ci: calls.get(header))
+    assert {k: [list(r) for r in v] for k, v in refined.items()} == json.loads((G / "refined_boundaries.json").read_text())
+    rep2 = prophage_report_loaded(eng, src.load(), regions, 2000, 1500, refined_boundaries=refined)
+    write_prophage_report(rep2, tmp_path / "z_prophages")
+    assert (tmp_path / "z_prophages" / "prophages_jaeger.tsv").read_text() == (G / "prophages_jaeger_refined.tsv").read_text()
+    assert int(rep2["att_alignment_length"].iloc[4]) > int(rep["att_alignment_length"].iloc[4])
     # nothing on contigs <= 500 kbp, no file without rows (prophages.py:759, 866)
     none = prophage_report_loaded(eng, src.load(), {"plasmid": regions["plasmid"]}, 2000, 1500)
     assert len(none) == 0

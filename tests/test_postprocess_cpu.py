@@ -219,7 +219,7 @@ def test_prophage_report_oracle_vs_reference_golden(tmp_path):
     df["contig_id"] = df["contig_id"].apply(lambda x: x.replace("___", ","))
     df.to_csv(tmp_path / "p.tsv", sep="\t", index=False, float_format="%.3f")
     assert (tmp_path / "p.tsv").read_text() == (G / "prophages_jaeger.tsv").read_text()
-    assert [r["att_type"] for r in rows] == ["DTR", "ITR", "DTR", "DTR"] and rows[2]["reject"] is True
+    assert [r["att_type"] for r in rows] == ["DTR", "ITR", "DTR", "DTR", "DTR"] and rows[2]["reject"] is True
 
 
 def test_refinement_oracle_on_reference_known_answers(tmp_path):
@@ -461,3 +461,62 @@ def test_optimal_partition_is_the_exact_optimum_on_short_signals():
     # the stated tie-break on an all-tie signal: no change point at pen 0 on a constant track
     assert opro.optimal_partition(np.zeros(9), 0.0, 3) == [9]
     assert opro.optimal_partition(np.zeros(9), 1.0, 3) == [9]
+
+
+def test_prophage_boundary_refinement_vs_reference(tmp_path):
+    """Gene-aware prophage boundaries (postprocess/prophage_boundaries.py:52-193): the known answers of the reference's
+    tests/unit/test_prophage_boundaries.py, and `refine_regions` against what the reference's own `refine_prophage_boundaries` returned
+    for the test genomes with its gene caller replaced by a fixed gene table (tests/golden/refined_boundaries.json); gene tables in the
+    three accepted formats give the same intervals."""
+    from jaeger_b200 import prophage_boundaries as pb
+    from tests.helpers import prophage_gene_calls, prophage_genomes
+    genes = [(100, 200), (300, 400)]
+    assert pb.refine_boundary(50, genes, "left") == 50 and pb.refine_boundary(250, genes, "right") == 250
+    assert pb.refine_boundary(150, [(100, 200)], "left") == 100 and pb.refine_boundary(150, [(100, 200)], "right") == 200
+    assert pb.refine_boundary(900, [(0, 1000)], "left", max_extension=50) == 850
+    assert pb.refine_boundary(100, [(0, 1000)], "right", max_extension=50) == 150
+    assert pb.refine_region(150, 550, [(100, 200), (500, 600)]) == (100, 600)
+    assert pb.refine_region(250, 700, [(100, 200), (500, 600)]) == (250, 700)
+    with pytest.raises(ValueError, match="side must be 'left' or 'right'"):
+        pb.refine_boundary(50, [(0, 100)], "upstream")
+    recs, cords = prophage_genomes()
+    calls = prophage_gene_calls()
+    want = {k: [tuple(r) for r in v] for k, v in json.loads((G / "refined_boundaries.json").read_text()).items()}
+    got = pb.refine_regions(cords, [n for n, _ in recs], [len(s) for _, s in recs], 2000, 1500, lambda header, ci: calls.get(header))
+    assert got == want
+    assert any((r[0], r[1]) != (r[2], r[3]) for r in got["genome1___with___commas"])
+    assert got["genome1___with___commas"][2] == (450000, 455000, 446000, 459000)          # both extensions capped at 2 * fsize
+    # the same calls as GFF3 (1-based closed), BED (0-based half-open), TSV (1-based closed)
+    gff, bed, tsv = tmp_path / "g.gff", tmp_path / "g.bed", tmp_path / "g.tsv"
+    with open(gff, "w") as a, open(bed, "w") as b, open(tsv, "w") as c:
+        a.write("##gff-version 3\n")
+        c.write("contig\tbegin\tend\n")
+        for contig, iv in calls.items():
+            name = contig.replace("___", ",")
+            for s, e in iv:
+                a.write(f"{name} a description\tprodigal\tCDS\t{s + 1}\t{e}\t.\t+\t0\tID=x\n")
+                a.write(f"{name}\tprodigal\tregion\t1\t9\t.\t+\t0\tID=y\n")
+                b.write(f"{name}\t{s}\t{e}\n")
+                c.write(f"{name}\t{s + 1}\t{e}\n")
+    for path in (gff, bed, tsv):
+        table = pb.load_gene_table(path)
+        assert table == {k: sorted(v) for k, v in calls.items()}, path
+        src = pb.gene_source(table, None)
+        assert pb.refine_regions(cords, [n for n, _ in recs], [len(s) for _, s in recs], 2000, 1500, src) == want
+
+
+def test_prophage_report_with_refined_boundaries_oracle_vs_reference_golden(tmp_path):
+    """The reference's prophage_report run on the ends its own refine_prophage_boundaries produced (aligner and gene caller stubbed,
+    tests/golden/make_termini_goldens.py): the oracle writes the same file; the refined ends bring a planted repeat into reach
+    that the raw window-grid ends miss."""
+    import pandas as pd
+    from oracle import termini as ot
+    from tests.helpers import prophage_genomes
+    recs, cords = prophage_genomes()
+    refined = {k: [tuple(r) for r in v] for k, v in json.loads((G / "refined_boundaries.json").read_text()).items()}
+    rows = ot.prophage_report(recs, cords, fsize=2000, stride=1500, refined_boundaries=refined)
+    df = pd.DataFrame(rows)
+    df["contig_id"] = df["contig_id"].apply(lambda x: x.replace("___", ","))
+    df.to_csv(tmp_path / "p.tsv", sep="\t", index=False, float_format="%.3f")
+    assert (tmp_path / "p.tsv").read_text() == (G / "prophages_jaeger_refined.tsv").read_text()
+    assert (G / "prophages_jaeger_refined.tsv").read_text() != (G / "prophages_jaeger.tsv").read_text()
