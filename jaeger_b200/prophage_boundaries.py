@@ -84,12 +84,18 @@ def refine_regions(regions: dict[str, Any], names: Iterable[str], lengths: Itera
     return out
 
 
+_TABLES: dict[tuple[str, float], dict[str, Genes]] = {}      # parsed gene tables (a streamed run asks once per chunk)
+
+
 def load_gene_table(path: str | Path) -> dict[str, Genes]:
     """Gene intervals per contig from a gene caller's output: GFF3 / GTF (columns 1, 4, 5: 1-based closed; `CDS` / `gene`
     features), BED (columns 1-3: 0-based half-open) or a headerless TSV `contig, begin, end` with 1-based closed coordinates
     (what pyrodigal's `Gene.begin` / `.end` are, prophage_boundaries.py:45-48).  Contig ids are matched after the same clean-up
     as the FASTA headers (first word; `,` -> `___`).  Returns sorted 0-based half-open intervals."""
     path = Path(path)
+    key = (str(path.resolve()), path.stat().st_mtime)
+    if key in _TABLES:
+        return _TABLES[key]
     opener = gzip.open if path.suffix == ".gz" else open
     kind = path.name[:-3] if path.suffix == ".gz" else path.name
     kind = kind.rsplit(".", 1)[-1].lower()
@@ -114,6 +120,7 @@ def load_gene_table(path: str | Path) -> dict[str, Genes]:
             genes.setdefault(contig.split()[0].replace(",", "___"), []).append((begin, end))
     for v in genes.values():
         v.sort()
+    _TABLES[key] = genes
     return genes
 
 
