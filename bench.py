@@ -131,7 +131,7 @@ class Workload:
         return {"workload": WORKLOADS[self.cfg], "config_id": self.cfg,
                 "step": f"one pass of the hot path over {unit} per {'job' if strong else 'GPU'}",
                 "l2_policy": "inputs larger than L2: a different batch every step, activations per step >> 126 MB L2",
-                "parallelism": "length-balanced contig sharding (LPT on window counts), one gather of per-contig records per step"}
+                "parallelism": "length-balanced contig sharding (LPT on window counts), per-contig records gathered on rank 0 once, after the last step of a leg"}
 
 
 class ClockSampler(threading.Thread):
