@@ -114,6 +114,9 @@ def _make_engine(kwargs: dict[str, Any]):
                          "Pass --allow-random-weights to run it anyway.")
     if kwargs.get("cpu"):
         raise RuntimeError("--cpu: this engine has no CPU path (use the reference's own engine for CPU runs)")
+    for other in ("onnx", "quantized", "xla"):                           # the reference's alternate backends (predict.py:687-745)
+        if kwargs.get(other):
+            raise RuntimeError(f"--{other}: this is the B200 engine; the ONNX / TFLite / XLA backends belong to the reference's own driver")
     precision = kwargs.get("precision") or "fp16"                          # predict.py:604-613
     if precision not in ("fp32", "fp16", "bf16"):
         raise ValueError(f"--precision {precision!r} (use fp32, fp16 or bf16)")
@@ -510,6 +513,8 @@ def main(argv=None) -> int:
     ap.add_argument("--mem", type=float, default=None, help="device workspace cap in GB (default 16)")
     ap.add_argument("--precision", choices=["fp32", "fp16", "bf16"], default="fp16")
     ap.add_argument("--cpu", action="store_true", help="rejected: there is no CPU path")
+    for other in ("--onnx", "--quantized", "--xla"):
+        ap.add_argument(other, action="store_true", help="rejected: an alternate backend of the reference's own driver")
     ap.add_argument("--workers", type=int, default=4, help="accepted for CLI compatibility: windowing / encoding run on the device")
     ap.add_argument("--plot-type", dest="plot_type", default="none", choices=["circular", "linear", "both", "none"],
                     help="accepted for CLI compatibility: plots are outside the hot path and are not drawn")

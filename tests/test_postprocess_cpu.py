@@ -320,6 +320,9 @@ def test_driver_rejects_cpu_and_bad_precision_before_touching_a_device(tmp_path)
     fa.write_text(">a\n" + "ACGT" * 600 + "\n")
     with pytest.raises(RuntimeError, match="no CPU path"):
         run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, cpu=True)
+    for backend in ("onnx", "quantized", "xla"):          # the reference's alternate backends are not this engine's
+        with pytest.raises(RuntimeError, match="belong to the reference"):
+            run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, **{backend: True})
     with pytest.raises(ValueError, match="precision"):
         run_core(input=str(fa), output=str(tmp_path / "o"), model="standin", allow_random_weights=True, precision="int8")
     for prec in ("fp32", "bf16"):            # one numeric mode: another precision is refused, not silently ignored
