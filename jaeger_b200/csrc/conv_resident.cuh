@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
     for (long long w = w0; w < p.n_windows && g < n_tiles; w += wstep, ++itw) {      // a group beyond the tile count has no rows
       const int lp = lp_next;
       if (w + wstep < p.n_windows) lp_next = p.lpad[w + wstep];
+      bool win_clean = false;          // the builder's flag for this window, read once (after the stem's first accumulator is up)
       for (int l = 0; l < n_layers; ++l, ++gl) {
         const LayerRs& L = p.layer[l];
         EpiLayer E;
@@ -511,7 +512,8 @@ __global__ void __launch_bounds__(kThreadsRs, 1) stack_resident_kernel(const __g
         E.acc = tmem + (static_cast<uint32_t>(q * 32) << 16) + (gl & 1u) * 256u;
         E.parity = gl & 1u;
         E.bar0 = smem_u32(s_bar);
-        E.slow_mask = L.masking && !(L.zero_tap && s_clean_of(s_clean, itw, smem_u32(s_bar), g, gl));
+        if (l == 0) win_clean = s_clean_of(s_clean, itw, smem_u32(s_bar), g, gl);
+        E.slow_mask = L.masking && !(L.zero_tap && win_clean);
         E.pool = p.pool + w * p.pool_pitch + lane;
         E.count = L.count_id >= 0 ? p.count + static_cast<long long>(L.count_id) * p.cap_windows + w : nullptr;
         E.tap = L.tap_mode ? p.tap_sum + (static_cast<long long>(L.tap_slot) * p.n_windows + w) * p.tap_width + lane : nullptr;
